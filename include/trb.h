@@ -1,0 +1,252 @@
+/*
+ * trb.h - C ABI of the B200 rasterization backend ("tinyrenderder-b200").
+ *
+ * This is the drop-in boundary for the hot path of AnnaUshnova/tinyrenderder:
+ * the reference has no FFI layer, its boundary is the C++ header our_gl.h plus
+ * the Model accessors.  Every entry point below names the reference interface
+ * it replaces (file:line relative to the reference checkout).
+ *
+ * Conventions
+ *   - every call returns int: 0 = ok, <0 = error class (TRB_E_*);
+ *     trb_last_error(ctx) returns the CUDA / argument error string.
+ *   - the caller owns every host pointer; the library owns device memory behind
+ *     opaque handles.  Host buffers may be pageable or pinned.
+ *   - matrices are row-major double[16], exactly mat<4,4>::rows of the
+ *     reference (geometry.h:155-166), column-vector convention (M*v).
+ *   - colours are BGR bytes (TGAColor layout, tgaimage.h:29-63); row y=0 of the
+ *     framebuffer is the bottom of the picture (tgaimage.cpp:176).
+ *   - one context per GPU; a context is NOT thread-safe (the reference keeps its
+ *     state in unsynchronised globals, our_gl.cpp:12-22); different contexts may
+ *     be driven from different host threads.  All work of a context is queued on
+ *     one CUDA stream; trb_read_* / trb_get_stats synchronise.
+ *   - there is no CPU fallback: every entry point fails with TRB_E_CUDA when no
+ *     sm_100 device is usable.
+ *
+ * The CPU oracle (oracle/, test infrastructure only) implements the SAME
+ * signatures under the prefix orc_ by defining TRB_FN before including this
+ * header; the product library exports trb_*.
+ */
+#ifndef TRB_H_
+#define TRB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef TRB_FN
+#define TRB_FN(name) trb_##name
+#endif
+
+#if defined(__GNUC__)
+#define TRB_EXPORT __attribute__((visibility("default")))
+#else
+#define TRB_EXPORT
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct TrbCtx TrbCtx;
+typedef uint64_t TrbMesh; /* 0 = invalid */
+typedef uint64_t TrbTex;  /* 0 = "texture absent" (model.cpp:416,429,447 fallbacks) */
+
+enum TrbError {
+    TRB_OK = 0,
+    TRB_E_ARG = -1,      /* bad argument / call out of sequence */
+    TRB_E_CUDA = -2,     /* CUDA runtime error, see trb_last_error */
+    TRB_E_NOMEM = -3,    /* device or host allocation failed */
+    TRB_E_SHADER = -4,   /* shader kind unknown to the device (no CPU fallback) */
+    TRB_E_COMM = -5      /* multi-GPU composite misuse */
+};
+
+/* Device-resident fragment shaders.  A GPU cannot call the host virtual
+ * IShader::fragment (our_gl.h:51), so the shaders of the reference are
+ * identified by kind + a POD uniform block. */
+enum TrbShaderKind {
+    TRB_SHADER_FLAT_BARY = 0, /* BGR = (u8)min(255,max(0,255*pc[i])), test shader of SURVEY K1-K7 / C5 */
+    TRB_SHADER_PHONG = 1,     /* PhongShader, main.cpp:39-171 */
+    TRB_SHADER_EYE = 2,       /* EyeShader,   main.cpp:176-262 */
+    TRB_SHADER_DEPTH = 3,     /* depth-only pass (no colour write), shadow pass 1 of config 2 */
+    TRB_SHADER_SHADOW_PHONG = 4, /* Phong + shadow-map lookup, config 2 (authored here) */
+    TRB_SHADER_GOURAUD = 5    /* per-vertex diffuse intensity interpolated, config 2 family */
+};
+
+/* Uniform block of PHONG / EYE / GOURAUD.  Light directions are ALREADY in eye
+ * space and normalised, i.e. the result of PhongShader::initLightDirections
+ * (main.cpp:55-69) / EyeShader::initLightDirections (main.cpp:187-197); use
+ * trb_light_dir_eye() to compute them with the reference's operation order. */
+typedef struct TrbPhongUniforms {
+    double key_dir_eye[3];
+    double fill_dir_eye[3];        /* unused by EYE */
+    double rim_dir_eye[3];
+    double normal_map_strength;    /* PhongShader::normal_map_strength, main.cpp:51 */
+    TrbTex diffuse;                /* Model::diffuse  source, model.cpp:415-425 */
+    TrbTex normal;                 /* Model::normal   source, model.cpp:428-444 */
+    TrbTex specular;               /* Model::specular source, model.cpp:446-459 */
+} TrbPhongUniforms;
+
+/* Uniform block of SHADOW_PHONG: Phong block + the light-space transform used
+ * by the depth pass and the shadow map it produced (a depth snapshot handle). */
+typedef struct TrbShadowUniforms {
+    TrbPhongUniforms phong;
+    double light_modelview[16];    /* ModelView of the depth pass */
+    double light_perspective[16];  /* Perspective of the depth pass */
+    double light_viewport[16];     /* Viewport of the depth pass */
+    double shadow_bias;            /* NDC-z bias; lit if z_light <= shadow_z + bias */
+    double shadow_darkening;       /* multiplier applied to diffuse+specular when occluded */
+    int32_t shadow_map;            /* index returned by trb_keep_depth_as_shadow_map */
+    int32_t shadow_w, shadow_h;
+    int32_t _pad;
+} TrbShadowUniforms;
+
+/* Counters.  triangles_submitted / bbox / z_min mirror the statics of
+ * our_gl.cpp:18-22 printed by print_render_stats (our_gl.cpp:204-210).
+ * The reference's fragments_drawn and max_z depend on submission order
+ * (SURVEY K5), so the order-independent equivalents are reported instead. */
+typedef struct TrbStats {
+    uint64_t triangles_submitted;  /* == triangles_rasterized, our_gl.cpp:90 */
+    uint64_t triangles_binned;     /* survived all rejects of our_gl.cpp:94-135 */
+    uint64_t tile_entries;         /* R: (triangle,16x16 tile) pairs written by binning */
+    uint64_t fragments_covered;    /* samples passing our_gl.cpp:152 and :160 */
+    uint64_t pixels_shaded;        /* pixels whose colour was written by flush */
+    uint64_t visible_triangles;    /* distinct winning triangles at flush (0 if not counted) */
+    int32_t bbox_min_x, bbox_min_y, bbox_max_x, bbox_max_y; /* our_gl.cpp:138-141 */
+    double z_min;                  /* == min_z of our_gl.cpp:197 (order independent) */
+    double z_max_covered;          /* max z over covered samples (>= reference max_z) */
+    uint64_t fragments_drawn_ref;  /* oracle only: the reference's order-dependent counter */
+    double z_max_ref;              /* oracle only: the reference's order-dependent max_z */
+} TrbStats;
+
+/* ---- contexts -------------------------------------------------------------------- */
+TRB_EXPORT int TRB_FN(create)(int device, TrbCtx** out);
+TRB_EXPORT int TRB_FN(destroy)(TrbCtx* ctx);
+TRB_EXPORT const char* TRB_FN(last_error)(TrbCtx* ctx);
+TRB_EXPORT const char* TRB_FN(backend_name)(void); /* "cuda-sm100a", "oracle-ref", "oracle-port" */
+
+/* ---- resources: upload once (replaces Model's host arrays, model.h:118-121, and the
+ *      accessors Model::vert/normal/uv(iface,nthvert), model.cpp:396-412) --------------
+ * pos3/nrm3: nverts*3 floats, uv2: nverts*2 floats (Assimp hands back floats,
+ * model.cpp:160-185).  nrm3 / uv2 may be NULL -> (0,0,1) / (0,0) like the accessors'
+ * fallbacks.  idx: nidx (multiple of 3) vertex indices; NULL = implicit 0..nidx-1. */
+TRB_EXPORT int TRB_FN(upload_mesh)(TrbCtx* ctx, const float* pos3, const float* nrm3,
+                                   const float* uv2, uint32_t nverts, const uint32_t* idx,
+                                   uint64_t nidx, TrbMesh* out);
+TRB_EXPORT int TRB_FN(free_mesh)(TrbCtx* ctx, TrbMesh mesh);
+/* texels: h rows of w texels of bpp (1,3,4) bytes in TGAImage memory order
+ * ((x+y*w)*bpp, BGR(A), tgaimage.cpp:24-30); sampled nearest with trunc+clamp like
+ * model.cpp:420-423. */
+TRB_EXPORT int TRB_FN(upload_texture)(TrbCtx* ctx, const uint8_t* texels, int w, int h, int bpp,
+                                      TrbTex* out);
+TRB_EXPORT int TRB_FN(free_texture)(TrbCtx* ctx, TrbTex tex);
+
+/* ---- frame ------------------------------------------------------------------------- */
+/* init_zbuffer(w,h) (our_gl.cpp:72-74) + TGAImage framebuffer(w,h,RGB) (main.cpp:606):
+ * depth = +inf, colour = clear colour (default 0,0,0), counters reset.
+ * nviews > 1 renders a batch of independent frames (camera orbit) in one launch set. */
+TRB_EXPORT int TRB_FN(begin_frame)(TrbCtx* ctx, int width, int height);
+TRB_EXPORT int TRB_FN(begin_batch)(TrbCtx* ctx, int width, int height, int nviews);
+TRB_EXPORT int TRB_FN(set_clear_color)(TrbCtx* ctx, uint8_t b, uint8_t g, uint8_t r);
+/* the global Viewport (our_gl.h:19) as set by init_viewport (our_gl.cpp:59-69) */
+TRB_EXPORT int TRB_FN(set_viewport)(TrbCtx* ctx, const double viewport[16]);
+
+/* ---- draw: one call replaces the per-face loop main.cpp:660-666 / 692-698 / 715-721 -- */
+/* for face in [first_tri, first_tri+ntris): clip[v] = shader.vertex(face,v);
+ * rasterize(clip, shader, framebuffer).  modelview/perspective are the globals
+ * ModelView / Perspective (our_gl.h:17-18) at the time of the loop. */
+TRB_EXPORT int TRB_FN(draw)(TrbCtx* ctx, TrbMesh mesh, const double modelview[16],
+                            const double perspective[16], int shader_kind, const void* uniforms,
+                            size_t uniform_bytes, uint64_t first_tri, uint64_t ntris);
+/* batch form: modelview / perspective are nviews*16 doubles, uniforms nviews blocks */
+TRB_EXPORT int TRB_FN(draw_batch)(TrbCtx* ctx, TrbMesh mesh, const double* modelview,
+                                  const double* perspective, int shader_kind,
+                                  const void* uniforms, size_t uniform_bytes, uint64_t first_tri,
+                                  uint64_t ntris);
+/* immediate mode behind rasterize(const Triangle&, const IShader&, TGAImage&)
+ * (our_gl.cpp:89): n clip-space triangles, clip12 = n*12 doubles (3 x vec4).
+ * varyings (may be NULL for FLAT_BARY/DEPTH): n*24 doubles per triangle =
+ * 3 x {uv.x, uv.y, position_eye.xyz, normal_eye.xyz}, the state PhongShader::vertex
+ * leaves in the shader object (main.cpp:75-87). modelview is read by
+ * PhongShader::fragment (main.cpp:116). */
+TRB_EXPORT int TRB_FN(submit_clip_triangles)(TrbCtx* ctx, const double* clip12,
+                                             const double* varyings, uint64_t n,
+                                             const double modelview[16], int shader_kind,
+                                             const void* uniforms, size_t uniform_bytes);
+
+/* z-buffer copy at a draw boundary (std::vector<double> zbuffer_before_eyes = zbuffer,
+ * main.cpp:700) and roll-back (zbuffer = zbuffer_before_eyes, main.cpp:730).  Restore
+ * shades everything drawn so far first, so colours persist like in the reference. */
+TRB_EXPORT int TRB_FN(depth_snapshot)(TrbCtx* ctx);
+TRB_EXPORT int TRB_FN(depth_restore)(TrbCtx* ctx);
+/* keep the current depth buffer of view 0 as a shadow map for later frames */
+TRB_EXPORT int TRB_FN(keep_depth_as_shadow_map)(TrbCtx* ctx, int32_t* out_index);
+
+/* resolve visibility -> colour (the fragment() calls of our_gl.cpp:187-192, run once per
+ * visible pixel).  Implied by end_frame / read_color / depth_restore. */
+TRB_EXPORT int TRB_FN(flush)(TrbCtx* ctx);
+TRB_EXPORT int TRB_FN(end_frame)(TrbCtx* ctx);
+
+/* ---- post passes on the resident z-buffer ------------------------- */
+/* compute_ssao_at over the frame (main.cpp:324-362, 756-763): ao[x+y*w] = (u8)(255*ao) */
+TRB_EXPORT int TRB_FN(ssao)(TrbCtx* ctx, int view, uint8_t* ao_out);
+/* save_zbuffer_image grey map (main.cpp:269-314) without the file write */
+TRB_EXPORT int TRB_FN(depth_image)(TrbCtx* ctx, int view, uint8_t* grey_out);
+/* final = phong * ao (main.cpp:768-783), BGR out */
+TRB_EXPORT int TRB_FN(composite_ao)(TrbCtx* ctx, int view, uint8_t* bgr_out);
+
+/* ---- readback ------------------------------------------------------------------------ */
+/* framebuffer bytes, BGR, (x+y*w)*3 like TGAImage(w,h,RGB) (tgaimage.cpp:32-39) */
+TRB_EXPORT int TRB_FN(read_color)(TrbCtx* ctx, int view, uint8_t* bgr_out);
+/* the global zbuffer (our_gl.h:20): w*h doubles, +inf where nothing was drawn */
+TRB_EXPORT int TRB_FN(read_depth)(TrbCtx* ctx, int view, double* z_out);
+/* winning triangle id per pixel BEFORE flush: 0xFFFFFFFF = none, 0 = already shaded,
+ * else 1 + global submission index over all draws since begin_frame (diagnostic) */
+TRB_EXPORT int TRB_FN(read_visibility)(TrbCtx* ctx, int view, uint32_t* id_out);
+TRB_EXPORT int TRB_FN(get_stats)(TrbCtx* ctx, int view, TrbStats* out);
+TRB_EXPORT int TRB_FN(synchronize)(TrbCtx* ctx);
+
+/* device-side timing of everything queued between the two marks (CUDA events on the
+ * context's stream); used by bench.py. */
+TRB_EXPORT int TRB_FN(timer_start)(TrbCtx* ctx);
+TRB_EXPORT int TRB_FN(timer_stop_ms)(TrbCtx* ctx, float* ms_out);
+/* per-kernel accumulated device time and launch counts since the last reset
+ * (CUDA events around each launch; enabled by trb_profile_enable(ctx,1)). */
+typedef struct TrbKernelTime {
+    char name[32];
+    uint64_t launches;
+    double ms;
+} TrbKernelTime;
+TRB_EXPORT int TRB_FN(profile_enable)(TrbCtx* ctx, int on);
+TRB_EXPORT int TRB_FN(profile_read)(TrbCtx* ctx, TrbKernelTime* out, int capacity, int* n_out,
+                                    int reset);
+TRB_EXPORT uint64_t TRB_FN(launch_count)(TrbCtx* ctx); /* kernels launched since create */
+
+/* ---- multi-GPU sort-last composite (config 4) ----------------------------------------
+ * Raw device pointers of view 0's depth-key (uint64, order preserving)
+ * and visibility-id (uint32) planes so that the host (torch.distributed / NCCL) can
+ * all-reduce them in place; then trb_composite_mask drops local ids that lost. */
+TRB_EXPORT int TRB_FN(device_planes)(TrbCtx* ctx, uint64_t* depth_key_ptr, uint64_t* vis_id_ptr,
+                                     uint64_t* npixels);
+TRB_EXPORT int TRB_FN(set_triangle_id_base)(TrbCtx* ctx, uint64_t base);
+TRB_EXPORT int TRB_FN(composite_save_local_depth)(TrbCtx* ctx);
+TRB_EXPORT int TRB_FN(composite_mask)(TrbCtx* ctx);
+/* restrict flush to rows [y0,y1) (the screen slice this rank owns after the composite) */
+TRB_EXPORT int TRB_FN(set_shade_rows)(TrbCtx* ctx, int y0, int y1);
+
+/* ---- host helpers with the reference's operation order (no device work) --------------- */
+/* normalized(ModelView[0..2][0..2] * dir_world), main.cpp:59-68 */
+TRB_EXPORT void TRB_FN(light_dir_eye)(const double modelview[16], const double dir_world[3],
+                                      double out[3]);
+/* lookat (our_gl.cpp:25-41), init_perspective (our_gl.cpp:44-56), init_viewport
+ * (our_gl.cpp:59-69) writing a row-major 4x4 */
+TRB_EXPORT void TRB_FN(lookat)(const double eye[3], const double center[3], const double up[3],
+                               double out[16]);
+TRB_EXPORT void TRB_FN(perspective)(double fov_deg, double aspect, double znear, double zfar,
+                                    double out[16]);
+TRB_EXPORT void TRB_FN(viewport)(int x, int y, int w, int h, double out[16]);
+/* mat<4,4> * mat<4,4> (geometry.h:195-205) */
+TRB_EXPORT void TRB_FN(mat4_mul)(const double a[16], const double b[16], double out[16]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRB_H_ */

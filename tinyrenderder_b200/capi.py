@@ -1,0 +1,419 @@
+"""ctypes binding of the C ABI declared in include/trb.h.
+
+`Api(path, prefix)` binds one shared library exporting `<prefix>_*` with the signatures of
+include/trb.h.  The product uses `load_cuda()` (libtrb.so, prefix ``trb``); the test-suite and
+bench.py's cpu_baseline leg bind the CPU oracle (prefix ``orc``) through the same class, which
+is what makes the parity tests read the same for both sides.  Nothing in this package imports
+or falls back to the oracle: if libtrb.so is missing, `load_cuda()` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB = os.path.join(_PKG, "libtrb.so")
+
+SHADER_FLAT_BARY = 0
+SHADER_PHONG = 1
+SHADER_EYE = 2
+SHADER_DEPTH = 3
+SHADER_SHADOW_PHONG = 4
+SHADER_GOURAUD = 5
+
+VIS_NONE = 0xFFFFFFFF
+VIS_SHADED = 0
+
+
+class TrbError(RuntimeError):
+    pass
+
+
+class PhongUniforms(C.Structure):
+    _fields_ = [
+        ("key_dir_eye", C.c_double * 3),
+        ("fill_dir_eye", C.c_double * 3),
+        ("rim_dir_eye", C.c_double * 3),
+        ("normal_map_strength", C.c_double),
+        ("diffuse", C.c_uint64),
+        ("normal", C.c_uint64),
+        ("specular", C.c_uint64),
+    ]
+
+
+class ShadowUniforms(C.Structure):
+    _fields_ = [
+        ("phong", PhongUniforms),
+        ("light_modelview", C.c_double * 16),
+        ("light_perspective", C.c_double * 16),
+        ("light_viewport", C.c_double * 16),
+        ("shadow_bias", C.c_double),
+        ("shadow_darkening", C.c_double),
+        ("shadow_map", C.c_int32),
+        ("shadow_w", C.c_int32),
+        ("shadow_h", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("triangles_submitted", C.c_uint64),
+        ("triangles_binned", C.c_uint64),
+        ("tile_entries", C.c_uint64),
+        ("fragments_covered", C.c_uint64),
+        ("pixels_shaded", C.c_uint64),
+        ("visible_triangles", C.c_uint64),
+        ("bbox_min_x", C.c_int32),
+        ("bbox_min_y", C.c_int32),
+        ("bbox_max_x", C.c_int32),
+        ("bbox_max_y", C.c_int32),
+        ("z_min", C.c_double),
+        ("z_max_covered", C.c_double),
+        ("fragments_drawn_ref", C.c_uint64),
+        ("z_max_ref", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("ms", C.c_double)]
+
+
+_P = C.c_void_p
+_D = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against trb.h
+SIGNATURES = {
+    "create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "destroy": (C.c_int, [_P]),
+    "last_error": (C.c_char_p, [_P]),
+    "backend_name": (C.c_char_p, []),
+    "upload_mesh": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "free_mesh": (C.c_int, [_P, C.c_uint64]),
+    "upload_texture": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+    "free_texture": (C.c_int, [_P, C.c_uint64]),
+    "begin_frame": (C.c_int, [_P, C.c_int, C.c_int]),
+    "begin_batch": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
+    "set_clear_color": (C.c_int, [_P, C.c_uint8, C.c_uint8, C.c_uint8]),
+    "set_viewport": (C.c_int, [_P, _P]),
+    "draw": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_int, _P, C.c_size_t, C.c_uint64, C.c_uint64]),
+    "draw_batch": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_int, _P, C.c_size_t, C.c_uint64, C.c_uint64]),
+    "submit_clip_triangles": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_int, _P, C.c_size_t]),
+    "depth_snapshot": (C.c_int, [_P]),
+    "depth_restore": (C.c_int, [_P]),
+    "keep_depth_as_shadow_map": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "flush": (C.c_int, [_P]),
+    "end_frame": (C.c_int, [_P]),
+    "ssao": (C.c_int, [_P, C.c_int, _P]),
+    "depth_image": (C.c_int, [_P, C.c_int, _P]),
+    "composite_ao": (C.c_int, [_P, C.c_int, _P]),
+    "read_color": (C.c_int, [_P, C.c_int, _P]),
+    "read_depth": (C.c_int, [_P, C.c_int, _P]),
+    "read_visibility": (C.c_int, [_P, C.c_int, _P]),
+    "get_stats": (C.c_int, [_P, C.c_int, C.POINTER(Stats)]),
+    "synchronize": (C.c_int, [_P]),
+    "timer_start": (C.c_int, [_P]),
+    "timer_stop_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "profile_enable": (C.c_int, [_P, C.c_int]),
+    "profile_read": (C.c_int, [_P, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "launch_count": (C.c_uint64, [_P]),
+    "device_planes": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "set_triangle_id_base": (C.c_int, [_P, C.c_uint64]),
+    "composite_save_local_depth": (C.c_int, [_P]),
+    "composite_mask": (C.c_int, [_P]),
+    "set_shade_rows": (C.c_int, [_P, C.c_int, C.c_int]),
+    "light_dir_eye": (None, [_P, _P, _P]),
+    "lookat": (None, [_P, _P, _P, _P]),
+    "perspective": (None, [C.c_double, C.c_double, C.c_double, C.c_double, _P]),
+    "viewport": (None, [C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "mat4_mul": (None, [_P, _P, _P]),
+}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+def _f64(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and a.size != n:
+        raise ValueError("expected %d doubles, got %d" % (n, a.size))
+    return a
+
+
+class Api:
+    """One loaded backend library (CUDA product or CPU oracle)."""
+
+    def __init__(self, path, prefix):
+        if not os.path.exists(path):
+            raise TrbError("backend library not found: %s" % path)
+        self.path = path
+        self.prefix = prefix
+        self.lib = C.CDLL(path)
+        self.fn = {}
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(self.lib, "%s_%s" % (prefix, name))
+            f.restype = res
+            f.argtypes = args
+            self.fn[name] = f
+
+    def backend_name(self):
+        return self.fn["backend_name"]().decode()
+
+    # host helpers (reference operation order) ------------------------------------------
+    def lookat(self, eye, center, up):
+        out = np.empty(16)
+        self.fn["lookat"](_ptr(_f64(eye, 3)), _ptr(_f64(center, 3)), _ptr(_f64(up, 3)), _ptr(out))
+        return out.reshape(4, 4)
+
+    def perspective(self, fov_deg, aspect, znear, zfar):
+        out = np.empty(16)
+        self.fn["perspective"](fov_deg, aspect, znear, zfar, _ptr(out))
+        return out.reshape(4, 4)
+
+    def viewport(self, x, y, w, h):
+        out = np.empty(16)
+        self.fn["viewport"](x, y, w, h, _ptr(out))
+        return out.reshape(4, 4)
+
+    def mat4_mul(self, a, b):
+        out = np.empty(16)
+        self.fn["mat4_mul"](_ptr(_f64(a, 16)), _ptr(_f64(b, 16)), _ptr(out))
+        return out.reshape(4, 4)
+
+    def light_dir_eye(self, modelview, dir_world):
+        out = np.empty(3)
+        self.fn["light_dir_eye"](_ptr(_f64(modelview, 16)), _ptr(_f64(dir_world, 3)), _ptr(out))
+        return out
+
+
+class Renderer:
+    """A context of one backend; thin, 1:1 over the C ABI."""
+
+    def __init__(self, api, device=0):
+        self.api = api
+        self._fn = api.fn
+        h = _P()
+        rc = self._fn["create"](device, C.byref(h))
+        if rc != 0 or not h:
+            raise TrbError("%s_create(device=%d) failed: rc=%d (no CPU fallback)" % (api.prefix, device, rc))
+        self.h = h
+        self.width = self.height = 0
+        self.nviews = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self._fn["destroy"](self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self._fn["last_error"](self.h)
+            raise TrbError("%s_%s -> %d: %s" % (self.api.prefix, what, rc, msg.decode() if msg else ""))
+
+    # resources ---------------------------------------------------------------------------
+    def upload_mesh(self, pos, nrm=None, uv=None, idx=None):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        nv = pos.shape[0]
+        nrm = None if nrm is None else np.ascontiguousarray(nrm, dtype=np.float32).reshape(nv, 3)
+        uv = None if uv is None else np.ascontiguousarray(uv, dtype=np.float32).reshape(nv, 2)
+        if idx is None:
+            nidx = nv
+        else:
+            idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1)
+            nidx = idx.size
+        out = C.c_uint64(0)
+        self._ck(self._fn["upload_mesh"](self.h, _ptr(pos), _ptr(nrm), _ptr(uv), nv, _ptr(idx), nidx,
+                                         C.byref(out)), "upload_mesh")
+        return out.value
+
+    def free_mesh(self, mesh):
+        self._ck(self._fn["free_mesh"](self.h, mesh), "free_mesh")
+
+    def upload_texture(self, texels):
+        t = np.ascontiguousarray(texels, dtype=np.uint8)
+        if t.ndim == 2:
+            t = t[:, :, None]
+        h, w, bpp = t.shape
+        out = C.c_uint64(0)
+        self._ck(self._fn["upload_texture"](self.h, _ptr(t), w, h, bpp, C.byref(out)), "upload_texture")
+        return out.value
+
+    def free_texture(self, tex):
+        self._ck(self._fn["free_texture"](self.h, tex), "free_texture")
+
+    # frame -------------------------------------------------------------------------------
+    def begin_frame(self, w, h, nviews=1, viewport=None):
+        if nviews == 1:
+            self._ck(self._fn["begin_frame"](self.h, w, h), "begin_frame")
+        else:
+            self._ck(self._fn["begin_batch"](self.h, w, h, nviews), "begin_batch")
+        self.width, self.height, self.nviews = w, h, nviews
+        self.set_viewport(self.api.viewport(0, 0, w, h) if viewport is None else viewport)
+
+    def set_clear_color(self, b, g, r):
+        self._ck(self._fn["set_clear_color"](self.h, b, g, r), "set_clear_color")
+
+    def set_viewport(self, m):
+        self._ck(self._fn["set_viewport"](self.h, _ptr(_f64(m, 16))), "set_viewport")
+
+    def draw(self, mesh, modelview, perspective, kind=SHADER_FLAT_BARY, uniforms=None, first_tri=0,
+             ntris=None, mesh_ntris=None):
+        """modelview/perspective: (4,4) or (nviews,4,4); uniforms: one struct or a ctypes array."""
+        mv = _f64(modelview, 16 * self.nviews)
+        pr = np.ascontiguousarray(perspective, dtype=np.float64)
+        if pr.size == 16 and self.nviews > 1:
+            pr = np.tile(pr.reshape(1, 16), (self.nviews, 1))
+        pr = _f64(pr, 16 * self.nviews)
+        if ntris is None:
+            if mesh_ntris is None:
+                raise ValueError("ntris required")
+            ntris = mesh_ntris
+        if uniforms is None:
+            up, ub = None, 0
+        else:
+            if not isinstance(uniforms, C.Array):
+                arr = (type(uniforms) * self.nviews)(*([uniforms] * self.nviews))
+            else:
+                arr = uniforms
+            up, ub = C.cast(arr, _P), C.sizeof(arr._type_)
+            self._keep.append(arr)
+        name = "draw" if self.nviews == 1 else "draw_batch"
+        self._ck(self._fn[name](self.h, mesh, _ptr(mv), _ptr(pr), kind, up, ub, first_tri, ntris), name)
+
+    def submit_clip_triangles(self, clip, varyings=None, modelview=None, kind=SHADER_FLAT_BARY, uniforms=None):
+        clip = np.ascontiguousarray(clip, dtype=np.float64).reshape(-1, 12)
+        n = clip.shape[0]
+        vr = None if varyings is None else _f64(varyings, n * 24)
+        mv = None if modelview is None else _f64(modelview, 16)
+        up, ub = (None, 0) if uniforms is None else (C.cast(C.pointer(uniforms), _P), C.sizeof(uniforms))
+        self._ck(self._fn["submit_clip_triangles"](self.h, _ptr(clip), _ptr(vr), n, _ptr(mv), kind, up, ub),
+                 "submit_clip_triangles")
+
+    def depth_snapshot(self):
+        self._ck(self._fn["depth_snapshot"](self.h), "depth_snapshot")
+
+    def depth_restore(self):
+        self._ck(self._fn["depth_restore"](self.h), "depth_restore")
+
+    def keep_depth_as_shadow_map(self):
+        out = C.c_int32(-1)
+        self._ck(self._fn["keep_depth_as_shadow_map"](self.h, C.byref(out)), "keep_depth_as_shadow_map")
+        return out.value
+
+    def flush(self):
+        self._ck(self._fn["flush"](self.h), "flush")
+
+    def end_frame(self):
+        self._ck(self._fn["end_frame"](self.h), "end_frame")
+        self._keep.clear()
+
+    # readback ----------------------------------------------------------------------------
+    def read_color(self, view=0, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 3), dtype=np.uint8)
+        self._ck(self._fn["read_color"](self.h, view, _ptr(out)), "read_color")
+        return out
+
+    def read_depth(self, view=0, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width), dtype=np.float64)
+        self._ck(self._fn["read_depth"](self.h, view, _ptr(out)), "read_depth")
+        return out
+
+    def read_visibility(self, view=0):
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        self._ck(self._fn["read_visibility"](self.h, view, _ptr(out)), "read_visibility")
+        return out
+
+    def ssao(self, view=0):
+        out = np.empty((self.height, self.width), dtype=np.uint8)
+        self._ck(self._fn["ssao"](self.h, view, _ptr(out)), "ssao")
+        return out
+
+    def depth_image(self, view=0):
+        out = np.empty((self.height, self.width), dtype=np.uint8)
+        self._ck(self._fn["depth_image"](self.h, view, _ptr(out)), "depth_image")
+        return out
+
+    def composite_ao(self, view=0):
+        out = np.empty((self.height, self.width, 3), dtype=np.uint8)
+        self._ck(self._fn["composite_ao"](self.h, view, _ptr(out)), "composite_ao")
+        return out
+
+    def stats(self, view=0):
+        s = Stats()
+        self._ck(self._fn["get_stats"](self.h, view, C.byref(s)), "get_stats")
+        return s.as_dict()
+
+    def synchronize(self):
+        self._ck(self._fn["synchronize"](self.h), "synchronize")
+
+    # timing ------------------------------------------------------------------------------
+    def timer_start(self):
+        self._ck(self._fn["timer_start"](self.h), "timer_start")
+
+    def timer_stop_ms(self):
+        ms = C.c_float(0)
+        self._ck(self._fn["timer_stop_ms"](self.h, C.byref(ms)), "timer_stop_ms")
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self._ck(self._fn["profile_enable"](self.h, 1 if on else 0), "profile_enable")
+
+    def profile_read(self, reset=True):
+        buf = (KernelTime * 64)()
+        n = C.c_int(0)
+        self._ck(self._fn["profile_read"](self.h, buf, 64, C.byref(n), 1 if reset else 0), "profile_read")
+        return {buf[i].name.decode(): (buf[i].launches, buf[i].ms) for i in range(n.value)}
+
+    def launch_count(self):
+        return int(self._fn["launch_count"](self.h))
+
+    # multi-GPU composite -------------------------------------------------------------------
+    def device_planes(self):
+        a, b, n = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._ck(self._fn["device_planes"](self.h, C.byref(a), C.byref(b), C.byref(n)), "device_planes")
+        return a.value, b.value, n.value
+
+    def set_triangle_id_base(self, base):
+        self._ck(self._fn["set_triangle_id_base"](self.h, base), "set_triangle_id_base")
+
+    def composite_save_local_depth(self):
+        self._ck(self._fn["composite_save_local_depth"](self.h), "composite_save_local_depth")
+
+    def composite_mask(self):
+        self._ck(self._fn["composite_mask"](self.h), "composite_mask")
+
+    def set_shade_rows(self, y0, y1):
+        self._ck(self._fn["set_shade_rows"](self.h, y0, y1), "set_shade_rows")
+
+
+_cuda_api = None
+
+
+def load_cuda():
+    """The product backend.  Raises (never falls back) when the CUDA library is not built."""
+    global _cuda_api
+    if _cuda_api is None:
+        if not os.path.exists(CUDA_LIB):
+            raise TrbError("CUDA backend %s is not built; run `python -c 'import __graft_entry__ as g; "
+                           "g.build()'` (there is no CPU fallback)" % CUDA_LIB)
+        _cuda_api = Api(CUDA_LIB, "trb")
+    return _cuda_api
