@@ -531,8 +531,9 @@ int orc_get_stats(TrbCtx* c, int view, TrbStats* out) {
     std::memset(out, 0, sizeof(*out));
     RefStats now = parse_reference_stats();
     // the reference's counters are process-wide statics: deltas since begin, over ALL views
-    out->triangles_submitted = now.triangles - c->at_begin.triangles;
-    out->fragments_drawn_ref = now.fragments - c->at_begin.fragments;
+    // every view is sent the same draws, so the per-view count is the total / nviews
+    out->triangles_submitted = (now.triangles - c->at_begin.triangles) / (uint64_t)c->nviews;
+    out->fragments_drawn_ref = now.fragments - c->at_begin.fragments;  // all views together
     out->bbox_min_x = now.bx0;  // cumulative since the library was loaded
     out->bbox_min_y = now.by0;
     out->bbox_max_x = now.bx1;

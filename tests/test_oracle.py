@@ -1,0 +1,104 @@
+"""CPU tests: the oracle is pinned to the reference's own rasterizer (oracle/_ref, built from
+/root/reference when present) through the survey's known-answer tests and the committed golden
+vectors; the restatement (oracle/libtrb_port.so) must agree with both bit for bit."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import compare
+import tinyrenderder_b200 as trb
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "golden.json")) as f:
+    GOLDEN = json.load(f)
+
+FAST = sorted(cases.CASES)
+FULL = sorted(cases.FULL_SIZE_CASES)
+
+
+def run_case(api, name):
+    fn = cases.CASES.get(name) or cases.FULL_SIZE_CASES[name]
+    with trb.Renderer(api) as r:
+        return fn(api, r)
+
+
+@pytest.mark.parametrize("name", FAST + FULL)
+def test_port_matches_golden(port_api, name):
+    compare.assert_matches_golden(name, run_case(port_api, name), GOLDEN[name])
+
+
+@pytest.mark.parametrize("name", FAST + ["k7b"])
+def test_reference_matches_golden(ref_api, name):
+    # the reference's own our_gl.cpp; it cannot report the order-independent counters
+    compare.assert_matches_golden(name, run_case(ref_api, name), GOLDEN[name], skip=("stats_port",))
+
+
+def test_survey_kats_on_reference(fresh_ref_api):
+    """SURVEY section 4, K1-K6, numbers obtained from the reference itself during the survey"""
+    api = fresh_ref_api
+    with trb.Renderer(api) as r:
+        o = cases.k1(api, r)
+        assert np.isfinite(o["z"]).sum() == 648
+        assert o["z"][32, 32] == 0.93526860193526862
+        s = r.stats()
+        assert (s["bbox_min_x"], s["bbox_min_y"], s["bbox_max_x"], s["bbox_max_y"]) == (13, 13, 51, 51)
+        assert s["fragments_drawn_ref"] == 648
+        o = cases.k2(api, r)
+        assert np.isfinite(o["z"]).sum() == 289 and r.stats()["fragments_drawn_ref"] == 153 + 136
+        o = cases.k3(api, r)
+        assert np.isfinite(o["z"]).sum() == 512 and abs(o["z"][np.isfinite(o["z"])].max() - 2.859) < 1e-3
+        assert np.isfinite(cases.k4(api, r)["z"]).sum() == 0
+        cases.k5_far_near(api, r)
+        assert r.stats()["fragments_drawn_ref"] == 1024
+        cases.k5_near_far(api, r)
+        assert r.stats()["fragments_drawn_ref"] == 512
+        assert np.isfinite(cases.k6(api, r)["z"]).sum() == 0
+
+
+def test_survey_k7_counts(port_api):
+    """592 743 / 3 571 218 covered pixels, fragments_drawn 12 962 226 over the three runs"""
+    total = 0
+    for name, px in (("k7a", 592743), ("k7b", 3571218), ("k7c", None)):
+        with trb.Renderer(port_api) as r:
+            o = cases.FULL_SIZE_CASES[name](port_api, r)
+            total += r.stats()["fragments_drawn_ref"]
+            if px is not None:
+                assert int(np.isfinite(o["z"]).sum()) == px
+    assert total == 12962226
+
+
+def test_k2_first_triangle_keeps_the_diagonal(port_api):
+    with trb.Renderer(port_api) as r:
+        o = cases.k2(port_api, r)
+    # the 17 pixels on the shared diagonal A-C carry triangle 1's colour: the weight of its vertex B
+    # (channel 1) is 0 there and C's (channel 2) grows; triangle 2 would give the opposite
+    diag = [o["bgr"][8 + i, 8 + i] for i in range(17)]
+    assert all(int(c[1]) == 0 for c in diag)
+    assert all(int(c[2]) > 0 for c in diag[1:])
+
+
+def test_port_counters_are_consistent(port_api):
+    with trb.Renderer(port_api) as r:
+        cases.k5_far_near(port_api, r)
+        s = r.stats()
+        assert s["fragments_covered"] == 1024 and s["fragments_drawn_ref"] == 1024 and s["pixels_shaded"] == 512
+        cases.k5_near_far(port_api, r)
+        s = r.stats()
+        assert s["fragments_covered"] == 1024 and s["fragments_drawn_ref"] == 512
+
+
+def test_host_helpers_agree(port_api, ref_api):
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        eye, ctr, up = rng.normal(size=3) * 3, rng.normal(size=3), np.array([0.0, 1.0, 0.0])
+        assert np.array_equal(port_api.lookat(eye, ctr, up), ref_api.lookat(eye, ctr, up))
+        fov, asp = rng.uniform(20, 110), rng.uniform(0.5, 2.5)
+        assert np.array_equal(port_api.perspective(fov, asp, 0.05, 500.0), ref_api.perspective(fov, asp, 0.05, 500.0))
+        a, b = rng.normal(size=(4, 4)), rng.normal(size=(4, 4))
+        assert np.array_equal(port_api.mat4_mul(a, b), ref_api.mat4_mul(a, b))
+        d = rng.normal(size=3)
+        assert np.array_equal(port_api.light_dir_eye(a, d), ref_api.light_dir_eye(a, d))
+    assert np.array_equal(port_api.viewport(3, 5, 1201, 799), ref_api.viewport(3, 5, 1201, 799))

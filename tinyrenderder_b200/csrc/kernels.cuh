@@ -1,0 +1,656 @@
+// kernels.cuh - CUDA kernels of the rasterization path for sm_100a (B200).
+//
+// Pipeline per draw call (one call == the per-face loop of main.cpp:660-666):
+//   k_vertex_*     per unique vertex: ModelView/Perspective/perspective divide/Viewport -> VRec (32 B)
+//   k_setup_count  per triangle: rejects of our_gl.cpp:94-135, pixel bbox -> 16x16 tile range,
+//                  warp-aggregated per-tile counts, statistics bbox
+//   k_scan_*       exclusive prefix sum of the tile counts -> bin offsets
+//   k_fill         per triangle: warp-aggregated slot claim, triangle id written into its tiles' bins
+//   k_raster       one CTA per 16x16 tile: the tile's depth keys + ids staged in shared memory,
+//                  exact per-sample evaluation, order-independent (depth, id) resolve
+//   k_shade        (flush) one thread per pixel: winner's barycentrics recomputed, fragment shader run
+//                  once per visible pixel, BGR written
+// All arithmetic is in exact.cuh; nothing here reorders a floating-point operation.
+#pragma once
+#include <cuda_runtime.h>
+#include "exact.cuh"
+
+namespace trbk {
+using namespace trbx;
+
+constexpr int TILE = 16;
+constexpr int TILE_SHIFT = 4;
+constexpr int TPB = 256;               // threads per block everywhere (== pixels per tile)
+constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
+constexpr uint32_t VIS_SHADED = 0u;    // pixel already shaded by an earlier flush; ties keep it
+constexpr int QCAP = 1024;             // candidate queue entries per CTA
+constexpr int BIG_NS = 64;             // triangles covering >= this many samples of a tile take the
+                                       // pixel-owner path (no atomics)
+
+struct DevStats {
+    unsigned long long tri_binned, tile_entries, frag_covered, pixels_shaded;
+    int bx0, by0, bx1, by1;
+    unsigned long long zmin_key, zmax_key;
+};
+
+struct FrameDev {
+    int W, H, tw, th, ntiles, nviews;
+    unsigned long long npix;
+    unsigned long long* zkey;  // [nviews][npix] order-preserving depth keys
+    uint32_t* vis;             // [nviews][npix] winning triangle id
+    uint8_t* color;            // [nviews][npix][3] BGR
+    DevStats* stats;           // [nviews]
+    double viewport[16];
+};
+
+struct DrawDev {               // one draw call, kept until flush (the shade kernel needs it)
+    uint32_t id_base;          // vis id of local triangle t is id_base + t + 1
+    uint32_t ntris;
+    uint32_t first_tri;        // offset (in triangles) into idx
+    uint32_t nverts;
+    const uint32_t* idx;       // nullptr: implicit soup, vertex 3t+k
+    const float* attr8;        // [nverts][8] pos,nrm,uv (mesh draws)
+    const VRec* vrec;          // [nviews][nverts]
+    const double* mats;        // [nviews][32] ModelView, Perspective
+    const LitUniforms* uniforms;  // [nviews] or nullptr
+    const double* varyings;    // immediate mode: [ntris][24]
+    int kind;
+    int _pad;
+};
+
+__device__ __forceinline__ uint32_t vertex_index(const uint32_t* idx, uint32_t first_tri, uint32_t t, int k) {
+    size_t e = ((size_t)first_tri + t) * 3 + k;
+    return idx ? __ldg(idx + e) : (uint32_t)e;
+}
+__device__ __forceinline__ VRec load_vrec(const VRec* p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    VRec r;
+    r.sx = a.x; r.sy = a.y; r.z = b.x; r.w = b.y;
+    return r;
+}
+__device__ __forceinline__ void store_vrec(VRec* p, const VRec& r) {
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(r.sx, r.sy);
+    q[1] = make_double2(r.z, r.w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame clear: init_zbuffer (our_gl.cpp:72-74) + TGAImage(w,h,RGB,clear) (tgaimage.cpp:8-17)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_clear(FrameDev f, uint8_t cb, uint8_t cg, uint8_t cr) {
+    unsigned long long total = f.npix * f.nviews;
+    unsigned long long stride = (unsigned long long)gridDim.x * TPB;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < total; i += stride) {
+        f.zkey[i] = KEY_PLUS_INF;
+        f.vis[i] = VIS_NONE;
+        f.color[3 * i] = cb;
+        f.color[3 * i + 1] = cg;
+        f.color[3 * i + 2] = cr;
+    }
+    for (int v = threadIdx.x; blockIdx.x == 0 && v < f.nviews; v += TPB) {
+        DevStats s;
+        s.tri_binned = s.tile_entries = s.frag_covered = s.pixels_shaded = 0;
+        s.bx0 = s.by0 = INT_MAX;
+        s.bx1 = s.by1 = INT_MIN;
+        s.zmin_key = ~0ull;
+        s.zmax_key = 0ull;
+        f.stats[v] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vertex stage
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_vertex_mesh(FrameDev f, const float4* __restrict__ pos4, uint32_t nverts,
+                                                     const double* __restrict__ mats, VRec* __restrict__ out) {
+    __shared__ double m[32];
+    const int view = blockIdx.y;
+    if (threadIdx.x < 32) m[threadIdx.x] = mats[view * 32 + threadIdx.x];
+    __syncthreads();
+    uint32_t v = blockIdx.x * TPB + threadIdx.x;
+    if (v >= nverts) return;
+    float4 p = __ldg(pos4 + v);
+    VRec r = vrec_from_position(m, m + 16, f.viewport, (double)p.x, (double)p.y, (double)p.z);
+    store_vrec(out + (size_t)view * nverts + v, r);
+}
+
+__global__ void __launch_bounds__(TPB) k_vertex_clip(FrameDev f, const double* __restrict__ clip4, uint32_t nverts,
+                                                     VRec* __restrict__ out) {
+    uint32_t v = blockIdx.x * TPB + threadIdx.x;
+    if (v >= nverts) return;
+    const double2* q = reinterpret_cast<const double2*>(clip4) + (size_t)v * 2;
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    store_vrec(out + v, vrec_from_clip(f.viewport, a.x, a.y, b.x, b.y));
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup + per-tile count
+// ---------------------------------------------------------------------------------------------
+struct GeomArgs {
+    const uint32_t* idx;
+    uint32_t first_tri, ntris, nverts, id_base;
+    const VRec* vrec;          // [nviews][nverts]
+};
+
+constexpr uint32_t BOX_NONE = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int block_reduce_min(int v, int* sh) {
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < TPB / 32 ? sh[threadIdx.x] : INT_MAX;
+        for (int o = 4; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    __syncthreads();
+    return v;  // valid in thread 0
+}
+__device__ __forceinline__ unsigned long long block_reduce_sum(unsigned long long v, unsigned long long* sh) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < TPB / 32 ? sh[threadIdx.x] : 0ull;
+        for (int o = 4; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    __syncthreads();
+    return v;  // valid in thread 0
+}
+__device__ __forceinline__ unsigned long long block_reduce_min64(unsigned long long v, unsigned long long* sh) {
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < TPB / 32 ? sh[threadIdx.x] : ~0ull;
+        for (int o = 4; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uint2* __restrict__ tribox,
+                                                     uint32_t* __restrict__ tile_count) {
+    __shared__ int sh_i[TPB / 32];
+    __shared__ unsigned long long sh_u[TPB / 32];
+    const int view = blockIdx.y;
+    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+    const VRec* vr = g.vrec + (size_t)view * g.nverts;
+    int res = SETUP_REJECT;
+    TriSetup ts;
+    if (t < g.ntris) {
+        VRec a = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 0));
+        VRec b = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 1));
+        VRec c = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 2));
+        res = setup_triangle(a, b, c, f.W, f.H, ts);
+    }
+    // statistics bbox + "survived the rejects" count, our_gl.cpp:138-141
+    const bool counted = res != SETUP_REJECT;
+    int bx0 = block_reduce_min(counted ? ts.x0 : INT_MAX, sh_i);
+    int by0 = block_reduce_min(counted ? ts.y0 : INT_MAX, sh_i);
+    int bx1 = -block_reduce_min(counted ? -ts.x1 : INT_MAX, sh_i);
+    int by1 = -block_reduce_min(counted ? -ts.y1 : INT_MAX, sh_i);
+    unsigned long long nb = block_reduce_sum(counted ? 1ull : 0ull, sh_u);
+
+    uint2 box = make_uint2(BOX_NONE, 0u);
+    uint32_t ntile = 0;
+    int tx0 = 0, ty0 = 0, tx1 = -1, ty1 = -1;
+    if (res == SETUP_DRAW) {
+        tx0 = ts.x0 >> TILE_SHIFT; tx1 = ts.x1 >> TILE_SHIFT;
+        ty0 = ts.y0 >> TILE_SHIFT; ty1 = ts.y1 >> TILE_SHIFT;
+        box = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
+        ntile = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+    }
+    if (t < g.ntris) tribox[(size_t)view * g.ntris + t] = box;
+    unsigned long long ne = block_reduce_sum(ntile, sh_u);
+    if (threadIdx.x == 0 && nb) {
+        DevStats* s = f.stats + view;
+        atomicMin(&s->bx0, bx0); atomicMin(&s->by0, by0);
+        atomicMax(&s->bx1, bx1); atomicMax(&s->by1, by1);
+        atomicAdd(&s->tri_binned, nb);
+        if (ne) atomicAdd(&s->tile_entries, ne);
+    }
+    // per-tile counts; single-tile triangles (the common case for small triangles) are aggregated
+    // across the warp with match_any so that coherent meshes do not serialise on one counter
+    uint32_t* cnt = tile_count + (size_t)view * f.ntiles;
+    const unsigned lane = threadIdx.x & 31;
+    unsigned key = 0x80000000u | lane;  // unique: no aggregation
+    if (ntile == 1) key = (unsigned)(ty0 * f.tw + tx0);
+    unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (ntile == 1) {
+        if ((unsigned)(__ffs(peers) - 1) == lane) atomicAdd(cnt + key, (uint32_t)__popc(peers));
+    } else if (ntile > 1) {
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt + ty * f.tw + tx, 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of the tile counts (three small kernels; 2048 elements per block)
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = TPB * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sh, uint32_t& total) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (unsigned)o) x += y;
+    }
+    if (lane == 31) sh[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < TPB / 32 ? sh[lane] : 0u;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= (unsigned)o) w += y;
+        }
+        if (lane < TPB / 32) sh[lane] = w;
+    }
+    __syncthreads();
+    uint32_t warp_off = warp ? sh[warp - 1] : 0u;
+    total = sh[TPB / 32 - 1];
+    __syncthreads();
+    return warp_off + x - v;
+}
+
+__global__ void __launch_bounds__(TPB) k_scan_partial(const uint32_t* __restrict__ in, uint32_t n,
+                                                      uint32_t* __restrict__ block_sum) {
+    __shared__ unsigned long long sh[TPB / 32];
+    size_t base = (size_t)blockIdx.x * SCAN_BLOCK;
+    unsigned long long s = 0;
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        size_t e = base + (size_t)i * TPB + threadIdx.x;
+        if (e < n) s += in[e];
+    }
+    s = block_reduce_sum(s, sh);
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = (uint32_t)s;
+}
+// single block: exclusive scan of the block sums in place, total written to *total_out
+__global__ void __launch_bounds__(TPB) k_scan_sums(uint32_t* __restrict__ block_sum, uint32_t nblocks,
+                                                   uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t sh[TPB / 32];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nblocks; base += TPB) {
+        uint32_t e = base + threadIdx.x;
+        uint32_t v = e < nblocks ? block_sum[e] : 0u, tot;
+        uint32_t ex = block_exclusive_scan(v, sh, tot);
+        if (e < nblocks) block_sum[e] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(TPB) k_scan_final(const uint32_t* __restrict__ in, uint32_t n,
+                                                    const uint32_t* __restrict__ block_sum,
+                                                    uint32_t* __restrict__ out) {
+    __shared__ uint32_t sh[TPB / 32];
+    size_t base = (size_t)blockIdx.x * SCAN_BLOCK + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = base + i < n ? in[base + i] : 0u;
+        s += v[i];
+    }
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(s, sh, tot) + block_sum[blockIdx.x];
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bin fill: order inside a bin is irrelevant, the resolve is order independent
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_fill(FrameDev f, uint32_t ntris, const uint2* __restrict__ tribox,
+                                              const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
+                                              uint32_t* __restrict__ bins) {
+    const int view = blockIdx.y;
+    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+    uint2 box = make_uint2(BOX_NONE, 0u);
+    if (t < ntris) box = tribox[(size_t)view * ntris + t];
+    const bool has = box.x != BOX_NONE;
+    const int tx0 = box.x & 0xffff, ty0 = box.x >> 16, tx1 = box.y & 0xffff, ty1 = box.y >> 16;
+    const bool single = has && tx0 == tx1 && ty0 == ty1;
+    const size_t vbase = (size_t)view * f.ntiles;
+    const unsigned lane = threadIdx.x & 31;
+    unsigned key = 0x80000000u | lane;
+    if (single) key = (unsigned)(ty0 * f.tw + tx0);
+    unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (single) {
+        int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((unsigned)leader == lane) base = atomicAdd(cursor + vbase + key, (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        bins[offsets[vbase + key] + base + rank] = t;
+    } else if (has) {
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                size_t tile = vbase + (size_t)ty * f.tw + tx;
+                uint32_t slot = atomicAdd(cursor + tile, 1u);
+                bins[offsets[tile] + slot] = t;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fine raster: one CTA owns one 16x16 tile
+// ---------------------------------------------------------------------------------------------
+struct BigTri {
+    double ax, ay, s00, s01, s10, s11, uz, z0, z1, z2;
+    int x0, y0, x1, y1;   // bbox clipped to the tile, absolute pixels
+    uint32_t id;
+    uint32_t _pad;
+};
+
+struct RasterArgs {
+    GeomArgs g;
+    const uint32_t* counts;   // [nviews][ntiles]
+    const uint32_t* offsets;  // [nviews][ntiles]
+    const uint32_t* bins;
+};
+
+__global__ void __launch_bounds__(TPB) k_raster(FrameDev f, RasterArgs a) {
+    const int tile = blockIdx.x, view = blockIdx.y;
+    const size_t tslot = (size_t)view * f.ntiles + tile;
+    const uint32_t n = a.counts[tslot];
+    if (n == 0) return;
+    const uint32_t off = a.offsets[tslot];
+
+    __shared__ unsigned long long zk[TPB];
+    __shared__ uint32_t vid[TPB];
+    __shared__ unsigned long long qk[QCAP];
+    __shared__ uint32_t qid[QCAP];
+    __shared__ uint8_t qp[QCAP];
+    __shared__ BigTri big[TPB];
+    __shared__ unsigned int qn, nbig, overflow;
+    __shared__ unsigned long long red[TPB / 32];
+
+    const int tid = threadIdx.x;
+    const int tx0 = (tile % f.tw) << TILE_SHIFT, ty0 = (tile / f.tw) << TILE_SHIFT;
+    const int px = tx0 + (tid & 15), py = ty0 + (tid >> 4);
+    const bool pvalid = px < f.W && py < f.H;
+    const size_t gp = (size_t)view * f.npix + (size_t)py * f.W + px;
+    zk[tid] = pvalid ? f.zkey[gp] : 0ull;
+    vid[tid] = pvalid ? f.vis[gp] : VIS_NONE;
+    unsigned long long prev = zk[tid];
+    if (tid == 0) { qn = 0; nbig = 0; overflow = 0; }
+    __syncthreads();
+
+    const VRec* vr = a.g.vrec + (size_t)view * a.g.nverts;
+    unsigned long long covered = 0, zmin = ~0ull, zmax = 0ull;
+
+    for (uint32_t base = 0; base < n; base += TPB) {
+        TriSetup ts;
+        uint32_t gid = 0;
+        int cx0 = 0, cy0 = 0, cx1 = -1, cy1 = -1;
+        bool pending = false;
+        if (base + tid < n) {
+            uint32_t t = __ldg(a.bins + off + base + tid);
+            VRec va = load_vrec(vr + vertex_index(a.g.idx, a.g.first_tri, t, 0));
+            VRec vb = load_vrec(vr + vertex_index(a.g.idx, a.g.first_tri, t, 1));
+            VRec vc = load_vrec(vr + vertex_index(a.g.idx, a.g.first_tri, t, 2));
+            setup_triangle(va, vb, vc, f.W, f.H, ts);   // SETUP_DRAW by construction of the bins
+            gid = a.g.id_base + t + 1u;
+            cx0 = max(ts.x0, tx0); cx1 = min(ts.x1, tx0 + TILE - 1);
+            cy0 = max(ts.y0, ty0); cy1 = min(ts.y1, ty0 + TILE - 1);
+            int ns = (cx1 - cx0 + 1) * (cy1 - cy0 + 1);
+            if (ns >= BIG_NS) {
+                unsigned s = atomicAdd(&nbig, 1u);
+                BigTri& B = big[s];
+                B.ax = ts.ax; B.ay = ts.ay; B.s00 = ts.s00; B.s01 = ts.s01; B.s10 = ts.s10; B.s11 = ts.s11;
+                B.uz = ts.uz; B.z0 = ts.z0; B.z1 = ts.z1; B.z2 = ts.z2;
+                B.x0 = cx0; B.y0 = cy0; B.x1 = cx1; B.y1 = cy1; B.id = gid;
+            } else {
+                pending = ns > 0;
+            }
+        }
+        // ---- small triangles: one thread per triangle, atomics on the tile's keys -------------
+        int sx = cx0, sy = cy0;  // resume position when the candidate queue fills up
+        for (;;) {
+            if (pending) {
+                bool full = false;
+                while (sy <= cy1) {
+                    double b[3], z;
+                    if (eval_sample(ts, sx, sy, b, z)) {
+                        const unsigned long long k = fragment_key(z);
+                        const int p = ((sy - ty0) << TILE_SHIFT) | (sx - tx0);
+                        if (k <= *(volatile unsigned long long*)&zk[p]) {
+                            unsigned long long old = atomicMin(&zk[p], k);
+                            if (old >= k) {  // current minimum or a tie: remember who asked
+                                unsigned s = atomicAdd(&qn, 1u);
+                                if (s >= (unsigned)QCAP) { overflow = 1u; full = true; break; }
+                                qk[s] = k; qid[s] = gid; qp[s] = (uint8_t)p;
+                            }
+                        }
+                        ++covered;
+                        zmin = min(zmin, k); zmax = max(zmax, k);
+                    }
+                    if (++sx > cx1) { sx = cx0; ++sy; }
+                }
+                if (!full) pending = false;
+            }
+            __syncthreads();
+            // a pixel whose depth got strictly smaller forgets its previous winner
+            if (zk[tid] != prev) { vid[tid] = VIS_NONE; prev = zk[tid]; }
+            __syncthreads();
+            const unsigned qc = min(qn, (unsigned)QCAP);
+            for (unsigned e = tid; e < qc; e += TPB)
+                if (zk[qp[e]] == qk[e]) atomicMin(&vid[qp[e]], qid[e]);  // ties: lowest id = first submitted
+            const bool more = overflow != 0u;
+            __syncthreads();
+            if (tid == 0) { qn = 0; overflow = 0; }
+            __syncthreads();
+            if (!more) break;
+        }
+        // ---- big triangles: every thread owns its pixel, no atomics -----------------------------
+        const unsigned nb = nbig;
+        if (nb) {
+            unsigned long long myk = zk[tid];
+            uint32_t myid = vid[tid];
+            for (unsigned j = 0; j < nb; ++j) {
+                const BigTri& B = big[j];
+                if (px < B.x0 || px > B.x1 || py < B.y0 || py > B.y1) continue;
+                TriSetup t2;
+                t2.ax = B.ax; t2.ay = B.ay; t2.s00 = B.s00; t2.s01 = B.s01; t2.s10 = B.s10; t2.s11 = B.s11;
+                t2.uz = B.uz; t2.z0 = B.z0; t2.z1 = B.z1; t2.z2 = B.z2;
+                double b[3], z;
+                if (!eval_sample(t2, px, py, b, z)) continue;
+                unsigned long long k = fragment_key(z);
+                ++covered;
+                zmin = min(zmin, k); zmax = max(zmax, k);
+                if (k < myk) { myk = k; myid = B.id; }
+                else if (k == myk && B.id < myid) myid = B.id;
+            }
+            zk[tid] = myk; vid[tid] = myid; prev = myk;
+            __syncthreads();
+            if (tid == 0) nbig = 0;
+            __syncthreads();
+        }
+    }
+    if (pvalid) { f.zkey[gp] = zk[tid]; f.vis[gp] = vid[tid]; }
+    covered = block_reduce_sum(covered, red);
+    zmin = block_reduce_min64(zmin, red);
+    zmax = ~block_reduce_min64(~zmax, red);
+    if (tid == 0 && covered) {
+        DevStats* s = f.stats + view;
+        atomicAdd(&s->frag_covered, covered);
+        atomicMin(&s->zmin_key, zmin);
+        atomicMax(&s->zmax_key, zmax);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// flush: the fragment() calls of our_gl.cpp:187-192, once per visible pixel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_shade(FrameDev f, const DrawDev* __restrict__ draws, int ndraws, int row0,
+                                               int row1) {
+    const int view = blockIdx.y;
+    const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
+    const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
+    if (p < last) {
+        const size_t gp = (size_t)view * f.npix + p;
+        const uint32_t id = f.vis[gp];
+        if (id != VIS_NONE && id != VIS_SHADED) {
+            int lo = 0, hi = ndraws - 1;  // last draw with id_base < id
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (draws[mid].id_base < id) lo = mid; else hi = mid - 1;
+            }
+            const DrawDev D = draws[lo];
+            const uint32_t t = id - D.id_base - 1u;
+            const uint32_t i0 = vertex_index(D.idx, D.first_tri, t, 0);
+            const uint32_t i1 = vertex_index(D.idx, D.first_tri, t, 1);
+            const uint32_t i2 = vertex_index(D.idx, D.first_tri, t, 2);
+            const VRec* vr = D.vrec + (size_t)view * D.nverts;
+            const VRec va = load_vrec(vr + i0), vb = load_vrec(vr + i1), vc = load_vrec(vr + i2);
+            TriSetup ts;
+            setup_triangle(va, vb, vc, f.W, f.H, ts);
+            const int x = (int)(p % f.W), y = (int)(p / f.W);
+            double b[3], z, pc[3];
+            if (eval_sample(ts, x, y, b, z)) {          // always true for a recorded winner
+                f.zkey[gp] = depth_key(z);              // exact bits of the reference's zbuffer[idx] (keeps -0.0)
+                perspective_bary(b, va.w, vb.w, vc.w, pc);
+                uint8_t col[3];
+                bool write = true;
+                if (D.kind == 0 /*FLAT_BARY*/) {
+                    shade_flat_bary(pc, col);
+                } else if (D.kind == 3 /*DEPTH*/) {
+                    write = false;
+                } else {
+                    const double* MV = D.mats + (size_t)view * 32;
+                    Varyings vy;
+                    if (D.varyings) {
+                        const double* q = D.varyings + (size_t)t * 24;
+                        for (int k = 0; k < 3; ++k) {
+                            vy.u[k] = q[k * 8]; vy.v[k] = q[k * 8 + 1];
+                            vy.pos_eye[k] = D3{q[k * 8 + 2], q[k * 8 + 3], q[k * 8 + 4]};
+                            vy.nrm_eye[k] = D3{q[k * 8 + 5], q[k * 8 + 6], q[k * 8 + 7]};
+                        }
+                    } else {
+                        const uint32_t vi[3] = {i0, i1, i2};
+                        for (int k = 0; k < 3; ++k) {
+                            const float4* q = reinterpret_cast<const float4*>(D.attr8 + (size_t)vi[k] * 8);
+                            float4 q0 = __ldg(q), q1 = __ldg(q + 1);
+                            float at[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                            varyings_from_attr(MV, at, k, vy);
+                        }
+                    }
+                    shade_lit(D.kind == 2 /*EYE*/, MV, D.uniforms[view], vy, pc, col);
+                }
+                if (write) {
+                    uint8_t* c = f.color + gp * 3;
+                    c[0] = col[0]; c[1] = col[1]; c[2] = col[2];
+                }
+            }
+            f.vis[gp] = VIS_SHADED;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// readback helpers and post passes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_unmap_depth(const unsigned long long* __restrict__ zkey,
+                                                     unsigned long long n, double* __restrict__ out) {
+    unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) out[i] = depth_from_key(zkey[i]);
+}
+__global__ void __launch_bounds__(TPB) k_count_finite(const unsigned long long* __restrict__ zkey,
+                                                      unsigned long long n, unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long red[TPB / 32];
+    unsigned long long s = 0, stride = (unsigned long long)gridDim.x * TPB;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride)
+        s += finite_d(depth_from_key(zkey[i])) ? 1ull : 0ull;
+    s = block_reduce_sum(s, red);
+    if (threadIdx.x == 0 && s) atomicAdd(out, s);
+}
+
+// compute_ssao_at (main.cpp:324-362) per pixel; dir[] = cos/sin of main.cpp:333-334 evaluated by the
+// host's libm so that the sample offsets are the reference's
+struct SsaoDirs { double dx[8], dy[8]; };
+__device__ __forceinline__ uint8_t ssao_at(const unsigned long long* zkey, int W, int H, int px, int py,
+                                           const SsaoDirs& d) {
+    double centre = depth_from_key(zkey[(size_t)px + (size_t)py * W]);
+    double ao = 1.0;
+    if (finite_d(centre)) {
+        int occluded = 0, total = 0;
+        for (int k = 0; k < 8; ++k)
+            for (int s = 1; s <= 8; ++s) {
+                double radius = (double)s / 8 * 16.0;                 // main.cpp:337
+                int sx = (int)round(px + d.dx[k] * radius);
+                int sy = (int)round(py + d.dy[k] * radius);
+                if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
+                double sd = depth_from_key(zkey[(size_t)sx + (size_t)sy * W]);
+                if (!finite_d(sd)) { total++; continue; }
+                if (sd < centre - 1e-3) occluded++;
+                total++;
+            }
+        if (total != 0) ao = 1.0 - ((double)occluded / (double)total) * 0.35;
+    }
+    return (uint8_t)(int)(255.0 * ao);                                  // main.cpp:760
+}
+__global__ void __launch_bounds__(TPB) k_ssao(const unsigned long long* __restrict__ zkey, int W, int H, SsaoDirs d,
+                                              uint8_t* __restrict__ ao) {
+    int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (x < W && y < H) ao[(size_t)x + (size_t)y * W] = ssao_at(zkey, W, H, x, y, d);
+}
+// final = phong * ao, main.cpp:768-783
+__global__ void __launch_bounds__(TPB) k_composite_ao(const unsigned long long* __restrict__ zkey,
+                                                      const uint8_t* __restrict__ color, int W, int H, SsaoDirs d,
+                                                      uint8_t* __restrict__ out) {
+    int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (x >= W || y >= H) return;
+    size_t i = (size_t)x + (size_t)y * W;
+    double fct = (double)ssao_at(zkey, W, H, x, y, d) / 255.0;
+    for (int ch = 0; ch < 3; ++ch) out[3 * i + ch] = (uint8_t)(int)std_min(255.0, (double)color[3 * i + ch] * fct);
+}
+// save_zbuffer_image (main.cpp:269-314): pass 1 min/max over finite depths, pass 2 grey map
+__global__ void __launch_bounds__(TPB) k_depth_range(const unsigned long long* __restrict__ zkey,
+                                                     unsigned long long n, unsigned long long* __restrict__ lohi) {
+    __shared__ unsigned long long red[TPB / 32];
+    unsigned long long lo = ~0ull, hi = 0ull, stride = (unsigned long long)gridDim.x * TPB;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) {
+        unsigned long long k = zkey[i];
+        if (finite_d(depth_from_key(k))) { lo = min(lo, k); hi = max(hi, k); }
+    }
+    lo = block_reduce_min64(lo, red);
+    hi = ~block_reduce_min64(~hi, red);
+    if (threadIdx.x == 0) { atomicMin(lohi, lo); atomicMax(lohi + 1, hi); }
+}
+__global__ void __launch_bounds__(TPB) k_depth_image(const unsigned long long* __restrict__ zkey,
+                                                     unsigned long long n, const unsigned long long* __restrict__ lohi,
+                                                     uint8_t* __restrict__ grey) {
+    unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    // main.cpp:275: the search starts from the FINITE values 1e9 / -1e9
+    double lo = std_min(1e9, lohi[0] == ~0ull ? 1e9 : depth_from_key(lohi[0]));
+    double hi = std_max(-1e9, lohi[1] == 0ull ? -1e9 : depth_from_key(lohi[1]));
+    if (hi - lo < 1e-7) hi = lo + 1e-7;                                 // main.cpp:294
+    double z = depth_from_key(zkey[i]);
+    uint8_t v = 255;
+    if (finite_d(z)) {
+        double t = (z - lo) / (hi - lo);
+        v = (uint8_t)(int)(255.0 * (1.0 - t));                          // main.cpp:306
+    }
+    grey[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sort-last composite helpers (config 4): after the host all-reduced (min) the depth keys,
+// drop local winners that lost; the id plane is then min-reduced too (lowest id == first submitted)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_composite_mask(const unsigned long long* __restrict__ local_key,
+                                                        const unsigned long long* __restrict__ global_key,
+                                                        uint32_t* __restrict__ vis, unsigned long long n) {
+    unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x;
+    if (i < n && local_key[i] != global_key[i]) vis[i] = VIS_NONE;
+}
+__global__ void __launch_bounds__(TPB) k_key_to_sortable_i64(unsigned long long* __restrict__ key, unsigned long long n) {
+    // uint64 order -> int64 order (for collectives that only know signed types): flip the top bit
+    unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) key[i] ^= KEY_SIGN;
+}
+
+}  // namespace trbk

@@ -1,0 +1,1001 @@
+// trb.cu - host side of the B200 rasterization backend: the C ABI of include/trb.h over the
+// kernels of kernels.cuh.  One context = one GPU = one CUDA stream.  No CPU fallback: every
+// entry point that needs the device fails with TRB_E_CUDA when it is not there.
+#include "../../include/trb.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace trbk;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, cudaStream_t st) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) {
+            cudaStreamSynchronize(st);  // kernels in flight may still read the old block
+            cudaFree(p);
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Frame arena: bump allocator for everything that must live until the next flush (vertex
+// records, per-draw matrices and uniforms).  Reset at begin_frame / after flush; grows by chaining.
+struct Arena {
+    struct Block { char* p; size_t cap, used; };
+    std::vector<Block> blocks;
+    size_t next_cap = (size_t)64 << 20;
+    void* alloc(size_t bytes, cudaError_t& err) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (auto& b : blocks)
+            if (b.cap - b.used >= bytes) {
+                void* r = b.p + b.used;
+                b.used += bytes;
+                return r;
+            }
+        size_t cap = next_cap;
+        while (cap < bytes) cap *= 2;
+        Block nb{nullptr, cap, 0};
+        err = cudaMalloc((void**)&nb.p, cap);
+        if (err != cudaSuccess) return nullptr;
+        next_cap = cap * 2;
+        nb.used = bytes;
+        blocks.push_back(nb);
+        return nb.p;
+    }
+    void reset() {
+        for (auto& b : blocks) b.used = 0;
+    }
+    void release() {
+        for (auto& b : blocks) cudaFree(b.p);
+        blocks.clear();
+    }
+};
+
+struct Mesh {
+    float4* pos4 = nullptr;
+    float* attr8 = nullptr;
+    uint32_t* idx = nullptr;   // nullptr = implicit
+    uint32_t nverts = 0;
+    uint64_t nidx = 0;
+    bool alive = false;
+};
+struct Tex {
+    uint8_t* px = nullptr;
+    int w = 0, h = 0, bpp = 0;
+    bool alive = false;
+};
+
+struct ProfEntry {
+    const char* name;
+    cudaEvent_t a, b;
+};
+struct ProfAcc {
+    std::string name;
+    uint64_t launches = 0;
+    double ms = 0;
+};
+
+}  // namespace
+
+struct TrbCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    std::vector<Mesh> meshes;
+    std::vector<Tex> textures;
+
+    // frame
+    FrameDev frame{};
+    bool in_frame = false;
+    uint8_t clear[3] = {0, 0, 0};
+    DevBuf zkey, vis, color, stats, zsnap, zlocal;
+    bool have_snapshot = false;
+    std::vector<DevBuf> shadow_maps;
+    Arena arena;
+    std::vector<DrawDev> draws;     // since the last flush
+    DevBuf draw_table;
+    uint64_t next_id = 0;
+    uint64_t tris_submitted = 0;
+    int shade_row0 = 0, shade_row1 = -1;
+
+    // per-draw scratch (stream ordered reuse)
+    DevBuf tribox, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
+    uint32_t* host_total = nullptr;  // pinned
+
+    // timing
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    bool profiling = false;
+    std::vector<ProfEntry> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<ProfAcc> prof_acc;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int fail(TrbCtx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? TRB_E_NOMEM : TRB_E_CUDA,             \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+    } while (0)
+
+struct Launch {  // RAII around one kernel launch: counts it and, when profiling, brackets it with events
+    TrbCtx* c;
+    const char* name;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Launch(TrbCtx* c_, const char* n) : c(c_), name(n) {
+        ++c->launches;
+        if (c->profiling) {
+            a = get_event();
+            b = get_event();
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    ~Launch() {
+        if (c->profiling) {
+            cudaEventRecord(b, c->stream);
+            c->prof_pending.push_back(ProfEntry{name, a, b});
+        }
+    }
+    cudaEvent_t get_event() {
+        if (!c->ev_pool.empty()) {
+            cudaEvent_t e = c->ev_pool.back();
+            c->ev_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
+void prof_collect(TrbCtx* c) {
+    if (c->prof_pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& p : c->prof_pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        ProfAcc* acc = nullptr;
+        for (auto& a : c->prof_acc)
+            if (a.name == p.name) acc = &a;
+        if (!acc) {
+            c->prof_acc.push_back(ProfAcc{p.name, 0, 0});
+            acc = &c->prof_acc.back();
+        }
+        acc->launches++;
+        acc->ms += ms;
+        c->ev_pool.push_back(p.a);
+        c->ev_pool.push_back(p.b);
+    }
+    c->prof_pending.clear();
+}
+
+inline unsigned blocks_for(unsigned long long n) { return (unsigned)((n + TPB - 1) / TPB); }
+
+int check_device(TrbCtx* c) {
+    CU(cudaSetDevice(c->device));
+    return TRB_OK;
+}
+
+// upload the draw table and run the shade kernel over [row0,row1)
+int do_flush(TrbCtx* c) {
+    if (!c->in_frame) return fail(c, TRB_E_ARG, "flush: no frame");
+    if (c->draws.empty()) return TRB_OK;
+    int rc = check_device(c);
+    if (rc) return rc;
+    size_t bytes = c->draws.size() * sizeof(DrawDev);
+    CU(c->draw_table.ensure(bytes, c->stream));
+    CU(cudaMemcpyAsync(c->draw_table.p, c->draws.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    int r0 = 0, r1 = c->frame.H;
+    if (c->shade_row1 >= 0) {
+        r0 = c->shade_row0;
+        r1 = c->shade_row1;
+    }
+    if (r1 > r0) {
+        unsigned long long n = (unsigned long long)(r1 - r0) * c->frame.W;
+        dim3 grid(blocks_for(n), c->frame.nviews);
+        Launch L(c, "k_shade");
+        k_shade<<<grid, TPB, 0, c->stream>>>(c->frame, c->draw_table.as<DrawDev>(), (int)c->draws.size(), r0, r1);
+    }
+    CU(cudaGetLastError());
+    // the pageable->device copy of the table is staged before cudaMemcpyAsync returns, so the
+    // host vector may be cleared now; device memory of the arena is recycled at begin_frame only
+    c->draws.clear();
+    return TRB_OK;
+}
+
+int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* total_dev) {
+    uint32_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    CU(c->scan_sums.ensure((size_t)nblocks * 4, c->stream));
+    {
+        Launch L(c, "k_scan_partial");
+        k_scan_partial<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>());
+    }
+    {
+        Launch L(c, "k_scan_sums");
+        k_scan_sums<<<1, TPB, 0, c->stream>>>(c->scan_sums.as<uint32_t>(), nblocks, total_dev);
+    }
+    {
+        Launch L(c, "k_scan_final");
+        k_scan_final<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>(), out);
+    }
+    CU(cudaGetLastError());
+    return TRB_OK;
+}
+
+// bin + rasterise one draw whose vertex records are already in `vrec`
+int raster_draw(TrbCtx* c, const GeomArgs& g) {
+    const FrameDev& f = c->frame;
+    if (g.ntris == 0) return TRB_OK;
+    const size_t nslots = (size_t)f.nviews * f.ntiles;
+    if (nslots >= 0xFFFFFFFFull) return fail(c, TRB_E_ARG, "draw: too many tiles x views");
+    CU(c->tribox.ensure((size_t)f.nviews * g.ntris * sizeof(uint2), c->stream));
+    CU(c->counts.ensure(nslots * 4, c->stream));
+    CU(c->offsets.ensure(nslots * 4, c->stream));
+    CU(c->cursor.ensure(nslots * 4, c->stream));
+    CU(c->scan_total.ensure(16, c->stream));
+    CU(cudaMemsetAsync(c->counts.p, 0, nslots * 4, c->stream));
+    CU(cudaMemsetAsync(c->cursor.p, 0, nslots * 4, c->stream));
+    dim3 tgrid(blocks_for(g.ntris), f.nviews);
+    {
+        Launch L(c, "k_setup_count");
+        k_setup_count<<<tgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->counts.as<uint32_t>());
+    }
+    CU(cudaGetLastError());
+    int rc = exclusive_scan(c, c->counts.as<uint32_t>(), (uint32_t)nslots, c->offsets.as<uint32_t>(),
+                            c->scan_total.as<uint32_t>());
+    if (rc) return rc;
+    // the bin array is sized by the count pass (SURVEY 7 "hard parts": config 5 memory)
+    CU(cudaMemcpyAsync(c->host_total, c->scan_total.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint32_t R = *c->host_total;
+    if (R == 0) return TRB_OK;
+    CU(c->bins.ensure((size_t)R * 4, c->stream));
+    {
+        Launch L(c, "k_fill");
+        k_fill<<<tgrid, TPB, 0, c->stream>>>(f, g.ntris, c->tribox.as<uint2>(), c->offsets.as<uint32_t>(),
+                                            c->cursor.as<uint32_t>(), c->bins.as<uint32_t>());
+    }
+    RasterArgs ra;
+    ra.g = g;
+    ra.counts = c->counts.as<uint32_t>();
+    ra.offsets = c->offsets.as<uint32_t>();
+    ra.bins = c->bins.as<uint32_t>();
+    {
+        Launch L(c, "k_raster");
+        k_raster<<<dim3(f.ntiles, f.nviews), TPB, 0, c->stream>>>(f, ra);
+    }
+    CU(cudaGetLastError());
+    return TRB_OK;
+}
+
+int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, int nviews, LitUniforms** dev_out) {
+    *dev_out = nullptr;
+    if (kind == TRB_SHADER_FLAT_BARY || kind == TRB_SHADER_DEPTH) return TRB_OK;
+    if (kind != TRB_SHADER_PHONG && kind != TRB_SHADER_EYE)
+        return fail(c, TRB_E_SHADER, "shader kind has no device implementation (no CPU fallback)");
+    if (!uniforms || ubytes != sizeof(TrbPhongUniforms)) return fail(c, TRB_E_ARG, "draw: uniform block size");
+    std::vector<LitUniforms> host(nviews);
+    const TrbPhongUniforms* u = (const TrbPhongUniforms*)uniforms;
+    auto tex = [&](TrbTex t, TexView& out) -> bool {
+        out = TexView{nullptr, 0, 0, 0};
+        if (t == 0) return true;
+        if (t > c->textures.size() || !c->textures[t - 1].alive) return false;
+        const Tex& x = c->textures[t - 1];
+        out = TexView{x.px, x.w, x.h, x.bpp};
+        return true;
+    };
+    for (int v = 0; v < nviews; ++v) {
+        LitUniforms& L = host[v];
+        L.key = D3{u[v].key_dir_eye[0], u[v].key_dir_eye[1], u[v].key_dir_eye[2]};
+        L.fill = D3{u[v].fill_dir_eye[0], u[v].fill_dir_eye[1], u[v].fill_dir_eye[2]};
+        L.rim = D3{u[v].rim_dir_eye[0], u[v].rim_dir_eye[1], u[v].rim_dir_eye[2]};
+        L.normal_map_strength = u[v].normal_map_strength;
+        if (!tex(u[v].diffuse, L.diffuse) || !tex(u[v].normal, L.normal) || !tex(u[v].specular, L.specular))
+            return fail(c, TRB_E_ARG, "draw: bad texture handle");
+    }
+    cudaError_t e = cudaSuccess;
+    LitUniforms* d = (LitUniforms*)c->arena.alloc(sizeof(LitUniforms) * nviews, e);
+    CU(e);
+    CU(cudaMemcpyAsync(d, host.data(), sizeof(LitUniforms) * nviews, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // `host` dies at return; pageable copies are staged, but be explicit
+    *dev_out = d;
+    return TRB_OK;
+}
+
+void ssao_dirs(SsaoDirs& d) {
+    for (int k = 0; k < 8; ++k) {
+        double angle = 2.0 * M_PI * k / 8;  // main.cpp:333, host libm like the reference
+        d.dx[k] = cos(angle);
+        d.dy[k] = sin(angle);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int trb_create(int device, TrbCtx** out) {
+    if (!out) return TRB_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return TRB_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TRB_E_CUDA;
+    if (prop.major != 10) return TRB_E_CUDA;  // the library only carries sm_100a code
+    if (cudaSetDevice(device) != cudaSuccess) return TRB_E_CUDA;
+    TrbCtx* c = new TrbCtx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_a) != cudaSuccess || cudaEventCreate(&c->ev_b) != cudaSuccess ||
+        cudaMallocHost((void**)&c->host_total, 64) != cudaSuccess) {
+        delete c;
+        return TRB_E_CUDA;
+    }
+    *out = c;
+    return TRB_OK;
+}
+
+int trb_destroy(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& m : c->meshes)
+        if (m.alive) {
+            cudaFree(m.pos4);
+            cudaFree(m.attr8);
+            if (m.idx) cudaFree(m.idx);
+        }
+    for (auto& t : c->textures)
+        if (t.alive) cudaFree(t.px);
+    DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->tribox,
+                      &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->scratch_a,
+                      &c->scratch_b};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& b : c->shadow_maps) b.release();
+    c->arena.release();
+    for (auto& p : c->prof_pending) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaEventDestroy(c->ev_a);
+    cudaEventDestroy(c->ev_b);
+    cudaFreeHost(c->host_total);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return TRB_OK;
+}
+
+const char* trb_last_error(TrbCtx* c) { return c ? c->err.c_str() : "null context"; }
+const char* trb_backend_name(void) { return "cuda-sm100a"; }
+
+int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float* uv2, uint32_t nverts,
+                    const uint32_t* idx, uint64_t nidx, TrbMesh* out) {
+    if (!c || !pos3 || !out || nidx % 3 || nverts == 0) return fail(c, TRB_E_ARG, "upload_mesh: bad argument");
+    if (nidx / 3 >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "upload_mesh: too many triangles");
+    int rc = check_device(c);
+    if (rc) return rc;
+    if (idx)
+        for (uint64_t i = 0; i < nidx; ++i)
+            if (idx[i] >= nverts) return fail(c, TRB_E_ARG, "upload_mesh: index out of range");
+    if (!idx && nidx > nverts) return fail(c, TRB_E_ARG, "upload_mesh: implicit indices exceed nverts");
+    // host-side interleave into the two device layouts: float4 positions for the coalesced vertex
+    // kernel, 32-byte {pos,nrm,uv} records (one DRAM sector) for the shade kernel's gathers
+    std::vector<float> p4((size_t)nverts * 4), a8((size_t)nverts * 8);
+    for (uint32_t v = 0; v < nverts; ++v) {
+        float* p = &p4[(size_t)v * 4];
+        float* a = &a8[(size_t)v * 8];
+        p[0] = a[0] = pos3[3 * (size_t)v];
+        p[1] = a[1] = pos3[3 * (size_t)v + 1];
+        p[2] = a[2] = pos3[3 * (size_t)v + 2];
+        p[3] = 1.0f;
+        a[3] = nrm3 ? nrm3[3 * (size_t)v] : 0.f;       // Model::normal fallback (0,0,1), model.cpp:404
+        a[4] = nrm3 ? nrm3[3 * (size_t)v + 1] : 0.f;
+        a[5] = nrm3 ? nrm3[3 * (size_t)v + 2] : 1.f;
+        a[6] = uv2 ? uv2[2 * (size_t)v] : 0.f;
+        a[7] = uv2 ? uv2[2 * (size_t)v + 1] : 0.f;
+    }
+    Mesh m;
+    m.nverts = nverts;
+    m.nidx = nidx;
+    CU(cudaMalloc((void**)&m.pos4, p4.size() * 4));
+    CU(cudaMalloc((void**)&m.attr8, a8.size() * 4));
+    CU(cudaMemcpyAsync(m.pos4, p4.data(), p4.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(m.attr8, a8.data(), a8.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (idx) {
+        CU(cudaMalloc((void**)&m.idx, nidx * 4));
+        CU(cudaMemcpyAsync(m.idx, idx, nidx * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    m.alive = true;
+    c->meshes.push_back(m);
+    *out = c->meshes.size();
+    return TRB_OK;
+}
+
+int trb_free_mesh(TrbCtx* c, TrbMesh h) {
+    if (!c || h == 0 || h > c->meshes.size() || !c->meshes[h - 1].alive) return fail(c, TRB_E_ARG, "free_mesh");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    Mesh& m = c->meshes[h - 1];
+    cudaFree(m.pos4);
+    cudaFree(m.attr8);
+    if (m.idx) cudaFree(m.idx);
+    m = Mesh();
+    return TRB_OK;
+}
+
+int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, TrbTex* out) {
+    if (!c || !texels || !out || w <= 0 || h <= 0 || (bpp != 1 && bpp != 3 && bpp != 4))
+        return fail(c, TRB_E_ARG, "upload_texture: bad argument");
+    int rc = check_device(c);
+    if (rc) return rc;
+    Tex t;
+    t.w = w;
+    t.h = h;
+    t.bpp = bpp;
+    size_t bytes = (size_t)w * h * bpp;
+    CU(cudaMalloc((void**)&t.px, bytes));
+    CU(cudaMemcpyAsync(t.px, texels, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    t.alive = true;
+    c->textures.push_back(t);
+    *out = c->textures.size();
+    return TRB_OK;
+}
+
+int trb_free_texture(TrbCtx* c, TrbTex h) {
+    if (!c || h == 0 || h > c->textures.size() || !c->textures[h - 1].alive) return fail(c, TRB_E_ARG, "free_texture");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->textures[h - 1].px);
+    c->textures[h - 1] = Tex();
+    return TRB_OK;
+}
+
+int trb_begin_batch(TrbCtx* c, int w, int h, int nviews) {
+    if (!c || w <= 0 || h <= 0 || nviews <= 0 || nviews > 65535 || w > 65535 * TILE || h > 65535 * TILE)
+        return fail(c, TRB_E_ARG, "begin_batch: bad size");
+    int rc = check_device(c);
+    if (rc) return rc;
+    FrameDev& f = c->frame;
+    f.W = w;
+    f.H = h;
+    f.tw = (w + TILE - 1) / TILE;
+    f.th = (h + TILE - 1) / TILE;
+    f.ntiles = f.tw * f.th;
+    f.nviews = nviews;
+    f.npix = (unsigned long long)w * h;
+    const size_t total = (size_t)f.npix * nviews;
+    CU(c->zkey.ensure(total * 8, c->stream));
+    CU(c->vis.ensure(total * 4, c->stream));
+    CU(c->color.ensure(total * 3, c->stream));
+    CU(c->stats.ensure(sizeof(DevStats) * nviews, c->stream));
+    f.zkey = c->zkey.as<unsigned long long>();
+    f.vis = c->vis.as<uint32_t>();
+    f.color = c->color.as<uint8_t>();
+    f.stats = c->stats.as<DevStats>();
+    for (int i = 0; i < 16; ++i) f.viewport[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    c->draws.clear();
+    c->arena.reset();
+    c->next_id = 0;
+    c->tris_submitted = 0;
+    c->have_snapshot = false;
+    c->shade_row0 = 0;
+    c->shade_row1 = -1;
+    {
+        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(total), 148ull * 32);
+        Launch L(c, "k_clear");
+        k_clear<<<grid, TPB, 0, c->stream>>>(f, c->clear[0], c->clear[1], c->clear[2]);
+    }
+    CU(cudaGetLastError());
+    c->in_frame = true;
+    return TRB_OK;
+}
+int trb_begin_frame(TrbCtx* c, int w, int h) { return trb_begin_batch(c, w, h, 1); }
+
+int trb_set_clear_color(TrbCtx* c, uint8_t b, uint8_t g, uint8_t r) {
+    if (!c) return TRB_E_ARG;
+    c->clear[0] = b;
+    c->clear[1] = g;
+    c->clear[2] = r;
+    return TRB_OK;
+}
+int trb_set_viewport(TrbCtx* c, const double* v) {
+    if (!c || !v) return fail(c, TRB_E_ARG, "set_viewport");
+    memcpy(c->frame.viewport, v, sizeof(double) * 16);
+    return TRB_OK;
+}
+
+int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
+                   size_t ubytes, uint64_t first_tri, uint64_t ntris) {
+    if (!c || !c->in_frame) return fail(c, TRB_E_ARG, "draw: no frame");
+    if (!mv || !pr) return fail(c, TRB_E_ARG, "draw: null matrix");
+    if (mesh == 0 || mesh > c->meshes.size() || !c->meshes[mesh - 1].alive) return fail(c, TRB_E_ARG, "draw: bad mesh");
+    const Mesh& m = c->meshes[mesh - 1];
+    if ((first_tri + ntris) * 3 > m.nidx) return fail(c, TRB_E_ARG, "draw: triangle range");
+    if (c->next_id + ntris >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "draw: triangle id space exhausted");
+    int rc = check_device(c);
+    if (rc) return rc;
+    const int nv = c->frame.nviews;
+    c->tris_submitted += ntris;
+    if (ntris == 0) return TRB_OK;
+    LitUniforms* dun = nullptr;
+    rc = resolve_uniforms(c, kind, uniforms, ubytes, nv, &dun);
+    if (rc) return rc;
+    cudaError_t e = cudaSuccess;
+    double* mats = (double*)c->arena.alloc(sizeof(double) * 32 * nv, e);
+    CU(e);
+    std::vector<double> hm((size_t)32 * nv);
+    for (int v = 0; v < nv; ++v) {
+        memcpy(&hm[(size_t)v * 32], mv + 16 * v, 128);
+        memcpy(&hm[(size_t)v * 32 + 16], pr + 16 * v, 128);
+    }
+    CU(cudaMemcpyAsync(mats, hm.data(), hm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    VRec* vrec = (VRec*)c->arena.alloc(sizeof(VRec) * (size_t)m.nverts * nv, e);
+    CU(e);
+    {
+        Launch L(c, "k_vertex_mesh");
+        k_vertex_mesh<<<dim3(blocks_for(m.nverts), nv), TPB, 0, c->stream>>>(c->frame, m.pos4, m.nverts, mats, vrec);
+    }
+    CU(cudaGetLastError());
+    GeomArgs g;
+    g.idx = m.idx;
+    g.first_tri = (uint32_t)first_tri;
+    g.ntris = (uint32_t)ntris;
+    g.nverts = m.nverts;
+    g.id_base = (uint32_t)c->next_id;
+    g.vrec = vrec;
+    rc = raster_draw(c, g);   // synchronises once (bin sizing), which also covers `hm`
+    if (rc) return rc;
+    DrawDev d{};
+    d.id_base = g.id_base;
+    d.ntris = g.ntris;
+    d.first_tri = g.first_tri;
+    d.nverts = g.nverts;
+    d.idx = m.idx;
+    d.attr8 = m.attr8;
+    d.vrec = vrec;
+    d.mats = mats;
+    d.uniforms = dun;
+    d.varyings = nullptr;
+    d.kind = kind;
+    c->draws.push_back(d);
+    c->next_id += ntris;
+    return TRB_OK;
+}
+
+int trb_draw(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
+             size_t ubytes, uint64_t first_tri, uint64_t ntris) {
+    if (c && c->in_frame && c->frame.nviews != 1) return fail(c, TRB_E_ARG, "draw: batch frame needs draw_batch");
+    return trb_draw_batch(c, mesh, mv, pr, kind, uniforms, ubytes, first_tri, ntris);
+}
+
+int trb_submit_clip_triangles(TrbCtx* c, const double* clip12, const double* varyings, uint64_t n, const double* mv,
+                              int kind, const void* uniforms, size_t ubytes) {
+    if (!c || !c->in_frame || c->frame.nviews != 1) return fail(c, TRB_E_ARG, "submit: needs a single-view frame");
+    if (!clip12 && n) return fail(c, TRB_E_ARG, "submit: null clip");
+    if (n * 3 >= 0xFFFFFFF0ull || c->next_id + n >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "submit: too many triangles");
+    const bool lit = kind == TRB_SHADER_PHONG || kind == TRB_SHADER_EYE;
+    if (lit && !varyings) return fail(c, TRB_E_ARG, "submit: varyings required");
+    int rc = check_device(c);
+    if (rc) return rc;
+    c->tris_submitted += n;
+    if (n == 0) return TRB_OK;
+    LitUniforms* dun = nullptr;
+    rc = resolve_uniforms(c, kind, uniforms, ubytes, 1, &dun);
+    if (rc) return rc;
+    cudaError_t e = cudaSuccess;
+    const uint32_t nverts = (uint32_t)(n * 3);
+    double* mats = (double*)c->arena.alloc(sizeof(double) * 32, e);
+    CU(e);
+    double hm[32];
+    for (int i = 0; i < 32; ++i) hm[i] = (i % 16) % 5 == 0 ? 1.0 : 0.0;
+    if (mv) memcpy(hm, mv, 128);
+    CU(cudaMemcpyAsync(mats, hm, sizeof(hm), cudaMemcpyHostToDevice, c->stream));
+    VRec* vrec = (VRec*)c->arena.alloc(sizeof(VRec) * (size_t)nverts, e);
+    CU(e);
+    double* dvary = nullptr;
+    if (lit) {
+        dvary = (double*)c->arena.alloc(sizeof(double) * 24 * n, e);
+        CU(e);
+        CU(cudaMemcpyAsync(dvary, varyings, sizeof(double) * 24 * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(c->scratch_a.ensure(sizeof(double) * 12 * n, c->stream));
+    CU(cudaMemcpyAsync(c->scratch_a.p, clip12, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, c->stream));
+    {
+        Launch L(c, "k_vertex_clip");
+        k_vertex_clip<<<blocks_for(nverts), TPB, 0, c->stream>>>(c->frame, c->scratch_a.as<double>(), nverts, vrec);
+    }
+    CU(cudaGetLastError());
+    GeomArgs g;
+    g.idx = nullptr;
+    g.first_tri = 0;
+    g.ntris = (uint32_t)n;
+    g.nverts = nverts;
+    g.id_base = (uint32_t)c->next_id;
+    g.vrec = vrec;
+    rc = raster_draw(c, g);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));  // caller may reuse clip12 / varyings / hm
+    DrawDev d{};
+    d.id_base = g.id_base;
+    d.ntris = g.ntris;
+    d.first_tri = 0;
+    d.nverts = nverts;
+    d.idx = nullptr;
+    d.attr8 = nullptr;
+    d.vrec = vrec;
+    d.mats = mats;
+    d.uniforms = dun;
+    d.varyings = dvary;
+    d.kind = kind;
+    c->draws.push_back(d);
+    c->next_id += n;
+    return TRB_OK;
+}
+
+int trb_depth_snapshot(TrbCtx* c) {
+    if (!c || !c->in_frame) return fail(c, TRB_E_ARG, "depth_snapshot: no frame");
+    int rc = check_device(c);
+    if (rc) return rc;
+    size_t bytes = (size_t)c->frame.npix * c->frame.nviews * 8;
+    CU(c->zsnap.ensure(bytes, c->stream));
+    // unflushed pixels hold canonical keys; exact -0.0 bits only appear after their shade pass,
+    // so resolve first to snapshot what the reference's vector copy (main.cpp:700) would hold
+    rc = do_flush(c);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->zsnap.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->have_snapshot = true;
+    return TRB_OK;
+}
+int trb_depth_restore(TrbCtx* c) {
+    if (!c || !c->in_frame || !c->have_snapshot) return fail(c, TRB_E_ARG, "depth_restore: no snapshot");
+    int rc = do_flush(c);  // colours of everything drawn so far persist (main.cpp:730)
+    if (rc) return rc;
+    size_t bytes = (size_t)c->frame.npix * c->frame.nviews * 8;
+    CU(cudaMemcpyAsync(c->zkey.p, c->zsnap.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return TRB_OK;
+}
+int trb_keep_depth_as_shadow_map(TrbCtx* c, int32_t* out) {
+    if (!c || !c->in_frame || !out) return fail(c, TRB_E_ARG, "keep_depth_as_shadow_map");
+    int rc = do_flush(c);
+    if (rc) return rc;
+    DevBuf b;
+    size_t bytes = (size_t)c->frame.npix * 8;
+    CU(b.ensure(bytes, c->stream));
+    CU(cudaMemcpyAsync(b.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->shadow_maps.push_back(b);
+    *out = (int32_t)c->shadow_maps.size() - 1;
+    return TRB_OK;
+}
+
+int trb_flush(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    return do_flush(c);
+}
+int trb_end_frame(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    return do_flush(c);
+}
+
+int trb_read_color(TrbCtx* c, int view, uint8_t* out) {
+    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "read_color");
+    int rc = do_flush(c);
+    if (rc) return rc;
+    size_t bytes = (size_t)c->frame.npix * 3;
+    CU(cudaMemcpyAsync(out, c->color.as<uint8_t>() + bytes * view, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+int trb_read_depth(TrbCtx* c, int view, double* out) {
+    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "read_depth");
+    int rc = do_flush(c);
+    if (rc) return rc;
+    const unsigned long long n = c->frame.npix;
+    CU(c->scratch_b.ensure(n * 8, c->stream));
+    {
+        Launch L(c, "k_unmap_depth");
+        k_unmap_depth<<<blocks_for(n), TPB, 0, c->stream>>>(c->frame.zkey + n * view, n, c->scratch_b.as<double>());
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->scratch_b.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+int trb_read_visibility(TrbCtx* c, int view, uint32_t* out) {
+    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "read_visibility");
+    int rc = check_device(c);
+    if (rc) return rc;
+    size_t n = (size_t)c->frame.npix;
+    CU(cudaMemcpyAsync(out, c->frame.vis + n * view, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+
+int trb_get_stats(TrbCtx* c, int view, TrbStats* out) {
+    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "get_stats");
+    int rc = check_device(c);
+    if (rc) return rc;
+    const unsigned long long n = c->frame.npix;
+    CU(c->scratch_b.ensure(64, c->stream));
+    CU(cudaMemsetAsync(c->scratch_b.p, 0, 8, c->stream));
+    {
+        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(n), 148ull * 16);
+        Launch L(c, "k_count_finite");
+        k_count_finite<<<grid, TPB, 0, c->stream>>>(c->frame.zkey + n * view, n, c->scratch_b.as<unsigned long long>());
+    }
+    CU(cudaGetLastError());
+    DevStats s;
+    unsigned long long finite = 0;
+    CU(cudaMemcpyAsync(&s, c->frame.stats + view, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&finite, c->scratch_b.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof(*out));
+    out->triangles_submitted = c->tris_submitted;
+    out->triangles_binned = s.tri_binned;
+    out->tile_entries = s.tile_entries;
+    out->fragments_covered = s.frag_covered;
+    out->pixels_shaded = finite;
+    out->bbox_min_x = s.bx0;
+    out->bbox_min_y = s.by0;
+    out->bbox_max_x = s.bx1;
+    out->bbox_max_y = s.by1;
+    out->z_min = s.frag_covered ? depth_from_key(s.zmin_key) : INFINITY;
+    out->z_max_covered = s.frag_covered ? depth_from_key(s.zmax_key) : -INFINITY;
+    out->z_max_ref = NAN;
+    return TRB_OK;
+}
+
+int trb_synchronize(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+
+// ---- post passes -----------------------------------------------------------------------------
+int trb_ssao(TrbCtx* c, int view, uint8_t* out) {
+    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "ssao");
+    int rc = do_flush(c);
+    if (rc) return rc;
+    const FrameDev& f = c->frame;
+    CU(c->scratch_a.ensure(f.npix, c->stream));
+    SsaoDirs d;
+    ssao_dirs(d);
+    {
+        Launch L(c, "k_ssao");
+        k_ssao<<<dim3(f.tw, f.th), TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.W, f.H, d, c->scratch_a.as<uint8_t>());
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->scratch_a.p, f.npix, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+int trb_composite_ao(TrbCtx* c, int view, uint8_t* out) {
+    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "composite_ao");
+    int rc = do_flush(c);
+    if (rc) return rc;
+    const FrameDev& f = c->frame;
+    CU(c->scratch_a.ensure(f.npix * 3, c->stream));
+    SsaoDirs d;
+    ssao_dirs(d);
+    {
+        Launch L(c, "k_composite_ao");
+        k_composite_ao<<<dim3(f.tw, f.th), TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.color + f.npix * 3 * view,
+                                                                 f.W, f.H, d, c->scratch_a.as<uint8_t>());
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->scratch_a.p, f.npix * 3, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+int trb_depth_image(TrbCtx* c, int view, uint8_t* out) {
+    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "depth_image");
+    int rc = do_flush(c);
+    if (rc) return rc;
+    const FrameDev& f = c->frame;
+    CU(c->scratch_a.ensure(f.npix, c->stream));
+    CU(c->scratch_b.ensure(64, c->stream));
+    unsigned long long init[2] = {~0ull, 0ull};
+    CU(cudaMemcpyAsync(c->scratch_b.p, init, 16, cudaMemcpyHostToDevice, c->stream));
+    {
+        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(f.npix), 148ull * 16);
+        Launch L(c, "k_depth_range");
+        k_depth_range<<<grid, TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.npix, c->scratch_b.as<unsigned long long>());
+    }
+    {
+        Launch L(c, "k_depth_image");
+        k_depth_image<<<blocks_for(f.npix), TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.npix,
+                                                                  c->scratch_b.as<unsigned long long>(),
+                                                                  c->scratch_a.as<uint8_t>());
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->scratch_a.p, f.npix, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+
+// ---- timing -------------------------------------------------------------------------------------
+int trb_timer_start(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev_a, c->stream));
+    return TRB_OK;
+}
+int trb_timer_stop_ms(TrbCtx* c, float* ms) {
+    if (!c || !ms) return TRB_E_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev_b, c->stream));
+    CU(cudaEventSynchronize(c->ev_b));
+    CU(cudaEventElapsedTime(ms, c->ev_a, c->ev_b));
+    return TRB_OK;
+}
+int trb_profile_enable(TrbCtx* c, int on) {
+    if (!c) return TRB_E_ARG;
+    cudaSetDevice(c->device);
+    prof_collect(c);
+    c->profiling = on != 0;
+    return TRB_OK;
+}
+int trb_profile_read(TrbCtx* c, TrbKernelTime* out, int capacity, int* n_out, int reset) {
+    if (!c || !n_out) return TRB_E_ARG;
+    cudaSetDevice(c->device);
+    prof_collect(c);
+    int n = 0;
+    for (auto& a : c->prof_acc) {
+        if (n >= capacity || !out) break;
+        memset(&out[n], 0, sizeof(out[n]));
+        strncpy(out[n].name, a.name.c_str(), sizeof(out[n].name) - 1);
+        out[n].launches = a.launches;
+        out[n].ms = a.ms;
+        ++n;
+    }
+    *n_out = n;
+    if (reset) c->prof_acc.clear();
+    return TRB_OK;
+}
+uint64_t trb_launch_count(TrbCtx* c) { return c ? c->launches : 0; }
+
+// ---- multi-GPU composite ----------------------------------------------------------------------
+int trb_device_planes(TrbCtx* c, uint64_t* key_ptr, uint64_t* vis_ptr, uint64_t* npix) {
+    if (!c || !c->in_frame || !key_ptr || !vis_ptr || !npix) return fail(c, TRB_E_COMM, "device_planes: no frame");
+    *key_ptr = (uint64_t)(uintptr_t)c->frame.zkey;
+    *vis_ptr = (uint64_t)(uintptr_t)c->frame.vis;
+    *npix = c->frame.npix;
+    return TRB_OK;
+}
+int trb_set_triangle_id_base(TrbCtx* c, uint64_t base) {
+    if (!c || base >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "set_triangle_id_base");
+    c->next_id = base;
+    return TRB_OK;
+}
+// The host all-reduces (min) the depth-key plane in place as int64; keys are made signed-sortable
+// for the collective and restored by composite_mask.
+int trb_composite_save_local_depth(TrbCtx* c) {
+    if (!c || !c->in_frame || c->frame.nviews != 1) return fail(c, TRB_E_COMM, "composite: needs a single-view frame");
+    int rc = check_device(c);
+    if (rc) return rc;
+    const unsigned long long n = c->frame.npix;
+    CU(c->zlocal.ensure(n * 8, c->stream));
+    CU(cudaMemcpyAsync(c->zlocal.p, c->zkey.p, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    {
+        Launch L(c, "k_key_to_sortable_i64");
+        k_key_to_sortable_i64<<<blocks_for(n), TPB, 0, c->stream>>>(c->frame.zkey, n);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+int trb_composite_mask(TrbCtx* c) {
+    if (!c || !c->in_frame || c->frame.nviews != 1 || c->zlocal.cap < c->frame.npix * 8)
+        return fail(c, TRB_E_COMM, "composite_mask: call composite_save_local_depth first");
+    int rc = check_device(c);
+    if (rc) return rc;
+    const unsigned long long n = c->frame.npix;
+    {
+        Launch L(c, "k_key_to_sortable_i64");
+        k_key_to_sortable_i64<<<blocks_for(n), TPB, 0, c->stream>>>(c->frame.zkey, n);
+    }
+    {
+        Launch L(c, "k_composite_mask");
+        k_composite_mask<<<blocks_for(n), TPB, 0, c->stream>>>(c->zlocal.as<unsigned long long>(), c->frame.zkey,
+                                                               c->frame.vis, n);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+int trb_set_shade_rows(TrbCtx* c, int y0, int y1) {
+    if (!c || !c->in_frame || y0 < 0 || y1 < y0 || y1 > c->frame.H) return fail(c, TRB_E_ARG, "set_shade_rows");
+    c->shade_row0 = y0;
+    c->shade_row1 = y1;
+    return TRB_OK;
+}
+
+// ---- host helpers (reference operation order, no device work) -------------------------------------
+void trb_light_dir_eye(const double* mv, const double* dir, double* out) {
+    // main.cpp:59-68: mat<3,3> * vec3 (dot<3> from +0.0) then normalized()
+    D3 d{dir[0], dir[1], dir[2]};
+    D3 r{dot3(D3{mv[0], mv[1], mv[2]}, d), dot3(D3{mv[4], mv[5], mv[6]}, d), dot3(D3{mv[8], mv[9], mv[10]}, d)};
+    r = normalize3(r);
+    out[0] = r.x;
+    out[1] = r.y;
+    out[2] = r.z;
+}
+void trb_lookat(const double* eye, const double* center, const double* up, double* out) {
+    // our_gl.cpp:25-41
+    D3 e{eye[0], eye[1], eye[2]}, ce{center[0], center[1], center[2]}, u{up[0], up[1], up[2]};
+    D3 z = normalize3(sub3(e, ce));
+    D3 x = normalize3(D3{u.y * z.z - u.z * z.y, u.z * z.x - u.x * z.z, u.x * z.y - u.y * z.x});
+    D3 y{z.y * x.z - z.z * x.y, z.z * x.x - z.x * x.z, z.x * x.y - z.y * x.x};
+    for (int i = 0; i < 16; ++i) out[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = -dot3(x, e);
+    out[4] = y.x; out[5] = y.y; out[6] = y.z; out[7] = -dot3(y, e);
+    out[8] = z.x; out[9] = z.y; out[10] = z.z; out[11] = -dot3(z, e);
+}
+void trb_perspective(double fov_deg, double aspect, double zn, double zf, double* out) {
+    // our_gl.cpp:44-56
+    double fov_rad = fov_deg * M_PI / 180.0;
+    double t = tan(fov_rad / 2.0);
+    for (int i = 0; i < 16; ++i) out[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    out[0] = 1.0 / (aspect * t);
+    out[5] = 1.0 / t;
+    out[10] = (zf + zn) / (zn - zf);
+    out[11] = (2.0 * zf * zn) / (zn - zf);
+    out[14] = -1.0;
+    out[15] = 0.0;
+}
+void trb_viewport(int x, int y, int w, int h, double* out) {
+    // our_gl.cpp:59-69
+    for (int i = 0; i < 16; ++i) out[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    out[0] = w / 2.0;
+    out[5] = h / 2.0;
+    out[3] = x + w / 2.0;
+    out[7] = y + h / 2.0;
+    out[10] = 1.0;
+    out[11] = 0.0;
+}
+void trb_mat4_mul(const double* a, const double* b, double* out) {
+    // geometry.h:195-205
+    double r[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+            r[i * 4 + j] = s;
+        }
+    memcpy(out, r, sizeof(r));
+}
+
+}  // extern "C"

@@ -193,7 +193,7 @@ def _value_noise(size, cells, seed, channels):
 
 def texture_diffuse(size=1024, seed=11):
     n = 0.6 * _value_noise(size, 16, seed, 3) + 0.4 * _value_noise(size, 64, seed + 100, 3)
-    return np.clip(40 + 200 * n, 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(40 + 200 * n, 0, 255).astype(np.uint8))
 
 
 def texture_normal(size=1024, seed=12, strength=6.0):
