@@ -1,0 +1,462 @@
+#!/usr/bin/env python3
+"""bench.py - the rasterization hot path on N B200s (one process per GPU), or the reference's
+CPU implementation of the same path (--impl reference).
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+  c3 (default)  F frames of the 1920x1080 camera orbit of the three-model scene (config 3,
+                SURVEY 8d) per rank per step: vertex -> bin -> raster -> shade for every frame.
+                Frames are independent, ranks share nothing: weak scaling, no collective.
+  c4            the 20 971 520-triangle sphere at 3840x2160 (config 4), one frame per step.
+  c5            tiny-triangle stress, --c5-tris sub-pixel triangles at 8192x8192 (config 5).
+  c1            the 800x800 head (config 1), one frame per step (launch bound; reported only).
+
+One JSON line on stdout (rank 0); see DESIGN.md "Measurement" for every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "triangles/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--frames-per-step", type=int, default=32, help="c3: frames per rank per step")
+    ap.add_argument("--c4-level", type=int, default=10)
+    ap.add_argument("--c5-tris", type=int, default=100_000_000)
+    ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (0 = min(nproc, 8))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------
+class Workload:
+    """Synthetic inputs of one config plus how to draw one step of it through a Renderer."""
+
+    def __init__(self, args, api):
+        from tinyrenderder_b200 import scenes
+        self.scenes = scenes
+        self.name = args.workload
+        self.args = args
+        w = args.workload
+        if w == "c3":
+            self.scene = scenes.orbit_scene()
+            self.frames = args.frames_per_step
+            self.label = "c3_orbit_1920x1080_%dtri_x%dframes" % (self.scene.ntris, self.frames)
+        elif w == "c1":
+            self.scene = scenes.head_scene()
+            self.frames = 1
+            self.label = "c1_head_800x800_%dtri" % self.scene.ntris
+        elif w == "c4":
+            self.scene = scenes.sphere_scene(args.c4_level)
+            self.frames = 1
+            self.label = "c4_icosphere_l%d_3840x2160_%dtri" % (args.c4_level, self.scene.ntris)
+        else:
+            n = args.c5_tris
+            _, pos = scenes.triangle_soup(n, 8192, 8192, 0.4, 5, True)
+            mesh = scenes.MeshData(pos, np.zeros((1, 3), np.float32).repeat(pos.shape[0], 0),
+                                   np.zeros((pos.shape[0], 2), np.float32), np.arange(pos.shape[0], dtype=np.uint32),
+                                   "soup")
+            self.scene = scenes.Scene("c5_soup", 8192, 8192, [scenes.DrawItem(mesh, np.eye(4), 0)], 60, 0.1, 10)
+            self.frames = 1
+            self.label = "c5_soup_8192x8192_%dtri_r0.4" % n
+        sc = self.scene
+        self.width, self.height = sc.width, sc.height
+        if w == "c5":
+            self.perspective = np.eye(4)
+        else:
+            self.perspective = api.perspective(sc.fov, sc.width / sc.height, sc.znear, sc.zfar)
+        self.tris_per_frame = sc.ntris
+
+    def views(self, api, step, rank, world):
+        sc = self.scenes
+        if self.name == "c3":
+            first = ((step * world) + rank) * self.frames
+            return sc.orbit_views(api, [(first + j) % 1024 for j in range(self.frames)])
+        if self.name == "c1":
+            return sc.head_view(api)[None]
+        if self.name == "c4":
+            return sc.sphere_view(api)[None]
+        return np.eye(4)[None]
+
+
+def algorithmic_bytes(V, T, P, R, T_vis, C, frames=1):
+    """SURVEY 8(d) per-frame formula, split by kernel (DESIGN.md 'Algorithmic bytes')."""
+    b = {
+        "k_vertex_mesh": V * (12 + 32),
+        "k_setup_count": T * (12 + 96),
+        "k_fill": 4 * R,
+        "k_raster": R * (4 + 96) + 12 * P,
+        "k_shade": 12 * P + 96 * T_vis + 9 * C + 3 * P,
+        "k_clear": 8 * P,
+    }
+    return {k: v * frames for k, v in b.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU rasterizer on the host cores
+# ---------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _ref_worker_init(libpath, workload_args):
+    import tinyrenderder_b200 as trb
+    api = trb.Api(libpath, "orc")
+    args = argparse.Namespace(**workload_args)
+    wl = Workload(args, api)
+    r = trb.Renderer(api)
+    up = wl.scenes.UploadedScene(r, wl.scene)
+    _W.update(api=api, wl=wl, r=r, up=up)
+
+
+def _ref_worker_frame(job):
+    step, slot, world, tri_first, tri_count = job
+    wl, api, up, r = _W["wl"], _W["api"], _W["up"], _W["r"]
+    if wl.name == "c3":
+        views = wl.scenes.orbit_views(api, [(step * world + slot) % 1024])
+    else:
+        views = wl.views(api, step, 0, 1)
+    t0 = time.perf_counter()
+    if tri_count is None:
+        up.render(views, wl.perspective)
+        ntri = wl.tris_per_frame
+    else:  # bounded sample of a huge single frame: a contiguous triangle range (frame clear not timed)
+        it = wl.scene.items[0]
+        r.begin_frame(wl.width, wl.height)
+        mv = api.mat4_mul(views[0], it.model_matrix)
+        t0 = time.perf_counter()
+        r.draw(up.mesh_h[id(it.mesh)], mv, wl.perspective, kind=it.kind, first_tri=tri_first, ntris=tri_count)
+        r.end_frame()
+        ntri = tri_count
+    dt = time.perf_counter() - t0
+    return ntri, r.stats()["fragments_covered"] if api.backend_name() == "oracle-port" else 0, dt
+
+
+def oracle_library():
+    ref = os.path.join(ROOT, "oracle", "_ref", "libtrb_ref.so")
+    if os.path.exists(ref):
+        return ref, "reference"
+    return os.path.join(ROOT, "oracle", "libtrb_port.so"), "port"
+
+
+def run_reference(args, steps, warmup):
+    """The reference's CPU path (oracle/_ref = its own our_gl.cpp; else the port) on the host cores.
+    It keeps its state in unsynchronised globals (our_gl.cpp:12-22), so parallelism is one process
+    per frame (c3) / per triangle range (c4, c5), as SURVEY 8(d) prescribes."""
+    import multiprocessing as mp
+    lib, kind = oracle_library()
+    procs = args.ref_procs or min(os.cpu_count() or 1, 8)
+    wargs = dict(vars(args))
+    if args.workload == "c5":
+        wargs["c5_tris"] = min(args.c5_tris, 4_000_000 * procs)  # bounded sample: a prefix of the soup
+    ctx = mp.get_context("fork")
+    pool = ctx.Pool(procs, initializer=_ref_worker_init, initargs=(lib, wargs))
+    try:
+        tris_per_frame = None
+        times = []
+        tris_total = 0
+        sample = ""
+        for s in range(warmup + steps):
+            if args.workload == "c3" or args.workload == "c1":
+                jobs = [(s, p, procs, 0, None) for p in range(procs)]
+                sample = "%d frame(s) per step, one per process" % procs
+            else:
+                # one frame is tens of seconds on a CPU: each process rasterises a 1/64 range
+                import tinyrenderder_b200  # noqa: F401
+                total = wargs["c5_tris"] if args.workload == "c5" else 20 * 4 ** args.c4_level
+                chunk = max(1, total // 64 // procs) if args.workload == "c4" else total // procs
+                jobs = [(s, p, procs, ((s * procs + p) * chunk) % max(1, total - chunk), chunk) for p in range(procs)]
+                sample = "%d triangle ranges of %d per step (1/%d of a frame each)" % (procs, chunk, max(1, total // chunk))
+            res = pool.map(_ref_worker_frame, jobs)
+            dt = max(x[2] for x in res)  # the processes run side by side: the step ends with the slowest
+            if s >= warmup:
+                times.append(dt)
+                tris_total += sum(r[0] for r in res)
+            tris_per_frame = res[0][0]
+    finally:
+        pool.close()
+        pool.join()
+    total_t = sum(times)
+    value = tris_total / total_t
+    return {"value": value, "kind": kind, "cores": procs, "sample": sample, "ms_per_step": 1e3 * total_t / max(1, len(times)),
+            "tris_per_step": tris_total / max(1, len(times)), "tris_per_unit": tris_per_frame}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import __graft_entry__ as g
+        g.build_scenegen()
+        steps, warmup = args.steps, args.warmup
+        res = run_reference(args, steps, warmup)
+        import tinyrenderder_b200 as trb
+        wl_label = Workload(args, trb.Api(oracle_library()[0], "orc")).label if args.workload != "c5" else "c5_soup"
+        line = {
+            "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "triangles/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_label, "cpu_threads": res["cores"], "sample": res["sample"]},
+            "cpu_baseline": {"value": res["value"], "unit": "triangles/s", "cores": res["cores"], "kind": res["kind"],
+                             "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "triangles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import tinyrenderder_b200 as trb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    api = trb.load_cuda()
+    r = trb.Renderer(api, local_rank)
+    wl = Workload(args, api)
+    up = wl.scenes.UploadedScene(r, wl.scene)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(s):
+        up.render(wl.views(api, s, rank, world), wl.perspective)
+
+    # ---- diagnostics pass (untimed): counters for the algorithmic-bytes formula ---------------------
+    step(0)
+    st = r.stats(0)
+    nviews = wl.frames
+    R = sum(r.stats(v)["tile_entries"] for v in range(nviews))
+    C = sum(r.stats(v)["pixels_shaded"] for v in range(nviews))
+    frag = sum(r.stats(v)["fragments_covered"] for v in range(nviews))
+    # distinct winning triangles: re-draw view 0 without the flush and look at the id plane
+    views0 = wl.views(api, 0, rank, world)[:1]
+    r.begin_frame(wl.width, wl.height)
+    tvis = 0
+    for it in wl.scene.items:
+        mv = api.mat4_mul(views0[0], it.model_matrix)
+        r.draw(up.mesh_h[id(it.mesh)], mv, wl.perspective, kind=0, ntris=it.mesh.ntris)
+    vis = r.read_visibility(0)
+    tvis = int(np.unique(vis[(vis != 0xFFFFFFFF) & (vis != 0)]).size) * nviews
+    r.end_frame()
+    V = sum(it.mesh.nverts for it in wl.scene.items)
+    T = wl.tris_per_frame
+    P = wl.width * wl.height
+    balg = algorithmic_bytes(V * nviews, T * nviews, P * nviews, R, tvis, C)
+
+    # ---- warm-up + timed region -----------------------------------------------------------------------
+    for s in range(args.warmup):
+        step(s)
+    r.profile_enable(True)
+    r.profile_read(reset=True)
+    launches0 = r.launch_count()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    r.timer_start()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        step(args.warmup + s)
+    ms = r.timer_stop_ms()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    prof = r.profile_read(reset=True)
+    r.profile_enable(False)
+    launches = r.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    tris_step_all = T * nviews * world
+    value = tris_step_all * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end: host buffers in, host buffers out, every step --------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+        color_host = [pin((wl.height, wl.width, 3), torch.uint8) for _ in range(nviews)]
+        depth_host = [pin((wl.height, wl.width), torch.float64) for _ in range(nviews)]
+        e_steps = max(1, min(args.steps, 3 if wl.name in ("c4", "c5") else args.steps))
+
+        def e2e_step(s):
+            up2 = wl.scenes.UploadedScene(r, wl.scene)                 # H2D: meshes + textures
+            up2.render(wl.views(api, s, rank, world), wl.perspective)  # H2D: matrices, uniforms
+            for v in range(nviews):                                    # D2H: framebuffer + z-buffer
+                r.read_color(v, color_host[v])
+                r.read_depth(v, depth_host[v])
+            up2.free()
+            return up2.h2d_bytes
+
+        h2d = e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(e_steps):
+            e2e_step(1 + s)
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": tris_step_all * e_steps / float(t.item()), "unit": "triangles/s",
+               "h2d_bytes_per_step": int(h2d + nviews * 3 * 256), "d2h_bytes_per_step": int(nviews * P * (3 + 8)),
+               "steps": e_steps, "ms_per_step": 1e3 * float(t.item()) / e_steps,
+               "note": "per step: upload meshes+textures, render, read back BGR framebuffer + f64 z-buffer of every frame"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    kern = {k: {"launches": int(n), "ms": float(m)} for k, (n, m) in prof.items()}
+    total_k_ms = sum(v["ms"] for v in kern.values()) or 1.0
+    dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+    roof = None
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tr_path):
+        try:
+            traffic = json.load(open(tr_path)).get(wl.name, {}).get(dom)
+        except Exception:
+            traffic = None
+    if dom:
+        per_launch_ms = kern[dom]["ms"] / kern[dom]["launches"]
+        # launches of the dominant kernel per step (one per draw call) share the step's algorithmic bytes
+        bytes_per_launch = balg.get(dom, 0) * args.steps / kern[dom]["launches"]
+        achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
+                "share_of_kernel_time": kern[dom]["ms"] / total_k_ms}
+    step_bytes = sum(balg.values())
+    step_gbs = step_bytes * args.steps / (ms_max * 1e-3) / 1e9
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+                   "--steps", "2", "--warmup", "0", "--c4-level", str(args.c4_level), "--c5-tris", str(args.c5_tris)]
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            ref_line = json.loads(out.stdout.strip().splitlines()[-1])
+            cpu = ref_line["cpu_baseline"]
+        except Exception as e:  # the baseline is a reported figure; never let it sink the GPU line
+            cpu = {"value": None, "unit": "triangles/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "triangles/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.label, "frames_per_step_per_gpu": nviews, "width": wl.width, "height": wl.height,
+                   "triangles_per_frame": T, "l2": "inputs larger than L2 (depth+id+colour planes of one step = %d MB)"
+                   % (nviews * P * 15 // 2 ** 20), "parallelism": "frames sharded, no collective" if world > 1 else "1 GPU"},
+        "fragments_per_s": frag * world * args.steps / (ms_max * 1e-3),
+        "pixels_shaded_per_s": C * world * args.steps / (ms_max * 1e-3),
+        "frame_ms": ms_max / args.steps / nviews,
+        "frames_per_s": nviews * world * args.steps / (ms_max * 1e-3),
+        "roofline": roof,
+        "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / peak,
+                          "counters": {"V": V * nviews, "T": T * nviews, "P": P * nviews, "R": R, "T_vis": tvis, "C": C}},
+        "kernels": kern,
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "clocks": clk,
+        "wall_ms_per_step": 1e3 * t_wall / args.steps,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
