@@ -24,8 +24,8 @@ constexpr int TPB = 256;               // threads per block everywhere (== pixel
 constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
 constexpr uint32_t VIS_SHADED = 0u;    // pixel already shaded by an earlier flush; ties keep it
 constexpr int QCAP = 1024;             // candidate queue entries per CTA
-constexpr int BIG_NS = 64;             // triangles covering >= this many samples of a tile take the
-                                       // pixel-owner path (no atomics)
+constexpr int BIG_NS_DEFAULT = 16;     // triangles covering >= this many samples of a tile take the
+                                       // pixel-owner path (no atomics); TRB_BIG_NS overrides
 
 struct DevStats {
     unsigned long long tri_binned, tile_entries, frag_covered, pixels_shaded;
@@ -135,6 +135,37 @@ struct GeomArgs {
 
 constexpr uint32_t BOX_NONE = 0xFFFFFFFFu;
 
+// Per-triangle raster record written once by k_setup_count and gathered by k_raster through the
+// bins: everything eval_sample needs plus the clamped pixel bbox.  96 bytes = 3 DRAM sectors.
+struct __align__(32) TriRec {
+    double ax, ay, s00, s01, s10, s11, uz, z0, z1, z2;
+    unsigned short x0, y0, x1, y1;
+    uint32_t pad0, pad1;
+};
+static_assert(sizeof(TriRec) == 96, "TriRec must be 96 bytes");
+
+__device__ __forceinline__ void store_trirec(TriRec* p, const TriSetup& t) {
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(t.ax, t.ay);
+    q[1] = make_double2(t.s00, t.s01);
+    q[2] = make_double2(t.s10, t.s11);
+    q[3] = make_double2(t.uz, t.z0);
+    q[4] = make_double2(t.z1, t.z2);
+    uint4 b;
+    b.x = (uint32_t)t.x0 | ((uint32_t)t.y0 << 16);
+    b.y = (uint32_t)t.x1 | ((uint32_t)t.y1 << 16);
+    b.z = 0u; b.w = 0u;
+    reinterpret_cast<uint4*>(p)[5] = b;
+}
+__device__ __forceinline__ void load_trirec(const TriRec* p, TriSetup& t) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
+    uint4 bb = __ldg(reinterpret_cast<const uint4*>(p) + 5);
+    t.ax = a.x; t.ay = a.y; t.s00 = b.x; t.s01 = b.y; t.s10 = c.x; t.s11 = c.y;
+    t.uz = d.x; t.z0 = d.y; t.z1 = e.x; t.z2 = e.y;
+    t.x0 = bb.x & 0xffff; t.y0 = bb.x >> 16; t.x1 = bb.y & 0xffff; t.y1 = bb.y >> 16;
+}
+
 __device__ __forceinline__ int block_reduce_min(int v, int* sh) {
     for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
@@ -170,7 +201,7 @@ __device__ __forceinline__ unsigned long long block_reduce_min64(unsigned long l
 }
 
 __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uint2* __restrict__ tribox,
-                                                     uint32_t* __restrict__ tile_count) {
+                                                     TriRec* __restrict__ trirec, uint32_t* __restrict__ tile_count) {
     __shared__ int sh_i[TPB / 32];
     __shared__ unsigned long long sh_u[TPB / 32];
     const int view = blockIdx.y;
@@ -200,6 +231,7 @@ __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uin
         ty0 = ts.y0 >> TILE_SHIFT; ty1 = ts.y1 >> TILE_SHIFT;
         box = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
         ntile = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+        store_trirec(trirec + (size_t)view * g.ntris + t, ts);
     }
     if (t < g.ntris) tribox[(size_t)view * g.ntris + t] = box;
     unsigned long long ne = block_reduce_sum(ntile, sh_u);
@@ -336,22 +368,30 @@ __global__ void __launch_bounds__(TPB) k_fill(FrameDev f, uint32_t ntris, const 
 
 // ---------------------------------------------------------------------------------------------
 // fine raster: one CTA owns one 16x16 tile
+//
+// The tile's depth keys and winner ids live in shared memory / registers for the whole bin.
+// Triangles of the bin are taken in chunks of CHUNK.  Per chunk every thread gathers one
+// triangle record, then the chunk is rasterised by one or both of
+//   pixel-owner path  every thread owns one pixel and walks the chunk's (big) triangles from
+//                     shared memory: no atomics, no barriers between triangles;
+//   small path        one thread per (small) triangle walks its <= big_ns-1 samples and resolves
+//                     through shared-memory atomicMin on the depth key + a candidate queue, so
+//                     that the (depth, id) minimum is exact whatever the order.
+// A chunk with only a handful of small triangles sends them down the pixel-owner path too.
 // ---------------------------------------------------------------------------------------------
-struct BigTri {
-    double ax, ay, s00, s01, s10, s11, uz, z0, z1, z2;
-    int x0, y0, x1, y1;   // bbox clipped to the tile, absolute pixels
-    uint32_t id;
-    uint32_t _pad;
-};
+constexpr int CHUNK = TPB;
+constexpr int SMALL_MIN_DEFAULT = 24;   // fewer small triangles than this in a chunk: not worth the atomic phases
 
 struct RasterArgs {
-    GeomArgs g;
+    uint32_t ntris, id_base;
+    const TriRec* trirec;     // [nviews][ntris]
     const uint32_t* counts;   // [nviews][ntiles]
     const uint32_t* offsets;  // [nviews][ntiles]
     const uint32_t* bins;
+    int big_ns, small_min;
 };
 
-__global__ void __launch_bounds__(TPB) k_raster(FrameDev f, RasterArgs a) {
+__global__ void __launch_bounds__(TPB, 4) k_raster(FrameDev f, RasterArgs a) {
     const int tile = blockIdx.x, view = blockIdx.y;
     const size_t tslot = (size_t)view * f.ntiles + tile;
     const uint32_t n = a.counts[tslot];
@@ -363,8 +403,8 @@ __global__ void __launch_bounds__(TPB) k_raster(FrameDev f, RasterArgs a) {
     __shared__ unsigned long long qk[QCAP];
     __shared__ uint32_t qid[QCAP];
     __shared__ uint8_t qp[QCAP];
-    __shared__ BigTri big[TPB];
-    __shared__ unsigned int qn, nbig, overflow;
+    __shared__ TriRec recs[CHUNK];       // big triangles of the current chunk (pad0 carries the id)
+    __shared__ unsigned int qn, nbig[2];
     __shared__ unsigned long long red[TPB / 32];
 
     const int tid = threadIdx.x;
@@ -372,104 +412,104 @@ __global__ void __launch_bounds__(TPB) k_raster(FrameDev f, RasterArgs a) {
     const int px = tx0 + (tid & 15), py = ty0 + (tid >> 4);
     const bool pvalid = px < f.W && py < f.H;
     const size_t gp = (size_t)view * f.npix + (size_t)py * f.W + px;
-    zk[tid] = pvalid ? f.zkey[gp] : 0ull;
-    vid[tid] = pvalid ? f.vis[gp] : VIS_NONE;
-    unsigned long long prev = zk[tid];
-    if (tid == 0) { qn = 0; nbig = 0; overflow = 0; }
+    unsigned long long myk = pvalid ? f.zkey[gp] : 0ull;   // this thread's pixel
+    uint32_t myid = pvalid ? f.vis[gp] : VIS_NONE;
+    if (tid == 0) { qn = 0; nbig[0] = 0; nbig[1] = 0; }
     __syncthreads();
 
-    const VRec* vr = a.g.vrec + (size_t)view * a.g.nverts;
+    const TriRec* tr = a.trirec + (size_t)view * a.ntris;
     unsigned long long covered = 0, zmin = ~0ull, zmax = 0ull;
+    int parity = 0;
 
-    for (uint32_t base = 0; base < n; base += TPB) {
+    for (uint32_t base = 0; base < n; base += CHUNK, parity ^= 1) {
         TriSetup ts;
         uint32_t gid = 0;
-        int cx0 = 0, cy0 = 0, cx1 = -1, cy1 = -1;
-        bool pending = false;
-        if (base + tid < n) {
-            uint32_t t = __ldg(a.bins + off + base + tid);
-            VRec va = load_vrec(vr + vertex_index(a.g.idx, a.g.first_tri, t, 0));
-            VRec vb = load_vrec(vr + vertex_index(a.g.idx, a.g.first_tri, t, 1));
-            VRec vc = load_vrec(vr + vertex_index(a.g.idx, a.g.first_tri, t, 2));
-            setup_triangle(va, vb, vc, f.W, f.H, ts);   // SETUP_DRAW by construction of the bins
-            gid = a.g.id_base + t + 1u;
+        int cx0 = 0, cy0 = 0, cx1 = -1, cy1 = -1, ns = 0;
+        const bool has = base + tid < n;
+        if (has) {
+            const uint32_t t = __ldg(a.bins + off + base + tid);
+            load_trirec(tr + t, ts);
+            gid = a.id_base + t + 1u;
             cx0 = max(ts.x0, tx0); cx1 = min(ts.x1, tx0 + TILE - 1);
             cy0 = max(ts.y0, ty0); cy1 = min(ts.y1, ty0 + TILE - 1);
-            int ns = (cx1 - cx0 + 1) * (cy1 - cy0 + 1);
-            if (ns >= BIG_NS) {
-                unsigned s = atomicAdd(&nbig, 1u);
-                BigTri& B = big[s];
-                B.ax = ts.ax; B.ay = ts.ay; B.s00 = ts.s00; B.s01 = ts.s01; B.s10 = ts.s10; B.s11 = ts.s11;
-                B.uz = ts.uz; B.z0 = ts.z0; B.z1 = ts.z1; B.z2 = ts.z2;
-                B.x0 = cx0; B.y0 = cy0; B.x1 = cx1; B.y1 = cy1; B.id = gid;
-            } else {
-                pending = ns > 0;
-            }
+            ns = (cx1 - cx0 + 1) * (cy1 - cy0 + 1);
         }
-        // ---- small triangles: one thread per triangle, atomics on the tile's keys -------------
-        int sx = cx0, sy = cy0;  // resume position when the candidate queue fills up
-        for (;;) {
-            if (pending) {
+        bool small = has && ns < a.big_ns;
+        const int nsmall = __syncthreads_count(small);      // also: previous chunk is done with recs[]
+        if (nsmall < a.small_min) small = false;
+        if (has && !small) {
+            const unsigned s = atomicAdd(&nbig[parity], 1u);
+            TriRec& B = recs[s];
+            B.ax = ts.ax; B.ay = ts.ay; B.s00 = ts.s00; B.s01 = ts.s01; B.s10 = ts.s10; B.s11 = ts.s11;
+            B.uz = ts.uz; B.z0 = ts.z0; B.z1 = ts.z1; B.z2 = ts.z2;
+            B.x0 = (unsigned short)cx0; B.y0 = (unsigned short)cy0; B.x1 = (unsigned short)cx1; B.y1 = (unsigned short)cy1;
+            B.pad0 = gid;
+        }
+        if (nsmall >= a.small_min) {
+            // ---- small triangles: one thread per triangle, atomics on the tile's keys ------------
+            zk[tid] = myk; vid[tid] = myid;
+            __syncthreads();
+            bool pending = small;
+            int sx = cx0, sy = cy0;  // resume position when the candidate queue fills up
+            for (;;) {
                 bool full = false;
-                while (sy <= cy1) {
-                    double b[3], z;
-                    if (eval_sample(ts, sx, sy, b, z)) {
-                        const unsigned long long k = fragment_key(z);
-                        const int p = ((sy - ty0) << TILE_SHIFT) | (sx - tx0);
-                        if (k <= *(volatile unsigned long long*)&zk[p]) {
-                            unsigned long long old = atomicMin(&zk[p], k);
-                            if (old >= k) {  // current minimum or a tie: remember who asked
-                                unsigned s = atomicAdd(&qn, 1u);
-                                if (s >= (unsigned)QCAP) { overflow = 1u; full = true; break; }
-                                qk[s] = k; qid[s] = gid; qp[s] = (uint8_t)p;
+                if (pending) {
+                    while (sy <= cy1) {
+                        double b[3], z;
+                        if (eval_sample(ts, sx, sy, b, z)) {
+                            const unsigned long long k = fragment_key(z);
+                            const int p = ((sy - ty0) << TILE_SHIFT) | (sx - tx0);
+                            if (k <= *(volatile unsigned long long*)&zk[p]) {
+                                unsigned long long old = atomicMin(&zk[p], k);
+                                if (old >= k) {  // current minimum or a tie: remember who asked
+                                    unsigned s = atomicAdd(&qn, 1u);
+                                    if (s >= (unsigned)QCAP) { full = true; break; }
+                                    qk[s] = k; qid[s] = gid; qp[s] = (uint8_t)p;
+                                }
                             }
+                            ++covered;
+                            zmin = min(zmin, k); zmax = max(zmax, k);
                         }
-                        ++covered;
-                        zmin = min(zmin, k); zmax = max(zmax, k);
+                        if (++sx > cx1) { sx = cx0; ++sy; }
                     }
-                    if (++sx > cx1) { sx = cx0; ++sy; }
+                    if (!full) pending = false;
                 }
-                if (!full) pending = false;
+                __syncthreads();
+                // a pixel whose depth got strictly smaller forgets its previous winner
+                if (zk[tid] != myk) { vid[tid] = VIS_NONE; myk = zk[tid]; }
+                __syncthreads();
+                const unsigned qc = min(qn, (unsigned)QCAP);
+                for (unsigned e = tid; e < qc; e += TPB)
+                    if (zk[qp[e]] == qk[e]) atomicMin(&vid[qp[e]], qid[e]);  // ties: lowest id = first submitted
+                const int more = __syncthreads_or(full);
+                if (tid == 0) qn = 0;
+                if (!more) break;
+                __syncthreads();
             }
-            __syncthreads();
-            // a pixel whose depth got strictly smaller forgets its previous winner
-            if (zk[tid] != prev) { vid[tid] = VIS_NONE; prev = zk[tid]; }
-            __syncthreads();
-            const unsigned qc = min(qn, (unsigned)QCAP);
-            for (unsigned e = tid; e < qc; e += TPB)
-                if (zk[qp[e]] == qk[e]) atomicMin(&vid[qp[e]], qid[e]);  // ties: lowest id = first submitted
-            const bool more = overflow != 0u;
-            __syncthreads();
-            if (tid == 0) { qn = 0; overflow = 0; }
-            __syncthreads();
-            if (!more) break;
+            myid = vid[tid];
+        } else {
+            __syncthreads();   // recs[] and nbig[parity] are complete
         }
-        // ---- big triangles: every thread owns its pixel, no atomics -----------------------------
-        const unsigned nb = nbig;
-        if (nb) {
-            unsigned long long myk = zk[tid];
-            uint32_t myid = vid[tid];
-            for (unsigned j = 0; j < nb; ++j) {
-                const BigTri& B = big[j];
-                if (px < B.x0 || px > B.x1 || py < B.y0 || py > B.y1) continue;
-                TriSetup t2;
-                t2.ax = B.ax; t2.ay = B.ay; t2.s00 = B.s00; t2.s01 = B.s01; t2.s10 = B.s10; t2.s11 = B.s11;
-                t2.uz = B.uz; t2.z0 = B.z0; t2.z1 = B.z1; t2.z2 = B.z2;
-                double b[3], z;
-                if (!eval_sample(t2, px, py, b, z)) continue;
-                unsigned long long k = fragment_key(z);
-                ++covered;
-                zmin = min(zmin, k); zmax = max(zmax, k);
-                if (k < myk) { myk = k; myid = B.id; }
-                else if (k == myk && B.id < myid) myid = B.id;
-            }
-            zk[tid] = myk; vid[tid] = myid; prev = myk;
-            __syncthreads();
-            if (tid == 0) nbig = 0;
-            __syncthreads();
+        // ---- pixel-owner path: every thread owns its pixel, no atomics -----------------------------
+        const unsigned nb = nbig[parity];
+        if (tid == 0) nbig[parity ^ 1] = 0;   // nobody touches the other counter before the next chunk's barrier
+        for (unsigned j = 0; j < nb; ++j) {
+            const TriRec& B = recs[j];
+            if (px < (int)B.x0 || px > (int)B.x1 || py < (int)B.y0 || py > (int)B.y1) continue;
+            TriSetup t2;
+            t2.ax = B.ax; t2.ay = B.ay; t2.s00 = B.s00; t2.s01 = B.s01; t2.s10 = B.s10; t2.s11 = B.s11;
+            t2.uz = B.uz; t2.z0 = B.z0; t2.z1 = B.z1; t2.z2 = B.z2;
+            double b[3], z;
+            if (!eval_sample(t2, px, py, b, z)) continue;
+            const unsigned long long k = fragment_key(z);
+            const uint32_t id = B.pad0;
+            ++covered;
+            zmin = min(zmin, k); zmax = max(zmax, k);
+            if (k < myk) { myk = k; myid = id; }
+            else if (k == myk && id < myid) myid = id;
         }
     }
-    if (pvalid) { f.zkey[gp] = zk[tid]; f.vis[gp] = vid[tid]; }
+    if (pvalid) { f.zkey[gp] = myk; f.vis[gp] = myid; }
     covered = block_reduce_sum(covered, red);
     zmin = block_reduce_min64(zmin, red);
     zmax = ~block_reduce_min64(~zmax, red);

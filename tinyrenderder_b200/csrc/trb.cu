@@ -122,7 +122,7 @@ struct TrbCtx {
     int shade_row0 = 0, shade_row1 = -1;
 
     // per-draw scratch (stream ordered reuse)
-    DevBuf tribox, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
+    DevBuf tribox, trirec, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
     uint32_t* host_total = nullptr;  // pinned
 
     // timing
@@ -132,6 +132,7 @@ struct TrbCtx {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<ProfAcc> prof_acc;
     uint64_t launches = 0;
+    int big_ns = BIG_NS_DEFAULT, small_min = SMALL_MIN_DEFAULT;
 };
 
 namespace {
@@ -259,6 +260,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     const size_t nslots = (size_t)f.nviews * f.ntiles;
     if (nslots >= 0xFFFFFFFFull) return fail(c, TRB_E_ARG, "draw: too many tiles x views");
     CU(c->tribox.ensure((size_t)f.nviews * g.ntris * sizeof(uint2), c->stream));
+    CU(c->trirec.ensure((size_t)f.nviews * g.ntris * sizeof(TriRec), c->stream));
     CU(c->counts.ensure(nslots * 4, c->stream));
     CU(c->offsets.ensure(nslots * 4, c->stream));
     CU(c->cursor.ensure(nslots * 4, c->stream));
@@ -268,7 +270,8 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     dim3 tgrid(blocks_for(g.ntris), f.nviews);
     {
         Launch L(c, "k_setup_count");
-        k_setup_count<<<tgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->counts.as<uint32_t>());
+        k_setup_count<<<tgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
+                                                     c->counts.as<uint32_t>());
     }
     CU(cudaGetLastError());
     int rc = exclusive_scan(c, c->counts.as<uint32_t>(), (uint32_t)nslots, c->offsets.as<uint32_t>(),
@@ -286,10 +289,14 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
                                             c->cursor.as<uint32_t>(), c->bins.as<uint32_t>());
     }
     RasterArgs ra;
-    ra.g = g;
+    ra.ntris = g.ntris;
+    ra.id_base = g.id_base;
+    ra.trirec = c->trirec.as<TriRec>();
     ra.counts = c->counts.as<uint32_t>();
     ra.offsets = c->offsets.as<uint32_t>();
     ra.bins = c->bins.as<uint32_t>();
+    ra.big_ns = c->big_ns;
+    ra.small_min = c->small_min;
     {
         Launch L(c, "k_raster");
         k_raster<<<dim3(f.ntiles, f.nviews), TPB, 0, c->stream>>>(f, ra);
@@ -355,6 +362,8 @@ int trb_create(int device, TrbCtx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return TRB_E_CUDA;
     TrbCtx* c = new TrbCtx();
     c->device = device;
+    if (const char* e = getenv("TRB_BIG_NS")) c->big_ns = std::max(1, atoi(e));
+    if (const char* e = getenv("TRB_SMALL_MIN")) c->small_min = std::max(1, atoi(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_a) != cudaSuccess || cudaEventCreate(&c->ev_b) != cudaSuccess ||
         cudaMallocHost((void**)&c->host_total, 64) != cudaSuccess) {
@@ -377,7 +386,7 @@ int trb_destroy(TrbCtx* c) {
         }
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
-    DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->tribox,
+    DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->tribox, &c->trirec,
                       &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->scratch_a,
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
@@ -484,7 +493,7 @@ int trb_free_texture(TrbCtx* c, TrbTex h) {
 }
 
 int trb_begin_batch(TrbCtx* c, int w, int h, int nviews) {
-    if (!c || w <= 0 || h <= 0 || nviews <= 0 || nviews > 65535 || w > 65535 * TILE || h > 65535 * TILE)
+    if (!c || w <= 0 || h <= 0 || nviews <= 0 || nviews > 65535 || w > 65536 || h > 65536)
         return fail(c, TRB_E_ARG, "begin_batch: bad size");
     int rc = check_device(c);
     if (rc) return rc;
