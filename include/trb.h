@@ -112,7 +112,7 @@ typedef struct TrbStats {
     uint64_t visible_triangles;    /* distinct winning triangles at flush (0 if not counted) */
     int32_t bbox_min_x, bbox_min_y, bbox_max_x, bbox_max_y; /* our_gl.cpp:138-141 */
     double z_min;                  /* == min_z of our_gl.cpp:197 (order independent) */
-    double z_max_covered;          /* max z over covered samples (>= reference max_z) */
+    double z_max_covered;          /* largest finite depth left in the z-buffer (visible surfaces) */
     uint64_t fragments_drawn_ref;  /* oracle only: the reference's order-dependent counter */
     double z_max_ref;              /* oracle only: the reference's order-dependent max_z */
 } TrbStats;

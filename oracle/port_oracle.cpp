@@ -271,7 +271,6 @@ void rasterize_port(View& view, int W, int H, const M4& viewport, const double c
             double z = b0 * ndc[0][2] + b1 * ndc[1][2] + b2 * ndc[2][2];  // (13) :156-158
             if (!std::isfinite(z)) continue;                              // (14) :160
             ++st.fragments_covered;
-            st.z_max_covered = std::max(st.z_max_covered, z);
             size_t idx = (size_t)x + (size_t)y * W;                       // (15) :162-165
             if (!(z < view.z[idx])) continue;
             double iw0 = (std::abs(w0) > 1e-12) ? (1.0 / w0) : 0.0;       // (16) :168-185
@@ -560,8 +559,14 @@ int orc_get_stats(TrbCtx* c, int view, TrbStats* out) {
     if (!c || view < 0 || view >= c->nviews || !out) return fail(c, TRB_E_ARG, "get_stats");
     *out = c->views[view].st;
     uint64_t px = 0;
-    for (double z : c->views[view].z) px += std::isfinite(z) ? 1 : 0;
+    double zmax = -std::numeric_limits<double>::infinity();
+    for (double z : c->views[view].z)
+        if (std::isfinite(z)) {
+            ++px;
+            zmax = std::max(zmax, z);
+        }
     out->pixels_shaded = px;
+    out->z_max_covered = zmax;
     return TRB_OK;
 }
 int orc_synchronize(TrbCtx* c) { return c ? TRB_OK : TRB_E_ARG; }

@@ -391,7 +391,10 @@ struct RasterArgs {
     int big_ns, small_min;
 };
 
-__global__ void __launch_bounds__(TPB, 4) k_raster(FrameDev f, RasterArgs a) {
+#ifndef TRB_RASTER_MIN_BLOCKS
+#define TRB_RASTER_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev f, RasterArgs a) {
     const int tile = blockIdx.x, view = blockIdx.y;
     const size_t tslot = (size_t)view * f.ntiles + tile;
     const uint32_t n = a.counts[tslot];
@@ -414,11 +417,12 @@ __global__ void __launch_bounds__(TPB, 4) k_raster(FrameDev f, RasterArgs a) {
     const size_t gp = (size_t)view * f.npix + (size_t)py * f.W + px;
     unsigned long long myk = pvalid ? f.zkey[gp] : 0ull;   // this thread's pixel
     uint32_t myid = pvalid ? f.vis[gp] : VIS_NONE;
+    const unsigned long long k_in = myk;
     if (tid == 0) { qn = 0; nbig[0] = 0; nbig[1] = 0; }
     __syncthreads();
 
     const TriRec* tr = a.trirec + (size_t)view * a.ntris;
-    unsigned long long covered = 0, zmin = ~0ull, zmax = 0ull;
+    uint32_t covered = 0;
     int parity = 0;
 
     for (uint32_t base = 0; base < n; base += CHUNK, parity ^= 1) {
@@ -468,7 +472,6 @@ __global__ void __launch_bounds__(TPB, 4) k_raster(FrameDev f, RasterArgs a) {
                                 }
                             }
                             ++covered;
-                            zmin = min(zmin, k); zmax = max(zmax, k);
                         }
                         if (++sx > cx1) { sx = cx0; ++sy; }
                     }
@@ -504,28 +507,30 @@ __global__ void __launch_bounds__(TPB, 4) k_raster(FrameDev f, RasterArgs a) {
             const unsigned long long k = fragment_key(z);
             const uint32_t id = B.pad0;
             ++covered;
-            zmin = min(zmin, k); zmax = max(zmax, k);
             if (k < myk) { myk = k; myid = id; }
             else if (k == myk && id < myid) myid = id;
         }
     }
     if (pvalid) { f.zkey[gp] = myk; f.vis[gp] = myid; }
-    covered = block_reduce_sum(covered, red);
-    zmin = block_reduce_min64(zmin, red);
-    zmax = ~block_reduce_min64(~zmax, red);
-    if (tid == 0 && covered) {
-        DevStats* s = f.stats + view;
-        atomicAdd(&s->frag_covered, covered);
-        atomicMin(&s->zmin_key, zmin);
-        atomicMax(&s->zmax_key, zmax);
+    const unsigned long long total = block_reduce_sum((unsigned long long)covered, red);
+    // min_z of our_gl.cpp:197: the smallest drawn depth.  A pixel's new key is the minimum of this
+    // draw's fragments there, and fragments that lost to an older, smaller depth cannot be the minimum.
+    const unsigned long long zmin = block_reduce_min64(myk != k_in ? myk : ~0ull, red);
+    if (tid == 0 && total) {
+        atomicAdd(&f.stats[view].frag_covered, total);
+        atomicMin(&f.stats[view].zmin_key, zmin);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // flush: the fragment() calls of our_gl.cpp:187-192, once per visible pixel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_shade(FrameDev f, const DrawDev* __restrict__ draws, int ndraws, int row0,
+__global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __restrict__ draws, int ndraws, int row0,
                                                int row1) {
+    constexpr int MAX_SM_DRAWS = 32;
+    __shared__ uint32_t sm_base[MAX_SM_DRAWS];
+    for (int i = threadIdx.x; i < ndraws && i < MAX_SM_DRAWS; i += TPB) sm_base[i] = draws[i].id_base;
+    __syncthreads();
     const int view = blockIdx.y;
     const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
     const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
@@ -536,7 +541,8 @@ __global__ void __launch_bounds__(TPB) k_shade(FrameDev f, const DrawDev* __rest
             int lo = 0, hi = ndraws - 1;  // last draw with id_base < id
             while (lo < hi) {
                 int mid = (lo + hi + 1) >> 1;
-                if (draws[mid].id_base < id) lo = mid; else hi = mid - 1;
+                const uint32_t bse = mid < MAX_SM_DRAWS ? sm_base[mid] : draws[mid].id_base;
+                if (bse < id) lo = mid; else hi = mid - 1;
             }
             const DrawDev D = draws[lo];
             const uint32_t t = id - D.id_base - 1u;

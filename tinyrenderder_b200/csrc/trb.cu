@@ -758,18 +758,25 @@ int trb_get_stats(TrbCtx* c, int view, TrbStats* out) {
     if (rc) return rc;
     const unsigned long long n = c->frame.npix;
     CU(c->scratch_b.ensure(64, c->stream));
-    CU(cudaMemsetAsync(c->scratch_b.p, 0, 8, c->stream));
+    unsigned long long init[3] = {0ull, ~0ull, 0ull};  // finite count, min key, max key
+    CU(cudaMemcpyAsync(c->scratch_b.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     {
         unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(n), 148ull * 16);
         Launch L(c, "k_count_finite");
         k_count_finite<<<grid, TPB, 0, c->stream>>>(c->frame.zkey + n * view, n, c->scratch_b.as<unsigned long long>());
     }
+    {
+        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(n), 148ull * 16);
+        Launch L(c, "k_depth_range");
+        k_depth_range<<<grid, TPB, 0, c->stream>>>(c->frame.zkey + n * view, n, c->scratch_b.as<unsigned long long>() + 1);
+    }
     CU(cudaGetLastError());
     DevStats s;
-    unsigned long long finite = 0;
+    unsigned long long res[3] = {0, 0, 0};
     CU(cudaMemcpyAsync(&s, c->frame.stats + view, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(&finite, c->scratch_b.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(res, c->scratch_b.p, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    const unsigned long long finite = res[0];
     memset(out, 0, sizeof(*out));
     out->triangles_submitted = c->tris_submitted;
     out->triangles_binned = s.tri_binned;
@@ -780,8 +787,10 @@ int trb_get_stats(TrbCtx* c, int view, TrbStats* out) {
     out->bbox_min_y = s.by0;
     out->bbox_max_x = s.bx1;
     out->bbox_max_y = s.by1;
-    out->z_min = s.frag_covered ? depth_from_key(s.zmin_key) : INFINITY;
-    out->z_max_covered = s.frag_covered ? depth_from_key(s.zmax_key) : -INFINITY;
+    // z_min is tracked by the raster kernel over drawn fragments (it must survive a depth_restore,
+    // like the reference's static min_z); the max is the largest depth left in the buffer
+    out->z_min = s.zmin_key != ~0ull ? depth_from_key(s.zmin_key) : INFINITY;
+    out->z_max_covered = finite ? depth_from_key(res[2]) : -INFINITY;
     out->z_max_ref = NAN;
     return TRB_OK;
 }
