@@ -1,0 +1,177 @@
+"""The C++ host layer (tinyrenderder_b200/host: our_gl.h mirror, Model OBJ/TGA loader, ModelManager,
+PhongShader/EyeShader) through the example program that mirrors the reference's main().
+
+CPU: the ORACLE build of the example (reference headers + the reference's own our_gl.cpp/tgaimage.cpp)
+must produce the z-buffer the Python-driven reference oracle produces for the same meshes, and our TGA
+writer must be byte-identical to the reference's.  GPU: the DEVICE build of the same source must match the
+oracle build's outputs."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import tinyrenderder_b200 as trb
+from tinyrenderder_b200 import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXAMPLE = os.path.join(ROOT, "tinyrenderder_b200", "host", "bin", "example")
+TGA_TOOL = os.path.join(ROOT, "tinyrenderder_b200", "host", "bin", "tga_tool")
+EXAMPLE_REF = os.path.join(ROOT, "oracle", "_ref", "example_ref")
+TGA_TOOL_REF = os.path.join(ROOT, "oracle", "_ref", "tga_tool_ref")
+W, H = 300, 200
+
+
+def write_obj(path, mesh):
+    with open(path, "w") as f:
+        for p in mesh.pos:
+            f.write("v %.9g %.9g %.9g\n" % tuple(p))
+        for t in mesh.uv:
+            f.write("vt %.9g %.9g\n" % (t[0], np.float32(1.0) - t[1]))  # the loader flips v (aiProcess_FlipUVs)
+        for n in mesh.nrm:
+            f.write("vn %.9g %.9g %.9g\n" % tuple(n))
+        for a, b, c in mesh.idx.reshape(-1, 3) + 1:
+            f.write("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % (a, a, a, b, b, b, c, c, c))
+
+
+def write_tga(path, bgr):
+    h, w, bpp = bgr.shape
+    with open(path, "wb") as f:  # type 2, top-left origin: read_tga_file keeps the rows as they are
+        f.write(struct.pack("<BBBHHBHHHHBB", 0, 0, 2, 0, 0, 0, 0, 0, w, h, bpp * 8, 0x20))
+        f.write(np.ascontiguousarray(bgr).tobytes())
+
+
+def read_tga(path):
+    raw = open(path, "rb").read()
+    idl, _, typ, _, _, _, _, _, w, h, bits, desc = struct.unpack("<BBBHHBHHHHBB", raw[:18])
+    bpp = bits // 8
+    body = raw[18 + idl:]
+    if typ in (2, 3):
+        px = np.frombuffer(body[:w * h * bpp], dtype=np.uint8)
+    else:
+        out = bytearray()
+        i = 0
+        while len(out) < w * h * bpp:
+            hd = body[i]
+            i += 1
+            n = (hd & 127) + 1
+            if hd < 128:
+                out += body[i:i + n * bpp]
+                i += n * bpp
+            else:
+                out += body[i:i + bpp] * n
+                i += bpp
+        px = np.frombuffer(bytes(out), dtype=np.uint8)
+    return px.reshape(h, w, bpp)  # rows in file order (descriptor 0x00: row 0 = bottom = framebuffer y 0)
+
+
+@pytest.fixture(scope="module")
+def assets(tmp_path_factory, built):
+    d = str(tmp_path_factory.mktemp("assets"))
+    sc = scenes.orbit_scene(W, H, room_quads=((24, 12), (24, 6), (12, 12)), head_res=(20, 14), eye_res=(10, 8),
+                            tex_size=64)
+    names = {"room": "sponza", "head": "head", "eyes": "eyes"}
+    for it in sc.items:
+        stem = os.path.join(d, names[it.mesh.name])
+        write_obj(stem + ".obj", it.mesh)
+        for key, sfx in (("diffuse", "_diffuse"), ("normal", "_nm"), ("specular", "_spec")):
+            if key in it.textures:
+                write_tga(stem + sfx + ".tga", it.textures[key])
+    return d, sc
+
+
+def run_example(exe, assets_dir, outdir, *extra):
+    os.makedirs(outdir, exist_ok=True)
+    cmd = [exe, os.path.join(assets_dir, "head.obj"), os.path.join(assets_dir, "eyes.obj"),
+           os.path.join(assets_dir, "sponza.obj"), str(W), str(H), outdir] + list(extra)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    out = {n: read_tga(os.path.join(outdir, n + ".tga")) for n in ("phong", "zbuffer", "ao", "final")}
+    out["z"] = np.fromfile(os.path.join(outdir, "zbuffer.bin"), dtype=np.float64).reshape(H, W)
+    out["stderr"] = res.stderr
+    out["dir"] = outdir
+    return out
+
+
+def need(path):
+    if not os.path.exists(path):
+        pytest.skip("%s not built (needs /root/reference)" % os.path.relpath(path, ROOT))
+
+
+def test_oracle_build_matches_python_driven_reference(assets, tmp_path, ref_api):
+    need(EXAMPLE_REF)
+    d, sc = assets
+    got = run_example(EXAMPLE_REF, d, str(tmp_path / "ref"))
+    # same scene through the Python frame driver + the reference's rasterize (arrays, no OBJ/TGA files)
+    with trb.Renderer(ref_api) as r:
+        up = scenes.UploadedScene(r, sc)
+        view = ref_api.lookat([-3.4019, 2.2001, 1.8026], [1.3555, 1.5116, -0.9686], [0, 1, 0])
+        up.render(view[None], ref_api.perspective(70.0, W / H, 0.05, 500.0))
+        z = r.read_depth()
+        ao = r.ssao()
+        zi = r.depth_image()
+    assert np.array_equal(got["z"].view(np.uint64), z.view(np.uint64))     # OBJ loader + draw flow + z restore
+    assert np.array_equal(got["ao"][:, :, 0], ao) and np.array_equal(got["zbuffer"][:, :, 0], zi)
+    assert "triangles=" in got["stderr"]
+
+
+def test_tga_writer_is_byte_identical_to_the_reference(assets, tmp_path, built):
+    need(TGA_TOOL_REF)
+    d, _ = assets
+    rng = np.random.default_rng(1)
+    img = np.zeros((40, 300, 3), np.uint8)
+    img[:, :100] = rng.integers(0, 255, (40, 100, 3))            # raw packets
+    img[:, 100:260] = rng.integers(0, 255, (40, 1, 3))            # runs longer than 128
+    img[::3, 260:] = 7                                            # short runs / alternations
+    grey = rng.integers(0, 3, (33, 77, 1)).astype(np.uint8) * 100
+    for name, arr in (("rgb", img), ("grey", grey), ("diffuse", None)):
+        src = os.path.join(d, "head_diffuse.tga") if arr is None else str(tmp_path / (name + ".tga"))
+        if arr is not None:
+            write_tga(src, arr)
+        for mode in ([], ["raw"]):
+            a, b = str(tmp_path / "ours.tga"), str(tmp_path / "ref.tga")
+            assert subprocess.run([TGA_TOOL, src, a] + mode).returncode == 0
+            assert subprocess.run([TGA_TOOL_REF, src, b] + mode).returncode == 0
+            assert open(a, "rb").read() == open(b, "rb").read(), (name, mode)
+            # and our reader understands what was written (RLE round trip)
+            c = str(tmp_path / "again.tga")
+            assert subprocess.run([TGA_TOOL, a, c, "raw"]).returncode == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [[], ["--immediate"]])
+def test_device_build_matches_oracle_build(assets, tmp_path, mode):
+    """the same example source: device build (libtrb.so) vs oracle build (the reference's our_gl.cpp)"""
+    need(EXAMPLE_REF)
+    d, _ = assets
+    want = run_example(EXAMPLE_REF, d, str(tmp_path / "ref"))
+    got = run_example(EXAMPLE, d, str(tmp_path / "dev"), *mode)
+    assert np.array_equal(got["z"].view(np.uint64), want["z"].view(np.uint64))
+    assert np.array_equal(got["ao"], want["ao"]) and np.array_equal(got["zbuffer"], want["zbuffer"])
+    for k in ("phong", "final"):
+        diff = np.abs(got[k].astype(int) - want[k].astype(int)).max(axis=-1)
+        assert (diff <= 1).mean() >= 0.999, k
+    # ao.tga / zbuffer.tga files written by our TGA writer are byte-identical to the reference's
+    for n in ("ao", "zbuffer"):
+        assert open(os.path.join(got["dir"], n + ".tga"), "rb").read() == open(os.path.join(want["dir"], n + ".tga"), "rb").read()
+
+
+@pytest.mark.gpu
+def test_unknown_shader_is_an_error_not_a_fallback(tmp_path, built):
+    src = tmp_path / "unknown.cpp"
+    src.write_text('''#include <our_gl.h>
+#include <iostream>
+struct Mine : IShader { std::pair<bool, TGAColor> fragment(const vec3) const override { return {false, TGAColor()}; } };
+int main() { TGAImage fb(8, 8, TGAImage::RGB); init_zbuffer(8, 8); Mine s; vec4 clip[3];
+  try { rasterize(clip, s, fb); } catch (const std::exception& e) { std::cout << "threw: " << e.what() << std::endl; return 0; }
+  return 1; }
+''')
+    host = os.path.join(ROOT, "tinyrenderder_b200", "host")
+    exe = str(tmp_path / "unknown")
+    subprocess.check_call(["g++", "-std=c++17", "-I", host, str(src), os.path.join(host, "our_gl.cpp"),
+                           os.path.join(host, "model.cpp"), os.path.join(host, "tgaimage.cpp"), "-L",
+                           os.path.join(ROOT, "tinyrenderder_b200"), "-ltrb",
+                           "-Wl,-rpath," + os.path.join(ROOT, "tinyrenderder_b200"), "-o", exe])
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0 and "no CPU fallback" in res.stdout

@@ -1,0 +1,352 @@
+// our_gl.cpp - the reference's pipeline API (our_gl.cpp:12-280) over the B200 backend's C ABI.
+// Host code only: matrices and batching; every fragment is produced by libtrb.so.
+#include <our_gl.h>
+#include <model.h>
+
+#include "../../include/trb.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+
+mat<4, 4> ModelView = mat<4, 4>::identity();
+mat<4, 4> Perspective = mat<4, 4>::identity();
+mat<4, 4> Viewport = mat<4, 4>::identity();
+std::vector<double> zbuffer;
+
+namespace {
+
+struct Backend {
+    TrbCtx* ctx = nullptr;
+    int w = 0, h = 0;
+    bool frame = false;
+    // pending immediate-mode batch (consecutive rasterize() calls with the same shader state)
+    std::vector<double> clip, vary;
+    TrbDeviceShader key;
+    double key_mv[16];
+    bool have_key = false;
+    std::vector<uint8_t> color_tmp;
+    std::vector<uint32_t> vis_tmp;
+};
+Backend& B() {
+    static Backend b;
+    return b;
+}
+
+[[noreturn]] void die(const char* what, int rc) {
+    std::string msg = std::string("tinyrenderder-b200: ") + what + " failed (rc=" + std::to_string(rc) + "): " +
+                      (B().ctx ? trb_last_error(B().ctx) : "no context");
+    std::cerr << msg << std::endl;
+    throw std::runtime_error(msg);
+}
+#define CK(call)                         \
+    do {                                 \
+        int rc_ = (call);                \
+        if (rc_ != TRB_OK) die(#call, rc_); \
+    } while (0)
+
+void flat(const mat<4, 4>& m, double* out) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) out[i * 4 + j] = m[i][j];
+}
+
+void upload_model(const Model& m) {
+    if (m.dev_uploaded) return;
+    TrbCtx* c = gl_context();
+    const auto& V = m.getVertices();
+    const auto& I = m.getIndices();
+    std::vector<float> pos(V.size() * 3), nrm(V.size() * 3), uv(V.size() * 2);
+    for (size_t i = 0; i < V.size(); ++i) {
+        for (int k = 0; k < 3; ++k) {
+            pos[3 * i + k] = (float)V[i].position[k];   // values originate as fp32 (model.cpp:160-185)
+            nrm[3 * i + k] = (float)V[i].normal[k];
+        }
+        uv[2 * i] = (float)V[i].texcoord.x;
+        uv[2 * i + 1] = (float)V[i].texcoord.y;
+    }
+    std::vector<uint32_t> idx(I.begin(), I.end());
+    TrbMesh h = 0;
+    CK(trb_upload_mesh(c, pos.data(), nrm.data(), uv.data(), (uint32_t)V.size(), idx.data(), idx.size(), &h));
+    m.dev_mesh = h;
+    auto tex = [&](const TGAImage& t, std::uint64_t& out) {
+        out = 0;
+        if (t.width() <= 0) return;
+        TrbTex th = 0;
+        CK(trb_upload_texture(c, t.buffer(), t.width(), t.height(), t.bytespp(), &th));
+        out = th;
+    };
+    if (m.getMaterialCount() > 0) {  // only materials[0] is ever sampled (model.cpp:416-425)
+        tex(m.getMaterial(0).diffuse, m.dev_diffuse);
+        tex(m.getMaterial(0).normal, m.dev_normal);
+        tex(m.getMaterial(0).specular, m.dev_specular);
+    }
+    m.dev_uploaded = true;
+}
+
+void fill_uniforms(const TrbDeviceShader& d, TrbPhongUniforms& u) {
+    std::memset(&u, 0, sizeof(u));
+    for (int i = 0; i < 3; ++i) {
+        u.key_dir_eye[i] = d.key_dir_eye[i];
+        u.fill_dir_eye[i] = d.fill_dir_eye[i];
+        u.rim_dir_eye[i] = d.rim_dir_eye[i];
+    }
+    u.normal_map_strength = d.normal_map_strength;
+    if (d.model) {
+        upload_model(*d.model);
+        u.diffuse = d.model->dev_diffuse;
+        u.normal = d.model->dev_normal;
+        u.specular = d.model->dev_specular;
+    }
+}
+
+void require_frame() {
+    if (!B().frame) throw std::runtime_error("tinyrenderder-b200: call init_zbuffer(width, height) before drawing");
+}
+
+void submit_pending() {
+    Backend& b = B();
+    if (b.clip.empty()) return;
+    TrbPhongUniforms u;
+    fill_uniforms(b.key, u);
+    double vp[16];
+    flat(Viewport, vp);
+    CK(trb_set_viewport(b.ctx, vp));
+    const bool lit = b.key.kind == TRB_SHADER_PHONG || b.key.kind == TRB_SHADER_EYE;
+    CK(trb_submit_clip_triangles(b.ctx, b.clip.data(), lit ? b.vary.data() : nullptr, b.clip.size() / 12, b.key_mv,
+                                 b.key.kind, lit ? &u : nullptr, lit ? sizeof(u) : 0));
+    b.clip.clear();
+    b.vary.clear();
+    b.have_key = false;
+}
+
+bool same_state(const TrbDeviceShader& a, const TrbDeviceShader& c, const double* mv_a, const double* mv_c) {
+    return a.kind == c.kind && a.model == c.model && a.normal_map_strength == c.normal_map_strength &&
+           !std::memcmp(a.key_dir_eye, c.key_dir_eye, 24) && !std::memcmp(a.fill_dir_eye, c.fill_dir_eye, 24) &&
+           !std::memcmp(a.rim_dir_eye, c.rim_dir_eye, 24) && !std::memcmp(mv_a, mv_c, 128);
+}
+
+}  // namespace
+
+void trb_host_release_model(const Model& m) {
+    Backend& b = B();
+    if (!b.ctx || !m.dev_uploaded) return;
+    if (m.dev_mesh) trb_free_mesh(b.ctx, m.dev_mesh);
+    if (m.dev_diffuse) trb_free_texture(b.ctx, m.dev_diffuse);
+    if (m.dev_normal) trb_free_texture(b.ctx, m.dev_normal);
+    if (m.dev_specular) trb_free_texture(b.ctx, m.dev_specular);
+    m.dev_mesh = m.dev_diffuse = m.dev_normal = m.dev_specular = 0;
+    m.dev_uploaded = false;
+}
+
+TrbCtx* gl_context() {
+    Backend& b = B();
+    if (!b.ctx) {
+        const char* e = std::getenv("TRB_DEVICE");
+        int rc = trb_create(e ? std::atoi(e) : 0, &b.ctx);
+        if (rc != TRB_OK) {
+            b.ctx = nullptr;
+            die("trb_create (no sm_100 device, and there is no CPU fallback)", rc);
+        }
+    }
+    return b.ctx;
+}
+
+// ---- setup functions: host math through the backend's reference-order helpers ---------------
+void lookat(const vec3 eye, const vec3 center, const vec3 up) {
+    double e[3] = {eye.x, eye.y, eye.z}, c[3] = {center.x, center.y, center.z}, u[3] = {up.x, up.y, up.z}, m[16];
+    trb_lookat(e, c, u, m);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) ModelView[i][j] = m[i * 4 + j];
+}
+void init_perspective(double fov_deg, double aspect, double znear, double zfar) {
+    double m[16];
+    trb_perspective(fov_deg, aspect, znear, zfar, m);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) Perspective[i][j] = m[i * 4 + j];
+}
+void init_viewport(int x, int y, int w, int h) {
+    double m[16];
+    trb_viewport(x, y, w, h, m);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) Viewport[i][j] = m[i * 4 + j];
+}
+void init_zbuffer(int width, int height) {
+    Backend& b = B();
+    gl_context();
+    b.clip.clear();
+    b.vary.clear();
+    b.have_key = false;
+    zbuffer.assign((size_t)width * height, std::numeric_limits<double>::infinity());
+    CK(trb_begin_frame(b.ctx, width, height));
+    b.w = width;
+    b.h = height;
+    b.frame = true;
+}
+
+// ---- drawing -------------------------------------------------------------------------------------
+void rasterize(const Triangle& clip, const IShader& shader, TGAImage& framebuffer) {
+    (void)framebuffer;
+    require_frame();
+    Backend& b = B();
+    TrbDeviceShader d;
+    if (!shader.device_shader(d))
+        throw std::runtime_error("tinyrenderder-b200: rasterize() got a shader without a device implementation "
+                                 "(IShader::device_shader); a GPU cannot call a host fragment() and there is no CPU fallback");
+    double mv[16];
+    flat(ModelView, mv);
+    if (b.have_key && !same_state(b.key, d, b.key_mv, mv)) submit_pending();
+    if (!b.have_key) {
+        b.key = d;
+        std::memcpy(b.key_mv, mv, sizeof(mv));
+        b.have_key = true;
+    }
+    for (int v = 0; v < 3; ++v)
+        for (int k = 0; k < 4; ++k) b.clip.push_back(clip[v][k]);
+    if (d.varyings) b.vary.insert(b.vary.end(), d.varyings, d.varyings + 24);
+    else b.vary.insert(b.vary.end(), 24, 0.0);
+}
+
+void gl_draw_model(const Model& model, const IShader& shader, TGAImage& framebuffer) {
+    (void)framebuffer;
+    require_frame();
+    Backend& b = B();
+    submit_pending();
+    TrbDeviceShader d;
+    if (!shader.device_shader(d))
+        throw std::runtime_error("tinyrenderder-b200: gl_draw_model() got a shader without a device implementation");
+    d.model = &model;
+    upload_model(model);
+    TrbPhongUniforms u;
+    fill_uniforms(d, u);
+    double mv[16], pr[16], vp[16];
+    flat(ModelView, mv);
+    flat(Perspective, pr);
+    flat(Viewport, vp);
+    CK(trb_set_viewport(b.ctx, vp));
+    const bool lit = d.kind == TRB_SHADER_PHONG || d.kind == TRB_SHADER_EYE;
+    CK(trb_draw(b.ctx, model.dev_mesh, mv, pr, d.kind, lit ? &u : nullptr, lit ? sizeof(u) : 0, 0,
+                (uint64_t)model.nfaces()));
+}
+
+void gl_flush(TGAImage& framebuffer) {
+    require_frame();
+    Backend& b = B();
+    submit_pending();
+    CK(trb_flush(b.ctx));
+    const size_t n = (size_t)b.w * b.h;
+    b.color_tmp.resize(n * 3);
+    b.vis_tmp.resize(n);
+    CK(trb_read_color(b.ctx, 0, b.color_tmp.data()));
+    CK(trb_read_visibility(b.ctx, 0, b.vis_tmp.data()));
+    // only pixels some fragment was drawn to are copied: the caller's framebuffer keeps whatever it
+    // held elsewhere, exactly like framebuffer.set() per fragment (our_gl.cpp:192)
+    if (framebuffer.width() == b.w && framebuffer.height() == b.h)
+        for (int y = 0; y < b.h; ++y)
+            for (int x = 0; x < b.w; ++x) {
+                size_t p = (size_t)x + (size_t)y * b.w;
+                if (b.vis_tmp[p] != 0u) continue;  // 0 == shaded at least once since begin
+                TGAColor c = framebuffer.get(x, y);
+                c[0] = b.color_tmp[3 * p];
+                c[1] = b.color_tmp[3 * p + 1];
+                c[2] = b.color_tmp[3 * p + 2];
+                framebuffer.set(x, y, c);
+            }
+    zbuffer.resize(n);
+    CK(trb_read_depth(b.ctx, 0, zbuffer.data()));
+}
+
+void gl_zbuffer_snapshot() {
+    require_frame();
+    submit_pending();
+    CK(trb_depth_snapshot(B().ctx));
+}
+void gl_zbuffer_restore(TGAImage& framebuffer) {
+    require_frame();
+    submit_pending();
+    CK(trb_depth_restore(B().ctx));
+    gl_flush(framebuffer);
+}
+
+static void grey_to_image(const std::vector<uint8_t>& g, int w, int h, TGAImage& img) {
+    img = TGAImage(w, h, TGAImage::RGB);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            uint8_t v = g[(size_t)x + (size_t)y * w];
+            img.set(x, y, TGAColor(v, v, v));
+        }
+}
+void gl_ssao(TGAImage& ao_map) {
+    require_frame();
+    submit_pending();
+    Backend& b = B();
+    std::vector<uint8_t> g((size_t)b.w * b.h);
+    CK(trb_ssao(b.ctx, 0, g.data()));
+    grey_to_image(g, b.w, b.h, ao_map);
+}
+void gl_zbuffer_image(TGAImage& grey) {
+    require_frame();
+    submit_pending();
+    Backend& b = B();
+    std::vector<uint8_t> g((size_t)b.w * b.h);
+    CK(trb_depth_image(b.ctx, 0, g.data()));
+    grey_to_image(g, b.w, b.h, grey);
+}
+void gl_composite_ao(TGAImage& final_result) {
+    require_frame();
+    submit_pending();
+    Backend& b = B();
+    std::vector<uint8_t> c((size_t)b.w * b.h * 3);
+    CK(trb_composite_ao(b.ctx, 0, c.data()));
+    final_result = TGAImage(b.w, b.h, TGAImage::RGB);
+    std::memcpy(final_result.buffer(), c.data(), c.size());
+}
+
+void print_render_stats() {
+    Backend& b = B();
+    if (!b.frame) {
+        std::cerr << "DEBUG: triangles=0 (no frame)\n";
+        return;
+    }
+    submit_pending();
+    TrbStats s;
+    CK(trb_get_stats(b.ctx, 0, &s));
+    std::cerr << "DEBUG: triangles=" << s.triangles_submitted << " fragments_covered=" << s.fragments_covered
+              << " pixels_shaded=" << s.pixels_shaded << " bbox=[" << s.bbox_min_x << "," << s.bbox_min_y << "] - ["
+              << s.bbox_max_x << "," << s.bbox_max_y << "]"
+              << " z-range=[" << (std::isfinite(s.z_min) ? std::to_string(s.z_min) : "inf") << ","
+              << (std::isfinite(s.z_max_covered) ? std::to_string(s.z_max_covered) : "-inf") << "]\n";
+}
+
+// ---- frustum (host, bug-for-bug with our_gl.cpp:212-280) --------------------------------------------
+Frustum Frustum::createFromMatrix(const mat<4, 4>& m) {
+    Frustum f;
+    // the reference reads COLUMN 3 +- column k of each row, i.e. planes of the transposed matrix
+    const int col[6] = {0, 0, 1, 1, 2, 2};
+    const double sgn[6] = {1, -1, 1, -1, 1, -1};
+    for (int p = 0; p < 6; ++p) {
+        f.planes[p].normal.x = m[0][3] + sgn[p] * m[0][col[p]];
+        f.planes[p].normal.y = m[1][3] + sgn[p] * m[1][col[p]];
+        f.planes[p].normal.z = m[2][3] + sgn[p] * m[2][col[p]];
+        f.planes[p].d = m[3][3] + sgn[p] * m[3][col[p]];
+        double len = norm(f.planes[p].normal);
+        if (len > 0.0) {
+            f.planes[p].normal = f.planes[p].normal / len;
+            f.planes[p].d /= len;
+        }
+    }
+    return f;
+}
+bool Frustum::intersects(const AABB& box) const {
+    for (int i = 0; i < 6; ++i) {
+        const Plane& pl = planes[i];
+        vec3 far_corner = box.min;  // the corner furthest along the normal
+        if (pl.normal.x >= 0) far_corner.x = box.max.x;
+        if (pl.normal.y >= 0) far_corner.y = box.max.y;
+        if (pl.normal.z >= 0) far_corner.z = box.max.z;
+        if (pl.distance(far_corner) < 0) return false;
+    }
+    return true;
+}

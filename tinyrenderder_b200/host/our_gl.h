@@ -1,0 +1,85 @@
+// our_gl.h - the reference's pipeline header (our_gl.h:17-86) re-implemented over the B200 backend.
+// Same globals, same function names and argument meaning; what changes for a caller is listed in
+// INTEGRATION.md:
+//   * a GPU cannot call the host virtual IShader::fragment, so shaders the device knows describe
+//     themselves through IShader::device_shader(); rasterize() with any other shader throws
+//     (there is no CPU fallback);
+//   * rasterize() calls are batched; gl_flush(framebuffer) resolves them and refreshes the
+//     caller-visible framebuffer and the global zbuffer (the reference writes both immediately);
+//   * gl_draw_model() replaces a whole per-face loop (main.cpp:660-666) by one device draw call.
+#pragma once
+#define TRB_DEVICE_BACKEND 1
+#include <geometry.h>
+#include <tgaimage.h>
+
+#include <limits>
+#include <utility>
+#include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+extern mat<4, 4> ModelView;          // our_gl.h:17
+extern mat<4, 4> Perspective;        // our_gl.h:18
+extern mat<4, 4> Viewport;           // our_gl.h:19
+extern std::vector<double> zbuffer;  // our_gl.h:20 - refreshed by gl_flush / gl_zbuffer_restore
+
+void lookat(const vec3 eye, const vec3 center, const vec3 up);                         // our_gl.cpp:25-41
+void init_perspective(double fov_deg, double aspect, double znear, double zfar);       // our_gl.cpp:44-56
+void init_viewport(int x, int y, int w, int h);                                        // our_gl.cpp:59-69
+void init_zbuffer(int width, int height);  // our_gl.cpp:72-74; also begins a device frame of that size
+
+class Model;
+
+// What a device-resident shader tells the backend about itself.
+struct TrbDeviceShader {
+    int kind = -1;                     // TrbShaderKind
+    double key_dir_eye[3] = {0, 0, 0}, fill_dir_eye[3] = {0, 0, 0}, rim_dir_eye[3] = {0, 0, 0};
+    double normal_map_strength = 1.0;
+    const Model* model = nullptr;      // mesh + textures (materials[0], model.cpp:416-459)
+    const double* varyings = nullptr;  // immediate mode: 3 x {uv.x, uv.y, position_eye.xyz, normal_eye.xyz}
+};
+
+struct IShader {
+    static TGAColor sample2D(const TGAImage& img, const vec2& uv) {  // our_gl.h:38-44
+        int x = std::min<int>(img.width() - 1, std::max<int>(0, int(uv.x * img.width())));
+        int y = std::min<int>(img.height() - 1, std::max<int>(0, int(uv.y * img.height())));
+        return img.get(x, y);
+    }
+    virtual vec4 vertex(int face_index, int vertex_index) { (void)face_index; (void)vertex_index; return vec4(); }
+    virtual std::pair<bool, TGAColor> fragment(const vec3 barycentric) const = 0;
+    // B200 backend: fill `out` and return true when this shader has a device implementation
+    virtual bool device_shader(TrbDeviceShader& out) const { (void)out; return false; }
+    virtual ~IShader() {}
+};
+
+typedef vec<4> Triangle[3];  // our_gl.h:55
+
+// our_gl.cpp:89-201.  Batched; throws std::runtime_error for a shader without device_shader().
+void rasterize(const Triangle& clip, const IShader& shader, TGAImage& framebuffer);
+void print_render_stats();   // our_gl.cpp:204-210 (order-independent counters, see trb.h TrbStats)
+
+// ---- additions of the backend ---------------------------------------------------------------
+// for face in model: clip[v] = shader.vertex(face, v); rasterize(clip, shader, framebuffer)  -> one draw
+void gl_draw_model(const Model& model, const IShader& shader, TGAImage& framebuffer);
+// resolve everything submitted so far: colours into `framebuffer`, depths into the global zbuffer
+void gl_flush(TGAImage& framebuffer);
+// `std::vector<double> saved = zbuffer;` ... `zbuffer = saved;` around a draw (main.cpp:700,730)
+void gl_zbuffer_snapshot();
+void gl_zbuffer_restore(TGAImage& framebuffer);
+// post passes of main.cpp:269-362, 756-786 on the device-resident z-buffer
+void gl_ssao(TGAImage& ao_map);
+void gl_zbuffer_image(TGAImage& grey);
+void gl_composite_ao(TGAImage& final_result);
+struct TrbCtx;
+TrbCtx* gl_context();        // the process-wide device context (device = $TRB_DEVICE, default 0)
+
+// Frustum culling of whole models (our_gl.h:68-86, our_gl.cpp:212-280): host side, bug-for-bug -
+// the planes are extracted from the matrix as if it were transposed.
+struct Frustum {
+    Plane planes[6];
+    enum PlaneIndex { LEFT = 0, RIGHT = 1, BOTTOM = 2, TOP = 3, NEAR = 4, FAR = 5 };
+    static Frustum createFromMatrix(const mat<4, 4>& matrix);
+    bool intersects(const AABB& aabb) const;
+};
