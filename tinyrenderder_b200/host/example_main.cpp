@@ -18,16 +18,7 @@
 #include <string>
 
 #ifdef EXAMPLE_ORACLE
-struct TrbCtx;
-#define TRB_OK 0
-#define TRB_E_ARG -1
-static const double* orc_view_depth(TrbCtx*, int, int* w, int* h);
-static const unsigned char* orc_view_color(TrbCtx*, int);
-static int g_w, g_h;
-static const unsigned char* g_color;
-#include "../../oracle/post_restate.inc"
-static const double* orc_view_depth(TrbCtx*, int, int* w, int* h) { *w = g_w; *h = g_h; return zbuffer.data(); }
-static const unsigned char* orc_view_color(TrbCtx*, int) { return g_color; }
+#include <example_oracle_glue.h>  // test-only: CPU post passes for the oracle build (tests/harness/ref_include)
 #endif
 
 static mat<4, 4> scale_matrix(double s) {  // main.cpp:365-371
