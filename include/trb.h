@@ -221,14 +221,24 @@ TRB_EXPORT int TRB_FN(profile_read)(TrbCtx* ctx, TrbKernelTime* out, int capacit
 TRB_EXPORT uint64_t TRB_FN(launch_count)(TrbCtx* ctx); /* kernels launched since create */
 
 /* ---- multi-GPU sort-last composite (config 4) ----------------------------------------
- * Raw device pointers of view 0's depth-key (uint64, order preserving)
- * and visibility-id (uint32) planes so that the host (torch.distributed / NCCL) can
- * all-reduce them in place; then trb_composite_mask drops local ids that lost. */
+ * Each rank draws a triangle range with global ids (trb_set_triangle_id_base) and does NOT
+ * flush.  Then, with the raw device pointers of view 0's depth-key (uint64) and
+ * visibility-id (uint32) planes from trb_device_planes:
+ *   1. trb_composite_save_local_depth  keeps a copy of the local keys and rewrites the plane as
+ *                                      int64-sortable so that a signed MIN all-reduce is exact;
+ *   2. host: all-reduce(MIN, int64) over the key plane (NCCL over NVLink);
+ *   3. trb_composite_mask              restores the key encoding; ids whose local key lost (or
+ *                                      that are empty) become 0x7FFFFFFF (largest int32);
+ *   4. host: all-reduce(MIN, int32) over the id plane - lowest id = first submitted, the
+ *                                      reference's tie rule (our_gl.cpp:165);
+ *   5. trb_composite_finish            0x7FFFFFFF -> "none"; trb_set_shade_rows + trb_flush shade
+ *                                      the slice this rank owns (every rank holds all meshes). */
 TRB_EXPORT int TRB_FN(device_planes)(TrbCtx* ctx, uint64_t* depth_key_ptr, uint64_t* vis_id_ptr,
                                      uint64_t* npixels);
 TRB_EXPORT int TRB_FN(set_triangle_id_base)(TrbCtx* ctx, uint64_t base);
 TRB_EXPORT int TRB_FN(composite_save_local_depth)(TrbCtx* ctx);
 TRB_EXPORT int TRB_FN(composite_mask)(TrbCtx* ctx);
+TRB_EXPORT int TRB_FN(composite_finish)(TrbCtx* ctx);
 /* restrict flush to rows [y0,y1) (the screen slice this rank owns after the composite) */
 TRB_EXPORT int TRB_FN(set_shade_rows)(TrbCtx* ctx, int y0, int y1);
 

@@ -567,6 +567,7 @@ int orc_device_planes(TrbCtx* c, uint64_t*, uint64_t*, uint64_t*) { return fail(
 int orc_set_triangle_id_base(TrbCtx* c, uint64_t) { return c ? TRB_OK : TRB_E_ARG; }
 int orc_composite_save_local_depth(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_composite_mask(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_composite_finish(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_set_shade_rows(TrbCtx* c, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 
 // ---- host helpers: straight through the reference's own functions ----------------------

@@ -1,0 +1,145 @@
+"""Multi-GPU logic.  CPU: world_size-2 gloo processes exercise the frame sharding of
+config 3 and the sort-last composite protocol of config 4 on the CPU oracle.  GPU: the composite
+entry points of libtrb.so with two 'ranks' emulated as two contexts on one device."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import tinyrenderder_b200 as trb
+from tinyrenderder_b200 import multigpu, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shards_partition_the_work():
+    for total, world in ((1024, 8), (1000, 7), (5, 8), (0, 3)):
+        seen = []
+        for r in range(world):
+            seen += list(multigpu.frame_shard(total, r, world))
+        assert seen == list(range(total))
+    for n, world in ((20971520, 8), (13, 4), (3, 5)):
+        first = 0
+        for r in range(world):
+            f, c = multigpu.triangle_shard(n, r, world)
+            assert f == first
+            first += c
+        assert first == n
+    rows = [multigpu.row_shard(2160, r, 8) for r in range(8)]
+    assert rows[0][0] == 0 and rows[-1][1] == 2160 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    api = trb.Api(os.path.join(ROOT, "oracle", "libtrb_port.so"), "orc")
+    # --- config 3: every rank renders its own frames, nothing is exchanged but the final gather
+    sc = scenes.orbit_scene(160, 90, room_quads=((8, 4), (8, 2), (4, 4)), head_res=(10, 8), eye_res=(6, 4), tex_size=32)
+    pr = api.perspective(sc.fov, 160 / 90, sc.znear, sc.zfar)
+    frames = list(multigpu.frame_shard(6, rank, world))
+    with trb.Renderer(api) as r:
+        up = scenes.UploadedScene(r, sc)
+        up.render(scenes.orbit_views(api, frames, total=6), pr)
+        mine = np.stack([r.read_depth(v) for v in range(len(frames))])
+    gathered = [torch.zeros(3, 90, 160, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(mine))
+    # --- config 4: triangle ranges + sort-last composite (MIN all-reduce of depth, lowest rank on ties)
+    m = scenes.icosphere(3)
+    mv, pr4 = scenes.sphere_view(api), api.perspective(60, 1.5, 0.1, 10)
+    first, count = multigpu.triangle_shard(m.ntris, rank, world)
+    with trb.Renderer(api) as r:
+        h = r.upload_mesh(m.pos, m.nrm, m.uv, m.idx)
+        r.begin_frame(150, 100)
+        r.draw(h, mv, pr4, first_tri=first, ntris=count)
+        r.end_frame()
+        z, c = r.read_depth(), r.read_color()
+    zt = torch.from_numpy(z.copy())
+    dist.all_reduce(zt, op=dist.ReduceOp.MIN)
+    owner = torch.from_numpy(np.where(z == zt.numpy(), rank, world).astype(np.int32))
+    dist.all_reduce(owner, op=dist.ReduceOp.MIN)             # lowest rank among the winners
+    col = torch.from_numpy(np.where((owner.numpy() == rank)[..., None], c, 0).astype(np.int32))
+    dist.all_reduce(col, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "out.npz"), frames=torch.cat(gathered).numpy(), z=zt.numpy(),
+                 c=col.numpy().astype(np.uint8))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path, port_api):
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    out = np.load(tmp_path / "out.npz")
+    api = port_api
+    # config 3: the gathered frames are the frames one process renders alone
+    sc = scenes.orbit_scene(160, 90, room_quads=((8, 4), (8, 2), (4, 4)), head_res=(10, 8), eye_res=(6, 4), tex_size=32)
+    with trb.Renderer(api) as r:
+        up = scenes.UploadedScene(r, sc)
+        up.render(scenes.orbit_views(api, range(6), total=6), api.perspective(sc.fov, 160 / 90, sc.znear, sc.zfar))
+        for v in range(6):
+            assert np.array_equal(out["frames"][v].view(np.uint64), r.read_depth(v).view(np.uint64))
+    # config 4: the composite equals the unsharded render, depth bits and colours
+    m = scenes.icosphere(3)
+    with trb.Renderer(api) as r:
+        h = r.upload_mesh(m.pos, m.nrm, m.uv, m.idx)
+        r.begin_frame(150, 100)
+        r.draw(h, scenes.sphere_view(api), api.perspective(60, 1.5, 0.1, 10), ntris=m.ntris)
+        r.end_frame()
+        assert np.array_equal(out["z"].view(np.uint64), r.read_depth().view(np.uint64))
+        assert np.array_equal(out["c"], r.read_color())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_sort_last_composite_on_one_gpu(cuda_api, port_api, nranks):
+    """N 'ranks' = N contexts on one GPU; the all-reduce is emulated by an element-wise minimum over
+    the ranks' planes (same result as NCCL MIN).  Composite + per-rank row shading == one render."""
+    import torch
+    m = scenes.icosphere(5)
+    w, h = 640, 400
+    mv, pr = scenes.sphere_view(cuda_api), cuda_api.perspective(60, w / h, 0.1, 10)
+    # duplicate the mesh's triangles so that exact depth ties ACROSS ranks exist
+    idx = np.concatenate([m.idx, m.idx])
+    ntris = idx.size // 3
+    rs = [trb.Renderer(cuda_api) for _ in range(nranks)]
+    planes = []
+    for rank, r in enumerate(rs):
+        mesh = r.upload_mesh(m.pos, m.nrm, m.uv, idx)
+        first, count = multigpu.triangle_shard(ntris, rank, nranks)
+        r.begin_frame(w, h)
+        r.set_triangle_id_base(first)
+        r.draw(mesh, mv, pr, first_tri=first, ntris=count)
+        r.composite_save_local_depth()
+        planes.append(multigpu.plane_tensors(r))
+    gmin = torch.stack([p[0] for p in planes]).min(dim=0).values
+    for p in planes:
+        p[0].copy_(gmin)
+    torch.cuda.synchronize()
+    for r in rs:
+        r.composite_mask()
+    imin = torch.stack([p[1] for p in planes]).min(dim=0).values
+    for p in planes:
+        p[1].copy_(imin)
+    torch.cuda.synchronize()
+    color = np.zeros((h, w, 3), np.uint8)
+    depth = np.zeros((h, w))
+    for rank, r in enumerate(rs):
+        r.composite_finish()
+        y0, y1 = multigpu.row_shard(h, rank, nranks)
+        r.set_shade_rows(y0, y1)
+        r.flush()
+        color[y0:y1] = r.read_color()[y0:y1]
+        depth[y0:y1] = r.read_depth()[y0:y1]
+    with trb.Renderer(port_api) as o:
+        mesh = o.upload_mesh(m.pos, m.nrm, m.uv, idx)
+        o.begin_frame(w, h)
+        o.draw(mesh, mv, pr, ntris=ntris)
+        o.end_frame()
+        assert np.array_equal(depth.view(np.uint64), o.read_depth().view(np.uint64))
+        assert np.array_equal(color, o.read_color())
+    for r in rs:
+        r.close()

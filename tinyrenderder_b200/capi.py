@@ -124,6 +124,7 @@ SIGNATURES = {
     "set_triangle_id_base": (C.c_int, [_P, C.c_uint64]),
     "composite_save_local_depth": (C.c_int, [_P]),
     "composite_mask": (C.c_int, [_P]),
+    "composite_finish": (C.c_int, [_P]),
     "set_shade_rows": (C.c_int, [_P, C.c_int, C.c_int]),
     "light_dir_eye": (None, [_P, _P, _P]),
     "lookat": (None, [_P, _P, _P, _P]),
@@ -400,6 +401,9 @@ class Renderer:
 
     def composite_mask(self):
         self._ck(self._fn["composite_mask"](self.h), "composite_mask")
+
+    def composite_finish(self):
+        self._ck(self._fn["composite_finish"](self.h), "composite_finish")
 
     def set_shade_rows(self, y0, y1):
         self._ck(self._fn["set_shade_rows"](self.h, y0, y1), "set_shade_rows")

@@ -691,7 +691,11 @@ __global__ void __launch_bounds__(TPB) k_composite_mask(const unsigned long long
                                                         const unsigned long long* __restrict__ global_key,
                                                         uint32_t* __restrict__ vis, unsigned long long n) {
     unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x;
-    if (i < n && local_key[i] != global_key[i]) vis[i] = VIS_NONE;
+    if (i < n && (local_key[i] != global_key[i] || vis[i] == VIS_NONE)) vis[i] = 0x7FFFFFFFu;  // max int32
+}
+__global__ void __launch_bounds__(TPB) k_composite_finish(uint32_t* __restrict__ vis, unsigned long long n) {
+    unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x;
+    if (i < n && vis[i] == 0x7FFFFFFFu) vis[i] = VIS_NONE;
 }
 __global__ void __launch_bounds__(TPB) k_key_to_sortable_i64(unsigned long long* __restrict__ key, unsigned long long n) {
     // uint64 order -> int64 order (for collectives that only know signed types): flip the top bit

@@ -954,6 +954,19 @@ int trb_composite_mask(TrbCtx* c) {
     CU(cudaStreamSynchronize(c->stream));
     return TRB_OK;
 }
+int trb_composite_finish(TrbCtx* c) {
+    if (!c || !c->in_frame || c->frame.nviews != 1) return fail(c, TRB_E_COMM, "composite_finish: needs a single-view frame");
+    int rc = check_device(c);
+    if (rc) return rc;
+    const unsigned long long n = c->frame.npix;
+    {
+        Launch L(c, "k_composite_finish");
+        k_composite_finish<<<blocks_for(n), TPB, 0, c->stream>>>(c->frame.vis, n);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
 int trb_set_shade_rows(TrbCtx* c, int y0, int y1) {
     if (!c || !c->in_frame || y0 < 0 || y1 < y0 || y1 > c->frame.H) return fail(c, TRB_E_ARG, "set_shade_rows");
     c->shade_row0 = y0;
