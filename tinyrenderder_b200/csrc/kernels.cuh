@@ -55,7 +55,8 @@ struct DrawDev {               // one draw call, kept until flush (the shade ker
     const LitUniforms* uniforms;  // [nviews] or nullptr
     const double* varyings;    // immediate mode: [ntris][24]
     int kind;
-    int _pad;
+    uint32_t mesh_ntris;       // triangles of the whole mesh (ids of ranges other ranks drew map here too)
+    long long mesh_id_base;    // id of mesh triangle g is mesh_id_base + g + 1  (= id_base - first_tri)
 };
 
 __device__ __forceinline__ uint32_t vertex_index(const uint32_t* idx, uint32_t first_tri, uint32_t t, int k) {
@@ -544,11 +545,23 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
                 const uint32_t bse = mid < MAX_SM_DRAWS ? sm_base[mid] : draws[mid].id_base;
                 if (bse < id) lo = mid; else hi = mid - 1;
             }
-            const DrawDev D = draws[lo];
-            const uint32_t t = id - D.id_base - 1u;
-            const uint32_t i0 = vertex_index(D.idx, D.first_tri, t, 0);
-            const uint32_t i1 = vertex_index(D.idx, D.first_tri, t, 1);
-            const uint32_t i2 = vertex_index(D.idx, D.first_tri, t, 2);
+            DrawDev D = draws[lo];
+            uint32_t t = id - D.id_base - 1u;                    // triangle inside the range this context drew
+            if (t >= D.ntris) {
+                // a winner another rank rasterised (sort-last composite): find the draw whose MESH holds it
+                int found = -1;
+                for (int d = 0; d < ndraws && found < 0; ++d) {
+                    const long long g = (long long)id - draws[d].mesh_id_base - 1;
+                    if (g >= 0 && g < (long long)draws[d].mesh_ntris) found = d;
+                }
+                if (found < 0) return;                           // not ours to shade
+                D = draws[found];
+                t = (uint32_t)((long long)id - D.mesh_id_base - 1) - D.first_tri;  // may wrap: first_tri + t is exact mod 2^32
+            }
+            const uint32_t g0 = D.first_tri + t;                 // triangle index in the mesh
+            const uint32_t i0 = vertex_index(D.idx, 0, g0, 0);
+            const uint32_t i1 = vertex_index(D.idx, 0, g0, 1);
+            const uint32_t i2 = vertex_index(D.idx, 0, g0, 2);
             const VRec* vr = D.vrec + (size_t)view * D.nverts;
             const VRec va = load_vrec(vr + i0), vb = load_vrec(vr + i1), vc = load_vrec(vr + i2);
             TriSetup ts;
@@ -568,7 +581,7 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
                     const double* MV = D.mats + (size_t)view * 32;
                     Varyings vy;
                     if (D.varyings) {
-                        const double* q = D.varyings + (size_t)t * 24;
+                        const double* q = D.varyings + (size_t)g0 * 24;
                         for (int k = 0; k < 3; ++k) {
                             vy.u[k] = q[k * 8]; vy.v[k] = q[k * 8 + 1];
                             vy.pos_eye[k] = D3{q[k * 8 + 2], q[k * 8 + 3], q[k * 8 + 4]};

@@ -599,6 +599,8 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
     d.uniforms = dun;
     d.varyings = nullptr;
     d.kind = kind;
+    d.mesh_ntris = (uint32_t)(m.nidx / 3);
+    d.mesh_id_base = (long long)g.id_base - (long long)g.first_tri;
     c->draws.push_back(d);
     c->next_id += ntris;
     return TRB_OK;
@@ -669,6 +671,8 @@ int trb_submit_clip_triangles(TrbCtx* c, const double* clip12, const double* var
     d.uniforms = dun;
     d.varyings = dvary;
     d.kind = kind;
+    d.mesh_ntris = g.ntris;
+    d.mesh_id_base = (long long)g.id_base;
     c->draws.push_back(d);
     c->next_id += n;
     return TRB_OK;
