@@ -52,7 +52,7 @@ int hx_render(int W, int H, const double* viewport,
             double b[3], z, pc[3];
             if (!eval_sample(ts, x, y, b, z)) return -2;
             zkey[p] = depth_key(z);
-            perspective_bary(b, a.w, b_.w, c.w, pc);
+            perspective_bary(b, a.iw, b_.iw, c.iw, pc);
             unsigned char col[3];
             if (kind == 0) shade_flat_bary(pc, col);
             else {

@@ -67,13 +67,13 @@ __device__ __forceinline__ VRec load_vrec(const VRec* p) {
     const double2* q = reinterpret_cast<const double2*>(p);
     double2 a = __ldg(q), b = __ldg(q + 1);
     VRec r;
-    r.sx = a.x; r.sy = a.y; r.z = b.x; r.w = b.y;
+    r.sx = a.x; r.sy = a.y; r.z = b.x; r.iw = b.y;
     return r;
 }
 __device__ __forceinline__ void store_vrec(VRec* p, const VRec& r) {
     double2* q = reinterpret_cast<double2*>(p);
     q[0] = make_double2(r.sx, r.sy);
-    q[1] = make_double2(r.z, r.w);
+    q[1] = make_double2(r.z, r.iw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -139,9 +139,8 @@ constexpr uint32_t BOX_NONE = 0xFFFFFFFFu;
 // Per-triangle raster record written once by k_setup_count and gathered by k_raster through the
 // bins: everything eval_sample needs plus the clamped pixel bbox.  96 bytes = 3 DRAM sectors.
 struct __align__(32) TriRec {
-    double ax, ay, s00, s01, s10, s11, uz, z0, z1, z2;
+    double ax, ay, s00, s01, s10, s11, uz, z0, z1, z2, ruz;
     unsigned short x0, y0, x1, y1;
-    uint32_t pad0, pad1;
 };
 static_assert(sizeof(TriRec) == 96, "TriRec must be 96 bytes");
 
@@ -152,19 +151,23 @@ __device__ __forceinline__ void store_trirec(TriRec* p, const TriSetup& t) {
     q[2] = make_double2(t.s10, t.s11);
     q[3] = make_double2(t.uz, t.z0);
     q[4] = make_double2(t.z1, t.z2);
-    uint4 b;
+    uint2 b;
     b.x = (uint32_t)t.x0 | ((uint32_t)t.y0 << 16);
     b.y = (uint32_t)t.x1 | ((uint32_t)t.y1 << 16);
-    b.z = 0u; b.w = 0u;
-    reinterpret_cast<uint4*>(p)[5] = b;
+    double2 last;
+    last.x = t.ruz;
+    last.y = __longlong_as_double((long long)(((unsigned long long)b.y << 32) | b.x));
+    q[5] = last;
 }
 __device__ __forceinline__ void load_trirec(const TriRec* p, TriSetup& t) {
     const double2* q = reinterpret_cast<const double2*>(p);
     double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
-    uint4 bb = __ldg(reinterpret_cast<const uint4*>(p) + 5);
+    double2 l = __ldg(q + 5);
+    const unsigned long long bbw = (unsigned long long)__double_as_longlong(l.y);
+    const uint32_t bx = (uint32_t)bbw, by = (uint32_t)(bbw >> 32);
     t.ax = a.x; t.ay = a.y; t.s00 = b.x; t.s01 = b.y; t.s10 = c.x; t.s11 = c.y;
-    t.uz = d.x; t.z0 = d.y; t.z1 = e.x; t.z2 = e.y;
-    t.x0 = bb.x & 0xffff; t.y0 = bb.x >> 16; t.x1 = bb.y & 0xffff; t.y1 = bb.y >> 16;
+    t.uz = d.x; t.z0 = d.y; t.z1 = e.x; t.z2 = e.y; t.ruz = l.x;
+    t.x0 = bx & 0xffff; t.y0 = bx >> 16; t.x1 = by & 0xffff; t.y1 = by >> 16;
 }
 
 __device__ __forceinline__ int block_reduce_min(int v, int* sh) {
@@ -407,7 +410,8 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
     __shared__ unsigned long long qk[QCAP];
     __shared__ uint32_t qid[QCAP];
     __shared__ uint8_t qp[QCAP];
-    __shared__ TriRec recs[CHUNK];       // big triangles of the current chunk (pad0 carries the id)
+    __shared__ TriRec recs[CHUNK];       // pixel-owner triangles of the current chunk, bbox clipped to the tile
+    __shared__ uint32_t rec_id[CHUNK];
     __shared__ unsigned int qn, nbig[2];
     __shared__ unsigned long long red[TPB / 32];
 
@@ -446,9 +450,9 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
             const unsigned s = atomicAdd(&nbig[parity], 1u);
             TriRec& B = recs[s];
             B.ax = ts.ax; B.ay = ts.ay; B.s00 = ts.s00; B.s01 = ts.s01; B.s10 = ts.s10; B.s11 = ts.s11;
-            B.uz = ts.uz; B.z0 = ts.z0; B.z1 = ts.z1; B.z2 = ts.z2;
+            B.uz = ts.uz; B.z0 = ts.z0; B.z1 = ts.z1; B.z2 = ts.z2; B.ruz = ts.ruz;
             B.x0 = (unsigned short)cx0; B.y0 = (unsigned short)cy0; B.x1 = (unsigned short)cx1; B.y1 = (unsigned short)cy1;
-            B.pad0 = gid;
+            rec_id[s] = gid;
         }
         if (nsmall >= a.small_min) {
             // ---- small triangles: one thread per triangle, atomics on the tile's keys ------------
@@ -502,11 +506,11 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
             if (px < (int)B.x0 || px > (int)B.x1 || py < (int)B.y0 || py > (int)B.y1) continue;
             TriSetup t2;
             t2.ax = B.ax; t2.ay = B.ay; t2.s00 = B.s00; t2.s01 = B.s01; t2.s10 = B.s10; t2.s11 = B.s11;
-            t2.uz = B.uz; t2.z0 = B.z0; t2.z1 = B.z1; t2.z2 = B.z2;
+            t2.uz = B.uz; t2.z0 = B.z0; t2.z1 = B.z1; t2.z2 = B.z2; t2.ruz = B.ruz;
             double b[3], z;
             if (!eval_sample(t2, px, py, b, z)) continue;
             const unsigned long long k = fragment_key(z);
-            const uint32_t id = B.pad0;
+            const uint32_t id = rec_id[j];
             ++covered;
             if (k < myk) { myk = k; myid = id; }
             else if (k == myk && id < myid) myid = id;
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
             double b[3], z, pc[3];
             if (eval_sample(ts, x, y, b, z)) {          // always true for a recorded winner
                 f.zkey[gp] = depth_key(z);              // exact bits of the reference's zbuffer[idx] (keeps -0.0)
-                perspective_bary(b, va.w, vb.w, vc.w, pc);
+                perspective_bary(b, va.iw, vb.iw, vc.iw, pc);
                 uint8_t col[3];
                 bool write = true;
                 if (D.kind == 0 /*FLAT_BARY*/) {
