@@ -10,7 +10,9 @@
  *   - every call returns int: 0 = ok, <0 = error class (TRB_E_*);
  *     trb_last_error(ctx) returns the CUDA / argument error string.
  *   - the caller owns every host pointer; the library owns device memory behind
- *     opaque handles.  Host buffers may be pageable or pinned.
+ *     opaque handles.  Host buffers may be pageable or pinned; a PINNED buffer handed to
+ *     trb_upload_* must stay unchanged until the next synchronising call (trb_read_*,
+ *     trb_get_stats, trb_synchronize), pageable ones are staged before the call returns.
  *   - matrices are row-major double[16], exactly mat<4,4>::rows of the
  *     reference (geometry.h:155-166), column-vector convention (M*v).
  *   - colours are BGR bytes (TGAColor layout, tgaimage.h:29-63); row y=0 of the

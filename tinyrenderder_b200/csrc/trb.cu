@@ -73,6 +73,30 @@ struct Arena {
     }
 };
 
+// Resource blocks (meshes, textures) are recycled instead of cudaFree'd: cudaFree synchronises the
+// whole device and a caller that re-uploads its scene every frame would pay it each time.  Reuse
+// is safe without a sync because every use of a block is ordered on the context's one stream.
+struct BlockCache {
+    std::vector<std::pair<size_t, void*>> free_blocks;
+    cudaError_t get(void** out, size_t bytes) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        for (size_t i = 0; i < free_blocks.size(); ++i)
+            if (free_blocks[i].first >= bytes && free_blocks[i].first <= bytes + bytes / 8 + 4096) {
+                *out = free_blocks[i].second;
+                free_blocks.erase(free_blocks.begin() + i);
+                return cudaSuccess;
+            }
+        return cudaMalloc(out, bytes);
+    }
+    void put(void* p, size_t bytes) {
+        if (p) free_blocks.emplace_back((bytes + 511) & ~(size_t)511, p);
+    }
+    void release() {
+        for (auto& b : free_blocks) cudaFree(b.second);
+        free_blocks.clear();
+    }
+};
+
 struct Mesh {
     float4* pos4 = nullptr;
     float* attr8 = nullptr;
@@ -106,6 +130,8 @@ struct TrbCtx {
 
     std::vector<Mesh> meshes;
     std::vector<Tex> textures;
+    BlockCache cache;
+    std::vector<float> stage_a, stage_b;  // host staging for the interleaved mesh layouts
 
     // frame
     FrameDev frame{};
@@ -333,8 +359,8 @@ int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, i
     cudaError_t e = cudaSuccess;
     LitUniforms* d = (LitUniforms*)c->arena.alloc(sizeof(LitUniforms) * nviews, e);
     CU(e);
+    // `host` is pageable: the copy is staged before cudaMemcpyAsync returns
     CU(cudaMemcpyAsync(d, host.data(), sizeof(LitUniforms) * nviews, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));  // `host` dies at return; pageable copies are staged, but be explicit
     *dev_out = d;
     return TRB_OK;
 }
@@ -392,6 +418,7 @@ int trb_destroy(TrbCtx* c) {
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.release();
     c->arena.release();
+    c->cache.release();
     for (auto& p : c->prof_pending) {
         cudaEventDestroy(p.a);
         cudaEventDestroy(p.b);
@@ -420,7 +447,10 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
     if (!idx && nidx > nverts) return fail(c, TRB_E_ARG, "upload_mesh: implicit indices exceed nverts");
     // host-side interleave into the two device layouts: float4 positions for the coalesced vertex
     // kernel, 32-byte {pos,nrm,uv} records (one DRAM sector) for the shade kernel's gathers
-    std::vector<float> p4((size_t)nverts * 4), a8((size_t)nverts * 8);
+    std::vector<float>&p4 = c->stage_a, &a8 = c->stage_b;
+    CU(cudaStreamSynchronize(c->stream));  // the staging vectors of the previous upload are free again
+    p4.resize((size_t)nverts * 4);
+    a8.resize((size_t)nverts * 8);
     for (uint32_t v = 0; v < nverts; ++v) {
         float* p = &p4[(size_t)v * 4];
         float* a = &a8[(size_t)v * 8];
@@ -437,29 +467,30 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
     Mesh m;
     m.nverts = nverts;
     m.nidx = nidx;
-    CU(cudaMalloc((void**)&m.pos4, p4.size() * 4));
-    CU(cudaMalloc((void**)&m.attr8, a8.size() * 4));
+    CU(c->cache.get((void**)&m.pos4, p4.size() * 4));
+    CU(c->cache.get((void**)&m.attr8, a8.size() * 4));
     CU(cudaMemcpyAsync(m.pos4, p4.data(), p4.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(m.attr8, a8.data(), a8.size() * 4, cudaMemcpyHostToDevice, c->stream));
     if (idx) {
-        CU(cudaMalloc((void**)&m.idx, nidx * 4));
+        CU(c->cache.get((void**)&m.idx, nidx * 4));
         CU(cudaMemcpyAsync(m.idx, idx, nidx * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    CU(cudaStreamSynchronize(c->stream));
+    // no sync: copies from pageable memory are staged before cudaMemcpyAsync returns, pinned callers
+    // must keep their arrays alive until the next synchronising call (documented in trb.h)
     m.alive = true;
-    c->meshes.push_back(m);
-    *out = c->meshes.size();
+    size_t slot = 0;
+    while (slot < c->meshes.size() && c->meshes[slot].alive) ++slot;  // handles of freed meshes are reused
+    if (slot == c->meshes.size()) c->meshes.push_back(m); else c->meshes[slot] = m;
+    *out = slot + 1;
     return TRB_OK;
 }
 
 int trb_free_mesh(TrbCtx* c, TrbMesh h) {
     if (!c || h == 0 || h > c->meshes.size() || !c->meshes[h - 1].alive) return fail(c, TRB_E_ARG, "free_mesh");
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
     Mesh& m = c->meshes[h - 1];
-    cudaFree(m.pos4);
-    cudaFree(m.attr8);
-    if (m.idx) cudaFree(m.idx);
+    c->cache.put(m.pos4, (size_t)m.nverts * 16);
+    c->cache.put(m.attr8, (size_t)m.nverts * 32);
+    if (m.idx) c->cache.put(m.idx, m.nidx * 4);
     m = Mesh();
     return TRB_OK;
 }
@@ -474,21 +505,21 @@ int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, 
     t.h = h;
     t.bpp = bpp;
     size_t bytes = (size_t)w * h * bpp;
-    CU(cudaMalloc((void**)&t.px, bytes));
+    CU(c->cache.get((void**)&t.px, bytes));
     CU(cudaMemcpyAsync(t.px, texels, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
     t.alive = true;
-    c->textures.push_back(t);
-    *out = c->textures.size();
+    size_t slot = 0;
+    while (slot < c->textures.size() && c->textures[slot].alive) ++slot;
+    if (slot == c->textures.size()) c->textures.push_back(t); else c->textures[slot] = t;
+    *out = slot + 1;
     return TRB_OK;
 }
 
 int trb_free_texture(TrbCtx* c, TrbTex h) {
     if (!c || h == 0 || h > c->textures.size() || !c->textures[h - 1].alive) return fail(c, TRB_E_ARG, "free_texture");
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    cudaFree(c->textures[h - 1].px);
-    c->textures[h - 1] = Tex();
+    Tex& x = c->textures[h - 1];
+    c->cache.put(x.px, (size_t)x.w * x.h * x.bpp);
+    x = Tex();
     return TRB_OK;
 }
 
