@@ -373,24 +373,25 @@ def main():
     e2e = None
     if not args.no_e2e and not sharded_c4:
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
-        color_host = [pin((wl.height, wl.width, 3), torch.uint8) for _ in range(nviews)]
-        depth_host = [pin((wl.height, wl.width), torch.float64) for _ in range(nviews)]
+        # two sets of pinned host buffers: the read-back of step s overlaps the rendering of step s+1
+        color_host = [[pin((wl.height, wl.width, 3), torch.uint8) for _ in range(nviews)] for _ in range(2)]
+        depth_host = [[pin((wl.height, wl.width), torch.float64) for _ in range(nviews)] for _ in range(2)]
         e_steps = max(1, min(args.steps, 3 if wl.name in ("c4", "c5") else args.steps))
 
         def e2e_step(s):
             up2 = wl.scenes.UploadedScene(r, wl.scene)                 # H2D: meshes + textures
             up2.render(wl.views(api, s, rank, world), wl.perspective)  # H2D: matrices, uniforms
-            for v in range(nviews):                                    # D2H: framebuffer + z-buffer
-                r.read_color(v, color_host[v])
-                r.read_depth(v, depth_host[v])
+            r.readback_async(color_host[s & 1], depth_host[s & 1])     # D2H: framebuffer + z-buffer of every frame
             up2.free()
             return up2.h2d_bytes
 
         h2d = e2e_step(0)
+        r.readback_wait()
         barrier()
         t0 = time.perf_counter()
         for s in range(e_steps):
             e2e_step(1 + s)
+        r.readback_wait()                                              # every host buffer is complete here
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")

@@ -203,6 +203,14 @@ TRB_EXPORT int TRB_FN(read_depth)(TrbCtx* ctx, int view, double* z_out);
 /* winning triangle id per pixel BEFORE flush: 0xFFFFFFFF = none, 0 = already shaded,
  * else 1 + global submission index over all draws since begin_frame (diagnostic) */
 TRB_EXPORT int TRB_FN(read_visibility)(TrbCtx* ctx, int view, uint32_t* id_out);
+/* Pipelined readback of EVERY view of the frame: BGR planes into color_out[v] and f64 depths into
+ * depth_out[v] (either array may be NULL).  The frame is resolved and snapshotted into a device
+ * staging area on the context's stream; the device->host copies run on a second stream, so they
+ * overlap the next frame's rendering.  Returns after queueing: the host buffers (pinned, for real
+ * overlap) are valid after trb_readback_wait.  Two readbacks may be in flight; a third call first
+ * waits for the oldest. */
+TRB_EXPORT int TRB_FN(readback_async)(TrbCtx* ctx, uint8_t* const* color_out, double* const* depth_out);
+TRB_EXPORT int TRB_FN(readback_wait)(TrbCtx* ctx);
 TRB_EXPORT int TRB_FN(get_stats)(TrbCtx* ctx, int view, TrbStats* out);
 TRB_EXPORT int TRB_FN(synchronize)(TrbCtx* ctx);
 

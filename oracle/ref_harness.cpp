@@ -525,6 +525,15 @@ int orc_read_depth(TrbCtx* c, int view, double* out) {
     std::memcpy(out, c->views[view].depth.data(), sizeof(double) * c->w * c->h);
     return TRB_OK;
 }
+int orc_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* depth_out) {
+    if (!c || c->views.empty()) return TRB_E_ARG;
+    for (int v = 0; v < c->nviews; ++v) {
+        if (color_out && color_out[v]) orc_read_color(c, v, color_out[v]);
+        if (depth_out && depth_out[v]) orc_read_depth(c, v, depth_out[v]);
+    }
+    return TRB_OK;
+}
+int orc_readback_wait(TrbCtx* c) { return c ? TRB_OK : TRB_E_ARG; }
 int orc_read_visibility(TrbCtx* c, int, uint32_t*) { return fail(c, TRB_E_SHADER, "not in oracle-ref"); }
 int orc_get_stats(TrbCtx* c, int view, TrbStats* out) {
     if (!c || view < 0 || view >= c->nviews || !out) return fail(c, TRB_E_ARG, "get_stats");

@@ -127,3 +127,31 @@ def test_batch_equals_single_frames(cuda_api):
             up.render(views[v:v + 1], pr)
             assert np.array_equal(r.read_depth(0).view(np.uint64), batch[v][0].view(np.uint64))
             assert np.array_equal(r.read_color(0), batch[v][1])
+
+
+def test_pipelined_readback_equals_blocking_reads(cuda_api):
+    """trb_readback_async (copy stream, staging area) returns what trb_read_color/depth return, also
+    when the next frame is rendered while the copies are in flight"""
+    import torch
+    sc = scenes.orbit_scene(320, 180, room_quads=((16, 8), (16, 4), (8, 8)), tex_size=64)
+    pr = cuda_api.perspective(sc.fov, 320 / 180, sc.znear, sc.zfar)
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+    with trb.Renderer(cuda_api) as r:
+        up = scenes.UploadedScene(r, sc)
+        want, got = [], []
+        for step in range(4):
+            views = scenes.orbit_views(cuda_api, [10 * step + 1, 10 * step + 400, 10 * step + 800])
+            up.render(views, pr)
+            want.append([(r.read_depth(v).copy(), r.read_color(v).copy()) for v in range(3)])
+        for step in range(4):
+            views = scenes.orbit_views(cuda_api, [10 * step + 1, 10 * step + 400, 10 * step + 800])
+            cs = [pin((180, 320, 3), torch.uint8) for _ in range(3)]
+            ds = [pin((180, 320), torch.float64) for _ in range(3)]
+            up.render(views, pr)
+            r.readback_async(cs, ds)      # no wait: the next iteration renders while these copy
+            got.append((cs, ds))
+        r.readback_wait()
+        for step in range(4):
+            for v in range(3):
+                assert np.array_equal(got[step][1][v].view(np.uint64), want[step][v][0].view(np.uint64))
+                assert np.array_equal(got[step][0][v], want[step][v][1])

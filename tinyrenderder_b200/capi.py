@@ -113,6 +113,8 @@ SIGNATURES = {
     "read_color": (C.c_int, [_P, C.c_int, _P]),
     "read_depth": (C.c_int, [_P, C.c_int, _P]),
     "read_visibility": (C.c_int, [_P, C.c_int, _P]),
+    "readback_async": (C.c_int, [_P, _P, _P]),
+    "readback_wait": (C.c_int, [_P]),
     "get_stats": (C.c_int, [_P, C.c_int, C.POINTER(Stats)]),
     "synchronize": (C.c_int, [_P]),
     "timer_start": (C.c_int, [_P]),
@@ -337,6 +339,19 @@ class Renderer:
             out = np.empty((self.height, self.width), dtype=np.float64)
         self._ck(self._fn["read_depth"](self.h, view, _ptr(out)), "read_depth")
         return out
+
+    def readback_async(self, colors=None, depths=None):
+        """queue the device->host copy of every view into the given lists of (pinned) numpy arrays"""
+        def table(arrs):
+            if arrs is None:
+                return None
+            t = (C.c_void_p * self.nviews)(*[a.ctypes.data for a in arrs])
+            self._keep.append(t)
+            return C.cast(t, _P)
+        self._ck(self._fn["readback_async"](self.h, table(colors), table(depths)), "readback_async")
+
+    def readback_wait(self):
+        self._ck(self._fn["readback_wait"](self.h), "readback_wait")
 
     def read_visibility(self, view=0):
         out = np.empty((self.height, self.width), dtype=np.uint32)

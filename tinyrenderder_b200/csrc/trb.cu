@@ -149,7 +149,15 @@ struct TrbCtx {
 
     // per-draw scratch (stream ordered reuse)
     DevBuf tribox, trirec, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
-    uint32_t* host_total = nullptr;  // pinned
+    uint32_t* host_total = nullptr;  // pinned + mapped: the scan kernel stores the bin total straight into it
+    uint32_t* host_total_dev = nullptr;
+
+    // pipelined readback
+    cudaStream_t copy_stream = nullptr;
+    DevBuf rb[2];
+    cudaEvent_t rb_ready[2] = {nullptr, nullptr}, rb_done[2] = {nullptr, nullptr};
+    bool rb_inflight[2] = {false, false};
+    int rb_idx = 0;
 
     // timing
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -300,11 +308,12 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
                                                      c->counts.as<uint32_t>());
     }
     CU(cudaGetLastError());
+    // the bin array is sized by the count pass (SURVEY 7 "hard parts": config 5 memory).  The total
+    // is stored by the scan kernel directly into mapped host memory: a cudaMemcpy would queue on
+    // the device->host copy engine behind a pipelined readback (trb_readback_async).
     int rc = exclusive_scan(c, c->counts.as<uint32_t>(), (uint32_t)nslots, c->offsets.as<uint32_t>(),
-                            c->scan_total.as<uint32_t>());
+                            c->host_total_dev);
     if (rc) return rc;
-    // the bin array is sized by the count pass (SURVEY 7 "hard parts": config 5 memory)
-    CU(cudaMemcpyAsync(c->host_total, c->scan_total.p, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const uint32_t R = *c->host_total;
     if (R == 0) return TRB_OK;
@@ -392,7 +401,8 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_SMALL_MIN")) c->small_min = std::max(1, atoi(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_a) != cudaSuccess || cudaEventCreate(&c->ev_b) != cudaSuccess ||
-        cudaMallocHost((void**)&c->host_total, 64) != cudaSuccess) {
+        cudaHostAlloc((void**)&c->host_total, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&c->host_total_dev, c->host_total, 0) != cudaSuccess) {
         delete c;
         return TRB_E_CUDA;
     }
@@ -417,6 +427,15 @@ int trb_destroy(TrbCtx* c) {
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.release();
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < 2; ++i) {
+            c->rb[i].release();
+            cudaEventDestroy(c->rb_ready[i]);
+            cudaEventDestroy(c->rb_done[i]);
+        }
+        cudaStreamDestroy(c->copy_stream);
+    }
     c->arena.release();
     c->cache.release();
     for (auto& p : c->prof_pending) {
@@ -775,6 +794,57 @@ int trb_read_depth(TrbCtx* c, int view, double* out) {
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, c->scratch_b.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+int trb_readback_wait(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    CU(cudaSetDevice(c->device));
+    for (int i = 0; i < 2; ++i)
+        if (c->rb_inflight[i]) {
+            CU(cudaEventSynchronize(c->rb_done[i]));
+            c->rb_inflight[i] = false;
+        }
+    return TRB_OK;
+}
+int trb_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* depth_out) {
+    if (!c || !c->in_frame) return fail(c, TRB_E_ARG, "readback_async: no frame");
+    int rc = do_flush(c);
+    if (rc) return rc;
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&c->rb_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->rb_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int i = (c->rb_idx ^= 1);
+    if (c->rb_inflight[i]) {  // staging area i is still being drained by the copy stream
+        CU(cudaEventSynchronize(c->rb_done[i]));
+        c->rb_inflight[i] = false;
+    }
+    const FrameDev& f = c->frame;
+    const size_t total = (size_t)f.npix * f.nviews;
+    const size_t color_bytes = color_out ? total * 3 : 0, depth_off = (color_bytes + 255) & ~(size_t)255;
+    CU(c->rb[i].ensure(depth_off + (depth_out ? total * 8 : 0), c->stream));
+    uint8_t* stage = c->rb[i].as<uint8_t>();
+    if (color_out) CU(cudaMemcpyAsync(stage, f.color, color_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (depth_out) {
+        Launch L(c, "k_unmap_depth");
+        k_unmap_depth<<<blocks_for(total), TPB, 0, c->stream>>>(f.zkey, total, reinterpret_cast<double*>(stage + depth_off));
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->rb_ready[i], c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->rb_ready[i], 0));
+    for (int v = 0; v < f.nviews; ++v) {
+        if (color_out && color_out[v])
+            CU(cudaMemcpyAsync(color_out[v], stage + (size_t)f.npix * 3 * v, (size_t)f.npix * 3, cudaMemcpyDeviceToHost,
+                               c->copy_stream));
+        if (depth_out && depth_out[v])
+            CU(cudaMemcpyAsync(depth_out[v], stage + depth_off + (size_t)f.npix * 8 * v, (size_t)f.npix * 8,
+                               cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    CU(cudaEventRecord(c->rb_done[i], c->copy_stream));
+    c->rb_inflight[i] = true;
     return TRB_OK;
 }
 int trb_read_visibility(TrbCtx* c, int view, uint32_t* out) {
