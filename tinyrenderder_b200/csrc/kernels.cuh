@@ -204,8 +204,18 @@ __device__ __forceinline__ unsigned long long block_reduce_min64(unsigned long l
     return v;
 }
 
+// Triangles whose WHOLE pixel bbox holds at most `direct_area` samples (the sub-pixel triangles of
+// configs 4 and 5) skip the bins: their fragments go straight to the global depth-key plane with a
+// 64-bit atomicMin, here in the setup kernel; a fragment that strictly lowers a pixel's depth
+// invalidates its id, and k_direct_resolve then gives every pixel the lowest id among the fragments
+// that reached its final depth - the same exact (depth, id) minimum as the tile path, no bins, no
+// barriers.  The tile kernels of the same draw run afterwards and see these pixels as older state.
+constexpr uint32_t BOX_DIRECT = 0xFFFFFFFEu;   // tribox.x of a direct triangle (y: 1 = may own a pixel)
+constexpr int DIRECT_AREA_DEFAULT = 16;
+
 __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uint2* __restrict__ tribox,
-                                                     TriRec* __restrict__ trirec, uint32_t* __restrict__ tile_count) {
+                                                     TriRec* __restrict__ trirec, uint32_t* __restrict__ tile_count,
+                                                     int direct_area) {
     __shared__ int sh_i[TPB / 32];
     __shared__ unsigned long long sh_u[TPB / 32];
     const int view = blockIdx.y;
@@ -230,6 +240,39 @@ __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uin
     uint2 box = make_uint2(BOX_NONE, 0u);
     uint32_t ntile = 0;
     int tx0 = 0, ty0 = 0, tx1 = -1, ty1 = -1;
+    unsigned long long direct_cov = 0, direct_zmin = ~0ull;
+    // Direct only when (nearly) the whole warp holds small triangles in DISTINCT tiles (a random
+    // soup).  Measured on B200: with half of the lanes idle (back faces of a closed mesh) or lanes
+    // hitting the same pixels the two direct passes cost more than the compacted bins of the tile path
+    // (config 4: 1.0 ms binned vs 1.55 ms direct at level 9; config 5: 6.3 ms binned vs 2.7 ms direct).
+    const bool small_tri = res == SETUP_DRAW && (ts.x1 - ts.x0 + 1) * (ts.y1 - ts.y0 + 1) <= direct_area;
+    const unsigned lane_id = threadIdx.x & 31;
+    const unsigned tkey = small_tri ? (unsigned)((ts.y0 >> TILE_SHIFT) * f.tw + (ts.x0 >> TILE_SHIFT)) : (0x80000000u | lane_id);
+    const unsigned same_tile = __match_any_sync(0xffffffffu, tkey);   // every lane takes part: no short-circuit
+    const bool lonely = small_tri && __popc(same_tile) <= 2;
+    const unsigned m_small = __ballot_sync(0xffffffffu, small_tri), m_lonely = __ballot_sync(0xffffffffu, lonely);
+    (void)m_small;
+    if (small_tri && __popc(m_lonely) >= 24) {
+        unsigned long long* zk = f.zkey + (size_t)view * f.npix;
+        uint32_t* vis = f.vis + (size_t)view * f.npix;
+        uint32_t candidate = 0;
+        for (int y = ts.y0; y <= ts.y1; ++y)
+            for (int x = ts.x0; x <= ts.x1; ++x) {
+                double b[3], z;
+                if (!eval_sample(ts, x, y, b, z)) continue;
+                const unsigned long long key = fragment_key(z);
+                const size_t p = (size_t)y * f.W + x;
+                ++direct_cov;
+                direct_zmin = min(direct_zmin, key);
+                if (key <= zk[p]) {
+                    const unsigned long long old = atomicMin(zk + p, key);
+                    if (old > key) vis[p] = VIS_NONE;      // strictly nearer: the old winner is gone
+                    if (old >= key) candidate = 1;
+                }
+            }
+        box = make_uint2(BOX_DIRECT, candidate);
+        res = SETUP_NO_COVERAGE;                            // handled: keep it out of the bins
+    }
     if (res == SETUP_DRAW) {
         tx0 = ts.x0 >> TILE_SHIFT; tx1 = ts.x1 >> TILE_SHIFT;
         ty0 = ts.y0 >> TILE_SHIFT; ty1 = ts.y1 >> TILE_SHIFT;
@@ -239,12 +282,18 @@ __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uin
     }
     if (t < g.ntris) tribox[(size_t)view * g.ntris + t] = box;
     unsigned long long ne = block_reduce_sum(ntile, sh_u);
+    direct_cov = block_reduce_sum(direct_cov, sh_u);
+    direct_zmin = block_reduce_min64(direct_zmin, sh_u);
     if (threadIdx.x == 0 && nb) {
         DevStats* s = f.stats + view;
         atomicMin(&s->bx0, bx0); atomicMin(&s->by0, by0);
         atomicMax(&s->bx1, bx1); atomicMax(&s->by1, by1);
         atomicAdd(&s->tri_binned, nb);
         if (ne) atomicAdd(&s->tile_entries, ne);
+        if (direct_cov) {
+            atomicAdd(&s->frag_covered, direct_cov);
+            atomicMin(&s->zmin_key, direct_zmin);
+        }
     }
     // per-tile counts; single-tile triangles (the common case for small triangles) are aggregated
     // across the warp with match_any so that coherent meshes do not serialise on one counter
@@ -259,6 +308,31 @@ __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uin
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt + ty * f.tw + tx, 1u);
     }
+}
+
+// second half of the direct path: ids of the fragments that sit at a pixel's final depth
+__global__ void __launch_bounds__(TPB) k_direct_resolve(FrameDev f, GeomArgs g, const uint2* __restrict__ tribox) {
+    const int view = blockIdx.y;
+    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+    if (t >= g.ntris) return;
+    const uint2 box = tribox[(size_t)view * g.ntris + t];
+    if (box.x != BOX_DIRECT || box.y == 0u) return;
+    const VRec* vr = g.vrec + (size_t)view * g.nverts;
+    VRec a = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 0));
+    VRec b_ = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 1));
+    VRec c = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 2));
+    TriSetup ts;
+    setup_triangle(a, b_, c, f.W, f.H, ts);
+    const unsigned long long* zk = f.zkey + (size_t)view * f.npix;
+    uint32_t* vis = f.vis + (size_t)view * f.npix;
+    const uint32_t gid = g.id_base + t + 1u;
+    for (int y = ts.y0; y <= ts.y1; ++y)
+        for (int x = ts.x0; x <= ts.x1; ++x) {
+            double b[3], z;
+            if (!eval_sample(ts, x, y, b, z)) continue;
+            const size_t p = (size_t)y * f.W + x;
+            if (fragment_key(z) == zk[p]) atomicMin(vis + p, gid);   // ties: lowest id = first submitted
+        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -345,7 +419,7 @@ __global__ void __launch_bounds__(TPB) k_fill(FrameDev f, uint32_t ntris, const 
     const uint32_t t = blockIdx.x * TPB + threadIdx.x;
     uint2 box = make_uint2(BOX_NONE, 0u);
     if (t < ntris) box = tribox[(size_t)view * ntris + t];
-    const bool has = box.x != BOX_NONE;
+    const bool has = box.x < BOX_DIRECT;   // neither rejected (BOX_NONE) nor handled by the direct path
     const int tx0 = box.x & 0xffff, ty0 = box.x >> 16, tx1 = box.y & 0xffff, ty1 = box.y >> 16;
     const bool single = has && tx0 == tx1 && ty0 == ty1;
     const size_t vbase = (size_t)view * f.ntiles;
@@ -374,17 +448,22 @@ __global__ void __launch_bounds__(TPB) k_fill(FrameDev f, uint32_t ntris, const 
 // fine raster: one CTA owns one 16x16 tile
 //
 // The tile's depth keys and winner ids live in shared memory / registers for the whole bin.
-// Triangles of the bin are taken in chunks of CHUNK.  Per chunk every thread gathers one
-// triangle record, then the chunk is rasterised by one or both of
-//   pixel-owner path  every thread owns one pixel and walks the chunk's (big) triangles from
-//                     shared memory: no atomics, no barriers between triangles;
-//   small path        one thread per (small) triangle walks its <= big_ns-1 samples and resolves
-//                     through shared-memory atomicMin on the depth key + a candidate queue, so
-//                     that the (depth, id) minimum is exact whatever the order.
-// A chunk with only a handful of small triangles sends them down the pixel-owner path too.
+// Triangles of the bin are taken in chunks of CHUNK records; per chunk every thread gathers one
+// triangle record and the chunk's triangles are split by how many samples of the tile their
+// clipped bbox holds (ns):
+//   tiny  (ns < big_ns, and the chunk has enough of them)  one THREAD per triangle walks its samples;
+//   mid   (everything else below large_ns)                 SAMPLE-parallel: the samples of all mid
+//         triangles are laid end to end (prefix sum) and dealt out to the 256 threads, so every
+//         lane evaluates an in-bbox sample whatever the triangle sizes are;
+//   large (ns >= large_ns, about half a tile)              PIXEL-owner: every thread owns one pixel
+//         and walks the large triangles from shared memory - no atomics, no barriers.
+// Tiny and mid fragments resolve through shared-memory atomicMin on the depth key plus a candidate
+// queue and an id atomicMin, which makes the (depth, id) minimum exact whatever the order.
 // ---------------------------------------------------------------------------------------------
 constexpr int CHUNK = TPB;
-constexpr int SMALL_MIN_DEFAULT = 24;   // fewer small triangles than this in a chunk: not worth the atomic phases
+constexpr int SMALL_MIN_DEFAULT = 24;   // fewer tiny triangles than this in a chunk: treat them as mid
+constexpr int LARGE_NS_DEFAULT = 128;   // clipped-bbox samples from which a triangle is pixel-owner
+constexpr int SP_GROUP = 3;             // sample-parallel rounds (of TPB samples) between two resolves
 
 struct RasterArgs {
     uint32_t ntris, id_base;
@@ -392,11 +471,17 @@ struct RasterArgs {
     const uint32_t* counts;   // [nviews][ntiles]
     const uint32_t* offsets;  // [nviews][ntiles]
     const uint32_t* bins;
-    int big_ns, small_min;
+    int big_ns, small_min, large_ns;
+};
+
+struct SpEntry {              // one mid triangle of the chunk in the sample-parallel list
+    uint32_t first;           // index of its first sample in the chunk's sample sequence
+    uint16_t inv;             // ceil(32768 / bw): l / bw == (l * inv) >> 15 for l < 256, bw <= 16
+    uint8_t rec, bw;          // slot in recs[], clipped bbox width
 };
 
 #ifndef TRB_RASTER_MIN_BLOCKS
-#define TRB_RASTER_MIN_BLOCKS 4
+#define TRB_RASTER_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev f, RasterArgs a) {
     const int tile = blockIdx.x, view = blockIdx.y;
@@ -410,9 +495,12 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
     __shared__ unsigned long long qk[QCAP];
     __shared__ uint32_t qid[QCAP];
     __shared__ uint8_t qp[QCAP];
-    __shared__ TriRec recs[CHUNK];       // pixel-owner triangles of the current chunk, bbox clipped to the tile
+    __shared__ TriRec recs[CHUNK];       // mid + large triangles of the current chunk, bbox clipped to the tile
     __shared__ uint32_t rec_id[CHUNK];
-    __shared__ unsigned int qn, nbig[2];
+    __shared__ SpEntry sp[CHUNK];
+    __shared__ uint8_t big_slot[CHUNK];
+    __shared__ uint32_t scan_sh[TPB / 32];
+    __shared__ unsigned int qn, nrec[2], nmid[2], nbig[2];
     __shared__ unsigned long long red[TPB / 32];
 
     const int tid = threadIdx.x;
@@ -423,12 +511,38 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
     unsigned long long myk = pvalid ? f.zkey[gp] : 0ull;   // this thread's pixel
     uint32_t myid = pvalid ? f.vis[gp] : VIS_NONE;
     const unsigned long long k_in = myk;
-    if (tid == 0) { qn = 0; nbig[0] = 0; nbig[1] = 0; }
+    if (tid == 0) { qn = 0; nrec[0] = nrec[1] = 0; nmid[0] = nmid[1] = 0; nbig[0] = nbig[1] = 0; }
     __syncthreads();
 
     const TriRec* tr = a.trirec + (size_t)view * a.ntris;
     uint32_t covered = 0;
     int parity = 0;
+
+    // one fragment of the atomic paths: key min, and a queue entry when it is (for now) the winner
+    auto fragment = [&](unsigned long long k, int p, uint32_t gid) -> bool {
+        if (k <= *(volatile unsigned long long*)&zk[p]) {
+            unsigned long long old = atomicMin(&zk[p], k);
+            if (old >= k) {  // current minimum or a tie: remember who asked
+                unsigned s = atomicAdd(&qn, 1u);
+                if (s >= (unsigned)QCAP) return false;
+                qk[s] = k; qid[s] = gid; qp[s] = (uint8_t)p;
+            }
+        }
+        return true;
+    };
+    // barrier-separated resolve of everything queued so far; returns the block-wide OR of `again`
+    auto resolve = [&](bool again) -> int {
+        __syncthreads();
+        if (zk[tid] != myk) { vid[tid] = VIS_NONE; myk = zk[tid]; }  // strictly nearer: forget the old winner
+        __syncthreads();
+        const unsigned qc = min(qn, (unsigned)QCAP);
+        for (unsigned e = tid; e < qc; e += TPB)
+            if (zk[qp[e]] == qk[e]) atomicMin(&vid[qp[e]], qid[e]);   // ties: lowest id = first submitted
+        const int more = __syncthreads_or(again);
+        if (tid == 0) qn = 0;
+        __syncthreads();
+        return more;
+    };
 
     for (uint32_t base = 0; base < n; base += CHUNK, parity ^= 1) {
         TriSetup ts;
@@ -443,66 +557,97 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
             cy0 = max(ts.y0, ty0); cy1 = min(ts.y1, ty0 + TILE - 1);
             ns = (cx1 - cx0 + 1) * (cy1 - cy0 + 1);
         }
-        bool small = has && ns < a.big_ns;
-        const int nsmall = __syncthreads_count(small);      // also: previous chunk is done with recs[]
-        if (nsmall < a.small_min) small = false;
-        if (has && !small) {
-            const unsigned s = atomicAdd(&nbig[parity], 1u);
+        bool tiny = has && ns < a.big_ns;
+        const int ntiny = __syncthreads_count(tiny);        // also: the previous chunk is done with the lists
+        if (ntiny < a.small_min) tiny = false;
+        const bool large = has && !tiny && ns >= a.large_ns;
+        const bool mid = has && !tiny && !large;
+        if (mid || large) {
+            const unsigned s = atomicAdd(&nrec[parity], 1u);
             TriRec& B = recs[s];
             B.ax = ts.ax; B.ay = ts.ay; B.s00 = ts.s00; B.s01 = ts.s01; B.s10 = ts.s10; B.s11 = ts.s11;
             B.uz = ts.uz; B.z0 = ts.z0; B.z1 = ts.z1; B.z2 = ts.z2; B.ruz = ts.ruz;
             B.x0 = (unsigned short)cx0; B.y0 = (unsigned short)cy0; B.x1 = (unsigned short)cx1; B.y1 = (unsigned short)cy1;
             rec_id[s] = gid;
+            if (large) {
+                big_slot[atomicAdd(&nbig[parity], 1u)] = (uint8_t)s;
+            } else {
+                const unsigned m = atomicAdd(&nmid[parity], 1u);
+                const int bw = cx1 - cx0 + 1;
+                SpEntry e;
+                e.first = (uint32_t)ns;                     // sample count for now; prefix-summed below
+                e.inv = (uint16_t)((32768 + bw - 1) / bw);
+                e.rec = (uint8_t)s;
+                e.bw = (uint8_t)bw;
+                sp[m] = e;
+            }
         }
-        if (nsmall >= a.small_min) {
-            // ---- small triangles: one thread per triangle, atomics on the tile's keys ------------
+        __syncthreads();
+        const unsigned nm = nmid[parity], nb = nbig[parity];
+        if (tid == 0) { nrec[parity ^ 1] = 0; nmid[parity ^ 1] = 0; nbig[parity ^ 1] = 0; }
+        const bool atomics = ntiny >= a.small_min || nm > 0;
+        uint32_t S = 0;
+        if (nm > 0) {   // lay the mid triangles' samples end to end
+            const uint32_t cnt = (unsigned)tid < nm ? sp[tid].first : 0u;
+            const uint32_t ex = block_exclusive_scan(cnt, scan_sh, S);
+            if ((unsigned)tid < nm) sp[tid].first = ex;
+        }
+        if (atomics) {
             zk[tid] = myk; vid[tid] = myid;
             __syncthreads();
-            bool pending = small;
-            int sx = cx0, sy = cy0;  // resume position when the candidate queue fills up
-            for (;;) {
-                bool full = false;
-                if (pending) {
-                    while (sy <= cy1) {
-                        double b[3], z;
-                        if (eval_sample(ts, sx, sy, b, z)) {
-                            const unsigned long long k = fragment_key(z);
-                            const int p = ((sy - ty0) << TILE_SHIFT) | (sx - tx0);
-                            if (k <= *(volatile unsigned long long*)&zk[p]) {
-                                unsigned long long old = atomicMin(&zk[p], k);
-                                if (old >= k) {  // current minimum or a tie: remember who asked
-                                    unsigned s = atomicAdd(&qn, 1u);
-                                    if (s >= (unsigned)QCAP) { full = true; break; }
-                                    qk[s] = k; qid[s] = gid; qp[s] = (uint8_t)p;
-                                }
+            // ---- tiny triangles: one thread per triangle ------------------------------------------------
+            if (ntiny >= a.small_min) {
+                bool pending = tiny;
+                int sx = cx0, sy = cy0;  // resume position when the candidate queue fills up
+                for (;;) {
+                    bool full = false;
+                    if (pending) {
+                        while (sy <= cy1) {
+                            double b[3], z;
+                            if (eval_sample(ts, sx, sy, b, z)) {
+                                if (!fragment(fragment_key(z), ((sy - ty0) << TILE_SHIFT) | (sx - tx0), gid)) { full = true; break; }
+                                ++covered;
                             }
-                            ++covered;
+                            if (++sx > cx1) { sx = cx0; ++sy; }
                         }
-                        if (++sx > cx1) { sx = cx0; ++sy; }
+                        if (!full) pending = false;
                     }
-                    if (!full) pending = false;
+                    if (!resolve(full)) break;
                 }
-                __syncthreads();
-                // a pixel whose depth got strictly smaller forgets its previous winner
-                if (zk[tid] != myk) { vid[tid] = VIS_NONE; myk = zk[tid]; }
-                __syncthreads();
-                const unsigned qc = min(qn, (unsigned)QCAP);
-                for (unsigned e = tid; e < qc; e += TPB)
-                    if (zk[qp[e]] == qk[e]) atomicMin(&vid[qp[e]], qid[e]);  // ties: lowest id = first submitted
-                const int more = __syncthreads_or(full);
-                if (tid == 0) qn = 0;
-                if (!more) break;
-                __syncthreads();
+            }
+            // ---- mid triangles: sample parallel ---------------------------------------------------------
+            for (uint32_t s0 = 0; s0 < S; s0 += SP_GROUP * TPB) {
+                #pragma unroll 1
+                for (int g = 0; g < SP_GROUP; ++g) {
+                    const uint32_t s = s0 + g * TPB + tid;
+                    if (s >= S) break;
+                    unsigned lo = 0, hi = nm;               // last entry with first <= s
+                    while (hi - lo > 1) {
+                        const unsigned m = (lo + hi) >> 1;
+                        if (sp[m].first <= s) lo = m; else hi = m;
+                    }
+                    const SpEntry e = sp[lo];
+                    const TriRec& B = recs[e.rec];
+                    const uint32_t l = s - e.first;
+                    const uint32_t row = (l * e.inv) >> 15;
+                    const int x = (int)B.x0 + (int)(l - row * e.bw), y = (int)B.y0 + (int)row;
+                    TriSetup t2;
+                    t2.ax = B.ax; t2.ay = B.ay; t2.s00 = B.s00; t2.s01 = B.s01; t2.s10 = B.s10; t2.s11 = B.s11;
+                    t2.uz = B.uz; t2.z0 = B.z0; t2.z1 = B.z1; t2.z2 = B.z2; t2.ruz = B.ruz;
+                    double b[3], z;
+                    if (eval_sample(t2, x, y, b, z)) {
+                        fragment(fragment_key(z), ((y - ty0) << TILE_SHIFT) | (x - tx0), rec_id[e.rec]);  // <= 768 per group: fits
+                        ++covered;
+                    }
+                }
+                resolve(false);
             }
             myid = vid[tid];
-        } else {
-            __syncthreads();   // recs[] and nbig[parity] are complete
         }
-        // ---- pixel-owner path: every thread owns its pixel, no atomics -----------------------------
-        const unsigned nb = nbig[parity];
-        if (tid == 0) nbig[parity ^ 1] = 0;   // nobody touches the other counter before the next chunk's barrier
+        // ---- large triangles: every thread owns its pixel, no atomics -----------------------------------
         for (unsigned j = 0; j < nb; ++j) {
-            const TriRec& B = recs[j];
+            const unsigned slot = big_slot[j];
+            const TriRec& B = recs[slot];
             if (px < (int)B.x0 || px > (int)B.x1 || py < (int)B.y0 || py > (int)B.y1) continue;
             TriSetup t2;
             t2.ax = B.ax; t2.ay = B.ay; t2.s00 = B.s00; t2.s01 = B.s01; t2.s10 = B.s10; t2.s11 = B.s11;
@@ -510,7 +655,7 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
             double b[3], z;
             if (!eval_sample(t2, px, py, b, z)) continue;
             const unsigned long long k = fragment_key(z);
-            const uint32_t id = rec_id[j];
+            const uint32_t id = rec_id[slot];
             ++covered;
             if (k < myk) { myk = k; myid = id; }
             else if (k == myk && id < myid) myid = id;

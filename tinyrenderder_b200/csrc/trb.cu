@@ -166,7 +166,8 @@ struct TrbCtx {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<ProfAcc> prof_acc;
     uint64_t launches = 0;
-    int big_ns = BIG_NS_DEFAULT, small_min = SMALL_MIN_DEFAULT;
+    int big_ns = BIG_NS_DEFAULT, small_min = SMALL_MIN_DEFAULT, large_ns = LARGE_NS_DEFAULT;
+    int direct_area = DIRECT_AREA_DEFAULT;
 };
 
 namespace {
@@ -305,7 +306,11 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     {
         Launch L(c, "k_setup_count");
         k_setup_count<<<tgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
-                                                     c->counts.as<uint32_t>());
+                                                     c->counts.as<uint32_t>(), c->direct_area);
+    }
+    if (c->direct_area > 0) {
+        Launch L(c, "k_direct_resolve");
+        k_direct_resolve<<<tgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>());
     }
     CU(cudaGetLastError());
     // the bin array is sized by the count pass (SURVEY 7 "hard parts": config 5 memory).  The total
@@ -332,6 +337,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     ra.bins = c->bins.as<uint32_t>();
     ra.big_ns = c->big_ns;
     ra.small_min = c->small_min;
+    ra.large_ns = c->large_ns;
     {
         Launch L(c, "k_raster");
         k_raster<<<dim3(f.ntiles, f.nviews), TPB, 0, c->stream>>>(f, ra);
@@ -399,6 +405,8 @@ int trb_create(int device, TrbCtx** out) {
     c->device = device;
     if (const char* e = getenv("TRB_BIG_NS")) c->big_ns = std::max(1, atoi(e));
     if (const char* e = getenv("TRB_SMALL_MIN")) c->small_min = std::max(1, atoi(e));
+    if (const char* e = getenv("TRB_LARGE_NS")) c->large_ns = std::max(1, atoi(e));
+    if (const char* e = getenv("TRB_DIRECT_AREA")) c->direct_area = std::max(0, atoi(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_a) != cudaSuccess || cudaEventCreate(&c->ev_b) != cudaSuccess ||
         cudaHostAlloc((void**)&c->host_total, 64, cudaHostAllocMapped) != cudaSuccess ||
