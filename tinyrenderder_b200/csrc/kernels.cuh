@@ -29,6 +29,9 @@ constexpr int BIG_NS_DEFAULT = 16;     // triangles covering >= this many sample
 
 struct DevStats {
     unsigned long long tri_binned, tile_entries, frag_covered, pixels_shaded;
+    unsigned long long touched;   // upper bound of the pixels with an unshaded winner (picks the shade kernel)
+    unsigned long long list_len;  // length of the compacted pixel list of the current flush
+    int shade_mode;               // 1: sparse frame, shade through the list; 0: dense, one thread per pixel
     int bx0, by0, bx1, by1;
     unsigned long long zmin_key, zmax_key;
 };
@@ -92,6 +95,8 @@ __global__ void __launch_bounds__(TPB) k_clear(FrameDev f, uint8_t cb, uint8_t c
     for (int v = threadIdx.x; blockIdx.x == 0 && v < f.nviews; v += TPB) {
         DevStats s;
         s.tri_binned = s.tile_entries = s.frag_covered = s.pixels_shaded = 0;
+        s.touched = s.list_len = 0;
+        s.shade_mode = 0;
         s.bx0 = s.by0 = INT_MAX;
         s.bx1 = s.by1 = INT_MIN;
         s.zmin_key = ~0ull;
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uin
         if (ne) atomicAdd(&s->tile_entries, ne);
         if (direct_cov) {
             atomicAdd(&s->frag_covered, direct_cov);
+            atomicAdd(&s->touched, direct_cov);
             atomicMin(&s->zmin_key, direct_zmin);
         }
     }
@@ -511,6 +517,7 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
     unsigned long long myk = pvalid ? f.zkey[gp] : 0ull;   // this thread's pixel
     uint32_t myid = pvalid ? f.vis[gp] : VIS_NONE;
     const unsigned long long k_in = myk;
+    const uint32_t id_in = myid;
     if (tid == 0) { qn = 0; nrec[0] = nrec[1] = 0; nmid[0] = nmid[1] = 0; nbig[0] = nbig[1] = 0; }
     __syncthreads();
 
@@ -666,94 +673,175 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
     // min_z of our_gl.cpp:197: the smallest drawn depth.  A pixel's new key is the minimum of this
     // draw's fragments there, and fragments that lost to an older, smaller depth cannot be the minimum.
     const unsigned long long zmin = block_reduce_min64(myk != k_in ? myk : ~0ull, red);
+    const unsigned long long touched = block_reduce_sum((myid != id_in && pvalid) ? 1ull : 0ull, red);
     if (tid == 0 && total) {
         atomicAdd(&f.stats[view].frag_covered, total);
         atomicMin(&f.stats[view].zmin_key, zmin);
+        if (touched) atomicAdd(&f.stats[view].touched, touched);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // flush: the fragment() calls of our_gl.cpp:187-192, once per visible pixel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __restrict__ draws, int ndraws, int row0,
-                                               int row1) {
-    constexpr int MAX_SM_DRAWS = 32;
-    __shared__ uint32_t sm_base[MAX_SM_DRAWS];
-    for (int i = threadIdx.x; i < ndraws && i < MAX_SM_DRAWS; i += TPB) sm_base[i] = draws[i].id_base;
+constexpr int SHADE_MAX_SM_DRAWS = 32;
+constexpr int SHADE_PX_PER_THREAD = 4;   // one 16-byte id load per thread: sparse frames (configs 4, 5) stay cheap
+
+// one visible pixel: p = x + y*W inside `view`, id = its winning triangle
+__device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
+                                            const uint32_t* sm_base, int view, unsigned long long p, uint32_t id) {
+    constexpr int MAX_SM_DRAWS = SHADE_MAX_SM_DRAWS;
+    const size_t gp = (size_t)view * f.npix + p;
+    int lo = 0, hi = ndraws - 1;  // last draw with id_base < id
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        const uint32_t bse = mid < MAX_SM_DRAWS ? sm_base[mid] : draws[mid].id_base;
+        if (bse < id) lo = mid; else hi = mid - 1;
+    }
+    DrawDev D = draws[lo];
+    uint32_t t = id - D.id_base - 1u;                    // triangle inside the range this context drew
+    if (t >= D.ntris) {
+        // a winner another rank rasterised (sort-last composite): find the draw whose MESH holds it
+        int found = -1;
+        for (int d = 0; d < ndraws && found < 0; ++d) {
+            const long long g = (long long)id - draws[d].mesh_id_base - 1;
+            if (g >= 0 && g < (long long)draws[d].mesh_ntris) found = d;
+        }
+        if (found < 0) return;                           // not ours to shade
+        D = draws[found];
+        t = (uint32_t)((long long)id - D.mesh_id_base - 1) - D.first_tri;  // may wrap: first_tri + t is exact mod 2^32
+    }
+    const uint32_t g0 = D.first_tri + t;                 // triangle index in the mesh
+    const uint32_t i0 = vertex_index(D.idx, 0, g0, 0);
+    const uint32_t i1 = vertex_index(D.idx, 0, g0, 1);
+    const uint32_t i2 = vertex_index(D.idx, 0, g0, 2);
+    const VRec* vr = D.vrec + (size_t)view * D.nverts;
+    const VRec va = load_vrec(vr + i0), vb = load_vrec(vr + i1), vc = load_vrec(vr + i2);
+    TriSetup ts;
+    setup_triangle(va, vb, vc, f.W, f.H, ts);
+    const int x = (int)(p % f.W), y = (int)(p / f.W);
+    double b[3], z, pc[3];
+    if (eval_sample(ts, x, y, b, z)) {          // always true for a recorded winner
+        f.zkey[gp] = depth_key(z);              // exact bits of the reference's zbuffer[idx] (keeps -0.0)
+        perspective_bary(b, va.iw, vb.iw, vc.iw, pc);
+        uint8_t col[3];
+        bool write = true;
+        if (D.kind == 0 /*FLAT_BARY*/) {
+            shade_flat_bary(pc, col);
+        } else if (D.kind == 3 /*DEPTH*/) {
+            write = false;
+        } else {
+            const double* MV = D.mats + (size_t)view * 32;
+            Varyings vy;
+            if (D.varyings) {
+                const double* q = D.varyings + (size_t)g0 * 24;
+                for (int k = 0; k < 3; ++k) {
+                    vy.u[k] = q[k * 8]; vy.v[k] = q[k * 8 + 1];
+                    vy.pos_eye[k] = D3{q[k * 8 + 2], q[k * 8 + 3], q[k * 8 + 4]};
+                    vy.nrm_eye[k] = D3{q[k * 8 + 5], q[k * 8 + 6], q[k * 8 + 7]};
+                }
+            } else {
+                const uint32_t vi[3] = {i0, i1, i2};
+                for (int k = 0; k < 3; ++k) {
+                    const float4* q = reinterpret_cast<const float4*>(D.attr8 + (size_t)vi[k] * 8);
+                    float4 q0 = __ldg(q), q1 = __ldg(q + 1);
+                    float at[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    varyings_from_attr(MV, at, k, vy);
+                }
+            }
+            shade_lit(D.kind == 2 /*EYE*/, MV, D.uniforms[view], vy, pc, col);
+        }
+        if (write) {
+            uint8_t* c = f.color + gp * 3;
+            c[0] = col[0]; c[1] = col[1]; c[2] = col[2];
+        }
+    }
+}
+
+// The flush picks its kernel on the device (no host round trip): sparse frames (configs 4, 5) shade
+// through a compacted pixel list so that warps stay full, dense frames take one thread per pixel.
+__global__ void k_shade_decide(FrameDev f, unsigned long long rows_px) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < f.nviews; v += gridDim.x * blockDim.x) {
+        DevStats* s = f.stats + v;
+        s->shade_mode = (s->touched * 2 < rows_px) ? 1 : 0;
+        s->touched = 0;
+        s->list_len = 0;
+    }
+}
+
+// Pass 1 of the flush: compact the pixels that have an unshaded winner into a dense list (one
+// 16-byte id load per thread, one atomicAdd per warp), so that the expensive shade pass runs with
+// full warps however sparse the frame is (config 5 touches ~10 % of its 67 M pixels).
+__global__ void __launch_bounds__(TPB) k_shade_collect(FrameDev f, int row0, int row1, uint32_t* __restrict__ list) {
+    const int view = blockIdx.y;
+    if (!f.stats[view].shade_mode) return;
+    unsigned long long* count = &f.stats[view].list_len;
+    const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
+    const unsigned long long p0 = first + ((unsigned long long)blockIdx.x * TPB + threadIdx.x) * SHADE_PX_PER_THREAD;
+    const uint32_t* vis = f.vis + (size_t)view * f.npix;
+    uint32_t ids[SHADE_PX_PER_THREAD];
+    for (int j = 0; j < SHADE_PX_PER_THREAD; ++j) ids[j] = VIS_NONE;
+    if (p0 < last) {
+        if (p0 + SHADE_PX_PER_THREAD <= last && ((reinterpret_cast<uintptr_t>(vis + p0) & 15) == 0)) {
+            const uint4 v = *reinterpret_cast<const uint4*>(vis + p0);
+            ids[0] = v.x; ids[1] = v.y; ids[2] = v.z; ids[3] = v.w;
+        } else {
+            for (int j = 0; j < SHADE_PX_PER_THREAD; ++j)
+                if (p0 + j < last) ids[j] = vis[p0 + j];
+        }
+    }
+    unsigned mine = 0;
+    for (int j = 0; j < SHADE_PX_PER_THREAD; ++j) mine += (ids[j] != VIS_NONE && ids[j] != VIS_SHADED) ? 1u : 0u;
+    // warp-aggregated append
+    const unsigned lane = threadIdx.x & 31;
+    unsigned incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += y;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(count, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint32_t* out = list + (size_t)view * f.npix + base + (incl - mine);
+    for (int j = 0; j < SHADE_PX_PER_THREAD; ++j)
+        if (ids[j] != VIS_NONE && ids[j] != VIS_SHADED) *out++ = (uint32_t)(p0 + j);
+}
+
+// Dense frames (most pixels have an unshaded winner): one thread per pixel, no list
+__global__ void __launch_bounds__(TPB, 3) k_shade_dense(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
+                                                     int row0, int row1) {
+    if (f.stats[blockIdx.y].shade_mode) return;
+    __shared__ uint32_t sm_base[SHADE_MAX_SM_DRAWS];
+    for (int i = threadIdx.x; i < ndraws && i < SHADE_MAX_SM_DRAWS; i += TPB) sm_base[i] = draws[i].id_base;
     __syncthreads();
     const int view = blockIdx.y;
     const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
     const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
-    if (p < last) {
-        const size_t gp = (size_t)view * f.npix + p;
-        const uint32_t id = f.vis[gp];
-        if (id != VIS_NONE && id != VIS_SHADED) {
-            int lo = 0, hi = ndraws - 1;  // last draw with id_base < id
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                const uint32_t bse = mid < MAX_SM_DRAWS ? sm_base[mid] : draws[mid].id_base;
-                if (bse < id) lo = mid; else hi = mid - 1;
-            }
-            DrawDev D = draws[lo];
-            uint32_t t = id - D.id_base - 1u;                    // triangle inside the range this context drew
-            if (t >= D.ntris) {
-                // a winner another rank rasterised (sort-last composite): find the draw whose MESH holds it
-                int found = -1;
-                for (int d = 0; d < ndraws && found < 0; ++d) {
-                    const long long g = (long long)id - draws[d].mesh_id_base - 1;
-                    if (g >= 0 && g < (long long)draws[d].mesh_ntris) found = d;
-                }
-                if (found < 0) return;                           // not ours to shade
-                D = draws[found];
-                t = (uint32_t)((long long)id - D.mesh_id_base - 1) - D.first_tri;  // may wrap: first_tri + t is exact mod 2^32
-            }
-            const uint32_t g0 = D.first_tri + t;                 // triangle index in the mesh
-            const uint32_t i0 = vertex_index(D.idx, 0, g0, 0);
-            const uint32_t i1 = vertex_index(D.idx, 0, g0, 1);
-            const uint32_t i2 = vertex_index(D.idx, 0, g0, 2);
-            const VRec* vr = D.vrec + (size_t)view * D.nverts;
-            const VRec va = load_vrec(vr + i0), vb = load_vrec(vr + i1), vc = load_vrec(vr + i2);
-            TriSetup ts;
-            setup_triangle(va, vb, vc, f.W, f.H, ts);
-            const int x = (int)(p % f.W), y = (int)(p / f.W);
-            double b[3], z, pc[3];
-            if (eval_sample(ts, x, y, b, z)) {          // always true for a recorded winner
-                f.zkey[gp] = depth_key(z);              // exact bits of the reference's zbuffer[idx] (keeps -0.0)
-                perspective_bary(b, va.iw, vb.iw, vc.iw, pc);
-                uint8_t col[3];
-                bool write = true;
-                if (D.kind == 0 /*FLAT_BARY*/) {
-                    shade_flat_bary(pc, col);
-                } else if (D.kind == 3 /*DEPTH*/) {
-                    write = false;
-                } else {
-                    const double* MV = D.mats + (size_t)view * 32;
-                    Varyings vy;
-                    if (D.varyings) {
-                        const double* q = D.varyings + (size_t)g0 * 24;
-                        for (int k = 0; k < 3; ++k) {
-                            vy.u[k] = q[k * 8]; vy.v[k] = q[k * 8 + 1];
-                            vy.pos_eye[k] = D3{q[k * 8 + 2], q[k * 8 + 3], q[k * 8 + 4]};
-                            vy.nrm_eye[k] = D3{q[k * 8 + 5], q[k * 8 + 6], q[k * 8 + 7]};
-                        }
-                    } else {
-                        const uint32_t vi[3] = {i0, i1, i2};
-                        for (int k = 0; k < 3; ++k) {
-                            const float4* q = reinterpret_cast<const float4*>(D.attr8 + (size_t)vi[k] * 8);
-                            float4 q0 = __ldg(q), q1 = __ldg(q + 1);
-                            float at[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                            varyings_from_attr(MV, at, k, vy);
-                        }
-                    }
-                    shade_lit(D.kind == 2 /*EYE*/, MV, D.uniforms[view], vy, pc, col);
-                }
-                if (write) {
-                    uint8_t* c = f.color + gp * 3;
-                    c[0] = col[0]; c[1] = col[1]; c[2] = col[2];
-                }
-            }
-            f.vis[gp] = VIS_SHADED;
-        }
+    if (p >= last) return;
+    uint32_t* vis = f.vis + (size_t)view * f.npix;
+    const uint32_t id = vis[p];
+    if (id == VIS_NONE || id == VIS_SHADED) return;
+    shade_pixel(f, draws, ndraws, sm_base, view, p, id);
+    vis[p] = VIS_SHADED;
+}
+
+// Sparse frames, pass 2: persistent grid-stride loop over the compacted list
+__global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
+                                               const uint32_t* __restrict__ list) {
+    if (!f.stats[blockIdx.y].shade_mode) return;
+    __shared__ uint32_t sm_base[SHADE_MAX_SM_DRAWS];
+    for (int i = threadIdx.x; i < ndraws && i < SHADE_MAX_SM_DRAWS; i += TPB) sm_base[i] = draws[i].id_base;
+    __syncthreads();
+    const int view = blockIdx.y;
+    const unsigned long long n = f.stats[view].list_len;
+    const uint32_t* mylist = list + (size_t)view * f.npix;
+    uint32_t* vis = f.vis + (size_t)view * f.npix;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * TPB) {
+        const uint32_t p = mylist[i];
+        shade_pixel(f, draws, ndraws, sm_base, view, p, vis[p]);
+        vis[p] = VIS_SHADED;
     }
 }
 

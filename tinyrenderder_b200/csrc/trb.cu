@@ -148,9 +148,10 @@ struct TrbCtx {
     int shade_row0 = 0, shade_row1 = -1;
 
     // per-draw scratch (stream ordered reuse)
-    DevBuf tribox, trirec, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
+    DevBuf shade_list, tribox, trirec, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
     uint32_t* host_total = nullptr;  // pinned + mapped: the scan kernel stores the bin total straight into it
     uint32_t* host_total_dev = nullptr;
+
 
     // pipelined readback
     cudaStream_t copy_stream = nullptr;
@@ -257,10 +258,30 @@ int do_flush(TrbCtx* c) {
         r1 = c->shade_row1;
     }
     if (r1 > r0) {
-        unsigned long long n = (unsigned long long)(r1 - r0) * c->frame.W;
-        dim3 grid(blocks_for(n), c->frame.nviews);
-        Launch L(c, "k_shade");
-        k_shade<<<grid, TPB, 0, c->stream>>>(c->frame, c->draw_table.as<DrawDev>(), (int)c->draws.size(), r0, r1);
+        const FrameDev& f = c->frame;
+        const unsigned long long n = (unsigned long long)(r1 - r0) * f.W;
+        CU(c->shade_list.ensure((size_t)f.npix * f.nviews * 4, c->stream));
+        {
+            Launch L(c, "k_shade_decide");
+            k_shade_decide<<<(f.nviews + TPB - 1) / TPB, TPB, 0, c->stream>>>(f, n);
+        }
+        {   // sparse views only (device-side predicate)
+            dim3 grid(blocks_for((n + SHADE_PX_PER_THREAD - 1) / SHADE_PX_PER_THREAD), f.nviews);
+            Launch L(c, "k_shade_collect");
+            k_shade_collect<<<grid, TPB, 0, c->stream>>>(f, r0, r1, c->shade_list.as<uint32_t>());
+        }
+        {
+            unsigned per_view = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(
+                blocks_for(n), (148ull * 3 * 4 + f.nviews - 1) / f.nviews));
+            Launch L(c, "k_shade");
+            k_shade<<<dim3(per_view, f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(), (int)c->draws.size(),
+                                                                      c->shade_list.as<uint32_t>());
+        }
+        {   // dense views only
+            Launch L(c, "k_shade_dense");
+            k_shade_dense<<<dim3(blocks_for(n), f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
+                                                                                (int)c->draws.size(), r0, r1);
+        }
     }
     CU(cudaGetLastError());
     // the pageable->device copy of the table is staged before cudaMemcpyAsync returns, so the
@@ -430,7 +451,7 @@ int trb_destroy(TrbCtx* c) {
         }
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
-    DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->tribox, &c->trirec,
+    DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
                       &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->scratch_a,
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
