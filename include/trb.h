@@ -181,6 +181,8 @@ TRB_EXPORT int TRB_FN(depth_snapshot)(TrbCtx* ctx);
 TRB_EXPORT int TRB_FN(depth_restore)(TrbCtx* ctx);
 /* keep the current depth buffer of view 0 as a shadow map for later frames */
 TRB_EXPORT int TRB_FN(keep_depth_as_shadow_map)(TrbCtx* ctx, int32_t* out_index);
+/* drop every kept shadow map (indices restart at 0) */
+TRB_EXPORT int TRB_FN(release_shadow_maps)(TrbCtx* ctx);
 
 /* resolve visibility -> colour (the fragment() calls of our_gl.cpp:187-192, run once per
  * visible pixel).  Implied by end_frame / read_color / depth_restore. */

@@ -97,11 +97,20 @@ struct Varyings {  // the per-triangle state PhongShader::vertex leaves behind, 
     double uv[3][2];
     D3 pos_eye[3];
     D3 nrm_eye[3];
+    double light_clip[3][4];   // SHADOW_PHONG only
+};
+
+struct ShadowEnv {   // SHADOW_PHONG, authored in ref_harness.cpp (ShadowPhongAuthored)
+    M4 lmv{}, lpr{}, lvp{};
+    double bias = 0, darkening = 1;
+    const std::vector<double>* map = nullptr;
+    int w = 0, h = 0;
 };
 
 struct ShadeEnv {
     int kind = 0;
     M4 modelview{};
+    ShadowEnv shadow;
     TrbPhongUniforms u{};
     const Tex* diffuse = nullptr;
     const Tex* normal = nullptr;
@@ -155,7 +164,31 @@ void shade(const ShadeEnv& e, const Varyings& v, const double b[3], uint8_t out[
     sample_diffuse(e, uv, base);
     D3 key = light(e.u.key_dir_eye), fill = light(e.u.fill_dir_eye), rim = light(e.u.rim_dir_eye);
 
-    if (e.kind == TRB_SHADER_PHONG) {  // main.cpp:92-170
+    if (e.kind == TRB_SHADER_GOURAUD) {  // GouraudAuthored in ref_harness.cpp
+        double vi[3];
+        for (int k = 0; k < 3; ++k) vi[k] = max_d(0.0, dot3(normalize3(v.nrm_eye[k]), key));
+        double I = vi[0] * b[0] + vi[1] * b[1] + vi[2] * b[2];
+        for (int ch = 0; ch < 3; ++ch) out[ch] = (unsigned char)min_d(255.0, (double)base[ch] * (0.1 + I));
+        return;
+    }
+    double sf = 1.0;
+    if (e.kind == TRB_SHADER_SHADOW_PHONG) {  // ShadowPhongAuthored::shadow_factor
+        const ShadowEnv& S = e.shadow;
+        double c[4];
+        for (int k = 0; k < 4; ++k) c[k] = v.light_clip[0][k] * b[0] + v.light_clip[1][k] * b[1] + v.light_clip[2][k] * b[2];
+        if (c[3] > 1e-12) {
+            double ndc[4] = {c[0] / c[3], c[1] / c[3], c[2] / c[3], c[3] / c[3]};
+            double sx = dot4(S.lvp.m[0], ndc), sy = dot4(S.lvp.m[1], ndc);
+            if (sx >= 0.0 && sy >= 0.0) {
+                int ix = x86_int(sx), iy = x86_int(sy);
+                if (ix >= 0 && iy >= 0 && ix < S.w && iy < S.h) {
+                    double zs = (*S.map)[(size_t)ix + (size_t)iy * S.w];
+                    if (ndc[2] > zs + S.bias) sf = S.darkening;
+                }
+            }
+        }
+    }
+    if (e.kind == TRB_SHADER_PHONG || e.kind == TRB_SHADER_SHADOW_PHONG) {  // main.cpp:92-170
         double spec_pow = max_d(1.0, (double)sample_specular(e, uv));
         double brightness = (base[0] + base[1] + base[2]) / (3.0 * 255.0);
         bool eye_px = (brightness >= 0.85) && (spec_pow <= 5.0);
@@ -175,7 +208,7 @@ void shade(const ShadeEnv& e, const Varyings& v, const double b[3], uint8_t out[
         double diff = key_d + fill_d + rim_d;
         for (int ch = 0; ch < 3; ++ch) {
             double cv = base[ch];
-            double val = cv * (0.10 + diff) + 255.0 * (0.35 * key_s);
+            double val = cv * (0.10 + diff * sf) + 255.0 * ((0.35 * key_s) * sf);
             out[ch] = (unsigned char)min_d(255.0, val);
         }
     } else {  // EYE, main.cpp:220-261
@@ -305,6 +338,8 @@ struct TrbCtx {
     std::vector<View> views;
     std::vector<std::unique_ptr<Mesh>> meshes;
     std::vector<std::unique_ptr<Tex>> textures;
+    struct ShadowMapCopy { std::vector<double> z; int w, h; };
+    std::vector<ShadowMapCopy> shadow_maps;
     int threads = 1;
 };
 
@@ -341,6 +376,11 @@ void draw_face(TrbCtx* c, View& view, const Mesh& m, const M4& mv, const M4& pr,
         mul_mv(mv, n, ne);
         vy.nrm_eye[k] = D3{ne[0], ne[1], ne[2]};
         mul_mv(pr, pe, clip[k]);
+        if (env.kind == TRB_SHADER_SHADOW_PHONG) {
+            double le[4];
+            mul_mv(env.shadow.lmv, p, le);
+            mul_mv(env.shadow.lpr, le, vy.light_clip[k]);
+        }
     }
     rasterize_port(view, c->w, c->h, c->viewport, clip, env, vy, write_color);
 }
@@ -439,7 +479,25 @@ static int make_env(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, in
                     ShadeEnv& env) {
     env.kind = kind;
     if (mv) env.modelview = load_mat(mv);
-    if (kind == TRB_SHADER_PHONG || kind == TRB_SHADER_EYE) {
+    if (kind == TRB_SHADER_SHADOW_PHONG) {
+        if (!uniforms || ubytes != sizeof(TrbShadowUniforms)) return fail(c, TRB_E_ARG, "draw: uniforms");
+        const TrbShadowUniforms& su = ((const TrbShadowUniforms*)uniforms)[vi];
+        if (su.shadow_map < 0 || (size_t)su.shadow_map >= c->shadow_maps.size()) return fail(c, TRB_E_ARG, "draw: shadow map");
+        const auto& sm = c->shadow_maps[su.shadow_map];
+        if (sm.w != su.shadow_w || sm.h != su.shadow_h) return fail(c, TRB_E_ARG, "draw: shadow map size");
+        env.u = su.phong;
+        env.diffuse = tex_of(c, env.u.diffuse);
+        env.normal = tex_of(c, env.u.normal);
+        env.specular = tex_of(c, env.u.specular);
+        env.shadow.lmv = load_mat(su.light_modelview);
+        env.shadow.lpr = load_mat(su.light_perspective);
+        env.shadow.lvp = load_mat(su.light_viewport);
+        env.shadow.bias = su.shadow_bias;
+        env.shadow.darkening = su.shadow_darkening;
+        env.shadow.map = &sm.z;
+        env.shadow.w = sm.w;
+        env.shadow.h = sm.h;
+    } else if (kind == TRB_SHADER_PHONG || kind == TRB_SHADER_EYE || kind == TRB_SHADER_GOURAUD) {
         if (!uniforms || ubytes != sizeof(TrbPhongUniforms)) return fail(c, TRB_E_ARG, "draw: uniforms");
         env.u = ((const TrbPhongUniforms*)uniforms)[vi];
         env.diffuse = tex_of(c, env.u.diffuse);
@@ -528,7 +586,17 @@ int orc_depth_restore(TrbCtx* c) {
     }
     return TRB_OK;
 }
-int orc_keep_depth_as_shadow_map(TrbCtx* c, int32_t*) { return fail(c, TRB_E_SHADER, "not in oracle-port yet"); }
+int orc_keep_depth_as_shadow_map(TrbCtx* c, int32_t* out) {
+    if (!c || c->views.empty() || !out) return fail(c, TRB_E_ARG, "keep_depth_as_shadow_map");
+    c->shadow_maps.push_back(TrbCtx::ShadowMapCopy{c->views[0].z, c->w, c->h});
+    *out = (int32_t)c->shadow_maps.size() - 1;
+    return TRB_OK;
+}
+int orc_release_shadow_maps(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    c->shadow_maps.clear();
+    return TRB_OK;
+}
 int orc_flush(TrbCtx* c) { return c ? TRB_OK : TRB_E_ARG; }
 int orc_end_frame(TrbCtx* c) { return c ? TRB_OK : TRB_E_ARG; }
 

@@ -189,6 +189,84 @@ struct EyeRestated : public LitShaderBase {
     }
 };
 
+// ---- config 2 shaders.  The fork has no shadow-mapping or Gouraud shader, so they are
+// AUTHORED here, once, as IShader subclasses that the reference's own rasterize() runs; the port
+// oracle and the CUDA backend restate exactly this arithmetic.
+// SHADOW_PHONG = PhongShader whose diffuse and specular terms are scaled by `darkening` when the
+// fragment lies behind the depth pass' z-buffer; the light-space clip position is a varying because
+// geometry.h has no matrix inverse.
+struct ShadowPhongAuthored : public PhongRestated {
+    mat<4, 4> light_mv, light_pr, light_vp;
+    double bias = 0, darkening = 1;
+    const std::vector<double>* shadow = nullptr;
+    int sw = 0, sh = 0;
+    vec4 varying_light_clip[3];
+
+    vec4 vertex(int face, int nth) override {
+        vec3 p = model->vert(face, nth);
+        varying_light_clip[nth] = light_pr * (light_mv * make_vec4(p[0], p[1], p[2], 1.0));
+        return PhongRestated::vertex(face, nth);
+    }
+    double shadow_factor(const vec3& bar) const {
+        vec4 c = varying_light_clip[0] * bar[0] + varying_light_clip[1] * bar[1] + varying_light_clip[2] * bar[2];
+        if (!(c[3] > 1e-12)) return 1.0;
+        vec4 ndc = c / c[3];
+        vec4 s = light_vp * ndc;
+        if (!(s[0] >= 0.0 && s[1] >= 0.0)) return 1.0;
+        int ix = int(s[0]), iy = int(s[1]);
+        if (ix < 0 || iy < 0 || ix >= sw || iy >= sh) return 1.0;
+        double zs = (*shadow)[(size_t)ix + (size_t)iy * sw];
+        return (ndc[2] > zs + bias) ? darkening : 1.0;
+    }
+    std::pair<bool, TGAColor> fragment(const vec3 bar) const override {
+        vec3 pos = mix3(varying_position_eye, bar);
+        vec3 gn = mix3(varying_normal_eye, bar);
+        vec2 uv = mix3(varying_uv, bar);
+        TGAColor base = model->diffuse(uv);
+        double spec_pow = std::max(1.0, (double)model->specular(uv));
+        double brightness = (base[0] + base[1] + base[2]) / (3.0 * 255.0);
+        bool eye_px = (brightness >= 0.85) && (spec_pow <= 5.0);
+        vec3 nm = model->normal(uv);
+        vec3 nm_eye = (ModelView * make_vec4(nm[0], nm[1], nm[2], 0.0)).xyz();
+        vec3 N = eye_px ? gn : normalized(gn * (1.0 - normal_map_strength) + nm_eye * normal_map_strength);
+        vec3 V = normalized(-pos);
+        double key_d = std::max(0.0, dot(N, key)) * 1.0;
+        vec3 R = normalized(N * (2.0 * dot(N, key)) - key);
+        double rv = std::max(0.0, dot(R, V));
+        double key_s = (rv > 0.0 ? std::pow(rv, spec_pow) : 0.0) * 1.0;
+        double fill_d = std::max(0.0, dot(N, fill)) * 0.35;
+        double rim_d = std::max(0.0, dot(N, rim)) * 0.6;
+        double diff = key_d + fill_d + rim_d;
+        double sf = shadow_factor(bar);
+        TGAColor out = base;
+        for (int ch = 0; ch < 3; ++ch) {
+            double cv = base[ch];
+            double v = cv * (0.10 + diff * sf) + 255.0 * ((0.35 * key_s) * sf);
+            out[ch] = (unsigned char)std::min(255.0, v);
+        }
+        return {false, out};
+    }
+};
+
+// GOURAUD: intensity max(0, normalized(normal_eye) . key) per vertex, interpolated; colour = diffuse * (0.1 + I)
+struct GouraudAuthored : public LitShaderBase {
+    vec3 key;
+    double varying_intensity[3];
+    vec4 vertex(int face, int nth) override {
+        vec4 clip = LitShaderBase::vertex(face, nth);
+        varying_intensity[nth] = std::max(0.0, dot(normalized(varying_normal_eye[nth]), key));
+        return clip;
+    }
+    std::pair<bool, TGAColor> fragment(const vec3 bar) const override {
+        double I = varying_intensity[0] * bar[0] + varying_intensity[1] * bar[1] + varying_intensity[2] * bar[2];
+        vec2 uv = mix3(varying_uv, bar);
+        TGAColor base = model->diffuse(uv);
+        TGAColor out = base;
+        for (int ch = 0; ch < 3; ++ch) out[ch] = (unsigned char)std::min(255.0, (double)base[ch] * (0.1 + I));
+        return {false, out};
+    }
+};
+
 // test shader of SURVEY K1-K7 / config 5: channel i = 255 * perspective-correct bary i
 struct FlatBaryShader : public IShader {
     vec4 clip[3];
@@ -256,6 +334,8 @@ struct TrbCtx {
     std::vector<std::unique_ptr<TGAImage>> textures;
     RefStats at_begin;
     TGAImage scratch;  // colour sink of DEPTH draws
+    struct ShadowMapCopy { std::vector<double> z; int w, h; };
+    std::vector<ShadowMapCopy> shadow_maps;
 };
 
 namespace {
@@ -419,6 +499,38 @@ int orc_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
             FlatBaryMeshShader sh;
             sh.model = &model;
             draw_faces(sh, view, kind == TRB_SHADER_DEPTH ? c->scratch : view.color, first, ntris);
+        } else if (kind == TRB_SHADER_GOURAUD) {
+            if (!uniforms || ubytes != sizeof(TrbPhongUniforms)) return fail(c, TRB_E_ARG, "draw: uniforms");
+            const TrbPhongUniforms& u = ((const TrbPhongUniforms*)uniforms)[vi];
+            model.diffuse_tex = tex_of(c, u.diffuse);
+            GouraudAuthored sh;
+            sh.model = &model;
+            sh.key = v3(u.key_dir_eye);
+            draw_faces(sh, view, view.color, first, ntris);
+        } else if (kind == TRB_SHADER_SHADOW_PHONG) {
+            if (!uniforms || ubytes != sizeof(TrbShadowUniforms)) return fail(c, TRB_E_ARG, "draw: uniforms");
+            const TrbShadowUniforms& su = ((const TrbShadowUniforms*)uniforms)[vi];
+            if (su.shadow_map < 0 || (size_t)su.shadow_map >= c->shadow_maps.size()) return fail(c, TRB_E_ARG, "draw: shadow map");
+            const auto& sm = c->shadow_maps[su.shadow_map];
+            if (sm.w != su.shadow_w || sm.h != su.shadow_h) return fail(c, TRB_E_ARG, "draw: shadow map size");
+            model.diffuse_tex = tex_of(c, su.phong.diffuse);
+            model.normal_tex = tex_of(c, su.phong.normal);
+            model.specular_tex = tex_of(c, su.phong.specular);
+            ShadowPhongAuthored sh;
+            sh.model = &model;
+            sh.key = v3(su.phong.key_dir_eye);
+            sh.fill = v3(su.phong.fill_dir_eye);
+            sh.rim = v3(su.phong.rim_dir_eye);
+            sh.normal_map_strength = su.phong.normal_map_strength;
+            sh.light_mv = load_mat(su.light_modelview);
+            sh.light_pr = load_mat(su.light_perspective);
+            sh.light_vp = load_mat(su.light_viewport);
+            sh.bias = su.shadow_bias;
+            sh.darkening = su.shadow_darkening;
+            sh.shadow = &sm.z;
+            sh.sw = sm.w;
+            sh.sh = sm.h;
+            draw_faces(sh, view, view.color, first, ntris);
         } else {
             return fail(c, TRB_E_SHADER, "draw: shader kind not available in oracle-ref");
         }
@@ -499,7 +611,17 @@ int orc_depth_restore(TrbCtx* c) {
     }
     return TRB_OK;
 }
-int orc_keep_depth_as_shadow_map(TrbCtx* c, int32_t*) { return fail(c, TRB_E_SHADER, "not in oracle-ref"); }
+int orc_keep_depth_as_shadow_map(TrbCtx* c, int32_t* out) {
+    if (!c || c->views.empty() || !out) return fail(c, TRB_E_ARG, "keep_depth_as_shadow_map");
+    c->shadow_maps.push_back(TrbCtx::ShadowMapCopy{c->views[0].depth, c->w, c->h});
+    *out = (int32_t)c->shadow_maps.size() - 1;
+    return TRB_OK;
+}
+int orc_release_shadow_maps(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    c->shadow_maps.clear();
+    return TRB_OK;
+}
 int orc_flush(TrbCtx* c) { return c ? TRB_OK : TRB_E_ARG; }
 int orc_end_frame(TrbCtx* c) { return c ? TRB_OK : TRB_E_ARG; }
 

@@ -6,7 +6,8 @@ import math
 
 import numpy as np
 
-from tinyrenderder_b200 import (PhongUniforms, SHADER_DEPTH, SHADER_EYE, SHADER_FLAT_BARY, SHADER_PHONG, scenes)
+from tinyrenderder_b200 import (PhongUniforms, SHADER_DEPTH, SHADER_EYE, SHADER_FLAT_BARY, SHADER_GOURAUD, SHADER_PHONG,
+                                SHADER_SHADOW_PHONG, scenes)
 
 INF = float("inf")
 
@@ -343,6 +344,22 @@ def lit_clip_triangles(api, r):
     return out
 
 
+def shadow(size, shadow_size, tex, res, ground, kind=SHADER_SHADOW_PHONG):
+    """config 2: depth pass from the light kept as a shadow map, then the shadow-mapped colour pass"""
+    def run(api, r):
+        sc = scenes.shadow_scene(size, size, body_res=res, ground_quads=ground, tex_size=tex)
+        up = scenes.UploadedScene(r, sc)
+        scenes.render_shadowed(up, scenes.head_view(api), api.perspective(sc.fov, 1.0, sc.znear, sc.zfar),
+                               shadow_size=(shadow_size, shadow_size), kind=kind)
+        return _grab(r, post=True)
+    return run
+
+
+shadow_small = shadow(256, 200, 64, (20, 14), 12)
+gouraud_small = shadow(200, 64, 64, (20, 14), 8, kind=SHADER_GOURAUD)
+shadow_c2 = shadow(2048, 2048, 1024, (42, 60), 32)
+
+
 def _dot4(row, v):
     s = 0.0
     for i in range(4):
@@ -360,6 +377,7 @@ CASES = {
     "big_triangles": big_triangles, "queue_overflow": queue_overflow, "dense_tile": dense_tile,
     "soup_mesh_fp32": soup_mesh_fp32, "head_small": head_small, "orbit_small": orbit_small,
     "depth_only_then_color": depth_only_then_color, "sub_range_draws": sub_range_draws,
-    "lit_clip_triangles": lit_clip_triangles,
+    "lit_clip_triangles": lit_clip_triangles, "shadow_small": shadow_small, "gouraud_small": gouraud_small,
 }
-FULL_SIZE_CASES = {"k7a": k7a, "k7b": k7b, "k7c": k7c, "head_c1": head_c1, "orbit_mid": orbit_mid}
+FULL_SIZE_CASES = {"k7a": k7a, "k7b": k7b, "k7c": k7c, "head_c1": head_c1, "orbit_mid": orbit_mid,
+                   "shadow_c2": shadow_c2}

@@ -105,6 +105,7 @@ SIGNATURES = {
     "depth_snapshot": (C.c_int, [_P]),
     "depth_restore": (C.c_int, [_P]),
     "keep_depth_as_shadow_map": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "release_shadow_maps": (C.c_int, [_P]),
     "flush": (C.c_int, [_P]),
     "end_frame": (C.c_int, [_P]),
     "ssao": (C.c_int, [_P, C.c_int, _P]),
@@ -319,6 +320,9 @@ class Renderer:
         out = C.c_int32(-1)
         self._ck(self._fn["keep_depth_as_shadow_map"](self.h, C.byref(out)), "keep_depth_as_shadow_map")
         return out.value
+
+    def release_shadow_maps(self):
+        self._ck(self._fn["release_shadow_maps"](self.h), "release_shadow_maps")
 
     def flush(self):
         self._ck(self._fn["flush"](self.h), "flush")

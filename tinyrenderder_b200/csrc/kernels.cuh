@@ -46,6 +46,11 @@ struct FrameDev {
     double viewport[16];
 };
 
+struct ShadowUniformsDev {
+    LitUniforms lit;
+    ShadowParams shadow;
+};
+
 struct DrawDev {               // one draw call, kept until flush (the shade kernel needs it)
     uint32_t id_base;          // vis id of local triangle t is id_base + t + 1
     uint32_t ntris;
@@ -55,7 +60,7 @@ struct DrawDev {               // one draw call, kept until flush (the shade ker
     const float* attr8;        // [nverts][8] pos,nrm,uv (mesh draws)
     const VRec* vrec;          // [nviews][nverts]
     const double* mats;        // [nviews][32] ModelView, Perspective
-    const LitUniforms* uniforms;  // [nviews] or nullptr
+    const void* uniforms;      // [nviews] LitUniforms (PHONG, EYE, GOURAUD) or ShadowUniformsDev (SHADOW_PHONG)
     const double* varyings;    // immediate mode: [ntris][24]
     int kind;
     uint32_t mesh_ntris;       // triangles of the whole mesh (ids of ranges other ranks drew map here too)
@@ -749,7 +754,20 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
                     varyings_from_attr(MV, at, k, vy);
                 }
             }
-            shade_lit(D.kind == 2 /*EYE*/, MV, D.uniforms[view], vy, pc, col);
+            if (D.kind == 5 /*GOURAUD*/) {
+                shade_gouraud(reinterpret_cast<const LitUniforms*>(D.uniforms)[view], vy, pc, col);
+            } else if (D.kind == 4 /*SHADOW_PHONG*/) {
+                const ShadowUniformsDev& SU = reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view];
+                double lc[3][4];
+                const uint32_t vj[3] = {i0, i1, i2};
+                for (int k = 0; k < 3; ++k) {
+                    const float* q = D.attr8 + (size_t)vj[k] * 8;
+                    light_clip_from_position(SU.shadow, (double)__ldg(q), (double)__ldg(q + 1), (double)__ldg(q + 2), lc[k]);
+                }
+                shade_lit(false, MV, SU.lit, vy, pc, col, shadow_factor(SU.shadow, lc, pc));
+            } else {
+                shade_lit(D.kind == 2 /*EYE*/, MV, reinterpret_cast<const LitUniforms*>(D.uniforms)[view], vy, pc, col);
+            }
         }
         if (write) {
             uint8_t* c = f.color + gp * 3;

@@ -111,6 +111,11 @@ struct Tex {
     bool alive = false;
 };
 
+struct ShadowMap {
+    DevBuf keys;
+    int w = 0, h = 0;
+};
+
 struct ProfEntry {
     const char* name;
     cudaEvent_t a, b;
@@ -139,7 +144,7 @@ struct TrbCtx {
     uint8_t clear[3] = {0, 0, 0};
     DevBuf zkey, vis, color, stats, zsnap, zlocal;
     bool have_snapshot = false;
-    std::vector<DevBuf> shadow_maps;
+    std::vector<ShadowMap> shadow_maps;
     Arena arena;
     std::vector<DrawDev> draws;     // since the last flush
     DevBuf draw_table;
@@ -367,14 +372,14 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     return TRB_OK;
 }
 
-int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, int nviews, LitUniforms** dev_out) {
+int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, int nviews, const void** dev_out) {
     *dev_out = nullptr;
     if (kind == TRB_SHADER_FLAT_BARY || kind == TRB_SHADER_DEPTH) return TRB_OK;
-    if (kind != TRB_SHADER_PHONG && kind != TRB_SHADER_EYE)
+    const bool shadow = kind == TRB_SHADER_SHADOW_PHONG;
+    if (kind != TRB_SHADER_PHONG && kind != TRB_SHADER_EYE && kind != TRB_SHADER_GOURAUD && !shadow)
         return fail(c, TRB_E_SHADER, "shader kind has no device implementation (no CPU fallback)");
-    if (!uniforms || ubytes != sizeof(TrbPhongUniforms)) return fail(c, TRB_E_ARG, "draw: uniform block size");
-    std::vector<LitUniforms> host(nviews);
-    const TrbPhongUniforms* u = (const TrbPhongUniforms*)uniforms;
+    const size_t want = shadow ? sizeof(TrbShadowUniforms) : sizeof(TrbPhongUniforms);
+    if (!uniforms || ubytes != want) return fail(c, TRB_E_ARG, "draw: uniform block size");
     auto tex = [&](TrbTex t, TexView& out) -> bool {
         out = TexView{nullptr, 0, 0, 0};
         if (t == 0) return true;
@@ -383,20 +388,48 @@ int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, i
         out = TexView{x.px, x.w, x.h, x.bpp};
         return true;
     };
-    for (int v = 0; v < nviews; ++v) {
-        LitUniforms& L = host[v];
-        L.key = D3{u[v].key_dir_eye[0], u[v].key_dir_eye[1], u[v].key_dir_eye[2]};
-        L.fill = D3{u[v].fill_dir_eye[0], u[v].fill_dir_eye[1], u[v].fill_dir_eye[2]};
-        L.rim = D3{u[v].rim_dir_eye[0], u[v].rim_dir_eye[1], u[v].rim_dir_eye[2]};
-        L.normal_map_strength = u[v].normal_map_strength;
-        if (!tex(u[v].diffuse, L.diffuse) || !tex(u[v].normal, L.normal) || !tex(u[v].specular, L.specular))
-            return fail(c, TRB_E_ARG, "draw: bad texture handle");
-    }
+    auto lit_of = [&](const TrbPhongUniforms& u, LitUniforms& L) -> bool {
+        L.key = D3{u.key_dir_eye[0], u.key_dir_eye[1], u.key_dir_eye[2]};
+        L.fill = D3{u.fill_dir_eye[0], u.fill_dir_eye[1], u.fill_dir_eye[2]};
+        L.rim = D3{u.rim_dir_eye[0], u.rim_dir_eye[1], u.rim_dir_eye[2]};
+        L.normal_map_strength = u.normal_map_strength;
+        return tex(u.diffuse, L.diffuse) && tex(u.normal, L.normal) && tex(u.specular, L.specular);
+    };
     cudaError_t e = cudaSuccess;
-    LitUniforms* d = (LitUniforms*)c->arena.alloc(sizeof(LitUniforms) * nviews, e);
+    if (!shadow) {
+        std::vector<LitUniforms> host(nviews);
+        const TrbPhongUniforms* u = (const TrbPhongUniforms*)uniforms;
+        for (int v = 0; v < nviews; ++v)
+            if (!lit_of(u[v], host[v])) return fail(c, TRB_E_ARG, "draw: bad texture handle");
+        void* d = c->arena.alloc(sizeof(LitUniforms) * nviews, e);
+        CU(e);
+        // `host` is pageable: the copy is staged before cudaMemcpyAsync returns
+        CU(cudaMemcpyAsync(d, host.data(), sizeof(LitUniforms) * nviews, cudaMemcpyHostToDevice, c->stream));
+        *dev_out = d;
+        return TRB_OK;
+    }
+    std::vector<ShadowUniformsDev> host(nviews);
+    const TrbShadowUniforms* u = (const TrbShadowUniforms*)uniforms;
+    for (int v = 0; v < nviews; ++v) {
+        if (!lit_of(u[v].phong, host[v].lit)) return fail(c, TRB_E_ARG, "draw: bad texture handle");
+        if (u[v].shadow_map < 0 || (size_t)u[v].shadow_map >= c->shadow_maps.size())
+            return fail(c, TRB_E_ARG, "draw: bad shadow map index");
+        const ShadowMap& sm = c->shadow_maps[u[v].shadow_map];
+        if (u[v].shadow_w != sm.w || u[v].shadow_h != sm.h) return fail(c, TRB_E_ARG, "draw: shadow map size mismatch");
+        ShadowParams& S = host[v].shadow;
+        memcpy(S.lmv, u[v].light_modelview, 128);
+        memcpy(S.lpr, u[v].light_perspective, 128);
+        memcpy(S.lvp, u[v].light_viewport, 128);
+        S.bias = u[v].shadow_bias;
+        S.darkening = u[v].shadow_darkening;
+        S.map_keys = sm.keys.as<unsigned long long>();
+        S.map_z = nullptr;
+        S.w = sm.w;
+        S.h = sm.h;
+    }
+    void* d = c->arena.alloc(sizeof(ShadowUniformsDev) * nviews, e);
     CU(e);
-    // `host` is pageable: the copy is staged before cudaMemcpyAsync returns
-    CU(cudaMemcpyAsync(d, host.data(), sizeof(LitUniforms) * nviews, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d, host.data(), sizeof(ShadowUniformsDev) * nviews, cudaMemcpyHostToDevice, c->stream));
     *dev_out = d;
     return TRB_OK;
 }
@@ -455,7 +488,7 @@ int trb_destroy(TrbCtx* c) {
                       &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->scratch_a,
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
-    for (auto& b : c->shadow_maps) b.release();
+    for (auto& b : c->shadow_maps) b.keys.release();
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         for (int i = 0; i < 2; ++i) {
@@ -638,7 +671,7 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
     const int nv = c->frame.nviews;
     c->tris_submitted += ntris;
     if (ntris == 0) return TRB_OK;
-    LitUniforms* dun = nullptr;
+    const void* dun = nullptr;
     rc = resolve_uniforms(c, kind, uniforms, ubytes, nv, &dun);
     if (rc) return rc;
     cudaError_t e = cudaSuccess;
@@ -702,7 +735,9 @@ int trb_submit_clip_triangles(TrbCtx* c, const double* clip12, const double* var
     if (rc) return rc;
     c->tris_submitted += n;
     if (n == 0) return TRB_OK;
-    LitUniforms* dun = nullptr;
+    const void* dun = nullptr;
+    if (kind == TRB_SHADER_SHADOW_PHONG || kind == TRB_SHADER_GOURAUD)
+        return fail(c, TRB_E_SHADER, "submit: this shader needs a mesh draw");
     rc = resolve_uniforms(c, kind, uniforms, ubytes, 1, &dun);
     if (rc) return rc;
     cudaError_t e = cudaSuccess;
@@ -783,12 +818,23 @@ int trb_keep_depth_as_shadow_map(TrbCtx* c, int32_t* out) {
     if (!c || !c->in_frame || !out) return fail(c, TRB_E_ARG, "keep_depth_as_shadow_map");
     int rc = do_flush(c);
     if (rc) return rc;
-    DevBuf b;
+    ShadowMap b;
     size_t bytes = (size_t)c->frame.npix * 8;
-    CU(b.ensure(bytes, c->stream));
-    CU(cudaMemcpyAsync(b.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(b.keys.ensure(bytes, c->stream));
+    CU(cudaMemcpyAsync(b.keys.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    b.w = c->frame.W;
+    b.h = c->frame.H;
     c->shadow_maps.push_back(b);
     *out = (int32_t)c->shadow_maps.size() - 1;
+    return TRB_OK;
+}
+
+int trb_release_shadow_maps(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto& b : c->shadow_maps) b.keys.release();
+    c->shadow_maps.clear();
     return TRB_OK;
 }
 

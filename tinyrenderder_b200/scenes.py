@@ -13,7 +13,8 @@ import os
 
 import numpy as np
 
-from .capi import (PhongUniforms, SHADER_EYE, SHADER_FLAT_BARY, SHADER_PHONG)
+from .capi import (PhongUniforms, ShadowUniforms, SHADER_DEPTH, SHADER_EYE, SHADER_FLAT_BARY, SHADER_GOURAUD, SHADER_PHONG,
+                   SHADER_SHADOW_PHONG)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 SCENEGEN_LIB = os.path.join(_PKG, "libtrb_scenegen.so")
@@ -382,3 +383,68 @@ def sphere_scene(level=10, width=3840, height=2160, name="c4_sphere"):
 
 def sphere_view(api):
     return api.lookat([0.0, 0.0, 2.2], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+
+
+# --------------------------------------------------------------------------------------------
+# config 2: two-pass shadow-mapped, normal-mapped shader (shaders authored in
+# the test oracle (ref_harness.cpp) because the fork has none)
+# --------------------------------------------------------------------------------------------
+LIGHT_POS = tuple(5.0 * c for c in normalized((1.0, 1.4, 1.0)))
+
+
+def shadow_scene(width=2048, height=2048, body_res=(42, 60), ground_quads=32, tex_size=1024, name="c2_shadow"):
+    """'diablo3_pose' stand-in: a 5040-triangle sphere standing on a subdivided ground plane that
+    receives its shadow; both drawn with SHADOW_PHONG."""
+    body = uv_sphere(body_res[0], body_res[1], 1.0, name="body")
+    p, n, u, i = _grid_face(np.array([-4.0, -1.0, 4.0]), np.array([8.0, 0.0, 0.0]), np.array([0.0, 0.0, -8.0]),
+                            ground_quads, ground_quads, np.array([0.0, 1.0, 0.0]))
+    ground = MeshData(p, n, u, i, "ground")
+    t_body = {"diffuse": texture_diffuse(tex_size, 41), "normal": texture_normal(tex_size, 42),
+              "specular": texture_specular(tex_size, 43)}
+    t_ground = {"diffuse": texture_diffuse(min(tex_size, 256), 44)}
+    items = [DrawItem(ground, np.eye(4), SHADER_SHADOW_PHONG, t_ground, 0.0),
+             DrawItem(body, np.eye(4), SHADER_SHADOW_PHONG, t_body, 1.0)]
+    return Scene(name, width, height, items, 60.0, 0.1, 100.0)
+
+
+def render_shadowed(up, view, perspective, shadow_size=None, bias=2e-3, darkening=0.35, kind=SHADER_SHADOW_PHONG):
+    """Pass 1: depth-only draw of every model from the light (TRB_SHADER_DEPTH) kept as the shadow map.
+    Pass 2: the camera frame with `kind` (SHADOW_PHONG, or GOURAUD / PHONG for the plain variants)."""
+    r, sc, api = up.r, up.scene, up.r.api
+    sw, sh = shadow_size or (sc.width, sc.height)
+    light_view = api.lookat(LIGHT_POS, [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    light_proj = api.perspective(40.0, sw / sh, 1.0, 20.0)
+    light_vp = api.viewport(0, 0, sw, sh)
+    r.release_shadow_maps()
+    r.begin_frame(sw, sh)
+    for it in sc.items:
+        r.draw(up.mesh_h[id(it.mesh)], api.mat4_mul(light_view, it.model_matrix), light_proj, kind=SHADER_DEPTH,
+               ntris=it.mesh.ntris)
+    r.end_frame()
+    smap = r.keep_depth_as_shadow_map()
+    key, fill, rim = normalized(KEY_LIGHT), normalized(FILL_LIGHT), normalized(RIM_LIGHT)
+    r.begin_frame(sc.width, sc.height)
+    for it in sc.items:
+        mv = api.mat4_mul(view, it.model_matrix)
+        ph = PhongUniforms()
+        ph.key_dir_eye[:] = api.light_dir_eye(mv, key)
+        ph.fill_dir_eye[:] = api.light_dir_eye(mv, fill)
+        ph.rim_dir_eye[:] = api.light_dir_eye(mv, rim)
+        ph.normal_map_strength = it.normal_map_strength
+        ph.diffuse = up.tex_h.get(id(it.textures.get("diffuse")), 0)
+        ph.normal = up.tex_h.get(id(it.textures.get("normal")), 0)
+        ph.specular = up.tex_h.get(id(it.textures.get("specular")), 0)
+        if kind == SHADER_SHADOW_PHONG:
+            u = ShadowUniforms()
+            u.phong = ph
+            u.light_modelview[:] = api.mat4_mul(light_view, it.model_matrix).reshape(-1)
+            u.light_perspective[:] = np.asarray(light_proj).reshape(-1)
+            u.light_viewport[:] = np.asarray(light_vp).reshape(-1)
+            u.shadow_bias = bias
+            u.shadow_darkening = darkening
+            u.shadow_map = smap
+            u.shadow_w, u.shadow_h = sw, sh
+        else:
+            u = ph
+        r.draw(up.mesh_h[id(it.mesh)], mv, perspective, kind=kind, uniforms=u, ntris=it.mesh.ntris)
+    r.end_frame()
