@@ -692,7 +692,10 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
 constexpr int SHADE_MAX_SM_DRAWS = 32;
 constexpr int SHADE_PX_PER_THREAD = 4;   // one 16-byte id load per thread: sparse frames (configs 4, 5) stay cheap
 
-// one visible pixel: p = x + y*W inside `view`, id = its winning triangle
+// one visible pixel: p = x + y*W inside `view`, id = its winning triangle.  C2 = the frame has a
+// config-2 shader (SHADOW_PHONG / GOURAUD); frames without one run the instantiation that does not
+// carry their registers.
+template <bool C2>
 __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
                                             const uint32_t* sm_base, int view, unsigned long long p, uint32_t id) {
     constexpr int MAX_SM_DRAWS = SHADE_MAX_SM_DRAWS;
@@ -754,9 +757,9 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
                     varyings_from_attr(MV, at, k, vy);
                 }
             }
-            if (D.kind == 5 /*GOURAUD*/) {
+            if (C2 && D.kind == 5 /*GOURAUD*/) {
                 shade_gouraud(reinterpret_cast<const LitUniforms*>(D.uniforms)[view], vy, pc, col);
-            } else if (D.kind == 4 /*SHADOW_PHONG*/) {
+            } else if (C2 && D.kind == 4 /*SHADOW_PHONG*/) {
                 const ShadowUniformsDev& SU = reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view];
                 double lc[3][4];
                 const uint32_t vj[3] = {i0, i1, i2};
@@ -828,6 +831,7 @@ __global__ void __launch_bounds__(TPB) k_shade_collect(FrameDev f, int row0, int
 }
 
 // Dense frames (most pixels have an unshaded winner): one thread per pixel, no list
+template <bool C2>
 __global__ void __launch_bounds__(TPB, 3) k_shade_dense(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
                                                      int row0, int row1) {
     if (f.stats[blockIdx.y].shade_mode) return;
@@ -841,11 +845,12 @@ __global__ void __launch_bounds__(TPB, 3) k_shade_dense(FrameDev f, const DrawDe
     uint32_t* vis = f.vis + (size_t)view * f.npix;
     const uint32_t id = vis[p];
     if (id == VIS_NONE || id == VIS_SHADED) return;
-    shade_pixel(f, draws, ndraws, sm_base, view, p, id);
+    shade_pixel<C2>(f, draws, ndraws, sm_base, view, p, id);
     vis[p] = VIS_SHADED;
 }
 
 // Sparse frames, pass 2: persistent grid-stride loop over the compacted list
+template <bool C2>
 __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
                                                const uint32_t* __restrict__ list) {
     if (!f.stats[blockIdx.y].shade_mode) return;
@@ -858,7 +863,7 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
     uint32_t* vis = f.vis + (size_t)view * f.npix;
     for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * TPB) {
         const uint32_t p = mylist[i];
-        shade_pixel(f, draws, ndraws, sm_base, view, p, vis[p]);
+        shade_pixel<C2>(f, draws, ndraws, sm_base, view, p, vis[p]);
         vis[p] = VIS_SHADED;
     }
 }

@@ -265,6 +265,8 @@ int do_flush(TrbCtx* c) {
     if (r1 > r0) {
         const FrameDev& f = c->frame;
         const unsigned long long n = (unsigned long long)(r1 - r0) * f.W;
+        bool config2 = false;
+        for (const DrawDev& d : c->draws) config2 |= d.kind >= 4;
         CU(c->shade_list.ensure((size_t)f.npix * f.nviews * 4, c->stream));
         {
             Launch L(c, "k_shade_decide");
@@ -279,13 +281,21 @@ int do_flush(TrbCtx* c) {
             unsigned per_view = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(
                 blocks_for(n), (148ull * 3 * 4 + f.nviews - 1) / f.nviews));
             Launch L(c, "k_shade");
-            k_shade<<<dim3(per_view, f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(), (int)c->draws.size(),
-                                                                      c->shade_list.as<uint32_t>());
+            if (config2)
+                k_shade<true><<<dim3(per_view, f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
+                                                                                (int)c->draws.size(), c->shade_list.as<uint32_t>());
+            else
+                k_shade<false><<<dim3(per_view, f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
+                                                                                 (int)c->draws.size(), c->shade_list.as<uint32_t>());
         }
         {   // dense views only
             Launch L(c, "k_shade_dense");
-            k_shade_dense<<<dim3(blocks_for(n), f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
-                                                                                (int)c->draws.size(), r0, r1);
+            if (config2)
+                k_shade_dense<true><<<dim3(blocks_for(n), f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
+                                                                                          (int)c->draws.size(), r0, r1);
+            else
+                k_shade_dense<false><<<dim3(blocks_for(n), f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
+                                                                                           (int)c->draws.size(), r0, r1);
         }
     }
     CU(cudaGetLastError());
