@@ -120,12 +120,13 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.samples = []
+        self.first = 0
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "10"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -136,10 +137,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
+    def mark(self):
+        """samples before this point were taken before the timed region"""
+        self.first = len(self.samples)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -147,7 +152,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in self.samples[max(0, self.first - 1):]:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
@@ -348,8 +353,10 @@ def main():
     r.profile_read(reset=True)
     launches0 = r.launch_count()
     clocks = ClockSampler(local_rank)
-    barrier()
     clocks.start()
+    time.sleep(0.2)
+    barrier()
+    clocks.mark()
     r.timer_start()
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
