@@ -492,7 +492,7 @@ struct SpEntry {              // one mid triangle of the chunk in the sample-par
 };
 
 #ifndef TRB_RASTER_MIN_BLOCKS
-#define TRB_RASTER_MIN_BLOCKS 3
+#define TRB_RASTER_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev f, RasterArgs a) {
     const int tile = blockIdx.x, view = blockIdx.y;
@@ -831,8 +831,11 @@ __global__ void __launch_bounds__(TPB) k_shade_collect(FrameDev f, int row0, int
 }
 
 // Dense frames (most pixels have an unshaded winner): one thread per pixel, no list
+#ifndef TRB_SHADE_MIN_BLOCKS
+#define TRB_SHADE_MIN_BLOCKS 4
+#endif
 template <bool C2>
-__global__ void __launch_bounds__(TPB, 3) k_shade_dense(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
+__global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
                                                      int row0, int row1) {
     if (f.stats[blockIdx.y].shade_mode) return;
     __shared__ uint32_t sm_base[SHADE_MAX_SM_DRAWS];
