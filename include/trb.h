@@ -265,6 +265,11 @@ TRB_EXPORT void TRB_FN(lookat)(const double eye[3], const double center[3], cons
 TRB_EXPORT void TRB_FN(perspective)(double fov_deg, double aspect, double znear, double zfar,
                                     double out[16]);
 TRB_EXPORT void TRB_FN(viewport)(int x, int y, int w, int h, double out[16]);
+/* batch forms for many views at once (camera orbits): out[v] = a[v] * b, and the eye-space direction
+ * of one world direction under every modelview */
+TRB_EXPORT void TRB_FN(mat4_mul_batch)(const double* a, int n, const double b[16], double* out);
+TRB_EXPORT void TRB_FN(light_dir_eye_batch)(const double* modelviews, int n, const double dir_world[3],
+                                            double* out);
 /* mat<4,4> * mat<4,4> (geometry.h:195-205) */
 TRB_EXPORT void TRB_FN(mat4_mul)(const double a[16], const double b[16], double out[16]);
 

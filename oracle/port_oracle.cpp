@@ -727,4 +727,11 @@ void orc_mat4_mul(const double* a, const double* b, double* out) {
     std::memcpy(out, r, sizeof(r));
 }
 
+void orc_mat4_mul_batch(const double* a, int n, const double* b, double* out) {
+    for (int v = 0; v < n; ++v) orc_mat4_mul(a + 16 * v, b, out + 16 * v);
+}
+void orc_light_dir_eye_batch(const double* mvs, int n, const double* dir, double* out) {
+    for (int v = 0; v < n; ++v) orc_light_dir_eye(mvs + 16 * v, dir, out + 3 * v);
+}
+
 }  // extern "C"

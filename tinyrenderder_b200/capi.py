@@ -134,6 +134,8 @@ SIGNATURES = {
     "perspective": (None, [C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     "viewport": (None, [C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mat4_mul": (None, [_P, _P, _P]),
+    "mat4_mul_batch": (None, [_P, C.c_int, _P, _P]),
+    "light_dir_eye_batch": (None, [_P, C.c_int, _P, _P]),
 }
 
 
@@ -187,6 +189,20 @@ class Api:
         out = np.empty(16)
         self.fn["mat4_mul"](_ptr(_f64(a, 16)), _ptr(_f64(b, 16)), _ptr(out))
         return out.reshape(4, 4)
+
+    def mat4_mul_batch(self, a, b):
+        a = _f64(a)
+        n = a.size // 16
+        out = np.empty((n, 4, 4))
+        self.fn["mat4_mul_batch"](_ptr(a), n, _ptr(_f64(b, 16)), _ptr(out))
+        return out
+
+    def light_dir_eye_batch(self, modelviews, dir_world):
+        mv = _f64(modelviews)
+        n = mv.size // 16
+        out = np.empty((n, 3))
+        self.fn["light_dir_eye_batch"](_ptr(mv), n, _ptr(_f64(dir_world, 3)), _ptr(out))
+        return out
 
     def light_dir_eye(self, modelview, dir_world):
         out = np.empty(3)

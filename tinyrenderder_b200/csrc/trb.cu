@@ -1174,6 +1174,12 @@ void trb_light_dir_eye(const double* mv, const double* dir, double* out) {
     out[1] = r.y;
     out[2] = r.z;
 }
+void trb_mat4_mul_batch(const double* a, int n, const double* b, double* out) {
+    for (int v = 0; v < n; ++v) trb_mat4_mul(a + 16 * v, b, out + 16 * v);
+}
+void trb_light_dir_eye_batch(const double* mvs, int n, const double* dir, double* out) {
+    for (int v = 0; v < n; ++v) trb_light_dir_eye(mvs + 16 * v, dir, out + 3 * v);
+}
 void trb_lookat(const double* eye, const double* center, const double* up, double* out) {
     // our_gl.cpp:25-41
     D3 e{eye[0], eye[1], eye[2]}, ce{center[0], center[1], center[2]}, u{up[0], up[1], up[2]};

@@ -26,6 +26,12 @@ FILL_LIGHT = (-0.3, 0.5, 0.2)
 RIM_LIGHT = (-1.0, 0.8, -1.5)
 
 
+# numpy mirror of TrbPhongUniforms (include/trb.h) for bulk fills
+_PHONG_DTYPE = np.dtype([("key", "<f8", 3), ("fill", "<f8", 3), ("rim", "<f8", 3), ("nms", "<f8"),
+                         ("diffuse", "<u8"), ("normal", "<u8"), ("specular", "<u8")])
+assert _PHONG_DTYPE.itemsize == C.sizeof(PhongUniforms)
+
+
 def normalized(v):
     """normalized(), geometry.h:136-140, in the reference's operation order."""
     v = np.asarray(v, dtype=np.float64)
@@ -303,19 +309,19 @@ class UploadedScene:
         for it in sc.items:
             if it.snapshot_before:
                 r.depth_snapshot()
-            mvs = np.stack([api.mat4_mul(views[v], it.model_matrix) for v in range(n)])
+            mvs = api.mat4_mul_batch(views, it.model_matrix)
             uni = None
             if it.kind in (SHADER_PHONG, SHADER_EYE):
+                # PhongUniforms for every view, filled through a numpy view of the ctypes array
                 arr = (PhongUniforms * n)()
-                for v in range(n):
-                    u = arr[v]
-                    u.key_dir_eye[:] = api.light_dir_eye(mvs[v], key)
-                    u.fill_dir_eye[:] = api.light_dir_eye(mvs[v], fill)
-                    u.rim_dir_eye[:] = api.light_dir_eye(mvs[v], rim)
-                    u.normal_map_strength = it.normal_map_strength
-                    u.diffuse = self.tex_h.get(id(it.textures.get("diffuse")), 0)
-                    u.normal = self.tex_h.get(id(it.textures.get("normal")), 0)
-                    u.specular = self.tex_h.get(id(it.textures.get("specular")), 0)
+                rec = np.frombuffer(arr, dtype=_PHONG_DTYPE)
+                rec["key"] = api.light_dir_eye_batch(mvs, key)
+                rec["fill"] = api.light_dir_eye_batch(mvs, fill)
+                rec["rim"] = api.light_dir_eye_batch(mvs, rim)
+                rec["nms"] = it.normal_map_strength
+                rec["diffuse"] = self.tex_h.get(id(it.textures.get("diffuse")), 0)
+                rec["normal"] = self.tex_h.get(id(it.textures.get("normal")), 0)
+                rec["specular"] = self.tex_h.get(id(it.textures.get("specular")), 0)
                 uni = arr
             r.draw(self.mesh_h[id(it.mesh)], mvs, perspective, kind=it.kind, uniforms=uni,
                    ntris=it.mesh.ntris)
