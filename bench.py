@@ -70,10 +70,8 @@ class Workload:
             self.label = "c4_icosphere_l%d_3840x2160_%dtri" % (args.c4_level, self.scene.ntris)
         else:
             n = args.c5_tris
-            _, pos = scenes.triangle_soup(n, 8192, 8192, 0.4, 5, True)
-            mesh = scenes.MeshData(pos, np.zeros((1, 3), np.float32).repeat(pos.shape[0], 0),
-                                   np.zeros((pos.shape[0], 2), np.float32), np.arange(pos.shape[0], dtype=np.uint32),
-                                   "soup")
+            _, pos = scenes.triangle_soup(n, 8192, 8192, 0.4, 5, True, want_clip=False)
+            mesh = scenes.MeshData(pos, None, None, None, "soup")   # V = 3T, implicit indices
             self.scene = scenes.Scene("c5_soup", 8192, 8192, [scenes.DrawItem(mesh, np.eye(4), 0)], 60, 0.1, 10)
             self.frames = 1
             self.label = "c5_soup_8192x8192_%dtri_r0.4" % n
@@ -383,7 +381,7 @@ def main():
         # two sets of pinned host buffers: the read-back of step s overlaps the rendering of step s+1
         color_host = [[pin((wl.height, wl.width, 3), torch.uint8) for _ in range(nviews)] for _ in range(2)]
         depth_host = [[pin((wl.height, wl.width), torch.float64) for _ in range(nviews)] for _ in range(2)]
-        e_steps = max(1, min(args.steps, 3 if wl.name in ("c4", "c5") else args.steps))
+        e_steps = max(1, min(args.steps, 1 if wl.name == "c5" else (3 if wl.name == "c4" else args.steps)))
 
         def e2e_step(s):
             up2 = wl.scenes.UploadedScene(r, wl.scene)                 # H2D: meshes + textures

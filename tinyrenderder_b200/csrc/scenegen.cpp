@@ -8,7 +8,7 @@
 extern "C" __attribute__((visibility("default")))
 int trb_gen_soup_clip(uint64_t seed, uint64_t ntris, int width, int height, double r, int round_fp32,
                       double* clip12, float* pos9) {
-    if (!clip12 || !pos9 || width <= 0 || height <= 0) return -1;
+    if ((!clip12 && !pos9) || width <= 0 || height <= 0) return -1;   // either output may be NULL
     std::mt19937_64 rng(seed);
     std::uniform_real_distribution<double> U(0.0, 1.0);
     const double W = width, H = height;
@@ -27,10 +27,14 @@ int trb_gen_soup_clip(uint64_t seed, uint64_t ntris, int width, int height, doub
                 y = (double)(float)y;
                 zz = (double)(float)zz;
             }
-            double* c = clip12 + t * 12 + v * 4;
-            c[0] = x; c[1] = y; c[2] = zz; c[3] = 1.0;
-            float* p = pos9 + t * 9 + v * 3;
-            p[0] = (float)x; p[1] = (float)y; p[2] = (float)zz;
+            if (clip12) {
+                double* c = clip12 + t * 12 + v * 4;
+                c[0] = x; c[1] = y; c[2] = zz; c[3] = 1.0;
+            }
+            if (pos9) {
+                float* p = pos9 + t * 9 + v * 3;
+                p[0] = (float)x; p[1] = (float)y; p[2] = (float)zz;
+            }
         }
     }
     return 0;

@@ -48,14 +48,15 @@ def normalized(v):
 class MeshData:
     def __init__(self, pos, nrm, uv, idx, name="mesh"):
         self.pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
-        self.nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
-        self.uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
-        self.idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1)
+        # nrm / uv / idx may be None: the accessors' fallbacks (0,0,1) / (0,0) and an implicit soup
+        self.nrm = None if nrm is None else np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
+        self.uv = None if uv is None else np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        self.idx = None if idx is None else np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1)
         self.name = name
 
     @property
     def ntris(self):
-        return self.idx.size // 3
+        return (self.pos.shape[0] if self.idx is None else self.idx.size) // 3
 
     @property
     def nverts(self):
@@ -167,15 +168,16 @@ def _scenegen():
     return lib
 
 
-def triangle_soup(ntris, width, height, r, seed, round_fp32):
+def triangle_soup(ntris, width, height, r, seed, round_fp32, want_clip=True):
     """K7 generator: per triangle cx=U*W, cy=U*H, z=2U-1 from uniform_real_distribution<double>
     (0,1) on mt19937_64(seed); verts (cx-r,cy-r),(cx+r,cy-r),(cx,cy+r); NDC = p/(W/2)-1, w=1.
     Returns (clip f64 [n,3,4], pos f32 [3n,3]); with round_fp32 every coordinate is rounded to
     fp32 first (config 5) so both forms describe the same triangles."""
-    clip = np.empty((ntris, 3, 4), dtype=np.float64)
+    clip = np.empty((ntris, 3, 4), dtype=np.float64) if want_clip else None
     pos = np.empty((ntris * 3, 3), dtype=np.float32)
     rc = _scenegen().trb_gen_soup_clip(seed, ntris, width, height, r, 1 if round_fp32 else 0,
-                                       clip.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p))
+                                       clip.ctypes.data_as(C.c_void_p) if want_clip else None,
+                                       pos.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError("trb_gen_soup_clip failed")
     return clip, pos
@@ -283,7 +285,7 @@ class UploadedScene:
             if id(it.mesh) not in self.mesh_h:
                 m = it.mesh
                 self.mesh_h[id(m)] = renderer.upload_mesh(m.pos, m.nrm, m.uv, m.idx)
-                self.h2d_bytes += m.pos.nbytes + m.nrm.nbytes + m.uv.nbytes + m.idx.nbytes
+                self.h2d_bytes += sum(a.nbytes for a in (m.pos, m.nrm, m.uv, m.idx) if a is not None)
             for t in it.textures.values():
                 if id(t) not in self.tex_h:
                     self.tex_h[id(t)] = renderer.upload_texture(t)
