@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--c4-level", type=int, default=10)
     ap.add_argument("--c5-tris", type=int, default=100_000_000)
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (0 = min(nproc, 8))")
+    ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="c4 on N>1 GPUs: fused NVLink kernel or NCCL all-reduces")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -305,6 +306,7 @@ def main():
 
     from tinyrenderder_b200 import multigpu
     sharded_c4 = wl.name == "c4" and world > 1
+    p2p = multigpu.P2PComposite(r, dist, rank, world) if sharded_c4 and args.composite == "p2p" else None
 
     def step(s):
         if not sharded_c4:
@@ -317,10 +319,13 @@ def main():
         r.set_triangle_id_base(first)
         mv = api.mat4_mul(wl.views(api, s, rank, world)[0], it.model_matrix)
         r.draw(up.mesh_h[id(it.mesh)], mv, wl.perspective, kind=it.kind, first_tri=first, ntris=count)
-        multigpu.composite(r, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MIN))
-        y0, y1 = multigpu.row_shard(wl.height, rank, world)
-        r.set_shade_rows(y0, y1)
-        r.end_frame()
+        if args.composite == "p2p":
+            p2p.run(wl.height)            # fused NVLink composite + shade of the owned rows
+        else:
+            multigpu.composite(r, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MIN))
+            y0, y1 = multigpu.row_shard(wl.height, rank, world)
+            r.set_shade_rows(y0, y1)
+            r.end_frame()
 
     # ---- diagnostics pass (untimed): counters for the algorithmic-bytes formula ---------------------
     step(0)
@@ -460,7 +465,8 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl.label, "frames_per_step_per_gpu": nviews, "width": wl.width, "height": wl.height,
                    "triangles_per_frame": T, "l2": "inputs larger than L2 (depth+id+colour planes of one step = %d MB)"
-                   % (nviews * P * 15 // 2 ** 20), "parallelism": ("triangle ranges + NCCL sort-last composite" if sharded_c4 else
+                   % (nviews * P * 15 // 2 ** 20), "parallelism": ("triangle ranges + %s sort-last composite" % ("fused NVLink P2P" if args.composite == "p2p" else "NCCL")
+                                   if sharded_c4 else
                                    "frames sharded, no collective") if world > 1 else "1 GPU"},
         "fragments_per_s": frag * world * args.steps / (ms_max * 1e-3),
         "pixels_shaded_per_s": C * world * args.steps / (ms_max * 1e-3),

@@ -251,6 +251,24 @@ TRB_EXPORT int TRB_FN(set_triangle_id_base)(TrbCtx* ctx, uint64_t base);
 TRB_EXPORT int TRB_FN(composite_save_local_depth)(TrbCtx* ctx);
 TRB_EXPORT int TRB_FN(composite_mask)(TrbCtx* ctx);
 TRB_EXPORT int TRB_FN(composite_finish)(TrbCtx* ctx);
+/* Fused NVLink composite (the sm_100a-native form of steps 1-5): every rank exports CUDA IPC
+ * handles of its two planes (trb_ipc_export_planes, 64 bytes each), the host exchanges them
+ * (e.g. torch.distributed.all_gather_object) and every rank opens its peers' planes once
+ * (trb_ipc_open_peers; handles[r] of the calling rank is ignored).  Then, per frame, after ALL ranks
+ * finished their draws (host barrier), trb_composite_shade_p2p runs ONE kernel that, for the rows
+ * [y0,y1) this rank owns, loads the n candidate (depth key, id) pairs straight from the peers' HBM
+ * over NVLink, keeps the exact lexicographic minimum (depth, then lowest id = first submitted) and
+ * shades the winner in the same pass.  Peers must not start their next frame before everybody is
+ * done reading (second host barrier). */
+TRB_EXPORT int TRB_FN(ipc_export_planes)(TrbCtx* ctx, void* key_handle64, void* vis_handle64);
+TRB_EXPORT int TRB_FN(ipc_open_peers)(TrbCtx* ctx, const void* key_handles, const void* vis_handles, int n,
+                                      int my_rank);
+/* same for ranks that live in ONE process (contexts on one or several GPUs with peer access):
+ * plain device pointers as returned by trb_device_planes, no IPC */
+TRB_EXPORT int TRB_FN(open_peers_raw)(TrbCtx* ctx, const uint64_t* key_ptrs, const uint64_t* vis_ptrs, int n,
+                                      int my_rank);
+TRB_EXPORT int TRB_FN(ipc_close_peers)(TrbCtx* ctx);
+TRB_EXPORT int TRB_FN(composite_shade_p2p)(TrbCtx* ctx, int y0, int y1);
 /* restrict flush to rows [y0,y1) (the screen slice this rank owns after the composite) */
 TRB_EXPORT int TRB_FN(set_shade_rows)(TrbCtx* ctx, int y0, int y1);
 

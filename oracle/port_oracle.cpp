@@ -663,6 +663,11 @@ int orc_set_triangle_id_base(TrbCtx* c, uint64_t) { return c ? TRB_OK : TRB_E_AR
 int orc_composite_save_local_depth(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_composite_mask(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_composite_finish(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_ipc_export_planes(TrbCtx* c, void*, void*) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_ipc_open_peers(TrbCtx* c, const void*, const void*, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_open_peers_raw(TrbCtx* c, const uint64_t*, const uint64_t*, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_ipc_close_peers(TrbCtx* c) { return c ? TRB_OK : TRB_E_ARG; }
+int orc_composite_shade_p2p(TrbCtx* c, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_set_shade_rows(TrbCtx* c, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 
 // ---- host helpers ------------------------------------------------------------------------

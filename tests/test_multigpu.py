@@ -143,3 +143,55 @@ def test_sort_last_composite_on_one_gpu(cuda_api, port_api, nranks):
         assert np.array_equal(color, o.read_color())
     for r in rs:
         r.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_fused_p2p_composite_shade_on_one_gpu(cuda_api, port_api, nranks):
+    """the fused composite+shade kernel (trb_composite_shade_p2p) with N contexts of one process as
+    ranks (raw peer pointers instead of CUDA IPC): equals the unsharded render bit for bit"""
+    m = scenes.icosphere(5)
+    w, h = 640, 400
+    mv, pr = scenes.sphere_view(cuda_api), cuda_api.perspective(60, w / h, 0.1, 10)
+    idx = np.concatenate([m.idx, m.idx])          # duplicates: exact depth ties across ranks
+    ntris = idx.size // 3
+    rs = [trb.Renderer(cuda_api) for _ in range(nranks)]
+    tex = scenes.texture_diffuse(64, 3)
+    for rank, r in enumerate(rs):
+        mesh = r.upload_mesh(m.pos, m.nrm, m.uv, idx)
+        first, count = multigpu.triangle_shard(ntris, rank, nranks)
+        u = trb.PhongUniforms()
+        u.key_dir_eye[:] = cuda_api.light_dir_eye(mv, scenes.normalized(scenes.KEY_LIGHT))
+        u.fill_dir_eye[:] = cuda_api.light_dir_eye(mv, scenes.normalized(scenes.FILL_LIGHT))
+        u.rim_dir_eye[:] = cuda_api.light_dir_eye(mv, scenes.normalized(scenes.RIM_LIGHT))
+        u.normal_map_strength = 0.0
+        u.diffuse = r.upload_texture(tex)
+        r.begin_frame(w, h)
+        r.set_triangle_id_base(first)
+        r.draw(mesh, mv, pr, kind=trb.SHADER_PHONG, uniforms=u, first_tri=first, ntris=count)
+        r.synchronize()
+    planes = [r.device_planes() for r in rs]
+    color = np.zeros((h, w, 3), np.uint8)
+    depth = np.zeros((h, w))
+    for rank, r in enumerate(rs):
+        r.open_peers_raw([p[0] for p in planes], [p[1] for p in planes], rank)
+    for rank, r in enumerate(rs):     # every rank composites + shades its rows; nobody has cleared yet
+        y0, y1 = multigpu.row_shard(h, rank, nranks)
+        r.composite_shade_p2p(y0, y1)
+        color[y0:y1] = r.read_color()[y0:y1]
+        depth[y0:y1] = r.read_depth()[y0:y1]
+    with trb.Renderer(port_api) as o:
+        mesh = o.upload_mesh(m.pos, m.nrm, m.uv, idx)
+        u = trb.PhongUniforms()
+        u.key_dir_eye[:] = port_api.light_dir_eye(mv, scenes.normalized(scenes.KEY_LIGHT))
+        u.fill_dir_eye[:] = port_api.light_dir_eye(mv, scenes.normalized(scenes.FILL_LIGHT))
+        u.rim_dir_eye[:] = port_api.light_dir_eye(mv, scenes.normalized(scenes.RIM_LIGHT))
+        u.normal_map_strength = 0.0
+        u.diffuse = o.upload_texture(tex)
+        o.begin_frame(w, h)
+        o.draw(mesh, mv, pr, kind=trb.SHADER_PHONG, uniforms=u, ntris=ntris)
+        o.end_frame()
+        assert np.array_equal(depth.view(np.uint64), o.read_depth().view(np.uint64))
+        assert np.abs(color.astype(int) - o.read_color().astype(int)).max() <= 1
+    for r in rs:
+        r.close()

@@ -129,6 +129,11 @@ SIGNATURES = {
     "composite_mask": (C.c_int, [_P]),
     "composite_finish": (C.c_int, [_P]),
     "set_shade_rows": (C.c_int, [_P, C.c_int, C.c_int]),
+    "ipc_export_planes": (C.c_int, [_P, _P, _P]),
+    "ipc_open_peers": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
+    "open_peers_raw": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
+    "ipc_close_peers": (C.c_int, [_P]),
+    "composite_shade_p2p": (C.c_int, [_P, C.c_int, C.c_int]),
     "light_dir_eye": (None, [_P, _P, _P]),
     "lookat": (None, [_P, _P, _P, _P]),
     "perspective": (None, [C.c_double, C.c_double, C.c_double, C.c_double, _P]),
@@ -439,6 +444,28 @@ class Renderer:
 
     def composite_finish(self):
         self._ck(self._fn["composite_finish"](self.h), "composite_finish")
+
+    def ipc_export_planes(self):
+        k, v = C.create_string_buffer(64), C.create_string_buffer(64)
+        self._ck(self._fn["ipc_export_planes"](self.h, k, v), "ipc_export_planes")
+        return k.raw, v.raw
+
+    def ipc_open_peers(self, key_handles, vis_handles, my_rank):
+        n = len(key_handles)
+        self._ck(self._fn["ipc_open_peers"](self.h, b"".join(key_handles), b"".join(vis_handles), n, my_rank),
+                 "ipc_open_peers")
+
+    def open_peers_raw(self, key_ptrs, vis_ptrs, my_rank):
+        n = len(key_ptrs)
+        k = (C.c_uint64 * n)(*key_ptrs)
+        v = (C.c_uint64 * n)(*vis_ptrs)
+        self._ck(self._fn["open_peers_raw"](self.h, k, v, n, my_rank), "open_peers_raw")
+
+    def ipc_close_peers(self):
+        self._ck(self._fn["ipc_close_peers"](self.h), "ipc_close_peers")
+
+    def composite_shade_p2p(self, y0, y1):
+        self._ck(self._fn["composite_shade_p2p"](self.h, y0, y1), "composite_shade_p2p")
 
     def set_shade_rows(self, y0, y1):
         self._ck(self._fn["set_shade_rows"](self.h, y0, y1), "set_shade_rows")

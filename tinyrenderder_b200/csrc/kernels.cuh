@@ -871,6 +871,39 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
     }
 }
 
+// Fused sort-last composite + shade over NVLink peer memory (config 4): one thread per owned pixel
+// loads the candidate (key, id) of every rank (peer pointers opened through CUDA IPC; loads of peer
+// addresses travel over NVLink and bypass the local L2), keeps the exact (depth, id) minimum, makes
+// it the local state and shades it - no intermediate all-reduced plane is ever written.
+constexpr int MAX_PEERS = 16;
+struct PeerPlanes {
+    const unsigned long long* key[MAX_PEERS];
+    const uint32_t* vis[MAX_PEERS];
+    int n;
+};
+template <bool C2>
+__global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p2p(FrameDev f, PeerPlanes peers,
+                                                                                  const DrawDev* __restrict__ draws,
+                                                                                  int ndraws, int row0, int row1) {
+    __shared__ uint32_t sm_base[SHADE_MAX_SM_DRAWS];
+    for (int i = threadIdx.x; i < ndraws && i < SHADE_MAX_SM_DRAWS; i += TPB) sm_base[i] = draws[i].id_base;
+    __syncthreads();
+    const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
+    const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
+    if (p >= last) return;
+    unsigned long long bk = ~0ull;
+    uint32_t bid = VIS_NONE;
+    for (int r = 0; r < peers.n; ++r) {
+        const unsigned long long kk = peers.key[r][p];
+        const uint32_t id = peers.vis[r][p];
+        if (kk < bk || (kk == bk && id < bid)) { bk = kk; bid = id; }
+    }
+    f.zkey[p] = bk;
+    if (bid == VIS_NONE || bid == VIS_SHADED) { f.vis[p] = bid; return; }
+    shade_pixel<C2>(f, draws, ndraws, sm_base, 0, p, bid);
+    f.vis[p] = VIS_SHADED;
+}
+
 // ---------------------------------------------------------------------------------------------
 // readback helpers and post passes
 // ---------------------------------------------------------------------------------------------

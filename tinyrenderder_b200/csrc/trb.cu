@@ -158,6 +158,11 @@ struct TrbCtx {
     uint32_t* host_total_dev = nullptr;
 
 
+    // fused P2P composite: peers' planes opened through CUDA IPC
+    PeerPlanes peers{};
+    void* peer_open[2 * MAX_PEERS] = {};
+    int peer_rank = -1;
+
     // pipelined readback
     cudaStream_t copy_stream = nullptr;
     DevBuf rb[2];
@@ -499,6 +504,7 @@ int trb_destroy(TrbCtx* c) {
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.keys.release();
+    trb_ipc_close_peers(c);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         for (int i = 0; i < 2; ++i) {
@@ -1155,6 +1161,94 @@ int trb_composite_finish(TrbCtx* c) {
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+int trb_ipc_export_planes(TrbCtx* c, void* key_handle, void* vis_handle) {
+    if (!c || !c->in_frame || !key_handle || !vis_handle) return fail(c, TRB_E_COMM, "ipc_export_planes: no frame");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    int rc = check_device(c);
+    if (rc) return rc;
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)key_handle, c->zkey.p));
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)vis_handle, c->vis.p));
+    return TRB_OK;
+}
+int trb_ipc_close_peers(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void*& p : c->peer_open)
+        if (p) {
+            cudaIpcCloseMemHandle(p);
+            p = nullptr;
+        }
+    c->peers.n = 0;
+    c->peer_rank = -1;
+    return TRB_OK;
+}
+int trb_ipc_open_peers(TrbCtx* c, const void* key_handles, const void* vis_handles, int n, int my_rank) {
+    if (!c || !c->in_frame || !key_handles || !vis_handles || n < 1 || n > MAX_PEERS || my_rank < 0 || my_rank >= n)
+        return fail(c, TRB_E_COMM, "ipc_open_peers: bad argument");
+    int rc = check_device(c);
+    if (rc) return rc;
+    trb_ipc_close_peers(c);
+    const cudaIpcMemHandle_t* kh = (const cudaIpcMemHandle_t*)key_handles;
+    const cudaIpcMemHandle_t* vh = (const cudaIpcMemHandle_t*)vis_handles;
+    for (int r = 0; r < n; ++r) {
+        if (r == my_rank) {
+            c->peers.key[r] = c->frame.zkey;
+            c->peers.vis[r] = c->frame.vis;
+            continue;
+        }
+        void *pk = nullptr, *pv = nullptr;
+        CU(cudaIpcOpenMemHandle(&pk, kh[r], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&pv, vh[r], cudaIpcMemLazyEnablePeerAccess));
+        c->peer_open[2 * r] = pk;
+        c->peer_open[2 * r + 1] = pv;
+        c->peers.key[r] = (const unsigned long long*)pk;
+        c->peers.vis[r] = (const uint32_t*)pv;
+    }
+    c->peers.n = n;
+    c->peer_rank = my_rank;
+    return TRB_OK;
+}
+int trb_open_peers_raw(TrbCtx* c, const uint64_t* key_ptrs, const uint64_t* vis_ptrs, int n, int my_rank) {
+    if (!c || !c->in_frame || !key_ptrs || !vis_ptrs || n < 1 || n > MAX_PEERS || my_rank < 0 || my_rank >= n)
+        return fail(c, TRB_E_COMM, "open_peers_raw: bad argument");
+    trb_ipc_close_peers(c);
+    for (int r = 0; r < n; ++r) {
+        c->peers.key[r] = (const unsigned long long*)(uintptr_t)key_ptrs[r];
+        c->peers.vis[r] = (const uint32_t*)(uintptr_t)vis_ptrs[r];
+    }
+    c->peers.n = n;
+    c->peer_rank = my_rank;
+    return TRB_OK;
+}
+int trb_composite_shade_p2p(TrbCtx* c, int y0, int y1) {
+    if (!c || !c->in_frame || c->frame.nviews != 1 || c->peers.n < 1 || y0 < 0 || y1 < y0 || y1 > c->frame.H)
+        return fail(c, TRB_E_COMM, "composite_shade_p2p: open the peers first (single-view frame)");
+    int rc = check_device(c);
+    if (rc) return rc;
+    // the local planes may have been reallocated since the peers were opened
+    c->peers.key[c->peer_rank] = c->frame.zkey;
+    c->peers.vis[c->peer_rank] = c->frame.vis;
+    if (y1 > y0 && !c->draws.empty()) {
+        size_t bytes = c->draws.size() * sizeof(DrawDev);
+        CU(c->draw_table.ensure(bytes, c->stream));
+        CU(cudaMemcpyAsync(c->draw_table.p, c->draws.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+        bool config2 = false;
+        for (const DrawDev& d : c->draws) config2 |= d.kind >= 4;
+        const unsigned long long n = (unsigned long long)(y1 - y0) * c->frame.W;
+        Launch L(c, "k_composite_shade_p2p");
+        if (config2)
+            k_composite_shade_p2p<true><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, c->draw_table.as<DrawDev>(),
+                                                                             (int)c->draws.size(), y0, y1);
+        else
+            k_composite_shade_p2p<false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, c->draw_table.as<DrawDev>(),
+                                                                              (int)c->draws.size(), y0, y1);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));   // peers wait on a host barrier after this call
+    c->draws.clear();
     return TRB_OK;
 }
 int trb_set_shade_rows(TrbCtx* c, int y0, int y1) {

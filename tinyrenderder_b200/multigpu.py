@@ -58,6 +58,35 @@ def composite(renderer, all_reduce_min):
     renderer.composite_finish()
 
 
+class P2PComposite:
+    """Fused NVLink composite + shade (config 4): peers' planes are opened once through CUDA IPC,
+    then every frame costs two host barriers and ONE kernel per rank (trb_composite_shade_p2p)."""
+
+    def __init__(self, renderer, dist, rank, world):
+        self.r, self.dist, self.rank, self.world = renderer, dist, rank, world
+        self.key = None
+
+    def _open(self):
+        planes = self.r.device_planes()[:2]
+        if planes == self.key:
+            return
+        mine = self.r.ipc_export_planes()
+        every = [None] * self.world
+        self.dist.all_gather_object(every, mine)
+        self.r.ipc_open_peers([h[0] for h in every], [h[1] for h in every], self.rank)
+        self.key = planes
+
+    def run(self, height):
+        """call after the rank's draws of the frame (no flush); shades the rows this rank owns"""
+        self._open()                      # (re)exchange handles when the planes were (re)allocated
+        self.r.synchronize()              # my draws are complete ...
+        self.dist.barrier()               # ... and so are everybody else's
+        y0, y1 = row_shard(height, self.rank, self.world)
+        self.r.composite_shade_p2p(y0, y1)
+        self.dist.barrier()               # nobody clears its planes while a peer still reads them
+        return y0, y1
+
+
 def composite_depth_color_cpu(z_list, bgr_list):
     """The same protocol on host arrays (used by the gloo tests with the CPU oracle): the winner of a
     pixel is the rank with the smallest depth, lowest rank on ties (lower ranks hold lower ids)."""
