@@ -155,3 +155,15 @@ def test_pipelined_readback_equals_blocking_reads(cuda_api):
             for v in range(3):
                 assert np.array_equal(got[step][1][v].view(np.uint64), want[step][v][0].view(np.uint64))
                 assert np.array_equal(got[step][0][v], want[step][v][1])
+
+
+@pytest.mark.parametrize("warp_max", ["0", "8", "1000000000"])
+@pytest.mark.parametrize("name", ["k2", "k7b_small", "signed_zero_ties", "duplicate_triangles", "big_triangles",
+                                  "queue_overflow", "dense_tile", "soup_mesh_fp32", "orbit_small", "sub_range_draws"])
+def test_both_raster_kernels_match_oracle(cuda_api, port_api, monkeypatch, name, warp_max):
+    """TRB_WARP_MAX = 0 sends every bin to the CTA-per-tile kernel, a huge value sends every bin to the
+    warp-per-tile kernel, 8 splits the tiles of one draw between the two: all must give the oracle's bits"""
+    monkeypatch.setenv("TRB_WARP_MAX", warp_max)
+    got = run_case(cuda_api, name)
+    want = run_case(port_api, name)
+    compare.assert_outputs_match(name, got, want)

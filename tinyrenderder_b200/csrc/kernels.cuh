@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "exact.cuh"
+#include "fastshade.cuh"
 
 namespace trbk {
 using namespace trbx;
@@ -62,6 +63,7 @@ struct DrawDev {               // one draw call, kept until flush (the shade ker
     const double* mats;        // [nviews][32] ModelView, Perspective
     const void* uniforms;      // [nviews] LitUniforms (PHONG, EYE, GOURAUD) or ShadowUniformsDev (SHADOW_PHONG)
     const double* varyings;    // immediate mode: [ntris][24]
+    const void* litf;          // [nviews] trbf::LitF: fp32 copies for the fp32 lighting path (mesh draws of lit kinds)
     int kind;
     uint32_t mesh_ntris;       // triangles of the whole mesh (ids of ranges other ranks drew map here too)
     long long mesh_id_base;    // id of mesh triangle g is mesh_id_base + g + 1  (= id_base - first_tri)
@@ -377,20 +379,27 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 }
 
 __global__ void __launch_bounds__(TPB) k_scan_partial(const uint32_t* __restrict__ in, uint32_t n,
-                                                      uint32_t* __restrict__ block_sum) {
+                                                      uint32_t* __restrict__ block_sum, uint32_t* __restrict__ max_acc) {
     __shared__ unsigned long long sh[TPB / 32];
     size_t base = (size_t)blockIdx.x * SCAN_BLOCK;
     unsigned long long s = 0;
+    uint32_t m = 0;
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         size_t e = base + (size_t)i * TPB + threadIdx.x;
-        if (e < n) s += in[e];
+        if (e < n) {
+            const uint32_t v = in[e];
+            s += v;
+            m = max(m, v);
+        }
     }
     s = block_reduce_sum(s, sh);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_acc, m);   // longest bin: picks the raster kernels of the draw
     if (threadIdx.x == 0) block_sum[blockIdx.x] = (uint32_t)s;
 }
-// single block: exclusive scan of the block sums in place, total written to *total_out
+// single block: exclusive scan of the block sums in place; total and longest bin written to total_out[0..1]
 __global__ void __launch_bounds__(TPB) k_scan_sums(uint32_t* __restrict__ block_sum, uint32_t nblocks,
-                                                   uint32_t* __restrict__ total_out) {
+                                                   uint32_t* __restrict__ total_out, uint32_t* __restrict__ max_acc) {
     __shared__ uint32_t sh[TPB / 32];
     uint32_t carry = 0;
     for (uint32_t base = 0; base < nblocks; base += TPB) {
@@ -400,7 +409,11 @@ __global__ void __launch_bounds__(TPB) k_scan_sums(uint32_t* __restrict__ block_
         if (e < nblocks) block_sum[e] = carry + ex;
         carry += tot;
     }
-    if (threadIdx.x == 0) *total_out = carry;
+    if (threadIdx.x == 0) {
+        total_out[0] = carry;
+        total_out[1] = *max_acc;
+        *max_acc = 0u;                                          // ready for the next draw
+    }
 }
 __global__ void __launch_bounds__(TPB) k_scan_final(const uint32_t* __restrict__ in, uint32_t n,
                                                     const uint32_t* __restrict__ block_sum,
@@ -483,6 +496,7 @@ struct RasterArgs {
     const uint32_t* offsets;  // [nviews][ntiles]
     const uint32_t* bins;
     int big_ns, small_min, large_ns;
+    uint32_t warp_max;        // bins of 1..warp_max triangles go to k_raster_warp, longer ones to k_raster
 };
 
 struct SpEntry {              // one mid triangle of the chunk in the sample-parallel list
@@ -498,7 +512,7 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
     const int tile = blockIdx.x, view = blockIdx.y;
     const size_t tslot = (size_t)view * f.ntiles + tile;
     const uint32_t n = a.counts[tslot];
-    if (n == 0) return;
+    if (n <= a.warp_max) return;            // empty, or short enough for k_raster_warp
     const uint32_t off = a.offsets[tslot];
 
     __shared__ unsigned long long zk[TPB];
@@ -687,6 +701,162 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
 }
 
 // ---------------------------------------------------------------------------------------------
+// fine raster, warp flavour: one WARP owns one 16x16 tile (bins of at most warp_max triangles)
+//
+// No block barrier, no atomics, no candidate queue.  The warp keeps the tile's depth keys and ids
+// in its private slice of shared memory and takes the bin in batches of 32 triangles: every lane
+// gathers one TriRec into shared memory, the clipped-bbox samples of the batch are laid end to end
+// (warp prefix sum) and dealt out 32 at a time, so every lane evaluates an in-bbox sample whatever
+// the triangle sizes are.  A lane finds the triangle of its sample with one reduce_or + popc (the
+// triangles' start positions inside the 32-sample window are a bit mask).  Fragments are applied
+// with a plain read-compare-write of (key, id); lanes of a round that hit the same pixel (only
+// possible when the window spans several triangles) take turns (match_any), so the result is the
+// lexicographic (depth, id) minimum whatever the order - the reference's first-wins on ties.
+// ---------------------------------------------------------------------------------------------
+constexpr int RW_WARPS = 4;                 // tiles per CTA
+constexpr uint32_t WARP_MAX_DEFAULT = 1024; // longest bin a single warp takes; TRB_WARP_MAX overrides (0: k_raster only)
+struct __align__(16) WarpTile {
+    unsigned long long zk[TILE * TILE];
+    uint32_t vid[TILE * TILE];
+    TriRec recs[32];
+};
+static_assert(sizeof(WarpTile) == 6144, "WarpTile size");
+
+#ifndef TRB_RW_MIN_BLOCKS
+#define TRB_RW_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_warp(FrameDev f, RasterArgs a) {
+    __shared__ WarpTile tiles[RW_WARPS];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * RW_WARPS + warp, view = blockIdx.y;
+    if (tile >= f.ntiles) return;
+    const size_t tslot = (size_t)view * f.ntiles + tile;
+    const uint32_t n = __ldg(a.counts + tslot);
+    if (n == 0 || n > a.warp_max) return;
+    const uint32_t off = __ldg(a.offsets + tslot);
+    WarpTile& sm = tiles[warp];
+    const int tx0 = (tile % f.tw) << TILE_SHIFT, ty0 = (tile / f.tw) << TILE_SHIFT;
+    unsigned long long* gz = f.zkey + (size_t)view * f.npix;
+    uint32_t* gv = f.vis + (size_t)view * f.npix;
+    const TriRec* tr = a.trirec + (size_t)view * a.ntris;
+
+    // first batch's bin entry: in flight while the tile is staged
+    uint32_t t_next = lane < (int)n ? __ldg(a.bins + off + lane) : 0u;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
+        const bool valid = x < f.W && y < f.H;
+        const size_t gp = (size_t)y * f.W + x;
+        sm.zk[p] = valid ? gz[gp] : 0ull;          // key 0 never loses: pixels outside the frame stay untouched
+        sm.vid[p] = valid ? gv[gp] : VIS_NONE;
+    }
+    uint32_t covered = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const bool has = base + lane < n;
+        uint32_t gid = 0, pack = 0, ns = 0;
+        if (has) {
+            const uint32_t t = t_next;
+            const double2* q = reinterpret_cast<const double2*>(tr + t);
+            const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
+            if (base + 32 + lane < n) t_next = __ldg(a.bins + off + base + 32 + lane);
+            const unsigned long long bbw = (unsigned long long)__double_as_longlong(r5.y);
+            const int bx0 = (int)(bbw & 0xffff), by0 = (int)((bbw >> 16) & 0xffff);
+            const int bx1 = (int)((bbw >> 32) & 0xffff), by1 = (int)(bbw >> 48);
+            const int cx0 = max(bx0, tx0) - tx0, cx1 = min(bx1, tx0 + TILE - 1) - tx0;
+            const int cy0 = max(by0, ty0) - ty0, cy1 = min(by1, ty0 + TILE - 1) - ty0;
+            const int bw = cx1 - cx0 + 1;
+            ns = (uint32_t)(bw * (cy1 - cy0 + 1));
+            // x0 | y0 | width-1 | ceil(2^15 / width): l / width == (l * inv) >> 15 for l < 256, width <= 16
+            pack = (uint32_t)cx0 | ((uint32_t)cy0 << 4) | ((uint32_t)(bw - 1) << 8) | ((uint32_t)((32768 + bw - 1) / bw) << 12);
+            gid = a.id_base + t + 1u;
+            double2* d = reinterpret_cast<double2*>(&sm.recs[lane]);
+            d[0] = r0; d[1] = r1; d[2] = r2; d[3] = r3; d[4] = r4; d[5] = r5;
+        }
+        uint32_t incl = ns;                          // samples of the batch laid end to end
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t first = incl - ns, S = __shfl_sync(FULL, incl, 31);
+        __syncwarp();
+        for (uint32_t bs = 0; bs < S; bs += 32) {
+            const uint32_t s = bs + lane;
+            const uint32_t rel = first - bs;         // wraps for triangles that started in an earlier window
+            const unsigned starts = __reduce_or_sync(FULL, (has && rel < 32u) ? (1u << rel) : 0u);
+            const int before = __popc(__ballot_sync(FULL, has && first < bs));
+            const bool act = s < S;
+            const int e = act ? before + __popc(starts & (FULL >> (31 - lane))) - 1 : 0;
+            const uint32_t first_e = __shfl_sync(FULL, first, e);
+            const uint32_t pk = __shfl_sync(FULL, pack, e);
+            const uint32_t gid_e = __shfl_sync(FULL, gid, e);
+            bool frag = false;
+            unsigned long long key = 0;
+            int p = 0;
+            if (act) {
+                const uint32_t l = s - first_e, bw = ((pk >> 8) & 15u) + 1u;
+                const uint32_t row = (l * (pk >> 12)) >> 15;
+                const int lx = (int)((pk & 15u) + (l - row * bw)), ly = (int)(((pk >> 4) & 15u) + row);
+                const double2* q = reinterpret_cast<const double2*>(&sm.recs[e]);
+                const double2 r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3], r4 = q[4];
+                TriSetup ts;
+                ts.ax = r0.x; ts.ay = r0.y; ts.s00 = r1.x; ts.s01 = r1.y; ts.s10 = r2.x; ts.s11 = r2.y;
+                ts.uz = r3.x; ts.z0 = r3.y; ts.z1 = r4.x; ts.z2 = r4.y; ts.ruz = q[5].x;
+                double b[3], z;
+                if (eval_sample(ts, tx0 + lx, ty0 + ly, b, z)) {
+                    frag = true;
+                    key = fragment_key(z);
+                    p = (ly << TILE_SHIFT) | lx;
+                    ++covered;
+                }
+            }
+            if ((starts & ~1u) == 0u) {              // the whole window is one triangle: distinct pixels
+                if (frag) {
+                    const unsigned long long cur = sm.zk[p];
+                    if (key < cur || (key == cur && gid_e < sm.vid[p])) { sm.zk[p] = key; sm.vid[p] = gid_e; }
+                }
+            } else {
+                const unsigned peers = __match_any_sync(FULL, frag ? (unsigned)p : 256u + (unsigned)lane);
+                const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+                const unsigned turns = __reduce_max_sync(FULL, rank);
+                for (unsigned r = 0; r <= turns; ++r) {
+                    if (frag && rank == r) {
+                        const unsigned long long cur = sm.zk[p];
+                        if (key < cur || (key == cur && gid_e < sm.vid[p])) { sm.zk[p] = key; sm.vid[p] = gid_e; }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // write back what changed; statistics as in k_raster
+    unsigned long long zmin = ~0ull;
+    uint32_t touched = 0;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
+        if (x < f.W && y < f.H) {
+            const size_t gp = (size_t)y * f.W + x;
+            const unsigned long long nk = sm.zk[p];
+            const uint32_t ni = sm.vid[p];
+            if (nk != gz[gp]) { gz[gp] = nk; zmin = min(zmin, nk); }
+            if (ni != gv[gp]) { gv[gp] = ni; ++touched; }
+        }
+    }
+    covered = __reduce_add_sync(FULL, covered);
+    if (covered == 0) return;
+    touched = __reduce_add_sync(FULL, touched);
+    for (int o = 16; o; o >>= 1) zmin = min(zmin, __shfl_xor_sync(FULL, zmin, o));
+    if (lane == 0) {
+        atomicAdd(&f.stats[view].frag_covered, (unsigned long long)covered);
+        atomicMin(&f.stats[view].zmin_key, zmin);
+        if (touched) atomicAdd(&f.stats[view].touched, (unsigned long long)touched);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // flush: the fragment() calls of our_gl.cpp:187-192, once per visible pixel
 // ---------------------------------------------------------------------------------------------
 constexpr int SHADE_MAX_SM_DRAWS = 32;
@@ -695,7 +865,7 @@ constexpr int SHADE_PX_PER_THREAD = 4;   // one 16-byte id load per thread: spar
 // one visible pixel: p = x + y*W inside `view`, id = its winning triangle.  C2 = the frame has a
 // config-2 shader (SHADOW_PHONG / GOURAUD); frames without one run the instantiation that does not
 // carry their registers.
-template <bool C2>
+template <bool C2, bool FAST>
 __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
                                             const uint32_t* sm_base, int view, unsigned long long p, uint32_t id) {
     constexpr int MAX_SM_DRAWS = SHADE_MAX_SM_DRAWS;
@@ -730,7 +900,8 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
     const int x = (int)(p % f.W), y = (int)(p / f.W);
     double b[3], z, pc[3];
     if (eval_sample(ts, x, y, b, z)) {          // always true for a recorded winner
-        f.zkey[gp] = depth_key(z);              // exact bits of the reference's zbuffer[idx] (keeps -0.0)
+        // exact bits of the reference's zbuffer[idx]: the stored key already is K(z) unless z is -0.0
+        if (z == 0.0) f.zkey[gp] = depth_key(z);
         perspective_bary(b, va.iw, vb.iw, vc.iw, pc);
         uint8_t col[3];
         bool write = true;
@@ -738,6 +909,38 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
             shade_flat_bary(pc, col);
         } else if (D.kind == 3 /*DEPTH*/) {
             write = false;
+        } else if (FAST && D.litf && D.kind != 5 /*GOURAUD*/) {
+            // fp32 lighting (fastshade.cuh): texture coordinates, texel choice and the shadow test stay fp64
+            const uint32_t vi[3] = {i0, i1, i2};
+            float at[3][8];
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4* q = reinterpret_cast<const float4*>(D.attr8 + (size_t)vi[k] * 8);
+                const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
+                at[k][0] = q0.x; at[k][1] = q0.y; at[k][2] = q0.z; at[k][3] = q0.w;
+                at[k][4] = q1.x; at[k][5] = q1.y; at[k][6] = q1.z; at[k][7] = q1.w;
+            }
+            const bool shadowed = C2 && D.kind == 4 /*SHADOW_PHONG*/;
+            const LitUniforms& U = shadowed ? reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view].lit
+                                            : reinterpret_cast<const LitUniforms*>(D.uniforms)[view];
+            const double tu = (double)at[0][6] * pc[0] + (double)at[1][6] * pc[1] + (double)at[2][6] * pc[2];  // main.cpp:100-101
+            const double tv = (double)at[0][7] * pc[0] + (double)at[1][7] * pc[1] + (double)at[2][7] * pc[2];
+            int base[4] = {255, 255, 255, 255}, nmc[4] = {0, 0, 0, 0}, sc[4];
+            if (U.diffuse.px) fetch_texel(U.diffuse, tu, tv, base);
+            const bool eye = D.kind == 2 /*EYE*/;
+            const bool has_nm = !eye && U.normal.px != nullptr;
+            if (has_nm) fetch_texel(U.normal, tu, tv, nmc);
+            float spec_f = 1.0f;
+            if (U.specular.px) { fetch_texel(U.specular, tu, tv, sc); spec_f = (float)sc[0] / 255.0f; }
+            float sf = 1.0f;
+            if (shadowed) {
+                const ShadowUniformsDev& SU = reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view];
+                double lc[3][4];
+                for (int k = 0; k < 3; ++k)
+                    light_clip_from_position(SU.shadow, (double)at[k][0], (double)at[k][1], (double)at[k][2], lc[k]);
+                sf = (float)shadow_factor(SU.shadow, lc, pc);
+            }
+            trbf::shade_lit_f32(eye, reinterpret_cast<const trbf::LitF*>(D.litf)[view], at, pc, base, has_nm, nmc, spec_f, sf, col);
         } else {
             const double* MV = D.mats + (size_t)view * 32;
             Varyings vy;
@@ -834,7 +1037,7 @@ __global__ void __launch_bounds__(TPB) k_shade_collect(FrameDev f, int row0, int
 #ifndef TRB_SHADE_MIN_BLOCKS
 #define TRB_SHADE_MIN_BLOCKS 4
 #endif
-template <bool C2>
+template <bool C2, bool FAST>
 __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
                                                      int row0, int row1) {
     if (f.stats[blockIdx.y].shade_mode) return;
@@ -848,12 +1051,12 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(Frame
     uint32_t* vis = f.vis + (size_t)view * f.npix;
     const uint32_t id = vis[p];
     if (id == VIS_NONE || id == VIS_SHADED) return;
-    shade_pixel<C2>(f, draws, ndraws, sm_base, view, p, id);
+    shade_pixel<C2, FAST>(f, draws, ndraws, sm_base, view, p, id);
     vis[p] = VIS_SHADED;
 }
 
 // Sparse frames, pass 2: persistent grid-stride loop over the compacted list
-template <bool C2>
+template <bool C2, bool FAST>
 __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
                                                const uint32_t* __restrict__ list) {
     if (!f.stats[blockIdx.y].shade_mode) return;
@@ -866,7 +1069,7 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
     uint32_t* vis = f.vis + (size_t)view * f.npix;
     for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * TPB) {
         const uint32_t p = mylist[i];
-        shade_pixel<C2>(f, draws, ndraws, sm_base, view, p, vis[p]);
+        shade_pixel<C2, FAST>(f, draws, ndraws, sm_base, view, p, vis[p]);
         vis[p] = VIS_SHADED;
     }
 }
@@ -881,7 +1084,7 @@ struct PeerPlanes {
     const uint32_t* vis[MAX_PEERS];
     int n;
 };
-template <bool C2>
+template <bool C2, bool FAST>
 __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p2p(FrameDev f, PeerPlanes peers,
                                                                                   const DrawDev* __restrict__ draws,
                                                                                   int ndraws, int row0, int row1) {
@@ -900,7 +1103,7 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p
     }
     f.zkey[p] = bk;
     if (bid == VIS_NONE || bid == VIS_SHADED) { f.vis[p] = bid; return; }
-    shade_pixel<C2>(f, draws, ndraws, sm_base, 0, p, bid);
+    shade_pixel<C2, FAST>(f, draws, ndraws, sm_base, 0, p, bid);
     f.vis[p] = VIS_SHADED;
 }
 

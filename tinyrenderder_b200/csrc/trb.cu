@@ -179,6 +179,8 @@ struct TrbCtx {
     uint64_t launches = 0;
     int big_ns = BIG_NS_DEFAULT, small_min = SMALL_MIN_DEFAULT, large_ns = LARGE_NS_DEFAULT;
     int direct_area = DIRECT_AREA_DEFAULT;
+    uint32_t warp_max = WARP_MAX_DEFAULT;
+    bool shade_exact = false;   // true: all-fp64 lighting (exact.cuh); false: fp32 lighting (fastshade.cuh)
 };
 
 namespace {
@@ -282,25 +284,31 @@ int do_flush(TrbCtx* c) {
             Launch L(c, "k_shade_collect");
             k_shade_collect<<<grid, TPB, 0, c->stream>>>(f, r0, r1, c->shade_list.as<uint32_t>());
         }
+        const DrawDev* table = c->draw_table.as<DrawDev>();
+        const int nd = (int)c->draws.size();
+        const uint32_t* list = c->shade_list.as<uint32_t>();
+        const int variant = (config2 ? 2 : 0) | (c->shade_exact ? 0 : 1);   // template <C2, FAST>
         {
             unsigned per_view = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(
                 blocks_for(n), (148ull * 3 * 4 + f.nviews - 1) / f.nviews));
+            const dim3 grid(per_view, f.nviews);
             Launch L(c, "k_shade");
-            if (config2)
-                k_shade<true><<<dim3(per_view, f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
-                                                                                (int)c->draws.size(), c->shade_list.as<uint32_t>());
-            else
-                k_shade<false><<<dim3(per_view, f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
-                                                                                 (int)c->draws.size(), c->shade_list.as<uint32_t>());
+            switch (variant) {
+                case 0: k_shade<false, false><<<grid, TPB, 0, c->stream>>>(f, table, nd, list); break;
+                case 1: k_shade<false, true><<<grid, TPB, 0, c->stream>>>(f, table, nd, list); break;
+                case 2: k_shade<true, false><<<grid, TPB, 0, c->stream>>>(f, table, nd, list); break;
+                default: k_shade<true, true><<<grid, TPB, 0, c->stream>>>(f, table, nd, list); break;
+            }
         }
         {   // dense views only
+            const dim3 grid(blocks_for(n), f.nviews);
             Launch L(c, "k_shade_dense");
-            if (config2)
-                k_shade_dense<true><<<dim3(blocks_for(n), f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
-                                                                                          (int)c->draws.size(), r0, r1);
-            else
-                k_shade_dense<false><<<dim3(blocks_for(n), f.nviews), TPB, 0, c->stream>>>(f, c->draw_table.as<DrawDev>(),
-                                                                                           (int)c->draws.size(), r0, r1);
+            switch (variant) {
+                case 0: k_shade_dense<false, false><<<grid, TPB, 0, c->stream>>>(f, table, nd, r0, r1); break;
+                case 1: k_shade_dense<false, true><<<grid, TPB, 0, c->stream>>>(f, table, nd, r0, r1); break;
+                case 2: k_shade_dense<true, false><<<grid, TPB, 0, c->stream>>>(f, table, nd, r0, r1); break;
+                default: k_shade_dense<true, true><<<grid, TPB, 0, c->stream>>>(f, table, nd, r0, r1); break;
+            }
         }
     }
     CU(cudaGetLastError());
@@ -315,11 +323,11 @@ int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uin
     CU(c->scan_sums.ensure((size_t)nblocks * 4, c->stream));
     {
         Launch L(c, "k_scan_partial");
-        k_scan_partial<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>());
+        k_scan_partial<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>(), c->scan_total.as<uint32_t>());
     }
     {
         Launch L(c, "k_scan_sums");
-        k_scan_sums<<<1, TPB, 0, c->stream>>>(c->scan_sums.as<uint32_t>(), nblocks, total_dev);
+        k_scan_sums<<<1, TPB, 0, c->stream>>>(c->scan_sums.as<uint32_t>(), nblocks, total_dev, c->scan_total.as<uint32_t>());
     }
     {
         Launch L(c, "k_scan_final");
@@ -340,7 +348,10 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     CU(c->counts.ensure(nslots * 4, c->stream));
     CU(c->offsets.ensure(nslots * 4, c->stream));
     CU(c->cursor.ensure(nslots * 4, c->stream));
-    CU(c->scan_total.ensure(16, c->stream));
+    if (!c->scan_total.p) {   // longest-bin accumulator: zero once, k_scan_sums re-arms it
+        CU(c->scan_total.ensure(16, c->stream));
+        CU(cudaMemsetAsync(c->scan_total.p, 0, 16, c->stream));
+    }
     CU(cudaMemsetAsync(c->counts.p, 0, nslots * 4, c->stream));
     CU(cudaMemsetAsync(c->cursor.p, 0, nslots * 4, c->stream));
     dim3 tgrid(blocks_for(g.ntris), f.nviews);
@@ -361,7 +372,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
                             c->host_total_dev);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
-    const uint32_t R = *c->host_total;
+    const uint32_t R = c->host_total[0], longest = c->host_total[1];
     if (R == 0) return TRB_OK;
     CU(c->bins.ensure((size_t)R * 4, c->stream));
     {
@@ -379,7 +390,12 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     ra.big_ns = c->big_ns;
     ra.small_min = c->small_min;
     ra.large_ns = c->large_ns;
-    {
+    ra.warp_max = c->warp_max;
+    if (c->warp_max > 0) {   // bins of 1..warp_max triangles: one warp per tile
+        Launch L(c, "k_raster_warp");
+        k_raster_warp<<<dim3((f.ntiles + RW_WARPS - 1) / RW_WARPS, f.nviews), RW_WARPS * 32, 0, c->stream>>>(f, ra);
+    }
+    if (longest > c->warp_max) {   // longer bins: one CTA per tile
         Launch L(c, "k_raster");
         k_raster<<<dim3(f.ntiles, f.nviews), TPB, 0, c->stream>>>(f, ra);
     }
@@ -476,6 +492,8 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_SMALL_MIN")) c->small_min = std::max(1, atoi(e));
     if (const char* e = getenv("TRB_LARGE_NS")) c->large_ns = std::max(1, atoi(e));
     if (const char* e = getenv("TRB_DIRECT_AREA")) c->direct_area = std::max(0, atoi(e));
+    if (const char* e = getenv("TRB_WARP_MAX")) c->warp_max = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("TRB_SHADE_EXACT")) c->shade_exact = atoi(e) != 0;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_a) != cudaSuccess || cudaEventCreate(&c->ev_b) != cudaSuccess ||
         cudaHostAlloc((void**)&c->host_total, 64, cudaHostAllocMapped) != cudaSuccess ||
@@ -483,6 +501,8 @@ int trb_create(int device, TrbCtx** out) {
         delete c;
         return TRB_E_CUDA;
     }
+    // 8 CTAs x 24 KB of per-warp tiles per SM: ask for the large shared-memory carveout
+    cudaFuncSetAttribute(k_raster_warp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = c;
     return TRB_OK;
 }
@@ -699,6 +719,25 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
         memcpy(&hm[(size_t)v * 32 + 16], pr + 16 * v, 128);
     }
     CU(cudaMemcpyAsync(mats, hm.data(), hm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    const void* litf = nullptr;
+    std::vector<trbf::LitF> hl;
+    if (kind == TRB_SHADER_PHONG || kind == TRB_SHADER_EYE || kind == TRB_SHADER_SHADOW_PHONG) {
+        hl.resize(nv);
+        for (int v = 0; v < nv; ++v) {
+            const TrbPhongUniforms& u = kind == TRB_SHADER_SHADOW_PHONG ? ((const TrbShadowUniforms*)uniforms)[v].phong
+                                                                        : ((const TrbPhongUniforms*)uniforms)[v];
+            trbf::LitF& L = hl[v];
+            for (int i = 0; i < 12; ++i) L.mv[i] = (float)mv[16 * v + i];
+            L.key = trbf::F3{(float)u.key_dir_eye[0], (float)u.key_dir_eye[1], (float)u.key_dir_eye[2]};
+            L.fill = trbf::F3{(float)u.fill_dir_eye[0], (float)u.fill_dir_eye[1], (float)u.fill_dir_eye[2]};
+            L.rim = trbf::F3{(float)u.rim_dir_eye[0], (float)u.rim_dir_eye[1], (float)u.rim_dir_eye[2]};
+            L.normal_map_strength = (float)u.normal_map_strength;
+        }
+        void* dl = c->arena.alloc(sizeof(trbf::LitF) * nv, e);
+        CU(e);
+        CU(cudaMemcpyAsync(dl, hl.data(), sizeof(trbf::LitF) * nv, cudaMemcpyHostToDevice, c->stream));
+        litf = dl;
+    }
     VRec* vrec = (VRec*)c->arena.alloc(sizeof(VRec) * (size_t)m.nverts * nv, e);
     CU(e);
     {
@@ -726,6 +765,7 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
     d.mats = mats;
     d.uniforms = dun;
     d.varyings = nullptr;
+    d.litf = litf;
     d.kind = kind;
     d.mesh_ntris = (uint32_t)(m.nidx / 3);
     d.mesh_id_base = (long long)g.id_base - (long long)g.first_tri;
@@ -1239,12 +1279,14 @@ int trb_composite_shade_p2p(TrbCtx* c, int y0, int y1) {
         for (const DrawDev& d : c->draws) config2 |= d.kind >= 4;
         const unsigned long long n = (unsigned long long)(y1 - y0) * c->frame.W;
         Launch L(c, "k_composite_shade_p2p");
-        if (config2)
-            k_composite_shade_p2p<true><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, c->draw_table.as<DrawDev>(),
-                                                                             (int)c->draws.size(), y0, y1);
-        else
-            k_composite_shade_p2p<false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, c->draw_table.as<DrawDev>(),
-                                                                              (int)c->draws.size(), y0, y1);
+        const DrawDev* table = c->draw_table.as<DrawDev>();
+        const int nd = (int)c->draws.size();
+        switch ((config2 ? 2 : 0) | (c->shade_exact ? 0 : 1)) {
+            case 0: k_composite_shade_p2p<false, false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
+            case 1: k_composite_shade_p2p<false, true><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
+            case 2: k_composite_shade_p2p<true, false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
+            default: k_composite_shade_p2p<true, true><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
+        }
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));   // peers wait on a host barrier after this call
