@@ -167,3 +167,36 @@ def test_both_raster_kernels_match_oracle(cuda_api, port_api, monkeypatch, name,
     got = run_case(cuda_api, name)
     want = run_case(port_api, name)
     compare.assert_outputs_match(name, got, want)
+
+
+LIT_CASES = ["head_small", "orbit_small", "shadow_small", "gouraud_small", "lit_clip_triangles"]
+
+
+@pytest.mark.parametrize("name", LIT_CASES)
+def test_exact_shading_mode_matches_oracle(cuda_api, port_api, monkeypatch, name):
+    """TRB_SHADE_EXACT=1: all-fp64 lighting in the reference's operation order - depth bit-exact and
+    the colour equal to the oracle's on (practically) every pixel"""
+    monkeypatch.setenv("TRB_SHADE_EXACT", "1")
+    got = run_case(cuda_api, name)
+    want = run_case(port_api, name)
+    compare.assert_outputs_match(name, got, want)
+    for key in want:
+        if key.startswith("bgr"):
+            same = float((got[key] == want[key]).all(axis=-1).mean())
+            assert same >= 0.9999, "%s/%s: only %.6f of the pixels identical in exact mode" % (name, key, same)
+
+
+@pytest.mark.parametrize("name", LIT_CASES)
+def test_fp32_lighting_stays_within_one_code(cuda_api, port_api, monkeypatch, name):
+    """default mode (fp32 lighting, fp64 coverage / depth / barycentrics / texel choice): no channel of
+    any pixel is further than 1 LSB from the oracle - stricter than north_star's 99.9 % - because the
+    lighting is continuous up to the final truncation"""
+    monkeypatch.delenv("TRB_SHADE_EXACT", raising=False)
+    got = run_case(cuda_api, name)
+    want = run_case(port_api, name)
+    compare.assert_outputs_match(name, got, want)
+    for key in want:
+        if key.startswith("bgr"):
+            d = np.abs(got[key].astype(np.int32) - want[key].astype(np.int32))
+            frac = float((d.max(axis=-1) <= 1).mean())
+            assert frac >= 0.9999, "%s/%s: %.6f within 1 LSB, max diff %d" % (name, key, frac, int(d.max()))
