@@ -200,3 +200,27 @@ def test_fp32_lighting_stays_within_one_code(cuda_api, port_api, monkeypatch, na
             d = np.abs(got[key].astype(np.int32) - want[key].astype(np.int32))
             frac = float((d.max(axis=-1) <= 1).mean())
             assert frac >= 0.9999, "%s/%s: %.6f within 1 LSB, max diff %d" % (name, key, frac, int(d.max()))
+
+
+DRAW_PATH_CASES = ["k2", "k5_far_near", "k7b_small", "signed_zero_ties", "duplicate_triangles", "big_triangles",
+                   "dense_tile", "soup_mesh_fp32", "head_small", "orbit_small", "sub_range_draws", "rejects"]
+
+
+@pytest.mark.parametrize("name", DRAW_PATH_CASES)
+def test_bin_overflow_takes_the_unbinned_kernels(cuda_api, port_api, monkeypatch, name):
+    """draws are enqueued without a host round trip, so the bin buffer is sized from an estimate;
+    TRB_BIN_CAP=16 makes every draw with more than 16 bin entries overflow it: the unbinned kernels
+    must then produce the oracle's bits (a performance cliff, never an error)"""
+    monkeypatch.setenv("TRB_BIN_CAP", "16")
+    got = run_case(cuda_api, name)
+    want = run_case(port_api, name)
+    compare.assert_outputs_match(name, got, want)
+
+
+@pytest.mark.parametrize("name", DRAW_PATH_CASES)
+def test_synchronous_draws_match_oracle(cuda_api, port_api, monkeypatch, name):
+    """TRB_SYNC_DRAWS=1: bins sized exactly after one stream synchronisation per draw (the pre-async path)"""
+    monkeypatch.setenv("TRB_SYNC_DRAWS", "1")
+    got = run_case(cuda_api, name)
+    want = run_case(port_api, name)
+    compare.assert_outputs_match(name, got, want)

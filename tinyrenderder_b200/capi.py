@@ -478,8 +478,9 @@ def load_cuda():
     """The product backend.  Raises (never falls back) when the CUDA library is not built."""
     global _cuda_api
     if _cuda_api is None:
-        if not os.path.exists(CUDA_LIB):
+        lib = os.environ.get("TRB_CUDA_LIB", CUDA_LIB)   # tuning builds of the same sources (profiles/ sweeps)
+        if not os.path.exists(lib):
             raise TrbError("CUDA backend %s is not built; run `python -c 'import __graft_entry__ as g; "
-                           "g.build()'` (there is no CPU fallback)" % CUDA_LIB)
-        _cuda_api = Api(CUDA_LIB, "trb")
+                           "g.build()'` (there is no CPU fallback)" % lib)
+        _cuda_api = Api(lib, "trb")
     return _cuda_api

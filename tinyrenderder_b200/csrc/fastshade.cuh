@@ -24,9 +24,14 @@ struct F3 {
 __device__ __forceinline__ float dot3f(F3 a, F3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, a.x * b.x)); }
 __device__ __forceinline__ F3 scale3f(F3 v, float s) { return F3{v.x * s, v.y * s, v.z * s}; }
 // normalized(), geometry.h:136-140 (a zero vector is returned unchanged)
+__device__ __forceinline__ float rsqrt_fast(float x) {   // MUFU.RSQ, 2 ulp
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ F3 normalize3f(F3 v) {
     const float l2 = dot3f(v, v);
-    return l2 > 0.0f ? scale3f(v, rsqrtf(l2)) : v;
+    return l2 >= 1.17549435e-38f ? scale3f(v, rsqrt_fast(l2)) : v;   // below FLT_MIN the ftz reciprocal root is inf
 }
 // rows 0..2 of a row-major 4x4 (12 floats) times (v, w)
 __device__ __forceinline__ F3 mul_m34f(const float* M, F3 v, float w) {

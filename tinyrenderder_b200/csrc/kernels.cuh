@@ -354,6 +354,15 @@ __global__ void __launch_bounds__(TPB) k_direct_resolve(FrameDev f, GeomArgs g, 
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_BLOCK = TPB * SCAN_ITEMS;
 
+// Per-context control block of the draw in flight, zeroed before every draw.  It is what lets a
+// draw run without a host round trip: the kernels that follow the scan read their work from it.
+struct DrawCtl {
+    uint32_t heavy_n;    // tiles whose bin is longer than warp_max: the work list of k_raster
+    uint32_t longest;    // longest bin of the draw
+    uint32_t total;      // R, the bin entries of the draw
+    uint32_t overflow;   // R does not fit the bin buffer: the unbinned kernels take the draw instead
+};
+
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sh, uint32_t& total) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t x = v;
@@ -379,7 +388,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 }
 
 __global__ void __launch_bounds__(TPB) k_scan_partial(const uint32_t* __restrict__ in, uint32_t n,
-                                                      uint32_t* __restrict__ block_sum, uint32_t* __restrict__ max_acc) {
+                                                      uint32_t* __restrict__ block_sum, DrawCtl* __restrict__ ctl,
+                                                      uint32_t warp_max, uint32_t* __restrict__ heavy_list) {
     __shared__ unsigned long long sh[TPB / 32];
     size_t base = (size_t)blockIdx.x * SCAN_BLOCK;
     unsigned long long s = 0;
@@ -390,16 +400,19 @@ __global__ void __launch_bounds__(TPB) k_scan_partial(const uint32_t* __restrict
             const uint32_t v = in[e];
             s += v;
             m = max(m, v);
+            if (v > warp_max) heavy_list[atomicAdd(&ctl->heavy_n, 1u)] = (uint32_t)e;   // rare: a CTA's worth of work each
         }
     }
     s = block_reduce_sum(s, sh);
     m = __reduce_max_sync(0xffffffffu, m);
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_acc, m);   // longest bin: picks the raster kernels of the draw
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&ctl->longest, m);
     if (threadIdx.x == 0) block_sum[blockIdx.x] = (uint32_t)s;
 }
-// single block: exclusive scan of the block sums in place; total and longest bin written to total_out[0..1]
+// single block: exclusive scan of the block sums in place; R, the longest bin and the overflow verdict
+// go to ctl and to host_out[0..2] (mapped host memory: the host reads them without a copy)
 __global__ void __launch_bounds__(TPB) k_scan_sums(uint32_t* __restrict__ block_sum, uint32_t nblocks,
-                                                   uint32_t* __restrict__ total_out, uint32_t* __restrict__ max_acc) {
+                                                   uint32_t* __restrict__ host_out, DrawCtl* __restrict__ ctl,
+                                                   uint32_t bin_capacity) {
     __shared__ uint32_t sh[TPB / 32];
     uint32_t carry = 0;
     for (uint32_t base = 0; base < nblocks; base += TPB) {
@@ -410,9 +423,11 @@ __global__ void __launch_bounds__(TPB) k_scan_sums(uint32_t* __restrict__ block_
         carry += tot;
     }
     if (threadIdx.x == 0) {
-        total_out[0] = carry;
-        total_out[1] = *max_acc;
-        *max_acc = 0u;                                          // ready for the next draw
+        ctl->total = carry;
+        ctl->overflow = carry > bin_capacity ? 1u : 0u;
+        host_out[0] = carry;
+        host_out[1] = ctl->longest;
+        host_out[2] = ctl->overflow;
     }
 }
 __global__ void __launch_bounds__(TPB) k_scan_final(const uint32_t* __restrict__ in, uint32_t n,
@@ -438,7 +453,8 @@ __global__ void __launch_bounds__(TPB) k_scan_final(const uint32_t* __restrict__
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_fill(FrameDev f, uint32_t ntris, const uint2* __restrict__ tribox,
                                               const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
-                                              uint32_t* __restrict__ bins) {
+                                              uint32_t* __restrict__ bins, const DrawCtl* __restrict__ ctl) {
+    if (ctl->overflow) return;
     const int view = blockIdx.y;
     const uint32_t t = blockIdx.x * TPB + threadIdx.x;
     uint2 box = make_uint2(BOX_NONE, 0u);
@@ -497,6 +513,8 @@ struct RasterArgs {
     const uint32_t* bins;
     int big_ns, small_min, large_ns;
     uint32_t warp_max;        // bins of 1..warp_max triangles go to k_raster_warp, longer ones to k_raster
+    const DrawCtl* ctl;
+    const uint32_t* heavy_list;   // [ctl->heavy_n] tile slots (view * ntiles + tile) of the long bins
 };
 
 struct SpEntry {              // one mid triangle of the chunk in the sample-parallel list
@@ -508,11 +526,10 @@ struct SpEntry {              // one mid triangle of the chunk in the sample-par
 #ifndef TRB_RASTER_MIN_BLOCKS
 #define TRB_RASTER_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev f, RasterArgs a) {
-    const int tile = blockIdx.x, view = blockIdx.y;
-    const size_t tslot = (size_t)view * f.ntiles + tile;
+__device__ __forceinline__ void raster_tile_cta(const FrameDev& f, const RasterArgs& a, uint32_t tslot_) {
+    const int tile = (int)(tslot_ % (uint32_t)f.ntiles), view = (int)(tslot_ / (uint32_t)f.ntiles);
+    const size_t tslot = tslot_;
     const uint32_t n = a.counts[tslot];
-    if (n <= a.warp_max) return;            // empty, or short enough for k_raster_warp
     const uint32_t off = a.offsets[tslot];
 
     __shared__ unsigned long long zk[TPB];
@@ -699,6 +716,15 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
         if (touched) atomicAdd(&f.stats[view].touched, touched);
     }
 }
+// persistent grid over the (usually short or empty) list of long bins
+__global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev f, RasterArgs a) {
+    if (a.ctl->overflow) return;
+    const uint32_t nh = a.ctl->heavy_n;
+    for (uint32_t i = blockIdx.x; i < nh; i += gridDim.x) {
+        raster_tile_cta(f, a, a.heavy_list[i]);
+        __syncthreads();                     // the tile's shared state is reused by the next one
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // fine raster, warp flavour: one WARP owns one 16x16 tile (bins of at most warp_max triangles)
@@ -715,7 +741,7 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
 // ---------------------------------------------------------------------------------------------
 constexpr int RW_WARPS = 4;                 // tiles per CTA
 constexpr uint32_t WARP_MAX_DEFAULT = 1024; // longest bin a single warp takes; TRB_WARP_MAX overrides (0: k_raster only)
-struct __align__(16) WarpTile {
+struct __align__(32) WarpTile {
     unsigned long long zk[TILE * TILE];
     uint32_t vid[TILE * TILE];
     TriRec recs[32];
@@ -733,7 +759,7 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
     if (tile >= f.ntiles) return;
     const size_t tslot = (size_t)view * f.ntiles + tile;
     const uint32_t n = __ldg(a.counts + tslot);
-    if (n == 0 || n > a.warp_max) return;
+    if (n == 0 || n > a.warp_max || a.ctl->overflow) return;
     const uint32_t off = __ldg(a.offsets + tslot);
     WarpTile& sm = tiles[warp];
     const int tx0 = (tile % f.tw) << TILE_SHIFT, ty0 = (tile / f.tw) << TILE_SHIFT;
@@ -857,6 +883,64 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
 }
 
 // ---------------------------------------------------------------------------------------------
+// unbinned fallback.  A draw is enqueued without a host round trip, so its bin buffer is sized
+// from an estimate; when the scan finds that R does not fit (ctl->overflow) the fill and tile
+// kernels stand down and these two take the draw's binned triangles straight from their TriRecs:
+// one warp per triangle, lanes over the samples of its clamped bbox, 64-bit atomicMin on the global
+// key plane, then the lowest id among the fragments that sit at a pixel's final depth - the same
+// exact (depth, id) minimum as the other paths (it is the direct path of k_setup_count with a warp
+// per triangle).  Slower than the tile kernels, but only ever a performance cliff, never an error.
+// ---------------------------------------------------------------------------------------------
+template <bool IDS>
+__global__ void __launch_bounds__(TPB) k_unbinned(FrameDev f, uint32_t ntris, uint32_t id_base,
+                                                  const uint2* __restrict__ tribox, const TriRec* __restrict__ trirec,
+                                                  const DrawCtl* __restrict__ ctl) {
+    if (!ctl->overflow) return;
+    const unsigned FULL = 0xffffffffu;
+    const int view = blockIdx.y, lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * (TPB / 32), w0 = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+    unsigned long long* zk = f.zkey + (size_t)view * f.npix;
+    uint32_t* vis = f.vis + (size_t)view * f.npix;
+    unsigned long long covered = 0, zmin = ~0ull;
+    for (uint32_t t = w0; t < ntris; t += nwarps) {
+        if (tribox[(size_t)view * ntris + t].x >= BOX_DIRECT) continue;   // rejected, or already drawn by the direct path
+        TriSetup ts;
+        load_trirec(trirec + (size_t)view * ntris + t, ts);
+        const uint32_t bw = (uint32_t)(ts.x1 - ts.x0 + 1), ns = bw * (uint32_t)(ts.y1 - ts.y0 + 1);
+        const uint32_t gid = id_base + t + 1u;
+        for (uint32_t s = lane; s < ns; s += 32) {
+            const uint32_t row = s / bw;
+            const int x = ts.x0 + (int)(s - row * bw), y = ts.y0 + (int)row;
+            double b[3], z;
+            if (!eval_sample(ts, x, y, b, z)) continue;
+            const unsigned long long key = fragment_key(z);
+            const size_t p = (size_t)y * f.W + x;
+            if (!IDS) {
+                ++covered;
+                zmin = min(zmin, key);
+                if (key <= zk[p]) {
+                    const unsigned long long old = atomicMin(zk + p, key);
+                    if (old > key) vis[p] = VIS_NONE;          // strictly nearer: the old winner is gone
+                }
+            } else if (key == zk[p]) {
+                atomicMin(vis + p, gid);                       // ties: lowest id = first submitted
+            }
+        }
+    }
+    if constexpr (!IDS) {
+        for (int o = 16; o; o >>= 1) {
+            covered += __shfl_xor_sync(FULL, covered, o);
+            zmin = min(zmin, __shfl_xor_sync(FULL, zmin, o));
+        }
+        if (lane == 0 && covered) {
+            atomicAdd(&f.stats[view].frag_covered, covered);
+            atomicAdd(&f.stats[view].touched, covered);
+            atomicMin(&f.stats[view].zmin_key, zmin);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // flush: the fragment() calls of our_gl.cpp:187-192, once per visible pixel
 // ---------------------------------------------------------------------------------------------
 constexpr int SHADE_MAX_SM_DRAWS = 32;
@@ -897,7 +981,8 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
     const VRec va = load_vrec(vr + i0), vb = load_vrec(vr + i1), vc = load_vrec(vr + i2);
     TriSetup ts;
     setup_triangle(va, vb, vc, f.W, f.H, ts);
-    const int x = (int)(p % f.W), y = (int)(p / f.W);
+    const uint32_t yq = (uint32_t)p / (uint32_t)f.W;     // p < 2^32: a frame has fewer than 2^32 pixels
+    const int x = (int)((uint32_t)p - yq * (uint32_t)f.W), y = (int)yq;
     double b[3], z, pc[3];
     if (eval_sample(ts, x, y, b, z)) {          // always true for a recorded winner
         // exact bits of the reference's zbuffer[idx]: the stored key already is K(z) unless z is -0.0
@@ -909,7 +994,7 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
             shade_flat_bary(pc, col);
         } else if (D.kind == 3 /*DEPTH*/) {
             write = false;
-        } else if (FAST && D.litf && D.kind != 5 /*GOURAUD*/) {
+        } else if (FAST && !(C2 && D.kind == 5 /*GOURAUD*/)) {
             // fp32 lighting (fastshade.cuh): texture coordinates, texel choice and the shadow test stay fp64
             const uint32_t vi[3] = {i0, i1, i2};
             float at[3][8];
@@ -925,13 +1010,28 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
                                             : reinterpret_cast<const LitUniforms*>(D.uniforms)[view];
             const double tu = (double)at[0][6] * pc[0] + (double)at[1][6] * pc[1] + (double)at[2][6] * pc[2];  // main.cpp:100-101
             const double tv = (double)at[0][7] * pc[0] + (double)at[1][7] * pc[1] + (double)at[2][7] * pc[2];
-            int base[4] = {255, 255, 255, 255}, nmc[4] = {0, 0, 0, 0}, sc[4];
-            if (U.diffuse.px) fetch_texel(U.diffuse, tu, tv, base);
+            // the three maps are sampled at the same (u, v): one texel index serves every map of the same size
+            int base[4] = {255, 255, 255, 255}, nmc[4] = {0, 0, 0, 0};
+            size_t ti = 0;
+            int tw = -1, th = -1;
+            auto index_in = [&](const TexView& t) -> size_t {
+                if (t.w != tw || t.h != th) { ti = texel_index(t, tu, tv); tw = t.w; th = t.h; }
+                return ti;
+            };
+            if (U.diffuse.px) {
+                const uint8_t* q = U.diffuse.px + index_in(U.diffuse) * U.diffuse.bpp;
+                #pragma unroll
+                for (int i = 0; i < 3; ++i) base[i] = i < U.diffuse.bpp ? (int)__ldg(q + i) : 0;
+            }
             const bool eye = D.kind == 2 /*EYE*/;
             const bool has_nm = !eye && U.normal.px != nullptr;
-            if (has_nm) fetch_texel(U.normal, tu, tv, nmc);
+            if (has_nm) {
+                const uint8_t* q = U.normal.px + index_in(U.normal) * U.normal.bpp;
+                #pragma unroll
+                for (int i = 0; i < 3; ++i) nmc[i] = i < U.normal.bpp ? (int)__ldg(q + i) : 0;
+            }
             float spec_f = 1.0f;
-            if (U.specular.px) { fetch_texel(U.specular, tu, tv, sc); spec_f = (float)sc[0] / 255.0f; }
+            if (U.specular.px) spec_f = (float)__ldg(U.specular.px + index_in(U.specular) * U.specular.bpp) / 255.0f;
             float sf = 1.0f;
             if (shadowed) {
                 const ShadowUniformsDev& SU = reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view];
@@ -941,10 +1041,10 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
                 sf = (float)shadow_factor(SU.shadow, lc, pc);
             }
             trbf::shade_lit_f32(eye, reinterpret_cast<const trbf::LitF*>(D.litf)[view], at, pc, base, has_nm, nmc, spec_f, sf, col);
-        } else {
+        } else if (!FAST || C2) {   // fp64 lighting; the fp32 kernels only carry it for GOURAUD
             const double* MV = D.mats + (size_t)view * 32;
             Varyings vy;
-            if (D.varyings) {
+            if (!FAST && D.varyings) {
                 const double* q = D.varyings + (size_t)g0 * 24;
                 for (int k = 0; k < 3; ++k) {
                     vy.u[k] = q[k * 8]; vy.v[k] = q[k * 8 + 1];
@@ -962,6 +1062,8 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
             }
             if (C2 && D.kind == 5 /*GOURAUD*/) {
                 shade_gouraud(reinterpret_cast<const LitUniforms*>(D.uniforms)[view], vy, pc, col);
+            } else if (FAST) {
+                write = false;   // unreachable: the host only runs the fp32 kernels when every lit draw has a LitF block
             } else if (C2 && D.kind == 4 /*SHADOW_PHONG*/) {
                 const ShadowUniformsDev& SU = reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view];
                 double lc[3][4];

@@ -74,26 +74,103 @@ struct Arena {
 };
 
 // Resource blocks (meshes, textures) are recycled instead of cudaFree'd: cudaFree synchronises the
-// whole device and a caller that re-uploads its scene every frame would pay it each time.  Reuse
-// is safe without a sync because every use of a block is ordered on the context's one stream.
+// whole device and a caller that re-uploads its scene every frame would pay it each time.  A block
+// is tagged with an event recorded on the render stream when it is freed; uploads run on their own
+// stream, so a block is handed out again once that event has completed (the kernels that read it
+// are done).  While fewer than two blocks of a size exist a new one is allocated instead of waiting:
+// a caller that uploads, renders and frees every frame settles into two alternating sets, and the
+// upload of frame n+1 overlaps the rendering of frame n.
 struct BlockCache {
-    std::vector<std::pair<size_t, void*>> free_blocks;
-    cudaError_t get(void** out, size_t bytes) {
+    struct Entry { size_t bytes; void* p; cudaEvent_t freed; };
+    std::vector<Entry> free_blocks;
+    std::vector<cudaEvent_t> ev_pool;
+    // *wait_for: event the consumer stream must wait on before writing the block (nullptr: none)
+    cudaError_t get(void** out, size_t bytes, cudaEvent_t* wait_for) {
         bytes = (bytes + 511) & ~(size_t)511;
-        for (size_t i = 0; i < free_blocks.size(); ++i)
-            if (free_blocks[i].first >= bytes && free_blocks[i].first <= bytes + bytes / 8 + 4096) {
-                *out = free_blocks[i].second;
+        *wait_for = nullptr;
+        int fits = 0, busy = -1;
+        for (size_t i = 0; i < free_blocks.size(); ++i) {
+            Entry& e = free_blocks[i];
+            if (e.bytes < bytes || e.bytes > bytes + bytes / 8 + 4096) continue;
+            ++fits;
+            if (cudaEventQuery(e.freed) == cudaSuccess) {
+                *out = e.p;
+                ev_pool.push_back(e.freed);
                 free_blocks.erase(free_blocks.begin() + i);
                 return cudaSuccess;
             }
+            if (busy < 0) busy = (int)i;
+        }
+        (void)cudaGetLastError();   // cudaErrorNotReady from the queries is not an error
+        if (busy >= 0 && fits >= 2) {          // oldest matching block: let the consumer stream wait for its readers
+            Entry e = free_blocks[busy];
+            *out = e.p;
+            *wait_for = e.freed;               // stays valid: returned to the pool, never destroyed before release()
+            ev_pool.push_back(e.freed);
+            free_blocks.erase(free_blocks.begin() + busy);
+            return cudaSuccess;
+        }
         return cudaMalloc(out, bytes);
     }
-    void put(void* p, size_t bytes) {
-        if (p) free_blocks.emplace_back((bytes + 511) & ~(size_t)511, p);
+    void put(void* p, size_t bytes, cudaStream_t readers) {
+        if (!p) return;
+        cudaEvent_t ev = nullptr;
+        if (ev_pool.size() > 8) {              // keep a few in reserve: an event handed out as wait_for may still be pending
+            ev = ev_pool.front();
+            ev_pool.erase(ev_pool.begin());
+        } else {
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        }
+        cudaEventRecord(ev, readers);
+        free_blocks.push_back(Entry{(bytes + 511) & ~(size_t)511, p, ev});
     }
     void release() {
-        for (auto& b : free_blocks) cudaFree(b.second);
+        for (auto& b : free_blocks) {
+            cudaFree(b.p);
+            cudaEventDestroy(b.freed);
+        }
+        for (auto e : ev_pool) cudaEventDestroy(e);
         free_blocks.clear();
+        ev_pool.clear();
+    }
+};
+
+// Pinned staging ring of the upload stream: the host fills a chunk (interleaving vertex attributes
+// on the way) while earlier chunks are in flight; it only ever waits for the chunk it is about to reuse.
+struct UploadRing {
+    static constexpr size_t CHUNK = (size_t)8 << 20;
+    static constexpr int SLOTS = 4;
+    char* p[SLOTS] = {};
+    cudaEvent_t done[SLOTS] = {};
+    bool used[SLOTS] = {};
+    int next = 0;
+    cudaError_t slot(char** out, cudaEvent_t* ev) {
+        const int i = next;
+        next = (next + 1) % SLOTS;
+        if (!p[i]) {
+            cudaError_t e = cudaHostAlloc((void**)&p[i], CHUNK, cudaHostAllocDefault);
+            if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        } else if (used[i]) {
+            cudaError_t e = cudaEventSynchronize(done[i]);
+            if (e != cudaSuccess) return e;
+        }
+        used[i] = true;
+        *out = p[i];
+        *ev = done[i];
+        return cudaSuccess;
+    }
+    void release() {
+        for (int i = 0; i < SLOTS; ++i) {
+            if (p[i]) {
+                cudaEventSynchronize(done[i]);
+                cudaFreeHost(p[i]);
+                cudaEventDestroy(done[i]);
+            }
+            p[i] = nullptr;
+            used[i] = false;
+        }
     }
 };
 
@@ -136,7 +213,9 @@ struct TrbCtx {
     std::vector<Mesh> meshes;
     std::vector<Tex> textures;
     BlockCache cache;
-    std::vector<float> stage_a, stage_b;  // host staging for the interleaved mesh layouts
+    cudaStream_t upload_stream = nullptr; // H2D of meshes and textures, ordered against the render stream by events
+    cudaEvent_t upload_ev = nullptr;
+    UploadRing ring;
 
     // frame
     FrameDev frame{};
@@ -154,6 +233,10 @@ struct TrbCtx {
 
     // per-draw scratch (stream ordered reuse)
     DevBuf shade_list, tribox, trirec, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
+    DevBuf ctl, heavy_list;          // DrawCtl of the draw in flight, tile slots of its long bins
+    bool sync_draws = false;         // TRB_SYNC_DRAWS=1: size the bins exactly (one stream sync per draw)
+    uint64_t bin_hint = 0;           // entries: 1.25 x the largest R seen so far
+    uint32_t bin_cap_fixed = 0;      // TRB_BIN_CAP: fixed bin capacity in entries (tests force the overflow path with it)
     uint32_t* host_total = nullptr;  // pinned + mapped: the scan kernel stores the bin total straight into it
     uint32_t* host_total_dev = nullptr;
 
@@ -287,7 +370,11 @@ int do_flush(TrbCtx* c) {
         const DrawDev* table = c->draw_table.as<DrawDev>();
         const int nd = (int)c->draws.size();
         const uint32_t* list = c->shade_list.as<uint32_t>();
-        const int variant = (config2 ? 2 : 0) | (c->shade_exact ? 0 : 1);   // template <C2, FAST>
+        // fp32 lighting needs the LitF block of a mesh draw: immediate-mode lit triangles (rasterize() with
+        // host-computed varyings) send the whole flush down the fp64 kernels
+        bool fast = !c->shade_exact;
+        for (const DrawDev& d : c->draws) fast &= !((d.kind == 1 || d.kind == 2 || d.kind == 4) && !d.litf);
+        const int variant = (config2 ? 2 : 0) | (fast ? 1 : 0);   // template <C2, FAST>
         {
             unsigned per_view = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(
                 blocks_for(n), (148ull * 3 * 4 + f.nviews - 1) / f.nviews));
@@ -318,16 +405,18 @@ int do_flush(TrbCtx* c) {
     return TRB_OK;
 }
 
-int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* total_dev) {
+int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t bin_capacity) {
     uint32_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     CU(c->scan_sums.ensure((size_t)nblocks * 4, c->stream));
     {
         Launch L(c, "k_scan_partial");
-        k_scan_partial<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>(), c->scan_total.as<uint32_t>());
+        k_scan_partial<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>(), c->ctl.as<DrawCtl>(), c->warp_max,
+                                                       c->heavy_list.as<uint32_t>());
     }
     {
         Launch L(c, "k_scan_sums");
-        k_scan_sums<<<1, TPB, 0, c->stream>>>(c->scan_sums.as<uint32_t>(), nblocks, total_dev, c->scan_total.as<uint32_t>());
+        k_scan_sums<<<1, TPB, 0, c->stream>>>(c->scan_sums.as<uint32_t>(), nblocks, c->host_total_dev, c->ctl.as<DrawCtl>(),
+                                              bin_capacity);
     }
     {
         Launch L(c, "k_scan_final");
@@ -337,7 +426,13 @@ int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uin
     return TRB_OK;
 }
 
-// bin + rasterise one draw whose vertex records are already in `vrec`
+// bin + rasterise one draw whose vertex records are already in `vrec`.
+//
+// Default (asynchronous): nothing here waits for the device.  The bin buffer is sized from an
+// estimate (4 entries per triangle and view, grown from the R of earlier draws, which the scan
+// kernel leaves in mapped host memory); the kernels after the scan take their work from the
+// device-side DrawCtl, and a draw whose R does not fit is rasterised by the unbinned kernels.
+// TRB_SYNC_DRAWS=1 restores the exact sizing: one stream synchronisation per draw to read R.
 int raster_draw(TrbCtx* c, const GeomArgs& g) {
     const FrameDev& f = c->frame;
     if (g.ntris == 0) return TRB_OK;
@@ -348,12 +443,21 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     CU(c->counts.ensure(nslots * 4, c->stream));
     CU(c->offsets.ensure(nslots * 4, c->stream));
     CU(c->cursor.ensure(nslots * 4, c->stream));
-    if (!c->scan_total.p) {   // longest-bin accumulator: zero once, k_scan_sums re-arms it
-        CU(c->scan_total.ensure(16, c->stream));
-        CU(cudaMemsetAsync(c->scan_total.p, 0, 16, c->stream));
-    }
+    CU(c->heavy_list.ensure(nslots * 4, c->stream));
+    CU(c->ctl.ensure(sizeof(DrawCtl), c->stream));
     CU(cudaMemsetAsync(c->counts.p, 0, nslots * 4, c->stream));
     CU(cudaMemsetAsync(c->cursor.p, 0, nslots * 4, c->stream));
+    CU(cudaMemsetAsync(c->ctl.p, 0, sizeof(DrawCtl), c->stream));
+    uint32_t capacity = 0xFFFFFFFFu;   // synchronous draws size the buffer after the scan
+    if (!c->sync_draws) {
+        // R of the most recent draw the device has finished scanning: a hint, never waited for
+        c->bin_hint = std::max<uint64_t>(c->bin_hint, (uint64_t)c->host_total[0] + c->host_total[0] / 4);
+        uint64_t want = std::max<uint64_t>(c->bin_hint, 4ull * g.ntris * f.nviews + 4ull * nslots + 65536);
+        want = std::min<uint64_t>(want, 0xFFFFFFF0ull);
+        if (c->bin_cap_fixed) want = c->bin_cap_fixed;
+        CU(c->bins.ensure((size_t)want * 4, c->stream));
+        capacity = c->bin_cap_fixed ? c->bin_cap_fixed : (uint32_t)std::min<uint64_t>(c->bins.cap / 4, 0xFFFFFFF0ull);
+    }
     dim3 tgrid(blocks_for(g.ntris), f.nviews);
     {
         Launch L(c, "k_setup_count");
@@ -365,20 +469,22 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         k_direct_resolve<<<tgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>());
     }
     CU(cudaGetLastError());
-    // the bin array is sized by the count pass (SURVEY 7 "hard parts": config 5 memory).  The total
-    // is stored by the scan kernel directly into mapped host memory: a cudaMemcpy would queue on
-    // the device->host copy engine behind a pipelined readback (trb_readback_async).
-    int rc = exclusive_scan(c, c->counts.as<uint32_t>(), (uint32_t)nslots, c->offsets.as<uint32_t>(),
-                            c->host_total_dev);
+    int rc = exclusive_scan(c, c->counts.as<uint32_t>(), (uint32_t)nslots, c->offsets.as<uint32_t>(), capacity);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(c->stream));
-    const uint32_t R = c->host_total[0], longest = c->host_total[1];
-    if (R == 0) return TRB_OK;
-    CU(c->bins.ensure((size_t)R * 4, c->stream));
+    bool long_bins = true;             // unknown without a round trip: k_raster's persistent grid finds an empty list
+    if (c->sync_draws) {
+        // the total is stored by the scan kernel directly into mapped host memory: a cudaMemcpy would
+        // queue on the device->host copy engine behind a pipelined readback (trb_readback_async)
+        CU(cudaStreamSynchronize(c->stream));
+        const uint32_t R = c->host_total[0];
+        if (R == 0) return TRB_OK;
+        long_bins = c->host_total[1] > c->warp_max;
+        CU(c->bins.ensure((size_t)R * 4, c->stream));
+    }
     {
         Launch L(c, "k_fill");
         k_fill<<<tgrid, TPB, 0, c->stream>>>(f, g.ntris, c->tribox.as<uint2>(), c->offsets.as<uint32_t>(),
-                                            c->cursor.as<uint32_t>(), c->bins.as<uint32_t>());
+                                            c->cursor.as<uint32_t>(), c->bins.as<uint32_t>(), c->ctl.as<DrawCtl>());
     }
     RasterArgs ra;
     ra.ntris = g.ntris;
@@ -391,13 +497,30 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     ra.small_min = c->small_min;
     ra.large_ns = c->large_ns;
     ra.warp_max = c->warp_max;
+    ra.ctl = c->ctl.as<DrawCtl>();
+    ra.heavy_list = c->heavy_list.as<uint32_t>();
     if (c->warp_max > 0) {   // bins of 1..warp_max triangles: one warp per tile
         Launch L(c, "k_raster_warp");
         k_raster_warp<<<dim3((f.ntiles + RW_WARPS - 1) / RW_WARPS, f.nviews), RW_WARPS * 32, 0, c->stream>>>(f, ra);
     }
-    if (longest > c->warp_max) {   // longer bins: one CTA per tile
+    if (long_bins) {         // longer bins: one CTA per tile, persistent grid over the device-side list
+        const unsigned grid = (unsigned)std::min<size_t>(nslots, (size_t)148 * TRB_RASTER_MIN_BLOCKS);
         Launch L(c, "k_raster");
-        k_raster<<<dim3(f.ntiles, f.nviews), TPB, 0, c->stream>>>(f, ra);
+        k_raster<<<grid, TPB, 0, c->stream>>>(f, ra);
+    }
+    if (!c->sync_draws) {    // stand-ins for a draw that overflowed its bins (exit at once otherwise)
+        const dim3 grid((unsigned)std::min<unsigned>(blocks_for((unsigned long long)g.ntris * 32),
+                                                    std::max(1u, 148u * 8 / (unsigned)f.nviews)), f.nviews);
+        {
+            Launch L(c, "k_unbinned_depth");
+            k_unbinned<false><<<grid, TPB, 0, c->stream>>>(f, g.ntris, g.id_base, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
+                                                          c->ctl.as<DrawCtl>());
+        }
+        {
+            Launch L(c, "k_unbinned_ids");
+            k_unbinned<true><<<grid, TPB, 0, c->stream>>>(f, g.ntris, g.id_base, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
+                                                         c->ctl.as<DrawCtl>());
+        }
     }
     CU(cudaGetLastError());
     return TRB_OK;
@@ -494,13 +617,18 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_DIRECT_AREA")) c->direct_area = std::max(0, atoi(e));
     if (const char* e = getenv("TRB_WARP_MAX")) c->warp_max = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("TRB_SHADE_EXACT")) c->shade_exact = atoi(e) != 0;
+    if (const char* e = getenv("TRB_SYNC_DRAWS")) c->sync_draws = atoi(e) != 0;
+    if (const char* e = getenv("TRB_BIN_CAP")) c->bin_cap_fixed = (uint32_t)std::max(1, atoi(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->upload_ev, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&c->ev_a) != cudaSuccess || cudaEventCreate(&c->ev_b) != cudaSuccess ||
         cudaHostAlloc((void**)&c->host_total, 64, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&c->host_total_dev, c->host_total, 0) != cudaSuccess) {
         delete c;
         return TRB_E_CUDA;
     }
+    memset(c->host_total, 0, 64);
     // 8 CTAs x 24 KB of per-warp tiles per SM: ask for the large shared-memory carveout
     cudaFuncSetAttribute(k_raster_warp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = c;
@@ -511,6 +639,7 @@ int trb_destroy(TrbCtx* c) {
     if (!c) return TRB_E_ARG;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->upload_stream) cudaStreamSynchronize(c->upload_stream);
     for (auto& m : c->meshes)
         if (m.alive) {
             cudaFree(m.pos4);
@@ -520,7 +649,7 @@ int trb_destroy(TrbCtx* c) {
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
     DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
-                      &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->scratch_a,
+                      &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->ctl, &c->heavy_list, &c->scratch_a,
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.keys.release();
@@ -536,6 +665,9 @@ int trb_destroy(TrbCtx* c) {
     }
     c->arena.release();
     c->cache.release();
+    c->ring.release();
+    if (c->upload_ev) cudaEventDestroy(c->upload_ev);
+    if (c->upload_stream) cudaStreamDestroy(c->upload_stream);
     for (auto& p : c->prof_pending) {
         cudaEventDestroy(p.a);
         cudaEventDestroy(p.b);
@@ -552,6 +684,38 @@ int trb_destroy(TrbCtx* c) {
 const char* trb_last_error(TrbCtx* c) { return c ? c->err.c_str() : "null context"; }
 const char* trb_backend_name(void) { return "cuda-sm100a"; }
 
+}  // extern "C"
+
+namespace {
+// device block for a resource + `bytes` of it filled through the pinned ring on the upload stream.
+// fill(dst, offset, n) writes bytes [offset, offset + n) of the device layout into pinned memory.
+template <class Fill>
+int upload_block(TrbCtx* c, void** dev, size_t bytes, size_t granule, Fill fill) {
+    cudaEvent_t wait_for = nullptr;
+    CU(c->cache.get(dev, bytes, &wait_for));
+    if (wait_for) CU(cudaStreamWaitEvent(c->upload_stream, wait_for, 0));   // its last readers (render stream) first
+    const size_t step = UploadRing::CHUNK / granule * granule;
+    for (size_t off = 0; off < bytes; off += step) {
+        const size_t n = std::min(step, bytes - off);
+        char* stage = nullptr;
+        cudaEvent_t done = nullptr;
+        CU(c->ring.slot(&stage, &done));
+        fill(stage, off, n);
+        CU(cudaMemcpyAsync((char*)*dev + off, stage, n, cudaMemcpyHostToDevice, c->upload_stream));
+        CU(cudaEventRecord(done, c->upload_stream));
+    }
+    return TRB_OK;
+}
+// everything uploaded so far becomes visible to the render stream
+int publish_uploads(TrbCtx* c) {
+    CU(cudaEventRecord(c->upload_ev, c->upload_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->upload_ev, 0));
+    return TRB_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float* uv2, uint32_t nverts,
                     const uint32_t* idx, uint64_t nidx, TrbMesh* out) {
     if (!c || !pos3 || !out || nidx % 3 || nverts == 0) return fail(c, TRB_E_ARG, "upload_mesh: bad argument");
@@ -562,38 +726,44 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
         for (uint64_t i = 0; i < nidx; ++i)
             if (idx[i] >= nverts) return fail(c, TRB_E_ARG, "upload_mesh: index out of range");
     if (!idx && nidx > nverts) return fail(c, TRB_E_ARG, "upload_mesh: implicit indices exceed nverts");
-    // host-side interleave into the two device layouts: float4 positions for the coalesced vertex
-    // kernel, 32-byte {pos,nrm,uv} records (one DRAM sector) for the shade kernel's gathers
-    std::vector<float>&p4 = c->stage_a, &a8 = c->stage_b;
-    CU(cudaStreamSynchronize(c->stream));  // the staging vectors of the previous upload are free again
-    p4.resize((size_t)nverts * 4);
-    a8.resize((size_t)nverts * 8);
-    for (uint32_t v = 0; v < nverts; ++v) {
-        float* p = &p4[(size_t)v * 4];
-        float* a = &a8[(size_t)v * 8];
-        p[0] = a[0] = pos3[3 * (size_t)v];
-        p[1] = a[1] = pos3[3 * (size_t)v + 1];
-        p[2] = a[2] = pos3[3 * (size_t)v + 2];
-        p[3] = 1.0f;
-        a[3] = nrm3 ? nrm3[3 * (size_t)v] : 0.f;       // Model::normal fallback (0,0,1), model.cpp:404
-        a[4] = nrm3 ? nrm3[3 * (size_t)v + 1] : 0.f;
-        a[5] = nrm3 ? nrm3[3 * (size_t)v + 2] : 1.f;
-        a[6] = uv2 ? uv2[2 * (size_t)v] : 0.f;
-        a[7] = uv2 ? uv2[2 * (size_t)v + 1] : 0.f;
-    }
+    // The host interleaves into the two device layouts - float4 positions for the coalesced vertex
+    // kernel, 32-byte {pos,nrm,uv} records (one DRAM sector) for the shade kernel's gathers - straight
+    // into pinned chunks that the upload stream drains while the render stream keeps rendering.
+    // The caller's arrays are fully consumed when this returns.
     Mesh m;
     m.nverts = nverts;
     m.nidx = nidx;
-    CU(c->cache.get((void**)&m.pos4, p4.size() * 4));
-    CU(c->cache.get((void**)&m.attr8, a8.size() * 4));
-    CU(cudaMemcpyAsync(m.pos4, p4.data(), p4.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(m.attr8, a8.data(), a8.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    rc = upload_block(c, (void**)&m.pos4, (size_t)nverts * 16, 16, [&](char* dst, size_t off, size_t n) {
+        float* p = reinterpret_cast<float*>(dst);
+        const size_t v0 = off / 16, nv = n / 16;
+        for (size_t v = 0; v < nv; ++v, p += 4) {
+            const float* s = pos3 + 3 * (v0 + v);
+            p[0] = s[0]; p[1] = s[1]; p[2] = s[2]; p[3] = 1.0f;
+        }
+    });
+    if (rc) return rc;
+    rc = upload_block(c, (void**)&m.attr8, (size_t)nverts * 32, 32, [&](char* dst, size_t off, size_t n) {
+        float* a = reinterpret_cast<float*>(dst);
+        const size_t v0 = off / 32, nv = n / 32;
+        for (size_t v = 0; v < nv; ++v, a += 8) {
+            const size_t g = v0 + v;
+            a[0] = pos3[3 * g]; a[1] = pos3[3 * g + 1]; a[2] = pos3[3 * g + 2];
+            a[3] = nrm3 ? nrm3[3 * g] : 0.f;           // Model::normal fallback (0,0,1), model.cpp:404
+            a[4] = nrm3 ? nrm3[3 * g + 1] : 0.f;
+            a[5] = nrm3 ? nrm3[3 * g + 2] : 1.f;
+            a[6] = uv2 ? uv2[2 * g] : 0.f;
+            a[7] = uv2 ? uv2[2 * g + 1] : 0.f;
+        }
+    });
+    if (rc) return rc;
     if (idx) {
-        CU(c->cache.get((void**)&m.idx, nidx * 4));
-        CU(cudaMemcpyAsync(m.idx, idx, nidx * 4, cudaMemcpyHostToDevice, c->stream));
+        rc = upload_block(c, (void**)&m.idx, nidx * 4, 4, [&](char* dst, size_t off, size_t n) {
+            memcpy(dst, reinterpret_cast<const char*>(idx) + off, n);
+        });
+        if (rc) return rc;
     }
-    // no sync: copies from pageable memory are staged before cudaMemcpyAsync returns, pinned callers
-    // must keep their arrays alive until the next synchronising call (documented in trb.h)
+    rc = publish_uploads(c);
+    if (rc) return rc;
     m.alive = true;
     size_t slot = 0;
     while (slot < c->meshes.size() && c->meshes[slot].alive) ++slot;  // handles of freed meshes are reused
@@ -604,10 +774,12 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
 
 int trb_free_mesh(TrbCtx* c, TrbMesh h) {
     if (!c || h == 0 || h > c->meshes.size() || !c->meshes[h - 1].alive) return fail(c, TRB_E_ARG, "free_mesh");
+    int rc = check_device(c);
+    if (rc) return rc;
     Mesh& m = c->meshes[h - 1];
-    c->cache.put(m.pos4, (size_t)m.nverts * 16);
-    c->cache.put(m.attr8, (size_t)m.nverts * 32);
-    if (m.idx) c->cache.put(m.idx, m.nidx * 4);
+    c->cache.put(m.pos4, (size_t)m.nverts * 16, c->stream);   // tagged: reusable once the kernels queued so far are done
+    c->cache.put(m.attr8, (size_t)m.nverts * 32, c->stream);
+    if (m.idx) c->cache.put(m.idx, m.nidx * 4, c->stream);
     m = Mesh();
     return TRB_OK;
 }
@@ -622,8 +794,10 @@ int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, 
     t.h = h;
     t.bpp = bpp;
     size_t bytes = (size_t)w * h * bpp;
-    CU(c->cache.get((void**)&t.px, bytes));
-    CU(cudaMemcpyAsync(t.px, texels, bytes, cudaMemcpyHostToDevice, c->stream));
+    rc = upload_block(c, (void**)&t.px, bytes, 1, [&](char* dst, size_t off, size_t n) { memcpy(dst, texels + off, n); });
+    if (rc) return rc;
+    rc = publish_uploads(c);
+    if (rc) return rc;
     t.alive = true;
     size_t slot = 0;
     while (slot < c->textures.size() && c->textures[slot].alive) ++slot;
@@ -634,8 +808,10 @@ int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, 
 
 int trb_free_texture(TrbCtx* c, TrbTex h) {
     if (!c || h == 0 || h > c->textures.size() || !c->textures[h - 1].alive) return fail(c, TRB_E_ARG, "free_texture");
+    int rc = check_device(c);
+    if (rc) return rc;
     Tex& x = c->textures[h - 1];
-    c->cache.put(x.px, (size_t)x.w * x.h * x.bpp);
+    c->cache.put(x.px, (size_t)x.w * x.h * x.bpp, c->stream);
     x = Tex();
     return TRB_OK;
 }
@@ -752,7 +928,7 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
     g.nverts = m.nverts;
     g.id_base = (uint32_t)c->next_id;
     g.vrec = vrec;
-    rc = raster_draw(c, g);   // synchronises once (bin sizing), which also covers `hm`
+    rc = raster_draw(c, g);   // `hm`, `hl` are pageable: their copies were staged before cudaMemcpyAsync returned
     if (rc) return rc;
     DrawDev d{};
     d.id_base = g.id_base;
@@ -1281,7 +1457,9 @@ int trb_composite_shade_p2p(TrbCtx* c, int y0, int y1) {
         Launch L(c, "k_composite_shade_p2p");
         const DrawDev* table = c->draw_table.as<DrawDev>();
         const int nd = (int)c->draws.size();
-        switch ((config2 ? 2 : 0) | (c->shade_exact ? 0 : 1)) {
+        bool fast = !c->shade_exact;
+        for (const DrawDev& d : c->draws) fast &= !((d.kind == 1 || d.kind == 2 || d.kind == 4) && !d.litf);
+        switch ((config2 ? 2 : 0) | (fast ? 1 : 0)) {
             case 0: k_composite_shade_p2p<false, false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
             case 1: k_composite_shade_p2p<false, true><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
             case 2: k_composite_shade_p2p<true, false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
