@@ -416,6 +416,7 @@ def main():
             t0 = time.perf_counter()
             for s in range(e_steps):
                 e2e_step(1 + s, with_depth)
+            t_host = time.perf_counter() - t0                          # host time to enqueue the steps (nothing waited for)
             r.readback_wait()                                          # every host buffer is complete here
             barrier()
             dt = time.perf_counter() - t0
@@ -425,7 +426,8 @@ def main():
             return {"value": tris_step_all * e_steps / float(t.item()), "unit": "triangles/s",
                     "h2d_bytes_per_step": int(h2d + nviews * 3 * 256),
                     "d2h_bytes_per_step": int(nviews * P * (3 + (8 if with_depth else 0))),
-                    "steps": e_steps, "ms_per_step": 1e3 * float(t.item()) / e_steps}
+                    "steps": e_steps, "ms_per_step": 1e3 * float(t.item()) / e_steps,
+                    "host_enqueue_ms_per_step": 1e3 * t_host / e_steps}
 
         e2e = e2e_run(False)
         e2e["note"] = ("per step: upload meshes+textures, render, read back the BGR framebuffer of every frame into pinned "

@@ -197,9 +197,31 @@ TRB_EXPORT int TRB_FN(depth_image)(TrbCtx* ctx, int view, uint8_t* grey_out);
 /* final = phong * ao (main.cpp:768-783), BGR out */
 TRB_EXPORT int TRB_FN(composite_ao)(TrbCtx* ctx, int view, uint8_t* bgr_out);
 
+/* ---- TGA files of the frame ---------------------------------------- */
+/* The images main.cpp writes out: framebuffer.tga (main.cpp:743), zbuffer.tga (:312), ssao.tga
+ * (:765), final.tga (:785). */
+enum TrbImage {
+    TRB_IMAGE_COLOR = 0,  /* BGR framebuffer, 24 bit */
+    TRB_IMAGE_DEPTH = 1,  /* save_zbuffer_image grey map, 8 bit */
+    TRB_IMAGE_SSAO = 2,   /* ambient-occlusion map, 8 bit */
+    TRB_IMAGE_FINAL = 3   /* framebuffer * ao, 24 bit */
+};
+/* Replaces TGAImage::write_tga_file(name, vflip = true, rle = true) (tgaimage.cpp:160-191) and its
+ * packetiser unload_rle_data (tgaimage.cpp:193-242) for every view of the batch: out[v] receives the
+ * complete file image - 18-byte header + run-length packets, byte for byte what the reference
+ * writes - and sizes[v] its length.  The packets are built on the device, so only the compressed
+ * bytes cross PCIe.  out[v] may be NULL (size query only); `capacity` is the size of each out[v]
+ * (width*height*bpp + width*height/2 + 19 always suffices:
+ * the shortest packet the encoder emits away from the image end is a raw packet of two pixels).  Synchronises. */
+TRB_EXPORT int TRB_FN(encode_tga)(TrbCtx* ctx, int which, uint8_t* const* out, uint64_t capacity, uint64_t* sizes);
+
 /* ---- readback ------------------------------------------------------------------------ */
 /* framebuffer bytes, BGR, (x+y*w)*3 like TGAImage(w,h,RGB) (tgaimage.cpp:32-39) */
 TRB_EXPORT int TRB_FN(read_color)(TrbCtx* ctx, int view, uint8_t* bgr_out);
+/* The inverse: replace the view's framebuffer by a host image in TGAImage order (the caller owns a
+ * TGAImage in the reference and may set() pixels itself, tgaimage.cpp:32-39; this is the bulk form
+ * of that).  Pending draws are resolved first.  Depth is untouched. */
+TRB_EXPORT int TRB_FN(write_color)(TrbCtx* ctx, int view, const uint8_t* bgr);
 /* the global zbuffer (our_gl.h:20): w*h doubles, +inf where nothing was drawn */
 TRB_EXPORT int TRB_FN(read_depth)(TrbCtx* ctx, int view, double* z_out);
 /* winning triangle id per pixel BEFORE flush: 0xFFFFFFFF = none, 0 = already shaded,

@@ -617,6 +617,11 @@ int orc_read_color(TrbCtx* c, int view, uint8_t* out) {
     std::memcpy(out, c->views[view].bgr.data(), c->views[view].bgr.size());
     return TRB_OK;
 }
+int orc_write_color(TrbCtx* c, int view, const uint8_t* bgr) {
+    if (!c || view < 0 || view >= c->nviews || !bgr) return fail(c, TRB_E_ARG, "write_color");
+    std::memcpy(c->views[view].bgr.data(), bgr, c->views[view].bgr.size());
+    return TRB_OK;
+}
 int orc_read_depth(TrbCtx* c, int view, double* out) {
     if (!c || view < 0 || view >= c->nviews || !out) return fail(c, TRB_E_ARG, "read_depth");
     std::memcpy(out, c->views[view].z.data(), sizeof(double) * c->views[view].z.size());

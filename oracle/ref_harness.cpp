@@ -635,11 +635,17 @@ static const uint8_t* orc_view_color(TrbCtx* c, int view) {
     if (!c || view < 0 || view >= c->nviews) return nullptr;
     return c->views[view].color.buffer();
 }
+#define ORC_HAVE_REFERENCE_TGA 1   // post_restate.inc: encode through the reference's own TGAImage writer
 #include "post_restate.inc"
 
 int orc_read_color(TrbCtx* c, int view, uint8_t* out) {
     if (!c || view < 0 || view >= c->nviews || !out) return fail(c, TRB_E_ARG, "read_color");
     std::memcpy(out, c->views[view].color.buffer(), (size_t)c->w * c->h * 3);
+    return TRB_OK;
+}
+int orc_write_color(TrbCtx* c, int view, const uint8_t* bgr) {
+    if (!c || view < 0 || view >= c->nviews || !bgr) return fail(c, TRB_E_ARG, "write_color");
+    std::memcpy(c->views[view].color.buffer(), bgr, (size_t)c->w * c->h * 3);
     return TRB_OK;
 }
 int orc_read_depth(TrbCtx* c, int view, double* out) {

@@ -10,6 +10,7 @@ static const double* orc_view_depth(TrbCtx*, int, int* w, int* h);
 static const unsigned char* orc_view_color(TrbCtx*, int);
 static int g_w, g_h;
 static const unsigned char* g_color;
+#define ORC_POST_PASSES_ONLY 1
 #include "../../../oracle/post_restate.inc"
 static const double* orc_view_depth(TrbCtx*, int, int* w, int* h) { *w = g_w; *h = g_h; return zbuffer.data(); }
 static const unsigned char* orc_view_color(TrbCtx*, int) { return g_color; }

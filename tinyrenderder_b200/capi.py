@@ -21,6 +21,11 @@ SHADER_DEPTH = 3
 SHADER_SHADOW_PHONG = 4
 SHADER_GOURAUD = 5
 
+IMAGE_COLOR = 0
+IMAGE_DEPTH = 1
+IMAGE_SSAO = 2
+IMAGE_FINAL = 3
+
 VIS_NONE = 0xFFFFFFFF
 VIS_SHADED = 0
 
@@ -111,7 +116,9 @@ SIGNATURES = {
     "ssao": (C.c_int, [_P, C.c_int, _P]),
     "depth_image": (C.c_int, [_P, C.c_int, _P]),
     "composite_ao": (C.c_int, [_P, C.c_int, _P]),
+    "encode_tga": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _P]),
     "read_color": (C.c_int, [_P, C.c_int, _P]),
+    "write_color": (C.c_int, [_P, C.c_int, _P]),
     "read_depth": (C.c_int, [_P, C.c_int, _P]),
     "read_visibility": (C.c_int, [_P, C.c_int, _P]),
     "readback_async": (C.c_int, [_P, _P, _P]),
@@ -365,6 +372,10 @@ class Renderer:
         self._ck(self._fn["read_depth"](self.h, view, _ptr(out)), "read_depth")
         return out
 
+    def write_color(self, bgr, view=0):
+        a = np.ascontiguousarray(bgr, dtype=np.uint8).reshape(self.height, self.width, 3)
+        self._ck(self._fn["write_color"](self.h, view, _ptr(a)), "write_color")
+
     def readback_async(self, colors=None, depths=None):
         """queue the device->host copy of every view into the given lists of (pinned) numpy arrays"""
         def table(arrs):
@@ -387,6 +398,16 @@ class Renderer:
         out = np.empty((self.height, self.width), dtype=np.uint8)
         self._ck(self._fn["ssao"](self.h, view, _ptr(out)), "ssao")
         return out
+
+    def encode_tga(self, which=0):
+        """TGA file images (18-byte header + RLE packets, tgaimage.cpp:160-242) of every view: list of bytes"""
+        n = self.nviews
+        cap = self.width * self.height * 3 + self.width * self.height // 2 + 64
+        bufs = [np.empty(cap, dtype=np.uint8) for _ in range(n)]
+        table = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_uint64 * n)()
+        self._ck(self._fn["encode_tga"](self.h, which, C.cast(table, _P), cap, C.cast(sizes, _P)), "encode_tga")
+        return [bufs[v][:sizes[v]].tobytes() for v in range(n)]
 
     def depth_image(self, view=0):
         out = np.empty((self.height, self.width), dtype=np.uint8)

@@ -3,6 +3,7 @@
 // entry point that needs the device fails with TRB_E_CUDA when it is not there.
 #include "../../include/trb.h"
 #include "kernels.cuh"
+#include "tga_rle.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -234,6 +235,7 @@ struct TrbCtx {
     // per-draw scratch (stream ordered reuse)
     DevBuf shade_list, tribox, trirec, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
     DevBuf ctl, heavy_list;          // DrawCtl of the draw in flight, tile slots of its long bins
+    DevBuf rle_work, rle_src, rle_out; // device-side TGA RLE encoder (tga_rle.cuh)
     bool sync_draws = false;         // TRB_SYNC_DRAWS=1: size the bins exactly (one stream sync per draw)
     uint64_t bin_hint = 0;           // entries: 1.25 x the largest R seen so far
     uint32_t bin_cap_fixed = 0;      // TRB_BIN_CAP: fixed bin capacity in entries (tests force the overflow path with it)
@@ -649,7 +651,7 @@ int trb_destroy(TrbCtx* c) {
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
     DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
-                      &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->ctl, &c->heavy_list, &c->scratch_a,
+                      &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->ctl, &c->heavy_list, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.keys.release();
@@ -1088,6 +1090,15 @@ int trb_read_color(TrbCtx* c, int view, uint8_t* out) {
     CU(cudaStreamSynchronize(c->stream));
     return TRB_OK;
 }
+int trb_write_color(TrbCtx* c, int view, const uint8_t* bgr) {
+    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !bgr) return fail(c, TRB_E_ARG, "write_color");
+    int rc = do_flush(c);
+    if (rc) return rc;
+    size_t bytes = (size_t)c->frame.npix * 3;
+    CU(cudaMemcpyAsync(c->color.as<uint8_t>() + bytes * view, bgr, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // the caller's image may be pageable and reused at once
+    return TRB_OK;
+}
 int trb_read_depth(TrbCtx* c, int view, double* out) {
     if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "read_depth");
     int rc = do_flush(c);
@@ -1215,63 +1226,178 @@ int trb_synchronize(TrbCtx* c) {
 }
 
 // ---- post passes -----------------------------------------------------------------------------
-int trb_ssao(TrbCtx* c, int view, uint8_t* out) {
-    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "ssao");
-    int rc = do_flush(c);
-    if (rc) return rc;
+}  // extern "C"
+
+namespace {
+// one post-pass image of `view` into device memory: TRB_IMAGE_SSAO / _DEPTH (1 byte per pixel),
+// TRB_IMAGE_FINAL (3 bytes per pixel).  The frame must be flushed.
+int post_plane(TrbCtx* c, int which, int view, uint8_t* dst) {
     const FrameDev& f = c->frame;
-    CU(c->scratch_a.ensure(f.npix, c->stream));
     SsaoDirs d;
     ssao_dirs(d);
-    {
+    if (which == TRB_IMAGE_SSAO) {
         Launch L(c, "k_ssao");
-        k_ssao<<<dim3(f.tw, f.th), TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.W, f.H, d, c->scratch_a.as<uint8_t>());
-    }
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, c->scratch_a.p, f.npix, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return TRB_OK;
-}
-int trb_composite_ao(TrbCtx* c, int view, uint8_t* out) {
-    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "composite_ao");
-    int rc = do_flush(c);
-    if (rc) return rc;
-    const FrameDev& f = c->frame;
-    CU(c->scratch_a.ensure(f.npix * 3, c->stream));
-    SsaoDirs d;
-    ssao_dirs(d);
-    {
+        k_ssao<<<dim3(f.tw, f.th), TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.W, f.H, d, dst);
+    } else if (which == TRB_IMAGE_FINAL) {
         Launch L(c, "k_composite_ao");
         k_composite_ao<<<dim3(f.tw, f.th), TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.color + f.npix * 3 * view,
-                                                                 f.W, f.H, d, c->scratch_a.as<uint8_t>());
+                                                                 f.W, f.H, d, dst);
+    } else if (which == TRB_IMAGE_DEPTH) {
+        CU(c->scratch_b.ensure(64, c->stream));
+        unsigned long long init[2] = {~0ull, 0ull};
+        CU(cudaMemcpyAsync(c->scratch_b.p, init, 16, cudaMemcpyHostToDevice, c->stream));
+        {
+            unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(f.npix), 148ull * 16);
+            Launch L(c, "k_depth_range");
+            k_depth_range<<<grid, TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.npix, c->scratch_b.as<unsigned long long>());
+        }
+        {
+            Launch L(c, "k_depth_image");
+            k_depth_image<<<blocks_for(f.npix), TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.npix,
+                                                                      c->scratch_b.as<unsigned long long>(), dst);
+        }
+    } else {
+        return fail(c, TRB_E_ARG, "post pass: unknown image");
     }
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, c->scratch_a.p, f.npix * 3, cudaMemcpyDeviceToHost, c->stream));
+    return TRB_OK;
+}
+int post_to_host(TrbCtx* c, int which, int view, uint8_t* out, const char* what) {
+    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, what);
+    int rc = do_flush(c);
+    if (rc) return rc;
+    const size_t bytes = (size_t)c->frame.npix * (which == TRB_IMAGE_FINAL ? 3 : 1);
+    CU(c->scratch_a.ensure(bytes, c->stream));
+    rc = post_plane(c, which, view, c->scratch_a.as<uint8_t>());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, c->scratch_a.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return TRB_OK;
 }
-int trb_depth_image(TrbCtx* c, int view, uint8_t* out) {
-    if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "depth_image");
+
+// the five passes of tga_rle.cuh over `total` = nviews * npix pixels of BPP bytes at `px`
+template <int BPP>
+int rle_passes(TrbCtx* c, const uint8_t* px, size_t npix, uint32_t nviews, uint8_t* out, uint32_t* view_offsets_dev) {
+    using namespace trbr;
+    const size_t total = npix * nviews;
+    const size_t ns_max = total / 2 + nviews + 2;                     // a long run is at least two pixels
+    // one allocation: flags | ls_excl | seg_start | long_end | bytes | base | map | prefix | scan aggregates | totals
+    const size_t nb_px = (total + RBLOCK - 1) / RBLOCK, nb_seg = (ns_max + RBLOCK - 1) / RBLOCK;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_ls = take(total * 4), o_start = take(ns_max * 4), o_end = take(ns_max * 4), o_bytes = take(ns_max * 4),
+                 o_base = take(ns_max * 4), o_agg = take(std::max(nb_px, nb_seg) * 4), o_tot = take(64),
+                 o_flags = take(total), o_map = take(ns_max), o_prefix = take(ns_max);
+    CU(c->rle_work.ensure(off, c->stream));
+    char* w = c->rle_work.as<char>();
+    uint8_t* flags = (uint8_t*)(w + o_flags);
+    uint32_t* ls_excl = (uint32_t*)(w + o_ls);
+    uint32_t* agg = (uint32_t*)(w + o_agg);
+    uint32_t* ls_total = (uint32_t*)(w + o_tot);
+    RleTables t;
+    t.seg_start = (uint32_t*)(w + o_start);
+    t.long_end = (uint32_t*)(w + o_end);
+    t.bytes = (uint32_t*)(w + o_bytes);
+    t.base = (uint32_t*)(w + o_base);
+    t.map = (uint8_t*)(w + o_map);
+    t.prefix = (uint8_t*)(w + o_prefix);
+    const unsigned gpx = (unsigned)((total + RTPB - 1) / RTPB), gseg = (unsigned)((ns_max + RTPB - 1) / RTPB);
+    // segments past the real count (only known on the device) are given neutral inputs: a zero map would
+    // be wrong, so their tables are zeroed and the per-segment kernels stop at the device-side count
+    CU(cudaMemsetAsync(t.bytes, 0, ns_max * 4, c->stream));
+    CU(cudaMemsetAsync(t.map, 2, ns_max, c->stream));                 // identity map
+    {
+        Launch L(c, "k_rle_flags");
+        k_rle_flags<BPP><<<gpx, RTPB, 0, c->stream>>>(px, npix, total, flags);
+    }
+    {   // 2: segment index of every pixel
+        Launch L(c, "k_rle_scan");
+        LoadLongStart ld{flags};
+        k_rscan_partial<AddU32, LoadLongStart><<<(unsigned)nb_px, RTPB, 0, c->stream>>>(ld, total, agg);
+        k_rscan_sums<AddU32><<<1, RTPB, 0, c->stream>>>(agg, (uint32_t)nb_px, ls_total);
+        k_rscan_final<AddU32, LoadLongStart><<<(unsigned)nb_px, RTPB, 0, c->stream>>>(ld, total, agg, ls_excl);
+    }
+    {
+        Launch L(c, "k_rle_segments");
+        k_rle_segments<<<gpx, RTPB, 0, c->stream>>>(flags, ls_excl, ls_total, npix, total, nviews, t);
+    }
+    {   // 3: entry class of every segment
+        Launch L(c, "k_rle_maps");
+        k_rle_maps<<<gseg, RTPB, 0, c->stream>>>(ls_total, nviews, t);
+        LoadPlain<uint8_t> ld{t.map};
+        uint8_t* agg8 = (uint8_t*)agg;
+        k_rscan_partial<MapCompose, LoadPlain<uint8_t>><<<(unsigned)nb_seg, RTPB, 0, c->stream>>>(ld, ns_max, agg8);
+        k_rscan_sums<MapCompose><<<1, RTPB, 0, c->stream>>>(agg8, (uint32_t)nb_seg, (uint8_t*)(ls_total + 2));
+        k_rscan_final<MapCompose, LoadPlain<uint8_t>><<<(unsigned)nb_seg, RTPB, 0, c->stream>>>(ld, ns_max, agg8, t.prefix);
+    }
+    {   // 4: where every segment writes
+        Launch L(c, "k_rle_sizes");
+        k_rle_sizes<BPP><<<gseg, RTPB, 0, c->stream>>>(ls_total, nviews, t);
+        LoadPlain<uint32_t> ld{t.bytes};
+        k_rscan_partial<AddU32, LoadPlain<uint32_t>><<<(unsigned)nb_seg, RTPB, 0, c->stream>>>(ld, ns_max, agg);
+        k_rscan_sums<AddU32><<<1, RTPB, 0, c->stream>>>(agg, (uint32_t)nb_seg, ls_total + 1);
+        k_rscan_final<AddU32, LoadPlain<uint32_t>><<<(unsigned)nb_seg, RTPB, 0, c->stream>>>(ld, ns_max, agg, t.base);
+    }
+    {
+        Launch L(c, "k_rle_emit");
+        k_rle_emit<BPP><<<gpx, RTPB, 0, c->stream>>>(px, flags, ls_excl, npix, total, t, out);
+        k_rle_view_offsets<<<(nviews + 1 + 255) / 256, 256, 0, c->stream>>>(ls_excl, ls_total, npix, nviews, t, view_offsets_dev);
+    }
+    CU(cudaGetLastError());
+    return TRB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int trb_ssao(TrbCtx* c, int view, uint8_t* out) { return post_to_host(c, TRB_IMAGE_SSAO, view, out, "ssao"); }
+int trb_composite_ao(TrbCtx* c, int view, uint8_t* out) { return post_to_host(c, TRB_IMAGE_FINAL, view, out, "composite_ao"); }
+int trb_depth_image(TrbCtx* c, int view, uint8_t* out) { return post_to_host(c, TRB_IMAGE_DEPTH, view, out, "depth_image"); }
+
+int trb_encode_tga(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity, uint64_t* sizes) {
+    if (!c || !c->in_frame || !out || !sizes || which < TRB_IMAGE_COLOR || which > TRB_IMAGE_FINAL)
+        return fail(c, TRB_E_ARG, "encode_tga: bad argument");
     int rc = do_flush(c);
     if (rc) return rc;
     const FrameDev& f = c->frame;
-    CU(c->scratch_a.ensure(f.npix, c->stream));
-    CU(c->scratch_b.ensure(64, c->stream));
-    unsigned long long init[2] = {~0ull, 0ull};
-    CU(cudaMemcpyAsync(c->scratch_b.p, init, 16, cudaMemcpyHostToDevice, c->stream));
-    {
-        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(f.npix), 148ull * 16);
-        Launch L(c, "k_depth_range");
-        k_depth_range<<<grid, TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.npix, c->scratch_b.as<unsigned long long>());
+    const int bpp = (which == TRB_IMAGE_COLOR || which == TRB_IMAGE_FINAL) ? 3 : 1;
+    const size_t total = (size_t)f.npix * f.nviews;
+    if (total * (bpp + 1) >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "encode_tga: batch too large for 32-bit offsets");
+    if (f.W > 65535 || f.H > 65535) return fail(c, TRB_E_ARG, "encode_tga: TGA dimensions are 16 bit");
+    const uint8_t* src = f.color;
+    if (which != TRB_IMAGE_COLOR) {
+        CU(c->rle_src.ensure(total * bpp, c->stream));
+        for (int v = 0; v < f.nviews; ++v) {
+            rc = post_plane(c, which, v, c->rle_src.as<uint8_t>() + (size_t)f.npix * bpp * v);
+            if (rc) return rc;
+        }
+        src = c->rle_src.as<uint8_t>();
     }
-    {
-        Launch L(c, "k_depth_image");
-        k_depth_image<<<blocks_for(f.npix), TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.npix,
-                                                                  c->scratch_b.as<unsigned long long>(),
-                                                                  c->scratch_a.as<uint8_t>());
+    const size_t out_cap = total * bpp + total / 2 + f.nviews + 1024;  // worst case: a raw packet of two pixels per header
+    const size_t offs_at = (out_cap + 3) & ~(size_t)3;                // per-view byte ranges behind the packets
+    CU(c->rle_out.ensure(offs_at + ((size_t)f.nviews + 2) * 4, c->stream));
+    uint32_t* offs_dev = reinterpret_cast<uint32_t*>(c->rle_out.as<uint8_t>() + offs_at);
+    rc = bpp == 3 ? rle_passes<3>(c, src, f.npix, (uint32_t)f.nviews, c->rle_out.as<uint8_t>(), offs_dev)
+                  : rle_passes<1>(c, src, f.npix, (uint32_t)f.nviews, c->rle_out.as<uint8_t>(), offs_dev);
+    if (rc) return rc;
+    std::vector<uint32_t> offs((size_t)f.nviews + 1);
+    CU(cudaMemcpyAsync(offs.data(), offs_dev, offs.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // TGAHeader of write_tga_file (tgaimage.cpp:167-178): 18 packed bytes, origin bottom-left (vflip = true)
+    for (int v = 0; v < f.nviews; ++v) {
+        const uint64_t n = (uint64_t)offs[v + 1] - offs[v];
+        sizes[v] = 18 + n;
+        if (!out[v]) continue;
+        if (sizes[v] > capacity) return fail(c, TRB_E_ARG, "encode_tga: output buffer too small");
+        uint8_t* h = out[v];
+        memset(h, 0, 18);
+        h[2] = (uint8_t)(bpp == 1 ? 11 : 10);                         // datatypecode: RLE grayscale / RLE true-colour
+        h[12] = (uint8_t)(f.W & 255); h[13] = (uint8_t)(f.W >> 8);
+        h[14] = (uint8_t)(f.H & 255); h[15] = (uint8_t)(f.H >> 8);
+        h[16] = (uint8_t)(bpp * 8);
+        h[17] = 0x00;
+        CU(cudaMemcpyAsync(h + 18, c->rle_out.as<uint8_t>() + offs[v], n, cudaMemcpyDeviceToHost, c->stream));
     }
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, c->scratch_a.p, f.npix, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return TRB_OK;
 }
