@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="c4 on N>1 GPUs: fused NVLink kernel or NCCL all-reduces")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tga", action="store_true", help="also time trb_encode_tga (device RLE packetiser) on one step's frames")
     return ap.parse_args()
 
 
@@ -400,22 +401,55 @@ def main():
         depth_host = [[pin((wl.height, wl.width), torch.float64) for _ in range(nviews)] for _ in range(2)]
         e_steps = max(1, min(args.steps, 1 if wl.name == "c5" else (3 if wl.name == "c4" else args.steps)))
 
+        host_ms = {"upload": 0.0, "render": 0.0, "readback": 0.0, "free": 0.0}
+
+        def pinned(a):
+            if a is None:
+                return None
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t.numpy()
+
+        pinned_tex = {}
+        # the step's inputs live in pinned host memory (the contract's H2D source): meshes and textures
+        for it in wl.scene.items:
+            m = it.mesh
+            if not getattr(m, "_pinned", False):
+                m.pos, m.nrm, m.uv, m.idx = pinned(m.pos), pinned(m.nrm), pinned(m.uv), pinned(m.idx)
+                m._pinned = True
+            for k in list(it.textures):
+                t = it.textures[k]
+                if id(t) not in pinned_tex:              # maps shared between models stay shared
+                    p = pinned(t)
+                    pinned_tex[id(t)] = p
+                    pinned_tex[id(p)] = p
+                it.textures[k] = pinned_tex[id(t)]
+
         def e2e_step(s, with_depth):
+            t = [time.perf_counter()]
             up2 = wl.scenes.UploadedScene(r, wl.scene)                 # H2D: meshes + textures
+            t.append(time.perf_counter())
             up2.render(wl.views(api, s, rank, world), wl.perspective)  # H2D: matrices, uniforms
+            t.append(time.perf_counter())
             # D2H: the BGR framebuffer of every frame (what the reference writes out, main.cpp:743);
             # with_depth also brings back the f64 z-buffer the reference keeps in a host global
             r.readback_async(color_host[s & 1], depth_host[s & 1] if with_depth else None)
+            t.append(time.perf_counter())
             up2.free()
+            t.append(time.perf_counter())
+            for k, a, b in zip(("upload", "render", "readback", "free"), t[:-1], t[1:]):
+                host_ms[k] += 1e3 * (b - a)
             return up2.h2d_bytes
 
         def e2e_run(with_depth):
             h2d = e2e_step(0, with_depth)
+            e2e_step(1, with_depth)                                    # the block cache settles after two frames
+            for k in host_ms:
+                host_ms[k] = 0.0
             r.readback_wait()
             barrier()
             t0 = time.perf_counter()
             for s in range(e_steps):
-                e2e_step(1 + s, with_depth)
+                e2e_step(2 + s, with_depth)
             t_host = time.perf_counter() - t0                          # host time to enqueue the steps (nothing waited for)
             r.readback_wait()                                          # every host buffer is complete here
             barrier()
@@ -427,12 +461,27 @@ def main():
                     "h2d_bytes_per_step": int(h2d + nviews * 3 * 256),
                     "d2h_bytes_per_step": int(nviews * P * (3 + (8 if with_depth else 0))),
                     "steps": e_steps, "ms_per_step": 1e3 * float(t.item()) / e_steps,
-                    "host_enqueue_ms_per_step": 1e3 * t_host / e_steps}
+                    "host_enqueue_ms_per_step": 1e3 * t_host / e_steps,
+                    "host_ms_per_step": {k: v / e_steps for k, v in host_ms.items()}}
 
         e2e = e2e_run(False)
         e2e["note"] = ("per step: upload meshes+textures, render, read back the BGR framebuffer of every frame into pinned "
                        "host memory; the z-buffer stays in HBM for the device-side post passes")
         e2e["with_depth_readback"] = e2e_run(True)   # same, plus the f64 z-buffer of every frame (PCIe bound)
+
+    tga = None
+    if args.tga and not sharded_c4:
+        step(0)
+        r.profile_enable(True)
+        r.profile_read(reset=True)
+        t0 = time.perf_counter()
+        files = r.encode_tga(0)                                        # framebuffer.tga of every frame, main.cpp:743
+        dt = time.perf_counter() - t0
+        kt = r.profile_read(reset=True)
+        r.profile_enable(False)
+        tga = {"frames": len(files), "bytes": sum(len(f) for f in files), "raw_bytes": nviews * P * 3,
+               "wall_ms": 1e3 * dt, "device_ms": sum(m for k, (n, m) in kt.items() if k.startswith("k_rle")),
+               "note": "device-side packetiser of tgaimage.cpp:193-242 + D2H of the packets, one blocking call"}
 
     if rank != 0:
         if world > 1:
@@ -504,6 +553,7 @@ def main():
         "clocks": clk,
         "wall_ms_per_step": 1e3 * t_wall / args.steps,
         "ms_per_step_unprofiled": ms_unprofiled / args.steps,
+        "tga_encode": tga,
     }
     print(json.dumps(line))
     if world > 1:

@@ -129,7 +129,12 @@ TRB_EXPORT const char* TRB_FN(backend_name)(void); /* "cuda-sm100a", "oracle-ref
  *      accessors Model::vert/normal/uv(iface,nthvert), model.cpp:396-412) --------------
  * pos3/nrm3: nverts*3 floats, uv2: nverts*2 floats (Assimp hands back floats,
  * model.cpp:160-185).  nrm3 / uv2 may be NULL -> (0,0,1) / (0,0) like the accessors'
- * fallbacks.  idx: nidx (multiple of 3) vertex indices; NULL = implicit 0..nidx-1. */
+ * fallbacks.  idx: nidx (multiple of 3) vertex indices; NULL = implicit 0..nidx-1.
+ * Uploads run on their own stream, so they overlap rendering that is already queued.
+ * Pageable arrays are consumed (staged through pinned chunks) when the call returns.
+ * Page-locked arrays (cudaHostAlloc / cudaHostRegister) are read by the copy engine directly,
+ * without a CPU copy: the caller keeps them alive and unchanged until the next synchronising
+ * call (synchronize, read_*, readback_wait, get_stats).  Same for upload_texture. */
 TRB_EXPORT int TRB_FN(upload_mesh)(TrbCtx* ctx, const float* pos3, const float* nrm3,
                                    const float* uv2, uint32_t nverts, const uint32_t* idx,
                                    uint64_t nidx, TrbMesh* out);

@@ -224,3 +224,49 @@ def test_synchronous_draws_match_oracle(cuda_api, port_api, monkeypatch, name):
     got = run_case(cuda_api, name)
     want = run_case(port_api, name)
     compare.assert_outputs_match(name, got, want)
+
+
+def test_pinned_uploads_and_block_recycling(cuda_api):
+    """meshes / textures handed over in page-locked memory go to the device by DMA + an interleave kernel
+    (no CPU staging); uploading, rendering and freeing the whole scene every frame recycles the
+    event-tagged device blocks while earlier frames are still in flight.  Every frame must equal the
+    frame rendered from pageable arrays uploaded once."""
+    import torch
+    sc = scenes.orbit_scene(320, 180, room_quads=((16, 8), (16, 4), (8, 8)), tex_size=64)
+    pr = cuda_api.perspective(sc.fov, 320 / 180, sc.znear, sc.zfar)
+    frames = [[5 * k + 1, 5 * k + 300, 5 * k + 700] for k in range(6)]
+    with trb.Renderer(cuda_api) as r:
+        up = scenes.UploadedScene(r, sc)
+        want = []
+        for ids in frames:
+            up.render(scenes.orbit_views(cuda_api, ids), pr)
+            want.append([(r.read_depth(v).copy(), r.read_color(v).copy()) for v in range(3)])
+        up.free()
+    pin = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    seen = {}
+    for it in sc.items:
+        m = it.mesh
+        if id(m) not in seen:
+            m.pos, m.nrm, m.uv, m.idx = pin(m.pos), pin(m.nrm), pin(m.uv), pin(m.idx)
+            seen[id(m)] = True
+        for k, t in list(it.textures.items()):
+            if id(t) not in seen:
+                seen[id(t)] = pin(t)
+                seen[id(seen[id(t)])] = seen[id(t)]
+            it.textures[k] = seen[id(t)]
+    pinbuf = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+    with trb.Renderer(cuda_api) as r:
+        got = []
+        for ids in frames:                      # no synchronising call inside the loop
+            up = scenes.UploadedScene(r, sc)
+            up.render(scenes.orbit_views(cuda_api, ids), pr)
+            cs = [pinbuf((180, 320, 3), torch.uint8) for _ in range(3)]
+            ds = [pinbuf((180, 320), torch.float64) for _ in range(3)]
+            r.readback_async(cs, ds)
+            up.free()
+            got.append((cs, ds))
+        r.readback_wait()
+    for k in range(len(frames)):
+        for v in range(3):
+            assert np.array_equal(got[k][1][v].view(np.uint64), want[k][v][0].view(np.uint64)), (k, v)
+            assert np.array_equal(got[k][0][v], want[k][v][1]), (k, v)

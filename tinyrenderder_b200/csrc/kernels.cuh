@@ -113,6 +113,29 @@ __global__ void __launch_bounds__(TPB) k_clear(FrameDev f, uint8_t cb, uint8_t c
 }
 
 // ---------------------------------------------------------------------------------------------
+// mesh upload from pinned host arrays: the raw pos3 / nrm3 / uv2 arrays are DMA'd as they are and
+// interleaved here into the two device layouts (float4 positions, 32-byte attribute records)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_interleave_mesh(const float* __restrict__ pos3, const float* __restrict__ nrm3,
+                                                         const float* __restrict__ uv2, uint32_t nverts,
+                                                         float4* __restrict__ pos4, float* __restrict__ attr8) {
+    const uint32_t v = blockIdx.x * TPB + threadIdx.x;
+    if (v >= nverts) return;
+    const float x = pos3[3 * (size_t)v], y = pos3[3 * (size_t)v + 1], z = pos3[3 * (size_t)v + 2];
+    pos4[v] = make_float4(x, y, z, 1.0f);
+    float4 a0, a1;
+    a0.x = x; a0.y = y; a0.z = z;
+    a0.w = nrm3 ? nrm3[3 * (size_t)v] : 0.f;              // Model::normal fallback (0,0,1), model.cpp:404
+    a1.x = nrm3 ? nrm3[3 * (size_t)v + 1] : 0.f;
+    a1.y = nrm3 ? nrm3[3 * (size_t)v + 2] : 1.f;
+    a1.z = uv2 ? uv2[2 * (size_t)v] : 0.f;
+    a1.w = uv2 ? uv2[2 * (size_t)v + 1] : 0.f;
+    float4* a = reinterpret_cast<float4*>(attr8 + (size_t)v * 8);
+    a[0] = a0;
+    a[1] = a1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // vertex stage
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_vertex_mesh(FrameDev f, const float4* __restrict__ pos4, uint32_t nverts,

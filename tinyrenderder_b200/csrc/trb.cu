@@ -286,17 +286,18 @@ struct Launch {  // RAII around one kernel launch: counts it and, when profiling
     TrbCtx* c;
     const char* name;
     cudaEvent_t a = nullptr, b = nullptr;
-    Launch(TrbCtx* c_, const char* n) : c(c_), name(n) {
+    cudaStream_t st;
+    Launch(TrbCtx* c_, const char* n, cudaStream_t s = nullptr) : c(c_), name(n), st(s ? s : c_->stream) {
         ++c->launches;
         if (c->profiling) {
             a = get_event();
             b = get_event();
-            cudaEventRecord(a, c->stream);
+            cudaEventRecord(a, st);
         }
     }
     ~Launch() {
         if (c->profiling) {
-            cudaEventRecord(b, c->stream);
+            cudaEventRecord(b, st);
             c->prof_pending.push_back(ProfEntry{name, a, b});
         }
     }
@@ -315,6 +316,7 @@ struct Launch {  // RAII around one kernel launch: counts it and, when profiling
 void prof_collect(TrbCtx* c) {
     if (c->prof_pending.empty()) return;
     cudaStreamSynchronize(c->stream);
+    if (c->upload_stream) cudaStreamSynchronize(c->upload_stream);
     for (auto& p : c->prof_pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, p.a, p.b);
@@ -708,6 +710,25 @@ int upload_block(TrbCtx* c, void** dev, size_t bytes, size_t granule, Fill fill)
     }
     return TRB_OK;
 }
+// page-locked host memory can be handed to the copy engine as it is (cudaHostAlloc / cudaHostRegister /
+// torch pin_memory): no staging copy on the CPU.  The caller keeps such arrays alive and unchanged
+// until the next synchronising call (trb.h).
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+// device block filled by one DMA straight from pinned host memory
+int upload_pinned(TrbCtx* c, void** dev, const void* src, size_t bytes) {
+    cudaEvent_t wait_for = nullptr;
+    CU(c->cache.get(dev, bytes, &wait_for));
+    if (wait_for) CU(cudaStreamWaitEvent(c->upload_stream, wait_for, 0));
+    CU(cudaMemcpyAsync(*dev, src, bytes, cudaMemcpyHostToDevice, c->upload_stream));
+    return TRB_OK;
+}
 // everything uploaded so far becomes visible to the render stream
 int publish_uploads(TrbCtx* c) {
     CU(cudaEventRecord(c->upload_ev, c->upload_stream));
@@ -735,6 +756,36 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
     Mesh m;
     m.nverts = nverts;
     m.nidx = nidx;
+    if (is_pinned(pos3) && (!nrm3 || is_pinned(nrm3)) && (!uv2 || is_pinned(uv2)) && (!idx || is_pinned(idx))) {
+        // pinned caller: raw arrays by DMA, interleaved by a kernel on the upload stream - no CPU copy at all
+        float *rp = nullptr, *rn = nullptr, *ru = nullptr;
+        rc = upload_pinned(c, (void**)&rp, pos3, (size_t)nverts * 12);
+        if (!rc && nrm3) rc = upload_pinned(c, (void**)&rn, nrm3, (size_t)nverts * 12);
+        if (!rc && uv2) rc = upload_pinned(c, (void**)&ru, uv2, (size_t)nverts * 8);
+        if (!rc && idx) rc = upload_pinned(c, (void**)&m.idx, idx, nidx * 4);
+        if (rc) return rc;
+        cudaEvent_t w0 = nullptr, w1 = nullptr;
+        CU(c->cache.get((void**)&m.pos4, (size_t)nverts * 16, &w0));
+        CU(c->cache.get((void**)&m.attr8, (size_t)nverts * 32, &w1));
+        if (w0) CU(cudaStreamWaitEvent(c->upload_stream, w0, 0));
+        if (w1) CU(cudaStreamWaitEvent(c->upload_stream, w1, 0));
+        {
+            Launch L(c, "k_interleave_mesh", c->upload_stream);
+            k_interleave_mesh<<<blocks_for(nverts), TPB, 0, c->upload_stream>>>(rp, rn, ru, nverts, m.pos4, m.attr8);
+        }
+        CU(cudaGetLastError());
+        c->cache.put(rp, (size_t)nverts * 12, c->upload_stream);   // raw arrays: free again once the kernel has run
+        c->cache.put(rn, (size_t)nverts * 12, c->upload_stream);
+        c->cache.put(ru, (size_t)nverts * 8, c->upload_stream);
+        rc = publish_uploads(c);
+        if (rc) return rc;
+        m.alive = true;
+        size_t slot = 0;
+        while (slot < c->meshes.size() && c->meshes[slot].alive) ++slot;
+        if (slot == c->meshes.size()) c->meshes.push_back(m); else c->meshes[slot] = m;
+        *out = slot + 1;
+        return TRB_OK;
+    }
     rc = upload_block(c, (void**)&m.pos4, (size_t)nverts * 16, 16, [&](char* dst, size_t off, size_t n) {
         float* p = reinterpret_cast<float*>(dst);
         const size_t v0 = off / 16, nv = n / 16;
@@ -796,7 +847,10 @@ int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, 
     t.h = h;
     t.bpp = bpp;
     size_t bytes = (size_t)w * h * bpp;
-    rc = upload_block(c, (void**)&t.px, bytes, 1, [&](char* dst, size_t off, size_t n) { memcpy(dst, texels + off, n); });
+    if (is_pinned(texels))
+        rc = upload_pinned(c, (void**)&t.px, texels, bytes);
+    else
+        rc = upload_block(c, (void**)&t.px, bytes, 1, [&](char* dst, size_t off, size_t n) { memcpy(dst, texels + off, n); });
     if (rc) return rc;
     rc = publish_uploads(c);
     if (rc) return rc;
