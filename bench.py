@@ -392,6 +392,20 @@ def main():
     tris_step_all = T * nviews * (1 if sharded_c4 else world)
     value = tris_step_all * args.steps / (ms_max * 1e-3)
 
+    tga = None
+    if args.tga and not sharded_c4:
+        step(0)
+        r.profile_enable(True)
+        r.profile_read(reset=True)
+        t0 = time.perf_counter()
+        files = r.encode_tga(0)                                        # framebuffer.tga of every frame, main.cpp:743
+        dt = time.perf_counter() - t0
+        kt = r.profile_read(reset=True)
+        r.profile_enable(False)
+        tga = {"frames": len(files), "bytes": sum(len(f) for f in files), "raw_bytes": nviews * P * 3,
+               "wall_ms": 1e3 * dt, "device_ms": sum(m for k, (n, m) in kt.items() if k.startswith("k_rle")),
+               "note": "device-side packetiser of tgaimage.cpp:193-242 + D2H of the packets, one blocking call"}
+
     # ---- end-to-end: host buffers in, host buffers out, every step --------------------------------------
     e2e = None
     if not args.no_e2e and not sharded_c4:
@@ -423,11 +437,21 @@ def main():
                     pinned_tex[id(t)] = p
                     pinned_tex[id(p)] = p
                 it.textures[k] = pinned_tex[id(t)]
+        up_resident = wl.scenes.UploadedScene(r, wl.scene) if os.environ.get("TRB_E2E_VARIANT") == "noupload" else None
 
         def e2e_step(s, with_depth):
             t = [time.perf_counter()]
+            variant = os.environ.get("TRB_E2E_VARIANT", "")             # diagnostics only
+            if variant == "noupload":
+                up_resident.render(wl.views(api, s, rank, world), wl.perspective)
+                r.readback_async(color_host[s & 1], depth_host[s & 1] if with_depth else None)
+                return 0
             up2 = wl.scenes.UploadedScene(r, wl.scene)                 # H2D: meshes + textures
             t.append(time.perf_counter())
+            if variant == "noreadback":
+                up2.render(wl.views(api, s, rank, world), wl.perspective)
+                up2.free()
+                return up2.h2d_bytes
             up2.render(wl.views(api, s, rank, world), wl.perspective)  # H2D: matrices, uniforms
             t.append(time.perf_counter())
             # D2H: the BGR framebuffer of every frame (what the reference writes out, main.cpp:743);
@@ -468,20 +492,6 @@ def main():
         e2e["note"] = ("per step: upload meshes+textures, render, read back the BGR framebuffer of every frame into pinned "
                        "host memory; the z-buffer stays in HBM for the device-side post passes")
         e2e["with_depth_readback"] = e2e_run(True)   # same, plus the f64 z-buffer of every frame (PCIe bound)
-
-    tga = None
-    if args.tga and not sharded_c4:
-        step(0)
-        r.profile_enable(True)
-        r.profile_read(reset=True)
-        t0 = time.perf_counter()
-        files = r.encode_tga(0)                                        # framebuffer.tga of every frame, main.cpp:743
-        dt = time.perf_counter() - t0
-        kt = r.profile_read(reset=True)
-        r.profile_enable(False)
-        tga = {"frames": len(files), "bytes": sum(len(f) for f in files), "raw_bytes": nviews * P * 3,
-               "wall_ms": 1e3 * dt, "device_ms": sum(m for k, (n, m) in kt.items() if k.startswith("k_rle")),
-               "note": "device-side packetiser of tgaimage.cpp:193-242 + D2H of the packets, one blocking call"}
 
     if rank != 0:
         if world > 1:

@@ -207,8 +207,8 @@ TRB_EXPORT int TRB_FN(composite_ao)(TrbCtx* ctx, int view, uint8_t* bgr_out);
  * (:765), final.tga (:785). */
 enum TrbImage {
     TRB_IMAGE_COLOR = 0,  /* BGR framebuffer, 24 bit */
-    TRB_IMAGE_DEPTH = 1,  /* save_zbuffer_image grey map, 8 bit */
-    TRB_IMAGE_SSAO = 2,   /* ambient-occlusion map, 8 bit */
+    TRB_IMAGE_DEPTH = 1,  /* save_zbuffer_image grey map, stored as TGAColor(v,v,v): 24 bit like the reference's file */
+    TRB_IMAGE_SSAO = 2,   /* ambient-occlusion map, likewise 24 bit */
     TRB_IMAGE_FINAL = 3   /* framebuffer * ao, 24 bit */
 };
 /* Replaces TGAImage::write_tga_file(name, vflip = true, rle = true) (tgaimage.cpp:160-191) and its

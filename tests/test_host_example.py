@@ -155,6 +155,12 @@ def test_device_build_matches_oracle_build(assets, tmp_path, mode):
     # ao.tga / zbuffer.tga files written by our TGA writer are byte-identical to the reference's
     for n in ("ao", "zbuffer"):
         assert open(os.path.join(got["dir"], n + ".tga"), "rb").read() == open(os.path.join(want["dir"], n + ".tga"), "rb").read()
+    # gl_write_tga_file: the same four files packetised on the device (trb_encode_tga) are byte-identical
+    # to what the host-side TGAImage::write_tga_file wrote from the read-back pixels
+    for n in ("phong", "zbuffer", "ao", "final"):
+        a = open(os.path.join(got["dir"], n + "_dev.tga"), "rb").read()
+        b = open(os.path.join(got["dir"], n + ".tga"), "rb").read()
+        assert a == b, n
 
 
 @pytest.mark.gpu

@@ -1162,6 +1162,9 @@ __global__ void __launch_bounds__(TPB) k_shade_collect(FrameDev f, int row0, int
 #ifndef TRB_SHADE_MIN_BLOCKS
 #define TRB_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef TRB_SHADE_2D
+#define TRB_SHADE_2D 0   // measured on B200 (config 3): 8x4 warp footprints 1.18 ms vs 1.10 ms for 32 pixels of a row
+#endif
 template <bool C2, bool FAST>
 __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
                                                      int row0, int row1) {
@@ -1170,9 +1173,21 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(Frame
     for (int i = threadIdx.x; i < ndraws && i < SHADE_MAX_SM_DRAWS; i += TPB) sm_base[i] = draws[i].id_base;
     __syncthreads();
     const int view = blockIdx.y;
+#if TRB_SHADE_2D
+    // a CTA shades a 32x8 pixel block, each warp an 8x4 footprint: the lanes of a warp then share far
+    // fewer winning triangles than 32 pixels of one row do, so their VRec / attribute / texel gathers
+    // fall into fewer distinct sectors
+    const int nbx = (f.W + 31) >> 5;
+    const int bx = (int)(blockIdx.x % (unsigned)nbx), by = (int)(blockIdx.x / (unsigned)nbx);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = (bx << 5) + ((warp & 3) << 3) + (lane & 7), y = row0 + (by << 3) + ((warp >> 2) << 2) + (lane >> 3);
+    if (x >= f.W || y >= row1) return;
+    const unsigned long long p = (unsigned long long)y * f.W + x;
+#else
     const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
     const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
     if (p >= last) return;
+#endif
     uint32_t* vis = f.vis + (size_t)view * f.npix;
     const uint32_t id = vis[p];
     if (id == VIS_NONE || id == VIS_SHADED) return;
@@ -1318,6 +1333,15 @@ __global__ void __launch_bounds__(TPB) k_depth_image(const unsigned long long* _
         v = (uint8_t)(int)(255.0 * (1.0 - t));                          // main.cpp:306
     }
     grey[i] = v;
+}
+
+// TGAColor(v, v, v) per pixel: the grey maps are written as 24-bit images (main.cpp:309, 761)
+__global__ void __launch_bounds__(TPB) k_grey_to_bgr(const uint8_t* __restrict__ grey, unsigned long long n,
+                                                     uint8_t* __restrict__ bgr) {
+    unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t v = grey[i];
+    bgr[3 * i] = v; bgr[3 * i + 1] = v; bgr[3 * i + 2] = v;
 }
 
 // ---------------------------------------------------------------------------------------------

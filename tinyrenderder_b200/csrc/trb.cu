@@ -392,7 +392,11 @@ int do_flush(TrbCtx* c) {
             }
         }
         {   // dense views only
+#if TRB_SHADE_2D
+            const dim3 grid((unsigned)(((f.W + 31) / 32) * ((r1 - r0 + 7) / 8)), f.nviews);
+#else
             const dim3 grid(blocks_for(n), f.nviews);
+#endif
             Launch L(c, "k_shade_dense");
             switch (variant) {
                 case 0: k_shade_dense<false, false><<<grid, TPB, 0, c->stream>>>(f, table, nd, r0, r1); break;
@@ -1414,25 +1418,32 @@ int trb_encode_tga(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity,
     int rc = do_flush(c);
     if (rc) return rc;
     const FrameDev& f = c->frame;
-    const int bpp = (which == TRB_IMAGE_COLOR || which == TRB_IMAGE_FINAL) ? 3 : 1;
+    const int bpp = 3;   // all four are TGAImage::RGB files: the grey maps store TGAColor(v, v, v) (main.cpp:309, 761)
     const size_t total = (size_t)f.npix * f.nviews;
     if (total * (bpp + 1) >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "encode_tga: batch too large for 32-bit offsets");
     if (f.W > 65535 || f.H > 65535) return fail(c, TRB_E_ARG, "encode_tga: TGA dimensions are 16 bit");
     const uint8_t* src = f.color;
     if (which != TRB_IMAGE_COLOR) {
         CU(c->rle_src.ensure(total * bpp, c->stream));
+        const bool grey = which != TRB_IMAGE_FINAL;
+        if (grey) CU(c->scratch_a.ensure(f.npix, c->stream));
         for (int v = 0; v < f.nviews; ++v) {
-            rc = post_plane(c, which, v, c->rle_src.as<uint8_t>() + (size_t)f.npix * bpp * v);
+            uint8_t* dst = c->rle_src.as<uint8_t>() + (size_t)f.npix * bpp * v;
+            rc = post_plane(c, which, v, grey ? c->scratch_a.as<uint8_t>() : dst);
             if (rc) return rc;
+            if (grey) {
+                Launch L(c, "k_grey_to_bgr");
+                k_grey_to_bgr<<<blocks_for(f.npix), TPB, 0, c->stream>>>(c->scratch_a.as<uint8_t>(), f.npix, dst);
+            }
         }
+        CU(cudaGetLastError());
         src = c->rle_src.as<uint8_t>();
     }
     const size_t out_cap = total * bpp + total / 2 + f.nviews + 1024;  // worst case: a raw packet of two pixels per header
     const size_t offs_at = (out_cap + 3) & ~(size_t)3;                // per-view byte ranges behind the packets
     CU(c->rle_out.ensure(offs_at + ((size_t)f.nviews + 2) * 4, c->stream));
     uint32_t* offs_dev = reinterpret_cast<uint32_t*>(c->rle_out.as<uint8_t>() + offs_at);
-    rc = bpp == 3 ? rle_passes<3>(c, src, f.npix, (uint32_t)f.nviews, c->rle_out.as<uint8_t>(), offs_dev)
-                  : rle_passes<1>(c, src, f.npix, (uint32_t)f.nviews, c->rle_out.as<uint8_t>(), offs_dev);
+    rc = rle_passes<3>(c, src, f.npix, (uint32_t)f.nviews, c->rle_out.as<uint8_t>(), offs_dev);
     if (rc) return rc;
     std::vector<uint32_t> offs((size_t)f.nviews + 1);
     CU(cudaMemcpyAsync(offs.data(), offs_dev, offs.size() * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1445,7 +1456,7 @@ int trb_encode_tga(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity,
         if (sizes[v] > capacity) return fail(c, TRB_E_ARG, "encode_tga: output buffer too small");
         uint8_t* h = out[v];
         memset(h, 0, 18);
-        h[2] = (uint8_t)(bpp == 1 ? 11 : 10);                         // datatypecode: RLE grayscale / RLE true-colour
+        h[2] = 10;                                                    // datatypecode: RLE true-colour
         h[12] = (uint8_t)(f.W & 255); h[13] = (uint8_t)(f.W >> 8);
         h[14] = (uint8_t)(f.H & 255); h[15] = (uint8_t)(f.H >> 8);
         h[16] = (uint8_t)(bpp * 8);

@@ -144,6 +144,13 @@ int main(int argc, char** argv) {
         memcpy(fin.buffer(), c.data(), c.size());
     }
 #endif
+#ifdef TRB_DEVICE_BACKEND
+    // the same four files once more, packetised on the device (tests compare them byte for byte)
+    gl_write_tga_file(0, out + "/phong_dev.tga");
+    gl_write_tga_file(1, out + "/zbuffer_dev.tga");
+    gl_write_tga_file(2, out + "/ao_dev.tga");
+    gl_write_tga_file(3, out + "/final_dev.tga");
+#endif
     zimg.write_tga_file(out + "/zbuffer.tga");                                                     // main.cpp:751
     ao.write_tga_file(out + "/ao.tga");                                                            // main.cpp:764
     fin.write_tga_file(out + "/final.tga");                                                        // main.cpp:784

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -302,6 +303,24 @@ void gl_composite_ao(TGAImage& final_result) {
     CK(trb_composite_ao(b.ctx, 0, c.data()));
     final_result = TGAImage(b.w, b.h, TGAImage::RGB);
     std::memcpy(final_result.buffer(), c.data(), c.size());
+}
+
+bool gl_write_tga_file(int image, const std::string& filename) {
+    require_frame();
+    submit_pending();
+    Backend& b = B();
+    const size_t cap = (size_t)b.w * b.h * 3 + (size_t)b.w * b.h / 2 + 64;
+    std::vector<uint8_t> file(cap);
+    uint8_t* out[1] = {file.data()};
+    uint64_t size = 0;
+    CK(trb_encode_tga(b.ctx, image, out, cap, &size));
+    std::ofstream f(filename, std::ios::binary);
+    if (!f.is_open()) {
+        std::cerr << "can't open " << filename << "\n";   // same message as tgaimage.cpp:163
+        return false;
+    }
+    f.write((const char*)file.data(), (std::streamsize)size);
+    return f.good();
 }
 
 void print_render_stats() {

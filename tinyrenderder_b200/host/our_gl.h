@@ -8,6 +8,7 @@
 //     caller-visible framebuffer and the global zbuffer (the reference writes both immediately);
 //   * gl_draw_model() replaces a whole per-face loop (main.cpp:660-666) by one device draw call.
 #pragma once
+#include <string>
 #define TRB_DEVICE_BACKEND 1
 #include <geometry.h>
 #include <tgaimage.h>
@@ -72,6 +73,10 @@ void gl_zbuffer_restore(TGAImage& framebuffer);
 void gl_ssao(TGAImage& ao_map);
 void gl_zbuffer_image(TGAImage& grey);
 void gl_composite_ao(TGAImage& final_result);
+// framebuffer.write_tga_file(name) (main.cpp:743) and the three post-pass files (main.cpp:312, 765, 785)
+// without bringing the pixels to the host: the RLE packets of tgaimage.cpp:193-242 are built on the
+// device, only the file image crosses PCIe.  image: 0 framebuffer, 1 z-buffer grey map, 2 ssao, 3 final.
+bool gl_write_tga_file(int image, const std::string& filename);
 struct TrbCtx;
 TrbCtx* gl_context();        // the process-wide device context (device = $TRB_DEVICE, default 0)
 
