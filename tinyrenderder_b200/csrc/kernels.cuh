@@ -245,14 +245,19 @@ __device__ __forceinline__ unsigned long long block_reduce_min64(unsigned long l
 // invalidates its id, and k_direct_resolve then gives every pixel the lowest id among the fragments
 // that reached its final depth - the same exact (depth, id) minimum as the tile path, no bins, no
 // barriers.  The tile kernels of the same draw run afterwards and see these pixels as older state.
-constexpr uint32_t BOX_DIRECT = 0xFFFFFFFEu;   // tribox.x of a direct triangle (y: 1 = may own a pixel)
+constexpr uint32_t BOX_DIRECT = 0xFFFFFFFEu;   // tribox.x of a direct triangle
+#ifndef TRB_SETUP_MIN_BLOCKS
+#define TRB_SETUP_MIN_BLOCKS 4
+#endif
 constexpr int DIRECT_AREA_DEFAULT = 16;
 
-__global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uint2* __restrict__ tribox,
+__global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(FrameDev f, GeomArgs g, uint2* __restrict__ tribox,
                                                      TriRec* __restrict__ trirec, uint32_t* __restrict__ tile_count,
-                                                     int direct_area) {
-    __shared__ int sh_i[TPB / 32];
-    __shared__ unsigned long long sh_u[TPB / 32];
+                                                     int direct_area, uint32_t* __restrict__ direct_list,
+                                                     uint32_t* __restrict__ direct_n) {
+    __shared__ int sh_i[4 * 8];
+    __shared__ unsigned sh_w[5 * 8];
+    static_assert(TPB / 32 == 8, "block totals are laid out for 8 warps");
     const int view = blockIdx.y;
     const uint32_t t = blockIdx.x * TPB + threadIdx.x;
     const VRec* vr = g.vrec + (size_t)view * g.nverts;
@@ -264,13 +269,9 @@ __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uin
         VRec c = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 2));
         res = setup_triangle(a, b, c, f.W, f.H, ts);
     }
-    // statistics bbox + "survived the rejects" count, our_gl.cpp:138-141
+    // statistics bbox + "survived the rejects" count, our_gl.cpp:138-141 (reduced with the other
+    // per-block totals in ONE pass at the end of the kernel)
     const bool counted = res != SETUP_REJECT;
-    int bx0 = block_reduce_min(counted ? ts.x0 : INT_MAX, sh_i);
-    int by0 = block_reduce_min(counted ? ts.y0 : INT_MAX, sh_i);
-    int bx1 = -block_reduce_min(counted ? -ts.x1 : INT_MAX, sh_i);
-    int by1 = -block_reduce_min(counted ? -ts.y1 : INT_MAX, sh_i);
-    unsigned long long nb = block_reduce_sum(counted ? 1ull : 0ull, sh_u);
 
     uint2 box = make_uint2(BOX_NONE, 0u);
     uint32_t ntile = 0;
@@ -307,6 +308,16 @@ __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uin
             }
         box = make_uint2(BOX_DIRECT, candidate);
         res = SETUP_NO_COVERAGE;                            // handled: keep it out of the bins
+        // triangles that may own a pixel go on the view's list: k_direct_resolve then runs full warps
+        // over ~the visible fraction instead of idling through every triangle of the draw
+        const unsigned act = __activemask(), cm = __ballot_sync(act, candidate != 0);
+        if (cm) {
+            const int leader = __ffs(cm) - 1;
+            uint32_t base = 0;
+            if ((int)lane_id == leader) base = atomicAdd(direct_n + view, (uint32_t)__popc(cm));
+            base = __shfl_sync(act, base, leader);
+            if (candidate) direct_list[(size_t)view * g.ntris + base + __popc(cm & ((1u << lane_id) - 1u))] = t;
+        }
     }
     if (res == SETUP_DRAW) {
         tx0 = ts.x0 >> TILE_SHIFT; tx1 = ts.x1 >> TILE_SHIFT;
@@ -316,19 +327,44 @@ __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uin
         store_trirec(trirec + (size_t)view * g.ntris + t, ts);
     }
     if (t < g.ntris) tribox[(size_t)view * g.ntris + t] = box;
-    unsigned long long ne = block_reduce_sum(ntile, sh_u);
-    direct_cov = block_reduce_sum(direct_cov, sh_u);
-    direct_zmin = block_reduce_min64(direct_zmin, sh_u);
-    if (threadIdx.x == 0 && nb) {
-        DevStats* s = f.stats + view;
-        atomicMin(&s->bx0, bx0); atomicMin(&s->by0, by0);
-        atomicMax(&s->bx1, bx1); atomicMax(&s->by1, by1);
-        atomicAdd(&s->tri_binned, nb);
-        if (ne) atomicAdd(&s->tile_entries, ne);
-        if (direct_cov) {
-            atomicAdd(&s->frag_covered, direct_cov);
-            atomicAdd(&s->touched, direct_cov);
-            atomicMin(&s->zmin_key, direct_zmin);
+    {   // block totals: one REDUX per value and warp, one barrier, one more REDUX in warp 0
+        const unsigned FULL = 0xffffffffu;
+        const unsigned lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+        int bx0 = __reduce_min_sync(FULL, counted ? ts.x0 : INT_MAX), by0 = __reduce_min_sync(FULL, counted ? ts.y0 : INT_MAX);
+        int bx1 = __reduce_max_sync(FULL, counted ? ts.x1 : INT_MIN), by1 = __reduce_max_sync(FULL, counted ? ts.y1 : INT_MIN);
+        unsigned nb = __reduce_add_sync(FULL, counted ? 1u : 0u), ne = __reduce_add_sync(FULL, ntile);
+        unsigned dcov = __reduce_add_sync(FULL, (unsigned)direct_cov);
+        unsigned zhi = __reduce_min_sync(FULL, (unsigned)(direct_zmin >> 32));
+        unsigned zlo = __reduce_min_sync(FULL, (unsigned)(direct_zmin >> 32) == zhi ? (unsigned)direct_zmin : 0xffffffffu);
+        if (lane_ == 0) {
+            sh_i[warp_] = bx0; sh_i[8 + warp_] = by0; sh_i[16 + warp_] = bx1; sh_i[24 + warp_] = by1;
+            sh_w[warp_] = nb; sh_w[8 + warp_] = ne; sh_w[16 + warp_] = dcov; sh_w[24 + warp_] = zhi; sh_w[32 + warp_] = zlo;
+        }
+        __syncthreads();
+        if (warp_ == 0) {
+            const bool in = lane_ < TPB / 32;
+            bx0 = __reduce_min_sync(FULL, in ? sh_i[lane_] : INT_MAX);
+            by0 = __reduce_min_sync(FULL, in ? sh_i[8 + lane_] : INT_MAX);
+            bx1 = __reduce_max_sync(FULL, in ? sh_i[16 + lane_] : INT_MIN);
+            by1 = __reduce_max_sync(FULL, in ? sh_i[24 + lane_] : INT_MIN);
+            nb = __reduce_add_sync(FULL, in ? sh_w[lane_] : 0u);
+            ne = __reduce_add_sync(FULL, in ? sh_w[8 + lane_] : 0u);
+            dcov = __reduce_add_sync(FULL, in ? sh_w[16 + lane_] : 0u);
+            const unsigned whi = in ? sh_w[24 + lane_] : 0xffffffffu, wlo = in ? sh_w[32 + lane_] : 0xffffffffu;
+            zhi = __reduce_min_sync(FULL, whi);
+            zlo = __reduce_min_sync(FULL, whi == zhi ? wlo : 0xffffffffu);
+            if (lane_ == 0 && nb) {
+                DevStats* s = f.stats + view;
+                atomicMin(&s->bx0, bx0); atomicMin(&s->by0, by0);
+                atomicMax(&s->bx1, bx1); atomicMax(&s->by1, by1);
+                atomicAdd(&s->tri_binned, (unsigned long long)nb);
+                if (ne) atomicAdd(&s->tile_entries, (unsigned long long)ne);
+                if (dcov) {
+                    atomicAdd(&s->frag_covered, (unsigned long long)dcov);
+                    atomicAdd(&s->touched, (unsigned long long)dcov);
+                    atomicMin(&s->zmin_key, ((unsigned long long)zhi << 32) | zlo);
+                }
+            }
         }
     }
     // per-tile counts; single-tile triangles (the common case for small triangles) are aggregated
@@ -346,13 +382,14 @@ __global__ void __launch_bounds__(TPB) k_setup_count(FrameDev f, GeomArgs g, uin
     }
 }
 
-// second half of the direct path: ids of the fragments that sit at a pixel's final depth
-__global__ void __launch_bounds__(TPB) k_direct_resolve(FrameDev f, GeomArgs g, const uint2* __restrict__ tribox) {
+// second half of the direct path: ids of the fragments that sit at a pixel's final depth, over the
+// compacted list of the triangles that were (for a moment at least) nearest somewhere
+__global__ void __launch_bounds__(TPB) k_direct_resolve(FrameDev f, GeomArgs g, const uint32_t* __restrict__ direct_list,
+                                                        const uint32_t* __restrict__ direct_n) {
     const int view = blockIdx.y;
-    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
-    if (t >= g.ntris) return;
-    const uint2 box = tribox[(size_t)view * g.ntris + t];
-    if (box.x != BOX_DIRECT || box.y == 0u) return;
+    const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= direct_n[view]) return;
+    const uint32_t t = direct_list[(size_t)view * g.ntris + i];
     const VRec* vr = g.vrec + (size_t)view * g.nverts;
     VRec a = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 0));
     VRec b_ = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 1));

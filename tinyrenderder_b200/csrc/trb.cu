@@ -235,6 +235,7 @@ struct TrbCtx {
     // per-draw scratch (stream ordered reuse)
     DevBuf shade_list, tribox, trirec, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
     DevBuf ctl, heavy_list;          // DrawCtl of the draw in flight, tile slots of its long bins
+    DevBuf direct_list, direct_n;    // direct path: triangles that may own a pixel, per view
     DevBuf rle_work, rle_src, rle_out; // device-side TGA RLE encoder (tga_rle.cuh)
     bool sync_draws = false;         // TRB_SYNC_DRAWS=1: size the bins exactly (one stream sync per draw)
     uint64_t bin_hint = 0;           // entries: 1.25 x the largest R seen so far
@@ -456,6 +457,11 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     CU(cudaMemsetAsync(c->counts.p, 0, nslots * 4, c->stream));
     CU(cudaMemsetAsync(c->cursor.p, 0, nslots * 4, c->stream));
     CU(cudaMemsetAsync(c->ctl.p, 0, sizeof(DrawCtl), c->stream));
+    if (c->direct_area > 0) {
+        CU(c->direct_list.ensure((size_t)f.nviews * g.ntris * 4, c->stream));
+        CU(c->direct_n.ensure((size_t)f.nviews * 4, c->stream));
+        CU(cudaMemsetAsync(c->direct_n.p, 0, (size_t)f.nviews * 4, c->stream));
+    }
     uint32_t capacity = 0xFFFFFFFFu;   // synchronous draws size the buffer after the scan
     if (!c->sync_draws) {
         // R of the most recent draw the device has finished scanning: a hint, never waited for
@@ -470,11 +476,12 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     {
         Launch L(c, "k_setup_count");
         k_setup_count<<<tgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
-                                                     c->counts.as<uint32_t>(), c->direct_area);
+                                                     c->counts.as<uint32_t>(), c->direct_area, c->direct_list.as<uint32_t>(),
+                                                     c->direct_n.as<uint32_t>());
     }
     if (c->direct_area > 0) {
         Launch L(c, "k_direct_resolve");
-        k_direct_resolve<<<tgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>());
+        k_direct_resolve<<<tgrid, TPB, 0, c->stream>>>(f, g, c->direct_list.as<uint32_t>(), c->direct_n.as<uint32_t>());
     }
     CU(cudaGetLastError());
     int rc = exclusive_scan(c, c->counts.as<uint32_t>(), (uint32_t)nslots, c->offsets.as<uint32_t>(), capacity);
@@ -657,7 +664,7 @@ int trb_destroy(TrbCtx* c) {
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
     DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
-                      &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->ctl, &c->heavy_list, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
+                      &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->ctl, &c->heavy_list, &c->direct_list, &c->direct_n, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.keys.release();
@@ -714,6 +721,19 @@ int upload_block(TrbCtx* c, void** dev, size_t bytes, size_t granule, Fill fill)
     }
     return TRB_OK;
 }
+// largest vertex index of a mesh (upload_mesh validates the range before anything reaches the device);
+// written as a reduction so that the AVX2 clone runs at memory speed on multi-million-triangle meshes
+__attribute__((target("avx2"))) uint32_t max_index_avx2(const uint32_t* idx, uint64_t n) {
+    uint32_t m = 0;
+    for (uint64_t i = 0; i < n; ++i) m = idx[i] > m ? idx[i] : m;
+    return m;
+}
+uint32_t max_index(const uint32_t* idx, uint64_t n) {
+    if (__builtin_cpu_supports("avx2")) return max_index_avx2(idx, n);
+    uint32_t m = 0;
+    for (uint64_t i = 0; i < n; ++i) m = idx[i] > m ? idx[i] : m;
+    return m;
+}
 // page-locked host memory can be handed to the copy engine as it is (cudaHostAlloc / cudaHostRegister /
 // torch pin_memory): no staging copy on the CPU.  The caller keeps such arrays alive and unchanged
 // until the next synchronising call (trb.h).
@@ -749,9 +769,7 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
     if (nidx / 3 >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "upload_mesh: too many triangles");
     int rc = check_device(c);
     if (rc) return rc;
-    if (idx)
-        for (uint64_t i = 0; i < nidx; ++i)
-            if (idx[i] >= nverts) return fail(c, TRB_E_ARG, "upload_mesh: index out of range");
+    if (idx && nidx && max_index(idx, nidx) >= nverts) return fail(c, TRB_E_ARG, "upload_mesh: index out of range");
     if (!idx && nidx > nverts) return fail(c, TRB_E_ARG, "upload_mesh: implicit indices exceed nverts");
     // The host interleaves into the two device layouts - float4 positions for the coalesced vertex
     // kernel, 32-byte {pos,nrm,uv} records (one DRAM sector) for the shade kernel's gathers - straight
