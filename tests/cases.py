@@ -294,6 +294,22 @@ def depth_only_then_color(api, r):
     return _grab(r)
 
 
+def snapshot_restore_twice(api, r):
+    """`saved = zbuffer` ... `zbuffer = saved` (main.cpp:700,730) used repeatedly: colours of everything
+    drawn persist, depths return to the snapshot each time, and draws after a restore are tested against it"""
+    r.begin_frame(96, 96)
+    r.submit_clip_triangles(_screen_tri([(10, 10), (80, 12), (40, 85)], 0.5, 96, 96))
+    r.depth_snapshot()
+    r.submit_clip_triangles(_screen_tri([(5, 40), (90, 30), (50, 90)], 0.2, 96, 96))    # nearer: wins where it overlaps
+    r.depth_restore()
+    r.depth_restore()                                                                    # idempotent
+    r.submit_clip_triangles(_screen_tri([(20, 5), (95, 50), (30, 70)], 0.35, 96, 96))   # behind the 0.2 one, but that depth is gone
+    r.depth_restore()
+    r.submit_clip_triangles(_screen_tri([(0, 0), (60, 5), (10, 60)], 0.7, 96, 96))      # behind the snapshot where they overlap
+    r.end_frame()
+    return _grab(r)
+
+
 def sub_range_draws(api, r):
     """drawing a mesh as three triangle ranges == drawing it at once (config-4 sharding unit)"""
     m = scenes.icosphere(3)
@@ -377,6 +393,7 @@ CASES = {
     "big_triangles": big_triangles, "queue_overflow": queue_overflow, "dense_tile": dense_tile,
     "soup_mesh_fp32": soup_mesh_fp32, "head_small": head_small, "orbit_small": orbit_small,
     "depth_only_then_color": depth_only_then_color, "sub_range_draws": sub_range_draws,
+    "snapshot_restore_twice": snapshot_restore_twice,
     "lit_clip_triangles": lit_clip_triangles, "shadow_small": shadow_small, "gouraud_small": gouraud_small,
 }
 FULL_SIZE_CASES = {"k7a": k7a, "k7b": k7b, "k7c": k7c, "head_c1": head_c1, "orbit_mid": orbit_mid,

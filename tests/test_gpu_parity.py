@@ -203,7 +203,8 @@ def test_fp32_lighting_stays_within_one_code(cuda_api, port_api, monkeypatch, na
 
 
 DRAW_PATH_CASES = ["k2", "k5_far_near", "k7b_small", "signed_zero_ties", "duplicate_triangles", "big_triangles",
-                   "dense_tile", "soup_mesh_fp32", "head_small", "orbit_small", "sub_range_draws", "rejects"]
+                   "dense_tile", "soup_mesh_fp32", "head_small", "orbit_small", "sub_range_draws", "rejects",
+                   "snapshot_restore_twice"]
 
 
 @pytest.mark.parametrize("name", DRAW_PATH_CASES)

@@ -224,6 +224,7 @@ struct TrbCtx {
     uint8_t clear[3] = {0, 0, 0};
     DevBuf zkey, vis, color, stats, zsnap, zlocal;
     bool have_snapshot = false;
+    bool snap_stale = false;        // restored by pointer swap: zsnap must be refreshed before the key plane changes
     std::vector<ShadowMap> shadow_maps;
     Arena arena;
     std::vector<DrawDev> draws;     // since the last flush
@@ -435,6 +436,16 @@ int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uin
     return TRB_OK;
 }
 
+// after a pointer-swap restore the spare plane no longer holds the snapshot: copy it back before the
+// key plane changes again
+int refresh_snapshot(TrbCtx* c) {
+    if (!c->have_snapshot || !c->snap_stale) return TRB_OK;
+    size_t bytes = (size_t)c->frame.npix * c->frame.nviews * 8;
+    CU(cudaMemcpyAsync(c->zsnap.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    c->snap_stale = false;
+    return TRB_OK;
+}
+
 // bin + rasterise one draw whose vertex records are already in `vrec`.
 //
 // Default (asynchronous): nothing here waits for the device.  The bin buffer is sized from an
@@ -445,6 +456,8 @@ int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uin
 int raster_draw(TrbCtx* c, const GeomArgs& g) {
     const FrameDev& f = c->frame;
     if (g.ntris == 0) return TRB_OK;
+    int rs = refresh_snapshot(c);
+    if (rs) return rs;
     const size_t nslots = (size_t)f.nviews * f.ntiles;
     if (nslots >= 0xFFFFFFFFull) return fail(c, TRB_E_ARG, "draw: too many tiles x views");
     CU(c->tribox.ensure((size_t)f.nviews * g.ntris * sizeof(uint2), c->stream));
@@ -922,6 +935,7 @@ int trb_begin_batch(TrbCtx* c, int w, int h, int nviews) {
     c->next_id = 0;
     c->tris_submitted = 0;
     c->have_snapshot = false;
+    c->snap_stale = false;
     c->shade_row0 = 0;
     c->shade_row1 = -1;
     {
@@ -1114,14 +1128,25 @@ int trb_depth_snapshot(TrbCtx* c) {
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->zsnap.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
     c->have_snapshot = true;
+    c->snap_stale = false;
     return TRB_OK;
 }
 int trb_depth_restore(TrbCtx* c) {
     if (!c || !c->in_frame || !c->have_snapshot) return fail(c, TRB_E_ARG, "depth_restore: no snapshot");
     int rc = do_flush(c);  // colours of everything drawn so far persist (main.cpp:730)
     if (rc) return rc;
+    if (c->snap_stale) return TRB_OK;   // restored already and nothing drawn since: the key plane IS the snapshot
     size_t bytes = (size_t)c->frame.npix * c->frame.nviews * 8;
-    CU(cudaMemcpyAsync(c->zkey.p, c->zsnap.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->peers.n > 0) {               // peers hold the address of the key plane: copy
+        CU(cudaMemcpyAsync(c->zkey.p, c->zsnap.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        return TRB_OK;
+    }
+    // `zbuffer = zbuffer_before_eyes` (main.cpp:730) without moving 8 bytes per pixel: the saved plane
+    // becomes the key plane; the old one is refreshed from it only if something is drawn before the next
+    // snapshot / frame (refresh_snapshot), so that a later restore still finds the saved state
+    std::swap(c->zkey, c->zsnap);
+    c->frame.zkey = c->zkey.as<unsigned long long>();
+    c->snap_stale = true;
     return TRB_OK;
 }
 int trb_keep_depth_as_shadow_map(TrbCtx* c, int32_t* out) {
