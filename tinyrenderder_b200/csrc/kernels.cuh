@@ -1004,6 +1004,14 @@ __global__ void __launch_bounds__(TPB) k_unbinned(FrameDev f, uint32_t ntris, ui
 // flush: the fragment() calls of our_gl.cpp:187-192, once per visible pixel
 // ---------------------------------------------------------------------------------------------
 constexpr int SHADE_MAX_SM_DRAWS = 32;
+static_assert(sizeof(DrawDev) % 4 == 0, "DrawDev is staged word by word");
+__device__ __forceinline__ void stage_draw_table(DrawDev* sm_draws, const DrawDev* __restrict__ draws, int ndraws) {
+    const int words = min(ndraws, SHADE_MAX_SM_DRAWS) * (int)(sizeof(DrawDev) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(draws);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sm_draws);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
 constexpr int SHADE_PX_PER_THREAD = 4;   // one 16-byte id load per thread: sparse frames (configs 4, 5) stay cheap
 
 // one visible pixel: p = x + y*W inside `view`, id = its winning triangle.  C2 = the frame has a
@@ -1011,16 +1019,17 @@ constexpr int SHADE_PX_PER_THREAD = 4;   // one 16-byte id load per thread: spar
 // carry their registers.
 template <bool C2, bool FAST>
 __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
-                                            const uint32_t* sm_base, int view, unsigned long long p, uint32_t id) {
+                                            const DrawDev* sm_draws, int view, unsigned long long p, uint32_t id) {
     constexpr int MAX_SM_DRAWS = SHADE_MAX_SM_DRAWS;
     const size_t gp = (size_t)view * f.npix + p;
     int lo = 0, hi = ndraws - 1;  // last draw with id_base < id
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
-        const uint32_t bse = mid < MAX_SM_DRAWS ? sm_base[mid] : draws[mid].id_base;
+        const uint32_t bse = mid < MAX_SM_DRAWS ? sm_draws[mid].id_base : draws[mid].id_base;
         if (bse < id) lo = mid; else hi = mid - 1;
     }
-    DrawDev D = draws[lo];
+    // the draw table sits in shared memory: one level less in the dependent chain id -> draw -> indices -> records -> texels
+    DrawDev D = lo < MAX_SM_DRAWS ? sm_draws[lo] : draws[lo];
     uint32_t t = id - D.id_base - 1u;                    // triangle inside the range this context drew
     if (t >= D.ntris) {
         // a winner another rank rasterised (sort-last composite): find the draw whose MESH holds it
@@ -1163,36 +1172,40 @@ __global__ void __launch_bounds__(TPB) k_shade_collect(FrameDev f, int row0, int
     if (!f.stats[view].shade_mode) return;
     unsigned long long* count = &f.stats[view].list_len;
     const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
-    const unsigned long long p0 = first + ((unsigned long long)blockIdx.x * TPB + threadIdx.x) * SHADE_PX_PER_THREAD;
     const uint32_t* vis = f.vis + (size_t)view * f.npix;
-    uint32_t ids[SHADE_PX_PER_THREAD];
-    for (int j = 0; j < SHADE_PX_PER_THREAD; ++j) ids[j] = VIS_NONE;
-    if (p0 < last) {
-        if (p0 + SHADE_PX_PER_THREAD <= last && ((reinterpret_cast<uintptr_t>(vis + p0) & 15) == 0)) {
-            const uint4 v = *reinterpret_cast<const uint4*>(vis + p0);
-            ids[0] = v.x; ids[1] = v.y; ids[2] = v.z; ids[3] = v.w;
-        } else {
-            for (int j = 0; j < SHADE_PX_PER_THREAD; ++j)
-                if (p0 + j < last) ids[j] = vis[p0 + j];
-        }
-    }
-    unsigned mine = 0;
-    for (int j = 0; j < SHADE_PX_PER_THREAD; ++j) mine += (ids[j] != VIS_NONE && ids[j] != VIS_SHADED) ? 1u : 0u;
-    // warp-aggregated append
     const unsigned lane = threadIdx.x & 31;
-    unsigned incl = mine;
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += y;
+    const unsigned long long per_block = (unsigned long long)TPB * SHADE_PX_PER_THREAD;
+    // grid-stride over blocks of TPB * 4 pixels: dense views cost a handful of CTAs that exit at once
+    for (unsigned long long b0 = first + blockIdx.x * per_block; b0 < last; b0 += gridDim.x * per_block) {
+        const unsigned long long p0 = b0 + (unsigned long long)threadIdx.x * SHADE_PX_PER_THREAD;
+        uint32_t ids[SHADE_PX_PER_THREAD];
+        for (int j = 0; j < SHADE_PX_PER_THREAD; ++j) ids[j] = VIS_NONE;
+        if (p0 < last) {
+            if (p0 + SHADE_PX_PER_THREAD <= last && ((reinterpret_cast<uintptr_t>(vis + p0) & 15) == 0)) {
+                const uint4 v = *reinterpret_cast<const uint4*>(vis + p0);
+                ids[0] = v.x; ids[1] = v.y; ids[2] = v.z; ids[3] = v.w;
+            } else {
+                for (int j = 0; j < SHADE_PX_PER_THREAD; ++j)
+                    if (p0 + j < last) ids[j] = vis[p0 + j];
+            }
+        }
+        unsigned mine = 0;
+        for (int j = 0; j < SHADE_PX_PER_THREAD; ++j) mine += (ids[j] != VIS_NONE && ids[j] != VIS_SHADED) ? 1u : 0u;
+        // warp-aggregated append
+        unsigned incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += y;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 31) base = atomicAdd(count, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t* out = list + (size_t)view * f.npix + base + (incl - mine);
+        for (int j = 0; j < SHADE_PX_PER_THREAD; ++j)
+            if (ids[j] != VIS_NONE && ids[j] != VIS_SHADED) *out++ = (uint32_t)(p0 + j);
     }
-    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;
-    unsigned long long base = 0;
-    if (lane == 31) base = atomicAdd(count, (unsigned long long)total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    uint32_t* out = list + (size_t)view * f.npix + base + (incl - mine);
-    for (int j = 0; j < SHADE_PX_PER_THREAD; ++j)
-        if (ids[j] != VIS_NONE && ids[j] != VIS_SHADED) *out++ = (uint32_t)(p0 + j);
 }
 
 // Dense frames (most pixels have an unshaded winner): one thread per pixel, no list
@@ -1206,9 +1219,8 @@ template <bool C2, bool FAST>
 __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
                                                      int row0, int row1) {
     if (f.stats[blockIdx.y].shade_mode) return;
-    __shared__ uint32_t sm_base[SHADE_MAX_SM_DRAWS];
-    for (int i = threadIdx.x; i < ndraws && i < SHADE_MAX_SM_DRAWS; i += TPB) sm_base[i] = draws[i].id_base;
-    __syncthreads();
+    __shared__ DrawDev sm_draws[SHADE_MAX_SM_DRAWS];
+    stage_draw_table(sm_draws, draws, ndraws);
     const int view = blockIdx.y;
 #if TRB_SHADE_2D
     // a CTA shades a 32x8 pixel block, each warp an 8x4 footprint: the lanes of a warp then share far
@@ -1228,7 +1240,7 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(Frame
     uint32_t* vis = f.vis + (size_t)view * f.npix;
     const uint32_t id = vis[p];
     if (id == VIS_NONE || id == VIS_SHADED) return;
-    shade_pixel<C2, FAST>(f, draws, ndraws, sm_base, view, p, id);
+    shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, p, id);
     vis[p] = VIS_SHADED;
 }
 
@@ -1237,16 +1249,15 @@ template <bool C2, bool FAST>
 __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
                                                const uint32_t* __restrict__ list) {
     if (!f.stats[blockIdx.y].shade_mode) return;
-    __shared__ uint32_t sm_base[SHADE_MAX_SM_DRAWS];
-    for (int i = threadIdx.x; i < ndraws && i < SHADE_MAX_SM_DRAWS; i += TPB) sm_base[i] = draws[i].id_base;
-    __syncthreads();
+    __shared__ DrawDev sm_draws[SHADE_MAX_SM_DRAWS];
+    stage_draw_table(sm_draws, draws, ndraws);
     const int view = blockIdx.y;
     const unsigned long long n = f.stats[view].list_len;
     const uint32_t* mylist = list + (size_t)view * f.npix;
     uint32_t* vis = f.vis + (size_t)view * f.npix;
     for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * TPB) {
         const uint32_t p = mylist[i];
-        shade_pixel<C2, FAST>(f, draws, ndraws, sm_base, view, p, vis[p]);
+        shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, p, vis[p]);
         vis[p] = VIS_SHADED;
     }
 }
@@ -1265,9 +1276,8 @@ template <bool C2, bool FAST>
 __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p2p(FrameDev f, PeerPlanes peers,
                                                                                   const DrawDev* __restrict__ draws,
                                                                                   int ndraws, int row0, int row1) {
-    __shared__ uint32_t sm_base[SHADE_MAX_SM_DRAWS];
-    for (int i = threadIdx.x; i < ndraws && i < SHADE_MAX_SM_DRAWS; i += TPB) sm_base[i] = draws[i].id_base;
-    __syncthreads();
+    __shared__ DrawDev sm_draws[SHADE_MAX_SM_DRAWS];
+    stage_draw_table(sm_draws, draws, ndraws);
     const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
     const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
     if (p >= last) return;
@@ -1280,7 +1290,7 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p
     }
     f.zkey[p] = bk;
     if (bid == VIS_NONE || bid == VIS_SHADED) { f.vis[p] = bid; return; }
-    shade_pixel<C2, FAST>(f, draws, ndraws, sm_base, 0, p, bid);
+    shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, 0, p, bid);
     f.vis[p] = VIS_SHADED;
 }
 

@@ -369,7 +369,8 @@ int do_flush(TrbCtx* c) {
             k_shade_decide<<<(f.nviews + TPB - 1) / TPB, TPB, 0, c->stream>>>(f, n);
         }
         {   // sparse views only (device-side predicate)
-            dim3 grid(blocks_for((n + SHADE_PX_PER_THREAD - 1) / SHADE_PX_PER_THREAD), f.nviews);
+            const unsigned need = blocks_for((n + SHADE_PX_PER_THREAD - 1) / SHADE_PX_PER_THREAD);
+            dim3 grid(std::min(need, std::max(1u, 148u * 16 / (unsigned)f.nviews)), f.nviews);
             Launch L(c, "k_shade_collect");
             k_shade_collect<<<grid, TPB, 0, c->stream>>>(f, r0, r1, c->shade_list.as<uint32_t>());
         }
