@@ -12,15 +12,18 @@
  *   - the caller owns every host pointer; the library owns device memory behind
  *     opaque handles.  Host buffers may be pageable or pinned; a PINNED buffer handed to
  *     trb_upload_* must stay unchanged until the next synchronising call (trb_read_*,
- *     trb_get_stats, trb_synchronize), pageable ones are staged before the call returns.
+ *     trb_get_stats, trb_readback_wait, trb_synchronize), pageable ones are consumed
+ *     before the call returns.
  *   - matrices are row-major double[16], exactly mat<4,4>::rows of the
  *     reference (geometry.h:155-166), column-vector convention (M*v).
  *   - colours are BGR bytes (TGAColor layout, tgaimage.h:29-63); row y=0 of the
  *     framebuffer is the bottom of the picture (tgaimage.cpp:176).
  *   - one context per GPU; a context is NOT thread-safe (the reference keeps its
  *     state in unsynchronised globals, our_gl.cpp:12-22); different contexts may
- *     be driven from different host threads.  All work of a context is queued on
- *     one CUDA stream; trb_read_* / trb_get_stats synchronise.
+ *     be driven from different host threads.  Rendering of a context is queued on
+ *     one CUDA stream (uploads and pipelined read-backs on two more, ordered by
+ *     events); draw calls never wait for the device.  trb_read_* / trb_get_stats /
+ *     trb_encode_tga / trb_readback_wait / trb_synchronize are the synchronising calls.
  *   - there is no CPU fallback: every entry point fails with TRB_E_CUDA when no
  *     sm_100 device is usable.
  *

@@ -6,6 +6,7 @@
 #include "tga_rle.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -76,42 +77,49 @@ struct Arena {
 
 // Resource blocks (meshes, textures) are recycled instead of cudaFree'd: cudaFree synchronises the
 // whole device and a caller that re-uploads its scene every frame would pay it each time.  A block
-// is tagged with an event recorded on the render stream when it is freed; uploads run on their own
-// stream, so a block is handed out again once that event has completed (the kernels that read it
-// are done).  While fewer than two blocks of a size exist a new one is allocated instead of waiting:
-// a caller that uploads, renders and frees every frame settles into two alternating sets, and the
-// upload of frame n+1 overlaps the rendering of frame n.
+// is tagged with an event recorded on the render stream when it is freed, and with the frame it
+// was freed in; uploads run on their own stream, so a block is handed out again once that event has
+// completed (the kernels that read it are done).  When no matching block is complete, one freed in an
+// EARLIER frame is handed out with its event for the upload stream to wait on (the upload then starts
+// when that older frame has rendered, i.e. it still overlaps the frame in flight); blocks freed in the
+// current frame are left alone and a new block is allocated instead.  A caller that uploads, renders
+// and frees every frame therefore settles into two alternating sets, and the upload of frame n+1
+// overlaps the rendering of frame n.
 struct BlockCache {
-    struct Entry { size_t bytes; void* p; cudaEvent_t freed; };
+    struct Entry { size_t bytes; void* p; cudaEvent_t freed; uint64_t frame; };
     std::vector<Entry> free_blocks;
     std::vector<cudaEvent_t> ev_pool;
+    uint64_t frame = 0;                        // advanced by begin_batch
+    size_t cached_bytes = 0;
+    static constexpr size_t SOFT_LIMIT = (size_t)16 << 30;   // beyond this, wait for a busy block rather than grow
     // *wait_for: event the consumer stream must wait on before writing the block (nullptr: none)
     cudaError_t get(void** out, size_t bytes, cudaEvent_t* wait_for) {
         bytes = (bytes + 511) & ~(size_t)511;
         *wait_for = nullptr;
-        int fits = 0, busy = -1;
+        int busy = -1;
         for (size_t i = 0; i < free_blocks.size(); ++i) {
             Entry& e = free_blocks[i];
             if (e.bytes < bytes || e.bytes > bytes + bytes / 8 + 4096) continue;
-            ++fits;
             if (cudaEventQuery(e.freed) == cudaSuccess) {
                 *out = e.p;
-                ev_pool.push_back(e.freed);
-                free_blocks.erase(free_blocks.begin() + i);
+                take(i);
                 return cudaSuccess;
             }
-            if (busy < 0) busy = (int)i;
+            if (busy < 0 && (e.frame < frame || cached_bytes > SOFT_LIMIT)) busy = (int)i;
         }
         (void)cudaGetLastError();   // cudaErrorNotReady from the queries is not an error
-        if (busy >= 0 && fits >= 2) {          // oldest matching block: let the consumer stream wait for its readers
-            Entry e = free_blocks[busy];
-            *out = e.p;
-            *wait_for = e.freed;               // stays valid: returned to the pool, never destroyed before release()
-            ev_pool.push_back(e.freed);
-            free_blocks.erase(free_blocks.begin() + busy);
+        if (busy >= 0) {            // oldest acceptable block: the consumer stream waits for its readers
+            *out = free_blocks[busy].p;
+            *wait_for = free_blocks[busy].freed;   // stays valid: returned to the pool, never destroyed before release()
+            take((size_t)busy);
             return cudaSuccess;
         }
         return cudaMalloc(out, bytes);
+    }
+    void take(size_t i) {
+        ev_pool.push_back(free_blocks[i].freed);
+        cached_bytes -= free_blocks[i].bytes;
+        free_blocks.erase(free_blocks.begin() + i);
     }
     void put(void* p, size_t bytes, cudaStream_t readers) {
         if (!p) return;
@@ -123,7 +131,9 @@ struct BlockCache {
             cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
         }
         cudaEventRecord(ev, readers);
-        free_blocks.push_back(Entry{(bytes + 511) & ~(size_t)511, p, ev});
+        bytes = (bytes + 511) & ~(size_t)511;
+        free_blocks.push_back(Entry{bytes, p, ev, frame});
+        cached_bytes += bytes;
     }
     void release() {
         for (auto& b : free_blocks) {
@@ -133,6 +143,7 @@ struct BlockCache {
         for (auto e : ev_pool) cudaEventDestroy(e);
         free_blocks.clear();
         ev_pool.clear();
+        cached_bytes = 0;
     }
 };
 
@@ -261,6 +272,7 @@ struct TrbCtx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     bool profiling = false;
     std::vector<ProfEntry> prof_pending;
+    cudaEvent_t trace_base = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<ProfAcc> prof_acc;
     uint64_t launches = 0;
@@ -289,8 +301,8 @@ struct Launch {  // RAII around one kernel launch: counts it and, when profiling
     const char* name;
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t st;
-    Launch(TrbCtx* c_, const char* n, cudaStream_t s = nullptr) : c(c_), name(n), st(s ? s : c_->stream) {
-        ++c->launches;
+    Launch(TrbCtx* c_, const char* n, cudaStream_t s = nullptr, bool kernel = true) : c(c_), name(n), st(s ? s : c_->stream) {
+        if (kernel) ++c->launches;   // copies are bracketed for the timeline but are not kernel launches
         if (c->profiling) {
             a = get_event();
             b = get_event();
@@ -319,9 +331,23 @@ void prof_collect(TrbCtx* c) {
     if (c->prof_pending.empty()) return;
     cudaStreamSynchronize(c->stream);
     if (c->upload_stream) cudaStreamSynchronize(c->upload_stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    // TRB_TRACE=<file>: per-launch timeline (start relative to the first traced launch, duration) for
+    // hunting gaps between kernels; developer aid, off by default
+    FILE* trace = nullptr;
+    if (const char* path = getenv("TRB_TRACE")) trace = fopen(path, "a");
     for (auto& p : c->prof_pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, p.a, p.b);
+        if (trace) {
+            if (!c->trace_base) {
+                c->trace_base = p.a;
+                p.a = nullptr;            // kept for the lifetime of the context
+            }
+            float t0 = 0;
+            if (p.a) cudaEventElapsedTime(&t0, c->trace_base, p.a);
+            fprintf(trace, "%.4f %.4f %s\n", t0, ms, p.name);
+        }
         ProfAcc* acc = nullptr;
         for (auto& a : c->prof_acc)
             if (a.name == p.name) acc = &a;
@@ -331,11 +357,31 @@ void prof_collect(TrbCtx* c) {
         }
         acc->launches++;
         acc->ms += ms;
-        c->ev_pool.push_back(p.a);
+        if (p.a) c->ev_pool.push_back(p.a);
         c->ev_pool.push_back(p.b);
     }
+    if (trace) fclose(trace);
     c->prof_pending.clear();
 }
+
+// TRB_TRACE: host wall-clock of the entry points that should never wait for the device (developer aid)
+struct HostSpan {
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit HostSpan(const char* n) : name(n), on(getenv("TRB_TRACE") != nullptr) {
+        if (on) t0 = std::chrono::steady_clock::now();
+    }
+    ~HostSpan() {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms < 0.2) return;
+        if (FILE* f = fopen((std::string(getenv("TRB_TRACE")) + ".host").c_str(), "a")) {
+            fprintf(f, "%.3f %s\n", ms, name);
+            fclose(f);
+        }
+    }
+};
 
 inline unsigned blocks_for(unsigned long long n) { return (unsigned)((n + TPB - 1) / TPB); }
 
@@ -779,6 +825,7 @@ extern "C" {
 
 int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float* uv2, uint32_t nverts,
                     const uint32_t* idx, uint64_t nidx, TrbMesh* out) {
+    HostSpan host_span_("trb_upload_mesh");
     if (!c || !pos3 || !out || nidx % 3 || nverts == 0) return fail(c, TRB_E_ARG, "upload_mesh: bad argument");
     if (nidx / 3 >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "upload_mesh: too many triangles");
     int rc = check_device(c);
@@ -862,6 +909,7 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
 }
 
 int trb_free_mesh(TrbCtx* c, TrbMesh h) {
+    HostSpan host_span_("trb_free_mesh");
     if (!c || h == 0 || h > c->meshes.size() || !c->meshes[h - 1].alive) return fail(c, TRB_E_ARG, "free_mesh");
     int rc = check_device(c);
     if (rc) return rc;
@@ -874,6 +922,7 @@ int trb_free_mesh(TrbCtx* c, TrbMesh h) {
 }
 
 int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, TrbTex* out) {
+    HostSpan host_span_("trb_upload_texture");
     if (!c || !texels || !out || w <= 0 || h <= 0 || (bpp != 1 && bpp != 3 && bpp != 4))
         return fail(c, TRB_E_ARG, "upload_texture: bad argument");
     int rc = check_device(c);
@@ -899,6 +948,7 @@ int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, 
 }
 
 int trb_free_texture(TrbCtx* c, TrbTex h) {
+    HostSpan host_span_("trb_free_texture");
     if (!c || h == 0 || h > c->textures.size() || !c->textures[h - 1].alive) return fail(c, TRB_E_ARG, "free_texture");
     int rc = check_device(c);
     if (rc) return rc;
@@ -909,6 +959,7 @@ int trb_free_texture(TrbCtx* c, TrbTex h) {
 }
 
 int trb_begin_batch(TrbCtx* c, int w, int h, int nviews) {
+    HostSpan host_span_("trb_begin_batch");
     if (!c || w <= 0 || h <= 0 || nviews <= 0 || nviews > 65535 || w > 65536 || h > 65536)
         return fail(c, TRB_E_ARG, "begin_batch: bad size");
     int rc = check_device(c);
@@ -933,6 +984,7 @@ int trb_begin_batch(TrbCtx* c, int w, int h, int nviews) {
     for (int i = 0; i < 16; ++i) f.viewport[i] = (i % 5 == 0) ? 1.0 : 0.0;
     c->draws.clear();
     c->arena.reset();
+    ++c->cache.frame;
     c->next_id = 0;
     c->tris_submitted = 0;
     c->have_snapshot = false;
@@ -965,6 +1017,7 @@ int trb_set_viewport(TrbCtx* c, const double* v) {
 
 int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
                    size_t ubytes, uint64_t first_tri, uint64_t ntris) {
+    HostSpan host_span_("trb_draw_batch");
     if (!c || !c->in_frame) return fail(c, TRB_E_ARG, "draw: no frame");
     if (!mv || !pr) return fail(c, TRB_E_ARG, "draw: null matrix");
     if (mesh == 0 || mesh > c->meshes.size() || !c->meshes[mesh - 1].alive) return fail(c, TRB_E_ARG, "draw: bad mesh");
@@ -1118,6 +1171,7 @@ int trb_submit_clip_triangles(TrbCtx* c, const double* clip12, const double* var
 }
 
 int trb_depth_snapshot(TrbCtx* c) {
+    HostSpan host_span_("trb_depth_snapshot");
     if (!c || !c->in_frame) return fail(c, TRB_E_ARG, "depth_snapshot: no frame");
     int rc = check_device(c);
     if (rc) return rc;
@@ -1127,12 +1181,16 @@ int trb_depth_snapshot(TrbCtx* c) {
     // so resolve first to snapshot what the reference's vector copy (main.cpp:700) would hold
     rc = do_flush(c);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(c->zsnap.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    {
+        Launch L(c, "copy_depth_snapshot", nullptr, false);
+        CU(cudaMemcpyAsync(c->zsnap.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
     c->have_snapshot = true;
     c->snap_stale = false;
     return TRB_OK;
 }
 int trb_depth_restore(TrbCtx* c) {
+    HostSpan host_span_("trb_depth_restore");
     if (!c || !c->in_frame || !c->have_snapshot) return fail(c, TRB_E_ARG, "depth_restore: no snapshot");
     int rc = do_flush(c);  // colours of everything drawn so far persist (main.cpp:730)
     if (rc) return rc;
@@ -1179,6 +1237,7 @@ int trb_flush(TrbCtx* c) {
     return do_flush(c);
 }
 int trb_end_frame(TrbCtx* c) {
+    HostSpan host_span_("trb_end_frame");
     if (!c) return TRB_E_ARG;
     return do_flush(c);
 }
@@ -1227,6 +1286,7 @@ int trb_readback_wait(TrbCtx* c) {
     return TRB_OK;
 }
 int trb_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* depth_out) {
+    HostSpan host_span_("trb_readback_async");
     if (!c || !c->in_frame) return fail(c, TRB_E_ARG, "readback_async: no frame");
     int rc = do_flush(c);
     if (rc) return rc;
@@ -1239,6 +1299,7 @@ int trb_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* dept
     }
     const int i = (c->rb_idx ^= 1);
     if (c->rb_inflight[i]) {  // staging area i is still being drained by the copy stream
+        HostSpan w("readback_async:wait_slot");
         CU(cudaEventSynchronize(c->rb_done[i]));
         c->rb_inflight[i] = false;
     }
@@ -1247,7 +1308,10 @@ int trb_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* dept
     const size_t color_bytes = color_out ? total * 3 : 0, depth_off = (color_bytes + 255) & ~(size_t)255;
     CU(c->rb[i].ensure(depth_off + (depth_out ? total * 8 : 0), c->stream));
     uint8_t* stage = c->rb[i].as<uint8_t>();
-    if (color_out) CU(cudaMemcpyAsync(stage, f.color, color_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (color_out) {
+        Launch L(c, "copy_stage_color", nullptr, false);
+        CU(cudaMemcpyAsync(stage, f.color, color_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
     if (depth_out) {
         Launch L(c, "k_unmap_depth");
         k_unmap_depth<<<blocks_for(total), TPB, 0, c->stream>>>(f.zkey, total, reinterpret_cast<double*>(stage + depth_off));
@@ -1255,6 +1319,8 @@ int trb_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* dept
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->rb_ready[i], c->stream));
     CU(cudaStreamWaitEvent(c->copy_stream, c->rb_ready[i], 0));
+    Launch span(c, "copy_d2h_frames", c->copy_stream, false);
+    HostSpan d2h("readback_async:enqueue_d2h");
     for (int v = 0; v < f.nviews; ++v) {
         if (color_out && color_out[v])
             CU(cudaMemcpyAsync(color_out[v], stage + (size_t)f.npix * 3 * v, (size_t)f.npix * 3, cudaMemcpyDeviceToHost,
