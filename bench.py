@@ -261,6 +261,23 @@ def run_reference(args, steps, warmup):
             "tris_per_step": tris_total / max(1, len(times)), "tris_per_unit": tris_per_frame}
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPU cores next to its GPU (NVML's ideal affinity) before any pinned host
+    buffer is allocated: with 8 ranks the read-backs otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = [i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
@@ -297,6 +314,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api = trb.load_cuda()
@@ -563,6 +581,7 @@ def main():
         "wall_ms_per_step": 1e3 * t_wall / args.steps,
         "ms_per_step_unprofiled": ms_unprofiled / args.steps,
         "tga_encode": tga,
+        "cpu_affinity_cores": numa,
     }
     print(json.dumps(line))
     if world > 1:
