@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--frames-per-step", type=int, default=32, help="c3: frames per rank per step")
     ap.add_argument("--c4-level", type=int, default=10)
     ap.add_argument("--c5-tris", type=int, default=100_000_000)
@@ -66,6 +66,10 @@ class Workload:
             self.scene = scenes.head_scene()
             self.frames = 1
             self.label = "c1_head_800x800_%dtri" % self.scene.ntris
+        elif w == "c2":
+            self.scene = scenes.shadow_scene()
+            self.frames = 1
+            self.label = "c2_shadow_2048x2048_%dtri_depth_pass+shadow_pass" % self.scene.ntris
         elif w == "c4":
             self.scene = scenes.sphere_scene(args.c4_level)
             self.frames = 1
@@ -90,11 +94,19 @@ class Workload:
         if self.name == "c3":
             first = ((step * world) + rank) * self.frames
             return sc.orbit_views(api, [(first + j) % 1024 for j in range(self.frames)])
-        if self.name == "c1":
+        if self.name in ("c1", "c2"):
             return sc.head_view(api)[None]
         if self.name == "c4":
             return sc.sphere_view(api)[None]
         return np.eye(4)[None]
+
+
+    def render(self, up, views):
+        """one step through an UploadedScene: the frame loop of main.cpp; config 2 adds the light's depth pass"""
+        if self.name == "c2":
+            self.scenes.render_shadowed(up, views[0], self.perspective)
+        else:
+            up.render(views, self.perspective)
 
 
 def algorithmic_bytes(V, T, P, R, T_vis, C, frames=1):
@@ -197,7 +209,7 @@ def _ref_worker_frame(job):
         views = wl.views(api, step, 0, 1)
     t0 = time.perf_counter()
     if tri_count is None:
-        up.render(views, wl.perspective)
+        wl.render(up, views)
         ntri = wl.tris_per_frame
     else:  # bounded sample of a huge single frame: a contiguous triangle range (frame clear not timed)
         it = wl.scene.items[0]
@@ -236,7 +248,7 @@ def run_reference(args, steps, warmup):
         tris_total = 0
         sample = ""
         for s in range(warmup + steps):
-            if args.workload == "c3" or args.workload == "c1":
+            if args.workload in ("c1", "c2", "c3"):
                 jobs = [(s, p, procs, 0, None) for p in range(procs)]
                 sample = "%d frame(s) per step, one per process" % procs
             else:
@@ -333,7 +345,7 @@ def main():
 
     def step(s):
         if not sharded_c4:
-            up.render(wl.views(api, s, rank, world), wl.perspective)
+            wl.render(up, wl.views(api, s, rank, world))
             return
         # config 4 on N GPUs: triangle range per rank, sort-last composite over NCCL, shade own rows
         it = wl.scene.items[0]
@@ -461,12 +473,12 @@ def main():
         def e2e_step(s, with_depth, resident=False):
             t = [time.perf_counter()]
             if resident:   # meshes and textures uploaded once (north_star); per step only matrices and uniforms go up
-                up_resident.render(wl.views(api, s, rank, world), wl.perspective)
+                wl.render(up_resident, wl.views(api, s, rank, world))
                 r.readback_async(color_host[s & 1], depth_host[s & 1] if with_depth else None)
                 return per_step_uniform_bytes
             up2 = wl.scenes.UploadedScene(r, wl.scene)                 # H2D: meshes + textures
             t.append(time.perf_counter())
-            up2.render(wl.views(api, s, rank, world), wl.perspective)  # H2D: matrices, uniforms
+            wl.render(up2, wl.views(api, s, rank, world))              # H2D: matrices, uniforms
             t.append(time.perf_counter())
             # D2H: the BGR framebuffer of every frame (what the reference writes out, main.cpp:743);
             # with_depth also brings back the f64 z-buffer the reference keeps in a host global
