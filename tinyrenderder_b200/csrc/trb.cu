@@ -237,6 +237,7 @@ struct TrbCtx {
     bool have_snapshot = false;
     bool snap_stale = false;        // restored by pointer swap: zsnap must be refreshed before the key plane changes
     std::vector<ShadowMap> shadow_maps;
+    std::vector<DevBuf> shadow_pool;   // planes of released shadow maps, recycled by trb_keep_depth_as_shadow_map
     Arena arena;
     std::vector<DrawDev> draws;     // since the last flush
     DevBuf draw_table;
@@ -728,6 +729,7 @@ int trb_destroy(TrbCtx* c) {
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.keys.release();
+    for (auto& b : c->shadow_pool) b.release();
     trb_ipc_close_peers(c);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
@@ -1214,6 +1216,14 @@ int trb_keep_depth_as_shadow_map(TrbCtx* c, int32_t* out) {
     if (rc) return rc;
     ShadowMap b;
     size_t bytes = (size_t)c->frame.npix * 8;
+    // planes of released maps are recycled (stream order keeps their last readers ahead of this copy):
+    // a frame loop that builds a shadow map per frame neither allocates nor synchronises
+    for (size_t i = 0; i < c->shadow_pool.size(); ++i)
+        if (c->shadow_pool[i].cap >= bytes) {
+            b.keys = c->shadow_pool[i];
+            c->shadow_pool.erase(c->shadow_pool.begin() + i);
+            break;
+        }
     CU(b.keys.ensure(bytes, c->stream));
     CU(cudaMemcpyAsync(b.keys.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
     b.w = c->frame.W;
@@ -1226,9 +1236,13 @@ int trb_keep_depth_as_shadow_map(TrbCtx* c, int32_t* out) {
 int trb_release_shadow_maps(TrbCtx* c) {
     if (!c) return TRB_E_ARG;
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(c->stream));
-    for (auto& b : c->shadow_maps) b.keys.release();
+    for (auto& b : c->shadow_maps) c->shadow_pool.push_back(b.keys);   // no sync, no cudaFree: reused by the next keep
     c->shadow_maps.clear();
+    while (c->shadow_pool.size() > 4) {          // a caller that keeps many maps once should not pin them forever
+        CU(cudaStreamSynchronize(c->stream));
+        c->shadow_pool.back().release();
+        c->shadow_pool.pop_back();
+    }
     return TRB_OK;
 }
 
