@@ -193,3 +193,25 @@ def test_parallel_formulation_equals_the_sequential_packetiser(port_api):
     got = model.encode_views(px, 1000, len(same), 3)
     for n, g in zip(same, got):
         assert g == want[n][18:], n
+
+
+@pytest.mark.gpu
+def test_encode_tga_argument_errors(cuda_api):
+    """a too small output buffer is an error (nothing is truncated silently); a NULL buffer is a size query"""
+    import ctypes as C
+    img = _runs([1, 3, 1, 130, 2])
+    h, w = img.shape[:2]
+    with trb.Renderer(cuda_api) as r:
+        r.begin_frame(w, h)
+        r.write_color(img)
+        want = r.encode_tga(capi.IMAGE_COLOR)[0]
+        sizes = (C.c_uint64 * 1)()
+        table = (C.c_void_p * 1)(None)
+        rc = cuda_api.fn["encode_tga"](r.h, 0, C.cast(table, C.c_void_p), 0, C.cast(sizes, C.c_void_p))
+        assert rc == 0 and sizes[0] == len(want)
+        small = np.empty(len(want) - 1, dtype=np.uint8)
+        table = (C.c_void_p * 1)(small.ctypes.data)
+        rc = cuda_api.fn["encode_tga"](r.h, 0, C.cast(table, C.c_void_p), small.size, C.cast(sizes, C.c_void_p))
+        assert rc < 0
+        rc = cuda_api.fn["encode_tga"](r.h, 7, C.cast(table, C.c_void_p), small.size, C.cast(sizes, C.c_void_p))
+        assert rc < 0
