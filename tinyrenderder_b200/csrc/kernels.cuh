@@ -249,6 +249,10 @@ constexpr uint32_t BOX_DIRECT = 0xFFFFFFFEu;   // tribox.x of a direct triangle
 #ifndef TRB_SETUP_MIN_BLOCKS
 #define TRB_SETUP_MIN_BLOCKS 4
 #endif
+#ifndef TRB_SETUP_CHUNKS
+#define TRB_SETUP_CHUNKS 4
+#endif
+constexpr int SETUP_CHUNKS = TRB_SETUP_CHUNKS;   // chunks of TPB triangles per CTA of k_setup_count
 constexpr int DIRECT_AREA_DEFAULT = 16;
 
 __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(FrameDev f, GeomArgs g, uint2* __restrict__ tribox,
@@ -259,80 +263,117 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
     __shared__ unsigned sh_w[5 * 8];
     static_assert(TPB / 32 == 8, "block totals are laid out for 8 warps");
     const int view = blockIdx.y;
-    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
     const VRec* vr = g.vrec + (size_t)view * g.nverts;
-    int res = SETUP_REJECT;
-    TriSetup ts;
-    if (t < g.ntris) {
-        VRec a = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 0));
-        VRec b = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 1));
-        VRec c = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 2));
-        res = setup_triangle(a, b, c, f.W, f.H, ts);
-    }
-    // statistics bbox + "survived the rejects" count, our_gl.cpp:138-141 (reduced with the other
-    // per-block totals in ONE pass at the end of the kernel)
-    const bool counted = res != SETUP_REJECT;
-
-    uint2 box = make_uint2(BOX_NONE, 0u);
-    uint32_t ntile = 0;
-    int tx0 = 0, ty0 = 0, tx1 = -1, ty1 = -1;
-    unsigned long long direct_cov = 0, direct_zmin = ~0ull;
-    // Direct only when (nearly) the whole warp holds small triangles in DISTINCT tiles (a random
-    // soup).  Measured on B200: with half of the lanes idle (back faces of a closed mesh) or lanes
-    // hitting the same pixels the two direct passes cost more than the compacted bins of the tile path
-    // (config 4: 1.0 ms binned vs 1.55 ms direct at level 9; config 5: 6.3 ms binned vs 2.7 ms direct).
-    const bool small_tri = res == SETUP_DRAW && (ts.x1 - ts.x0 + 1) * (ts.y1 - ts.y0 + 1) <= direct_area;
     const unsigned lane_id = threadIdx.x & 31;
-    const unsigned tkey = small_tri ? (unsigned)((ts.y0 >> TILE_SHIFT) * f.tw + (ts.x0 >> TILE_SHIFT)) : (0x80000000u | lane_id);
-    const unsigned same_tile = __match_any_sync(0xffffffffu, tkey);   // every lane takes part: no short-circuit
-    const bool lonely = small_tri && __popc(same_tile) <= 2;
-    const unsigned m_small = __ballot_sync(0xffffffffu, small_tri), m_lonely = __ballot_sync(0xffffffffu, lonely);
-    (void)m_small;
-    if (small_tri && __popc(m_lonely) >= 24) {
-        unsigned long long* zk = f.zkey + (size_t)view * f.npix;
-        uint32_t* vis = f.vis + (size_t)view * f.npix;
-        uint32_t candidate = 0;
-        for (int y = ts.y0; y <= ts.y1; ++y)
-            for (int x = ts.x0; x <= ts.x1; ++x) {
-                double b[3], z;
-                if (!eval_sample(ts, x, y, b, z)) continue;
-                const unsigned long long key = fragment_key(z);
-                const size_t p = (size_t)y * f.W + x;
-                ++direct_cov;
-                direct_zmin = min(direct_zmin, key);
-                if (key <= zk[p]) {
-                    const unsigned long long old = atomicMin(zk + p, key);
-                    if (old > key) vis[p] = VIS_NONE;      // strictly nearer: the old winner is gone
-                    if (old >= key) candidate = 1;
+    uint32_t* cnt = tile_count + (size_t)view * f.ntiles;
+    // block totals, accumulated over the CTA's chunks and reduced once at the end
+    int acc_x0 = INT_MAX, acc_y0 = INT_MAX, acc_x1 = INT_MIN, acc_y1 = INT_MIN;
+    unsigned acc_nb = 0, acc_ne = 0;
+    unsigned long long direct_cov = 0, direct_zmin = ~0ull;
+    // A CTA takes SETUP_CHUNKS consecutive chunks of TPB triangles.  The vertex indices of the NEXT chunk are
+    // requested before the current chunk's vertex records are gathered, so the dependent chain
+    // index -> record -> setup only pays one memory latency per chunk instead of two.
+    const uint32_t t_first = blockIdx.x * (TPB * SETUP_CHUNKS) + threadIdx.x;
+    uint32_t n0 = 0, n1 = 0, n2 = 0;
+    if (t_first < g.ntris) {
+        n0 = vertex_index(g.idx, g.first_tri, t_first, 0);
+        n1 = vertex_index(g.idx, g.first_tri, t_first, 1);
+        n2 = vertex_index(g.idx, g.first_tri, t_first, 2);
+    }
+    #pragma unroll 1
+    for (int chunk = 0; chunk < SETUP_CHUNKS; ++chunk) {
+        const uint32_t t = t_first + chunk * TPB;
+        if (blockIdx.x * (TPB * SETUP_CHUNKS) + chunk * TPB >= g.ntris) break;   // uniform over the CTA
+        const uint32_t i0 = n0, i1 = n1, i2 = n2;
+        if (chunk + 1 < SETUP_CHUNKS && t + TPB < g.ntris) {
+            n0 = vertex_index(g.idx, g.first_tri, t + TPB, 0);
+            n1 = vertex_index(g.idx, g.first_tri, t + TPB, 1);
+            n2 = vertex_index(g.idx, g.first_tri, t + TPB, 2);
+        }
+        int res = SETUP_REJECT;
+        TriSetup ts;
+        if (t < g.ntris) {
+            VRec a = load_vrec(vr + i0);
+            VRec b = load_vrec(vr + i1);
+            VRec c = load_vrec(vr + i2);
+            res = setup_triangle(a, b, c, f.W, f.H, ts);
+        }
+        // statistics bbox + "survived the rejects" count, our_gl.cpp:138-141
+        if (res != SETUP_REJECT) {
+            acc_x0 = min(acc_x0, ts.x0); acc_y0 = min(acc_y0, ts.y0);
+            acc_x1 = max(acc_x1, ts.x1); acc_y1 = max(acc_y1, ts.y1);
+            ++acc_nb;
+        }
+        uint2 box = make_uint2(BOX_NONE, 0u);
+        uint32_t ntile = 0;
+        int tx0 = 0, ty0 = 0, tx1 = -1, ty1 = -1;
+        // Direct only when (nearly) the whole warp holds small triangles in DISTINCT tiles (a random
+        // soup).  Measured on B200: with half of the lanes idle (back faces of a closed mesh) or lanes
+        // hitting the same pixels the two direct passes cost more than the compacted bins of the tile path
+        // (config 4: 1.0 ms binned vs 1.55 ms direct at level 9; config 5: 6.3 ms binned vs 2.7 ms direct).
+        const bool small_tri = res == SETUP_DRAW && (ts.x1 - ts.x0 + 1) * (ts.y1 - ts.y0 + 1) <= direct_area;
+        const unsigned tkey = small_tri ? (unsigned)((ts.y0 >> TILE_SHIFT) * f.tw + (ts.x0 >> TILE_SHIFT)) : (0x80000000u | lane_id);
+        const unsigned same_tile = __match_any_sync(0xffffffffu, tkey);   // every lane takes part: no short-circuit
+        const bool lonely = small_tri && __popc(same_tile) <= 2;
+        const unsigned m_lonely = __ballot_sync(0xffffffffu, lonely);
+        if (small_tri && __popc(m_lonely) >= 24) {
+            unsigned long long* zk = f.zkey + (size_t)view * f.npix;
+            uint32_t* vis = f.vis + (size_t)view * f.npix;
+            uint32_t candidate = 0;
+            for (int y = ts.y0; y <= ts.y1; ++y)
+                for (int x = ts.x0; x <= ts.x1; ++x) {
+                    double b[3], z;
+                    if (!eval_sample(ts, x, y, b, z)) continue;
+                    const unsigned long long key = fragment_key(z);
+                    const size_t p = (size_t)y * f.W + x;
+                    ++direct_cov;
+                    direct_zmin = min(direct_zmin, key);
+                    if (key <= zk[p]) {
+                        const unsigned long long old = atomicMin(zk + p, key);
+                        if (old > key) vis[p] = VIS_NONE;      // strictly nearer: the old winner is gone
+                        if (old >= key) candidate = 1;
+                    }
                 }
+            box = make_uint2(BOX_DIRECT, candidate);
+            res = SETUP_NO_COVERAGE;                            // handled: keep it out of the bins
+            // triangles that may own a pixel go on the view's list: k_direct_resolve then runs full warps
+            // over ~the visible fraction instead of idling through every triangle of the draw
+            const unsigned act = __activemask(), cm = __ballot_sync(act, candidate != 0);
+            if (cm) {
+                const int leader = __ffs(cm) - 1;
+                uint32_t base = 0;
+                if ((int)lane_id == leader) base = atomicAdd(direct_n + view, (uint32_t)__popc(cm));
+                base = __shfl_sync(act, base, leader);
+                if (candidate) direct_list[(size_t)view * g.ntris + base + __popc(cm & ((1u << lane_id) - 1u))] = t;
             }
-        box = make_uint2(BOX_DIRECT, candidate);
-        res = SETUP_NO_COVERAGE;                            // handled: keep it out of the bins
-        // triangles that may own a pixel go on the view's list: k_direct_resolve then runs full warps
-        // over ~the visible fraction instead of idling through every triangle of the draw
-        const unsigned act = __activemask(), cm = __ballot_sync(act, candidate != 0);
-        if (cm) {
-            const int leader = __ffs(cm) - 1;
-            uint32_t base = 0;
-            if ((int)lane_id == leader) base = atomicAdd(direct_n + view, (uint32_t)__popc(cm));
-            base = __shfl_sync(act, base, leader);
-            if (candidate) direct_list[(size_t)view * g.ntris + base + __popc(cm & ((1u << lane_id) - 1u))] = t;
+        }
+        if (res == SETUP_DRAW) {
+            tx0 = ts.x0 >> TILE_SHIFT; tx1 = ts.x1 >> TILE_SHIFT;
+            ty0 = ts.y0 >> TILE_SHIFT; ty1 = ts.y1 >> TILE_SHIFT;
+            box = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
+            ntile = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+            acc_ne += ntile;
+            store_trirec(trirec + (size_t)view * g.ntris + t, ts);
+        }
+        if (t < g.ntris) tribox[(size_t)view * g.ntris + t] = box;
+        // per-tile counts; single-tile triangles (the common case for small triangles) are aggregated
+        // across the warp with match_any so that coherent meshes do not serialise on one counter
+        unsigned key = 0x80000000u | lane_id;  // unique: no aggregation
+        if (ntile == 1) key = (unsigned)(ty0 * f.tw + tx0);
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (ntile == 1) {
+            if ((unsigned)(__ffs(peers) - 1) == lane_id) atomicAdd(cnt + key, (uint32_t)__popc(peers));
+        } else if (ntile > 1) {
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt + ty * f.tw + tx, 1u);
         }
     }
-    if (res == SETUP_DRAW) {
-        tx0 = ts.x0 >> TILE_SHIFT; tx1 = ts.x1 >> TILE_SHIFT;
-        ty0 = ts.y0 >> TILE_SHIFT; ty1 = ts.y1 >> TILE_SHIFT;
-        box = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
-        ntile = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
-        store_trirec(trirec + (size_t)view * g.ntris + t, ts);
-    }
-    if (t < g.ntris) tribox[(size_t)view * g.ntris + t] = box;
     {   // block totals: one REDUX per value and warp, one barrier, one more REDUX in warp 0
         const unsigned FULL = 0xffffffffu;
         const unsigned lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
-        int bx0 = __reduce_min_sync(FULL, counted ? ts.x0 : INT_MAX), by0 = __reduce_min_sync(FULL, counted ? ts.y0 : INT_MAX);
-        int bx1 = __reduce_max_sync(FULL, counted ? ts.x1 : INT_MIN), by1 = __reduce_max_sync(FULL, counted ? ts.y1 : INT_MIN);
-        unsigned nb = __reduce_add_sync(FULL, counted ? 1u : 0u), ne = __reduce_add_sync(FULL, ntile);
+        int bx0 = __reduce_min_sync(FULL, acc_x0), by0 = __reduce_min_sync(FULL, acc_y0);
+        int bx1 = __reduce_max_sync(FULL, acc_x1), by1 = __reduce_max_sync(FULL, acc_y1);
+        unsigned nb = __reduce_add_sync(FULL, acc_nb), ne = __reduce_add_sync(FULL, acc_ne);
         unsigned dcov = __reduce_add_sync(FULL, (unsigned)direct_cov);
         unsigned zhi = __reduce_min_sync(FULL, (unsigned)(direct_zmin >> 32));
         unsigned zlo = __reduce_min_sync(FULL, (unsigned)(direct_zmin >> 32) == zhi ? (unsigned)direct_zmin : 0xffffffffu);
@@ -366,19 +407,6 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
                 }
             }
         }
-    }
-    // per-tile counts; single-tile triangles (the common case for small triangles) are aggregated
-    // across the warp with match_any so that coherent meshes do not serialise on one counter
-    uint32_t* cnt = tile_count + (size_t)view * f.ntiles;
-    const unsigned lane = threadIdx.x & 31;
-    unsigned key = 0x80000000u | lane;  // unique: no aggregation
-    if (ntile == 1) key = (unsigned)(ty0 * f.tw + tx0);
-    unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (ntile == 1) {
-        if ((unsigned)(__ffs(peers) - 1) == lane) atomicAdd(cnt + key, (uint32_t)__popc(peers));
-    } else if (ntile > 1) {
-        for (int ty = ty0; ty <= ty1; ++ty)
-            for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt + ty * f.tw + tx, 1u);
     }
 }
 

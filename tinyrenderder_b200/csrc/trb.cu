@@ -536,7 +536,8 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     dim3 tgrid(blocks_for(g.ntris), f.nviews);
     {
         Launch L(c, "k_setup_count");
-        k_setup_count<<<tgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
+        const dim3 sgrid((g.ntris + TPB * SETUP_CHUNKS - 1) / (TPB * SETUP_CHUNKS), f.nviews);
+        k_setup_count<<<sgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
                                                      c->counts.as<uint32_t>(), c->direct_area, c->direct_list.as<uint32_t>(),
                                                      c->direct_n.as<uint32_t>());
     }
