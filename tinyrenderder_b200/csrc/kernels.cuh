@@ -502,18 +502,25 @@ __global__ void __launch_bounds__(TPB) k_scan_sums(uint32_t* __restrict__ block_
                                                    uint32_t* __restrict__ host_out, DrawCtl* __restrict__ ctl,
                                                    uint32_t bin_capacity) {
     __shared__ uint32_t sh[TPB / 32];
+    __shared__ unsigned long long wide;        // R in 64 bits: offsets are 32 bit, a draw beyond that must not wrap silently
+    if (threadIdx.x == 0) wide = 0ull;
+    __syncthreads();
     uint32_t carry = 0;
+    unsigned long long mine = 0;
     for (uint32_t base = 0; base < nblocks; base += TPB) {
         uint32_t e = base + threadIdx.x;
         uint32_t v = e < nblocks ? block_sum[e] : 0u, tot;
+        mine += v;
         uint32_t ex = block_exclusive_scan(v, sh, tot);
         if (e < nblocks) block_sum[e] = carry + ex;
         carry += tot;
     }
+    if (mine) atomicAdd(&wide, mine);
+    __syncthreads();
     if (threadIdx.x == 0) {
         ctl->total = carry;
-        ctl->overflow = carry > bin_capacity ? 1u : 0u;
-        host_out[0] = carry;
+        ctl->overflow = wide > (unsigned long long)bin_capacity ? 1u : 0u;   // also true when R does not fit 32 bits
+        host_out[0] = wide > 0xffffffffull ? 0xffffffffu : carry;
         host_out[1] = ctl->longest;
         host_out[2] = ctl->overflow;
     }

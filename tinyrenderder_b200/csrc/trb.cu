@@ -556,7 +556,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         const uint32_t R = c->host_total[0];
         if (R == 0) return TRB_OK;
         long_bins = c->host_total[1] > c->warp_max;
-        CU(c->bins.ensure((size_t)R * 4, c->stream));
+        if (!c->host_total[2]) CU(c->bins.ensure((size_t)R * 4, c->stream));   // overflow (R >= 2^32): the unbinned kernels draw it
     }
     {
         Launch L(c, "k_fill");
@@ -585,7 +585,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         Launch L(c, "k_raster");
         k_raster<<<grid, TPB, 0, c->stream>>>(f, ra);
     }
-    if (!c->sync_draws) {    // stand-ins for a draw that overflowed its bins (exit at once otherwise)
+    {                        // stand-ins for a draw that overflowed its bins or 32-bit offsets (exit at once otherwise)
         const dim3 grid((unsigned)std::min<unsigned>(blocks_for((unsigned long long)g.ntris * 32),
                                                     std::max(1u, 148u * 8 / (unsigned)f.nviews)), f.nviews);
         {
