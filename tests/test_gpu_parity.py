@@ -271,3 +271,25 @@ def test_pinned_uploads_and_block_recycling(cuda_api):
         for v in range(3):
             assert np.array_equal(got[k][1][v].view(np.uint64), want[k][v][0].view(np.uint64)), (k, v)
             assert np.array_equal(got[k][0][v], want[k][v][1]), (k, v)
+
+
+@pytest.fixture(scope="module")
+def checks_api(built):
+    p = os.path.join(os.path.dirname(HERE), "tinyrenderder_b200", "libtrb_checks.so")
+    if not os.path.exists(p):
+        pytest.skip("libtrb_checks.so not built")
+    return trb.Api(p, "trb")
+
+
+@pytest.mark.parametrize("env", [{}, {"TRB_WARP_MAX": "0"}, {"TRB_BIN_CAP": "16"}, {"TRB_SYNC_DRAWS": "1"}])
+@pytest.mark.parametrize("name", ["k7b_small", "big_triangles", "dense_tile", "soup_mesh_fp32", "orbit_small",
+                                  "snapshot_restore_twice", "shadow_small"])
+def test_kernels_hold_their_indexing_invariants(checks_api, port_api, monkeypatch, name, env):
+    """the -DTRB_DEBUG_CHECKS build asserts bin slots, shared-memory tile indices and sample decoding inside
+    the kernels (a failed assert traps the kernel and the next call reports the CUDA error); results must
+    still equal the oracle's.  compute-sanitizer is not available on the GPU pool."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run_case(checks_api, name)
+    want = run_case(port_api, name)
+    compare.assert_outputs_match(name, got, want)

@@ -215,3 +215,15 @@ def test_encode_tga_argument_errors(cuda_api):
         assert rc < 0
         rc = cuda_api.fn["encode_tga"](r.h, 7, C.cast(table, C.c_void_p), small.size, C.cast(sizes, C.c_void_p))
         assert rc < 0
+
+
+@pytest.mark.gpu
+def test_device_encoder_holds_its_packet_offset_invariants(built, port_api):
+    """same images through the -DTRB_DEBUG_CHECKS build: every pixel asserts that it writes inside its segment"""
+    import os
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tinyrenderder_b200", "libtrb_checks.so")
+    if not os.path.exists(p):
+        pytest.skip("libtrb_checks.so not built")
+    a, b = encode_with(trb.Api(p, "trb"), IMAGES), encode_with(port_api, IMAGES)
+    for name in IMAGES:
+        assert a[name] == b[name], name

@@ -13,7 +13,16 @@
 // All arithmetic is in exact.cuh; nothing here reorders a floating-point operation.
 #pragma once
 #include <cuda_runtime.h>
+#include <cassert>
 #include "exact.cuh"
+// -DTRB_DEBUG_CHECKS builds a variant whose kernels assert their own indexing invariants (bin slots,
+// shared-memory tile indices, packet offsets); tests/test_gpu_parity.py runs against it when
+// TRB_CUDA_LIB points at that build.  compute-sanitizer is not available on the GPU pool.
+#if defined(TRB_DEBUG_CHECKS)
+#define TRB_CHECK(cond) assert(cond)
+#else
+#define TRB_CHECK(cond) ((void)0)
+#endif
 #include "fastshade.cuh"
 
 namespace trbk {
@@ -568,12 +577,14 @@ __global__ void __launch_bounds__(TPB) k_fill(FrameDev f, uint32_t ntris, const 
         if ((unsigned)leader == lane) base = atomicAdd(cursor + vbase + key, (uint32_t)__popc(peers));
         base = __shfl_sync(peers, base, leader);
         uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        TRB_CHECK(offsets[vbase + key] + base + rank < ctl->total);
         bins[offsets[vbase + key] + base + rank] = t;
     } else if (has) {
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
                 size_t tile = vbase + (size_t)ty * f.tw + tx;
                 uint32_t slot = atomicAdd(cursor + tile, 1u);
+                TRB_CHECK(offsets[tile] + slot < ctl->total);
                 bins[offsets[tile] + slot] = t;
             }
     }
@@ -863,6 +874,7 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
     const TriRec* tr = a.trirec + (size_t)view * a.ntris;
 
     // first batch's bin entry: in flight while the tile is staged
+    TRB_CHECK((unsigned long long)off + n <= a.ctl->total);
     uint32_t t_next = lane < (int)n ? __ldg(a.bins + off + lane) : 0u;
     #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -878,6 +890,7 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
         uint32_t gid = 0, pack = 0, ns = 0;
         if (has) {
             const uint32_t t = t_next;
+            TRB_CHECK(t < a.ntris);
             const double2* q = reinterpret_cast<const double2*>(tr + t);
             const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
             if (base + 32 + lane < n) t_next = __ldg(a.bins + off + base + 32 + lane);
@@ -909,6 +922,7 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
             const int before = __popc(__ballot_sync(FULL, has && first < bs));
             const bool act = s < S;
             const int e = act ? before + __popc(starts & (FULL >> (31 - lane))) - 1 : 0;
+            TRB_CHECK(e >= 0 && e < 32 && (uint32_t)e < n - base);
             const uint32_t first_e = __shfl_sync(FULL, first, e);
             const uint32_t pk = __shfl_sync(FULL, pack, e);
             const uint32_t gid_e = __shfl_sync(FULL, gid, e);
@@ -919,6 +933,7 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
                 const uint32_t l = s - first_e, bw = ((pk >> 8) & 15u) + 1u;
                 const uint32_t row = (l * (pk >> 12)) >> 15;
                 const int lx = (int)((pk & 15u) + (l - row * bw)), ly = (int)(((pk >> 4) & 15u) + row);
+                TRB_CHECK(lx >= 0 && lx < TILE && ly >= 0 && ly < TILE && l - row * bw < bw);
                 const double2* q = reinterpret_cast<const double2*>(&sm.recs[e]);
                 const double2 r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3], r4 = q[4];
                 TriSetup ts;
@@ -1006,6 +1021,7 @@ __global__ void __launch_bounds__(TPB) k_unbinned(FrameDev f, uint32_t ntris, ui
         for (uint32_t s = lane; s < ns; s += 32) {
             const uint32_t row = s / bw;
             const int x = ts.x0 + (int)(s - row * bw), y = ts.y0 + (int)row;
+            TRB_CHECK(x >= 0 && x < f.W && y >= 0 && y < f.H);
             double b[3], z;
             if (!eval_sample(ts, x, y, b, z)) continue;
             const unsigned long long key = fragment_key(z);

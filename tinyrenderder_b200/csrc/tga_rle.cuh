@@ -24,6 +24,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cassert>
+#if defined(TRB_DEBUG_CHECKS)
+#define TRB_RLE_CHECK(cond) assert(cond)
+#else
+#define TRB_RLE_CHECK(cond) ((void)0)
+#endif
 
 namespace trbr {
 
@@ -244,17 +250,20 @@ __global__ void __launch_bounds__(RTPB) k_rle_emit(const uint8_t* __restrict__ p
     const SegInfo g = seg_info(s, e, nxt, t.long_end[k + 1] != nxt, t.prefix[k] & 1u);
     uint8_t* o = out + t.base[k];
     const uint32_t pi = (uint32_t)i;
+    TRB_RLE_CHECK(pi >= g.p0 && pi < g.r0 + g.nraw && t.base[k + 1] - t.base[k] == t.bytes[k]);
     if (pi < g.r0) {
         const uint32_t d = pi - g.p0;
         if (d & 127u) return;                                  // only the first pixel of a run packet is stored
         const uint32_t q = d >> 7, len = min(128u, g.rle_px - (q << 7));
         o += q * (1 + BPP);
+        TRB_RLE_CHECK(q < g.rle_packets && len >= 2u);
         o[0] = (uint8_t)(128u + len - 1u);
         #pragma unroll
         for (int c = 0; c < BPP; ++c) o[1 + c] = px[i * BPP + c];
     } else {
         const uint32_t d = pi - g.r0, q = d >> 7, w = d & 127u;
         o += g.rle_packets * (1 + BPP) + q * (1 + 128 * BPP) + 1 + w * BPP;
+        TRB_RLE_CHECK((size_t)(o + BPP - out) <= (size_t)t.base[k + 1]);
         if (w == 0) o[-1] = (uint8_t)(min(128u, g.nraw - (q << 7)) - 1u);
         #pragma unroll
         for (int c = 0; c < BPP; ++c) o[c] = px[i * BPP + c];
