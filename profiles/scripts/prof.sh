@@ -1,6 +1,8 @@
+# ncu recipe of profiles/r01_c3_v3_ncu.txt (config 3, 8 frames per step).  Matching launches per step:
+# setup(room) raster(room) setup(head) raster(head) shade(full) setup(eyes) raster(eyes) shade(eyes);
+# 8 in the diagnostics step + 7 in the visible-triangle pass are skipped, the warm-up step is captured.
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 1 --frames-per-step 8 --no-e2e --no-cpu-baseline"
 timeout 200 $CMD > gpurun_out/plain2.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_c3_v3.csv $CMD > gpurun_out/ncu_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_raster_warp|k_shade_dense|k_setup_count' -s 10 -c 4 -o gpurun_out/r01_c3_v3 $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_raster_warp|k_shade_dense|k_setup_count' -s 15 -c 5 -o gpurun_out/r01_c3_v3 $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
