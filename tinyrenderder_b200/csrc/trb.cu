@@ -706,7 +706,7 @@ int trb_create(int device, TrbCtx** out) {
         return TRB_E_CUDA;
     }
     memset(c->host_total, 0, 64);
-    // 8 CTAs x 24 KB of per-warp tiles per SM: ask for the large shared-memory carveout
+    // 9 CTAs x 24 KB of per-warp tiles per SM: ask for the large shared-memory carveout
     cudaFuncSetAttribute(k_raster_warp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = c;
     return TRB_OK;
