@@ -492,14 +492,15 @@ def main():
 
         def e2e_run(with_depth, resident=False):
             h2d = e2e_step(0, with_depth, resident)
-            e2e_step(1, with_depth, resident)                          # the block cache settles after two frames
+            e2e_step(1, with_depth, resident)                          # the block cache settles after two or three frames
+            e2e_step(2, with_depth, resident)
             for k in host_ms:
                 host_ms[k] = 0.0
             r.readback_wait()
             barrier()
             t0 = time.perf_counter()
             for s in range(e_steps):
-                e2e_step(2 + s, with_depth, resident)
+                e2e_step(3 + s, with_depth, resident)
             t_host = time.perf_counter() - t0                          # host time to enqueue the steps (nothing waited for)
             r.readback_wait()                                          # every host buffer is complete here
             barrier()

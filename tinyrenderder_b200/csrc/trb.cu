@@ -92,8 +92,11 @@ struct BlockCache {
     uint64_t frame = 0;                        // advanced by begin_batch
     size_t cached_bytes = 0;
     static constexpr size_t SOFT_LIMIT = (size_t)16 << 30;   // beyond this, wait for a busy block rather than grow
-    // *wait_for: event the consumer stream must wait on before writing the block (nullptr: none)
-    cudaError_t get(void** out, size_t bytes, cudaEvent_t* wait_for) {
+    // *wait_for: event the consumer stream must wait on before writing the block (nullptr: none).
+    // A new block comes from the stream-ordered allocator on the consumer stream: unlike cudaMalloc it
+    // does not wait for the device, so growing the second set in the middle of a frame loop costs a
+    // driver call, not a pipeline drain (measured: ~60 ms of stalls over the first steps with cudaMalloc).
+    cudaError_t get(void** out, size_t bytes, cudaEvent_t* wait_for, cudaStream_t consumer) {
         bytes = (bytes + 511) & ~(size_t)511;
         *wait_for = nullptr;
         int busy = -1;
@@ -114,6 +117,8 @@ struct BlockCache {
             take((size_t)busy);
             return cudaSuccess;
         }
+        if (cudaMallocAsync(out, bytes, consumer) == cudaSuccess) return cudaSuccess;
+        (void)cudaGetLastError();
         return cudaMalloc(out, bytes);
     }
     void take(size_t i) {
@@ -770,7 +775,7 @@ namespace {
 template <class Fill>
 int upload_block(TrbCtx* c, void** dev, size_t bytes, size_t granule, Fill fill) {
     cudaEvent_t wait_for = nullptr;
-    CU(c->cache.get(dev, bytes, &wait_for));
+    CU(c->cache.get(dev, bytes, &wait_for, c->upload_stream));
     if (wait_for) CU(cudaStreamWaitEvent(c->upload_stream, wait_for, 0));   // its last readers (render stream) first
     const size_t step = UploadRing::CHUNK / granule * granule;
     for (size_t off = 0; off < bytes; off += step) {
@@ -811,7 +816,7 @@ bool is_pinned(const void* p) {
 // device block filled by one DMA straight from pinned host memory
 int upload_pinned(TrbCtx* c, void** dev, const void* src, size_t bytes) {
     cudaEvent_t wait_for = nullptr;
-    CU(c->cache.get(dev, bytes, &wait_for));
+    CU(c->cache.get(dev, bytes, &wait_for, c->upload_stream));
     if (wait_for) CU(cudaStreamWaitEvent(c->upload_stream, wait_for, 0));
     CU(cudaMemcpyAsync(*dev, src, bytes, cudaMemcpyHostToDevice, c->upload_stream));
     return TRB_OK;
@@ -851,8 +856,8 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
         if (!rc && idx) rc = upload_pinned(c, (void**)&m.idx, idx, nidx * 4);
         if (rc) return rc;
         cudaEvent_t w0 = nullptr, w1 = nullptr;
-        CU(c->cache.get((void**)&m.pos4, (size_t)nverts * 16, &w0));
-        CU(c->cache.get((void**)&m.attr8, (size_t)nverts * 32, &w1));
+        CU(c->cache.get((void**)&m.pos4, (size_t)nverts * 16, &w0, c->upload_stream));
+        CU(c->cache.get((void**)&m.attr8, (size_t)nverts * 32, &w1, c->upload_stream));
         if (w0) CU(cudaStreamWaitEvent(c->upload_stream, w0, 0));
         if (w1) CU(cudaStreamWaitEvent(c->upload_stream, w1, 0));
         {
