@@ -1100,11 +1100,12 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
     const VRec* vr = D.vrec + (size_t)view * D.nverts;
     const VRec va = load_vrec(vr + i0), vb = load_vrec(vr + i1), vc = load_vrec(vr + i2);
     TriSetup ts;
-    setup_triangle(va, vb, vc, f.W, f.H, ts);
+    setup_known_triangle(va, vb, vc, ts);   // a recorded winner passed every reject: no tests, no bbox
     const uint32_t yq = (uint32_t)p / (uint32_t)f.W;     // p < 2^32: a frame has fewer than 2^32 pixels
     const int x = (int)((uint32_t)p - yq * (uint32_t)f.W), y = (int)yq;
     double b[3], z, pc[3];
-    if (eval_sample(ts, x, y, b, z)) {          // always true for a recorded winner
+    eval_known_sample(ts, x, y, b, z);          // a recorded winner is covered: same arithmetic, no coverage tests
+    {
         // exact bits of the reference's zbuffer[idx]: the stored key already is K(z) unless z is -0.0
         if (z == 0.0) f.zkey[gp] = depth_key(z);
         perspective_bary(b, va.iw, vb.iw, vc.iw, pc);
