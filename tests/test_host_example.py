@@ -181,3 +181,79 @@ int main() { TGAImage fb(8, 8, TGAImage::RGB); init_zbuffer(8, 8); Mine s; vec4 
                            "-Wl,-rpath," + os.path.join(ROOT, "tinyrenderder_b200"), "-o", exe])
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0 and "no CPU fallback" in res.stdout
+
+
+@pytest.mark.gpu
+def test_views_api_equals_frame_by_frame(assets, tmp_path, built):
+    """gl_begin_views / gl_draw_model_views (several cameras in one launch set, the C++ face of config 3)
+    give the frames the classic one-frame-at-a-time calls give, and gl_write_tga_files writes the same
+    files as TGAImage::write_tga_file on the read-back pixels"""
+    d, _ = assets
+    src = tmp_path / "views.cpp"
+    src.write_text(r'''#include <our_gl.h>
+#include <model.h>
+#include <model_manager.h>
+#include <shaders.h>
+#include <fstream>
+#include <iostream>
+static void dump(const std::string& name, const TGAImage& fb) {
+    std::ofstream c(name + ".bgr", std::ios::binary);
+    c.write((const char*)const_cast<TGAImage&>(fb).buffer(), (std::streamsize)fb.width() * fb.height() * 3);
+    std::ofstream z(name + ".z", std::ios::binary);
+    z.write((const char*)zbuffer.data(), (std::streamsize)zbuffer.size() * sizeof(double));
+}
+int main(int argc, char** argv) {
+    const std::string dir = argv[1], out = argv[2];
+    const int W = 320, H = 200;
+    auto head = ModelManager::getInstance().loadModel(dir + "/head.obj");
+    auto eyes = ModelManager::getInstance().loadModel(dir + "/eyes.obj");
+    if (!head || !eyes) return 2;
+    const vec3 key{1.0, 1.2, 1.0}, fill{-1.0, 0.3, 0.5}, rim{0.0, 0.8, -1.0}, center{0.0, 0.0, 0.0}, up{0.0, 1.0, 0.0};
+    const vec3 cams[3] = {vec3{1.0, 1.0, 3.0}, vec3{-2.0, 0.5, 2.5}, vec3{0.3, 2.2, 2.0}};
+    init_perspective(60.0, (double)W / H, 0.1, 100.0);
+    init_viewport(0, 0, W, H);
+    std::vector<mat<4, 4>> views;
+    for (int k = 0; k < 3; ++k) {                       // classic: one frame at a time
+        lookat(cams[k], center, up);
+        views.push_back(ModelView);
+        TGAImage fb(W, H, TGAImage::RGB);
+        init_zbuffer(W, H);
+        PhongShader sh(head.get());
+        sh.initLightDirections(key, fill, rim);
+        sh.normal_map_strength = 1.0;
+        gl_draw_model(*head, sh, fb);
+        EyeShader eye(eyes.get());
+        eye.initLightDirections(key, rim);
+        gl_draw_model(*eyes, eye, fb);
+        gl_flush(fb);
+        dump(out + "/single" + std::to_string(k), fb);
+        fb.write_tga_file(out + "/single" + std::to_string(k) + ".tga");
+    }
+    gl_begin_views(views, W, H);                        // the same three frames in one launch set
+    gl_draw_model_views(*head, 1, mat<4, 4>::identity(), key, fill, rim, 1.0);
+    gl_draw_model_views(*eyes, 2, mat<4, 4>::identity(), key, fill, rim, 1.0);
+    gl_write_tga_files(0, {out + "/batch0.tga", out + "/batch1.tga", out + "/batch2.tga"});
+    for (int k = 0; k < 3; ++k) {
+        TGAImage fb;
+        gl_read_view(k, fb);
+        dump(out + "/batch" + std::to_string(k), fb);
+    }
+    std::cout << "ok" << std::endl;
+    return 0;
+}
+''')
+    host = os.path.join(ROOT, "tinyrenderder_b200", "host")
+    exe = str(tmp_path / "views")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", host, str(src)] +
+                          [os.path.join(host, f) for f in ("our_gl.cpp", "model.cpp", "model_manager.cpp", "tgaimage.cpp")] +
+                          ["-L", os.path.join(ROOT, "tinyrenderder_b200"), "-ltrb",
+                           "-Wl,-rpath," + os.path.join(ROOT, "tinyrenderder_b200"), "-o", exe])
+    out = tmp_path / "views_out"
+    out.mkdir()
+    res = subprocess.run([exe, d, str(out)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    for k in range(3):
+        for ext in ("bgr", "z", "tga"):
+            a = open(out / ("single%d.%s" % (k, ext)), "rb").read()
+            b = open(out / ("batch%d.%s" % (k, ext)), "rb").read()
+            assert a == b, (k, ext)

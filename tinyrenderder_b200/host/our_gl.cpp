@@ -24,6 +24,7 @@ struct Backend {
     TrbCtx* ctx = nullptr;
     int w = 0, h = 0;
     bool frame = false;
+    std::vector<double> views;   // gl_begin_views: row-major view matrices of the batch (empty: single frame)
     // pending immediate-mode batch (consecutive rasterize() calls with the same shader state)
     std::vector<double> clip, vary;
     TrbDeviceShader key;
@@ -185,6 +186,7 @@ void init_zbuffer(int width, int height) {
     b.w = width;
     b.h = height;
     b.frame = true;
+    b.views.clear();
 }
 
 // ---- drawing -------------------------------------------------------------------------------------
@@ -305,10 +307,102 @@ void gl_composite_ao(TGAImage& final_result) {
     std::memcpy(final_result.buffer(), c.data(), c.size());
 }
 
+void gl_begin_views(const std::vector<mat<4, 4>>& views, int width, int height) {
+    if (views.empty()) throw std::runtime_error("tinyrenderder-b200: gl_begin_views needs at least one view");
+    Backend& b = B();
+    gl_context();
+    b.clip.clear();
+    b.vary.clear();
+    b.have_key = false;
+    zbuffer.assign((size_t)width * height, std::numeric_limits<double>::infinity());
+    CK(trb_begin_batch(b.ctx, width, height, (int)views.size()));
+    b.w = width;
+    b.h = height;
+    b.frame = true;
+    b.views.resize(views.size() * 16);
+    for (size_t v = 0; v < views.size(); ++v) flat(views[v], &b.views[v * 16]);
+}
+
+void gl_draw_model_views(const Model& model, int kind, const mat<4, 4>& model_matrix, const vec3& key_world,
+                         const vec3& fill_world, const vec3& rim_world, double normal_map_strength) {
+    require_frame();
+    Backend& b = B();
+    if (b.views.empty()) throw std::runtime_error("tinyrenderder-b200: gl_draw_model_views needs gl_begin_views");
+    if (kind != TRB_SHADER_PHONG && kind != TRB_SHADER_EYE)
+        throw std::runtime_error("tinyrenderder-b200: gl_draw_model_views draws PhongShader (1) or EyeShader (2)");
+    upload_model(model);
+    const int n = (int)(b.views.size() / 16);
+    double mm[16], pr[16], vp[16];
+    flat(model_matrix, mm);
+    flat(Perspective, pr);
+    flat(Viewport, vp);
+    std::vector<double> mvs((size_t)n * 16), prs((size_t)n * 16), dirs((size_t)n * 9);
+    trb_mat4_mul_batch(b.views.data(), n, mm, mvs.data());            // ModelView_i = view_i * model (main.cpp:653)
+    for (int v = 0; v < n; ++v) std::memcpy(&prs[(size_t)v * 16], pr, sizeof(pr));
+    const double kw[3] = {key_world.x, key_world.y, key_world.z}, fw[3] = {fill_world.x, fill_world.y, fill_world.z},
+                 rw[3] = {rim_world.x, rim_world.y, rim_world.z};
+    std::vector<double> ke((size_t)n * 3), fe((size_t)n * 3), re((size_t)n * 3);
+    trb_light_dir_eye_batch(mvs.data(), n, kw, ke.data());            // initLightDirections per view
+    trb_light_dir_eye_batch(mvs.data(), n, fw, fe.data());
+    trb_light_dir_eye_batch(mvs.data(), n, rw, re.data());
+    std::vector<TrbPhongUniforms> u((size_t)n);
+    for (int v = 0; v < n; ++v) {
+        std::memset(&u[v], 0, sizeof(TrbPhongUniforms));
+        for (int i = 0; i < 3; ++i) {
+            u[v].key_dir_eye[i] = ke[(size_t)v * 3 + i];
+            u[v].fill_dir_eye[i] = fe[(size_t)v * 3 + i];
+            u[v].rim_dir_eye[i] = re[(size_t)v * 3 + i];
+        }
+        u[v].normal_map_strength = normal_map_strength;
+        u[v].diffuse = model.dev_diffuse;
+        u[v].normal = model.dev_normal;
+        u[v].specular = model.dev_specular;
+    }
+    CK(trb_set_viewport(b.ctx, vp));
+    CK(trb_draw_batch(b.ctx, model.dev_mesh, mvs.data(), prs.data(), kind, u.data(), sizeof(TrbPhongUniforms), 0,
+                      (uint64_t)model.nfaces()));
+}
+
+void gl_read_view(int view, TGAImage& framebuffer) {
+    require_frame();
+    Backend& b = B();
+    const size_t n = (size_t)b.w * b.h;
+    framebuffer = TGAImage(b.w, b.h, TGAImage::RGB);
+    CK(trb_read_color(b.ctx, view, framebuffer.buffer()));
+    zbuffer.resize(n);
+    CK(trb_read_depth(b.ctx, view, zbuffer.data()));
+}
+
+bool gl_write_tga_files(int image, const std::vector<std::string>& filenames) {
+    require_frame();
+    Backend& b = B();
+    const size_t nv = b.views.empty() ? 1 : b.views.size() / 16;
+    if (filenames.size() != nv) throw std::runtime_error("tinyrenderder-b200: gl_write_tga_files needs one name per frame");
+    const size_t cap = (size_t)b.w * b.h * 3 + (size_t)b.w * b.h / 2 + 64;
+    std::vector<std::vector<uint8_t>> files(nv, std::vector<uint8_t>(cap));
+    std::vector<uint8_t*> out(nv);
+    std::vector<uint64_t> sizes(nv);
+    for (size_t v = 0; v < nv; ++v) out[v] = files[v].data();
+    CK(trb_encode_tga(b.ctx, image, out.data(), cap, sizes.data()));
+    bool ok = true;
+    for (size_t v = 0; v < nv; ++v) {
+        std::ofstream f(filenames[v], std::ios::binary);
+        if (!f.is_open()) {
+            std::cerr << "can't open " << filenames[v] << "\n";
+            ok = false;
+            continue;
+        }
+        f.write((const char*)files[v].data(), (std::streamsize)sizes[v]);
+        ok = ok && f.good();
+    }
+    return ok;
+}
+
 bool gl_write_tga_file(int image, const std::string& filename) {
     require_frame();
     submit_pending();
     Backend& b = B();
+    if (b.views.size() > 16) throw std::runtime_error("tinyrenderder-b200: a batch of frames is written with gl_write_tga_files");
     const size_t cap = (size_t)b.w * b.h * 3 + (size_t)b.w * b.h / 2 + 64;
     std::vector<uint8_t> file(cap);
     uint8_t* out[1] = {file.data()};

@@ -77,6 +77,20 @@ void gl_composite_ao(TGAImage& final_result);
 // without bringing the pixels to the host: the RLE packets of tgaimage.cpp:193-242 are built on the
 // device, only the file image crosses PCIe.  image: 0 framebuffer, 1 z-buffer grey map, 2 ssao, 3 final.
 bool gl_write_tga_file(int image, const std::string& filename);
+// ---- several cameras in one launch set (a camera orbit, config 3) ----------------------------------
+// gl_begin_views is init_zbuffer + the framebuffer clear for views.size() independent frames of one size.
+// Until the next init_zbuffer / gl_begin_views, gl_draw_model_views draws a model into every frame (the
+// per-face loop of main.cpp:652-666 with ModelView_i = views[i] * model_matrix and the WORLD-space light
+// directions taken to each view's eye space like PhongShader::initLightDirections, main.cpp:55-69), and
+// gl_zbuffer_snapshot / gl_zbuffer_restore act on all frames.  One launch set renders them all, which is
+// what lifts small frames out of the launch-bound regime.  kind: 1 = PhongShader, 2 = EyeShader.
+void gl_begin_views(const std::vector<mat<4, 4>>& views, int width, int height);
+void gl_draw_model_views(const Model& model, int kind, const mat<4, 4>& model_matrix, const vec3& key_world,
+                         const vec3& fill_world, const vec3& rim_world, double normal_map_strength);
+// colours of frame `view` into `framebuffer` (resized to the frame), its depths into the global zbuffer
+void gl_read_view(int view, TGAImage& framebuffer);
+// gl_write_tga_file for every frame of the batch: filenames[i] receives frame i
+bool gl_write_tga_files(int image, const std::vector<std::string>& filenames);
 struct TrbCtx;
 TrbCtx* gl_context();        // the process-wide device context (device = $TRB_DEVICE, default 0)
 
