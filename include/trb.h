@@ -141,6 +141,9 @@ TRB_EXPORT const char* TRB_FN(backend_name)(void); /* "cuda-sm100a", "oracle-ref
 TRB_EXPORT int TRB_FN(upload_mesh)(TrbCtx* ctx, const float* pos3, const float* nrm3,
                                    const float* uv2, uint32_t nverts, const uint32_t* idx,
                                    uint64_t nidx, TrbMesh* out);
+/* Lifetime: a mesh / texture may be freed at any time, also between a draw that uses it and the flush
+ * that shades it - free_* then resolves the pending draws first (an implicit trb_flush), so the
+ * deferred shade pass never reads a recycled block. */
 TRB_EXPORT int TRB_FN(free_mesh)(TrbCtx* ctx, TrbMesh mesh);
 /* texels: h rows of w texels of bpp (1,3,4) bytes in TGAImage memory order
  * ((x+y*w)*bpp, BGR(A), tgaimage.cpp:24-30); sampled nearest with trunc+clamp like

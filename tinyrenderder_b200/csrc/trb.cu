@@ -921,6 +921,9 @@ int trb_free_mesh(TrbCtx* c, TrbMesh h) {
     if (!c || h == 0 || h > c->meshes.size() || !c->meshes[h - 1].alive) return fail(c, TRB_E_ARG, "free_mesh");
     int rc = check_device(c);
     if (rc) return rc;
+    // an unflushed draw still points at this mesh (the deferred shade kernels read idx / attr8 at the next
+    // flush): shade first, so the event the block is tagged with covers its last reader
+    if (!c->draws.empty() && (rc = do_flush(c))) return rc;
     Mesh& m = c->meshes[h - 1];
     c->cache.put(m.pos4, (size_t)m.nverts * 16, c->stream);   // tagged: reusable once the kernels queued so far are done
     c->cache.put(m.attr8, (size_t)m.nverts * 32, c->stream);
@@ -960,6 +963,7 @@ int trb_free_texture(TrbCtx* c, TrbTex h) {
     if (!c || h == 0 || h > c->textures.size() || !c->textures[h - 1].alive) return fail(c, TRB_E_ARG, "free_texture");
     int rc = check_device(c);
     if (rc) return rc;
+    if (!c->draws.empty() && (rc = do_flush(c))) return rc;   // pending draws sample it at the next flush (see free_mesh)
     Tex& x = c->textures[h - 1];
     c->cache.put(x.px, (size_t)x.w * x.h * x.bpp, c->stream);
     x = Tex();
@@ -1030,7 +1034,10 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
     if (!mv || !pr) return fail(c, TRB_E_ARG, "draw: null matrix");
     if (mesh == 0 || mesh > c->meshes.size() || !c->meshes[mesh - 1].alive) return fail(c, TRB_E_ARG, "draw: bad mesh");
     const Mesh& m = c->meshes[mesh - 1];
-    if ((first_tri + ntris) * 3 > m.nidx) return fail(c, TRB_E_ARG, "draw: triangle range");
+    {   // no wrap-around: both values end up below the mesh's 0xFFFFFFF0 triangle limit
+        const uint64_t mt = m.nidx / 3;
+        if (first_tri > mt || ntris > mt - first_tri) return fail(c, TRB_E_ARG, "draw: triangle range");
+    }
     if (c->next_id + ntris >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "draw: triangle id space exhausted");
     int rc = check_device(c);
     if (rc) return rc;

@@ -5,6 +5,8 @@
 //                 the reference's own rasterize() on the CPU.  TEST INFRASTRUCTURE ONLY.
 // tests/test_host_example.py renders the same OBJ/TGA assets with both and compares the outputs.
 // usage: example <head.obj> <eyes.obj> <sponza.obj> <width> <height> <outdir> [--immediate]
+//                [--eye x y z] [--target x y z]   (camera of main.cpp:587-589 by default; other cameras
+//                exercise the model-level frustum cull of main.cpp:647, 680, 706)
 #include <our_gl.h>
 #include <model.h>
 #include <model_manager.h>
@@ -49,7 +51,11 @@ static void draw(const Model& model, Shader& shader, TGAImage& framebuffer) {
     for (int face = 0; face < model.nfaces(); ++face) {
         vec4 clip[3];
         for (int v = 0; v < 3; ++v) clip[v] = shader.vertex(face, v);
+#ifdef TRB_DEVICE_BACKEND
+        triangle(clip, shader, framebuffer, zbuffer);   // upstream spelling of rasterize() (our_gl.h aliases)
+#else
         rasterize(clip, shader, framebuffer);
+#endif
     }
 }
 
@@ -63,7 +69,13 @@ int main(int argc, char** argv) {
     if (argc < 7) { std::cerr << "usage: example head.obj eyes.obj sponza.obj W H outdir [--immediate]\n"; return 2; }
     const int WIDTH = atoi(argv[4]), HEIGHT = atoi(argv[5]);
     const std::string out = argv[6];
-    g_immediate = argc > 7 && !strcmp(argv[7], "--immediate");
+    double eye_p[3] = {-3.4019, 2.2001, 1.8026}, target_p[3] = {1.3555, 1.5116, -0.9686};       // main.cpp:587-589
+    for (int a = 7; a < argc; ++a) {
+        if (!strcmp(argv[a], "--immediate")) g_immediate = true;
+        else if (!strcmp(argv[a], "--eye") && a + 3 < argc) { for (int k = 0; k < 3; ++k) eye_p[k] = atof(argv[++a]); }
+        else if (!strcmp(argv[a], "--target") && a + 3 < argc) { for (int k = 0; k < 3; ++k) target_p[k] = atof(argv[++a]); }
+        else { std::cerr << "unknown argument " << argv[a] << "\n"; return 2; }
+    }
 
     auto& mm = ModelManager::getInstance();
     auto head_model = mm.loadModel(argv[1]);
@@ -77,9 +89,14 @@ int main(int argc, char** argv) {
 
     TGAImage framebuffer(WIDTH, HEIGHT, TGAImage::RGB);
     init_zbuffer(WIDTH, HEIGHT);                                                                   // main.cpp:606-612
-    lookat(make_vec3(-3.4019, 2.2001, 1.8026), make_vec3(1.3555, 1.5116, -0.9686), make_vec3(0, 1, 0));
+    lookat(make_vec3(eye_p[0], eye_p[1], eye_p[2]), make_vec3(target_p[0], target_p[1], target_p[2]), make_vec3(0, 1, 0));
+#ifdef TRB_DEVICE_BACKEND
+    projection(70.0, (double)WIDTH / HEIGHT, 0.05, 500.0);     // upstream spellings of init_perspective / init_viewport
+    viewport(0, 0, WIDTH, HEIGHT);
+#else
     init_perspective(70.0, (double)WIDTH / HEIGHT, 0.05, 500.0);
     init_viewport(0, 0, WIDTH, HEIGHT);
+#endif
     vec3 key = normalized(make_vec3(1.0, 1.4, 1.0)), fill = normalized(make_vec3(-0.3, 0.5, 0.2)),
          rim = normalized(make_vec3(-1.0, 0.8, -1.5));                                            // main.cpp:615-617
     Frustum frustum = Frustum::createFromMatrix(Perspective * ModelView);                          // main.cpp:623-624
@@ -157,6 +174,8 @@ int main(int argc, char** argv) {
     std::ofstream zf(out + "/zbuffer.bin", std::ios::binary);
     zf.write((const char*)zbuffer.data(), zbuffer.size() * sizeof(double));
     print_render_stats();                                                                          // main.cpp:792
+    // main.cpp:794-804: which models the (transposed-plane) frustum kept
+    std::cout << "frustum sponza " << frustum.intersects(sponzaBox) << " head " << frustum.intersects(headBox) << std::endl;
     std::cout << "models rendered " << rendered << " culled " << culled << " faces "
               << sponza_model->nfaces() + head_model->nfaces() + eye_model->nfaces() << std::endl;
     return 0;

@@ -22,6 +22,38 @@ Model::Model(const std::string& fn) : filename(fn) {
 }
 Model::~Model() { unload(); }
 
+Model::Model(const Model& o)
+    : vertices(o.vertices), indices(o.indices), materials(o.materials), filename(o.filename), directory(o.directory),
+      isLoaded(o.isLoaded), localAABB(o.localAABB) {}   // dev_* stay 0: the copy uploads its own buffers on first use
+Model& Model::operator=(const Model& o) {
+    if (this == &o) return *this;
+    unload();                                            // releases this model's device buffers
+    vertices = o.vertices; indices = o.indices; materials = o.materials;
+    filename = o.filename; directory = o.directory; isLoaded = o.isLoaded; localAABB = o.localAABB;
+    return *this;
+}
+Model::Model(Model&& o) noexcept
+    : dev_mesh(o.dev_mesh), dev_diffuse(o.dev_diffuse), dev_normal(o.dev_normal), dev_specular(o.dev_specular),
+      dev_uploaded(o.dev_uploaded), vertices(std::move(o.vertices)), indices(std::move(o.indices)),
+      materials(std::move(o.materials)), filename(std::move(o.filename)), directory(std::move(o.directory)),
+      isLoaded(o.isLoaded), localAABB(o.localAABB) {
+    o.dev_mesh = o.dev_diffuse = o.dev_normal = o.dev_specular = 0;
+    o.dev_uploaded = false;
+    o.isLoaded = false;
+}
+Model& Model::operator=(Model&& o) noexcept {
+    if (this == &o) return *this;
+    unload();
+    vertices = std::move(o.vertices); indices = std::move(o.indices); materials = std::move(o.materials);
+    filename = std::move(o.filename); directory = std::move(o.directory); isLoaded = o.isLoaded; localAABB = o.localAABB;
+    dev_mesh = o.dev_mesh; dev_diffuse = o.dev_diffuse; dev_normal = o.dev_normal; dev_specular = o.dev_specular;
+    dev_uploaded = o.dev_uploaded;
+    o.dev_mesh = o.dev_diffuse = o.dev_normal = o.dev_specular = 0;
+    o.dev_uploaded = false;
+    o.isLoaded = false;
+    return *this;
+}
+
 void Model::unload() {
 #ifdef TRB_DEVICE_BACKEND
     if (dev_uploaded) trb_host_release_model(*this);

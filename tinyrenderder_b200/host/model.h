@@ -32,6 +32,13 @@ class Model {
 public:
     explicit Model(const std::string& filename);
     ~Model();
+    // The reference's Model is a plain copyable value type, so ported code may copy it.  The host arrays are
+    // copied; the device handles are NOT shared (two owners would free them twice): a copy starts without
+    // device buffers and uploads its own on first use, a move takes them over.
+    Model(const Model& o);
+    Model& operator=(const Model& o);
+    Model(Model&& o) noexcept;
+    Model& operator=(Model&& o) noexcept;
     bool load();
     void unload();
 

@@ -29,6 +29,7 @@ struct Backend {
     std::vector<double> clip, vary;
     TrbDeviceShader key;
     double key_mv[16];
+    double key_vp[16];           // Viewport at the time the batch was opened: the reference applies it per rasterize() call
     bool have_key = false;
     std::vector<uint8_t> color_tmp;
     std::vector<uint32_t> vis_tmp;
@@ -113,9 +114,7 @@ void submit_pending() {
     if (b.clip.empty()) return;
     TrbPhongUniforms u;
     fill_uniforms(b.key, u);
-    double vp[16];
-    flat(Viewport, vp);
-    CK(trb_set_viewport(b.ctx, vp));
+    CK(trb_set_viewport(b.ctx, b.key_vp));   // the viewport the queued triangles were submitted under
     const bool lit = b.key.kind == TRB_SHADER_PHONG || b.key.kind == TRB_SHADER_EYE;
     CK(trb_submit_clip_triangles(b.ctx, b.clip.data(), lit ? b.vary.data() : nullptr, b.clip.size() / 12, b.key_mv,
                                  b.key.kind, lit ? &u : nullptr, lit ? sizeof(u) : 0));
@@ -124,8 +123,9 @@ void submit_pending() {
     b.have_key = false;
 }
 
-bool same_state(const TrbDeviceShader& a, const TrbDeviceShader& c, const double* mv_a, const double* mv_c) {
-    return a.kind == c.kind && a.model == c.model && a.normal_map_strength == c.normal_map_strength &&
+bool same_state(const TrbDeviceShader& a, const TrbDeviceShader& c, const double* mv_a, const double* mv_c,
+                const double* vp_a, const double* vp_c) {
+    return !std::memcmp(vp_a, vp_c, 128) && a.kind == c.kind && a.model == c.model && a.normal_map_strength == c.normal_map_strength &&
            !std::memcmp(a.key_dir_eye, c.key_dir_eye, 24) && !std::memcmp(a.fill_dir_eye, c.fill_dir_eye, 24) &&
            !std::memcmp(a.rim_dir_eye, c.rim_dir_eye, 24) && !std::memcmp(mv_a, mv_c, 128);
 }
@@ -198,18 +198,27 @@ void rasterize(const Triangle& clip, const IShader& shader, TGAImage& framebuffe
     if (!shader.device_shader(d))
         throw std::runtime_error("tinyrenderder-b200: rasterize() got a shader without a device implementation "
                                  "(IShader::device_shader); a GPU cannot call a host fragment() and there is no CPU fallback");
-    double mv[16];
+    double mv[16], vp[16];
     flat(ModelView, mv);
-    if (b.have_key && !same_state(b.key, d, b.key_mv, mv)) submit_pending();
+    flat(Viewport, vp);
+    if (b.have_key && !same_state(b.key, d, b.key_mv, mv, b.key_vp, vp)) submit_pending();
     if (!b.have_key) {
         b.key = d;
         std::memcpy(b.key_mv, mv, sizeof(mv));
+        std::memcpy(b.key_vp, vp, sizeof(vp));
         b.have_key = true;
     }
     for (int v = 0; v < 3; ++v)
         for (int k = 0; k < 4; ++k) b.clip.push_back(clip[v][k]);
     if (d.varyings) b.vary.insert(b.vary.end(), d.varyings, d.varyings + 24);
     else b.vary.insert(b.vary.end(), 24, 0.0);
+}
+
+void triangle(const Triangle& clip_verts, const IShader& shader, TGAImage& image, std::vector<double>& zbuffer_arg) {
+    if (&zbuffer_arg != &zbuffer)
+        throw std::runtime_error("tinyrenderder-b200: triangle() depth-tests against the device-resident z-buffer behind the "
+                                 "global `zbuffer`; pass that vector");
+    rasterize(clip_verts, shader, image);
 }
 
 void gl_draw_model(const Model& model, const IShader& shader, TGAImage& framebuffer) {
@@ -375,6 +384,7 @@ void gl_read_view(int view, TGAImage& framebuffer) {
 
 bool gl_write_tga_files(int image, const std::vector<std::string>& filenames) {
     require_frame();
+    submit_pending();           // triangles queued by rasterize() belong to the picture (as in gl_write_tga_file)
     Backend& b = B();
     const size_t nv = b.views.empty() ? 1 : b.views.size() / 16;
     if (filenames.size() != nv) throw std::runtime_error("tinyrenderder-b200: gl_write_tga_files needs one name per frame");

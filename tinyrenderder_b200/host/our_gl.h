@@ -61,6 +61,14 @@ typedef vec<4> Triangle[3];  // our_gl.h:55
 void rasterize(const Triangle& clip, const IShader& shader, TGAImage& framebuffer);
 void print_render_stats();   // our_gl.cpp:204-210 (order-independent counters, see trb.h TrbStats)
 
+// Upstream-tinyrenderer spellings of the same three entry points (BASELINE north_star names them; the fork
+// renamed them).  Thin aliases: same arguments as the fork's functions; the z-buffer the
+// backend tests against is the device-resident one behind the global `zbuffer`, so that is the only
+// vector triangle() accepts.
+inline void projection(double fov_deg, double aspect, double znear, double zfar) { init_perspective(fov_deg, aspect, znear, zfar); }
+inline void viewport(int x, int y, int w, int h) { init_viewport(x, y, w, h); }
+void triangle(const Triangle& clip_verts, const IShader& shader, TGAImage& image, std::vector<double>& zbuffer_arg);
+
 // ---- additions of the backend ---------------------------------------------------------------
 // for face in model: clip[v] = shader.vertex(face, v); rasterize(clip, shader, framebuffer)  -> one draw
 void gl_draw_model(const Model& model, const IShader& shader, TGAImage& framebuffer);

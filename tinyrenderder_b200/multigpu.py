@@ -68,7 +68,11 @@ class P2PComposite:
 
     def _open(self):
         planes = self.r.device_planes()[:2]
-        if planes == self.key:
+        # whether to re-exchange handles is decided COLLECTIVELY: a rank whose planes were reallocated
+        # (DevBuf growth, depth restore by pointer swap) must not enter the all-gather alone
+        changed = [None] * self.world
+        self.dist.all_gather_object(changed, planes != self.key)
+        if not any(changed):
             return
         mine = self.r.ipc_export_planes()
         every = [None] * self.world
