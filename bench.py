@@ -43,6 +43,11 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tga", action="store_true", help="also time trb_encode_tga (device RLE packetiser) on one step's frames")
+    ap.add_argument("--no-also", action="store_true", help="c3 only: skip the short config-4 / config-5 runs appended as \"also\"")
+    ap.add_argument("--also-steps", type=int, default=5)
+    ap.add_argument("--no-exact-shade", action="store_true", help="skip the TRB_SHADE_EXACT=1 (all-fp64 lighting) timing")
+    ap.add_argument("--parity-dump", default="", help="reference arm: directory that receives z / bgr of --parity-frames")
+    ap.add_argument("--parity-frames", default="", help="reference arm: comma-separated c3 frame indices to dump")
     return ap.parse_args()
 
 
@@ -223,6 +228,16 @@ def _ref_worker_frame(job):
     return ntri, r.stats()["fragments_covered"] if api.backend_name() == "oracle-port" else 0, dt
 
 
+def _ref_worker_dump(job):
+    """parity material for the GPU arm: the reference's z-buffer and framebuffer of one orbit frame"""
+    k, out_dir = job
+    wl, api, up, r = _W["wl"], _W["api"], _W["up"], _W["r"]
+    wl.render(up, wl.scenes.orbit_views(api, [k]) if wl.name == "c3" else wl.views(api, 0, 0, 1))
+    np.save(os.path.join(out_dir, "z_%d.npy" % k), r.read_depth(0))
+    np.save(os.path.join(out_dir, "bgr_%d.npy" % k), r.read_color(0))
+    return k
+
+
 def oracle_library():
     ref = os.path.join(ROOT, "oracle", "_ref", "libtrb_ref.so")
     if os.path.exists(ref):
@@ -264,6 +279,9 @@ def run_reference(args, steps, warmup):
                 times.append(dt)
                 tris_total += sum(r[0] for r in res)
             tris_per_frame = res[0][0]
+        if args.parity_dump and args.parity_frames and args.workload in ("c1", "c2", "c3"):
+            os.makedirs(args.parity_dump, exist_ok=True)
+            pool.map(_ref_worker_dump, [(int(k), args.parity_dump) for k in args.parity_frames.split(",")])
     finally:
         pool.close()
         pool.join()
@@ -288,6 +306,402 @@ def bind_to_gpu_numa_node(index):
         return len(cpus)
     except Exception:
         return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# parity of what was just timed
+# ---------------------------------------------------------------------------------------------
+GOLDEN_FULLSIZE = os.path.join(ROOT, "tests", "golden", "golden_fullsize.json")
+
+
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def parity_check(wl, r, frames, env, sharded_rows=None):
+    """Compare the frames the timed region left in the context with the reference's own output: SHA-256 digests
+    of the z-buffers (tests/golden/golden_fullsize.json, made by oracle/_ref = the reference's rasterize() compiled
+    from /root/reference; every one of the 1024 orbit frames, the config-4 sphere, the config-5 soup).  The colour
+    of the lit config-3 frames is compared later with the frames the cpu_baseline run renders (returns them)."""
+    torch, dist, rank, world = env["torch"], env["dist"], env["rank"], env["world"]
+    try:
+        gold = json.load(open(GOLDEN_FULLSIZE))
+    except Exception as e:
+        return {"frames": 0, "depth": "unchecked: %r" % (e,)}, {}
+    out = {"source": "tests/golden/golden_fullsize.json (digests of the reference's own rasterize() output)"}
+    kept = {}
+    if wl.name == "c3":
+        g = gold.get("c3_orbit", {})
+        if g.get("workload") != wl.label.split("_x")[0]:
+            return {"frames": 0, "depth": "unchecked: no golden for %s" % wl.label}, {}
+        ok = 0
+        for v, k in enumerate(frames):
+            ok += 1 if _sha(r.read_depth(v)) == g["z_sha256"][k] else 0
+        for v in sorted({0, len(frames) - 1}):
+            kept[frames[v]] = r.read_color(v).copy()
+        t = torch.tensor([ok, len(frames)], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        ok, n = int(t[0].item()), int(t[1].item())
+        out.update(frames=n, depth="bit-exact" if ok == n else "MISMATCH in %d of %d frames" % (n - ok, n),
+                   frame_indices_rank0=[frames[0], frames[-1]])
+        return out, kept
+    key = {"c4": "c4_sphere", "c5": "c5_soup"}.get(wl.name)
+    g = gold.get(key or "", {})
+    if not g or g.get("workload") != wl.label:
+        return {"frames": 0, "depth": "unchecked: no golden for %s" % wl.label}, {}
+    z, c = r.read_depth(0), r.read_color(0)
+    if sharded_rows is not None:    # sort-last composite: every rank owns rows [y0, y1) of the picture
+        y0, y1 = sharded_rows
+        parts = [None] * world
+        dist.all_gather_object(parts, (y0, z[y0:y1].copy(), c[y0:y1].copy()))
+        for py0, pz, pc in parts:
+            z[py0:py0 + pz.shape[0]] = pz
+            c[py0:py0 + pc.shape[0]] = pc
+    zs, cs = _sha(z) == g["z_sha256"], _sha(c) == g["bgr_sha256"]
+    out.update(frames=1, depth="bit-exact" if zs else "MISMATCH", colour="bit-exact (flat shader)" if cs else "MISMATCH",
+               pixels_shaded=int(np.isfinite(z).sum()))
+    if sharded_rows is not None:
+        out["note"] = "composited picture of all ranks compared with the UNSHARDED reference render"
+    return out, {}
+
+
+# ---------------------------------------------------------------------------------------------
+# one workload: diagnostics, warm-up, timed region, parity, roofline (and for the primary one e2e + cpu baseline)
+# ---------------------------------------------------------------------------------------------
+def measure(args, env, workload, steps, warmup, primary, composite="p2p"):
+    import tinyrenderder_b200 as trb
+    from tinyrenderder_b200 import multigpu
+    torch, dist, rank, world, local_rank, api = (env[k] for k in ("torch", "dist", "rank", "world", "local_rank", "api"))
+    wargs = argparse.Namespace(**dict(vars(args), workload=workload))
+    r = trb.Renderer(api, local_rank)
+    wl = Workload(wargs, api)
+    up = wl.scenes.UploadedScene(r, wl.scene)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sharded_c4 = wl.name == "c4" and world > 1
+    p2p = multigpu.P2PComposite(r, dist, rank, world) if sharded_c4 and composite == "p2p" else None
+    rows = multigpu.row_shard(wl.height, rank, world) if sharded_c4 else None
+
+    def frames_of(s):
+        if wl.name != "c3":
+            return [0]
+        first = ((s * world) + rank) * wl.frames
+        return [(first + j) % 1024 for j in range(wl.frames)]
+
+    def step(s):
+        if not sharded_c4:
+            wl.render(up, wl.views(api, s, rank, world))
+            return
+        # config 4 on N GPUs: triangle range per rank, sort-last composite, shade own rows
+        it = wl.scene.items[0]
+        first, count = multigpu.triangle_shard(it.mesh.ntris, rank, world)
+        r.begin_frame(wl.width, wl.height)
+        r.set_triangle_id_base(first)
+        mv = api.mat4_mul(wl.views(api, s, rank, world)[0], it.model_matrix)
+        r.draw(up.mesh_h[id(it.mesh)], mv, wl.perspective, kind=it.kind, first_tri=first, ntris=count)
+        if composite == "p2p":
+            p2p.run(wl.height)            # fused NVLink composite + shade of the owned rows
+        else:
+            multigpu.composite(r, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MIN))
+            r.set_shade_rows(*rows)
+            r.end_frame()
+
+    # ---- diagnostics pass (untimed): counters for the algorithmic-bytes formula ---------------------
+    step(0)
+    nviews = wl.frames
+    R = sum(r.stats(v)["tile_entries"] for v in range(nviews))
+    C = sum(r.stats(v)["pixels_shaded"] for v in range(nviews))
+    frag = sum(r.stats(v)["fragments_covered"] for v in range(nviews))
+    # distinct winning triangles: re-draw view 0 without the flush and look at the id plane
+    views0 = wl.views(api, 0, rank, world)[:1]
+    r.begin_frame(wl.width, wl.height)
+    for it in wl.scene.items:
+        mv = api.mat4_mul(views0[0], it.model_matrix)
+        r.draw(up.mesh_h[id(it.mesh)], mv, wl.perspective, kind=0, ntris=it.mesh.ntris)
+    vis = r.read_visibility(0)
+    tvis = int(np.unique(vis[(vis != 0xFFFFFFFF) & (vis != 0)]).size) * nviews
+    del vis
+    r.end_frame()
+    V = sum(it.mesh.nverts for it in wl.scene.items)
+    T = wl.tris_per_frame
+    P = wl.width * wl.height
+    balg = algorithmic_bytes(V * nviews, T * nviews, P * nviews, R, tvis, C)
+
+    # ---- warm-up + timed region -----------------------------------------------------------------------
+    for s in range(warmup):
+        step(s)
+    # the same K steps once without the per-kernel events (reported as ms_per_step_unprofiled: what a
+    # caller sees), then the timed region proper with every launch bracketed by CUDA events
+    barrier()
+    r.timer_start()
+    for s in range(steps):
+        step(warmup + s)
+    ms_unprofiled = r.timer_stop_ms()
+    barrier()
+    r.profile_enable(True)
+    r.profile_read(reset=True)
+    launches0 = r.launch_count()
+    clocks = ClockSampler(local_rank) if primary else None
+    if clocks:
+        clocks.start()
+        time.sleep(0.2)
+    barrier()
+    if clocks:
+        clocks.mark()
+    r.timer_start()
+    t_wall0 = time.perf_counter()
+    for s in range(steps):
+        step(warmup + s)
+    ms = r.timer_stop_ms()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop() if clocks else None
+    prof = r.profile_read(reset=True)
+    r.profile_enable(False)
+    launches = r.launch_count() - launches0
+    t = torch.tensor([ms, ms_unprofiled], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, ms_unprofiled = float(t[0].item()), float(t[1].item())
+
+    tris_step_all = T * nviews * (1 if sharded_c4 else world)
+    value = tris_step_all * steps / (ms_max * 1e-3)
+
+    # ---- parity of the frames the timed region just produced (still resident in the context) -------------
+    last_frames = frames_of(warmup + steps - 1)
+    parity, kept_colour = parity_check(wl, r, last_frames, env, rows)
+
+    # ---- all-fp64 lighting (TRB_SHADE_EXACT=1) timed beside the default fp32 lighting --------------------
+    exact = None
+    if primary and not args.no_exact_shade and not sharded_c4 and wl.name in ("c1", "c2", "c3"):
+        os.environ["TRB_SHADE_EXACT"] = "1"
+        try:
+            with trb.Renderer(api, local_rank) as r2:
+                up2 = wl.scenes.UploadedScene(r2, wl.scene)
+                for s in range(2):
+                    wl.render(up2, wl.views(api, s, rank, world))
+                torch.cuda.synchronize()
+                r2.timer_start()
+                k2 = max(1, min(steps, 5))
+                for s in range(k2):
+                    wl.render(up2, wl.views(api, warmup + s, rank, world))
+                exact = {"ms_per_step": r2.timer_stop_ms() / k2, "steps": k2,
+                         "note": "same steps with PhongShader / EyeShader evaluated in fp64 in the reference's operation order"}
+        finally:
+            del os.environ["TRB_SHADE_EXACT"]
+
+    tga = None
+    if primary and args.tga and not sharded_c4:
+        step(0)
+        r.profile_enable(True)
+        r.profile_read(reset=True)
+        t0 = time.perf_counter()
+        files = r.encode_tga(0)                                        # framebuffer.tga of every frame, main.cpp:743
+        dt = time.perf_counter() - t0
+        kt = r.profile_read(reset=True)
+        r.profile_enable(False)
+        tga = {"frames": len(files), "bytes": sum(len(f) for f in files), "raw_bytes": nviews * P * 3,
+               "wall_ms": 1e3 * dt, "device_ms": sum(m for k, (n, m) in kt.items() if k.startswith("k_rle")),
+               "note": "device-side packetiser of tgaimage.cpp:193-242 + D2H of the packets, one blocking call"}
+
+    # ---- end-to-end: host buffers in, host buffers out, every step --------------------------------------
+    e2e = None
+    if primary and not args.no_e2e and not sharded_c4:
+        e2e = measure_e2e(args, env, wl, r, steps, tris_step_all, nviews, P, barrier)
+
+    if world > 1:
+        barrier()
+    r.close()
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    kern = {k: {"launches": int(n), "ms": float(m)} for k, (n, m) in prof.items()}
+    total_k_ms = sum(v["ms"] for v in kern.values()) or 1.0
+    dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+    roof = None
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tr_path):
+        try:
+            traffic = json.load(open(tr_path)).get(wl.name, {}).get(dom)
+        except Exception:
+            traffic = None
+    if dom:
+        per_launch_ms = kern[dom]["ms"] / kern[dom]["launches"]
+        # launches of the dominant kernel per step (one per draw call) share the step's algorithmic bytes
+        bytes_per_launch = balg.get(PASS_OF.get(dom, dom), 0) * steps / kern[dom]["launches"]
+        achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/ncu_traffic.json: dram bytes of one separate `ncu --set full` capture of this "
+                                  "kernel, scaled to this launch size (not measured in this run)" if traffic else None,
+                "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
+                "share_of_kernel_time": kern[dom]["ms"] / total_k_ms}
+    step_bytes = sum(balg.values())
+    step_gbs = step_bytes * steps / (ms_max * 1e-3) / 1e9
+
+    cpu = None
+    if primary and world == 1 and not args.no_cpu_baseline:
+        import shutil
+        import tempfile
+        dump = tempfile.mkdtemp(prefix="trb_parity_")
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+                   "--steps", "2", "--warmup", "0", "--c4-level", str(args.c4_level), "--c5-tris", str(args.c5_tris)]
+            if kept_colour:
+                cmd += ["--parity-dump", dump, "--parity-frames", ",".join(str(k) for k in sorted(kept_colour))]
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            ref_line = json.loads(out.stdout.strip().splitlines()[-1])
+            cpu = ref_line["cpu_baseline"]
+            # colour (and once more depth) of the frames both arms rendered: GPU frames kept from the timed step
+            fr, zok = [], True
+            for k, bgr in sorted(kept_colour.items()):
+                want = np.load(os.path.join(dump, "bgr_%d.npy" % k))
+                d = np.abs(bgr.astype(np.int32) - want.astype(np.int32)).max(axis=-1)
+                fr.append(float((d <= 1).mean()))
+                zok &= _sha(np.load(os.path.join(dump, "z_%d.npy" % k))) == json.load(open(GOLDEN_FULLSIZE))["c3_orbit"]["z_sha256"][k]
+            if fr:
+                parity["colour_within_1lsb"] = min(fr)
+                parity["colour_frames"] = sorted(kept_colour)
+                parity["colour_vs"] = "the same frames rendered by the cpu_baseline run (%s); its z-buffers %s the committed digests" % (
+                    cpu.get("kind"), "match" if zok else "DO NOT match")
+        except Exception as e:  # the baseline is a reported figure; never let it sink the GPU line
+            cpu = {"value": None, "unit": "triangles/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        finally:
+            shutil.rmtree(dump, ignore_errors=True)
+    if wl.name == "c3":
+        parity.setdefault("colour_within_1lsb", None)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "triangles/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
+        "scaling": "strong" if sharded_c4 else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "precision": "coverage, depth, barycentrics, texture coordinates and texel choice in f64 (bit-exact); "
+                     "lighting of the lit shaders in f32 (within 1 LSB, asserted by tests and parity_check)",
+        "config": {"workload": wl.label, "frames_per_step_per_gpu": nviews, "width": wl.width, "height": wl.height,
+                   "triangles_per_frame": T, "l2": "inputs larger than L2 (depth+id+colour planes of one step = %d MB)"
+                   % (nviews * P * 15 // 2 ** 20), "parallelism": ("triangle ranges + %s sort-last composite" % ("fused NVLink P2P" if composite == "p2p" else "NCCL")
+                                   if sharded_c4 else
+                                   "frames sharded, no collective") if world > 1 else "1 GPU"},
+        "fragments_per_s": frag * (1 if sharded_c4 else world) * steps / (ms_max * 1e-3),
+        "pixels_shaded_per_s": C * (1 if sharded_c4 else world) * steps / (ms_max * 1e-3),
+        "frame_ms": ms_max / steps / nviews,
+        "frames_per_s": nviews * (1 if sharded_c4 else world) * steps / (ms_max * 1e-3),
+        "parity_check": parity,
+        "roofline": roof,
+        "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / peak,
+                          "counters": {"V": V * nviews, "T": T * nviews, "P": P * nviews, "R": R, "T_vis": tvis, "C": C}},
+        "kernels": kern,
+        "gpu_launches": launches,
+        "ms_per_step_unprofiled": ms_unprofiled / steps,
+    }
+    if primary:
+        line.update({"cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "wall_ms_per_step": 1e3 * t_wall / steps,
+                     "shade_exact_f64": exact, "tga_encode": tga, "cpu_affinity_cores": env["numa"]})
+    return line
+
+
+def measure_e2e(args, env, wl, r, steps, tris_step_all, nviews, P, barrier):
+    """The same metric through the C ABI with HOST buffers: every step uploads its inputs from pinned host memory
+    and reads its frames back into pinned host memory (copies inside the timed region)."""
+    torch, dist, rank, world, api = (env[k] for k in ("torch", "dist", "rank", "world", "api"))
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+    # two sets of pinned host buffers: the read-back of step s overlaps the rendering of step s+1
+    color_host = [[pin((wl.height, wl.width, 3), torch.uint8) for _ in range(nviews)] for _ in range(2)]
+    depth_host = [[pin((wl.height, wl.width), torch.float64) for _ in range(nviews)] for _ in range(2)]
+    e_steps = max(1, min(steps, 1 if wl.name == "c5" else (3 if wl.name == "c4" else steps)))
+    host_ms = {"upload": 0.0, "render": 0.0, "readback": 0.0, "free": 0.0}
+
+    def pinned(a):
+        if a is None:
+            return None
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    pinned_tex = {}
+    # the step's inputs live in pinned host memory (the contract's H2D source): meshes and textures
+    for it in wl.scene.items:
+        m = it.mesh
+        if not getattr(m, "_pinned", False):
+            m.pos, m.nrm, m.uv, m.idx = pinned(m.pos), pinned(m.nrm), pinned(m.uv), pinned(m.idx)
+            m._pinned = True
+        for k in list(it.textures):
+            t = it.textures[k]
+            if id(t) not in pinned_tex:              # maps shared between models stay shared
+                p = pinned(t)
+                pinned_tex[id(t)] = p
+                pinned_tex[id(p)] = p
+            it.textures[k] = pinned_tex[id(t)]
+    up_resident = wl.scenes.UploadedScene(r, wl.scene)
+    per_step_uniform_bytes = nviews * sum(32 * 8 + (104 if it.kind in (1, 2) else 0) for it in wl.scene.items)
+
+    def e2e_step(s, with_depth, resident=False):
+        t = [time.perf_counter()]
+        if resident:   # meshes and textures uploaded once (north_star); per step only matrices and uniforms go up
+            wl.render(up_resident, wl.views(api, s, rank, world))
+            r.readback_async(color_host[s & 1], depth_host[s & 1] if with_depth else None)
+            return per_step_uniform_bytes
+        up2 = wl.scenes.UploadedScene(r, wl.scene)                 # H2D: meshes + textures
+        t.append(time.perf_counter())
+        wl.render(up2, wl.views(api, s, rank, world))              # H2D: matrices, uniforms
+        t.append(time.perf_counter())
+        # D2H: the BGR framebuffer of every frame (what the reference writes out, main.cpp:743);
+        # with_depth also brings back the f64 z-buffer the reference keeps in a host global
+        r.readback_async(color_host[s & 1], depth_host[s & 1] if with_depth else None)
+        t.append(time.perf_counter())
+        up2.free()
+        t.append(time.perf_counter())
+        for k, a, b in zip(("upload", "render", "readback", "free"), t[:-1], t[1:]):
+            host_ms[k] += 1e3 * (b - a)
+        return up2.h2d_bytes
+
+    def e2e_run(with_depth, resident=False):
+        h2d = e2e_step(0, with_depth, resident)
+        e2e_step(1, with_depth, resident)                          # the block cache settles after two or three frames
+        e2e_step(2, with_depth, resident)
+        for k in host_ms:
+            host_ms[k] = 0.0
+        r.readback_wait()
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(e_steps):
+            e2e_step(3 + s, with_depth, resident)
+        t_host = time.perf_counter() - t0                          # host time to enqueue the steps (nothing waited for)
+        r.readback_wait()                                          # every host buffer is complete here
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"value": tris_step_all * e_steps / float(t.item()), "unit": "triangles/s",
+                "h2d_bytes_per_step": int(h2d + (0 if resident else per_step_uniform_bytes)),
+                "d2h_bytes_per_step": int(nviews * P * (3 + (8 if with_depth else 0))),
+                "steps": e_steps, "ms_per_step": 1e3 * float(t.item()) / e_steps,
+                "host_enqueue_ms_per_step": 1e3 * t_host / e_steps,
+                "host_ms_per_step": {k: v / e_steps for k, v in host_ms.items()}}
+
+    e2e = e2e_run(False)
+    e2e["note"] = ("per step: upload meshes+textures, render, read back the BGR framebuffer of every frame into pinned "
+                   "host memory; the z-buffer stays in HBM for the device-side post passes")
+    e2e["with_depth_readback"] = e2e_run(True)   # same, plus the f64 z-buffer of every frame (PCIe bound)
+    # the deployment north_star describes: meshes / textures go to HBM once, a step uploads matrices and uniforms only
+    e2e["scene_resident"] = e2e_run(False, resident=True)
+    e2e["scene_resident"].pop("host_ms_per_step", None)
+    e2e["per_gpu_value"] = e2e["value"] / world
+    return e2e
 
 
 # ---------------------------------------------------------------------------------------------
@@ -329,274 +743,28 @@ def main():
     numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    api = trb.load_cuda()
-    r = trb.Renderer(api, local_rank)
-    wl = Workload(args, api)
-    up = wl.scenes.UploadedScene(r, wl.scene)
+    env = {"torch": torch, "dist": dist, "rank": rank, "world": world, "local_rank": local_rank, "api": trb.load_cuda(),
+           "numa": numa}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    from tinyrenderder_b200 import multigpu
-    sharded_c4 = wl.name == "c4" and world > 1
-    p2p = multigpu.P2PComposite(r, dist, rank, world) if sharded_c4 and args.composite == "p2p" else None
-
-    def step(s):
-        if not sharded_c4:
-            wl.render(up, wl.views(api, s, rank, world))
-            return
-        # config 4 on N GPUs: triangle range per rank, sort-last composite over NCCL, shade own rows
-        it = wl.scene.items[0]
-        first, count = multigpu.triangle_shard(it.mesh.ntris, rank, world)
-        r.begin_frame(wl.width, wl.height)
-        r.set_triangle_id_base(first)
-        mv = api.mat4_mul(wl.views(api, s, rank, world)[0], it.model_matrix)
-        r.draw(up.mesh_h[id(it.mesh)], mv, wl.perspective, kind=it.kind, first_tri=first, ntris=count)
-        if args.composite == "p2p":
-            p2p.run(wl.height)            # fused NVLink composite + shade of the owned rows
-        else:
-            multigpu.composite(r, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MIN))
-            y0, y1 = multigpu.row_shard(wl.height, rank, world)
-            r.set_shade_rows(y0, y1)
-            r.end_frame()
-
-    # ---- diagnostics pass (untimed): counters for the algorithmic-bytes formula ---------------------
-    step(0)
-    st = r.stats(0)
-    nviews = wl.frames
-    R = sum(r.stats(v)["tile_entries"] for v in range(nviews))
-    C = sum(r.stats(v)["pixels_shaded"] for v in range(nviews))
-    frag = sum(r.stats(v)["fragments_covered"] for v in range(nviews))
-    # distinct winning triangles: re-draw view 0 without the flush and look at the id plane
-    views0 = wl.views(api, 0, rank, world)[:1]
-    r.begin_frame(wl.width, wl.height)
-    tvis = 0
-    for it in wl.scene.items:
-        mv = api.mat4_mul(views0[0], it.model_matrix)
-        r.draw(up.mesh_h[id(it.mesh)], mv, wl.perspective, kind=0, ntris=it.mesh.ntris)
-    vis = r.read_visibility(0)
-    tvis = int(np.unique(vis[(vis != 0xFFFFFFFF) & (vis != 0)]).size) * nviews
-    r.end_frame()
-    V = sum(it.mesh.nverts for it in wl.scene.items)
-    T = wl.tris_per_frame
-    P = wl.width * wl.height
-    balg = algorithmic_bytes(V * nviews, T * nviews, P * nviews, R, tvis, C)
-
-    # ---- warm-up + timed region -----------------------------------------------------------------------
-    for s in range(args.warmup):
-        step(s)
-    # the same K steps once without the per-kernel events (reported as ms_per_step_unprofiled: what a
-    # caller sees), then the timed region proper with every launch bracketed by CUDA events
-    barrier()
-    r.timer_start()
-    for s in range(args.steps):
-        step(args.warmup + s)
-    ms_unprofiled = r.timer_stop_ms()
-    barrier()
-    r.profile_enable(True)
-    r.profile_read(reset=True)
-    launches0 = r.launch_count()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    time.sleep(0.2)
-    barrier()
-    clocks.mark()
-    r.timer_start()
-    t_wall0 = time.perf_counter()
-    for s in range(args.steps):
-        step(args.warmup + s)
-    ms = r.timer_stop_ms()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop()
-    prof = r.profile_read(reset=True)
-    r.profile_enable(False)
-    launches = r.launch_count() - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-
-    tris_step_all = T * nviews * (1 if sharded_c4 else world)
-    value = tris_step_all * args.steps / (ms_max * 1e-3)
-
-    tga = None
-    if args.tga and not sharded_c4:
-        step(0)
-        r.profile_enable(True)
-        r.profile_read(reset=True)
-        t0 = time.perf_counter()
-        files = r.encode_tga(0)                                        # framebuffer.tga of every frame, main.cpp:743
-        dt = time.perf_counter() - t0
-        kt = r.profile_read(reset=True)
-        r.profile_enable(False)
-        tga = {"frames": len(files), "bytes": sum(len(f) for f in files), "raw_bytes": nviews * P * 3,
-               "wall_ms": 1e3 * dt, "device_ms": sum(m for k, (n, m) in kt.items() if k.startswith("k_rle")),
-               "note": "device-side packetiser of tgaimage.cpp:193-242 + D2H of the packets, one blocking call"}
-
-    # ---- end-to-end: host buffers in, host buffers out, every step --------------------------------------
-    e2e = None
-    if not args.no_e2e and not sharded_c4:
-        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
-        # two sets of pinned host buffers: the read-back of step s overlaps the rendering of step s+1
-        color_host = [[pin((wl.height, wl.width, 3), torch.uint8) for _ in range(nviews)] for _ in range(2)]
-        depth_host = [[pin((wl.height, wl.width), torch.float64) for _ in range(nviews)] for _ in range(2)]
-        e_steps = max(1, min(args.steps, 1 if wl.name == "c5" else (3 if wl.name == "c4" else args.steps)))
-
-        host_ms = {"upload": 0.0, "render": 0.0, "readback": 0.0, "free": 0.0}
-
-        def pinned(a):
-            if a is None:
-                return None
-            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-            return t.numpy()
-
-        pinned_tex = {}
-        # the step's inputs live in pinned host memory (the contract's H2D source): meshes and textures
-        for it in wl.scene.items:
-            m = it.mesh
-            if not getattr(m, "_pinned", False):
-                m.pos, m.nrm, m.uv, m.idx = pinned(m.pos), pinned(m.nrm), pinned(m.uv), pinned(m.idx)
-                m._pinned = True
-            for k in list(it.textures):
-                t = it.textures[k]
-                if id(t) not in pinned_tex:              # maps shared between models stay shared
-                    p = pinned(t)
-                    pinned_tex[id(t)] = p
-                    pinned_tex[id(p)] = p
-                it.textures[k] = pinned_tex[id(t)]
-        up_resident = wl.scenes.UploadedScene(r, wl.scene)
-        per_step_uniform_bytes = nviews * sum(32 * 8 + (104 if it.kind in (1, 2) else 0) for it in wl.scene.items)
-
-        def e2e_step(s, with_depth, resident=False):
-            t = [time.perf_counter()]
-            if resident:   # meshes and textures uploaded once (north_star); per step only matrices and uniforms go up
-                wl.render(up_resident, wl.views(api, s, rank, world))
-                r.readback_async(color_host[s & 1], depth_host[s & 1] if with_depth else None)
-                return per_step_uniform_bytes
-            up2 = wl.scenes.UploadedScene(r, wl.scene)                 # H2D: meshes + textures
-            t.append(time.perf_counter())
-            wl.render(up2, wl.views(api, s, rank, world))              # H2D: matrices, uniforms
-            t.append(time.perf_counter())
-            # D2H: the BGR framebuffer of every frame (what the reference writes out, main.cpp:743);
-            # with_depth also brings back the f64 z-buffer the reference keeps in a host global
-            r.readback_async(color_host[s & 1], depth_host[s & 1] if with_depth else None)
-            t.append(time.perf_counter())
-            up2.free()
-            t.append(time.perf_counter())
-            for k, a, b in zip(("upload", "render", "readback", "free"), t[:-1], t[1:]):
-                host_ms[k] += 1e3 * (b - a)
-            return up2.h2d_bytes
-
-        def e2e_run(with_depth, resident=False):
-            h2d = e2e_step(0, with_depth, resident)
-            e2e_step(1, with_depth, resident)                          # the block cache settles after two or three frames
-            e2e_step(2, with_depth, resident)
-            for k in host_ms:
-                host_ms[k] = 0.0
-            r.readback_wait()
-            barrier()
-            t0 = time.perf_counter()
-            for s in range(e_steps):
-                e2e_step(3 + s, with_depth, resident)
-            t_host = time.perf_counter() - t0                          # host time to enqueue the steps (nothing waited for)
-            r.readback_wait()                                          # every host buffer is complete here
-            barrier()
-            dt = time.perf_counter() - t0
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    line = measure(args, env, args.workload, args.steps, args.warmup, True, args.composite)
+    # ---- configs 4 and 5 ride along on the default (config 3) run: short runs, each with its own roofline and
+    #      parity_check, so that the driver's record covers them; on N > 1 GPUs config 4 is the sharded one
+    if args.workload == "c3" and not args.no_also:
+        also = {}
+        k, w = max(1, args.also_steps), 2
+        try:
             if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return {"value": tris_step_all * e_steps / float(t.item()), "unit": "triangles/s",
-                    "h2d_bytes_per_step": int(h2d + (0 if resident else per_step_uniform_bytes)),
-                    "d2h_bytes_per_step": int(nviews * P * (3 + (8 if with_depth else 0))),
-                    "steps": e_steps, "ms_per_step": 1e3 * float(t.item()) / e_steps,
-                    "host_enqueue_ms_per_step": 1e3 * t_host / e_steps,
-                    "host_ms_per_step": {k: v / e_steps for k, v in host_ms.items()}}
-
-        e2e = e2e_run(False)
-        e2e["note"] = ("per step: upload meshes+textures, render, read back the BGR framebuffer of every frame into pinned "
-                       "host memory; the z-buffer stays in HBM for the device-side post passes")
-        e2e["with_depth_readback"] = e2e_run(True)   # same, plus the f64 z-buffer of every frame (PCIe bound)
-        # the deployment north_star describes: meshes / textures go to HBM once, a step uploads matrices and uniforms only
-        e2e["scene_resident"] = e2e_run(False, resident=True)
-        e2e["scene_resident"].pop("host_ms_per_step", None)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------
-    peaks = {}
-    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk_path):
-        peaks = json.load(open(pk_path))
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    kern = {k: {"launches": int(n), "ms": float(m)} for k, (n, m) in prof.items()}
-    total_k_ms = sum(v["ms"] for v in kern.values()) or 1.0
-    dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
-    roof = None
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tr_path):
-        try:
-            traffic = json.load(open(tr_path)).get(wl.name, {}).get(dom)
-        except Exception:
-            traffic = None
-    if dom:
-        per_launch_ms = kern[dom]["ms"] / kern[dom]["launches"]
-        # launches of the dominant kernel per step (one per draw call) share the step's algorithmic bytes
-        bytes_per_launch = balg.get(PASS_OF.get(dom, dom), 0) * args.steps / kern[dom]["launches"]
-        achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
-                "share_of_kernel_time": kern[dom]["ms"] / total_k_ms}
-    step_bytes = sum(balg.values())
-    step_gbs = step_bytes * args.steps / (ms_max * 1e-3) / 1e9
-
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
-                   "--steps", "2", "--warmup", "0", "--c4-level", str(args.c4_level), "--c5-tris", str(args.c5_tris)]
-            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-            ref_line = json.loads(out.stdout.strip().splitlines()[-1])
-            cpu = ref_line["cpu_baseline"]
-        except Exception as e:  # the baseline is a reported figure; never let it sink the GPU line
-            cpu = {"value": None, "unit": "triangles/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
-
-    line = {
-        "metric": METRIC, "value": value, "unit": "triangles/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "strong" if sharded_c4 else "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl.label, "frames_per_step_per_gpu": nviews, "width": wl.width, "height": wl.height,
-                   "triangles_per_frame": T, "l2": "inputs larger than L2 (depth+id+colour planes of one step = %d MB)"
-                   % (nviews * P * 15 // 2 ** 20), "parallelism": ("triangle ranges + %s sort-last composite" % ("fused NVLink P2P" if args.composite == "p2p" else "NCCL")
-                                   if sharded_c4 else
-                                   "frames sharded, no collective") if world > 1 else "1 GPU"},
-        "fragments_per_s": frag * world * args.steps / (ms_max * 1e-3),
-        "pixels_shaded_per_s": C * world * args.steps / (ms_max * 1e-3),
-        "frame_ms": ms_max / args.steps / nviews,
-        "frames_per_s": nviews * world * args.steps / (ms_max * 1e-3),
-        "roofline": roof,
-        "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / peak,
-                          "counters": {"V": V * nviews, "T": T * nviews, "P": P * nviews, "R": R, "T_vis": tvis, "C": C}},
-        "kernels": kern,
-        "cpu_baseline": cpu,
-        "e2e": e2e,
-        "gpu_launches": launches,
-        "clocks": clk,
-        "wall_ms_per_step": 1e3 * t_wall / args.steps,
-        "ms_per_step_unprofiled": ms_unprofiled / args.steps,
-        "tga_encode": tga,
-        "cpu_affinity_cores": numa,
-    }
-    print(json.dumps(line))
+                also["c4_p2p"] = measure(args, env, "c4", k, w, False, "p2p")
+                also["c4_nccl"] = measure(args, env, "c4", k, w, False, "nccl")
+            else:
+                also["c4"] = measure(args, env, "c4", k, w, False)
+                also["c5"] = measure(args, env, "c5", k, w, False)
+        except Exception as e:   # the secondary runs must never sink the headline line
+            also["error"] = repr(e)
+        if line is not None:
+            line["also"] = also
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

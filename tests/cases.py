@@ -283,6 +283,31 @@ def orbit(width, height, frames, room_quads, tex):
 
 orbit_small = orbit(320, 180, [0, 300, 700], ((32, 16), (32, 8), (16, 16)), 128)
 orbit_mid = orbit(960, 540, [5, 517], ((128, 64), (128, 32), (64, 64)), 256)
+# BASELINE config 3 at its stated size: the bench scene (262 144-triangle room + head + eyes, 1024^2 maps) at 1920x1080,
+# one batch whose frame indices straddle the k mod 1024 wrap of the orbit, plus a frame from the far side
+ORBIT_C3_FRAMES = [1022, 1023, 0, 1, 517]
+orbit_c3 = orbit(1920, 1080, ORBIT_C3_FRAMES, ((256, 128), (256, 64), (128, 128)), 1024)
+
+
+def sphere_c4(api, r):
+    """BASELINE config 4 at its stated size: icosphere level 10 (20 971 520 triangles) at 3840x2160, one draw"""
+    sc = scenes.sphere_scene(10)
+    up = scenes.UploadedScene(r, sc)
+    up.render(scenes.sphere_view(api)[None], api.perspective(sc.fov, sc.width / sc.height, sc.znear, sc.zfar))
+    return _grab(r)
+
+
+def soup_c5(api, r):
+    """BASELINE config 5 at its stated size: 100 000 000 sub-pixel triangles at 8192x8192 through the mesh path
+    (V = 3T, implicit indices, identity matrices), one draw.  Digest-only: see tests/golden/golden_fullsize.json"""
+    w = h = 8192
+    n = 100_000_000
+    _, pos = scenes.triangle_soup(n, w, h, 0.4, 5, True, want_clip=False)
+    mesh = r.upload_mesh(pos)
+    r.begin_frame(w, h)
+    r.draw(mesh, np.eye(4), np.eye(4), ntris=n)
+    r.end_frame()
+    return {"z": r.read_depth(0), "bgr": r.read_color(0)}
 
 
 def depth_only_then_color(api, r):
@@ -397,4 +422,7 @@ CASES = {
     "lit_clip_triangles": lit_clip_triangles, "shadow_small": shadow_small, "gouraud_small": gouraud_small,
 }
 FULL_SIZE_CASES = {"k7a": k7a, "k7b": k7b, "k7c": k7c, "head_c1": head_c1, "orbit_mid": orbit_mid,
-                   "shadow_c2": shadow_c2}
+                   "shadow_c2": shadow_c2, "orbit_c3": orbit_c3, "sphere_c4": sphere_c4}
+# too large for an oracle run inside the GPU test session: checked against SHA-256 digests of the reference's
+# own output (tests/golden/golden_fullsize.json, made by tests/golden/make_golden_fullsize.py)
+DIGEST_ONLY_CASES = {"soup_c5": soup_c5}

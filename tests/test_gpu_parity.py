@@ -19,8 +19,12 @@ with open(os.path.join(HERE, "golden", "golden.json")) as f:
     GOLDEN = json.load(f)
 
 
+with open(os.path.join(HERE, "golden", "golden_fullsize.json")) as f:
+    FULLSIZE = json.load(f)
+
+
 def run_case(api, name):
-    fn = cases.CASES.get(name) or cases.FULL_SIZE_CASES[name]
+    fn = cases.CASES.get(name) or cases.FULL_SIZE_CASES.get(name) or cases.DIGEST_ONLY_CASES[name]
     with trb.Renderer(api) as r:
         return fn(api, r)
 
@@ -52,6 +56,41 @@ def test_case_matches_golden_depth(cuda_api, name):
     """depth / ao / z-image digests made from the reference's own our_gl.cpp (tests/golden/make_golden.py)"""
     got = run_case(cuda_api, name)
     compare.assert_matches_golden(name, got, GOLDEN[name], skip=("bgr", "final"))
+
+
+def test_c3_bench_step_matches_reference_digests(cuda_api):
+    """BASELINE config 3 exactly as bench.py renders it: one 32-frame batch of the 1920x1080 orbit (and a second
+    one across the k mod 1024 wrap); every frame's z-buffer must hash to what the reference's own rasterize()
+    produced for that frame (tests/golden/golden_fullsize.json, all 1024 frames)"""
+    want = FULLSIZE["c3_orbit"]["z_sha256"]
+    sc = scenes.orbit_scene()
+    assert FULLSIZE["c3_orbit"]["workload"] == "c3_orbit_%dx%d_%dtri" % (sc.width, sc.height, sc.ntris)
+    pr = cuda_api.perspective(sc.fov, sc.width / sc.height, sc.znear, sc.zfar)
+    with trb.Renderer(cuda_api) as r:
+        up = scenes.UploadedScene(r, sc)
+        for first in (0, 1008):
+            frames = [(first + j) % 1024 for j in range(32)]
+            up.render(scenes.orbit_views(cuda_api, frames), pr)
+            for v, k in enumerate(frames):
+                assert compare.sha(r.read_depth(v)) == want[k], "frame %d differs from the reference's z-buffer" % k
+
+
+def test_c4_sphere_matches_reference_digests(cuda_api):
+    """BASELINE config 4 at full size (20 971 520 triangles, 3840x2160): depth AND the flat-shaded colour"""
+    got = run_case(cuda_api, "sphere_c4")
+    g = FULLSIZE["c4_sphere"]
+    assert int(np.isfinite(got["z"]).sum()) == g["pixels_shaded"]
+    assert compare.sha(got["z"]) == g["z_sha256"] and compare.sha(got["bgr"]) == g["bgr_sha256"]
+
+
+@pytest.mark.slow
+def test_c5_soup_matches_reference_digests(cuda_api):
+    """BASELINE config 5 at full size (100 000 000 sub-pixel triangles, 8192x8192): depth and colour digests of
+    the reference's own output"""
+    got = run_case(cuda_api, "soup_c5")
+    g = FULLSIZE["c5_soup"]
+    assert int(np.isfinite(got["z"]).sum()) == g["pixels_shaded"]
+    assert compare.sha(got["z"]) == g["z_sha256"] and compare.sha(got["bgr"]) == g["bgr_sha256"]
 
 
 def test_reference_library_agrees_when_present(cuda_api, ref_api):

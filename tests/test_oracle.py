@@ -36,6 +36,20 @@ def test_reference_matches_golden(ref_api, name):
     compare.assert_matches_golden(name, run_case(ref_api, name), GOLDEN[name], skip=("stats_port",))
 
 
+def test_fullsize_goldens_are_consistent():
+    """golden_fullsize.json (every frame of the config-3 orbit, configs 4 and 5, made by the reference itself) and
+    golden.json (the test cases) were generated independently: where they describe the same frame they must agree"""
+    with open(os.path.join(HERE, "golden", "golden_fullsize.json")) as f:
+        full = json.load(f)
+    assert len(full["c3_orbit"]["z_sha256"]) == 1024 and len(set(full["c3_orbit"]["z_sha256"])) == 1024
+    for v, k in enumerate(cases.ORBIT_C3_FRAMES):
+        assert GOLDEN["orbit_c3"]["z_v%d" % v]["sha256"] == full["c3_orbit"]["z_sha256"][k]
+    assert GOLDEN["sphere_c4"]["z"]["sha256"] == full["c4_sphere"]["z_sha256"]
+    assert GOLDEN["sphere_c4"]["bgr"]["sha256"] == full["c4_sphere"]["bgr_sha256"]
+    for k in ("c4_sphere", "c5_soup"):
+        assert len(full[k]["z_sha256"]) == 64 and full[k]["pixels_shaded"] > 0
+
+
 def test_survey_kats_on_reference(fresh_ref_api):
     """SURVEY section 4, K1-K6, numbers obtained from the reference itself during the survey"""
     api = fresh_ref_api

@@ -847,17 +847,29 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
 // ---------------------------------------------------------------------------------------------
 constexpr int RW_WARPS = 4;                 // tiles per CTA
 constexpr uint32_t WARP_MAX_DEFAULT = 1024; // longest bin a single warp takes; TRB_WARP_MAX overrides (0: k_raster only)
-struct __align__(32) WarpTile {
+// A triangle of the current batch as the warp keeps it in shared memory: the eleven doubles eval_sample reads
+// plus its id and the packed description of its bbox inside the tile.  96 bytes of payload on a 112-byte pitch:
+// consecutive records then start 28 banks apart, so the eight lanes of a quarter warp that read eight
+// different records with one LDS.128 (a window of tiny triangles) do not collide.
+struct __align__(16) SmTri {
+    double ax, ay, s00, s01, s10, s11, uz, ruz, z0, z1, z2;
+    uint32_t gid;
+    uint32_t pack;   // p0 = y0 * 16 + x0 (8 bits) | 16 - width (4) | u.z inside div_rn's window (1) | ceil(2^15 / width) (16)
+    double pad_;
+};
+static_assert(sizeof(SmTri) == 112, "SmTri pitch");
+struct __align__(16) WarpTile {
     unsigned long long zk[TILE * TILE];
     uint32_t vid[TILE * TILE];
-    TriRec recs[32];
+    SmTri recs[32];
 };
-static_assert(sizeof(WarpTile) == 6144, "WarpTile size");
+static_assert(sizeof(WarpTile) == 6656, "WarpTile size");
 
-#ifndef TRB_RW_MIN_BLOCKS
-#define TRB_RW_MIN_BLOCKS 9   // 9 x 24 KB of tiles = 221 KB of the SM's shared memory, 56 registers; measured 0.695 vs 0.708 ms at 8
-#endif
-__global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_warp(FrameDev f, RasterArgs a) {
+// MINB = resident CTAs per SM the register allocation aims for: 8 (64 registers, 208 KB of tiles per SM), 7 (72) or
+// 6 (80 registers, no spills).  TRB_RW_BLOCKS picks the instantiation at run time; the default is the measured best.
+constexpr int RW_BLOCKS_DEFAULT = 8;
+template <int MINB>
+__global__ void __launch_bounds__(RW_WARPS * 32, MINB) k_raster_warp(FrameDev f, RasterArgs a) {
     __shared__ WarpTile tiles[RW_WARPS];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -872,6 +884,7 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
     unsigned long long* gz = f.zkey + (size_t)view * f.npix;
     uint32_t* gv = f.vis + (size_t)view * f.npix;
     const TriRec* tr = a.trirec + (size_t)view * a.ntris;
+    const unsigned lane_le = FULL >> (31 - lane), lane_lt = lane_le >> 1;
 
     // first batch's bin entry: in flight while the tile is staged
     TRB_CHECK((unsigned long long)off + n <= a.ctl->total);
@@ -887,11 +900,12 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
     uint32_t covered = 0;
     for (uint32_t base = 0; base < n; base += 32) {
         const bool has = base + lane < n;
-        uint32_t gid = 0, pack = 0, ns = 0;
+        uint32_t ns = 0;
         if (has) {
             const uint32_t t = t_next;
             TRB_CHECK(t < a.ntris);
             const double2* q = reinterpret_cast<const double2*>(tr + t);
+            // TriRec: ax ay | s00 s01 | s10 s11 | uz z0 | z1 z2 | ruz bbox
             const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
             if (base + 32 + lane < n) t_next = __ldg(a.bins + off + base + 32 + lane);
             const unsigned long long bbw = (unsigned long long)__double_as_longlong(r5.y);
@@ -900,12 +914,17 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
             const int cx0 = max(bx0, tx0) - tx0, cx1 = min(bx1, tx0 + TILE - 1) - tx0;
             const int cy0 = max(by0, ty0) - ty0, cy1 = min(by1, ty0 + TILE - 1) - ty0;
             const int bw = cx1 - cx0 + 1;
+            TRB_CHECK(bw >= 1 && bw <= 16 && cy1 >= cy0 && cy1 < 16 && cy0 >= 0 && cx0 >= 0);
             ns = (uint32_t)(bw * (cy1 - cy0 + 1));
-            // x0 | y0 | width-1 | ceil(2^15 / width): l / width == (l * inv) >> 15 for l < 256, width <= 16
-            pack = (uint32_t)cx0 | ((uint32_t)cy0 << 4) | ((uint32_t)(bw - 1) << 8) | ((uint32_t)((32768 + bw - 1) / bw) << 12);
-            gid = a.id_base + t + 1u;
+            // sample l of the clipped bbox sits at pixel p0 + l + (l / width) * (16 - width);
+            // l / width == (l * ceil(2^15 / width)) >> 15 for l < 256, width <= 16
+            const uint32_t pack = (uint32_t)((cy0 << 4) | cx0) | ((uint32_t)(16 - bw) << 8) |
+                                  (exponent_in_window(r3.x) ? 0x1000u : 0u) | ((uint32_t)((32768 + bw - 1) / bw) << 16);
             double2* d = reinterpret_cast<double2*>(&sm.recs[lane]);
-            d[0] = r0; d[1] = r1; d[2] = r2; d[3] = r3; d[4] = r4; d[5] = r5;
+            d[0] = r0; d[1] = r1; d[2] = r2;
+            d[3] = make_double2(r3.x, r5.x);             // uz, ruz
+            d[4] = make_double2(r3.y, r4.x);             // z0, z1
+            d[5] = make_double2(r4.y, __longlong_as_double((long long)(((unsigned long long)pack << 32) | (a.id_base + t + 1u))));
         }
         uint32_t incl = ns;                          // samples of the batch laid end to end
         #pragma unroll
@@ -914,47 +933,57 @@ __global__ void __launch_bounds__(RW_WARPS * 32, TRB_RW_MIN_BLOCKS) k_raster_war
             if (lane >= o) incl += y;
         }
         const uint32_t first = incl - ns, S = __shfl_sync(FULL, incl, 31);
+        const uint32_t first_s = has ? first : 0x7fffffffu;   // lanes without a triangle never start one
         __syncwarp();
+        uint32_t before = 0;                         // triangles of the batch that start before the current window
         for (uint32_t bs = 0; bs < S; bs += 32) {
-            const uint32_t s = bs + lane;
-            const uint32_t rel = first - bs;         // wraps for triangles that started in an earlier window
-            const unsigned starts = __reduce_or_sync(FULL, (has && rel < 32u) ? (1u << rel) : 0u);
-            const int before = __popc(__ballot_sync(FULL, has && first < bs));
-            const bool act = s < S;
-            const int e = act ? before + __popc(starts & (FULL >> (31 - lane))) - 1 : 0;
+            // which triangle does sample bs + lane belong to?  The triangles' first samples inside this window of 32
+            // form a bit mask: one REDUX, one POPC.
+            // shl.b32 yields 0 for shift counts >= 32: triangles that started in an earlier window (the difference
+            // wraps) or start in a later one contribute nothing
+            unsigned startbit;
+            asm("shl.b32 %0, 1, %1;" : "=r"(startbit) : "r"(first_s - bs));
+            const unsigned starts = __reduce_or_sync(FULL, startbit);
+            const int e = (int)before + __popc(starts & lane_le) - 1;
+            before += (uint32_t)__popc(starts);
             TRB_CHECK(e >= 0 && e < 32 && (uint32_t)e < n - base);
-            const uint32_t first_e = __shfl_sync(FULL, first, e);
-            const uint32_t pk = __shfl_sync(FULL, pack, e);
-            const uint32_t gid_e = __shfl_sync(FULL, gid, e);
+            const uint32_t l = bs + lane - __shfl_sync(FULL, first, e);
+            const bool act = bs + lane < S;
+            const double2* q = reinterpret_cast<const double2*>(&sm.recs[e]);
+            const double2 r5 = q[5];
+            const unsigned long long gp = (unsigned long long)__double_as_longlong(r5.y);
+            const uint32_t gid_e = (uint32_t)gp, pk = (uint32_t)(gp >> 32);
+            const uint32_t row = (l * (pk >> 16)) >> 15;
+            const int p = (int)((pk & 255u) + l + row * ((pk >> 8) & 15u));
             bool frag = false;
             unsigned long long key = 0;
-            int p = 0;
             if (act) {
-                const uint32_t l = s - first_e, bw = ((pk >> 8) & 15u) + 1u;
-                const uint32_t row = (l * (pk >> 12)) >> 15;
-                const int lx = (int)((pk & 15u) + (l - row * bw)), ly = (int)(((pk >> 4) & 15u) + row);
-                TRB_CHECK(lx >= 0 && lx < TILE && ly >= 0 && ly < TILE && l - row * bw < bw);
-                const double2* q = reinterpret_cast<const double2*>(&sm.recs[e]);
+                TRB_CHECK(p >= 0 && p < TILE * TILE);
                 const double2 r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3], r4 = q[4];
-                TriSetup ts;
-                ts.ax = r0.x; ts.ay = r0.y; ts.s00 = r1.x; ts.s01 = r1.y; ts.s10 = r2.x; ts.s11 = r2.y;
-                ts.uz = r3.x; ts.z0 = r3.y; ts.z1 = r4.x; ts.z2 = r4.y; ts.ruz = q[5].x;
-                double b[3], z;
-                if (eval_sample(ts, tx0 + lx, ty0 + ly, b, z)) {
+                const double z = eval_sample_fast(reinterpret_cast<const double*>(q), r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x,
+                                                  r3.y, r4.x, r4.y, r5.x, (pk & 0x1000u) != 0u, tx0 + (p & 15), ty0 + (p >> 4));
+                if (finite_d(z)) {                                // our_gl.cpp:160 (NaN: not covered)
                     frag = true;
-                    key = fragment_key(z);
-                    p = (ly << TILE_SHIFT) | lx;
+                    key = depth_key_dev(__dadd_rn(z, 0.0));      // fragment_key: -0.0 + 0.0 == +0.0, everything else unchanged
                     ++covered;
                 }
             }
-            if ((starts & ~1u) == 0u) {              // the whole window is one triangle: distinct pixels
+            // apply: plain read-compare-write of (key, id).  Lanes of ONE triangle hit distinct pixels; when the window
+            // spans several triangles two lanes may meet in a pixel: they then take turns, so the outcome is the
+            // lexicographic minimum whatever the order.
+            bool clash = false;
+            unsigned rank = 0;
+            if (starts >> 1) {
+                const unsigned peers = __match_any_sync(FULL, frag ? (unsigned)p : 256u + (unsigned)lane);
+                rank = __popc(peers & lane_lt);
+                clash = __any_sync(FULL, rank != 0u);
+            }
+            if (!clash) {
                 if (frag) {
                     const unsigned long long cur = sm.zk[p];
                     if (key < cur || (key == cur && gid_e < sm.vid[p])) { sm.zk[p] = key; sm.vid[p] = gid_e; }
                 }
             } else {
-                const unsigned peers = __match_any_sync(FULL, frag ? (unsigned)p : 256u + (unsigned)lane);
-                const unsigned rank = __popc(peers & ((1u << lane) - 1u));
                 const unsigned turns = __reduce_max_sync(FULL, rank);
                 for (unsigned r = 0; r <= turns; ++r) {
                     if (frag && rank == r) {

@@ -285,6 +285,7 @@ struct TrbCtx {
     int big_ns = BIG_NS_DEFAULT, small_min = SMALL_MIN_DEFAULT, large_ns = LARGE_NS_DEFAULT;
     int direct_area = DIRECT_AREA_DEFAULT;
     uint32_t warp_max = WARP_MAX_DEFAULT;
+    int rw_blocks = RW_BLOCKS_DEFAULT;   // k_raster_warp instantiation (resident CTAs per SM the registers are sized for)
     bool shade_exact = false;   // true: all-fp64 lighting (exact.cuh); false: fp32 lighting (fastshade.cuh)
 };
 
@@ -583,7 +584,12 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     ra.heavy_list = c->heavy_list.as<uint32_t>();
     if (c->warp_max > 0) {   // bins of 1..warp_max triangles: one warp per tile
         Launch L(c, "k_raster_warp");
-        k_raster_warp<<<dim3((f.ntiles + RW_WARPS - 1) / RW_WARPS, f.nviews), RW_WARPS * 32, 0, c->stream>>>(f, ra);
+        const dim3 grid((f.ntiles + RW_WARPS - 1) / RW_WARPS, f.nviews);
+        switch (c->rw_blocks) {
+            case 6: k_raster_warp<6><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
+            case 7: k_raster_warp<7><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
+            default: k_raster_warp<8><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
+        }
     }
     if (long_bins) {         // longer bins: one CTA per tile, persistent grid over the device-side list
         const unsigned grid = (unsigned)std::min<size_t>(nslots, (size_t)148 * TRB_RASTER_MIN_BLOCKS);
@@ -698,6 +704,7 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_LARGE_NS")) c->large_ns = std::max(1, atoi(e));
     if (const char* e = getenv("TRB_DIRECT_AREA")) c->direct_area = std::max(0, atoi(e));
     if (const char* e = getenv("TRB_WARP_MAX")) c->warp_max = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("TRB_RW_BLOCKS")) c->rw_blocks = atoi(e);
     if (const char* e = getenv("TRB_SHADE_EXACT")) c->shade_exact = atoi(e) != 0;
     if (const char* e = getenv("TRB_SYNC_DRAWS")) c->sync_draws = atoi(e) != 0;
     if (const char* e = getenv("TRB_BIN_CAP")) c->bin_cap_fixed = (uint32_t)std::max(1, atoi(e));
@@ -712,7 +719,9 @@ int trb_create(int device, TrbCtx** out) {
     }
     memset(c->host_total, 0, 64);
     // 9 CTAs x 24 KB of per-warp tiles per SM: ask for the large shared-memory carveout
-    cudaFuncSetAttribute(k_raster_warp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_raster_warp<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_raster_warp<7>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_raster_warp<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = c;
     return TRB_OK;
 }
