@@ -845,34 +845,98 @@ __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev 
 // possible when the window spans several triangles) take turns (match_any), so the result is the
 // lexicographic (depth, id) minimum whatever the order - the reference's first-wins on ties.
 // ---------------------------------------------------------------------------------------------
-constexpr int RW_WARPS = 4;                 // tiles per CTA
+#ifndef TRB_RW_WARPS
+#define TRB_RW_WARPS 4
+#endif
+constexpr int RW_WARPS = TRB_RW_WARPS;      // tiles per CTA.  One: the warp's shared-memory block sits at a constant address
 constexpr uint32_t WARP_MAX_DEFAULT = 1024; // longest bin a single warp takes; TRB_WARP_MAX overrides (0: k_raster only)
 // A triangle of the current batch as the warp keeps it in shared memory: the eleven doubles eval_sample reads
-// plus its id and the packed description of its bbox inside the tile.  96 bytes of payload on a 112-byte pitch:
-// consecutive records then start 28 banks apart, so the eight lanes of a quarter warp that read eight
-// different records with one LDS.128 (a window of tiny triangles) do not collide.
+// plus its id.  96 bytes of payload on a 112-byte pitch: consecutive records start 28 banks apart, so the eight
+// lanes of a quarter warp that read different records with one LDS.128 do not collide.
 struct __align__(16) SmTri {
     double ax, ay, s00, s01, s10, s11, uz, ruz, z0, z1, z2;
     uint32_t gid;
-    uint32_t pack;   // p0 = y0 * 16 + x0 (8 bits) | 16 - width (4) | u.z inside div_rn's window (1) | ceil(2^15 / width) (16)
+    uint32_t flags;   // bit 0: u.z inside div_rn's exponent window
     double pad_;
 };
 static_assert(sizeof(SmTri) == 112, "SmTri pitch");
+constexpr int RW_SPAN_CAP = 32 * TILE;      // every row of every triangle of a batch
 struct __align__(16) WarpTile {
     unsigned long long zk[TILE * TILE];
     uint32_t vid[TILE * TILE];
     SmTri recs[32];
+    uint32_t spans[RW_SPAN_CAP];            // triangle (5 bits) | first column (4) | row (4) | length - 1 (4)
 };
-static_assert(sizeof(WarpTile) == 6656, "WarpTile size");
+static_assert(sizeof(WarpTile) == 8704, "WarpTile size");
 
-// MINB = resident CTAs per SM the register allocation aims for: 8 (64 registers, 208 KB of tiles per SM), 7 (72) or
-// 6 (80 registers, no spills).  TRB_RW_BLOCKS picks the instantiation at run time; the default is the measured best.
-constexpr int RW_BLOCKS_DEFAULT = 8;
+// Conservative row spans.  A sample of row y can only be covered when the three edge values the reference computes
+// (u.x <= 0, u.y <= 0, u.x + u.y >= u.z; our_gl.cpp:77-86, 152) allow it.  In real arithmetic each is linear in the
+// column, so each edge bounds the columns of the row from one side: column bound_k(y) = alpha_k + beta_k * s12 with
+// s12 = A.y - (y + 0.5).  The reference evaluates the edge values in floating point; alpha_k carries a margin that is
+// orders of magnitude larger than those rounding errors (and than the errors of this evaluation itself), always in the
+// direction that keeps MORE columns.  Columns outside the span are therefore certain to fail the reference's test and
+// are never enumerated; every column inside still goes through the exact evaluation, which alone decides coverage.
+// (-DTRB_DEBUG_CHECKS evaluates the skipped columns too and asserts that none of them is covered.)
+struct SpanEdges {
+    double ay;                       // A.y (0 when the triangle's coordinates are not finite: every edge is then disabled)
+    double a0, b0, a1, b1, a2, b2;   // bound_k = a_k + b_k * s12, stored so that floor() applies to all three
+    int m0, m1, m2;                  // INT_MIN: edge k bounds the columns from above (x <= floor(bound));
+                                     // INT_MAX: from below (x >= -floor(bound), the bound is stored negated)
+};
+__device__ __forceinline__ void span_edge(double num_const, double num_s12, double B, double centre, double s12max,
+                                          bool ge, double& a, double& b, int& m) {
+    // constraint  t * B >= num  (ge)  or  t * B <= num  (!ge)  with  t = A.x - px,  num = num_const + num_s12 * s12
+    //   ->  px <= A.x - num / B  when the inequality bounds t from below (ge == (B > 0)), else px >= A.x - num / B
+    double r;                                                   // 1 / B to ~2^-40: MUFU.RCP64H + one Newton step
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(B));
+    r = __fma_rn(__fma_rn(-B, r, 1.0), r, r);
+    const bool upper = ge == (B > 0.0);                         // columns bounded from above
+    double alpha = centre - num_const * r, beta = -num_s12 * r; // column + 0.5 = A.x - num / B
+    const double w = 2.9802322387695312e-08 * (fabs(alpha) + fabs(beta) * s12max + fabs(centre)) + 9.5367431640625e-07;  // 2^-25 rel + 2^-20
+    alpha = upper ? alpha + w : alpha - w;
+    const bool ok = fabs(r) <= 1.0e300 && fabs(alpha) <= 1.0e300 && fabs(beta) <= 1.0e300 && B != 0.0;   // false for NaN too
+    if (!ok) { a = 1.0e300; b = 0.0; m = INT_MIN; return; }      // no bound from this edge (floor saturates to INT_MAX)
+    if (upper) { a = alpha; b = beta; m = INT_MIN; }
+    else { a = -alpha; b = -beta; m = INT_MAX; }                // x >= ceil(v)  <=>  -x <= floor(-v)
+}
+__device__ __forceinline__ void span_setup(const double2& r0, const double2& r1, const double2& r2, double uz, int X0, int X1,
+                                           int Y0, int Y1, SpanEdges& E) {
+    const double ax = r0.x, ay = r0.y, s00 = r1.x, s01 = r1.y, s10 = r2.x, s11 = r2.y;
+    // magnitudes over the clipped bbox: |t| = |A.x - px| and |s12| = |A.y - py|
+    const double tmax = fmax(fabs(ax - pixel_centre(X0)), fabs(ax - pixel_centre(X1)));
+    const double s12max = fmax(fabs(ay - pixel_centre(Y0)), fabs(ay - pixel_centre(Y1)));
+    const double K = 1.4210854715202004e-14;                    // 2^-46: 64 x the rounding of a product / sum
+    const double e1 = K * (fabs(s01) * s12max + fabs(s11) * tmax), e2 = K * (fabs(s00) * s12max + fabs(s10) * tmax);
+    const double thr = fabs(uz) * 1e-290;
+    const double e3 = 4.0 * (e1 + e2) + K * fabs(uz);
+    const double centre = ax - 0.5;
+    // infinite / NaN coordinates make s12max (and with it every margin) non-finite, which disables all three edges;
+    // the row evaluation must then not multiply an infinite s12 by a zero slope
+    E.ay = fabs(ay) <= 1.0e300 ? ay : 0.0;
+    // u.x = s01*s12 - t*s11 <= thr            ->  t * s11 >= s01*s12 - (thr + e1)
+    span_edge(-(thr + e1), s01, s11, centre, s12max, true, E.a0, E.b0, E.m0);
+    // u.y = t*s10 - s00*s12 <= thr            ->  t * s10 <= s00*s12 + (thr + e2)
+    span_edge(thr + e2, s00, s10, centre, s12max, false, E.a1, E.b1, E.m1);
+    // u.x + u.y = (s01-s00)*s12 + t*(s10-s11) >= u.z*1.000001 - e3   ->  t * (s10-s11) >= (u.z*1.000001 - e3) - (s01-s00)*s12
+    span_edge(uz * 1.000001 - e3, -(s01 - s00), s10 - s11, centre, s12max, true, E.a2, E.b2, E.m2);
+}
+// columns [xa, xb] (absolute, clamped to [X0, X1]) of row y that can hold a covered sample; empty when xa > xb
+__device__ __forceinline__ void span_of_row(const SpanEdges& E, double s12, int X0, int X1, int& xa, int& xb) {
+    const int f0 = __double2int_rd(__fma_rn(E.b0, s12, E.a0)), f1 = __double2int_rd(__fma_rn(E.b1, s12, E.a1)),
+              f2 = __double2int_rd(__fma_rn(E.b2, s12, E.a2));
+    // m_k == INT_MIN: max(f_k, m_k) = f_k takes part in the upper bound, max(f_k, ~m_k) = INT_MAX drops out of the lower
+    xb = min(X1, min(min(max(f0, E.m0), max(f1, E.m1)), max(f2, E.m2)));
+    const int lo = min(min(max(f0, ~E.m0), max(f1, ~E.m1)), max(f2, ~E.m2));   // min over the lower edges of floor(-v)
+    xa = max(X0, lo == INT_MAX ? INT_MIN : -lo);                                // -INT_MIN wraps to INT_MIN: no bound, safe
+}
+
+// MINB = resident CTAs per SM the register allocation aims for.  TRB_RW_BLOCKS picks the instantiation at run time.
+constexpr int RW_BLOCKS_DEFAULT = 6;
 template <int MINB>
-__global__ void __launch_bounds__(RW_WARPS * 32, MINB) k_raster_warp(FrameDev f, RasterArgs a) {
+__global__ void __launch_bounds__(RW_WARPS * 32, MINB * (4 / RW_WARPS > 0 ? 4 / RW_WARPS : 1)) k_raster_warp(FrameDev f, RasterArgs a) {
     __shared__ WarpTile tiles[RW_WARPS];
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = RW_WARPS > 1 ? (int)(threadIdx.x >> 5) : 0;
     const int tile = blockIdx.x * RW_WARPS + warp, view = blockIdx.y;
     if (tile >= f.ntiles) return;
     const size_t tslot = (size_t)view * f.ntiles + tile;
@@ -897,10 +961,26 @@ __global__ void __launch_bounds__(RW_WARPS * 32, MINB) k_raster_warp(FrameDev f,
         sm.zk[p] = valid ? gz[gp] : 0ull;          // key 0 never loses: pixels outside the frame stay untouched
         sm.vid[p] = valid ? gv[gp] : VIS_NONE;
     }
-    uint32_t covered = 0;
+    uint32_t covered = 0, touched = 0;
+    unsigned zmin_hi = 0xffffffffu, zmin_lo = 0xffffffffu;   // smallest key written (min_z of our_gl.cpp:197)
+    auto apply = [&](int p, unsigned long long key, uint32_t gid) {
+        const unsigned long long cur = sm.zk[p];
+        if (key < cur || (key == cur && gid < sm.vid[p])) {
+            sm.zk[p] = key;
+            sm.vid[p] = gid;
+            ++touched;                                        // upper bound of the pixels that changed hands
+            const unsigned kh = (unsigned)(key >> 32), kl = (unsigned)key;
+            if (kh < zmin_hi || (kh == zmin_hi && kl < zmin_lo)) { zmin_hi = kh; zmin_lo = kl; }
+        }
+    };
     for (uint32_t base = 0; base < n; base += 32) {
+        // ---- the batch: every lane takes one triangle of the bin, keeps its record in shared memory and lists the
+        //      conservative spans of its rows inside the tile
         const bool has = base + lane < n;
-        uint32_t ns = 0;
+        int X0 = 0, X1 = -1, Y0 = 0, nrows = 0;
+        SpanEdges E;
+        E.ay = E.a0 = E.a1 = E.a2 = E.b0 = E.b1 = E.b2 = 0.0;
+        E.m0 = E.m1 = E.m2 = INT_MIN;
         if (has) {
             const uint32_t t = t_next;
             TRB_CHECK(t < a.ntris);
@@ -909,110 +989,136 @@ __global__ void __launch_bounds__(RW_WARPS * 32, MINB) k_raster_warp(FrameDev f,
             const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
             if (base + 32 + lane < n) t_next = __ldg(a.bins + off + base + 32 + lane);
             const unsigned long long bbw = (unsigned long long)__double_as_longlong(r5.y);
-            const int bx0 = (int)(bbw & 0xffff), by0 = (int)((bbw >> 16) & 0xffff);
-            const int bx1 = (int)((bbw >> 32) & 0xffff), by1 = (int)(bbw >> 48);
-            const int cx0 = max(bx0, tx0) - tx0, cx1 = min(bx1, tx0 + TILE - 1) - tx0;
-            const int cy0 = max(by0, ty0) - ty0, cy1 = min(by1, ty0 + TILE - 1) - ty0;
-            const int bw = cx1 - cx0 + 1;
-            TRB_CHECK(bw >= 1 && bw <= 16 && cy1 >= cy0 && cy1 < 16 && cy0 >= 0 && cx0 >= 0);
-            ns = (uint32_t)(bw * (cy1 - cy0 + 1));
-            // sample l of the clipped bbox sits at pixel p0 + l + (l / width) * (16 - width);
-            // l / width == (l * ceil(2^15 / width)) >> 15 for l < 256, width <= 16
-            const uint32_t pack = (uint32_t)((cy0 << 4) | cx0) | ((uint32_t)(16 - bw) << 8) |
-                                  (exponent_in_window(r3.x) ? 0x1000u : 0u) | ((uint32_t)((32768 + bw - 1) / bw) << 16);
+            X0 = max((int)(bbw & 0xffff), tx0); X1 = min((int)((bbw >> 32) & 0xffff), tx0 + TILE - 1);
+            Y0 = max((int)((bbw >> 16) & 0xffff), ty0);
+            const int Y1 = min((int)(bbw >> 48), ty0 + TILE - 1);
+            nrows = Y1 - Y0 + 1;
+            TRB_CHECK(X1 >= X0 && nrows >= 1 && nrows <= TILE && X1 - X0 < TILE);
+            span_setup(r0, r1, r2, r3.x, X0, X1, Y0, Y1, E);
             double2* d = reinterpret_cast<double2*>(&sm.recs[lane]);
             d[0] = r0; d[1] = r1; d[2] = r2;
             d[3] = make_double2(r3.x, r5.x);             // uz, ruz
             d[4] = make_double2(r3.y, r4.x);             // z0, z1
-            d[5] = make_double2(r4.y, __longlong_as_double((long long)(((unsigned long long)pack << 32) | (a.id_base + t + 1u))));
+            const uint32_t flags = exponent_in_window(r3.x) ? 1u : 0u;
+            d[5] = make_double2(r4.y, __longlong_as_double((long long)(((unsigned long long)flags << 32) | (a.id_base + t + 1u))));
         }
-        uint32_t incl = ns;                          // samples of the batch laid end to end
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += y;
+        uint32_t nspans = 0;
+        const int maxrows = __reduce_max_sync(FULL, nrows);
+        // s12 of the rows by repeated subtraction: within an ulp of the A.y - (y + 0.5) the exact evaluation uses, far
+        // inside the margins of the bounds
+        double s12 = E.ay - pixel_centre(Y0);
+        for (int r = 0; r < maxrows; ++r, s12 -= 1.0) {
+            int xa = 0, xb = -1;
+            if (r < nrows) span_of_row(E, s12, X0, X1, xa, xb);
+#if defined(TRB_DEBUG_CHECKS)
+            if (r < nrows) {      // the skipped columns must all fail the reference's test
+                const double2* q = reinterpret_cast<const double2*>(&sm.recs[lane]);
+                TriSetup ts;
+                ts.ax = q[0].x; ts.ay = q[0].y; ts.s00 = q[1].x; ts.s01 = q[1].y; ts.s10 = q[2].x; ts.s11 = q[2].y;
+                ts.uz = q[3].x; ts.ruz = q[3].y; ts.z0 = q[4].x; ts.z1 = q[4].y; ts.z2 = q[5].x;
+                ts.x0 = ts.y0 = ts.x1 = ts.y1 = 0;
+                for (int x = X0; x <= X1; ++x) {
+                    double bb[3], zz;
+                    if (x < xa || x > xb) assert(!eval_sample(ts, x, Y0 + r, bb, zz));
+                }
+            }
+#endif
+            const bool ne = xa <= xb;
+            const unsigned nb = __ballot_sync(FULL, ne);
+            if (ne) {
+                TRB_CHECK(xa >= X0 && xb <= X1 && nspans + __popc(nb & lane_lt) < (unsigned)RW_SPAN_CAP);
+                sm.spans[nspans + __popc(nb & lane_lt)] = (uint32_t)lane | ((uint32_t)(xa - tx0) << 5) |
+                                                          ((uint32_t)(Y0 + r - ty0) << 9) | ((uint32_t)(xb - xa) << 13);
+            }
+            nspans += (uint32_t)__popc(nb);
         }
-        const uint32_t first = incl - ns, S = __shfl_sync(FULL, incl, 31);
-        const uint32_t first_s = has ? first : 0x7fffffffu;   // lanes without a triangle never start one
         __syncwarp();
-        uint32_t before = 0;                         // triangles of the batch that start before the current window
-        for (uint32_t bs = 0; bs < S; bs += 32) {
-            // which triangle does sample bs + lane belong to?  The triangles' first samples inside this window of 32
-            // form a bit mask: one REDUX, one POPC.
-            // shl.b32 yields 0 for shift counts >= 32: triangles that started in an earlier window (the difference
-            // wraps) or start in a later one contribute nothing
-            unsigned startbit;
-            asm("shl.b32 %0, 1, %1;" : "=r"(startbit) : "r"(first_s - bs));
-            const unsigned starts = __reduce_or_sync(FULL, startbit);
-            const int e = (int)before + __popc(starts & lane_le) - 1;
-            before += (uint32_t)__popc(starts);
-            TRB_CHECK(e >= 0 && e < 32 && (uint32_t)e < n - base);
-            const uint32_t l = bs + lane - __shfl_sync(FULL, first, e);
-            const bool act = bs + lane < S;
-            const double2* q = reinterpret_cast<const double2*>(&sm.recs[e]);
-            const double2 r5 = q[5];
-            const unsigned long long gp = (unsigned long long)__double_as_longlong(r5.y);
-            const uint32_t gid_e = (uint32_t)gp, pk = (uint32_t)(gp >> 32);
-            const uint32_t row = (l * (pk >> 16)) >> 15;
-            const int p = (int)((pk & 255u) + l + row * ((pk >> 8) & 15u));
-            bool frag = false;
-            unsigned long long key = 0;
-            if (act) {
-                TRB_CHECK(p >= 0 && p < TILE * TILE);
-                const double2 r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3], r4 = q[4];
-                const double z = eval_sample_fast(reinterpret_cast<const double*>(q), r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x,
-                                                  r3.y, r4.x, r4.y, r5.x, (pk & 0x1000u) != 0u, tx0 + (p & 15), ty0 + (p >> 4));
-                if (finite_d(z)) {                                // our_gl.cpp:160 (NaN: not covered)
-                    frag = true;
-                    key = depth_key_dev(__dadd_rn(z, 0.0));      // fragment_key: -0.0 + 0.0 == +0.0, everything else unchanged
-                    ++covered;
-                }
+        // ---- the spans, 32 at a time: their samples are laid end to end and dealt out to the lanes
+        for (uint32_t g = 0; g < nspans; g += 32) {
+            const bool sv = g + lane < nspans;
+            const uint32_t ent = sv ? sm.spans[g + lane] : 0u;
+            const uint32_t len = sv ? (ent >> 13) + 1u : 0u;
+            uint32_t incl = len;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += y;
             }
-            // apply: plain read-compare-write of (key, id).  Lanes of ONE triangle hit distinct pixels; when the window
-            // spans several triangles two lanes may meet in a pixel: they then take turns, so the outcome is the
-            // lexicographic minimum whatever the order.
-            bool clash = false;
-            unsigned rank = 0;
-            if (starts >> 1) {
-                const unsigned peers = __match_any_sync(FULL, frag ? (unsigned)p : 256u + (unsigned)lane);
-                rank = __popc(peers & lane_lt);
-                clash = __any_sync(FULL, rank != 0u);
-            }
-            if (!clash) {
-                if (frag) {
-                    const unsigned long long cur = sm.zk[p];
-                    if (key < cur || (key == cur && gid_e < sm.vid[p])) { sm.zk[p] = key; sm.vid[p] = gid_e; }
-                }
-            } else {
-                const unsigned turns = __reduce_max_sync(FULL, rank);
-                for (unsigned r = 0; r <= turns; ++r) {
-                    if (frag && rank == r) {
-                        const unsigned long long cur = sm.zk[p];
-                        if (key < cur || (key == cur && gid_e < sm.vid[p])) { sm.zk[p] = key; sm.vid[p] = gid_e; }
+            const uint32_t first = incl - len, S = __shfl_sync(FULL, incl, 31);
+            const uint32_t first_s = sv ? first : 0x7fffffffu;   // lanes without a span never start one
+            uint32_t before = 0;                     // spans of the group that start before the current window
+            for (uint32_t bs = 0; bs < S; bs += 32) {
+                // which span does sample bs + lane belong to?  The spans' first samples inside this window of 32 form a
+                // bit mask: one REDUX, one POPC.  shl.b32 yields 0 for shift counts >= 32: spans that started in an
+                // earlier window (the difference wraps) or start in a later one contribute nothing
+                unsigned startbit;
+                asm("shl.b32 %0, 1, %1;" : "=r"(startbit) : "r"(first_s - bs));
+                const unsigned starts = __reduce_or_sync(FULL, startbit);
+                const int j = (int)before + __popc(starts & lane_le) - 1;
+                before += (uint32_t)__popc(starts);
+                TRB_CHECK(j >= 0 && j < 32);
+                const uint32_t ent_j = __shfl_sync(FULL, ent, j);
+                const uint32_t l = bs + lane - __shfl_sync(FULL, first, j);
+                const bool act = bs + lane < S;
+                const int p = (int)(((ent_j >> 5) & 255u) + l);       // row * 16 + first column + l
+                const double2* q = reinterpret_cast<const double2*>(&sm.recs[ent_j & 31u]);
+                const double2 r5 = q[5];
+                const unsigned long long gf = (unsigned long long)__double_as_longlong(r5.y);
+                const uint32_t gid_e = (uint32_t)gf;
+                bool frag = false;
+                unsigned long long key = 0;
+                if (act) {
+                    TRB_CHECK(p >= 0 && p < TILE * TILE && l <= (ent_j >> 13));
+                    const double2 r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3], r4 = q[4];
+                    const double z = eval_sample_fast(reinterpret_cast<const double*>(q), r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x,
+                                                      r3.y, r4.x, r4.y, r5.x, (gf >> 32) != 0ull, tx0 + (p & 15), ty0 + (p >> 4));
+                    if (finite_d(z)) {                                // our_gl.cpp:160 (NaN: not covered)
+                        frag = true;
+                        key = depth_key_dev(__dadd_rn(z, 0.0));      // fragment_key: -0.0 + 0.0 == +0.0, everything else unchanged
+                        ++covered;
                     }
-                    __syncwarp();
                 }
+                // apply: plain read-compare-write of (key, id).  Lanes of ONE triangle hit distinct pixels; lanes of different
+                // triangles may meet in a pixel: they then take turns, so the outcome is the lexicographic minimum
+                // whatever the order.
+                bool clash = false;
+                unsigned rank = 0;
+                if (starts >> 1) {
+                    const unsigned peers = __match_any_sync(FULL, frag ? (unsigned)p : 256u + (unsigned)lane);
+                    rank = __popc(peers & lane_lt);
+                    clash = __any_sync(FULL, rank != 0u);
+                }
+                if (!clash) {
+                    if (frag) apply(p, key, gid_e);
+                } else {
+                    const unsigned turns = __reduce_max_sync(FULL, rank);
+                    for (unsigned r = 0; r <= turns; ++r) {
+                        if (frag && rank == r) apply(p, key, gid_e);
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
+        __syncwarp();        // the records and the span list are rewritten by the next batch
     }
-    // write back what changed; statistics as in k_raster
-    unsigned long long zmin = ~0ull;
-    uint32_t touched = 0;
-    #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
-        if (x < f.W && y < f.H) {
-            const size_t gp = (size_t)y * f.W + x;
-            const unsigned long long nk = sm.zk[p];
-            const uint32_t ni = sm.vid[p];
-            if (nk != gz[gp]) { gz[gp] = nk; zmin = min(zmin, nk); }
-            if (ni != gv[gp]) { gv[gp] = ni; ++touched; }
-        }
-    }
+    // A tile without a single covered sample is left alone; otherwise the whole tile is stored (no read-back of the
+    // old values to find out what changed: the loads cost more than the stores of unchanged pixels save)
     covered = __reduce_add_sync(FULL, covered);
     if (covered == 0) return;
     touched = __reduce_add_sync(FULL, touched);
+    if (touched) {
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
+            if (x < f.W && y < f.H) {
+                const size_t gp = (size_t)y * f.W + x;
+                gz[gp] = sm.zk[p];
+                gv[gp] = sm.vid[p];
+            }
+        }
+    }
+    unsigned long long zmin = ((unsigned long long)zmin_hi << 32) | zmin_lo;
     for (int o = 16; o; o >>= 1) zmin = min(zmin, __shfl_xor_sync(FULL, zmin, o));
     if (lane == 0) {
         atomicAdd(&f.stats[view].frag_covered, (unsigned long long)covered);

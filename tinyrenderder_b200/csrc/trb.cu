@@ -586,9 +586,9 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         Launch L(c, "k_raster_warp");
         const dim3 grid((f.ntiles + RW_WARPS - 1) / RW_WARPS, f.nviews);
         switch (c->rw_blocks) {
-            case 6: k_raster_warp<6><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
+            case 8: k_raster_warp<8><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
             case 7: k_raster_warp<7><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
-            default: k_raster_warp<8><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
+            default: k_raster_warp<6><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
         }
     }
     if (long_bins) {         // longer bins: one CTA per tile, persistent grid over the device-side list
