@@ -321,6 +321,18 @@ TRB_EXPORT void TRB_FN(viewport)(int x, int y, int w, int h, double out[16]);
 TRB_EXPORT void TRB_FN(mat4_mul_batch)(const double* a, int n, const double b[16], double* out);
 TRB_EXPORT void TRB_FN(light_dir_eye_batch)(const double* modelviews, int n, const double dir_world[3],
                                             double* out);
+/* Model-level frustum culling, bug-for-bug with the reference (host scalars, no device work).
+ * frustum_planes = Frustum::createFromMatrix (our_gl.cpp:212-261, which reads the planes of the TRANSPOSED matrix):
+ * six planes as {nx, ny, nz, d}, order left, right, bottom, top, near, far.  frustum_intersects = Frustum::intersects
+ * (our_gl.cpp:263-280) -> 1 / 0.  aabb_transform = AABB::transform (geometry.h:297-327: eight corners through the
+ * matrix with the divide by w).  cull_batch answers, for n cameras at once, what main() asks per model:
+ * Frustum::createFromMatrix(Perspective * view[i]).intersects(box) (main.cpp:623-624, 647, 680, 706). */
+TRB_EXPORT void TRB_FN(frustum_planes)(const double view_projection[16], double planes24[24]);
+TRB_EXPORT int TRB_FN(frustum_intersects)(const double planes24[24], const double box_min[3], const double box_max[3]);
+TRB_EXPORT void TRB_FN(aabb_transform)(const double box_min[3], const double box_max[3], const double m[16],
+                                       double out_min[3], double out_max[3]);
+TRB_EXPORT void TRB_FN(cull_batch)(const double perspective[16], const double* views, int n, const double box_min[3],
+                                   const double box_max[3], uint8_t* visible_out);
 /* mat<4,4> * mat<4,4> (geometry.h:195-205) */
 TRB_EXPORT void TRB_FN(mat4_mul)(const double a[16], const double b[16], double out[16]);
 

@@ -737,6 +737,50 @@ void orc_mat4_mul(const double* a, const double* b, double* out) {
     std::memcpy(out, r, sizeof(r));
 }
 
+// Frustum::createFromMatrix / intersects (our_gl.cpp:212-280), AABB::transform (geometry.h:297-327), restated
+void orc_frustum_planes(const double* m, double* planes) {
+    for (int p = 0; p < 6; ++p) {
+        const int c = p / 2;
+        const double s = (p & 1) ? -1.0 : 1.0;
+        double nx = m[3] + s * m[c], ny = m[7] + s * m[4 + c], nz = m[11] + s * m[8 + c], d = m[15] + s * m[12 + c];
+        double len = sqrt(dot3(D3{nx, ny, nz}, D3{nx, ny, nz}));
+        if (len > 0.0) { nx = nx / len; ny = ny / len; nz = nz / len; d /= len; }
+        planes[4 * p] = nx; planes[4 * p + 1] = ny; planes[4 * p + 2] = nz; planes[4 * p + 3] = d;
+    }
+}
+int orc_frustum_intersects(const double* planes, const double* lo, const double* hi) {
+    for (int p = 0; p < 6; ++p) {
+        const double* pl = planes + 4 * p;
+        D3 c{pl[0] >= 0 ? hi[0] : lo[0], pl[1] >= 0 ? hi[1] : lo[1], pl[2] >= 0 ? hi[2] : lo[2]};
+        if (dot3(D3{pl[0], pl[1], pl[2]}, c) + pl[3] < 0) return 0;
+    }
+    return 1;
+}
+void orc_aabb_transform(const double* lo, const double* hi, const double* m, double* out_lo, double* out_hi) {
+    double nlo[3] = {1e9, 1e9, 1e9}, nhi[3] = {-1e9, -1e9, -1e9};
+    for (int i = 0; i < 8; ++i) {
+        const double cx = (i & 1) ? hi[0] : lo[0], cy = (i & 2) ? hi[1] : lo[1], cz = (i & 4) ? hi[2] : lo[2];
+        const double c4[4] = {cx, cy, cz, 1.0};
+        double t[4];
+        for (int r = 0; r < 4; ++r) t[r] = dot4(m + 4 * r, c4);
+        for (int k = 0; k < 3; ++k) {
+            const double v = t[k] / t[3];
+            if (v < nlo[k]) nlo[k] = v;
+            if (nhi[k] < v) nhi[k] = v;
+        }
+    }
+    for (int k = 0; k < 3; ++k) { out_lo[k] = nlo[k]; out_hi[k] = nhi[k]; }
+}
+void orc_mat4_mul(const double* a, const double* b, double* out);
+void orc_cull_batch(const double* perspective, const double* views, int n, const double* lo, const double* hi, uint8_t* out) {
+    for (int v = 0; v < n; ++v) {
+        double vp[16], planes[24];
+        orc_mat4_mul(perspective, views + 16 * v, vp);
+        orc_frustum_planes(vp, planes);
+        out[v] = (uint8_t)orc_frustum_intersects(planes, lo, hi);
+    }
+}
+
 void orc_mat4_mul_batch(const double* a, int n, const double* b, double* out) {
     for (int v = 0; v < n; ++v) orc_mat4_mul(a + 16 * v, b, out + 16 * v);
 }

@@ -739,6 +739,33 @@ void orc_mat4_mul(const double* a, const double* b, double* out) {
     store_mat(load_mat(a) * load_mat(b), out);  // geometry.h:195-205
 }
 
+// the reference's own Frustum / AABB (our_gl.cpp:212-280, geometry.h:272-328)
+void orc_frustum_planes(const double* m, double* planes) {
+    Frustum f = Frustum::createFromMatrix(load_mat(m));
+    for (int p = 0; p < 6; ++p) {
+        planes[4 * p] = f.planes[p].normal.x; planes[4 * p + 1] = f.planes[p].normal.y;
+        planes[4 * p + 2] = f.planes[p].normal.z; planes[4 * p + 3] = f.planes[p].d;
+    }
+}
+int orc_frustum_intersects(const double* planes, const double* lo, const double* hi) {
+    Frustum f;
+    for (int p = 0; p < 6; ++p) {
+        f.planes[p].normal = vec3{planes[4 * p], planes[4 * p + 1], planes[4 * p + 2]};
+        f.planes[p].d = planes[4 * p + 3];
+    }
+    return f.intersects(AABB(v3(lo), v3(hi))) ? 1 : 0;
+}
+void orc_aabb_transform(const double* lo, const double* hi, const double* m, double* out_lo, double* out_hi) {
+    AABB b = AABB(v3(lo), v3(hi)).transform(load_mat(m));
+    for (int k = 0; k < 3; ++k) { out_lo[k] = b.min[k]; out_hi[k] = b.max[k]; }
+}
+void orc_cull_batch(const double* perspective, const double* views, int n, const double* lo, const double* hi, uint8_t* out) {
+    for (int v = 0; v < n; ++v) {
+        Frustum f = Frustum::createFromMatrix(load_mat(perspective) * load_mat(views + 16 * v));   // main.cpp:623-624
+        out[v] = f.intersects(AABB(v3(lo), v3(hi))) ? 1 : 0;
+    }
+}
+
 void orc_mat4_mul_batch(const double* a, int n, const double* b, double* out) {
     for (int v = 0; v < n; ++v) orc_mat4_mul(a + 16 * v, b, out + 16 * v);
 }

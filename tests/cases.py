@@ -310,6 +310,23 @@ def soup_c5(api, r):
     return {"z": r.read_depth(0), "bgr": r.read_color(0)}
 
 
+def orbit_culled(api, r):
+    """model-level frustum cull (main.cpp:623-624, 647, 680, 706; bug-for-bug planes): a batch of three cameras of which
+    two drop the head - and with it the eyes, which main() tests with the head's box - while the third keeps everything"""
+    sc = scenes.orbit_scene(320, 180, room_quads=((32, 16), (32, 8), (16, 16)), tex_size=128)
+    up = scenes.UploadedScene(r, sc)
+    # camera 0 looks straight at the head, and the reference's frustum (planes of the transposed matrix) still drops it
+    cams = [((-1.869, 0.582, -0.816), (0.412, 2.723, -0.129)), ((-3.4019, 2.2001, 1.8026), (1.3555, 1.5116, -0.9686)), ((0, 5, 0), (3, 5, 0))]
+    views = np.stack([api.lookat(e, c, [0.0, 1.0, 0.0]) for e, c in cams])
+    up.render(views, api.perspective(sc.fov, 320 / 180, sc.znear, sc.zfar))
+    assert up.culled == 4, up.culled            # head + eyes for two of the three cameras
+    out = _grab(r, views=3, post=True, stats=False)
+    # the same cameras with the cull switched off draw the head: the test would be vacuous if that changed nothing
+    up.render(views, api.perspective(sc.fov, 320 / 180, sc.znear, sc.zfar), cull=False)
+    assert not np.array_equal(r.read_depth(0).view(np.uint64), out["z_v0"].view(np.uint64))
+    return out
+
+
 def depth_only_then_color(api, r):
     """DEPTH draws write z but no colour; later draws are tested against that z"""
     r.begin_frame(96, 96)
@@ -420,6 +437,7 @@ CASES = {
     "depth_only_then_color": depth_only_then_color, "sub_range_draws": sub_range_draws,
     "snapshot_restore_twice": snapshot_restore_twice,
     "lit_clip_triangles": lit_clip_triangles, "shadow_small": shadow_small, "gouraud_small": gouraud_small,
+    "orbit_culled": orbit_culled,
 }
 FULL_SIZE_CASES = {"k7a": k7a, "k7b": k7b, "k7c": k7c, "head_c1": head_c1, "orbit_mid": orbit_mid,
                    "shadow_c2": shadow_c2, "orbit_c3": orbit_c3, "sphere_c4": sphere_c4}

@@ -90,6 +90,7 @@ def run_example(exe, assets_dir, outdir, *extra):
     out = {n: read_tga(os.path.join(outdir, n + ".tga")) for n in ("phong", "zbuffer", "ao", "final")}
     out["z"] = np.fromfile(os.path.join(outdir, "zbuffer.bin"), dtype=np.float64).reshape(H, W)
     out["stderr"] = res.stderr
+    out["stdout"] = res.stdout
     out["dir"] = outdir
     return out
 
@@ -116,6 +117,26 @@ def test_oracle_build_matches_python_driven_reference(assets, tmp_path, ref_api)
     assert "triangles=" in got["stderr"]
 
 
+# the camera looks straight at the head and the reference's frustum (planes of the transposed matrix) still drops it
+CULL_CAMERA = ["--eye", "-1.869", "0.582", "-0.816", "--target", "0.412", "2.723", "-0.129"]
+
+
+def test_oracle_build_culls_like_the_python_driver(assets, tmp_path, ref_api):
+    """a camera for which main()'s frustum test (the reference's own Frustum in the oracle build) drops the head and
+    the eyes: the Python frame driver (trb_cull_batch) must skip the same models"""
+    need(EXAMPLE_REF)
+    d, sc = assets
+    got = run_example(EXAMPLE_REF, d, str(tmp_path / "ref"), *CULL_CAMERA)
+    assert "frustum sponza 1 head 0" in got["stdout"] and "models rendered 1 culled 1" in got["stdout"]
+    with trb.Renderer(ref_api) as r:
+        up = scenes.UploadedScene(r, sc)
+        view = ref_api.lookat([-1.869, 0.582, -0.816], [0.412, 2.723, -0.129], [0, 1, 0])
+        up.render(view[None], ref_api.perspective(70.0, W / H, 0.05, 500.0))
+        assert up.culled == 2
+        z = r.read_depth()
+    assert np.array_equal(got["z"].view(np.uint64), z.view(np.uint64))
+
+
 def test_tga_writer_is_byte_identical_to_the_reference(assets, tmp_path, built):
     need(TGA_TOOL_REF)
     d, _ = assets
@@ -140,13 +161,17 @@ def test_tga_writer_is_byte_identical_to_the_reference(assets, tmp_path, built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [[], ["--immediate"]])
+@pytest.mark.parametrize("mode", [[], ["--immediate"], CULL_CAMERA])
 def test_device_build_matches_oracle_build(assets, tmp_path, mode):
-    """the same example source: device build (libtrb.so) vs oracle build (the reference's our_gl.cpp)"""
+    """the same example source: device build (libtrb.so) vs oracle build (the reference's our_gl.cpp); the third
+    variant uses a camera whose frustum test drops the head and the eyes (main.cpp:680, 706)"""
     need(EXAMPLE_REF)
     d, _ = assets
-    want = run_example(EXAMPLE_REF, d, str(tmp_path / "ref"))
+    cam = mode if mode == CULL_CAMERA else []
+    want = run_example(EXAMPLE_REF, d, str(tmp_path / "ref"), *cam)
     got = run_example(EXAMPLE, d, str(tmp_path / "dev"), *mode)
+    assert [l for l in got["stdout"].splitlines() if l.startswith(("frustum", "models"))] == \
+           [l for l in want["stdout"].splitlines() if l.startswith(("frustum", "models"))]
     assert np.array_equal(got["z"].view(np.uint64), want["z"].view(np.uint64))
     assert np.array_equal(got["ao"], want["ao"]) and np.array_equal(got["zbuffer"], want["zbuffer"])
     for k in ("phong", "final"):

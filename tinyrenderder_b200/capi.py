@@ -148,6 +148,10 @@ SIGNATURES = {
     "mat4_mul": (None, [_P, _P, _P]),
     "mat4_mul_batch": (None, [_P, C.c_int, _P, _P]),
     "light_dir_eye_batch": (None, [_P, C.c_int, _P, _P]),
+    "frustum_planes": (None, [_P, _P]),
+    "frustum_intersects": (C.c_int, [_P, _P, _P]),
+    "aabb_transform": (None, [_P, _P, _P, _P, _P]),
+    "cull_batch": (None, [_P, _P, C.c_int, _P, _P, _P]),
 }
 
 
@@ -215,6 +219,27 @@ class Api:
         out = np.empty((n, 3))
         self.fn["light_dir_eye_batch"](_ptr(mv), n, _ptr(_f64(dir_world, 3)), _ptr(out))
         return out
+
+    # model-level frustum culling, bug-for-bug (our_gl.cpp:212-280, geometry.h:297-327) ----
+    def frustum_planes(self, view_projection):
+        out = np.empty(24)
+        self.fn["frustum_planes"](_ptr(_f64(view_projection, 16)), _ptr(out))
+        return out.reshape(6, 4)
+
+    def frustum_intersects(self, planes, box_min, box_max):
+        return bool(self.fn["frustum_intersects"](_ptr(_f64(planes, 24)), _ptr(_f64(box_min, 3)), _ptr(_f64(box_max, 3))))
+
+    def aabb_transform(self, box_min, box_max, m):
+        lo, hi = np.empty(3), np.empty(3)
+        self.fn["aabb_transform"](_ptr(_f64(box_min, 3)), _ptr(_f64(box_max, 3)), _ptr(_f64(m, 16)), _ptr(lo), _ptr(hi))
+        return lo, hi
+
+    def cull_batch(self, perspective, views, box_min, box_max):
+        v = _f64(views)
+        n = v.size // 16
+        out = np.empty(n, dtype=np.uint8)
+        self.fn["cull_batch"](_ptr(_f64(perspective, 16)), _ptr(v), n, _ptr(_f64(box_min, 3)), _ptr(_f64(box_max, 3)), _ptr(out))
+        return out.astype(bool)
 
     def light_dir_eye(self, modelview, dir_world):
         out = np.empty(3)

@@ -287,6 +287,9 @@ struct TrbCtx {
     uint32_t warp_max = WARP_MAX_DEFAULT;
     int rw_blocks = RW_BLOCKS_DEFAULT;   // k_raster_warp instantiation (resident CTAs per SM the registers are sized for)
     bool shade_exact = false;   // true: all-fp64 lighting (exact.cuh); false: fp32 lighting (fastshade.cuh)
+    bool foreign_ids = false;   // trb_set_triangle_id_base was used: the id plane may hold winners other ranks rasterised
+    bool shade_rec = true;      // dense fp32-lit flushes shade per visible triangle (TRB_SHADE_REC=0: everything per pixel)
+    DevBuf shade_flags, shade_recs;
 };
 
 namespace {
@@ -447,7 +450,37 @@ int do_flush(TrbCtx* c) {
                 default: k_shade<true, true><<<grid, TPB, 0, c->stream>>>(f, table, nd, list); break;
             }
         }
-        {   // dense views only
+        // dense views of fp32-lit flushes: per-triangle work once per visible triangle (k_shade_mark / build / rec).
+        // The record table is indexed by triangle id: frames whose ids x views would need more than 6 GB of it
+        // (configs 4 and 5, sparse anyway) keep the per-pixel kernels
+        const uint64_t nids = c->next_id + 1;
+        const bool by_rec = variant == 1 && c->shade_rec && !c->foreign_ids && nids * (uint64_t)f.nviews * sizeof(ShadeRec) <= (6ull << 30) &&
+                            nd <= SHADE_MAX_SM_DRAWS;
+        if (by_rec) {
+            const size_t flag_bytes = (size_t)nids * f.nviews;
+            if (c->shade_flags.cap < flag_bytes) {          // a fresh table: all flags down
+                CU(c->shade_flags.ensure(flag_bytes, c->stream));
+                CU(cudaMemsetAsync(c->shade_flags.p, 0, c->shade_flags.cap, c->stream));
+            }
+            CU(c->shade_recs.ensure((size_t)nids * f.nviews * sizeof(ShadeRec), c->stream));
+            uint8_t* flags = c->shade_flags.as<uint8_t>();
+            ShadeRec* recs = c->shade_recs.as<ShadeRec>();
+            {
+                const dim3 grid(blocks_for((n + 3) / 4), f.nviews);
+                Launch L(c, "k_shade_mark");
+                k_shade_mark<<<grid, TPB, 0, c->stream>>>(f, r0, r1, flags, (uint32_t)nids);
+            }
+            for (int d = 0; d < nd; ++d) {
+                const DrawDev& D = c->draws[d];
+                if (D.ntris == 0) continue;
+                Launch L(c, "k_shade_build");
+                k_shade_build<<<dim3(blocks_for(D.ntris), f.nviews), TPB, 0, c->stream>>>(f, D, d, flags, (uint32_t)nids, recs);
+            }
+            {
+                Launch L(c, "k_shade_rec");
+                k_shade_rec<<<dim3(blocks_for(n), f.nviews), TPB, 0, c->stream>>>(f, table, nd, r0, r1, (uint32_t)nids, recs);
+            }
+        } else {   // dense views only
 #if TRB_SHADE_2D
             const dim3 grid((unsigned)(((f.W + 31) / 32) * ((r1 - r0 + 7) / 8)), f.nviews);
 #else
@@ -706,6 +739,7 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_WARP_MAX")) c->warp_max = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("TRB_RW_BLOCKS")) c->rw_blocks = atoi(e);
     if (const char* e = getenv("TRB_SHADE_EXACT")) c->shade_exact = atoi(e) != 0;
+    if (const char* e = getenv("TRB_SHADE_REC")) c->shade_rec = atoi(e) != 0;
     if (const char* e = getenv("TRB_SYNC_DRAWS")) c->sync_draws = atoi(e) != 0;
     if (const char* e = getenv("TRB_BIN_CAP")) c->bin_cap_fixed = (uint32_t)std::max(1, atoi(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -741,7 +775,7 @@ int trb_destroy(TrbCtx* c) {
         if (t.alive) cudaFree(t.px);
     DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
                       &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->ctl, &c->heavy_list, &c->direct_list, &c->direct_n, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
-                      &c->scratch_b};
+                      &c->scratch_b, &c->shade_flags, &c->shade_recs};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.keys.release();
     for (auto& b : c->shadow_pool) b.release();
@@ -1007,6 +1041,7 @@ int trb_begin_batch(TrbCtx* c, int w, int h, int nviews) {
     c->arena.reset();
     ++c->cache.frame;
     c->next_id = 0;
+    c->foreign_ids = false;
     c->tris_submitted = 0;
     c->have_snapshot = false;
     c->snap_stale = false;
@@ -1665,6 +1700,7 @@ int trb_device_planes(TrbCtx* c, uint64_t* key_ptr, uint64_t* vis_ptr, uint64_t*
 int trb_set_triangle_id_base(TrbCtx* c, uint64_t base) {
     if (!c || base >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "set_triangle_id_base");
     c->next_id = base;
+    c->foreign_ids = true;
     return TRB_OK;
 }
 // The host all-reduces (min) the depth-key plane in place as int64; keys are made signed-sortable
@@ -1863,6 +1899,56 @@ void trb_viewport(int x, int y, int w, int h, double* out) {
     out[7] = y + h / 2.0;
     out[10] = 1.0;
     out[11] = 0.0;
+}
+void trb_frustum_planes(const double* m, double* planes) {
+    // our_gl.cpp:212-261: plane k reads m[r][3] +- m[r][col] for r = 0..2 and m[3][3] +- m[3][col] (sic: transposed)
+    static const int col[6] = {0, 0, 1, 1, 2, 2};
+    static const double sgn[6] = {1, -1, 1, -1, 1, -1};
+    for (int p = 0; p < 6; ++p) {
+        D3 n{m[3] + sgn[p] * m[col[p]], m[7] + sgn[p] * m[4 + col[p]], m[11] + sgn[p] * m[8 + col[p]]};
+        double d = m[15] + sgn[p] * m[12 + col[p]];
+        const double len = sqrt(dot3(n, n));                     // norm(), geometry.h:131-133
+        if (len > 0.0) {
+            n = D3{n.x / len, n.y / len, n.z / len};             // vec / double, geometry.h:113-118
+            d /= len;
+        }
+        planes[4 * p] = n.x; planes[4 * p + 1] = n.y; planes[4 * p + 2] = n.z; planes[4 * p + 3] = d;
+    }
+}
+int trb_frustum_intersects(const double* planes, const double* lo, const double* hi) {
+    // our_gl.cpp:263-280
+    for (int p = 0; p < 6; ++p) {
+        const double* pl = planes + 4 * p;
+        D3 far_corner{lo[0], lo[1], lo[2]};
+        if (pl[0] >= 0) far_corner.x = hi[0];
+        if (pl[1] >= 0) far_corner.y = hi[1];
+        if (pl[2] >= 0) far_corner.z = hi[2];
+        if (dot3(D3{pl[0], pl[1], pl[2]}, far_corner) + pl[3] < 0) return 0;   // Plane::distance, geometry.h:266-268
+    }
+    return 1;
+}
+void trb_aabb_transform(const double* lo, const double* hi, const double* m, double* out_lo, double* out_hi) {
+    // geometry.h:297-327
+    double nlo[3] = {1e9, 1e9, 1e9}, nhi[3] = {-1e9, -1e9, -1e9};
+    for (int i = 0; i < 8; ++i) {
+        const double cx = (i & 1) ? hi[0] : lo[0], cy = (i & 2) ? hi[1] : lo[1], cz = (i & 4) ? hi[2] : lo[2];
+        const double t[4] = {dot4(m, cx, cy, cz, 1.0), dot4(m + 4, cx, cy, cz, 1.0), dot4(m + 8, cx, cy, cz, 1.0),
+                             dot4(m + 12, cx, cy, cz, 1.0)};
+        for (int k = 0; k < 3; ++k) {
+            const double v = t[k] / t[3];
+            nlo[k] = std::min(nlo[k], v);
+            nhi[k] = std::max(nhi[k], v);
+        }
+    }
+    for (int k = 0; k < 3; ++k) { out_lo[k] = nlo[k]; out_hi[k] = nhi[k]; }
+}
+void trb_cull_batch(const double* perspective, const double* views, int n, const double* lo, const double* hi, uint8_t* out) {
+    for (int v = 0; v < n; ++v) {
+        double vp[16], planes[24];
+        trb_mat4_mul(perspective, views + 16 * v, vp);           // main.cpp:623
+        trb_frustum_planes(vp, planes);
+        out[v] = (uint8_t)trb_frustum_intersects(planes, lo, hi);
+    }
 }
 void trb_mat4_mul(const double* a, const double* b, double* out) {
     // geometry.h:195-205

@@ -250,7 +250,7 @@ class DrawItem:
     """One model of the frame: what main.cpp:647-669 sets up around a face loop."""
 
     def __init__(self, mesh, model_matrix, kind, textures=None, normal_map_strength=1.0,
-                 snapshot_before=False, restore_after=False):
+                 snapshot_before=False, restore_after=False, cull_with=None):
         self.mesh = mesh
         self.model_matrix = np.asarray(model_matrix, dtype=np.float64)
         self.kind = kind
@@ -258,6 +258,7 @@ class DrawItem:
         self.normal_map_strength = normal_map_strength
         self.snapshot_before = snapshot_before
         self.restore_after = restore_after
+        self.cull_with = cull_with     # index of the item whose box decides this item's visibility (None: its own)
 
 
 class Scene:
@@ -270,6 +271,33 @@ class Scene:
     @property
     def ntris(self):
         return sum(it.mesh.ntris for it in self.items)
+
+
+# --------------------------------------------------------------------------------------------
+# model-level frustum culling, bug-for-bug (our_gl.cpp:212-280, geometry.h:297-327, model.cpp:15-40):
+# host scalars, plain Python floats in the reference's operation order
+# --------------------------------------------------------------------------------------------
+def local_aabb(mesh):
+    """Model::computeAABB: min / max over the vertices widened by 1 % of the extent on every side"""
+    pos = np.asarray(mesh.pos, dtype=np.float64)
+    lo, hi = pos.min(axis=0), pos.max(axis=0)
+    margin = (hi - lo) * 0.01
+    return lo - margin, hi + margin
+
+
+def visible_items(scene, views, perspective, api):
+    """Which models main() would draw for each camera (main.cpp:623-624, 647, 680, 706): bool array (items, views),
+    through the backend's host helpers (trb_aabb_transform / trb_cull_batch: the reference's Frustum, bug-for-bug).
+    An item with `cull_with` set is tested with THAT item's box and only drawn when that item is: main.cpp:706 tests
+    the head's box for the eyes (sic) inside the head's own block."""
+    out = []
+    for it in scene.items:
+        src = scene.items[it.cull_with] if it.cull_with is not None else it
+        if getattr(src, "_world_aabb", None) is None:
+            lo, hi = local_aabb(src.mesh)
+            src._world_aabb = api.aabb_transform(lo, hi, src.model_matrix)     # Model::getWorldAABB, model.h:99
+        out.append(api.cull_batch(perspective, views, *src._world_aabb))
+    return np.stack(out)
 
 
 class UploadedScene:
@@ -298,20 +326,28 @@ class UploadedScene:
             self.r.free_texture(h)
         self.mesh_h, self.tex_h = {}, {}
 
-    def render(self, views, perspective):
-        """views: (n,4,4) view matrices.  Mirrors main.cpp:606-730 for every view: begin frame,
-        per model ModelView = view*model (main.cpp:653), light directions through the upper-left
-        3x3 (main.cpp:55-69), face loop -> one draw call, z snapshot/restore around the eyes
-        (main.cpp:700,730)."""
+    def render(self, views, perspective, cull=True):
+        """views: (n,4,4) view matrices.  Mirrors main.cpp:606-730 for every view: begin frame, the model-level
+        frustum test (main.cpp:623-624, 647, 680, 706; bug-for-bug), per model ModelView = view*model
+        (main.cpp:653), light directions through the upper-left 3x3 (main.cpp:55-69), face loop -> one draw
+        call, z snapshot/restore around the eyes (main.cpp:700,730)."""
         r, sc, api = self.r, self.scene, self.r.api
         views = np.asarray(views, dtype=np.float64).reshape(-1, 4, 4)
         n = views.shape[0]
         r.begin_frame(sc.width, sc.height, nviews=n)
         key, fill, rim = normalized(KEY_LIGHT), normalized(FILL_LIGHT), normalized(RIM_LIGHT)
-        for it in sc.items:
+        seen = visible_items(sc, views, perspective, api) if cull else None
+        self.culled = 0 if seen is None else int((~seen).sum())
+        for i, it in enumerate(sc.items):
+            if seen is not None and not seen[i].any():
+                continue                                  # culled for every camera of the batch: the block is skipped
             if it.snapshot_before:
                 r.depth_snapshot()
             mvs = api.mat4_mul_batch(views, it.model_matrix)
+            if seen is not None and not seen[i].all():
+                # a batch draws into every frame: cameras that cull the model get a ModelView of zeros, which sends
+                # every vertex to w = 0 and every triangle to the reject of our_gl.cpp:94 - nothing is drawn there
+                mvs = np.where(seen[i][:, None, None], mvs, 0.0)
             uni = None
             if it.kind in (SHADER_PHONG, SHADER_EYE):
                 # PhongUniforms for every view, filled through a numpy view of the ctypes array
@@ -368,7 +404,7 @@ def orbit_scene(width=1920, height=1080, room_quads=((256, 128), (256, 64), (128
     t_eye = {"diffuse": texture_diffuse(256, 31)}
     items = [DrawItem(room, scale_matrix(0.014), SHADER_PHONG, t_room, 0.5),
              DrawItem(head, head_m, SHADER_PHONG, t_head, 1.0),
-             DrawItem(eyes, head_m, SHADER_EYE, t_eye, 1.0, snapshot_before=True, restore_after=True)]
+             DrawItem(eyes, head_m, SHADER_EYE, t_eye, 1.0, snapshot_before=True, restore_after=True, cull_with=1)]
     return Scene(name, width, height, items, 70.0, 0.05, 500.0)
 
 
