@@ -385,7 +385,13 @@ def measure(args, env, workload, steps, warmup, primary, composite="p2p"):
         torch.cuda.synchronize()
 
     sharded_c4 = wl.name == "c4" and world > 1
-    p2p = multigpu.P2PComposite(r, dist, rank, world) if sharded_c4 and composite == "p2p" else None
+    def gather_objects(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    # composite group of the C ABI: IPC blobs exchanged once, then no host barrier per frame (trb_composite)
+    p2p = multigpu.CommComposite(r, gather_objects, rank, world) if sharded_c4 and composite == "p2p" else None
     rows = multigpu.row_shard(wl.height, rank, world) if sharded_c4 else None
 
     def frames_of(s):
@@ -402,11 +408,13 @@ def measure(args, env, workload, steps, warmup, primary, composite="p2p"):
         it = wl.scene.items[0]
         first, count = multigpu.triangle_shard(it.mesh.ntris, rank, world)
         r.begin_frame(wl.width, wl.height)
+        if p2p is not None and not p2p.opened:
+            p2p.open()                    # once: the planes of this frame size are exported to the peers
         r.set_triangle_id_base(first)
         mv = api.mat4_mul(wl.views(api, s, rank, world)[0], it.model_matrix)
         r.draw(up.mesh_h[id(it.mesh)], mv, wl.perspective, kind=it.kind, first_tri=first, ntris=count)
         if composite == "p2p":
-            p2p.run(wl.height)            # fused NVLink composite + shade of the owned rows
+            p2p.run()                     # fused NVLink composite + shade of the owned rows, stream-ordered against the peers
         else:
             multigpu.composite(r, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MIN))
             r.set_shade_rows(*rows)
@@ -594,7 +602,7 @@ def measure(args, env, workload, steps, warmup, primary, composite="p2p"):
                      "lighting of the lit shaders in f32 (within 1 LSB, asserted by tests and parity_check)",
         "config": {"workload": wl.label, "frames_per_step_per_gpu": nviews, "width": wl.width, "height": wl.height,
                    "triangles_per_frame": T, "l2": "inputs larger than L2 (depth+id+colour planes of one step = %d MB)"
-                   % (nviews * P * 15 // 2 ** 20), "parallelism": ("triangle ranges + %s sort-last composite" % ("fused NVLink P2P" if composite == "p2p" else "NCCL")
+                   % (nviews * P * 15 // 2 ** 20), "parallelism": ("triangle ranges + %s sort-last composite" % ("fused NVLink P2P (trb_composite: device-side frame counters, no host barrier)" if composite == "p2p" else "NCCL all-reduces")
                                    if sharded_c4 else
                                    "frames sharded, no collective") if world > 1 else "1 GPU"},
         "fragments_per_s": frag * (1 if sharded_c4 else world) * steps / (ms_max * 1e-3),

@@ -225,6 +225,13 @@ enum TrbImage {
  * (width*height*bpp + width*height/2 + 19 always suffices:
  * the shortest packet the encoder emits away from the image end is a raw packet of two pixels).  Synchronises. */
 TRB_EXPORT int TRB_FN(encode_tga)(TrbCtx* ctx, int which, uint8_t* const* out, uint64_t capacity, uint64_t* sizes);
+/* The asynchronous frame writer (what a 1024-frame orbit that ends in framebuffer.write_tga_file, main.cpp:743, needs):
+ * same output as trb_encode_tga, but the call only queues work.  The packets are built behind the frame on the
+ * context's stream; the per-view sizes travel to pinned host memory and, as soon as the host has them - at the latest
+ * inside the next trb_encode_tga_async or trb_readback_wait - the packets follow on the copy stream, overlapping the
+ * rendering of the next frames.  out[v] (page-locked for real overlap) and sizes[v] must stay valid and untouched until
+ * trb_readback_wait returns; two encodes may be in flight, a third call first waits for the oldest. */
+TRB_EXPORT int TRB_FN(encode_tga_async)(TrbCtx* ctx, int which, uint8_t* const* out, uint64_t capacity, uint64_t* sizes);
 
 /* ---- readback ------------------------------------------------------------------------ */
 /* framebuffer bytes, BGR, (x+y*w)*3 like TGAImage(w,h,RGB) (tgaimage.cpp:32-39) */
@@ -302,6 +309,32 @@ TRB_EXPORT int TRB_FN(open_peers_raw)(TrbCtx* ctx, const uint64_t* key_ptrs, con
                                       int my_rank);
 TRB_EXPORT int TRB_FN(ipc_close_peers)(TrbCtx* ctx);
 TRB_EXPORT int TRB_FN(composite_shade_p2p)(TrbCtx* ctx, int y0, int y1);
+/* ---- composite groups: trb_comm_init(ctx[], n) / trb_composite(ctx) of SURVEY 8(b) -----------------------
+ * The fused NVLink composite above without any host-side barrier.  A group is n ranks (one context each) that
+ * render triangle ranges of ONE picture; every member must have begun a single-view frame of the final size before the
+ * group is formed, and keeps that size while the group exists.
+ *   one process, n contexts (one per GPU, or several on one GPU):   trb_comm_init(ctxs, n)
+ *   one process per rank:   trb_comm_export(ctx, blob)  ->  exchange the TRB_COMM_BLOB_BYTES-byte blobs by any means
+ *                           (MPI, files, torch.distributed) into an array ordered by rank  ->  trb_comm_open(ctx, blobs, n, rank)
+ * Per frame every rank: trb_begin_frame, trb_comm_shard -> trb_set_triangle_id_base(first) + trb_draw(first, count)
+ * (ids stay global, so ties resolve like one sequential submission, our_gl.cpp:165), then trb_composite(ctx): the
+ * rank's stream publishes "drawn" in a counter in its own HBM, waits (a one-thread kernel) until every peer has
+ * published the same frame, runs ONE kernel that reads the n candidate (depth key, id) pairs of each pixel of the rows
+ * trb_comm_rows gives it straight from the peers' HBM, keeps the exact lexicographic minimum and shades it, and
+ * publishes "done reading"; the next trb_begin_frame waits for the peers' "done" before it clears the planes.  No call
+ * blocks the host; trb_read_color etc. of the owned rows are stream ordered as usual.  A peer that stays silent for
+ * 20 s makes the next call fail with TRB_E_COMM instead of hanging the GPU.
+ * Contexts that share a GPU (tests, small machines) cannot wait for each other with kernels: composite them with
+ * trb_composite_group(ctxs, n), which orders the streams with events - one host thread, all members in one call. */
+#define TRB_COMM_BLOB_BYTES 256
+TRB_EXPORT int TRB_FN(comm_init)(TrbCtx* const* ctxs, int n);
+TRB_EXPORT int TRB_FN(comm_export)(TrbCtx* ctx, void* blob, size_t blob_bytes);
+TRB_EXPORT int TRB_FN(comm_open)(TrbCtx* ctx, const void* blobs, int n, int rank);
+TRB_EXPORT int TRB_FN(comm_close)(TrbCtx* ctx);
+TRB_EXPORT int TRB_FN(comm_shard)(TrbCtx* ctx, uint64_t total_triangles, uint64_t* first, uint64_t* count);
+TRB_EXPORT int TRB_FN(comm_rows)(TrbCtx* ctx, int* y0, int* y1);
+TRB_EXPORT int TRB_FN(composite)(TrbCtx* ctx);
+TRB_EXPORT int TRB_FN(composite_group)(TrbCtx* const* ctxs, int n);
 /* restrict flush to rows [y0,y1) (the screen slice this rank owns after the composite) */
 TRB_EXPORT int TRB_FN(set_shade_rows)(TrbCtx* ctx, int y0, int y1);
 

@@ -673,6 +673,14 @@ int orc_ipc_open_peers(TrbCtx* c, const void*, const void*, int, int) { return f
 int orc_open_peers_raw(TrbCtx* c, const uint64_t*, const uint64_t*, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_ipc_close_peers(TrbCtx* c) { return c ? TRB_OK : TRB_E_ARG; }
 int orc_composite_shade_p2p(TrbCtx* c, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_comm_init(TrbCtx* const*, int) { return TRB_E_COMM; }
+int orc_comm_export(TrbCtx* c, void*, size_t) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_comm_open(TrbCtx* c, const void*, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_comm_close(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_comm_shard(TrbCtx* c, uint64_t, uint64_t*, uint64_t*) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_comm_rows(TrbCtx* c, int*, int*) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_composite(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
+int orc_composite_group(TrbCtx* const*, int) { return TRB_E_COMM; }
 int orc_set_shade_rows(TrbCtx* c, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 
 // ---- host helpers ------------------------------------------------------------------------

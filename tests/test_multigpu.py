@@ -195,3 +195,149 @@ def test_fused_p2p_composite_shade_on_one_gpu(cuda_api, port_api, nranks):
         assert np.abs(color.astype(int) - o.read_color().astype(int)).max() <= 1
     for r in rs:
         r.close()
+
+
+def _shard_frame(api, r, mesh, ntris, first, count, mv, pr, tex_handle):
+    u = trb.PhongUniforms()
+    u.key_dir_eye[:] = api.light_dir_eye(mv, scenes.normalized(scenes.KEY_LIGHT))
+    u.fill_dir_eye[:] = api.light_dir_eye(mv, scenes.normalized(scenes.FILL_LIGHT))
+    u.rim_dir_eye[:] = api.light_dir_eye(mv, scenes.normalized(scenes.RIM_LIGHT))
+    u.normal_map_strength = 0.0
+    u.diffuse = tex_handle
+    r.set_triangle_id_base(first)
+    r.draw(mesh, mv, pr, kind=trb.SHADER_PHONG, uniforms=u, first_tri=first, ntris=count)
+
+
+def _unsharded(port_api, m, idx, ntris, mv, pr, tex, w, h):
+    with trb.Renderer(port_api) as o:
+        mesh = o.upload_mesh(m.pos, m.nrm, m.uv, idx)
+        o.begin_frame(w, h)
+        _shard_frame(port_api, o, mesh, ntris, 0, ntris, mv, pr, o.upload_texture(tex))
+        o.end_frame()
+        return o.read_depth().copy(), o.read_color().copy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_composite_group_on_one_gpu(cuda_api, port_api, nranks):
+    """trb_comm_init + trb_composite_group: N contexts of one process (sharing the GPU) as ranks, three frames in a row
+    with a moving camera and NO host synchronisation between them - the streams are ordered by events: a rank's clear of
+    frame k+1 waits for every peer's composite of frame k.  Each frame equals the unsharded render."""
+    m = scenes.icosphere(5)
+    w, h = 640, 400
+    pr = cuda_api.perspective(60, w / h, 0.1, 10)
+    idx = np.concatenate([m.idx, m.idx])          # duplicates: exact depth ties across ranks
+    ntris = idx.size // 3
+    tex = scenes.texture_diffuse(64, 3)
+    rs = [trb.Renderer(cuda_api) for _ in range(nranks)]
+    meshes = [r.upload_mesh(m.pos, m.nrm, m.uv, idx) for r in rs]
+    texes = [r.upload_texture(tex) for r in rs]
+    for r in rs:
+        r.begin_frame(w, h)
+    trb.comm_init(rs)
+    cams = [[0.0, 0.0, 2.2], [0.7, 0.3, 2.0], [-0.5, 0.9, 1.9]]
+    outs = []
+    for cam in cams:
+        mv = cuda_api.lookat(cam, [0, 0, 0], [0, 1, 0])
+        for rank, r in enumerate(rs):
+            r.begin_frame(w, h)
+            first, count = r.comm_shard(ntris)
+            assert (first, count) == multigpu.triangle_shard(ntris, rank, nranks)
+            _shard_frame(cuda_api, r, meshes[rank], ntris, first, count, mv, pr, texes[rank])
+        trb.composite_group(rs)
+        # read-backs are queued behind the composite on each rank's stream; nothing else synchronises
+        color = np.zeros((h, w, 3), np.uint8)
+        depth = np.zeros((h, w))
+        for rank, r in enumerate(rs):
+            y0, y1 = r.comm_rows()
+            assert (y0, y1) == multigpu.row_shard(h, rank, nranks)
+            color[y0:y1] = r.read_color()[y0:y1]
+            depth[y0:y1] = r.read_depth()[y0:y1]
+        outs.append((depth, color))
+    for cam, (depth, color) in zip(cams, outs):
+        zo, co = _unsharded(port_api, m, idx, ntris, port_api.lookat(cam, [0, 0, 0], [0, 1, 0]), pr, tex, w, h)
+        assert np.array_equal(depth.view(np.uint64), zo.view(np.uint64))
+        assert np.abs(color.astype(int) - co.astype(int)).max() <= 1
+    with pytest.raises(trb.TrbError):             # contexts that share a device must be composited as a group
+        rs[0].composite()
+    with pytest.raises(trb.TrbError):             # the frame size is part of the group
+        rs[0].begin_frame(w // 2, h)
+    for r in rs:
+        r.close()
+
+
+def _ipc_rank(rank, world, out_dir):
+    """one process per GPU: blobs exchanged through files, then frames without any host barrier"""
+    import time
+    sys.path.insert(0, ROOT)
+    api = trb.load_cuda()
+    m = scenes.icosphere(6)
+    w, h = 960, 600
+    pr = api.perspective(60, w / h, 0.1, 10)
+    idx = np.concatenate([m.idx, m.idx])
+    ntris = idx.size // 3
+    tex = scenes.texture_diffuse(64, 3)
+    with trb.Renderer(api, rank) as r:
+        mesh, th = r.upload_mesh(m.pos, m.nrm, m.uv, idx), r.upload_texture(tex)
+        r.begin_frame(w, h)
+
+        def all_gather(blob):
+            with open(os.path.join(out_dir, "blob%d.tmp" % rank), "wb") as f:
+                f.write(blob)
+            os.rename(os.path.join(out_dir, "blob%d.tmp" % rank), os.path.join(out_dir, "blob%d" % rank))
+            blobs = []
+            for k in range(world):
+                p = os.path.join(out_dir, "blob%d" % k)
+                t0 = time.time()
+                while not os.path.exists(p):
+                    if time.time() - t0 > 60:
+                        raise RuntimeError("rank %d never exported" % k)
+                    time.sleep(0.01)
+                blobs.append(open(p, "rb").read())
+            return blobs
+
+        comm = multigpu.CommComposite(r, all_gather, rank, world)
+        comm.open()
+        res = []
+        for k, cam in enumerate([[0.0, 0.0, 2.2], [0.7, 0.3, 2.0], [-0.5, 0.9, 1.9], [0.1, -0.8, 2.1]]):
+            if rank == 1 and k == 2:
+                time.sleep(0.3)                   # a straggler: the peers' streams wait on the device, not the hosts
+            mv = api.lookat(cam, [0, 0, 0], [0, 1, 0])
+            r.begin_frame(w, h)
+            first, count = comm.shard(ntris)
+            _shard_frame(api, r, mesh, ntris, first, count, mv, pr, th)
+            y0, y1 = comm.run()
+            res.append((y0, r.read_depth()[y0:y1].copy(), r.read_color()[y0:y1].copy()))
+        np.save(os.path.join(out_dir, "rank%d.npy" % rank), np.array(res, dtype=object), allow_pickle=True)
+        r.synchronize()
+        # nobody may tear its planes down while a peer still reads them: wait for every rank's result file
+        t0 = time.time()
+        while not all(os.path.exists(os.path.join(out_dir, "rank%d.npy" % k)) for k in range(world)):
+            if time.time() - t0 > 60:
+                break
+            time.sleep(0.01)
+        r.comm_close()
+
+
+@pytest.mark.gpu
+def test_composite_across_processes_without_host_barriers(port_api, tmp_path):
+    """trb_comm_export / trb_comm_open / trb_composite with one PROCESS per GPU (CUDA IPC): four frames in a row, one
+    rank deliberately late - frame counters in device memory keep the ranks in step.  Needs >= 2 GPUs."""
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least two GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    mp.spawn(_ipc_rank, args=(world, str(tmp_path)), nprocs=world, join=True)
+    m = scenes.icosphere(6)
+    w, h = 960, 600
+    pr = port_api.perspective(60, w / h, 0.1, 10)
+    idx = np.concatenate([m.idx, m.idx])
+    tex = scenes.texture_diffuse(64, 3)
+    parts = [np.load(tmp_path / ("rank%d.npy" % k), allow_pickle=True) for k in range(world)]
+    for k, cam in enumerate([[0.0, 0.0, 2.2], [0.7, 0.3, 2.0], [-0.5, 0.9, 1.9], [0.1, -0.8, 2.1]]):
+        zo, co = _unsharded(port_api, m, idx, idx.size // 3, port_api.lookat(cam, [0, 0, 0], [0, 1, 0]), pr, tex, w, h)
+        for part in parts:
+            y0, z, c = part[k]
+            assert np.array_equal(z.view(np.uint64), zo[y0:y0 + z.shape[0]].view(np.uint64)), (k, y0)
+            assert np.abs(c.astype(int) - co[y0:y0 + c.shape[0]].astype(int)).max() <= 1

@@ -227,3 +227,39 @@ def test_device_encoder_holds_its_packet_offset_invariants(built, port_api):
     a, b = encode_with(trb.Api(p, "trb"), IMAGES), encode_with(port_api, IMAGES)
     for name in IMAGES:
         assert a[name] == b[name], name
+
+
+@pytest.mark.gpu
+def test_async_frame_writer_equals_the_blocking_one(cuda_api):
+    """trb_encode_tga_async in a frame loop that never synchronises (two encodes in flight, packets travelling on the
+    copy stream while the next batch renders): after readback_wait every file equals trb_encode_tga's"""
+    import torch
+    from tinyrenderder_b200 import scenes
+    sc = scenes.orbit_scene(320, 180, room_quads=((16, 8), (16, 4), (8, 8)), tex_size=64)
+    pr = cuda_api.perspective(sc.fov, 320 / 180, sc.znear, sc.zfar)
+    steps = [[7 * k + 1, 7 * k + 300, 7 * k + 700] for k in range(5)]
+    with trb.Renderer(cuda_api) as r:
+        up = scenes.UploadedScene(r, sc)
+        want = []
+        for ids in steps:
+            up.render(scenes.orbit_views(cuda_api, ids), pr)
+            want.append(r.encode_tga(capi.IMAGE_COLOR))
+        cap = 320 * 180 * 3 + 320 * 180 // 2 + 64
+        bufs = [[torch.empty(cap, dtype=torch.uint8).pin_memory().numpy() for _ in range(3)] for _ in steps]
+        sizes = [np.zeros(3, dtype=np.uint64) for _ in steps]
+        for k, ids in enumerate(steps):           # no synchronising call inside the loop
+            up.render(scenes.orbit_views(cuda_api, ids), pr)
+            r.encode_tga_async(bufs[k], sizes[k], capi.IMAGE_COLOR)
+        r.readback_wait()
+        for k in range(len(steps)):
+            for v in range(3):
+                assert bufs[k][v][:int(sizes[k][v])].tobytes() == want[k][v], (k, v)
+        # the other images through the same path, and a wait with nothing in flight is harmless
+        up.render(scenes.orbit_views(cuda_api, steps[0]), pr)
+        for which in (capi.IMAGE_DEPTH, capi.IMAGE_SSAO, capi.IMAGE_FINAL):
+            ref = r.encode_tga(which)
+            r.encode_tga_async(bufs[0], sizes[0], which)
+            r.readback_wait()
+            for v in range(3):
+                assert bufs[0][v][:int(sizes[0][v])].tobytes() == ref[v], (which, v)
+        r.readback_wait()

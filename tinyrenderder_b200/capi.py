@@ -117,6 +117,7 @@ SIGNATURES = {
     "depth_image": (C.c_int, [_P, C.c_int, _P]),
     "composite_ao": (C.c_int, [_P, C.c_int, _P]),
     "encode_tga": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _P]),
+    "encode_tga_async": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _P]),
     "read_color": (C.c_int, [_P, C.c_int, _P]),
     "write_color": (C.c_int, [_P, C.c_int, _P]),
     "read_depth": (C.c_int, [_P, C.c_int, _P]),
@@ -141,6 +142,14 @@ SIGNATURES = {
     "open_peers_raw": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
     "ipc_close_peers": (C.c_int, [_P]),
     "composite_shade_p2p": (C.c_int, [_P, C.c_int, C.c_int]),
+    "comm_init": (C.c_int, [_P, C.c_int]),
+    "comm_export": (C.c_int, [_P, _P, C.c_size_t]),
+    "comm_open": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "comm_close": (C.c_int, [_P]),
+    "comm_shard": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "comm_rows": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "composite": (C.c_int, [_P]),
+    "composite_group": (C.c_int, [_P, C.c_int]),
     "light_dir_eye": (None, [_P, _P, _P]),
     "lookat": (None, [_P, _P, _P, _P]),
     "perspective": (None, [C.c_double, C.c_double, C.c_double, C.c_double, _P]),
@@ -434,6 +443,14 @@ class Renderer:
         self._ck(self._fn["encode_tga"](self.h, which, C.cast(table, _P), cap, C.cast(sizes, _P)), "encode_tga")
         return [bufs[v][:sizes[v]].tobytes() for v in range(n)]
 
+    def encode_tga_async(self, bufs, sizes, which=0):
+        """queue the TGA files of every view into the (pinned) uint8 arrays `bufs`; `sizes` is a uint64 array of
+        nviews entries.  Both are valid after readback_wait()."""
+        n = self.nviews
+        table = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        self._keep.append(table)
+        self._ck(self._fn["encode_tga_async"](self.h, which, C.cast(table, _P), bufs[0].size, _ptr(sizes)), "encode_tga_async")
+
     def depth_image(self, view=0):
         out = np.empty((self.height, self.width), dtype=np.uint8)
         self._ck(self._fn["depth_image"](self.h, view, _ptr(out)), "depth_image")
@@ -513,8 +530,54 @@ class Renderer:
     def composite_shade_p2p(self, y0, y1):
         self._ck(self._fn["composite_shade_p2p"](self.h, y0, y1), "composite_shade_p2p")
 
+    # composite groups (trb_comm_*): no host barrier anywhere ---------------------------------
+    COMM_BLOB_BYTES = 256
+
+    def comm_export(self):
+        b = C.create_string_buffer(self.COMM_BLOB_BYTES)
+        self._ck(self._fn["comm_export"](self.h, b, self.COMM_BLOB_BYTES), "comm_export")
+        return b.raw
+
+    def comm_open(self, blobs, rank):
+        self._ck(self._fn["comm_open"](self.h, b"".join(blobs), len(blobs), rank), "comm_open")
+
+    def comm_close(self):
+        self._ck(self._fn["comm_close"](self.h), "comm_close")
+
+    def comm_shard(self, total):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self._fn["comm_shard"](self.h, total, C.byref(a), C.byref(b)), "comm_shard")
+        return a.value, b.value
+
+    def comm_rows(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self._ck(self._fn["comm_rows"](self.h, C.byref(a), C.byref(b)), "comm_rows")
+        return a.value, b.value
+
+    def composite(self):
+        self._ck(self._fn["composite"](self.h), "composite")
+        self._keep.clear()
+
     def set_shade_rows(self, y0, y1):
         self._ck(self._fn["set_shade_rows"](self.h, y0, y1), "set_shade_rows")
+
+
+def comm_init(renderers):
+    """trb_comm_init: the contexts of ONE process become the ranks of a composite group (rank = position)"""
+    arr = (C.c_void_p * len(renderers))(*[r.h for r in renderers])
+    rc = renderers[0]._fn["comm_init"](C.cast(arr, _P), len(renderers))
+    if rc != 0:
+        raise TrbError("trb_comm_init -> %d: %s" % (rc, " | ".join((r._fn["last_error"](r.h) or b"").decode() for r in renderers)))
+
+
+def composite_group(renderers):
+    """trb_composite_group: composite + shade the owned rows of every member, streams ordered by events"""
+    arr = (C.c_void_p * len(renderers))(*[r.h for r in renderers])
+    rc = renderers[0]._fn["composite_group"](C.cast(arr, _P), len(renderers))
+    if rc != 0:
+        raise TrbError("trb_composite_group -> %d: %s" % (rc, " | ".join((r._fn["last_error"](r.h) or b"").decode() for r in renderers)))
+    for r in renderers:
+        r._keep.clear()
 
 
 _cuda_api = None

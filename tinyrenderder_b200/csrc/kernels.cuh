@@ -28,6 +28,8 @@
 namespace trbk {
 using namespace trbx;
 
+constexpr int MAX_PEERS = 16;
+constexpr int MAX_PEERS_COMM = MAX_PEERS;
 constexpr int TILE = 16;
 constexpr int TILE_SHIFT = 4;
 constexpr int TPB = 256;               // threads per block everywhere (== pixels per tile)
@@ -1204,10 +1206,9 @@ constexpr int SHADE_PX_PER_THREAD = 4;   // one 16-byte id load per thread: spar
 // attributes, pc = the perspective-correct barycentrics (fp64, exact).  Texture coordinates, the texel choice and the
 // shadow test stay fp64 (fastshade.cuh explains why that keeps every channel within one code of the reference).
 template <bool C2>
-__device__ __forceinline__ void lit_fast(const DrawDev& D, int view, const float (*at)[8], const double pc[3], uint8_t col[3]) {
+__device__ __forceinline__ void lit_fast_core(const DrawDev& D, int view, const LitUniforms& U, const trbf::LitF& LF,
+                                              const float (*at)[8], const double pc[3], uint8_t col[3]) {
     const bool shadowed = C2 && D.kind == 4 /*SHADOW_PHONG*/;
-    const LitUniforms& U = shadowed ? reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view].lit
-                                    : reinterpret_cast<const LitUniforms*>(D.uniforms)[view];
     const double tu = (double)at[0][6] * pc[0] + (double)at[1][6] * pc[1] + (double)at[2][6] * pc[2];  // main.cpp:100-101
     const double tv = (double)at[0][7] * pc[0] + (double)at[1][7] * pc[1] + (double)at[2][7] * pc[2];
     // the three maps are sampled at the same (u, v): one texel index serves every map of the same size
@@ -1240,7 +1241,14 @@ __device__ __forceinline__ void lit_fast(const DrawDev& D, int view, const float
             light_clip_from_position(SU.shadow, (double)at[k][0], (double)at[k][1], (double)at[k][2], lc[k]);
         sf = (float)shadow_factor(SU.shadow, lc, pc);
     }
-    trbf::shade_lit_f32(eye, reinterpret_cast<const trbf::LitF*>(D.litf)[view], at, pc, base, has_nm, nmc, spec_f, sf, col);
+    trbf::shade_lit_f32(eye, LF, at, pc, base, has_nm, nmc, spec_f, sf, col);
+}
+template <bool C2>
+__device__ __forceinline__ void lit_fast(const DrawDev& D, int view, const float (*at)[8], const double pc[3], uint8_t col[3]) {
+    const bool shadowed = C2 && D.kind == 4 /*SHADOW_PHONG*/;
+    const LitUniforms& U = shadowed ? reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view].lit
+                                    : reinterpret_cast<const LitUniforms*>(D.uniforms)[view];
+    lit_fast_core<C2>(D, view, U, reinterpret_cast<const trbf::LitF*>(D.litf)[view], at, pc, col);
 }
 
 // one visible pixel: p = x + y*W inside `view`, id = its winning triangle.  C2 = the frame has a
@@ -1457,157 +1465,10 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
     }
 }
 
-// Dense frames, fp32-lit flushes: the per-TRIANGLE half of shading runs once per visible triangle instead of once
-// per pixel.  A winner covers ~29 pixels on config 3; per pixel the chain id -> draw -> three indices -> three vertex
-// records -> triangle set-up (a reciprocal refinement) -> three attribute records used to cost ~250 of ~650
-// instructions and three of the four dependent memory round trips.  Three passes, no host round trip:
-//   k_shade_mark   every pixel with an unshaded winner raises the flag of its triangle;
-//   k_shade_build  one thread per (view, triangle of the flush): flagged triangles get a ShadeRec (set-up constants,
-//                  1/w of the vertices, raw attributes) in a table indexed by triangle id; runs with full warps because
-//                  visible triangles come in runs of consecutive ids;
-//   k_shade_rec    one thread per pixel: id -> record (one 224-byte read that the pixel's neighbours share) -> exact
-//                  barycentrics -> texels -> fp32 lighting.
-// Triangles whose draw has no fp32 path (or host-computed varyings) get kind < 0 and their pixels take shade_pixel.
-struct __align__(16) ShadeRec {
-    double ax, ay, s00, s01, s10, s11, uz, ruz, z0, z1, z2;   // eval_known_sample's constants
-    double iw0, iw1, iw2;                                     // 1 / w of the vertices (our_gl.cpp:168-170)
-    float at[3][8];                                           // pos, nrm, uv as uploaded
-    int draw, kind;                                           // kind < 0: shade this triangle's pixels with shade_pixel
-    uint32_t pad_[2];
-};
-static_assert(sizeof(ShadeRec) == 224, "ShadeRec size");
-
-__global__ void __launch_bounds__(TPB) k_shade_mark(FrameDev f, int row0, int row1, uint8_t* __restrict__ flags, uint32_t nids) {
-    const int view = blockIdx.y;
-    if (f.stats[view].shade_mode) return;
-    const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
-    const unsigned long long p0 = first + ((unsigned long long)blockIdx.x * TPB + threadIdx.x) * 4ull;
-    if (p0 >= last) return;
-    const uint32_t* vis = f.vis + (size_t)view * f.npix;
-    uint32_t ids[4] = {VIS_NONE, VIS_NONE, VIS_NONE, VIS_NONE};
-    if (p0 + 4 <= last && ((reinterpret_cast<uintptr_t>(vis + p0) & 15) == 0)) {
-        const uint4 v = *reinterpret_cast<const uint4*>(vis + p0);
-        ids[0] = v.x; ids[1] = v.y; ids[2] = v.z; ids[3] = v.w;
-    } else {
-        for (int j = 0; j < 4; ++j)
-            if (p0 + j < last) ids[j] = vis[p0 + j];
-    }
-    uint8_t* fl = flags + (size_t)view * nids;
-    #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (ids[j] != VIS_NONE && ids[j] != VIS_SHADED && (j == 0 || ids[j] != ids[j - 1])) {
-            TRB_CHECK(ids[j] < nids);
-            fl[ids[j]] = 1;                         // same value from every writer
-        }
-}
-
-__global__ void __launch_bounds__(TPB) k_shade_build(FrameDev f, DrawDev D, int draw_index, uint8_t* __restrict__ flags,
-                                                     uint32_t nids, ShadeRec* __restrict__ recs) {
-    const int view = blockIdx.y;
-    if (f.stats[view].shade_mode) return;
-    const uint32_t t = blockIdx.x * TPB + threadIdx.x;
-    if (t >= D.ntris) return;
-    const uint32_t id = D.id_base + t + 1u;
-    uint8_t* fl = flags + (size_t)view * nids + id;
-    if (!*fl) return;
-    *fl = 0;                                        // the table of flags is all zero again when the flush is over
-    ShadeRec& R = recs[(size_t)view * nids + id];
-    const bool lit = D.kind == 1 || D.kind == 2;
-    if (D.varyings || !(D.kind == 0 || D.kind == 3 || (lit && D.litf && D.attr8))) {
-        R.kind = -1;
-        return;
-    }
-    const uint32_t g0 = D.first_tri + t;
-    const uint32_t i0 = vertex_index(D.idx, 0, g0, 0), i1 = vertex_index(D.idx, 0, g0, 1), i2 = vertex_index(D.idx, 0, g0, 2);
-    const VRec* vr = D.vrec + (size_t)view * D.nverts;
-    const VRec va = load_vrec(vr + i0), vb = load_vrec(vr + i1), vc = load_vrec(vr + i2);
-    float4* ra = reinterpret_cast<float4*>(&R.at[0][0]);
-    if (lit) {
-        const uint32_t vi[3] = {i0, i1, i2};
-        #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float4* q = reinterpret_cast<const float4*>(D.attr8 + (size_t)vi[k] * 8);
-            ra[2 * k] = __ldg(q);
-            ra[2 * k + 1] = __ldg(q + 1);
-        }
-    }
-    TriSetup ts;
-    setup_known_triangle(va, vb, vc, ts);           // a recorded winner passed every reject: no tests, no bbox
-    double2* q = reinterpret_cast<double2*>(&R);
-    q[0] = make_double2(ts.ax, ts.ay);
-    q[1] = make_double2(ts.s00, ts.s01);
-    q[2] = make_double2(ts.s10, ts.s11);
-    q[3] = make_double2(ts.uz, ts.ruz);
-    q[4] = make_double2(ts.z0, ts.z1);
-    q[5] = make_double2(ts.z2, va.iw);
-    q[6] = make_double2(vb.iw, vc.iw);
-    R.draw = draw_index;
-    R.kind = D.kind;
-}
-
-#ifndef TRB_SHADE_REC_MIN_BLOCKS
-#define TRB_SHADE_REC_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(TPB, TRB_SHADE_REC_MIN_BLOCKS) k_shade_rec(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
-                                                                               int row0, int row1, uint32_t nids,
-                                                                               const ShadeRec* __restrict__ recs) {
-    if (f.stats[blockIdx.y].shade_mode) return;
-    __shared__ DrawDev sm_draws[SHADE_MAX_SM_DRAWS];
-    stage_draw_table(sm_draws, draws, ndraws);
-    const int view = blockIdx.y;
-    const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
-    const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
-    if (p >= last) return;
-    uint32_t* vis = f.vis + (size_t)view * f.npix;
-    const uint32_t id = vis[p];
-    if (id == VIS_NONE || id == VIS_SHADED) return;
-    const double2* q = reinterpret_cast<const double2*>(recs + (size_t)view * nids + id);
-    const double2 r13 = __ldg(q + 13);              // {draw | kind << 32, padding}
-    const int draw = (int)((unsigned long long)__double_as_longlong(r13.x) & 0xffffffffull);
-    const int kind = (int)((unsigned long long)__double_as_longlong(r13.x) >> 32);
-    if (kind < 0 || draw >= SHADE_MAX_SM_DRAWS) {   // no fp32 record for this triangle: the pixel-by-pixel path
-        shade_pixel<false, true>(f, draws, ndraws, sm_draws, view, p, id);
-        vis[p] = VIS_SHADED;
-        return;
-    }
-    const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5),
-                  r6 = __ldg(q + 6);
-    TriSetup ts;
-    ts.ax = r0.x; ts.ay = r0.y; ts.s00 = r1.x; ts.s01 = r1.y; ts.s10 = r2.x; ts.s11 = r2.y;
-    ts.uz = r3.x; ts.ruz = r3.y; ts.z0 = r4.x; ts.z1 = r4.y; ts.z2 = r5.x;
-    ts.x0 = ts.y0 = ts.x1 = ts.y1 = 0;
-    const size_t gp = (size_t)view * f.npix + p;
-    const uint32_t yq = (uint32_t)p / (uint32_t)f.W;     // p < 2^32: a frame has fewer than 2^32 pixels
-    const int x = (int)((uint32_t)p - yq * (uint32_t)f.W), y = (int)yq;
-    double b[3], z, pc[3];
-    eval_known_sample(ts, x, y, b, z);              // a recorded winner is covered: same arithmetic, no coverage tests
-    if (z == 0.0) f.zkey[gp] = depth_key(z);        // exact bits of the reference's zbuffer[idx] when z is -0.0
-    perspective_bary(b, r5.y, r6.x, r6.y, pc);
-    uint8_t col[3];
-    if (kind == 3 /*DEPTH*/) { vis[p] = VIS_SHADED; return; }
-    if (kind == 0 /*FLAT_BARY*/) {
-        shade_flat_bary(pc, col);
-    } else {
-        float at[3][8];
-        const float4* qa = reinterpret_cast<const float4*>(q + 7);
-        #pragma unroll
-        for (int v = 0; v < 3; ++v) {
-            const float4 q0 = __ldg(qa + 2 * v), q1 = __ldg(qa + 2 * v + 1);
-            at[v][0] = q0.x; at[v][1] = q0.y; at[v][2] = q0.z; at[v][3] = q0.w;
-            at[v][4] = q1.x; at[v][5] = q1.y; at[v][6] = q1.z; at[v][7] = q1.w;
-        }
-        lit_fast<false>(sm_draws[draw], view, at, pc, col);
-    }
-    uint8_t* c = f.color + gp * 3;
-    c[0] = col[0]; c[1] = col[1]; c[2] = col[2];
-    vis[p] = VIS_SHADED;
-}
-
 // Fused sort-last composite + shade over NVLink peer memory (config 4): one thread per owned pixel
 // loads the candidate (key, id) of every rank (peer pointers opened through CUDA IPC; loads of peer
 // addresses travel over NVLink and bypass the local L2), keeps the exact (depth, id) minimum, makes
 // it the local state and shades it - no intermediate all-reduced plane is ever written.
-constexpr int MAX_PEERS = 16;
 struct PeerPlanes {
     const unsigned long long* key[MAX_PEERS];
     const uint32_t* vis[MAX_PEERS];
@@ -1633,6 +1494,46 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p
     if (bid == VIS_NONE || bid == VIS_SHADED) { f.vis[p] = bid; return; }
     shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, 0, p, bid);
     f.vis[p] = VIS_SHADED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rank-to-rank synchronisation of the sort-last composite WITHOUT the host: every rank owns two counters in its
+// own HBM (exported to its peers like the planes).  `drawn` = the last frame whose draws are complete, `done` = the
+// last frame whose composite has finished reading the peers' planes.  A rank publishes a counter with a one-thread
+// kernel behind the work it stands for (stream order) and waits for its peers' counters with another one-thread
+// kernel in front of the work that needs them, so the streams of the ranks run in lock-step per frame while no host
+// thread ever blocks.  The waiter occupies one thread of one SM and gives up after `timeout_ns` (a peer died): the
+// verdict goes to mapped host memory and the next call on the context reports it.
+// ---------------------------------------------------------------------------------------------
+struct CommFlags {
+    unsigned long long drawn, done, pad0_, pad1_;
+};
+struct CommWait {
+    const unsigned long long* flag[MAX_PEERS_COMM];
+    int n;
+};
+__global__ void k_comm_publish(unsigned long long* flag, unsigned long long value) {
+    __threadfence_system();                        // the work queued before this kernel is visible to the peers first
+    *reinterpret_cast<volatile unsigned long long*>(flag) = value;
+    __threadfence_system();
+}
+__global__ void k_comm_wait(CommWait w, unsigned long long target, unsigned long long timeout_ns, uint32_t* __restrict__ timed_out) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int r = 0; r < w.n; ++r) {
+        const volatile unsigned long long* f = w.flag[r];
+        while (*f < target) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) {
+                *timed_out = 1u;
+                __threadfence_system();
+                return;
+            }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------

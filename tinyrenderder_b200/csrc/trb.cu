@@ -267,12 +267,40 @@ struct TrbCtx {
     void* peer_open[2 * MAX_PEERS] = {};
     int peer_rank = -1;
 
+    // sort-last composite group (trb_comm_*): in-process members or IPC peers, device-side frame counters
+    struct Comm {
+        int n = 0, rank = -1;
+        bool in_process = false;              // members[] valid: contexts of this process (trb_comm_init)
+        TrbCtx* members[MAX_PEERS] = {};
+        CommFlags* my_flags = nullptr;        // device memory of this rank (own 2 MB block: exported through CUDA IPC)
+        const CommFlags* peer_flags[MAX_PEERS] = {};
+        void* opened[3 * MAX_PEERS] = {};     // IPC mappings to close
+        unsigned long long seq = 0;           // frames composited so far
+        cudaEvent_t ev_drawn = nullptr, ev_done = nullptr;   // in-process groups on one device synchronise by events
+        int W = 0, H = 0;
+        const void* key_at_init = nullptr;
+    } comm;
+
     // pipelined readback
     cudaStream_t copy_stream = nullptr;
     DevBuf rb[2];
     cudaEvent_t rb_ready[2] = {nullptr, nullptr}, rb_done[2] = {nullptr, nullptr};
     bool rb_inflight[2] = {false, false};
     int rb_idx = 0;
+
+    // asynchronous TGA frame writer (trb_encode_tga_async): two jobs in flight
+    struct TgaJob {
+        DevBuf out;                          // packets of every view + the views' byte offsets
+        uint32_t* offs_host = nullptr;       // pinned: nviews + 1 offsets
+        size_t offs_cap = 0;
+        cudaEvent_t offs_ready = nullptr, done = nullptr;
+        std::vector<uint8_t*> outs;
+        uint64_t* sizes = nullptr;
+        uint64_t capacity = 0;
+        int nviews = 0, W = 0, H = 0;
+        bool pending_copy = false, inflight = false;
+    } tga[2];
+    int tga_idx = 0;
 
     // timing
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -288,8 +316,6 @@ struct TrbCtx {
     int rw_blocks = RW_BLOCKS_DEFAULT;   // k_raster_warp instantiation (resident CTAs per SM the registers are sized for)
     bool shade_exact = false;   // true: all-fp64 lighting (exact.cuh); false: fp32 lighting (fastshade.cuh)
     bool foreign_ids = false;   // trb_set_triangle_id_base was used: the id plane may hold winners other ranks rasterised
-    bool shade_rec = true;      // dense fp32-lit flushes shade per visible triangle (TRB_SHADE_REC=0: everything per pixel)
-    DevBuf shade_flags, shade_recs;
 };
 
 namespace {
@@ -450,37 +476,7 @@ int do_flush(TrbCtx* c) {
                 default: k_shade<true, true><<<grid, TPB, 0, c->stream>>>(f, table, nd, list); break;
             }
         }
-        // dense views of fp32-lit flushes: per-triangle work once per visible triangle (k_shade_mark / build / rec).
-        // The record table is indexed by triangle id: frames whose ids x views would need more than 6 GB of it
-        // (configs 4 and 5, sparse anyway) keep the per-pixel kernels
-        const uint64_t nids = c->next_id + 1;
-        const bool by_rec = variant == 1 && c->shade_rec && !c->foreign_ids && nids * (uint64_t)f.nviews * sizeof(ShadeRec) <= (6ull << 30) &&
-                            nd <= SHADE_MAX_SM_DRAWS;
-        if (by_rec) {
-            const size_t flag_bytes = (size_t)nids * f.nviews;
-            if (c->shade_flags.cap < flag_bytes) {          // a fresh table: all flags down
-                CU(c->shade_flags.ensure(flag_bytes, c->stream));
-                CU(cudaMemsetAsync(c->shade_flags.p, 0, c->shade_flags.cap, c->stream));
-            }
-            CU(c->shade_recs.ensure((size_t)nids * f.nviews * sizeof(ShadeRec), c->stream));
-            uint8_t* flags = c->shade_flags.as<uint8_t>();
-            ShadeRec* recs = c->shade_recs.as<ShadeRec>();
-            {
-                const dim3 grid(blocks_for((n + 3) / 4), f.nviews);
-                Launch L(c, "k_shade_mark");
-                k_shade_mark<<<grid, TPB, 0, c->stream>>>(f, r0, r1, flags, (uint32_t)nids);
-            }
-            for (int d = 0; d < nd; ++d) {
-                const DrawDev& D = c->draws[d];
-                if (D.ntris == 0) continue;
-                Launch L(c, "k_shade_build");
-                k_shade_build<<<dim3(blocks_for(D.ntris), f.nviews), TPB, 0, c->stream>>>(f, D, d, flags, (uint32_t)nids, recs);
-            }
-            {
-                Launch L(c, "k_shade_rec");
-                k_shade_rec<<<dim3(blocks_for(n), f.nviews), TPB, 0, c->stream>>>(f, table, nd, r0, r1, (uint32_t)nids, recs);
-            }
-        } else {   // dense views only
+        {   // dense views only
 #if TRB_SHADE_2D
             const dim3 grid((unsigned)(((f.W + 31) / 32) * ((r1 - r0 + 7) / 8)), f.nviews);
 #else
@@ -709,6 +705,69 @@ int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, i
     return TRB_OK;
 }
 
+int tga_finish(TrbCtx* c, TrbCtx::TgaJob& j, bool wait_copies);   // asynchronous TGA writer, defined with trb_encode_tga_async
+
+constexpr unsigned long long COMM_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;   // a peer that stays silent for 20 s is gone
+
+int comm_check_timeout(TrbCtx* c) {
+    if (c->host_total[8]) return fail(c, TRB_E_COMM, "composite group: a peer did not reach the frame within 20 s");
+    return TRB_OK;
+}
+// make this rank's stream wait until every peer has published `drawn` (done == false) or `done` (true) for frame comm.seq
+int comm_wait_peers(TrbCtx* c, bool done) {
+    TrbCtx::Comm& m = c->comm;
+    if (m.seq == 0) return TRB_OK;
+    int rc = comm_check_timeout(c);
+    if (rc) return rc;
+    if (m.in_process && m.ev_drawn) {            // events: safe for several contexts on ONE device
+        for (int r = 0; r < m.n; ++r)
+            if (r != m.rank) CU(cudaStreamWaitEvent(c->stream, done ? m.members[r]->comm.ev_done : m.members[r]->comm.ev_drawn, 0));
+        return TRB_OK;
+    }
+    CommWait w;
+    w.n = 0;
+    for (int r = 0; r < m.n; ++r)
+        if (r != m.rank) w.flag[w.n++] = done ? &m.peer_flags[r]->done : &m.peer_flags[r]->drawn;
+    if (w.n == 0) return TRB_OK;
+    Launch L(c, "k_comm_wait");
+    k_comm_wait<<<1, 1, 0, c->stream>>>(w, m.seq, COMM_TIMEOUT_NS, c->host_total_dev + 8);
+    CU(cudaGetLastError());
+    return TRB_OK;
+}
+// the fused composite + shade of rows [y0, y1) queued on the context's stream; no synchronisation
+int enqueue_composite_shade(TrbCtx* c, int y0, int y1) {
+    // the local planes may have been reallocated since the peers were opened
+    c->peers.key[c->peer_rank] = c->frame.zkey;
+    c->peers.vis[c->peer_rank] = c->frame.vis;
+    if (y1 > y0 && !c->draws.empty()) {
+        size_t bytes = c->draws.size() * sizeof(DrawDev);
+        CU(c->draw_table.ensure(bytes, c->stream));
+        CU(cudaMemcpyAsync(c->draw_table.p, c->draws.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+        bool config2 = false;
+        for (const DrawDev& d : c->draws) config2 |= d.kind >= 4;
+        const unsigned long long n = (unsigned long long)(y1 - y0) * c->frame.W;
+        Launch L(c, "k_composite_shade_p2p");
+        const DrawDev* table = c->draw_table.as<DrawDev>();
+        const int nd = (int)c->draws.size();
+        bool fast = !c->shade_exact;
+        for (const DrawDev& d : c->draws) fast &= !((d.kind == 1 || d.kind == 2 || d.kind == 4) && !d.litf);
+        switch ((config2 ? 2 : 0) | (fast ? 1 : 0)) {
+            case 0: k_composite_shade_p2p<false, false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
+            case 1: k_composite_shade_p2p<false, true><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
+            case 2: k_composite_shade_p2p<true, false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
+            default: k_composite_shade_p2p<true, true><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
+        }
+    }
+    CU(cudaGetLastError());
+    c->draws.clear();      // the pageable table was staged before cudaMemcpyAsync returned
+    return TRB_OK;
+}
+void comm_rows(int H, int rank, int n, int* y0, int* y1) {
+    const int base = H / n, rem = H % n;
+    *y0 = rank * base + std::min(rank, rem);
+    *y1 = *y0 + base + (rank < rem ? 1 : 0);
+}
+
 void ssao_dirs(SsaoDirs& d) {
     for (int k = 0; k < 8; ++k) {
         double angle = 2.0 * M_PI * k / 8;  // main.cpp:333, host libm like the reference
@@ -739,7 +798,6 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_WARP_MAX")) c->warp_max = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("TRB_RW_BLOCKS")) c->rw_blocks = atoi(e);
     if (const char* e = getenv("TRB_SHADE_EXACT")) c->shade_exact = atoi(e) != 0;
-    if (const char* e = getenv("TRB_SHADE_REC")) c->shade_rec = atoi(e) != 0;
     if (const char* e = getenv("TRB_SYNC_DRAWS")) c->sync_draws = atoi(e) != 0;
     if (const char* e = getenv("TRB_BIN_CAP")) c->bin_cap_fixed = (uint32_t)std::max(1, atoi(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -775,10 +833,11 @@ int trb_destroy(TrbCtx* c) {
         if (t.alive) cudaFree(t.px);
     DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
                       &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->ctl, &c->heavy_list, &c->direct_list, &c->direct_n, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
-                      &c->scratch_b, &c->shade_flags, &c->shade_recs};
+                      &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.keys.release();
     for (auto& b : c->shadow_pool) b.release();
+    trb_comm_close(c);
     trb_ipc_close_peers(c);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
@@ -788,6 +847,12 @@ int trb_destroy(TrbCtx* c) {
             cudaEventDestroy(c->rb_done[i]);
         }
         cudaStreamDestroy(c->copy_stream);
+    }
+    for (auto& j : c->tga) {
+        j.out.release();
+        if (j.offs_host) cudaFreeHost(j.offs_host);
+        if (j.offs_ready) cudaEventDestroy(j.offs_ready);
+        if (j.done) cudaEventDestroy(j.done);
     }
     c->arena.release();
     c->cache.release();
@@ -1047,6 +1112,15 @@ int trb_begin_batch(TrbCtx* c, int w, int h, int nviews) {
     c->snap_stale = false;
     c->shade_row0 = 0;
     c->shade_row1 = -1;
+    if (c->comm.n > 0) {
+        // peers read this rank's planes during their composite: the planes must be the ones they opened, and the clear
+        // below must not start before every peer has finished reading the previous frame
+        if (nviews != 1 || w != c->comm.W || h != c->comm.H || c->zkey.p != c->comm.key_at_init)
+            return fail(c, TRB_E_COMM, "begin_frame: the frame differs from the one the composite group was opened with "
+                                       "(trb_comm_close, then open the group again)");
+        rc = comm_wait_peers(c, /*done=*/true);
+        if (rc) return rc;
+    }
     {
         unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(total), 148ull * 32);
         Launch L(c, "k_clear");
@@ -1354,6 +1428,10 @@ int trb_readback_wait(TrbCtx* c) {
             CU(cudaEventSynchronize(c->rb_done[i]));
             c->rb_inflight[i] = false;
         }
+    for (int i = 0; i < 2; ++i) {
+        int rc = tga_finish(c, c->tga[i], /*wait_copies=*/true);
+        if (rc) return rc;
+    }
     return TRB_OK;
 }
 int trb_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* depth_out) {
@@ -1593,9 +1671,12 @@ int trb_ssao(TrbCtx* c, int view, uint8_t* out) { return post_to_host(c, TRB_IMA
 int trb_composite_ao(TrbCtx* c, int view, uint8_t* out) { return post_to_host(c, TRB_IMAGE_FINAL, view, out, "composite_ao"); }
 int trb_depth_image(TrbCtx* c, int view, uint8_t* out) { return post_to_host(c, TRB_IMAGE_DEPTH, view, out, "depth_image"); }
 
-int trb_encode_tga(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity, uint64_t* sizes) {
-    if (!c || !c->in_frame || !out || !sizes || which < TRB_IMAGE_COLOR || which > TRB_IMAGE_FINAL)
-        return fail(c, TRB_E_ARG, "encode_tga: bad argument");
+}  // extern "C"
+
+namespace {
+// flush, build the source image of `which` for every view and packetise it into `outbuf` on the render stream;
+// *offs_dev = nviews + 1 byte offsets of the views' packet runs inside outbuf (device memory, behind the packets)
+int encode_on_device(TrbCtx* c, int which, DevBuf& outbuf, uint32_t** offs_dev) {
     int rc = do_flush(c);
     if (rc) return rc;
     const FrameDev& f = c->frame;
@@ -1622,29 +1703,124 @@ int trb_encode_tga(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity,
     }
     const size_t out_cap = total * bpp + total / 2 + f.nviews + 1024;  // worst case: a raw packet of two pixels per header
     const size_t offs_at = (out_cap + 3) & ~(size_t)3;                // per-view byte ranges behind the packets
-    CU(c->rle_out.ensure(offs_at + ((size_t)f.nviews + 2) * 4, c->stream));
-    uint32_t* offs_dev = reinterpret_cast<uint32_t*>(c->rle_out.as<uint8_t>() + offs_at);
-    rc = rle_passes<3>(c, src, f.npix, (uint32_t)f.nviews, c->rle_out.as<uint8_t>(), offs_dev);
+    CU(outbuf.ensure(offs_at + ((size_t)f.nviews + 2) * 4, c->stream));
+    *offs_dev = reinterpret_cast<uint32_t*>(outbuf.as<uint8_t>() + offs_at);
+    return rle_passes<3>(c, src, f.npix, (uint32_t)f.nviews, outbuf.as<uint8_t>(), *offs_dev);
+}
+// TGAHeader of write_tga_file (tgaimage.cpp:167-178): 18 packed bytes, origin bottom-left (vflip = true)
+void tga_header(uint8_t* h, int W, int H) {
+    memset(h, 0, 18);
+    h[2] = 10;                                                    // datatypecode: RLE true-colour
+    h[12] = (uint8_t)(W & 255); h[13] = (uint8_t)(W >> 8);
+    h[14] = (uint8_t)(H & 255); h[15] = (uint8_t)(H >> 8);
+    h[16] = 24;
+    h[17] = 0x00;
+}
+// the copies of an asynchronous encode whose per-view sizes have reached the host: headers + sizes now, packets on the
+// copy stream
+int tga_issue_copies(TrbCtx* c, TrbCtx::TgaJob& j) {
+    j.pending_copy = false;
+    for (int v = 0; v < j.nviews; ++v) {
+        const uint64_t n = (uint64_t)j.offs_host[v + 1] - j.offs_host[v];
+        j.sizes[v] = 18 + n;
+        if (!j.outs[v]) continue;
+        if (j.sizes[v] > j.capacity) return fail(c, TRB_E_ARG, "encode_tga: output buffer too small");
+        tga_header(j.outs[v], j.W, j.H);
+        CU(cudaMemcpyAsync(j.outs[v] + 18, j.out.as<uint8_t>() + j.offs_host[v], n, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    CU(cudaEventRecord(j.done, c->copy_stream));
+    return TRB_OK;
+}
+int tga_finish(TrbCtx* c, TrbCtx::TgaJob& j, bool wait_copies) {
+    if (!j.inflight) return TRB_OK;
+    if (j.pending_copy) {
+        CU(cudaEventSynchronize(j.offs_ready));
+        int rc = tga_issue_copies(c, j);
+        if (rc) return rc;
+    }
+    if (wait_copies) {
+        CU(cudaEventSynchronize(j.done));
+        j.inflight = false;
+    }
+    return TRB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int trb_encode_tga(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity, uint64_t* sizes) {
+    if (!c || !c->in_frame || !out || !sizes || which < TRB_IMAGE_COLOR || which > TRB_IMAGE_FINAL)
+        return fail(c, TRB_E_ARG, "encode_tga: bad argument");
+    uint32_t* offs_dev = nullptr;
+    int rc = encode_on_device(c, which, c->rle_out, &offs_dev);
     if (rc) return rc;
+    const FrameDev& f = c->frame;
     std::vector<uint32_t> offs((size_t)f.nviews + 1);
     CU(cudaMemcpyAsync(offs.data(), offs_dev, offs.size() * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    // TGAHeader of write_tga_file (tgaimage.cpp:167-178): 18 packed bytes, origin bottom-left (vflip = true)
     for (int v = 0; v < f.nviews; ++v) {
         const uint64_t n = (uint64_t)offs[v + 1] - offs[v];
         sizes[v] = 18 + n;
         if (!out[v]) continue;
         if (sizes[v] > capacity) return fail(c, TRB_E_ARG, "encode_tga: output buffer too small");
-        uint8_t* h = out[v];
-        memset(h, 0, 18);
-        h[2] = 10;                                                    // datatypecode: RLE true-colour
-        h[12] = (uint8_t)(f.W & 255); h[13] = (uint8_t)(f.W >> 8);
-        h[14] = (uint8_t)(f.H & 255); h[15] = (uint8_t)(f.H >> 8);
-        h[16] = (uint8_t)(bpp * 8);
-        h[17] = 0x00;
-        CU(cudaMemcpyAsync(h + 18, c->rle_out.as<uint8_t>() + offs[v], n, cudaMemcpyDeviceToHost, c->stream));
+        tga_header(out[v], f.W, f.H);
+        CU(cudaMemcpyAsync(out[v] + 18, c->rle_out.as<uint8_t>() + offs[v], n, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
+    return TRB_OK;
+}
+
+// The asynchronous frame writer: packets are built behind the frame on the render stream, their per-view sizes go to
+// pinned host memory, and the packets themselves come home on the copy stream as soon as the host knows the sizes -
+// at the latest inside the next trb_encode_tga_async / trb_readback_wait.  Two encodes may be in flight.
+int trb_encode_tga_async(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity, uint64_t* sizes) {
+    HostSpan host_span_("trb_encode_tga_async");
+    if (!c || !c->in_frame || !out || !sizes || which < TRB_IMAGE_COLOR || which > TRB_IMAGE_FINAL)
+        return fail(c, TRB_E_ARG, "encode_tga_async: bad argument");
+    int rc = check_device(c);
+    if (rc) return rc;
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&c->rb_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->rb_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int i = (c->tga_idx ^= 1);
+    TrbCtx::TgaJob& j = c->tga[i];
+    TrbCtx::TgaJob& other = c->tga[i ^ 1];
+    // the previous encode's sizes have usually arrived by now: send its packets on their way first
+    if (other.inflight && other.pending_copy && cudaEventQuery(other.offs_ready) == cudaSuccess) {
+        rc = tga_issue_copies(c, other);
+        if (rc) return rc;
+    }
+    (void)cudaGetLastError();
+    rc = tga_finish(c, j, /*wait_copies=*/true);      // slot i was used two encodes ago: its packets must be home
+    if (rc) return rc;
+    const FrameDev& f = c->frame;
+    if (!j.offs_ready) {
+        CU(cudaEventCreateWithFlags(&j.offs_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&j.done, cudaEventDisableTiming));
+    }
+    if (j.offs_cap < (size_t)f.nviews + 1) {
+        if (j.offs_host) cudaFreeHost(j.offs_host);
+        CU(cudaHostAlloc((void**)&j.offs_host, ((size_t)f.nviews + 1) * 4, cudaHostAllocDefault));
+        j.offs_cap = (size_t)f.nviews + 1;
+    }
+    uint32_t* offs_dev = nullptr;
+    rc = encode_on_device(c, which, j.out, &offs_dev);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(j.offs_host, offs_dev, ((size_t)f.nviews + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(j.offs_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, j.offs_ready, 0));   // the copy stream must not read the packets earlier
+    j.outs.assign(out, out + f.nviews);
+    j.sizes = sizes;
+    j.capacity = capacity;
+    j.nviews = f.nviews;
+    j.W = f.W;
+    j.H = f.H;
+    j.pending_copy = true;
+    j.inflight = true;
     return TRB_OK;
 }
 
@@ -1817,31 +1993,224 @@ int trb_composite_shade_p2p(TrbCtx* c, int y0, int y1) {
         return fail(c, TRB_E_COMM, "composite_shade_p2p: open the peers first (single-view frame)");
     int rc = check_device(c);
     if (rc) return rc;
-    // the local planes may have been reallocated since the peers were opened
-    c->peers.key[c->peer_rank] = c->frame.zkey;
-    c->peers.vis[c->peer_rank] = c->frame.vis;
-    if (y1 > y0 && !c->draws.empty()) {
-        size_t bytes = c->draws.size() * sizeof(DrawDev);
-        CU(c->draw_table.ensure(bytes, c->stream));
-        CU(cudaMemcpyAsync(c->draw_table.p, c->draws.data(), bytes, cudaMemcpyHostToDevice, c->stream));
-        bool config2 = false;
-        for (const DrawDev& d : c->draws) config2 |= d.kind >= 4;
-        const unsigned long long n = (unsigned long long)(y1 - y0) * c->frame.W;
-        Launch L(c, "k_composite_shade_p2p");
-        const DrawDev* table = c->draw_table.as<DrawDev>();
-        const int nd = (int)c->draws.size();
-        bool fast = !c->shade_exact;
-        for (const DrawDev& d : c->draws) fast &= !((d.kind == 1 || d.kind == 2 || d.kind == 4) && !d.litf);
-        switch ((config2 ? 2 : 0) | (fast ? 1 : 0)) {
-            case 0: k_composite_shade_p2p<false, false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
-            case 1: k_composite_shade_p2p<false, true><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
-            case 2: k_composite_shade_p2p<true, false><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
-            default: k_composite_shade_p2p<true, true><<<blocks_for(n), TPB, 0, c->stream>>>(c->frame, c->peers, table, nd, y0, y1); break;
+    rc = enqueue_composite_shade(c, y0, y1);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));   // peers wait on a host barrier after this call
+    return TRB_OK;
+}
+
+// ---- composite groups: the C face of the sort-last composite (SURVEY 8b trb_comm_init / trb_composite) ------------
+int trb_comm_close(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    TrbCtx::Comm& m = c->comm;
+    for (void*& p : m.opened)
+        if (p) {
+            cudaIpcCloseMemHandle(p);
+            p = nullptr;
+        }
+    if (m.my_flags) cudaFree(m.my_flags);
+    if (m.ev_drawn) cudaEventDestroy(m.ev_drawn);
+    if (m.ev_done) cudaEventDestroy(m.ev_done);
+    m = TrbCtx::Comm();
+    c->peers.n = 0;
+    c->peer_rank = -1;
+    c->host_total[8] = 0;
+    return TRB_OK;
+}
+static int comm_prepare(TrbCtx* c, int n, int rank) {
+    if (!c->in_frame || c->frame.nviews != 1) return fail(c, TRB_E_COMM, "composite group: begin a single-view frame of the final size first");
+    int rc = check_device(c);
+    if (rc) return rc;
+    trb_comm_close(c);
+    TrbCtx::Comm& m = c->comm;
+    CU(cudaMalloc((void**)&m.my_flags, (size_t)2 << 20));           // its own block: the IPC handle exports nothing else
+    CU(cudaMemsetAsync(m.my_flags, 0, sizeof(CommFlags), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    m.n = n;
+    m.rank = rank;
+    m.W = c->frame.W;
+    m.H = c->frame.H;
+    m.key_at_init = c->zkey.p;
+    m.peer_flags[rank] = m.my_flags;
+    c->peers.key[rank] = c->frame.zkey;
+    c->peers.vis[rank] = c->frame.vis;
+    c->peers.n = n;
+    c->peer_rank = rank;
+    return TRB_OK;
+}
+int trb_comm_init(TrbCtx* const* ctxs, int n) {
+    if (!ctxs || n < 1 || n > MAX_PEERS) return TRB_E_ARG;
+    for (int i = 0; i < n; ++i)
+        if (!ctxs[i]) return TRB_E_ARG;
+    bool one_device_twice = false;
+    for (int i = 0; i < n; ++i) {
+        TrbCtx* c = ctxs[i];
+        int rc = comm_prepare(c, n, i);
+        if (rc) return rc;
+        if (c->frame.W != ctxs[0]->frame.W || c->frame.H != ctxs[0]->frame.H) return fail(c, TRB_E_COMM, "comm_init: frames differ in size");
+        for (int j = 0; j < i; ++j) one_device_twice |= ctxs[j]->device == c->device;
+    }
+    for (int i = 0; i < n; ++i) {
+        TrbCtx* c = ctxs[i];
+        CU(cudaSetDevice(c->device));
+        c->comm.in_process = true;
+        for (int j = 0; j < n; ++j) {
+            c->comm.members[j] = ctxs[j];
+            if (j == i) continue;
+            if (ctxs[j]->device != c->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, c->device, ctxs[j]->device));
+                if (!can) return fail(c, TRB_E_COMM, "comm_init: no peer access between the devices of the group");
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+                (void)cudaGetLastError();
+            }
+            c->peers.key[j] = ctxs[j]->frame.zkey;
+            c->peers.vis[j] = ctxs[j]->frame.vis;
+            c->comm.peer_flags[j] = ctxs[j]->comm.my_flags;
+        }
+        if (one_device_twice) {     // a waiting kernel could starve the peer it waits for on the same device: events instead
+            CU(cudaEventCreateWithFlags(&c->comm.ev_drawn, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->comm.ev_done, cudaEventDisableTiming));
         }
     }
+    return TRB_OK;
+}
+int trb_comm_export(TrbCtx* c, void* blob, size_t blob_bytes) {
+    if (!c || !blob || blob_bytes < TRB_COMM_BLOB_BYTES) return fail(c, TRB_E_ARG, "comm_export: blob too small");
+    if (c->comm.n == 0) {                      // first the local half: flags, frame geometry (rank / size follow in comm_open)
+        int rc = comm_prepare(c, 1, 0);
+        if (rc) return rc;
+    }
+    int rc = check_device(c);
+    if (rc) return rc;
+    unsigned char* b = (unsigned char*)blob;
+    memset(b, 0, TRB_COMM_BLOB_BYTES);
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)b, c->zkey.p));
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)(b + 64), c->vis.p));
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)(b + 128), c->comm.my_flags));
+    int32_t meta[4] = {c->frame.W, c->frame.H, c->device, 0};
+    memcpy(b + 192, meta, sizeof(meta));
+    return TRB_OK;
+}
+int trb_comm_open(TrbCtx* c, const void* blobs, int n, int rank) {
+    if (!c || !blobs || n < 1 || n > MAX_PEERS || rank < 0 || rank >= n) return fail(c, TRB_E_ARG, "comm_open: bad argument");
+    if (c->comm.n == 0 || !c->comm.my_flags) return fail(c, TRB_E_COMM, "comm_open: call trb_comm_export on this context first");
+    int rc = check_device(c);
+    if (rc) return rc;
+    TrbCtx::Comm& m = c->comm;
+    CommFlags* mine = m.my_flags;
+    // keep the flags that were exported; forget any earlier peers
+    for (void*& p : m.opened)
+        if (p) {
+            cudaIpcCloseMemHandle(p);
+            p = nullptr;
+        }
+    m.n = n;
+    m.rank = rank;
+    m.in_process = false;
+    m.seq = 0;
+    const unsigned char* b = (const unsigned char*)blobs;
+    for (int r = 0; r < n; ++r) {
+        const unsigned char* br = b + (size_t)r * TRB_COMM_BLOB_BYTES;
+        int32_t meta[4];
+        memcpy(meta, br + 192, sizeof(meta));
+        if (meta[0] != m.W || meta[1] != m.H) return fail(c, TRB_E_COMM, "comm_open: a peer renders a frame of another size");
+        if (r == rank) {
+            c->peers.key[r] = c->frame.zkey;
+            c->peers.vis[r] = c->frame.vis;
+            m.peer_flags[r] = mine;
+            continue;
+        }
+        void *pk = nullptr, *pv = nullptr, *pf = nullptr;
+        CU(cudaIpcOpenMemHandle(&pk, *(const cudaIpcMemHandle_t*)br, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&pv, *(const cudaIpcMemHandle_t*)(br + 64), cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&pf, *(const cudaIpcMemHandle_t*)(br + 128), cudaIpcMemLazyEnablePeerAccess));
+        m.opened[3 * r] = pk; m.opened[3 * r + 1] = pv; m.opened[3 * r + 2] = pf;
+        c->peers.key[r] = (const unsigned long long*)pk;
+        c->peers.vis[r] = (const uint32_t*)pv;
+        m.peer_flags[r] = (const CommFlags*)pf;
+    }
+    c->peers.n = n;
+    c->peer_rank = rank;
+    return TRB_OK;
+}
+int trb_comm_shard(TrbCtx* c, uint64_t total, uint64_t* first, uint64_t* count) {
+    if (!c || c->comm.n < 1 || !first || !count) return fail(c, TRB_E_COMM, "comm_shard: no composite group");
+    const uint64_t n = (uint64_t)c->comm.n, r = (uint64_t)c->comm.rank, base = total / n, rem = total % n;
+    *first = r * base + std::min(r, rem);
+    *count = base + (r < rem ? 1 : 0);
+    return TRB_OK;
+}
+int trb_comm_rows(TrbCtx* c, int* y0, int* y1) {
+    if (!c || c->comm.n < 1 || !y0 || !y1) return fail(c, TRB_E_COMM, "comm_rows: no composite group");
+    comm_rows(c->comm.H, c->comm.rank, c->comm.n, y0, y1);
+    return TRB_OK;
+}
+// One rank's half of a frame's composite, entirely on its stream: publish "my draws are complete", wait for the peers'
+// draws, composite + shade the rows this rank owns, publish "I have finished reading".  Nothing here waits on the host.
+int trb_composite(TrbCtx* c) {
+    if (!c || !c->in_frame || c->frame.nviews != 1 || c->comm.n < 1) return fail(c, TRB_E_COMM, "composite: no composite group (trb_comm_init / trb_comm_open)");
+    if (c->comm.in_process && c->comm.ev_drawn)
+        return fail(c, TRB_E_COMM, "composite: contexts that share a device are composited together, with trb_composite_group");
+    int rc = check_device(c);
+    if (rc) return rc;
+    TrbCtx::Comm& m = c->comm;
+    ++m.seq;
+    {
+        Launch L(c, "k_comm_publish");
+        k_comm_publish<<<1, 1, 0, c->stream>>>(&m.my_flags->drawn, m.seq);
+    }
+    rc = comm_wait_peers(c, /*done=*/false);
+    if (rc) return rc;
+    int y0, y1;
+    comm_rows(m.H, m.rank, m.n, &y0, &y1);
+    rc = enqueue_composite_shade(c, y0, y1);
+    if (rc) return rc;
+    {
+        Launch L(c, "k_comm_publish");
+        k_comm_publish<<<1, 1, 0, c->stream>>>(&m.my_flags->done, m.seq);
+    }
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));   // peers wait on a host barrier after this call
-    c->draws.clear();
+    return TRB_OK;
+}
+// The same for every context of an in-process group at once (one host thread drives all of them; required when
+// contexts share a device): events order the streams.
+int trb_composite_group(TrbCtx* const* ctxs, int n) {
+    if (!ctxs || n < 1 || n > MAX_PEERS) return TRB_E_ARG;
+    for (int i = 0; i < n; ++i) {
+        TrbCtx* c = ctxs[i];
+        if (!c || !c->in_frame || c->frame.nviews != 1 || c->comm.n != n || c->comm.rank != i || !c->comm.in_process)
+            return fail(c, TRB_E_COMM, "composite_group: pass the contexts of trb_comm_init in the same order");
+    }
+    for (int i = 0; i < n; ++i) {          // everybody's draws are queued: mark them
+        TrbCtx* c = ctxs[i];
+        CU(cudaSetDevice(c->device));
+        ++c->comm.seq;
+        if (c->comm.ev_drawn) CU(cudaEventRecord(c->comm.ev_drawn, c->stream));
+        else {
+            Launch L(c, "k_comm_publish");
+            k_comm_publish<<<1, 1, 0, c->stream>>>(&c->comm.my_flags->drawn, c->comm.seq);
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        TrbCtx* c = ctxs[i];
+        CU(cudaSetDevice(c->device));
+        int rc = comm_wait_peers(c, /*done=*/false);
+        if (rc) return rc;
+        int y0, y1;
+        comm_rows(c->comm.H, i, n, &y0, &y1);
+        rc = enqueue_composite_shade(c, y0, y1);
+        if (rc) return rc;
+        if (c->comm.ev_done) CU(cudaEventRecord(c->comm.ev_done, c->stream));
+        else {
+            Launch L(c, "k_comm_publish");
+            k_comm_publish<<<1, 1, 0, c->stream>>>(&c->comm.my_flags->done, c->comm.seq);
+        }
+        CU(cudaGetLastError());
+    }
     return TRB_OK;
 }
 int trb_set_shade_rows(TrbCtx* c, int y0, int y1) {

@@ -91,6 +91,32 @@ class P2PComposite:
         return y0, y1
 
 
+class CommComposite:
+    """The composite group of the C ABI (trb_comm_export / trb_comm_open / trb_composite) for one process per rank:
+    the IPC blobs are exchanged ONCE with the host-side collective `all_gather(obj) -> list`; after that a frame costs no
+    host synchronisation at all - every rank's stream publishes and polls frame counters in device memory."""
+
+    def __init__(self, renderer, all_gather, rank, world):
+        self.r, self.all_gather, self.rank, self.world = renderer, all_gather, rank, world
+        self.opened = False
+
+    def open(self):
+        """call once, after the first begin_frame of the final size (the planes are exported as they are then)"""
+        blobs = self.all_gather(self.r.comm_export())
+        self.r.comm_open(blobs, self.rank)
+        self.opened = True
+
+    def shard(self, ntris):
+        return self.r.comm_shard(ntris) if self.opened else triangle_shard(ntris, self.rank, self.world)
+
+    def run(self):
+        """after the rank's draws of the frame (no flush): composite + shade the owned rows; returns them"""
+        if not self.opened:
+            self.open()
+        self.r.composite()
+        return self.r.comm_rows()
+
+
 def composite_depth_color_cpu(z_list, bgr_list):
     """The same protocol on host arrays (used by the gloo tests with the CPU oracle): the winner of a
     pixel is the rank with the smallest depth, lowest rank on ties (lower ranks hold lower ids)."""
