@@ -701,9 +701,47 @@ def measure_e2e(args, env, wl, r, steps, tris_step_all, nviews, P, barrier):
                 "host_enqueue_ms_per_step": 1e3 * t_host / e_steps,
                 "host_ms_per_step": {k: v / e_steps for k, v in host_ms.items()}}
 
+    # ---- the same with the frames coming home as TGA FILES (what main.cpp:743 produces): RLE packets built on the
+    #      device behind the frame (trb_encode_tga_async), only the packets cross PCIe
+    cap = wl.width * wl.height * 3 + wl.width * wl.height // 2 + 64
+    tga_host = [[pin((cap,), torch.uint8) for _ in range(nviews)] for _ in range(2)]
+    tga_sizes = [np.zeros(nviews, dtype=np.uint64) for _ in range(2)]
+
+    def tga_step(s):
+        up2 = wl.scenes.UploadedScene(r, wl.scene)
+        wl.render(up2, wl.views(api, s, rank, world))
+        r.encode_tga_async(tga_host[s & 1], tga_sizes[s & 1], 0)
+        up2.free()
+        return up2.h2d_bytes
+
+    def tga_run():
+        for s in range(3):
+            h2d = tga_step(s)
+        r.readback_wait()
+        barrier()
+        t0 = time.perf_counter()
+        sent = 0
+        for s in range(e_steps):
+            tga_step(3 + s)
+        r.readback_wait()
+        barrier()
+        dt = time.perf_counter() - t0
+        sent = int(tga_sizes[0].sum() + tga_sizes[1].sum()) // 2       # the last two steps' files
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"value": tris_step_all * e_steps / float(t.item()), "unit": "triangles/s",
+                "h2d_bytes_per_step": int(h2d + per_step_uniform_bytes), "d2h_bytes_per_step": sent,
+                "raw_bytes_per_step": int(nviews * P * 3), "steps": e_steps, "ms_per_step": 1e3 * float(t.item()) / e_steps,
+                "note": "frames returned as complete RLE TGA files (byte-identical to TGAImage::write_tga_file), packetised on "
+                        "the device; on a host whose ingest saturates (many GPUs) fewer bytes cross, on one GPU the encode "
+                        "costs more SM time than the raw copy saves"}
+
     e2e = e2e_run(False)
     e2e["note"] = ("per step: upload meshes+textures, render, read back the BGR framebuffer of every frame into pinned "
                    "host memory; the z-buffer stays in HBM for the device-side post passes")
+    if wl.name in ("c1", "c2", "c3"):
+        e2e["tga_files"] = tga_run()
     e2e["with_depth_readback"] = e2e_run(True)   # same, plus the f64 z-buffer of every frame (PCIe bound)
     # the deployment north_star describes: meshes / textures go to HBM once, a step uploads matrices and uniforms only
     e2e["scene_resident"] = e2e_run(False, resident=True)
