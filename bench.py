@@ -129,6 +129,7 @@ def algorithmic_bytes(V, T, P, R, T_vis, C, frames=1):
 
 # kernels that are flavours of one pass share that pass' algorithmic bytes
 PASS_OF = {"k_raster_warp": "k_raster", "k_shade_dense": "k_shade"}
+SYNC_KERNELS = ("k_comm_wait", "k_comm_publish")     # waiting for peers is not work: never the "dominant kernel"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -440,6 +441,14 @@ def measure(args, env, workload, steps, warmup, primary, composite="p2p"):
     T = wl.tris_per_frame
     P = wl.width * wl.height
     balg = algorithmic_bytes(V * nviews, T * nviews, P * nviews, R, tvis, C)
+    if sharded_c4:
+        # per RANK: its triangle range through set-up / bins / raster over the whole picture (R is this rank's own
+        # counter), the unsharded vertex stage, and the shading of the rows it owns
+        t_rank = multigpu.triangle_shard(T, rank, world)[1]
+        balg = algorithmic_bytes(V, t_rank, P, R, tvis // world, C // world)
+        balg["k_shade"] = (12 * P + 96 * tvis + 9 * C + 3 * P) // world
+        if composite == "p2p":
+            balg["k_composite_shade_p2p"] = 12 * P + balg.pop("k_shade")  # every rank reads world x 12 B for P / world pixels
 
     # ---- warm-up + timed region -----------------------------------------------------------------------
     for s in range(warmup):
@@ -538,7 +547,8 @@ def measure(args, env, workload, steps, warmup, primary, composite="p2p"):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     kern = {k: {"launches": int(n), "ms": float(m)} for k, (n, m) in prof.items()}
     total_k_ms = sum(v["ms"] for v in kern.values()) or 1.0
-    dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+    work = {k: v for k, v in kern.items() if k not in SYNC_KERNELS}
+    dom = max(work, key=lambda k: work[k]["ms"]) if work else None
     roof = None
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")

@@ -282,3 +282,90 @@ int main(int argc, char** argv) {
             a = open(out / ("single%d.%s" % (k, ext)), "rb").read()
             b = open(out / ("batch%d.%s" % (k, ext)), "rb").read()
             assert a == b, (k, ext)
+
+
+@pytest.mark.gpu
+def test_two_contexts_from_cpp_equal_one(assets, tmp_path, built):
+    """gl_set_devices: the C++ host layer driving two contexts (both on GPU 0 here).  A batch of cameras is split over
+    the contexts in blocks (config 3, nothing exchanged); one picture is split by triangle ranges and put together by
+    the composite group of the C ABI (config 4: trb_comm_init + trb_composite_group).  Both must equal what a single
+    context renders - z-buffer bits, colours, TGA files."""
+    d, _ = assets
+    src = tmp_path / "multi.cpp"
+    src.write_text(r'''#include <our_gl.h>
+#include <model.h>
+#include <model_manager.h>
+#include <shaders.h>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+static void dump(const std::string& name, const TGAImage& fb) {
+    std::ofstream c(name + ".bgr", std::ios::binary);
+    c.write((const char*)const_cast<TGAImage&>(fb).buffer(), (std::streamsize)fb.width() * fb.height() * 3);
+    std::ofstream z(name + ".z", std::ios::binary);
+    z.write((const char*)zbuffer.data(), (std::streamsize)zbuffer.size() * sizeof(double));
+}
+int main(int argc, char** argv) {
+    const std::string dir = argv[1], out = argv[2];
+    const int ndev = atoi(argv[3]);
+    if (ndev > 1) gl_set_devices(std::vector<int>(ndev, 0));
+    if (gl_device_count() != ndev) return 3;
+    const int W = 320, H = 200;
+    auto head = ModelManager::getInstance().loadModel(dir + "/head.obj");
+    auto eyes = ModelManager::getInstance().loadModel(dir + "/eyes.obj");
+    if (!head || !eyes) return 2;
+    const vec3 key{1.0, 1.2, 1.0}, fill{-1.0, 0.3, 0.5}, rim{0.0, 0.8, -1.0}, center{0.0, 0.0, 0.0}, up{0.0, 1.0, 0.0};
+    const vec3 cams[5] = {vec3{1.0, 1.0, 3.0}, vec3{-2.0, 0.5, 2.5}, vec3{0.3, 2.2, 2.0}, vec3{2.5, -0.4, 1.0}, vec3{0.0, 0.2, -3.0}};
+    init_perspective(60.0, (double)W / H, 0.1, 100.0);
+    init_viewport(0, 0, W, H);
+    std::vector<mat<4, 4>> views;
+    for (int k = 0; k < 5; ++k) { lookat(cams[k], center, up); views.push_back(ModelView); }
+    // config 3: five cameras, blocks of 3 + 2 when there are two contexts
+    gl_begin_views(views, W, H);
+    gl_draw_model_views(*head, 1, mat<4, 4>::identity(), key, fill, rim, 1.0);
+    gl_zbuffer_snapshot();
+    gl_draw_model_views(*eyes, 2, mat<4, 4>::identity(), key, fill, rim, 1.0);
+    TGAImage unused;
+    gl_zbuffer_restore(unused);
+    std::vector<std::string> names;
+    for (int k = 0; k < 5; ++k) names.push_back(out + "/view" + std::to_string(k) + ".tga");
+    if (!gl_write_tga_files(0, names)) return 4;
+    for (int k = 0; k < 5; ++k) { TGAImage fb; gl_read_view(k, fb); dump(out + "/view" + std::to_string(k), fb); }
+    // config 4: one picture, two models, triangle ranges per context + sort-last composite
+    for (int k = 0; k < 2; ++k) {                 // twice: the composite group is reused, frames follow each other without a host barrier
+        TGAImage fb(W, H, TGAImage::RGB);
+        init_zbuffer(W, H);
+        lookat(cams[k], center, up);
+        PhongShader sh(head.get());
+        sh.initLightDirections(key, fill, rim);
+        sh.normal_map_strength = 1.0;
+        gl_draw_model(*head, sh, fb);
+        EyeShader eye(eyes.get());
+        eye.initLightDirections(key, rim);
+        gl_draw_model(*eyes, eye, fb);
+        gl_flush(fb);
+        dump(out + "/picture" + std::to_string(k), fb);
+    }
+    std::cout << "ok" << std::endl;
+    return 0;
+}
+''')
+    host = os.path.join(ROOT, "tinyrenderder_b200", "host")
+    exe = str(tmp_path / "multi")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", host, str(src)] +
+                          [os.path.join(host, f) for f in ("our_gl.cpp", "model.cpp", "model_manager.cpp", "tgaimage.cpp")] +
+                          ["-L", os.path.join(ROOT, "tinyrenderder_b200"), "-ltrb",
+                           "-Wl,-rpath," + os.path.join(ROOT, "tinyrenderder_b200"), "-o", exe])
+    outs = {}
+    for ndev in (1, 2, 3):
+        out = tmp_path / ("multi_out%d" % ndev)
+        out.mkdir()
+        res = subprocess.run([exe, d, str(out), str(ndev)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        outs[ndev] = out
+    files = sorted(f for f in os.listdir(outs[1]))
+    assert len(files) == 5 * 3 + 2 * 2
+    for ndev in (2, 3):
+        for f in files:
+            a, b = open(outs[1] / f, "rb").read(), open(outs[ndev] / f, "rb").read()
+            assert a == b, (ndev, f)

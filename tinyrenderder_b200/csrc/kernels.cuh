@@ -1483,13 +1483,18 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p
     const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
     const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
     if (p >= last) return;
+    // depth keys of every rank first (8 B each over NVLink), ids only from the ranks that hold the minimum - usually one;
+    // a pixel nobody drew (key of +inf everywhere: fragments have finite depths) needs no id at all
     unsigned long long bk = ~0ull;
-    uint32_t bid = VIS_NONE;
+    unsigned holders = 0u;
     for (int r = 0; r < peers.n; ++r) {
         const unsigned long long kk = peers.key[r][p];
-        const uint32_t id = peers.vis[r][p];
-        if (kk < bk || (kk == bk && id < bid)) { bk = kk; bid = id; }
+        if (kk < bk) { bk = kk; holders = 1u << r; }
+        else if (kk == bk) holders |= 1u << r;
     }
+    uint32_t bid = VIS_NONE;
+    if (bk != KEY_PLUS_INF)
+        for (unsigned m = holders; m; m &= m - 1u) bid = min(bid, peers.vis[__ffs(m) - 1][p]);
     f.zkey[p] = bk;
     if (bid == VIS_NONE || bid == VIS_SHADED) { f.vis[p] = bid; return; }
     shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, 0, p, bid);

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <stdexcept>
 #include <string>
 
@@ -33,15 +34,24 @@ struct Backend {
     bool have_key = false;
     std::vector<uint8_t> color_tmp;
     std::vector<uint32_t> vis_tmp;
+    // several GPUs (gl_set_devices): context k of the table
+    int device = -1;             // -1: $TRB_DEVICE or 0
+    size_t view0 = 0;            // gl_begin_views: first global frame index of this context's block
+    struct Handles { std::uint64_t mesh = 0, diffuse = 0, normal = 0, specular = 0; };
+    std::map<const Model*, Handles> models;   // contexts 1..n-1 keep their copies of the models here (context 0: Model::dev_*)
 };
-Backend& B() {
-    static Backend b;
-    return b;
+std::vector<Backend>& BS() {
+    static std::vector<Backend> v(1);
+    return v;
 }
+Backend& B() { return BS()[0]; }     // the primary context: everything single-GPU goes through it
+bool g_comm_ready = false;           // composite group of the contexts formed (same frame size since)
+std::uint64_t g_next_id = 0;         // multi-GPU frames: submission index of the next triangle, the same on every context
 
 [[noreturn]] void die(const char* what, int rc) {
-    std::string msg = std::string("tinyrenderder-b200: ") + what + " failed (rc=" + std::to_string(rc) + "): " +
-                      (B().ctx ? trb_last_error(B().ctx) : "no context");
+    std::string msg = std::string("tinyrenderder-b200: ") + what + " failed (rc=" + std::to_string(rc) + "):";
+    for (Backend& b : BS())
+        if (b.ctx && trb_last_error(b.ctx)[0]) msg += std::string(" ") + trb_last_error(b.ctx);
     std::cerr << msg << std::endl;
     throw std::runtime_error(msg);
 }
@@ -56,9 +66,19 @@ void flat(const mat<4, 4>& m, double* out) {
         for (int j = 0; j < 4; ++j) out[i * 4 + j] = m[i][j];
 }
 
-void upload_model(const Model& m) {
-    if (m.dev_uploaded) return;
-    TrbCtx* c = gl_context();
+TrbCtx* context_of(Backend& b) {
+    if (!b.ctx) {
+        const char* e = std::getenv("TRB_DEVICE");
+        int rc = trb_create(b.device >= 0 ? b.device : (e ? std::atoi(e) : 0), &b.ctx);
+        if (rc != TRB_OK) {
+            b.ctx = nullptr;
+            die("trb_create (no sm_100 device, and there is no CPU fallback)", rc);
+        }
+    }
+    return b.ctx;
+}
+Backend::Handles upload_to(Backend& b, const Model& m) {
+    TrbCtx* c = context_of(b);
     const auto& V = m.getVertices();
     const auto& I = m.getIndices();
     std::vector<float> pos(V.size() * 3), nrm(V.size() * 3), uv(V.size() * 2);
@@ -71,9 +91,10 @@ void upload_model(const Model& m) {
         uv[2 * i + 1] = (float)V[i].texcoord.y;
     }
     std::vector<uint32_t> idx(I.begin(), I.end());
-    TrbMesh h = 0;
-    CK(trb_upload_mesh(c, pos.data(), nrm.data(), uv.data(), (uint32_t)V.size(), idx.data(), idx.size(), &h));
-    m.dev_mesh = h;
+    Backend::Handles h;
+    TrbMesh mh = 0;
+    CK(trb_upload_mesh(c, pos.data(), nrm.data(), uv.data(), (uint32_t)V.size(), idx.data(), idx.size(), &mh));
+    h.mesh = mh;
     auto tex = [&](const TGAImage& t, std::uint64_t& out) {
         out = 0;
         if (t.width() <= 0) return;
@@ -82,12 +103,30 @@ void upload_model(const Model& m) {
         out = th;
     };
     if (m.getMaterialCount() > 0) {  // only materials[0] is ever sampled (model.cpp:416-425)
-        tex(m.getMaterial(0).diffuse, m.dev_diffuse);
-        tex(m.getMaterial(0).normal, m.dev_normal);
-        tex(m.getMaterial(0).specular, m.dev_specular);
+        tex(m.getMaterial(0).diffuse, h.diffuse);
+        tex(m.getMaterial(0).normal, h.normal);
+        tex(m.getMaterial(0).specular, h.specular);
     }
-    m.dev_uploaded = true;
+    return h;
 }
+// the model's buffers in context `slot`, uploaded on first use
+Backend::Handles handles_of(size_t slot, const Model& m) {
+    Backend& b = BS()[slot];
+    if (slot == 0) {
+        if (!m.dev_uploaded) {
+            Backend::Handles h = upload_to(b, m);
+            m.dev_mesh = h.mesh; m.dev_diffuse = h.diffuse; m.dev_normal = h.normal; m.dev_specular = h.specular;
+            m.dev_uploaded = true;
+        }
+        Backend::Handles h;
+        h.mesh = m.dev_mesh; h.diffuse = m.dev_diffuse; h.normal = m.dev_normal; h.specular = m.dev_specular;
+        return h;
+    }
+    auto it = b.models.find(&m);
+    if (it == b.models.end()) it = b.models.emplace(&m, upload_to(b, m)).first;
+    return it->second;
+}
+void upload_model(const Model& m) { (void)handles_of(0, m); }
 
 void fill_uniforms(const TrbDeviceShader& d, TrbPhongUniforms& u) {
     std::memset(&u, 0, sizeof(u));
@@ -133,6 +172,16 @@ bool same_state(const TrbDeviceShader& a, const TrbDeviceShader& c, const double
 }  // namespace
 
 void trb_host_release_model(const Model& m) {
+    for (size_t k = 1; k < BS().size(); ++k) {        // the copies the other contexts hold
+        Backend& o = BS()[k];
+        auto it = o.models.find(&m);
+        if (it == o.models.end() || !o.ctx) continue;
+        if (it->second.mesh) trb_free_mesh(o.ctx, it->second.mesh);
+        if (it->second.diffuse) trb_free_texture(o.ctx, it->second.diffuse);
+        if (it->second.normal) trb_free_texture(o.ctx, it->second.normal);
+        if (it->second.specular) trb_free_texture(o.ctx, it->second.specular);
+        o.models.erase(it);
+    }
     Backend& b = B();
     if (!b.ctx || !m.dev_uploaded) return;
     if (m.dev_mesh) trb_free_mesh(b.ctx, m.dev_mesh);
@@ -143,18 +192,26 @@ void trb_host_release_model(const Model& m) {
     m.dev_uploaded = false;
 }
 
-TrbCtx* gl_context() {
-    Backend& b = B();
-    if (!b.ctx) {
-        const char* e = std::getenv("TRB_DEVICE");
-        int rc = trb_create(e ? std::atoi(e) : 0, &b.ctx);
-        if (rc != TRB_OK) {
-            b.ctx = nullptr;
-            die("trb_create (no sm_100 device, and there is no CPU fallback)", rc);
-        }
-    }
-    return b.ctx;
+TrbCtx* gl_context() { return context_of(B()); }
+
+// ---- several GPUs from one C++ program ------------------------------------------------------------
+void gl_set_devices(const std::vector<int>& devices) {
+    if (devices.empty()) throw std::runtime_error("tinyrenderder-b200: gl_set_devices needs at least one device");
+    for (Backend& b : BS())
+        if (b.ctx) throw std::runtime_error("tinyrenderder-b200: gl_set_devices must be called before the first frame");
+    BS().assign(devices.size(), Backend());
+    for (size_t k = 0; k < devices.size(); ++k) BS()[k].device = devices[k];
+    g_comm_ready = false;
 }
+int gl_device_count() { return (int)BS().size(); }
+
+namespace {
+void shard(size_t total, size_t k, size_t n, size_t& first, size_t& count) {   // contiguous blocks, the first ones take the remainder
+    const size_t base = total / n, rem = total % n;
+    first = k * base + std::min(k, rem);
+    count = base + (k < rem ? 1 : 0);
+}
+}  // namespace
 
 // ---- setup functions: host math through the backend's reference-order helpers ---------------
 void lookat(const vec3 eye, const vec3 center, const vec3 up) {
@@ -176,23 +233,33 @@ void init_viewport(int x, int y, int w, int h) {
         for (int j = 0; j < 4; ++j) Viewport[i][j] = m[i * 4 + j];
 }
 void init_zbuffer(int width, int height) {
-    Backend& b = B();
-    gl_context();
-    b.clip.clear();
-    b.vary.clear();
-    b.have_key = false;
     zbuffer.assign((size_t)width * height, std::numeric_limits<double>::infinity());
-    CK(trb_begin_frame(b.ctx, width, height));
-    b.w = width;
-    b.h = height;
-    b.frame = true;
-    b.views.clear();
+    if (BS().size() > 1 && g_comm_ready && (B().w != width || B().h != height)) {   // the group is tied to a frame size
+        for (Backend& o : BS()) CK(trb_comm_close(o.ctx));
+        g_comm_ready = false;
+    }
+    for (Backend& b : BS()) {    // with several GPUs every context takes part in the picture (sharded draws + composite)
+        context_of(b);
+        b.clip.clear();
+        b.vary.clear();
+        b.have_key = false;
+        CK(trb_begin_frame(b.ctx, width, height));
+        b.w = width;
+        b.h = height;
+        b.frame = true;
+        b.views.clear();
+        b.view0 = 0;
+    }
+    g_next_id = 0;
 }
 
 // ---- drawing -------------------------------------------------------------------------------------
 void rasterize(const Triangle& clip, const IShader& shader, TGAImage& framebuffer) {
     (void)framebuffer;
     require_frame();
+    if (BS().size() > 1)
+        throw std::runtime_error("tinyrenderder-b200: with several GPUs a picture is drawn model by model (gl_draw_model "
+                                 "shards the triangles); rasterize() one triangle at a time is a single-GPU path");
     Backend& b = B();
     TrbDeviceShader d;
     if (!shader.device_shader(d))
@@ -224,27 +291,69 @@ void triangle(const Triangle& clip_verts, const IShader& shader, TGAImage& image
 void gl_draw_model(const Model& model, const IShader& shader, TGAImage& framebuffer) {
     (void)framebuffer;
     require_frame();
-    Backend& b = B();
     submit_pending();
     TrbDeviceShader d;
     if (!shader.device_shader(d))
         throw std::runtime_error("tinyrenderder-b200: gl_draw_model() got a shader without a device implementation");
     d.model = &model;
-    upload_model(model);
-    TrbPhongUniforms u;
-    fill_uniforms(d, u);
     double mv[16], pr[16], vp[16];
     flat(ModelView, mv);
     flat(Perspective, pr);
     flat(Viewport, vp);
-    CK(trb_set_viewport(b.ctx, vp));
     const bool lit = d.kind == TRB_SHADER_PHONG || d.kind == TRB_SHADER_EYE;
-    CK(trb_draw(b.ctx, model.dev_mesh, mv, pr, d.kind, lit ? &u : nullptr, lit ? sizeof(u) : 0, 0,
-                (uint64_t)model.nfaces()));
+    const size_t n = BS().size(), ntris = (size_t)model.nfaces();
+    if (n > 1 && !B().views.empty()) throw std::runtime_error("tinyrenderder-b200: gl_draw_model inside gl_begin_views; use gl_draw_model_views");
+    // one GPU: the whole face loop is one draw.  Several GPUs: context k draws triangle range k of the model with GLOBAL
+    // submission indices, so that gl_composite resolves depth ties exactly like one sequential loop would
+    for (size_t k = 0; k < n; ++k) {
+        Backend& b = BS()[k];
+        const Backend::Handles h = handles_of(k, model);
+        TrbPhongUniforms u;
+        fill_uniforms(d, u);
+        u.diffuse = h.diffuse; u.normal = h.normal; u.specular = h.specular;
+        size_t first = 0, count = ntris;
+        if (n > 1) {
+            shard(ntris, k, n, first, count);
+            CK(trb_set_triangle_id_base(b.ctx, g_next_id + first));
+        }
+        CK(trb_set_viewport(b.ctx, vp));
+        CK(trb_draw(b.ctx, h.mesh, mv, pr, d.kind, lit ? &u : nullptr, lit ? sizeof(u) : 0, first, count));
+    }
+    g_next_id += ntris;
+}
+
+// several GPUs, one picture: the sort-last composite of the contexts' depth / id planes (trb_comm_init once per frame
+// size, then trb_composite_group: the exact (depth, submission index) minimum per pixel, every context shades the rows
+// it owns), rows gathered into `framebuffer` and the global zbuffer
+void gl_composite(TGAImage& framebuffer) {
+    require_frame();
+    const size_t n = BS().size();
+    if (n < 2) { gl_flush(framebuffer); return; }
+    std::vector<TrbCtx*> ctxs;
+    for (Backend& b : BS()) ctxs.push_back(b.ctx);
+    if (!g_comm_ready) {
+        CK(trb_comm_init(ctxs.data(), (int)n));
+        g_comm_ready = true;
+    }
+    CK(trb_composite_group(ctxs.data(), (int)n));
+    const int w = B().w, h = B().h;
+    framebuffer = TGAImage(w, h, TGAImage::RGB);
+    zbuffer.resize((size_t)w * h);
+    std::vector<uint8_t> col((size_t)w * h * 3);
+    std::vector<double> z((size_t)w * h);
+    for (size_t k = 0; k < n; ++k) {
+        int y0 = 0, y1 = 0;
+        CK(trb_comm_rows(ctxs[k], &y0, &y1));
+        CK(trb_read_color(ctxs[k], 0, col.data()));
+        CK(trb_read_depth(ctxs[k], 0, z.data()));
+        std::memcpy(framebuffer.buffer() + (size_t)y0 * w * 3, col.data() + (size_t)y0 * w * 3, (size_t)(y1 - y0) * w * 3);
+        std::memcpy(zbuffer.data() + (size_t)y0 * w, z.data() + (size_t)y0 * w, (size_t)(y1 - y0) * w * sizeof(double));
+    }
 }
 
 void gl_flush(TGAImage& framebuffer) {
     require_frame();
+    if (BS().size() > 1 && B().views.empty()) { gl_composite(framebuffer); return; }
     Backend& b = B();
     submit_pending();
     CK(trb_flush(b.ctx));
@@ -273,13 +382,17 @@ void gl_flush(TGAImage& framebuffer) {
 void gl_zbuffer_snapshot() {
     require_frame();
     submit_pending();
-    CK(trb_depth_snapshot(B().ctx));
+    if (BS().size() > 1 && B().views.empty())
+        throw std::runtime_error("tinyrenderder-b200: z-buffer snapshots of a picture that is split over several GPUs are not supported");
+    for (Backend& b : BS())
+        if (b.frame) CK(trb_depth_snapshot(b.ctx));
 }
 void gl_zbuffer_restore(TGAImage& framebuffer) {
     require_frame();
     submit_pending();
-    CK(trb_depth_restore(B().ctx));
-    gl_flush(framebuffer);
+    for (Backend& b : BS())
+        if (b.frame) CK(trb_depth_restore(b.ctx));
+    if (B().views.empty()) gl_flush(framebuffer);     // a batch of frames is read with gl_read_view / gl_write_tga_files
 }
 
 static void grey_to_image(const std::vector<uint8_t>& g, int w, int h, TGAImage& img) {
@@ -318,84 +431,129 @@ void gl_composite_ao(TGAImage& final_result) {
 
 void gl_begin_views(const std::vector<mat<4, 4>>& views, int width, int height) {
     if (views.empty()) throw std::runtime_error("tinyrenderder-b200: gl_begin_views needs at least one view");
-    Backend& b = B();
-    gl_context();
-    b.clip.clear();
-    b.vary.clear();
-    b.have_key = false;
     zbuffer.assign((size_t)width * height, std::numeric_limits<double>::infinity());
-    CK(trb_begin_batch(b.ctx, width, height, (int)views.size()));
-    b.w = width;
-    b.h = height;
-    b.frame = true;
-    b.views.resize(views.size() * 16);
-    for (size_t v = 0; v < views.size(); ++v) flat(views[v], &b.views[v * 16]);
+    if (g_comm_ready) {                            // a batch of frames is not the picture the composite group was formed for
+        for (Backend& o : BS()) CK(trb_comm_close(o.ctx));
+        g_comm_ready = false;
+    }
+    // frames are independent: with several GPUs context k takes block k of the cameras, nothing is
+    // ever exchanged between the contexts
+    const size_t n = BS().size();
+    for (size_t k = 0; k < n; ++k) {
+        Backend& b = BS()[k];
+        size_t first = 0, count = views.size();
+        shard(views.size(), k, n, first, count);
+        b.clip.clear();
+        b.vary.clear();
+        b.have_key = false;
+        b.views.clear();
+        b.frame = false;
+        b.view0 = first;
+        if (count == 0) continue;
+        context_of(b);
+        CK(trb_begin_batch(b.ctx, width, height, (int)count));
+        b.w = width;
+        b.h = height;
+        b.frame = true;
+        b.views.resize(count * 16);
+        for (size_t v = 0; v < count; ++v) flat(views[first + v], &b.views[v * 16]);
+    }
 }
 
 void gl_draw_model_views(const Model& model, int kind, const mat<4, 4>& model_matrix, const vec3& key_world,
                          const vec3& fill_world, const vec3& rim_world, double normal_map_strength) {
     require_frame();
-    Backend& b = B();
-    if (b.views.empty()) throw std::runtime_error("tinyrenderder-b200: gl_draw_model_views needs gl_begin_views");
+    if (B().views.empty()) throw std::runtime_error("tinyrenderder-b200: gl_draw_model_views needs gl_begin_views");
     if (kind != TRB_SHADER_PHONG && kind != TRB_SHADER_EYE)
         throw std::runtime_error("tinyrenderder-b200: gl_draw_model_views draws PhongShader (1) or EyeShader (2)");
-    upload_model(model);
-    const int n = (int)(b.views.size() / 16);
     double mm[16], pr[16], vp[16];
     flat(model_matrix, mm);
     flat(Perspective, pr);
     flat(Viewport, vp);
-    std::vector<double> mvs((size_t)n * 16), prs((size_t)n * 16), dirs((size_t)n * 9);
-    trb_mat4_mul_batch(b.views.data(), n, mm, mvs.data());            // ModelView_i = view_i * model (main.cpp:653)
-    for (int v = 0; v < n; ++v) std::memcpy(&prs[(size_t)v * 16], pr, sizeof(pr));
     const double kw[3] = {key_world.x, key_world.y, key_world.z}, fw[3] = {fill_world.x, fill_world.y, fill_world.z},
                  rw[3] = {rim_world.x, rim_world.y, rim_world.z};
-    std::vector<double> ke((size_t)n * 3), fe((size_t)n * 3), re((size_t)n * 3);
-    trb_light_dir_eye_batch(mvs.data(), n, kw, ke.data());            // initLightDirections per view
-    trb_light_dir_eye_batch(mvs.data(), n, fw, fe.data());
-    trb_light_dir_eye_batch(mvs.data(), n, rw, re.data());
-    std::vector<TrbPhongUniforms> u((size_t)n);
-    for (int v = 0; v < n; ++v) {
-        std::memset(&u[v], 0, sizeof(TrbPhongUniforms));
-        for (int i = 0; i < 3; ++i) {
-            u[v].key_dir_eye[i] = ke[(size_t)v * 3 + i];
-            u[v].fill_dir_eye[i] = fe[(size_t)v * 3 + i];
-            u[v].rim_dir_eye[i] = re[(size_t)v * 3 + i];
+    for (size_t k = 0; k < BS().size(); ++k) {
+        Backend& b = BS()[k];
+        if (!b.frame || b.views.empty()) continue;
+        const Backend::Handles h = handles_of(k, model);
+        const int n = (int)(b.views.size() / 16);
+        std::vector<double> mvs((size_t)n * 16), prs((size_t)n * 16);
+        trb_mat4_mul_batch(b.views.data(), n, mm, mvs.data());            // ModelView_i = view_i * model (main.cpp:653)
+        for (int v = 0; v < n; ++v) std::memcpy(&prs[(size_t)v * 16], pr, sizeof(pr));
+        std::vector<double> ke((size_t)n * 3), fe((size_t)n * 3), re((size_t)n * 3);
+        trb_light_dir_eye_batch(mvs.data(), n, kw, ke.data());            // initLightDirections per view
+        trb_light_dir_eye_batch(mvs.data(), n, fw, fe.data());
+        trb_light_dir_eye_batch(mvs.data(), n, rw, re.data());
+        std::vector<TrbPhongUniforms> u((size_t)n);
+        for (int v = 0; v < n; ++v) {
+            std::memset(&u[v], 0, sizeof(TrbPhongUniforms));
+            for (int i = 0; i < 3; ++i) {
+                u[v].key_dir_eye[i] = ke[(size_t)v * 3 + i];
+                u[v].fill_dir_eye[i] = fe[(size_t)v * 3 + i];
+                u[v].rim_dir_eye[i] = re[(size_t)v * 3 + i];
+            }
+            u[v].normal_map_strength = normal_map_strength;
+            u[v].diffuse = h.diffuse;
+            u[v].normal = h.normal;
+            u[v].specular = h.specular;
         }
-        u[v].normal_map_strength = normal_map_strength;
-        u[v].diffuse = model.dev_diffuse;
-        u[v].normal = model.dev_normal;
-        u[v].specular = model.dev_specular;
+        CK(trb_set_viewport(b.ctx, vp));
+        CK(trb_draw_batch(b.ctx, h.mesh, mvs.data(), prs.data(), kind, u.data(), sizeof(TrbPhongUniforms), 0,
+                          (uint64_t)model.nfaces()));
     }
-    CK(trb_set_viewport(b.ctx, vp));
-    CK(trb_draw_batch(b.ctx, model.dev_mesh, mvs.data(), prs.data(), kind, u.data(), sizeof(TrbPhongUniforms), 0,
-                      (uint64_t)model.nfaces()));
 }
+
+namespace {
+// the context that renders global frame `view` of the current batch, and the frame's index inside that context
+Backend& owner_of_view(int view, int& local) {
+    for (Backend& b : BS()) {
+        const size_t n = b.views.size() / 16;
+        if (b.frame && (size_t)view >= b.view0 && (size_t)view < b.view0 + n) {
+            local = (int)((size_t)view - b.view0);
+            return b;
+        }
+    }
+    throw std::runtime_error("tinyrenderder-b200: no such frame in the current batch");
+}
+}  // namespace
 
 void gl_read_view(int view, TGAImage& framebuffer) {
     require_frame();
-    Backend& b = B();
+    int local = 0;
+    Backend& b = B().views.empty() ? B() : owner_of_view(view, local);
+    if (B().views.empty()) local = view;
     const size_t n = (size_t)b.w * b.h;
     framebuffer = TGAImage(b.w, b.h, TGAImage::RGB);
-    CK(trb_read_color(b.ctx, view, framebuffer.buffer()));
+    CK(trb_read_color(b.ctx, local, framebuffer.buffer()));
     zbuffer.resize(n);
-    CK(trb_read_depth(b.ctx, view, zbuffer.data()));
+    CK(trb_read_depth(b.ctx, local, zbuffer.data()));
 }
 
 bool gl_write_tga_files(int image, const std::vector<std::string>& filenames) {
     require_frame();
     submit_pending();           // triangles queued by rasterize() belong to the picture (as in gl_write_tga_file)
-    Backend& b = B();
-    const size_t nv = b.views.empty() ? 1 : b.views.size() / 16;
-    if (filenames.size() != nv) throw std::runtime_error("tinyrenderder-b200: gl_write_tga_files needs one name per frame");
-    const size_t cap = (size_t)b.w * b.h * 3 + (size_t)b.w * b.h / 2 + 64;
-    std::vector<std::vector<uint8_t>> files(nv, std::vector<uint8_t>(cap));
-    std::vector<uint8_t*> out(nv);
-    std::vector<uint64_t> sizes(nv);
-    for (size_t v = 0; v < nv; ++v) out[v] = files[v].data();
-    CK(trb_encode_tga(b.ctx, image, out.data(), cap, sizes.data()));
+    size_t total = 0;
+    for (Backend& b : BS())
+        if (b.frame) total += b.views.empty() ? (&b == &B() ? 1 : 0) : b.views.size() / 16;
+    if (filenames.size() != total) throw std::runtime_error("tinyrenderder-b200: gl_write_tga_files needs one name per frame");
+    const size_t cap = (size_t)B().w * B().h * 3 + (size_t)B().w * B().h / 2 + 64;
+    std::vector<std::vector<uint8_t>> files(total, std::vector<uint8_t>(cap));
+    std::vector<uint64_t> sizes(total);
+    // every context packetises its own frames on its own GPU (asynchronously: the GPUs work side by side), then one wait
+    std::vector<std::vector<uint8_t*>> outs(BS().size());
+    size_t at = 0;
+    for (size_t k = 0; k < BS().size(); ++k) {
+        Backend& b = BS()[k];
+        const size_t nv = !b.frame ? 0 : (b.views.empty() ? (k == 0 ? 1 : 0) : b.views.size() / 16);
+        if (nv == 0) continue;
+        for (size_t v = 0; v < nv; ++v) outs[k].push_back(files[at + v].data());
+        CK(trb_encode_tga_async(b.ctx, image, outs[k].data(), cap, &sizes[at]));
+        at += nv;
+    }
+    for (Backend& b : BS())
+        if (b.frame && b.ctx) CK(trb_readback_wait(b.ctx));
     bool ok = true;
-    for (size_t v = 0; v < nv; ++v) {
+    for (size_t v = 0; v < total; ++v) {
         std::ofstream f(filenames[v], std::ios::binary);
         if (!f.is_open()) {
             std::cerr << "can't open " << filenames[v] << "\n";

@@ -101,6 +101,19 @@ void gl_read_view(int view, TGAImage& framebuffer);
 bool gl_write_tga_files(int image, const std::vector<std::string>& filenames);
 struct TrbCtx;
 TrbCtx* gl_context();        // the process-wide device context (device = $TRB_DEVICE, default 0)
+// ---- several GPUs from one C++ program ---------------------------------------------------
+// gl_set_devices({0, 1, 2, 3}) before the first frame: one context per entry (an entry may repeat - two contexts on one
+// GPU, used by the tests).  From then on
+//   * gl_begin_views splits the cameras over the contexts in contiguous blocks (config 3: frames are independent,
+//     nothing is exchanged); gl_draw_model_views / gl_zbuffer_snapshot / restore act on every block, gl_read_view and
+//     gl_write_tga_files address frames by their global index;
+//   * init_zbuffer begins ONE picture on all contexts (config 4): gl_draw_model makes context k draw triangle range k of
+//     the model with global submission indices, and gl_composite (implied by gl_flush) runs the sort-last composite of
+//     the C ABI (trb_comm_init once, trb_composite_group per picture) and gathers the rows into the framebuffer and the
+//     global zbuffer.  The result is bit-identical to the single-GPU picture.
+void gl_set_devices(const std::vector<int>& devices);
+int gl_device_count();
+void gl_composite(TGAImage& framebuffer);
 
 // Frustum culling of whole models (our_gl.h:68-86, our_gl.cpp:212-280): host side, bug-for-bug -
 // the planes are extracted from the matrix as if it were transposed.
