@@ -1004,33 +1004,64 @@ __global__ void __launch_bounds__(RW_WARPS * 32, MINB * (4 / RW_WARPS > 0 ? 4 / 
             const uint32_t flags = exponent_in_window(r3.x) ? 1u : 0u;
             d[5] = make_double2(r4.y, __longlong_as_double((long long)(((unsigned long long)flags << 32) | (a.id_base + t + 1u))));
         }
+        // ---- the rows of the batch's triangles laid end to end and dealt out 32 at a time (a lane per triangle walking
+        //      its own rows would idle two lanes out of three: triangles have ~5 rows, the tallest of a batch 16).  A lane
+        //      finds the triangle of its row like a sample finds its span below, and fetches that triangle's bounds from
+        //      the lane that owns it with shuffles.
         uint32_t nspans = 0;
-        const int maxrows = __reduce_max_sync(FULL, nrows);
-        // s12 of the rows by repeated subtraction: within an ulp of the A.y - (y + 0.5) the exact evaluation uses, far
-        // inside the margins of the bounds
-        double s12 = E.ay - pixel_centre(Y0);
-        for (int r = 0; r < maxrows; ++r, s12 -= 1.0) {
+        uint32_t rincl = (uint32_t)nrows;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, rincl, o);
+            if (lane >= o) rincl += y;
+        }
+        const uint32_t rfirst = rincl - (uint32_t)nrows, R = __shfl_sync(FULL, rincl, 31);
+        const uint32_t rfirst_s = nrows > 0 ? rfirst : 0x7fffffffu;
+        // tile-local bbox corner + which side each edge bounds, in one word
+        const uint32_t geo = (uint32_t)(X0 - tx0) | ((uint32_t)(X1 - tx0) << 4) | ((uint32_t)(Y0 - ty0) << 8) |
+                             (E.m0 == INT_MAX ? 0x1000u : 0u) | (E.m1 == INT_MAX ? 0x2000u : 0u) | (E.m2 == INT_MAX ? 0x4000u : 0u);
+        uint32_t rbefore = 0;
+        for (uint32_t rb = 0; rb < R; rb += 32) {
+            unsigned rstart;
+            asm("shl.b32 %0, 1, %1;" : "=r"(rstart) : "r"(rfirst_s - rb));
+            const unsigned rstarts = __reduce_or_sync(FULL, rstart);
+            const int e = (int)rbefore + __popc(rstarts & lane_le) - 1;
+            rbefore += (uint32_t)__popc(rstarts);
+            TRB_CHECK(e >= 0 && e < 32);
+            const bool ract = rb + lane < R;
+            const int r = (int)(rb + lane - __shfl_sync(FULL, rfirst, e));
+            SpanEdges Ee;
+            Ee.ay = __shfl_sync(FULL, E.ay, e);
+            Ee.a0 = __shfl_sync(FULL, E.a0, e); Ee.b0 = __shfl_sync(FULL, E.b0, e);
+            Ee.a1 = __shfl_sync(FULL, E.a1, e); Ee.b1 = __shfl_sync(FULL, E.b1, e);
+            Ee.a2 = __shfl_sync(FULL, E.a2, e); Ee.b2 = __shfl_sync(FULL, E.b2, e);
+            const uint32_t ge = __shfl_sync(FULL, geo, e);
+            Ee.m0 = (ge & 0x1000u) ? INT_MAX : INT_MIN;
+            Ee.m1 = (ge & 0x2000u) ? INT_MAX : INT_MIN;
+            Ee.m2 = (ge & 0x4000u) ? INT_MAX : INT_MIN;
+            const int eX0 = tx0 + (int)(ge & 15u), eX1 = tx0 + (int)((ge >> 4) & 15u), ey = ty0 + (int)((ge >> 8) & 15u) + r;
             int xa = 0, xb = -1;
-            if (r < nrows) span_of_row(E, s12, X0, X1, xa, xb);
+            if (ract) span_of_row(Ee, Ee.ay - pixel_centre(ey), eX0, eX1, xa, xb);
 #if defined(TRB_DEBUG_CHECKS)
-            if (r < nrows) {      // the skipped columns must all fail the reference's test
-                const double2* q = reinterpret_cast<const double2*>(&sm.recs[lane]);
+            if (ract) {           // the skipped columns must all fail the reference's test
+                const double2* q = reinterpret_cast<const double2*>(&sm.recs[e]);
                 TriSetup ts;
                 ts.ax = q[0].x; ts.ay = q[0].y; ts.s00 = q[1].x; ts.s01 = q[1].y; ts.s10 = q[2].x; ts.s11 = q[2].y;
                 ts.uz = q[3].x; ts.ruz = q[3].y; ts.z0 = q[4].x; ts.z1 = q[4].y; ts.z2 = q[5].x;
                 ts.x0 = ts.y0 = ts.x1 = ts.y1 = 0;
-                for (int x = X0; x <= X1; ++x) {
+                assert(r >= 0 && ey < ty0 + TILE);
+                for (int x = eX0; x <= eX1; ++x) {
                     double bb[3], zz;
-                    if (x < xa || x > xb) assert(!eval_sample(ts, x, Y0 + r, bb, zz));
+                    if (x < xa || x > xb) assert(!eval_sample(ts, x, ey, bb, zz));
                 }
             }
 #endif
             const bool ne = xa <= xb;
             const unsigned nb = __ballot_sync(FULL, ne);
             if (ne) {
-                TRB_CHECK(xa >= X0 && xb <= X1 && nspans + __popc(nb & lane_lt) < (unsigned)RW_SPAN_CAP);
-                sm.spans[nspans + __popc(nb & lane_lt)] = (uint32_t)lane | ((uint32_t)(xa - tx0) << 5) |
-                                                          ((uint32_t)(Y0 + r - ty0) << 9) | ((uint32_t)(xb - xa) << 13);
+                TRB_CHECK(xa >= eX0 && xb <= eX1 && nspans + __popc(nb & lane_lt) < (unsigned)RW_SPAN_CAP);
+                sm.spans[nspans + __popc(nb & lane_lt)] = (uint32_t)e | ((uint32_t)(xa - tx0) << 5) |
+                                                          ((uint32_t)(ey - ty0) << 9) | ((uint32_t)(xb - xa) << 13);
             }
             nspans += (uint32_t)__popc(nb);
         }
@@ -1085,13 +1116,22 @@ __global__ void __launch_bounds__(RW_WARPS * 32, MINB * (4 / RW_WARPS > 0 ? 4 / 
                 // whatever the order.
                 bool clash = false;
                 unsigned rank = 0;
+                // the pixel's current (key, id): requested before the collision test so that the two latencies overlap
+                const unsigned long long cur0 = sm.zk[frag ? p : 0];
+                const uint32_t vid0 = sm.vid[frag ? p : 0];
                 if (starts >> 1) {
                     const unsigned peers = __match_any_sync(FULL, frag ? (unsigned)p : 256u + (unsigned)lane);
                     rank = __popc(peers & lane_lt);
                     clash = __any_sync(FULL, rank != 0u);
                 }
                 if (!clash) {
-                    if (frag) apply(p, key, gid_e);
+                    if (frag && (key < cur0 || (key == cur0 && gid_e < vid0))) {
+                        sm.zk[p] = key;
+                        sm.vid[p] = gid_e;
+                        ++touched;
+                        const unsigned kh = (unsigned)(key >> 32), kl = (unsigned)key;
+                        if (kh < zmin_hi || (kh == zmin_hi && kl < zmin_lo)) { zmin_hi = kh; zmin_lo = kl; }
+                    }
                 } else {
                     const unsigned turns = __reduce_max_sync(FULL, rank);
                     for (unsigned r = 0; r <= turns; ++r) {
