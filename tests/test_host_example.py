@@ -369,3 +369,99 @@ int main(int argc, char** argv) {
         for f in files:
             a, b = open(outs[1] / f, "rb").read(), open(outs[ndev] / f, "rb").read()
             assert a == b, (ndev, f)
+
+
+MODEL_TOOL = os.path.join(ROOT, "tinyrenderder_b200", "host", "bin", "model_tool")
+
+
+def _load_with_tool(path):
+    res = subprocess.run([MODEL_TOOL, path], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    out = {"sub": [], "mat": [], "v": []}
+    for line in res.stdout.splitlines():
+        f = line.split()
+        if f[0] == "vertices":
+            out["counts"] = (int(f[1]), int(f[3]), int(f[5]), int(f[7]))
+        elif f[0] == "submesh":
+            out["sub"].append({"name": f[3], "start": int(f[5]), "count": int(f[7]), "material": int(f[9]), "vertexStart": int(f[11]),
+                               "normals": int(f[13]), "uvs": int(f[15])})
+        elif f[0] == "material":
+            out["mat"].append(tuple(int(f[k]) for k in (3, 5, 7, 9)))
+        elif f[0] == "indices":
+            out["idx"] = [int(x) for x in f[1:]]
+        elif f[0] == "v":
+            out["v"].append([float(f[k]) for k in (1, 2, 3, 5, 6, 7, 9, 10)])
+    return out
+
+
+def test_loader_flattens_submeshes_and_reads_materials(tmp_path, built):
+    """model.cpp:143-205 / 207-267 / 269-312 without Assimp: sub-meshes per usemtl / o / g with their own vertex numbering
+    flattened with vertexStart, materials in newmtl order with textures from the .mtl or the <stem>_*.tga fallback, normals
+    regenerated for ALL vertices as soon as one is missing"""
+    d = tmp_path
+    rng = np.random.default_rng(0)
+    for name, size in (("skin.tga", 8), ("cloth_nm.tga", 4), ("thing_spec.tga", 2), ("thing_diffuse.tga", 16)):
+        write_tga(str(d / name), rng.integers(0, 255, (size, size, 3)).astype(np.uint8))
+    (d / "thing.mtl").write_text("# two materials\nnewmtl skin\nKd 1 1 1\nmap_Kd skin.tga\n\nnewmtl cloth\nmap_Bump -bm 1.0 cloth_nm.tga\n"
+                                 "map_Kd missing_file.tga\n")
+    (d / "thing.obj").write_text("""mtllib thing.mtl
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0
+v 0 0 1
+v 1 0 1
+vt 0 0
+vt 1 0
+vt 1 1
+vn 0 0 1
+o body
+usemtl skin
+f 1/1/1 2/2/1 3/3/1 4/1/1
+usemtl cloth
+f 1/1/1 2/2/1 6/3/1
+g tail
+f 5 6 3
+usemtl skin
+f 5/1 1/2 4/3
+""")
+    m = _load_with_tool(str(d / "thing.obj"))
+    # four sub-meshes: (body, skin) quad = 2 triangles; (body, cloth) 1; (tail, cloth) 1 without vt/vn; (tail, skin) 1 without vn
+    assert [(s["name"], s["material"], s["count"]) for s in m["sub"]] == [("body", 0, 6), ("body", 1, 3), ("tail", 1, 3), ("tail", 0, 3)]
+    assert [s["start"] for s in m["sub"]] == [0, 6, 9, 12]
+    assert [s["vertexStart"] for s in m["sub"]] == [0, 4, 7, 10]         # vertices are NOT shared across sub-meshes
+    assert m["counts"] == (13, 15, 4, 2)
+    assert m["idx"] == [0, 1, 2, 0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12]   # fan triangulation + vertexStart
+    assert [(s["normals"], s["uvs"]) for s in m["sub"]] == [(1, 1), (1, 1), (0, 0), (0, 1)]
+    # material 0: diffuse from the .mtl, specular from the fallback name; material 1: normal map from the .mtl (options
+    # skipped), its diffuse names a file that does not exist -> fallback thing_diffuse.tga
+    assert m["mat"] == [(8, 0, 2, 0), (16, 4, 2, 0)]
+    # uv.y is flipped (aiProcess_FlipUVs); one vertex lacked a normal, so ALL were regenerated from the faces, unit length
+    assert m["v"][1][6:] == [1.0, 1.0] and m["v"][2][6:] == [1.0, 0.0]
+    nrm = np.array([v[3:6] for v in m["v"]])
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-6)
+    assert np.allclose(nrm[:4], [[0, 0, 1]] * 4)                            # the quad keeps +z; computed, not copied
+
+
+def test_grouped_obj_renders_like_the_flat_one(assets, tmp_path, ref_api):
+    """the same head, written once as a single mesh and once split into groups / materials in the middle of its face list:
+    the flattened arrays differ (vertices are duplicated at the seams) but the reference's rasterize() draws the same picture"""
+    need(EXAMPLE_REF)
+    d, sc = assets
+    import shutil
+    g = tmp_path / "grouped"
+    shutil.copytree(d, g)
+    head = open(os.path.join(d, "head.obj")).read().splitlines()
+    faces = [i for i, l in enumerate(head) if l.startswith("f ")]
+    cut1, cut2 = faces[len(faces) // 3], faces[2 * len(faces) // 3]
+    head.insert(cut2, "usemtl b\ng lower")
+    head.insert(cut1, "usemtl a")
+    head.insert(faces[0], "mtllib head.mtl\no head\nusemtl b")
+    (g / "head.obj").write_text("\n".join(head) + "\n")
+    (g / "head.mtl").write_text("newmtl b\nmap_Kd head_diffuse.tga\nnewmtl a\n")
+    flat = run_example(EXAMPLE_REF, d, str(tmp_path / "flat"))
+    grouped = run_example(EXAMPLE_REF, str(g), str(tmp_path / "grp"))
+    assert np.array_equal(flat["z"].view(np.uint64), grouped["z"].view(np.uint64))
+    assert np.array_equal(flat["phong"], grouped["phong"])
+    m = _load_with_tool(str(g / "head.obj"))
+    assert m["counts"][2] == 3 and m["counts"][3] == 2

@@ -23,19 +23,22 @@ Model::Model(const std::string& fn) : filename(fn) {
 Model::~Model() { unload(); }
 
 Model::Model(const Model& o)
-    : vertices(o.vertices), indices(o.indices), materials(o.materials), filename(o.filename), directory(o.directory),
+    : vertices(o.vertices), indices(o.indices), materials(o.materials), subMeshes(o.subMeshes),
+      materialNames(o.materialNames), materialMaps(o.materialMaps), filename(o.filename), directory(o.directory),
       isLoaded(o.isLoaded), localAABB(o.localAABB) {}   // dev_* stay 0: the copy uploads its own buffers on first use
 Model& Model::operator=(const Model& o) {
     if (this == &o) return *this;
     unload();                                            // releases this model's device buffers
     vertices = o.vertices; indices = o.indices; materials = o.materials;
+    subMeshes = o.subMeshes; materialNames = o.materialNames; materialMaps = o.materialMaps;
     filename = o.filename; directory = o.directory; isLoaded = o.isLoaded; localAABB = o.localAABB;
     return *this;
 }
 Model::Model(Model&& o) noexcept
     : dev_mesh(o.dev_mesh), dev_diffuse(o.dev_diffuse), dev_normal(o.dev_normal), dev_specular(o.dev_specular),
       dev_uploaded(o.dev_uploaded), vertices(std::move(o.vertices)), indices(std::move(o.indices)),
-      materials(std::move(o.materials)), filename(std::move(o.filename)), directory(std::move(o.directory)),
+      materials(std::move(o.materials)), subMeshes(std::move(o.subMeshes)), materialNames(std::move(o.materialNames)),
+      materialMaps(std::move(o.materialMaps)), filename(std::move(o.filename)), directory(std::move(o.directory)),
       isLoaded(o.isLoaded), localAABB(o.localAABB) {
     o.dev_mesh = o.dev_diffuse = o.dev_normal = o.dev_specular = 0;
     o.dev_uploaded = false;
@@ -45,6 +48,7 @@ Model& Model::operator=(Model&& o) noexcept {
     if (this == &o) return *this;
     unload();
     vertices = std::move(o.vertices); indices = std::move(o.indices); materials = std::move(o.materials);
+    subMeshes = std::move(o.subMeshes); materialNames = std::move(o.materialNames); materialMaps = std::move(o.materialMaps);
     filename = std::move(o.filename); directory = std::move(o.directory); isLoaded = o.isLoaded; localAABB = o.localAABB;
     dev_mesh = o.dev_mesh; dev_diffuse = o.dev_diffuse; dev_normal = o.dev_normal; dev_specular = o.dev_specular;
     dev_uploaded = o.dev_uploaded;
@@ -61,6 +65,9 @@ void Model::unload() {
     vertices.clear();
     indices.clear();
     materials.clear();
+    subMeshes.clear();
+    materialNames.clear();
+    materialMaps.clear();
     isLoaded = false;
 }
 
@@ -84,23 +91,61 @@ bool Model::load() {
         return false;
     }
     computeAABB();
-    // textures by the fallback naming of model.cpp:252-262: <dir>/<stem>_diffuse.tga, _nm.tga, _spec.tga
+    // materials: one per newmtl block (or a single default one, model.cpp:119-123); per texture slot the path the .mtl
+    // names, else the fallback naming of model.cpp:252-262: <dir>/<stem>_diffuse.tga, _nm.tga, _spec.tga, _emission.tga
     materials.clear();
-    materials.emplace_back();
+    materials.resize(std::max<size_t>(1, materialNames.size()));
     size_t slash = filename.find_last_of("/\\");
     std::string base = slash == std::string::npos ? filename : filename.substr(slash + 1);
     size_t dot = base.find_last_of('.');
     std::string stem = directory + "/" + (dot == std::string::npos ? base : base.substr(0, dot));
-    auto try_load = [](TGAImage& img, const std::string& p) {
+    auto try_load = [](TGAImage& img, const std::string& p) -> bool {
         std::ifstream probe(p, std::ios::binary);
-        if (!probe.is_open()) return;  // absent texture: the accessors fall back (model.cpp:416,429,447)
+        if (!probe.is_open()) return false;  // absent texture: the accessors fall back (model.cpp:416,429,447)
         probe.close();
-        if (!img.read_tga_file(p)) img = TGAImage();
+        if (!img.read_tga_file(p)) { img = TGAImage(); return false; }
+        return true;
     };
-    try_load(materials[0].diffuse, stem + "_diffuse.tga");
-    try_load(materials[0].normal, stem + "_nm.tga");
-    try_load(materials[0].specular, stem + "_spec.tga");
+    for (size_t m = 0; m < materials.size(); ++m) {
+        const MtlMaps maps = m < materialMaps.size() ? materialMaps[m] : MtlMaps();
+        auto slot = [&](TGAImage& img, const std::string& named, const char* fallback) {
+            if (!named.empty() && try_load(img, directory + "/" + named)) return;
+            try_load(img, stem + fallback);
+        };
+        slot(materials[m].diffuse, maps.diffuse, "_diffuse.tga");
+        slot(materials[m].normal, maps.normal, "_nm.tga");
+        slot(materials[m].specular, maps.specular, "_spec.tga");
+        slot(materials[m].emission, maps.emission, "_emission.tga");
+    }
     isLoaded = true;
+    return true;
+}
+
+bool Model::loadMtl(const std::string& path) {
+    std::ifstream in(path);
+    if (!in.is_open()) return false;
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ss(line);
+        std::string tag, value;
+        ss >> tag;
+        if (tag.empty() || tag[0] == '#') continue;
+        if (tag == "newmtl") {
+            ss >> value;
+            materialNames.push_back(value);
+            materialMaps.emplace_back();
+            continue;
+        }
+        if (materialMaps.empty()) continue;
+        // the last token of the statement is the file name (options like -bm 1.0 come before it)
+        std::string tok;
+        while (ss >> tok) value = tok;
+        MtlMaps& m = materialMaps.back();
+        if (tag == "map_Kd") m.diffuse = value;
+        else if (tag == "map_Bump" || tag == "map_bump" || tag == "bump" || tag == "norm" || tag == "map_Kn") m.normal = value;
+        else if (tag == "map_Ks") m.specular = value;
+        else if (tag == "map_Ke") m.emission = value;
+    }
     return true;
 }
 
@@ -109,9 +154,21 @@ bool Model::loadObj(const std::string& path) {
     if (!in.is_open()) return false;
     std::vector<vec3> P, N;
     std::vector<vec2> T;
-    std::map<std::tuple<int, int, int>, unsigned int> weld;
-    bool had_normals = false;
+    std::map<std::tuple<int, int, int>, unsigned int> weld;   // per sub-mesh
+    std::string pending_name;          // set by o / g: the next faces open a new sub-mesh
+    int pending_material = 0;
+    bool open_new = true;
     std::string line;
+    auto begin_submesh = [&]() {
+        SubMesh sm;
+        sm.name = pending_name;
+        sm.startIndex = (unsigned int)indices.size();
+        sm.materialIndex = pending_material;
+        sm.vertexStart = (unsigned int)vertices.size();
+        subMeshes.push_back(sm);
+        weld.clear();                  // identical vertices are joined per mesh, not across meshes
+        open_new = false;
+    };
     while (std::getline(in, line)) {
         if (line.size() < 2) continue;
         std::istringstream ss(line);
@@ -132,7 +189,24 @@ bool Model::loadObj(const std::string& path) {
             ss >> u >> v;
             vec2 t; t.x = u; t.y = (float)(1.0f - v);  // aiProcess_FlipUVs
             T.push_back(t);
+        } else if (tag == "mtllib") {
+            std::string name;
+            ss >> name;
+            loadMtl(directory + "/" + name);
+        } else if (tag == "usemtl") {
+            std::string name;
+            ss >> name;
+            int idx = 0;
+            for (size_t m = 0; m < materialNames.size(); ++m)
+                if (materialNames[m] == name) idx = (int)m;
+            if (idx != pending_material || subMeshes.empty()) open_new = true;
+            pending_material = idx;
+        } else if (tag == "o" || tag == "g") {
+            ss >> pending_name;
+            open_new = true;
         } else if (tag == "f") {
+            if (open_new) begin_submesh();
+            SubMesh& sm = subMeshes.back();
             std::vector<unsigned int> poly;
             std::string tok;
             while (ss >> tok) {
@@ -153,26 +227,32 @@ bool Model::loadObj(const std::string& path) {
                 if (it == weld.end()) {
                     Vertex v;
                     v.position = P[vi];
-                    if (ti >= 0 && ti < (int)T.size()) v.texcoord = T[ti];
-                    if (ni >= 0 && ni < (int)N.size()) { v.normal = N[ni]; had_normals = true; }
-                    it = weld.emplace(key, (unsigned int)vertices.size()).first;
+                    if (ti >= 0 && ti < (int)T.size()) { v.texcoord = T[ti]; sm.hasTexCoords = true; }
+                    if (ni >= 0 && ni < (int)N.size()) { v.normal = N[ni]; sm.hasNormals = true; }
+                    // the sub-mesh numbers its vertices from 0; flattening adds vertexStart (model.cpp:152, 195)
+                    it = weld.emplace(key, (unsigned int)(vertices.size() - sm.vertexStart)).first;
                     vertices.push_back(v);
                 }
-                poly.push_back(it->second);
+                poly.push_back(sm.vertexStart + it->second);
             }
             for (size_t k = 1; k + 1 < poly.size(); ++k) {  // fan triangulation
                 indices.push_back(poly[0]);
                 indices.push_back(poly[k]);
                 indices.push_back(poly[k + 1]);
             }
+            sm.indexCount = (unsigned int)indices.size() - sm.startIndex;
         }
     }
-    generateNormalsIfNeeded(had_normals);
+    generateNormalsIfNeeded(false);
     return !vertices.empty() && !indices.empty();
 }
 
-void Model::generateNormalsIfNeeded(bool had_normals) {
-    if (had_normals) return;
+void Model::generateNormalsIfNeeded(bool) {
+    // model.cpp:269-312: as soon as ONE vertex has no usable normal, all normals are rebuilt from the faces
+    bool needs = false;
+    for (const Vertex& v : vertices)
+        if (norm(v.normal) < 0.001) { needs = true; break; }
+    if (!needs) return;
     for (Vertex& v : vertices) v.normal = vec3();
     for (size_t f = 0; f + 2 < indices.size(); f += 3) {
         Vertex &a = vertices[indices[f]], &b = vertices[indices[f + 1]], &c = vertices[indices[f + 2]];
@@ -180,8 +260,8 @@ void Model::generateNormalsIfNeeded(bool had_normals) {
         a.normal = a.normal + n; b.normal = b.normal + n; c.normal = c.normal + n;
     }
     for (Vertex& v : vertices) {
-        vec3 n = normalized(v.normal);
-        if (norm(n) == 0) { n = vec3(); n.z = 1; }
+        vec3 n = vec3();
+        if (norm(v.normal) > 0.001) n = normalized(v.normal); else n.z = 1;   // model.cpp:305-311
         v.normal.x = (float)n.x; v.normal.y = (float)n.y; v.normal.z = (float)n.z;  // keep fp32-representable
     }
 }

@@ -4,9 +4,16 @@
 // the oracle build (reference headers + reference our_gl.cpp) and in the device build.
 //
 // Loader conventions (the reference delegates these to Assimp, whose output order is unpinned):
-// faces in file order, polygons fan-triangulated, one vertex per distinct (v,vt,vn) tuple in
-// first-seen order (aiProcess_JoinIdenticalVertices), uv.y := 1 - uv.y (aiProcess_FlipUVs,
-// model.cpp:93), smooth normals generated when the file has none (aiProcess_GenNormals).
+// faces in file order, polygons fan-triangulated, uv.y := 1 - uv.y (aiProcess_FlipUVs, model.cpp:93).
+// A new SUB-MESH starts at every `usemtl` / `o` / `g` statement that is followed by faces (Assimp makes one aiMesh per
+// object and material); inside a sub-mesh there is one vertex per distinct (v,vt,vn) tuple in first-seen order
+// (aiProcess_JoinIdenticalVertices works per mesh), and the sub-meshes are flattened into ONE vertex / index array with
+// the sub-mesh's vertexStart added to its indices (processMesh, model.cpp:143-205).  Materials are the `newmtl` blocks of
+// the `mtllib` file in file order (a file without one gets a single default material); a material's textures come from
+// its map_Kd / map_Bump (bump, norm) / map_Ks / map_Ke statements and, when the .mtl names none or the file does not load,
+// from <stem>_diffuse.tga / _nm.tga / _spec.tga / _emission.tga next to the model (loadTexture, model.cpp:228-267).  Like
+// the reference only materials[0] is ever sampled (model.cpp:416-459).  When any vertex lacks a normal, ALL normals are
+// regenerated from the faces (generateNormalsIfNeeded, model.cpp:269-312).
 #pragma once
 #include <geometry.h>
 #include <tgaimage.h>
@@ -19,6 +26,13 @@ struct Vertex {  // model.h:14-20 (tangent space is computed by the reference bu
     vec3 position, normal;
     vec2 texcoord;
     vec3 tangent, bitangent;
+};
+struct SubMesh {  // model.h:23-31: a run of the flattened index array that shares a material
+    std::string name;
+    unsigned int startIndex = 0, indexCount = 0;
+    int materialIndex = 0;
+    unsigned int vertexStart = 0;   // offset added to the sub-mesh's own vertex numbering (model.cpp:152, 195)
+    bool hasNormals = false, hasTexCoords = false;
 };
 struct MaterialTextures {  // model.h:34-45
     TGAImage diffuse, normal, specular, emission;
@@ -45,6 +59,8 @@ public:
     int getVertexCount() const { return (int)vertices.size(); }
     int getIndexCount() const { return (int)indices.size(); }
     int getMaterialCount() const { return (int)materials.size(); }
+    int getSubMeshCount() const { return (int)subMeshes.size(); }
+    const SubMesh& getSubMesh(int i) const { return subMeshes[i]; }
     int nverts() const { return getVertexCount(); }
     int nfaces() const { return getIndexCount() / 3; }
     bool hasNormalMap() const { return !materials.empty() && materials[0].hasNormal(); }
@@ -78,6 +94,11 @@ private:
     std::vector<Vertex> vertices;
     std::vector<unsigned int> indices;
     std::vector<MaterialTextures> materials;
+    std::vector<SubMesh> subMeshes;
+    std::vector<std::string> materialNames;                       // order of the newmtl statements (material index)
+    struct MtlMaps { std::string diffuse, normal, specular, emission; };
+    std::vector<MtlMaps> materialMaps;                            // texture paths named by the .mtl file
+    bool loadMtl(const std::string& path);
     std::string filename, directory;
     bool isLoaded = false;
     AABB localAABB;
