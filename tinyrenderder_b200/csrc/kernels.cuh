@@ -13,6 +13,7 @@
 // All arithmetic is in exact.cuh; nothing here reorders a floating-point operation.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, nothing links libcuda)
 #include <cassert>
 #include "exact.cuh"
 // -DTRB_DEBUG_CHECKS builds a variant whose kernels assert their own indexing invariants (bin slots,
@@ -932,11 +933,47 @@ __device__ __forceinline__ void span_of_row(const SpanEdges& E, double s12, int 
     xa = max(X0, lo == INT_MAX ? INT_MIN : -lo);                                // -INT_MIN wraps to INT_MIN: no bound, safe
 }
 
+// ---- TMA (cp.async.bulk.tensor) staging of a tile: the depth-key and id planes are 3-D tensors [view][y][x]; a 16x16
+// box lands in shared memory exactly in the row-major order the warp uses, rows and columns beyond the frame come in
+// as zeros (key 0 never loses) and are clipped on the way back.  One lane issues the copies; their completion is
+// counted in bytes on the warp's mbarrier, so the tile travels while the warp already gathers its first batch of
+// triangle records.  Frames whose row pitch is not a multiple of 16 bytes (width not a multiple of 4) cannot be
+// described to the copy engine and take the LDG / STG path.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();    // a copy that never lands must fail the launch, not hang the GPU
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int v, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(v), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int x, int y, int v, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(x), "r"(y), "r"(v) : "memory");
+}
+struct TileMaps {           // tensor maps of the frame's two planes, passed by value in the kernel parameters
+    CUtensorMap key, vis;
+};
+
 // MINB = resident CTAs per SM the register allocation aims for.  TRB_RW_BLOCKS picks the instantiation at run time.
 constexpr int RW_BLOCKS_DEFAULT = 6;
 template <int MINB>
-__global__ void __launch_bounds__(RW_WARPS * 32, MINB * (4 / RW_WARPS > 0 ? 4 / RW_WARPS : 1)) k_raster_warp(FrameDev f, RasterArgs a) {
-    __shared__ WarpTile tiles[RW_WARPS];
+__global__ void __launch_bounds__(RW_WARPS * 32, MINB * (4 / RW_WARPS > 0 ? 4 / RW_WARPS : 1))
+k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, const int use_tma) {
+    __shared__ __align__(128) WarpTile tiles[RW_WARPS];
+    __shared__ __align__(8) unsigned long long tile_bar[RW_WARPS];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = RW_WARPS > 1 ? (int)(threadIdx.x >> 5) : 0;
     const int tile = blockIdx.x * RW_WARPS + warp, view = blockIdx.y;
@@ -955,14 +992,26 @@ __global__ void __launch_bounds__(RW_WARPS * 32, MINB * (4 / RW_WARPS > 0 ? 4 / 
     // first batch's bin entry: in flight while the tile is staged
     TRB_CHECK((unsigned long long)off + n <= a.ctl->total);
     uint32_t t_next = lane < (int)n ? __ldg(a.bins + off + lane) : 0u;
-    #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
-        const bool valid = x < f.W && y < f.H;
-        const size_t gp = (size_t)y * f.W + x;
-        sm.zk[p] = valid ? gz[gp] : 0ull;          // key 0 never loses: pixels outside the frame stay untouched
-        sm.vid[p] = valid ? gv[gp] : VIS_NONE;
+    const uint32_t bar = smem_addr(&tile_bar[warp]);
+    if (use_tma) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, (uint32_t)(sizeof(sm.zk) + sizeof(sm.vid)));
+            tma_load_3d(smem_addr(sm.zk), &maps.key, tx0, ty0, view, bar);
+            tma_load_3d(smem_addr(sm.vid), &maps.vis, tx0, ty0, view, bar);
+        }
+        __syncwarp();
+    } else {
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
+            const bool valid = x < f.W && y < f.H;
+            const size_t gp = (size_t)y * f.W + x;
+            sm.zk[p] = valid ? gz[gp] : 0ull;          // key 0 never loses: pixels outside the frame stay untouched
+            sm.vid[p] = valid ? gv[gp] : VIS_NONE;
+        }
     }
+    bool tile_landed = !use_tma;
     uint32_t covered = 0, touched = 0;
     unsigned zmin_hi = 0xffffffffu, zmin_lo = 0xffffffffu;   // smallest key written (min_z of our_gl.cpp:197)
     auto apply = [&](int p, unsigned long long key, uint32_t gid) {
@@ -1066,6 +1115,10 @@ __global__ void __launch_bounds__(RW_WARPS * 32, MINB * (4 / RW_WARPS > 0 ? 4 / 
             nspans += (uint32_t)__popc(nb);
         }
         __syncwarp();
+        if (!tile_landed) {            // the tile has been travelling while the records were gathered and the spans listed
+            mbar_wait(bar, 0);
+            tile_landed = true;
+        }
         // ---- the spans, 32 at a time: their samples are laid end to end and dealt out to the lanes
         for (uint32_t g = 0; g < nspans; g += 32) {
             const bool sv = g + lane < nspans;
@@ -1150,13 +1203,24 @@ __global__ void __launch_bounds__(RW_WARPS * 32, MINB * (4 / RW_WARPS > 0 ? 4 / 
     if (covered == 0) return;
     touched = __reduce_add_sync(FULL, touched);
     if (touched) {
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
-            if (x < f.W && y < f.H) {
-                const size_t gp = (size_t)y * f.W + x;
-                gz[gp] = sm.zk[p];
-                gv[gp] = sm.vid[p];
+        if (use_tma) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' shared-memory writes -> the copy engine
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_3d(&maps.key, tx0, ty0, view, smem_addr(sm.zk));
+                tma_store_3d(&maps.vis, tx0, ty0, view, smem_addr(sm.vid));
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile has left shared memory
+            }
+        } else {
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
+                if (x < f.W && y < f.H) {
+                    const size_t gp = (size_t)y * f.W + x;
+                    gz[gp] = sm.zk[p];
+                    gv[gp] = sm.vid[p];
+                }
             }
         }
     }

@@ -315,6 +315,13 @@ struct TrbCtx {
     uint32_t warp_max = WARP_MAX_DEFAULT;
     int rw_blocks = RW_BLOCKS_DEFAULT;   // k_raster_warp instantiation (resident CTAs per SM the registers are sized for)
     bool shade_exact = false;   // true: all-fp64 lighting (exact.cuh); false: fp32 lighting (fastshade.cuh)
+    // TMA descriptors of the current frame's depth-key / id planes (k_raster_warp stages its tiles with them)
+    TileMaps tile_maps{};
+    const void* maps_key = nullptr;     // what the descriptors were built for: rebuilt when any of it changes
+    const void* maps_vis = nullptr;
+    int maps_w = 0, maps_h = 0, maps_views = 0;
+    bool maps_ok = false;
+    bool use_tma = true;                // TRB_TMA=0: LDG / STG staging
     bool foreign_ids = false;   // trb_set_triangle_id_base was used: the id plane may hold winners other ranks rasterised
 };
 
@@ -529,6 +536,43 @@ int refresh_snapshot(TrbCtx* c) {
     return TRB_OK;
 }
 
+// Tensor maps of the frame's planes for the TMA tile staging of k_raster_warp.  cuTensorMapEncodeTiled is a driver
+// entry point; it is looked up at run time so that the library carries no link-time dependency on libcuda.
+bool tile_maps_for(TrbCtx* c) {
+    const FrameDev& f = c->frame;
+    if (!c->use_tma || (f.W & 3)) return false;            // row pitch of the id plane must be a multiple of 16 bytes
+    if (c->maps_key == f.zkey && c->maps_vis == f.vis && c->maps_w == f.W && c->maps_h == f.H && c->maps_views == f.nviews)
+        return c->maps_ok;
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        looked_up = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeTiled>(fn);
+        (void)cudaGetLastError();
+    }
+    c->maps_key = f.zkey; c->maps_vis = f.vis; c->maps_w = f.W; c->maps_h = f.H; c->maps_views = f.nviews;
+    c->maps_ok = false;
+    if (!encode) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)f.W, (cuuint64_t)f.H, (cuuint64_t)f.nviews};
+    const cuuint32_t box[3] = {TILE, TILE, 1}, estr[3] = {1, 1, 1};
+    const cuuint64_t kstr[2] = {(cuuint64_t)f.W * 8, (cuuint64_t)f.npix * 8}, vstr[2] = {(cuuint64_t)f.W * 4, (cuuint64_t)f.npix * 4};
+    const CUresult a = encode(&c->tile_maps.key, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)f.zkey, dims, kstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult b = encode(&c->tile_maps.vis, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)f.vis, dims, vstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    c->maps_ok = a == CUDA_SUCCESS && b == CUDA_SUCCESS;
+    return c->maps_ok;
+}
+
 // bin + rasterise one draw whose vertex records are already in `vrec`.
 //
 // Default (asynchronous): nothing here waits for the device.  The bin buffer is sized from an
@@ -614,10 +658,11 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     if (c->warp_max > 0) {   // bins of 1..warp_max triangles: one warp per tile
         Launch L(c, "k_raster_warp");
         const dim3 grid((f.ntiles + RW_WARPS - 1) / RW_WARPS, f.nviews);
+        const int tma = tile_maps_for(c) ? 1 : 0;
         switch (c->rw_blocks) {
-            case 8: k_raster_warp<8><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
-            case 7: k_raster_warp<7><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
-            default: k_raster_warp<6><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra); break;
+            case 8: k_raster_warp<8><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, tma); break;
+            case 7: k_raster_warp<7><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, tma); break;
+            default: k_raster_warp<6><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, tma); break;
         }
     }
     if (long_bins) {         // longer bins: one CTA per tile, persistent grid over the device-side list
@@ -798,6 +843,7 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_WARP_MAX")) c->warp_max = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("TRB_RW_BLOCKS")) c->rw_blocks = atoi(e);
     if (const char* e = getenv("TRB_SHADE_EXACT")) c->shade_exact = atoi(e) != 0;
+    if (const char* e = getenv("TRB_TMA")) c->use_tma = atoi(e) != 0;
     if (const char* e = getenv("TRB_SYNC_DRAWS")) c->sync_draws = atoi(e) != 0;
     if (const char* e = getenv("TRB_BIN_CAP")) c->bin_cap_fixed = (uint32_t)std::max(1, atoi(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
