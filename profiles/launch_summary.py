@@ -21,7 +21,8 @@ def main():
             v *= 1000.0
         launches.append((name, v))
     starts = [i for i, (n, _) in enumerate(launches) if n == first]
-    last = launches[starts[-1]:]
+    # the capture may stop in the middle of a step (ncu -c N): take the last COMPLETE one
+    last = launches[starts[-2]:starts[-1]] if len(starts) > 1 else launches[starts[-1]:]
     tot = {}
     for n, v in last:
         a = tot.setdefault(n, [0, 0.0])

@@ -869,8 +869,9 @@ struct __align__(16) WarpTile {
     uint32_t vid[TILE * TILE];
     SmTri recs[32];
     uint32_t spans[RW_SPAN_CAP];            // triangle (5 bits) | first column (4) | row (4) | length - 1 (4)
+    uint8_t claim[TILE * TILE];             // which lane last announced a fragment for the pixel (collision test)
 };
-static_assert(sizeof(WarpTile) == 8704, "WarpTile size");
+static_assert(sizeof(WarpTile) == 8960 && sizeof(WarpTile) % 128 == 0, "WarpTile size (TMA destinations need 128-byte alignment)");
 
 // Conservative row spans.  A sample of row y can only be covered when the three edge values the reference computes
 // (u.x <= 0, u.y <= 0, u.x + u.y >= u.z; our_gl.cpp:77-86, 152) allow it.  In real arithmetic each is linear in the
@@ -1173,9 +1174,18 @@ k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, c
                 const unsigned long long cur0 = sm.zk[frag ? p : 0];
                 const uint32_t vid0 = sm.vid[frag ? p : 0];
                 if (starts >> 1) {
-                    const unsigned peers = __match_any_sync(FULL, frag ? (unsigned)p : 256u + (unsigned)lane);
-                    rank = __popc(peers & lane_lt);
-                    clash = __any_sync(FULL, rank != 0u);
+                    // do two lanes of the window hit the same pixel?  Every lane with a fragment writes its number into the
+                    // pixel's claim byte and reads it back: when two lanes share a pixel one of them finds the other's
+                    // number.  (MATCH.ANY answers the same question, but the instruction behind it collected 16 % of the
+                    // kernel's stall samples; it is kept for the rare window that does collide.)
+                    if (frag) sm.claim[p] = (uint8_t)lane;
+                    __syncwarp();
+                    const bool lost = frag && sm.claim[p] != (uint8_t)lane;
+                    if (__any_sync(FULL, lost)) {
+                        const unsigned peers = __match_any_sync(FULL, frag ? (unsigned)p : 256u + (unsigned)lane);
+                        rank = __popc(peers & lane_lt);
+                        clash = true;
+                    }
                 }
                 if (!clash) {
                     if (frag && (key < cur0 || (key == cur0 && gid_e < vid0))) {
