@@ -1144,8 +1144,9 @@ k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, c
                 const int j = (int)before + __popc(starts & lane_le) - 1;
                 before += (uint32_t)__popc(starts);
                 TRB_CHECK(j >= 0 && j < 32);
-                const uint32_t ent_j = __shfl_sync(FULL, ent, j);
-                const uint32_t l = bs + lane - __shfl_sync(FULL, first, j);
+                const uint32_t pj = __shfl_sync(FULL, ent | (first << 17), j);   // span (17 bits) and its first sample (<= 512) in one shuffle
+                const uint32_t ent_j = pj & 0x1ffffu;
+                const uint32_t l = bs + lane - (pj >> 17);
                 const bool act = bs + lane < S;
                 const int p = (int)(((ent_j >> 5) & 255u) + l);       // row * 16 + first column + l
                 const double2* q = reinterpret_cast<const double2*>(&sm.recs[ent_j & 31u]);
