@@ -1530,6 +1530,10 @@ __global__ void __launch_bounds__(TPB) k_shade_collect(FrameDev f, int row0, int
 #ifndef TRB_SHADE_MIN_BLOCKS
 #define TRB_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef TRB_SHADE_DENSE_PX
+#define TRB_SHADE_DENSE_PX 8   // measured on config 3 (ms per step): 1 -> 1.975, 2 -> 1.81, 4 -> 1.70, 8 -> 1.665, 16 -> 1.654
+#endif
+constexpr int SHADE_DENSE_PX = TRB_SHADE_DENSE_PX;   // pixels per thread of k_shade_dense
 #ifndef TRB_SHADE_2D
 #define TRB_SHADE_2D 0   // measured on B200 (config 3): 8x4 warp footprints 1.18 ms vs 1.10 ms for 32 pixels of a row
 #endif
@@ -1551,15 +1555,26 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(Frame
     if (x >= f.W || y >= row1) return;
     const unsigned long long p = (unsigned long long)y * f.W + x;
 #else
+    // SHADE_DENSE_PX pixels per thread, TPB apart: their ids are requested together, so the first (cold: the id plane was
+    // just written by the raster pass and is larger than L2) load of all of them is one wait instead of one each
     const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
-    const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
-    if (p >= last) return;
-#endif
+    const unsigned long long p0 = first + (unsigned long long)blockIdx.x * (TPB * SHADE_DENSE_PX) + threadIdx.x;
     uint32_t* vis = f.vis + (size_t)view * f.npix;
-    const uint32_t id = vis[p];
-    if (id == VIS_NONE || id == VIS_SHADED) return;
-    shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, p, id);
-    vis[p] = VIS_SHADED;
+    uint32_t ids[SHADE_DENSE_PX];
+    #pragma unroll
+    for (int k = 0; k < SHADE_DENSE_PX; ++k) {
+        const unsigned long long p = p0 + (unsigned long long)k * TPB;
+        ids[k] = p < last ? vis[p] : VIS_NONE;
+    }
+    #pragma unroll 1
+    for (int k = 0; k < SHADE_DENSE_PX; ++k) {
+        const uint32_t id = ids[k];
+        if (id == VIS_NONE || id == VIS_SHADED) continue;
+        const unsigned long long p = p0 + (unsigned long long)k * TPB;
+        shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, p, id);
+        vis[p] = VIS_SHADED;
+    }
+#endif
 }
 
 // Sparse frames, pass 2: persistent grid-stride loop over the compacted list
@@ -1573,10 +1588,23 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
     const unsigned long long n = f.stats[view].list_len;
     const uint32_t* mylist = list + (size_t)view * f.npix;
     uint32_t* vis = f.vis + (size_t)view * f.npix;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * TPB) {
-        const uint32_t p = mylist[i];
-        shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, p, vis[p]);
-        vis[p] = VIS_SHADED;
+    // four list entries per trip, their pixel numbers and ids requested before the first of them is shaded
+    const unsigned long long stride = (unsigned long long)gridDim.x * TPB;
+    for (unsigned long long i0 = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        uint32_t ps[4], ids[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned long long i = i0 + (unsigned long long)k * stride;
+            ps[k] = i < n ? mylist[i] : 0xffffffffu;
+        }
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) ids[k] = ps[k] != 0xffffffffu ? vis[ps[k]] : VIS_NONE;
+        #pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            if (ps[k] == 0xffffffffu) break;
+            shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, ps[k], ids[k]);
+            vis[ps[k]] = VIS_SHADED;
+        }
     }
 }
 

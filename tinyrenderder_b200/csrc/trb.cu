@@ -487,7 +487,7 @@ int do_flush(TrbCtx* c) {
 #if TRB_SHADE_2D
             const dim3 grid((unsigned)(((f.W + 31) / 32) * ((r1 - r0 + 7) / 8)), f.nviews);
 #else
-            const dim3 grid(blocks_for(n), f.nviews);
+            const dim3 grid((unsigned)((n + (unsigned long long)TPB * SHADE_DENSE_PX - 1) / ((unsigned long long)TPB * SHADE_DENSE_PX)), f.nviews);
 #endif
             Launch L(c, "k_shade_dense");
             switch (variant) {
