@@ -224,6 +224,7 @@ struct ProfAcc {
 
 struct TrbCtx {
     int device = 0;
+    int sms = 148;
     cudaStream_t stream = nullptr;
     std::string err;
 
@@ -459,7 +460,7 @@ int do_flush(TrbCtx* c) {
         }
         {   // sparse views only (device-side predicate)
             const unsigned need = blocks_for((n + SHADE_PX_PER_THREAD - 1) / SHADE_PX_PER_THREAD);
-            dim3 grid(std::min(need, std::max(1u, 148u * 16 / (unsigned)f.nviews)), f.nviews);
+            dim3 grid(std::min(need, std::max(1u, (unsigned)c->sms * 16 / (unsigned)f.nviews)), f.nviews);
             Launch L(c, "k_shade_collect");
             k_shade_collect<<<grid, TPB, 0, c->stream>>>(f, r0, r1, c->shade_list.as<uint32_t>());
         }
@@ -473,7 +474,7 @@ int do_flush(TrbCtx* c) {
         const int variant = (config2 ? 2 : 0) | (fast ? 1 : 0);   // template <C2, FAST>
         {
             unsigned per_view = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(
-                blocks_for(n), (148ull * 3 * 4 + f.nviews - 1) / f.nviews));
+                blocks_for(n), ((unsigned long long)c->sms * 3 * 4 + f.nviews - 1) / f.nviews));
             const dim3 grid(per_view, f.nviews);
             Launch L(c, "k_shade");
             switch (variant) {
@@ -666,13 +667,13 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         }
     }
     if (long_bins) {         // longer bins: one CTA per tile, persistent grid over the device-side list
-        const unsigned grid = (unsigned)std::min<size_t>(nslots, (size_t)148 * TRB_RASTER_MIN_BLOCKS);
+        const unsigned grid = (unsigned)std::min<size_t>(nslots, (size_t)c->sms * TRB_RASTER_MIN_BLOCKS);
         Launch L(c, "k_raster");
         k_raster<<<grid, TPB, 0, c->stream>>>(f, ra);
     }
     {                        // stand-ins for a draw that overflowed its bins or 32-bit offsets (exit at once otherwise)
         const dim3 grid((unsigned)std::min<unsigned>(blocks_for((unsigned long long)g.ntris * 32),
-                                                    std::max(1u, 148u * 8 / (unsigned)f.nviews)), f.nviews);
+                                                    std::max(1u, (unsigned)c->sms * 8 / (unsigned)f.nviews)), f.nviews);
         {
             Launch L(c, "k_unbinned_depth");
             k_unbinned<false><<<grid, TPB, 0, c->stream>>>(f, g.ntris, g.id_base, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
@@ -836,6 +837,7 @@ int trb_create(int device, TrbCtx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return TRB_E_CUDA;
     TrbCtx* c = new TrbCtx();
     c->device = device;
+    c->sms = prop.multiProcessorCount;   // 148 on B200: persistent grids and grid caps are sized from it
     if (const char* e = getenv("TRB_BIG_NS")) c->big_ns = std::max(1, atoi(e));
     if (const char* e = getenv("TRB_SMALL_MIN")) c->small_min = std::max(1, atoi(e));
     if (const char* e = getenv("TRB_LARGE_NS")) c->large_ns = std::max(1, atoi(e));
@@ -1168,7 +1170,7 @@ int trb_begin_batch(TrbCtx* c, int w, int h, int nviews) {
         if (rc) return rc;
     }
     {
-        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(total), 148ull * 32);
+        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(total), (unsigned long long)c->sms * 32);
         Launch L(c, "k_clear");
         k_clear<<<grid, TPB, 0, c->stream>>>(f, c->clear[0], c->clear[1], c->clear[2]);
     }
@@ -1547,12 +1549,12 @@ int trb_get_stats(TrbCtx* c, int view, TrbStats* out) {
     unsigned long long init[3] = {0ull, ~0ull, 0ull};  // finite count, min key, max key
     CU(cudaMemcpyAsync(c->scratch_b.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     {
-        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(n), 148ull * 16);
+        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(n), (unsigned long long)c->sms * 16);
         Launch L(c, "k_count_finite");
         k_count_finite<<<grid, TPB, 0, c->stream>>>(c->frame.zkey + n * view, n, c->scratch_b.as<unsigned long long>());
     }
     {
-        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(n), 148ull * 16);
+        unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(n), (unsigned long long)c->sms * 16);
         Launch L(c, "k_depth_range");
         k_depth_range<<<grid, TPB, 0, c->stream>>>(c->frame.zkey + n * view, n, c->scratch_b.as<unsigned long long>() + 1);
     }
@@ -1610,7 +1612,7 @@ int post_plane(TrbCtx* c, int which, int view, uint8_t* dst) {
         unsigned long long init[2] = {~0ull, 0ull};
         CU(cudaMemcpyAsync(c->scratch_b.p, init, 16, cudaMemcpyHostToDevice, c->stream));
         {
-            unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(f.npix), 148ull * 16);
+            unsigned grid = (unsigned)std::min<unsigned long long>(blocks_for(f.npix), (unsigned long long)c->sms * 16);
             Launch L(c, "k_depth_range");
             k_depth_range<<<grid, TPB, 0, c->stream>>>(f.zkey + f.npix * view, f.npix, c->scratch_b.as<unsigned long long>());
         }
