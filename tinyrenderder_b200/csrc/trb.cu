@@ -252,9 +252,14 @@ struct TrbCtx {
     int shade_row0 = 0, shade_row1 = -1;
 
     // per-draw scratch (stream ordered reuse)
-    DevBuf shade_list, tribox, trirec, counts, offsets, cursor, bins, scan_sums, scan_total, scratch_a, scratch_b;
-    DevBuf ctl, heavy_list;          // DrawCtl of the draw in flight, tile slots of its long bins
-    DevBuf direct_list, direct_n;    // direct path: triangles that may own a pixel, per view
+    DevBuf shade_list, tribox, trirec, offsets, bins, scan_sums, scan_total, scratch_a, scratch_b;
+    // what a draw needs zeroed, in ONE block so that one memset does it: the DrawCtl of the draw in flight, the direct
+    // path's per-view list lengths, the per-tile counts and fill cursors
+    DevBuf drawzero;
+    DrawCtl* ctl_p = nullptr;
+    uint32_t *direct_n_p = nullptr, *counts_p = nullptr, *cursor_p = nullptr;
+    DevBuf heavy_list;               // tile slots of the draw's long bins
+    DevBuf direct_list;              // direct path: triangles that may own a pixel, per view
     DevBuf rle_work, rle_src, rle_out; // device-side TGA RLE encoder (tga_rle.cuh)
     bool sync_draws = false;         // TRB_SYNC_DRAWS=1: size the bins exactly (one stream sync per draw)
     uint64_t bin_hint = 0;           // entries: 1.25 x the largest R seen so far
@@ -511,17 +516,13 @@ int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uin
     CU(c->scan_sums.ensure((size_t)nblocks * 4, c->stream));
     {
         Launch L(c, "k_scan_partial");
-        k_scan_partial<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>(), c->ctl.as<DrawCtl>(), c->warp_max,
+        k_scan_partial<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>(), c->ctl_p, c->warp_max,
                                                        c->heavy_list.as<uint32_t>());
     }
     {
-        Launch L(c, "k_scan_sums");
-        k_scan_sums<<<1, TPB, 0, c->stream>>>(c->scan_sums.as<uint32_t>(), nblocks, c->host_total_dev, c->ctl.as<DrawCtl>(),
-                                              bin_capacity);
-    }
-    {
         Launch L(c, "k_scan_final");
-        k_scan_final<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>(), out);
+        k_scan_final<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>(), out, c->host_total_dev,
+                                                     c->ctl_p, bin_capacity);
     }
     CU(cudaGetLastError());
     return TRB_OK;
@@ -590,19 +591,21 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     if (nslots >= 0xFFFFFFFFull) return fail(c, TRB_E_ARG, "draw: too many tiles x views");
     CU(c->tribox.ensure((size_t)f.nviews * g.ntris * sizeof(uint2), c->stream));
     CU(c->trirec.ensure((size_t)f.nviews * g.ntris * sizeof(TriRec), c->stream));
-    CU(c->counts.ensure(nslots * 4, c->stream));
     CU(c->offsets.ensure(nslots * 4, c->stream));
-    CU(c->cursor.ensure(nslots * 4, c->stream));
     CU(c->heavy_list.ensure(nslots * 4, c->stream));
-    CU(c->ctl.ensure(sizeof(DrawCtl), c->stream));
-    CU(cudaMemsetAsync(c->counts.p, 0, nslots * 4, c->stream));
-    CU(cudaMemsetAsync(c->cursor.p, 0, nslots * 4, c->stream));
-    CU(cudaMemsetAsync(c->ctl.p, 0, sizeof(DrawCtl), c->stream));
-    if (c->direct_area > 0) {
-        CU(c->direct_list.ensure((size_t)f.nviews * g.ntris * 4, c->stream));
-        CU(c->direct_n.ensure((size_t)f.nviews * 4, c->stream));
-        CU(cudaMemsetAsync(c->direct_n.p, 0, (size_t)f.nviews * 4, c->stream));
+    {
+        const size_t o_dn = 256, o_counts = o_dn + (((size_t)f.nviews * 4 + 255) & ~(size_t)255),
+                     o_cursor = o_counts + ((nslots * 4 + 255) & ~(size_t)255), bytes = o_cursor + nslots * 4;
+        static_assert(sizeof(DrawCtl) <= 256, "DrawCtl sits in the first 256 bytes of the zeroed block");
+        CU(c->drawzero.ensure(bytes, c->stream));
+        char* z = c->drawzero.as<char>();
+        c->ctl_p = reinterpret_cast<DrawCtl*>(z);
+        c->direct_n_p = reinterpret_cast<uint32_t*>(z + o_dn);
+        c->counts_p = reinterpret_cast<uint32_t*>(z + o_counts);
+        c->cursor_p = reinterpret_cast<uint32_t*>(z + o_cursor);
+        CU(cudaMemsetAsync(z, 0, bytes, c->stream));
     }
+    if (c->direct_area > 0) CU(c->direct_list.ensure((size_t)f.nviews * g.ntris * 4, c->stream));
     uint32_t capacity = 0xFFFFFFFFu;   // synchronous draws size the buffer after the scan
     if (!c->sync_draws) {
         // R of the most recent draw the device has finished scanning: a hint, never waited for
@@ -618,15 +621,15 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         Launch L(c, "k_setup_count");
         const dim3 sgrid((g.ntris + TPB * SETUP_CHUNKS - 1) / (TPB * SETUP_CHUNKS), f.nviews);
         k_setup_count<<<sgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
-                                                     c->counts.as<uint32_t>(), c->direct_area, c->direct_list.as<uint32_t>(),
-                                                     c->direct_n.as<uint32_t>());
+                                                     c->counts_p, c->direct_area, c->direct_list.as<uint32_t>(),
+                                                     c->direct_n_p);
     }
     if (c->direct_area > 0) {
         Launch L(c, "k_direct_resolve");
-        k_direct_resolve<<<tgrid, TPB, 0, c->stream>>>(f, g, c->direct_list.as<uint32_t>(), c->direct_n.as<uint32_t>());
+        k_direct_resolve<<<tgrid, TPB, 0, c->stream>>>(f, g, c->direct_list.as<uint32_t>(), c->direct_n_p);
     }
     CU(cudaGetLastError());
-    int rc = exclusive_scan(c, c->counts.as<uint32_t>(), (uint32_t)nslots, c->offsets.as<uint32_t>(), capacity);
+    int rc = exclusive_scan(c, c->counts_p, (uint32_t)nslots, c->offsets.as<uint32_t>(), capacity);
     if (rc) return rc;
     bool long_bins = true;             // unknown without a round trip: k_raster's persistent grid finds an empty list
     if (c->sync_draws) {
@@ -635,26 +638,27 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         CU(cudaStreamSynchronize(c->stream));
         const uint32_t R = c->host_total[0];
         if (R == 0) return TRB_OK;
-        long_bins = c->host_total[1] > c->warp_max;
+        long_bins = c->host_total[1] > c->warp_max || c->host_total[2];   // k_raster also carries the overflow fallback's depth pass
         if (!c->host_total[2]) CU(c->bins.ensure((size_t)R * 4, c->stream));   // overflow (R >= 2^32): the unbinned kernels draw it
     }
     {
         Launch L(c, "k_fill");
         k_fill<<<tgrid, TPB, 0, c->stream>>>(f, g.ntris, c->tribox.as<uint2>(), c->offsets.as<uint32_t>(),
-                                            c->cursor.as<uint32_t>(), c->bins.as<uint32_t>(), c->ctl.as<DrawCtl>());
+                                            c->cursor_p, c->bins.as<uint32_t>(), c->ctl_p);
     }
     RasterArgs ra;
     ra.ntris = g.ntris;
     ra.id_base = g.id_base;
     ra.trirec = c->trirec.as<TriRec>();
-    ra.counts = c->counts.as<uint32_t>();
+    ra.tribox = c->tribox.as<uint2>();
+    ra.counts = c->counts_p;
     ra.offsets = c->offsets.as<uint32_t>();
     ra.bins = c->bins.as<uint32_t>();
     ra.big_ns = c->big_ns;
     ra.small_min = c->small_min;
     ra.large_ns = c->large_ns;
     ra.warp_max = c->warp_max;
-    ra.ctl = c->ctl.as<DrawCtl>();
+    ra.ctl = c->ctl_p;
     ra.heavy_list = c->heavy_list.as<uint32_t>();
     if (c->warp_max > 0) {   // bins of 1..warp_max triangles: one warp per tile
         Launch L(c, "k_raster_warp");
@@ -667,23 +671,18 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         }
     }
     if (long_bins) {         // longer bins: one CTA per tile, persistent grid over the device-side list
-        const unsigned grid = (unsigned)std::min<size_t>(nslots, (size_t)c->sms * TRB_RASTER_MIN_BLOCKS);
+        // asynchronous draws: the full persistent grid, because it may have to carry the unbinned depth pass
+        const unsigned grid = c->sync_draws && !c->host_total[2] ? (unsigned)std::min<size_t>(nslots, (size_t)c->sms * TRB_RASTER_MIN_BLOCKS)
+                                                                 : (unsigned)c->sms * TRB_RASTER_MIN_BLOCKS;
         Launch L(c, "k_raster");
         k_raster<<<grid, TPB, 0, c->stream>>>(f, ra);
     }
-    {                        // stand-ins for a draw that overflowed its bins or 32-bit offsets (exit at once otherwise)
+    {   // stand-in for a draw that overflowed its bins or 32-bit offsets (exits at once otherwise): the id pass of the
+        // unbinned fallback; its depth pass ran inside k_raster's grid
         const dim3 grid((unsigned)std::min<unsigned>(blocks_for((unsigned long long)g.ntris * 32),
                                                     std::max(1u, (unsigned)c->sms * 8 / (unsigned)f.nviews)), f.nviews);
-        {
-            Launch L(c, "k_unbinned_depth");
-            k_unbinned<false><<<grid, TPB, 0, c->stream>>>(f, g.ntris, g.id_base, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
-                                                          c->ctl.as<DrawCtl>());
-        }
-        {
-            Launch L(c, "k_unbinned_ids");
-            k_unbinned<true><<<grid, TPB, 0, c->stream>>>(f, g.ntris, g.id_base, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
-                                                         c->ctl.as<DrawCtl>());
-        }
+        Launch L(c, "k_unbinned_ids");
+        k_unbinned<true><<<grid, TPB, 0, c->stream>>>(f, g.ntris, g.id_base, c->tribox.as<uint2>(), c->trirec.as<TriRec>(), c->ctl_p);
     }
     CU(cudaGetLastError());
     return TRB_OK;
@@ -880,7 +879,7 @@ int trb_destroy(TrbCtx* c) {
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
     DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
-                      &c->counts, &c->offsets, &c->cursor, &c->bins, &c->scan_sums, &c->scan_total, &c->ctl, &c->heavy_list, &c->direct_list, &c->direct_n, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
+                      &c->drawzero, &c->offsets, &c->bins, &c->scan_sums, &c->scan_total, &c->heavy_list, &c->direct_list, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.keys.release();
