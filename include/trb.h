@@ -249,7 +249,7 @@ TRB_EXPORT int TRB_FN(read_visibility)(TrbCtx* ctx, int view, uint32_t* id_out);
  * depth_out[v] (either array may be NULL).  The frame is resolved and snapshotted into a device
  * staging area on the context's stream; the device->host copies run on a second stream, so they
  * overlap the next frame's rendering.  Returns after queueing: the host buffers (pinned, for real
- * overlap) are valid after trb_readback_wait.  Two readbacks may be in flight; a third call first
+ * overlap) are valid after trb_readback_wait.  Three readbacks may be in flight; a fourth call first
  * waits for the oldest. */
 TRB_EXPORT int TRB_FN(readback_async)(TrbCtx* ctx, uint8_t* const* color_out, double* const* depth_out);
 TRB_EXPORT int TRB_FN(readback_wait)(TrbCtx* ctx);

@@ -289,9 +289,13 @@ struct TrbCtx {
 
     // pipelined readback
     cudaStream_t copy_stream = nullptr;
-    DevBuf rb[2];
-    cudaEvent_t rb_ready[2] = {nullptr, nullptr}, rb_done[2] = {nullptr, nullptr};
-    bool rb_inflight[2] = {false, false};
+    // three staging areas: with two, the host can only run one step ahead of the copy engine (it blocks on the slot of
+    // step s-2 before it may queue step s), and its ~1 ms of enqueue work after that wait shows up as bubbles on both the
+    // render stream and the copy engine whenever rendering and the D2H copy take about equally long (config 3 on one GPU)
+    static constexpr int RB_SLOTS = 3;
+    DevBuf rb[RB_SLOTS];
+    cudaEvent_t rb_ready[RB_SLOTS] = {}, rb_done[RB_SLOTS] = {};
+    bool rb_inflight[RB_SLOTS] = {};
     int rb_idx = 0;
 
     // asynchronous TGA frame writer (trb_encode_tga_async): two jobs in flight
@@ -888,7 +892,7 @@ int trb_destroy(TrbCtx* c) {
     trb_ipc_close_peers(c);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < TrbCtx::RB_SLOTS; ++i) {
             c->rb[i].release();
             cudaEventDestroy(c->rb_ready[i]);
             cudaEventDestroy(c->rb_done[i]);
@@ -1470,7 +1474,7 @@ int trb_read_depth(TrbCtx* c, int view, double* out) {
 int trb_readback_wait(TrbCtx* c) {
     if (!c) return TRB_E_ARG;
     CU(cudaSetDevice(c->device));
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < TrbCtx::RB_SLOTS; ++i)
         if (c->rb_inflight[i]) {
             CU(cudaEventSynchronize(c->rb_done[i]));
             c->rb_inflight[i] = false;
@@ -1488,12 +1492,12 @@ int trb_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* dept
     if (rc) return rc;
     if (!c->copy_stream) {
         CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < TrbCtx::RB_SLOTS; ++i) {
             CU(cudaEventCreateWithFlags(&c->rb_ready[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&c->rb_done[i], cudaEventDisableTiming));
         }
     }
-    const int i = (c->rb_idx ^= 1);
+    const int i = c->rb_idx = (c->rb_idx + 1) % TrbCtx::RB_SLOTS;
     if (c->rb_inflight[i]) {  // staging area i is still being drained by the copy stream
         HostSpan w("readback_async:wait_slot");
         CU(cudaEventSynchronize(c->rb_done[i]));
@@ -1828,7 +1832,7 @@ int trb_encode_tga_async(TrbCtx* c, int which, uint8_t* const* out, uint64_t cap
     if (rc) return rc;
     if (!c->copy_stream) {
         CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < TrbCtx::RB_SLOTS; ++i) {
             CU(cudaEventCreateWithFlags(&c->rb_ready[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&c->rb_done[i], cudaEventDisableTiming));
         }
