@@ -352,6 +352,20 @@ def snapshot_restore_twice(api, r):
     return _grab(r)
 
 
+def snapshot_signed_zero(api, r):
+    """a -0.0 depth that is still unshaded when the z-buffer is saved: the saved copy must hold the sign bit too
+    (the device snapshots while it shades; the shade pass is what restores the exact bits)"""
+    b = [-0.8, -0.8, -0.0, 1, 0.8, -0.8, -0.0, 1, 0.0, 0.8, -0.0, 1]
+    r.begin_frame(64, 48)
+    r.submit_clip_triangles(np.array([b], dtype=np.float64))
+    r.depth_snapshot()
+    r.submit_clip_triangles(_screen_tri([(5, 5), (60, 8), (30, 44)], -0.5, 64, 48))     # nearer: overwrites the zeros
+    r.depth_restore()
+    r.submit_clip_triangles(_screen_tri([(2, 2), (40, 4), (10, 40)], 0.25, 64, 48))     # behind -0.0 where they overlap
+    r.end_frame()
+    return _grab(r)
+
+
 def sub_range_draws(api, r):
     """drawing a mesh as three triangle ranges == drawing it at once (config-4 sharding unit)"""
     m = scenes.icosphere(3)
@@ -435,7 +449,7 @@ CASES = {
     "big_triangles": big_triangles, "queue_overflow": queue_overflow, "dense_tile": dense_tile,
     "soup_mesh_fp32": soup_mesh_fp32, "head_small": head_small, "orbit_small": orbit_small,
     "depth_only_then_color": depth_only_then_color, "sub_range_draws": sub_range_draws,
-    "snapshot_restore_twice": snapshot_restore_twice,
+    "snapshot_restore_twice": snapshot_restore_twice, "snapshot_signed_zero": snapshot_signed_zero,
     "lit_clip_triangles": lit_clip_triangles, "shadow_small": shadow_small, "gouraud_small": gouraud_small,
     "orbit_culled": orbit_culled,
 }
