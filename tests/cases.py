@@ -380,6 +380,26 @@ def sub_range_draws(api, r):
     return _grab(r)
 
 
+def indexed_duplicates(api, r):
+    """an INDEXED mesh whose index buffer lists every triangle of a small sphere three times, shuffled, drawn as two
+    triangle ranges: every covered pixel is a depth tie between three ids from different parts of the buffer, and
+    the first submitted must win it (our_gl.cpp:160-166) - also when the backend visits the triangles in another
+    order (mesh processing order, TRB_MESH_ORDER_MIN_TRIS)"""
+    m = scenes.icosphere(3)
+    tri = m.idx.reshape(-1, 3)
+    rng = np.random.Generator(np.random.PCG64(11))
+    tri = np.concatenate([tri, tri, tri], axis=0)[rng.permutation(3 * tri.shape[0])]
+    h = r.upload_mesh(m.pos, m.nrm, m.uv, np.ascontiguousarray(tri.reshape(-1)).astype(m.idx.dtype))
+    mv = api.lookat([0.3, 0.2, 2.4], [0, 0, 0], [0, 1, 0])
+    pr = api.perspective(55, 1.25, 0.1, 10)
+    r.begin_frame(320, 256)
+    n = tri.shape[0]
+    for a, b in ((0, n // 2), (n // 2, n)):
+        r.draw(h, mv, pr, first_tri=a, ntris=b - a)
+    r.end_frame()
+    return _grab(r)
+
+
 def lit_clip_triangles(api, r):
     """immediate mode behind rasterize(clip, PhongShader, fb): clip + varyings supplied by the caller"""
     m = scenes.uv_sphere(12, 9)
@@ -451,7 +471,7 @@ CASES = {
     "depth_only_then_color": depth_only_then_color, "sub_range_draws": sub_range_draws,
     "snapshot_restore_twice": snapshot_restore_twice, "snapshot_signed_zero": snapshot_signed_zero,
     "lit_clip_triangles": lit_clip_triangles, "shadow_small": shadow_small, "gouraud_small": gouraud_small,
-    "orbit_culled": orbit_culled,
+    "orbit_culled": orbit_culled, "indexed_duplicates": indexed_duplicates,
 }
 FULL_SIZE_CASES = {"k7a": k7a, "k7b": k7b, "k7c": k7c, "head_c1": head_c1, "orbit_mid": orbit_mid,
                    "shadow_c2": shadow_c2, "orbit_c3": orbit_c3, "sphere_c4": sphere_c4}

@@ -243,7 +243,7 @@ def test_fp32_lighting_stays_within_one_code(cuda_api, port_api, monkeypatch, na
 
 DRAW_PATH_CASES = ["k2", "k5_far_near", "k7b_small", "signed_zero_ties", "duplicate_triangles", "big_triangles",
                    "dense_tile", "soup_mesh_fp32", "head_small", "orbit_small", "sub_range_draws", "rejects",
-                   "snapshot_restore_twice"]
+                   "snapshot_restore_twice", "indexed_duplicates"]
 
 
 @pytest.mark.parametrize("name", DRAW_PATH_CASES)
@@ -261,6 +261,22 @@ def test_bin_overflow_takes_the_unbinned_kernels(cuda_api, port_api, monkeypatch
 def test_synchronous_draws_match_oracle(cuda_api, port_api, monkeypatch, name):
     """TRB_SYNC_DRAWS=1: bins sized exactly after one stream synchronisation per draw (the pre-async path)"""
     monkeypatch.setenv("TRB_SYNC_DRAWS", "1")
+    got = run_case(cuda_api, name)
+    want = run_case(port_api, name)
+    compare.assert_outputs_match(name, got, want)
+
+
+@pytest.mark.parametrize("env", [{}, {"TRB_WARP_MAX": "0"}, {"TRB_BIN_CAP": "16"}, {"TRB_SYNC_DRAWS": "1"}, {"TRB_DIRECT_AREA": "0"}])
+@pytest.mark.parametrize("name", ["indexed_duplicates", "head_small", "orbit_small", "sub_range_draws", "orbit_culled",
+                                  "snapshot_restore_twice", "shadow_small", "gouraud_small"])
+def test_mesh_processing_order_matches_oracle(cuda_api, port_api, monkeypatch, name, env):
+    """TRB_MESH_ORDER_MIN_TRIS=1 gives EVERY indexed mesh the Morton processing order that only multi-million-triangle
+    meshes get by default (mesh_order.cu): set-up, bin fill, both raster kernels, the direct path and the unbinned fallback
+    then work on slots and map them to triangle ids through the permutation - the oracle's bits must come out, ties
+    included (ids stay those of the index buffer)"""
+    monkeypatch.setenv("TRB_MESH_ORDER_MIN_TRIS", "1")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     got = run_case(cuda_api, name)
     want = run_case(port_api, name)
     compare.assert_outputs_match(name, got, want)
@@ -320,7 +336,8 @@ def checks_api(built):
     return trb.Api(p, "trb")
 
 
-@pytest.mark.parametrize("env", [{}, {"TRB_WARP_MAX": "0"}, {"TRB_BIN_CAP": "16"}, {"TRB_SYNC_DRAWS": "1"}])
+@pytest.mark.parametrize("env", [{}, {"TRB_WARP_MAX": "0"}, {"TRB_BIN_CAP": "16"}, {"TRB_SYNC_DRAWS": "1"},
+                                 {"TRB_MESH_ORDER_MIN_TRIS": "1"}, {"TRB_MESH_ORDER_MIN_TRIS": "1", "TRB_BIN_CAP": "16"}])
 @pytest.mark.parametrize("name", ["k7b_small", "big_triangles", "dense_tile", "soup_mesh_fp32", "orbit_small",
                                   "snapshot_restore_twice", "shadow_small"])
 def test_kernels_hold_their_indexing_invariants(checks_api, port_api, monkeypatch, name, env):

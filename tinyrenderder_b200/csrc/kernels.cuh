@@ -179,7 +179,19 @@ struct GeomArgs {
     const uint32_t* idx;
     uint32_t first_tri, ntris, nverts, id_base;
     const VRec* vrec;          // [nviews][nverts]
+    // Coherent processing order of a large indexed mesh (built once at upload, trb.cu mesh_order): slot j of the draw
+    // holds mesh triangle perm[j], idx_perm[3j..3j+2] are its vertex indices.  The draw then runs over the nslots
+    // slots of the whole mesh; slots whose triangle lies outside [first_tri, first_tri + ntris) are rejected.  Everything
+    // per-draw (tribox, trirec, bins, direct_list) is indexed by SLOT; the id of slot j is id_base + (perm[j] - first_tri) + 1,
+    // so depth ties still go to the triangle submitted first.  perm == nullptr: slot == triangle of the range.
+    const uint32_t* perm;
+    const uint32_t* idx_perm;
+    uint32_t nslots;           // perm ? triangles of the mesh : ntris
 };
+// id of the triangle in slot `slot`: id_off = id_base - first_tri (mod 2^32) when idmap (= perm) is set, else id_base
+__device__ __forceinline__ uint32_t slot_gid(uint32_t id_off, const uint32_t* __restrict__ idmap, uint32_t slot) {
+    return id_off + (idmap ? __ldg(idmap + slot) : slot) + 1u;
+}
 
 constexpr uint32_t BOX_NONE = 0xFFFFFFFFu;
 
@@ -285,26 +297,33 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
     // A CTA takes SETUP_CHUNKS consecutive chunks of TPB triangles.  The vertex indices of the NEXT chunk are
     // requested before the current chunk's vertex records are gathered, so the dependent chain
     // index -> record -> setup only pays one memory latency per chunk instead of two.
+    // t = the SLOT this thread handles (== the triangle of the range unless the mesh carries a processing order)
     const uint32_t t_first = blockIdx.x * (TPB * SETUP_CHUNKS) + threadIdx.x;
-    uint32_t n0 = 0, n1 = 0, n2 = 0;
-    if (t_first < g.ntris) {
-        n0 = vertex_index(g.idx, g.first_tri, t_first, 0);
-        n1 = vertex_index(g.idx, g.first_tri, t_first, 1);
-        n2 = vertex_index(g.idx, g.first_tri, t_first, 2);
-    }
+    const uint32_t nslots = g.nslots;
+    uint32_t n0 = 0, n1 = 0, n2 = 0, nm = 0;
+    auto fetch_slot = [&](uint32_t slot) {
+        if (g.perm) {
+            nm = __ldg(g.perm + slot) - g.first_tri;               // triangle inside the range, or >= ntris (wraps)
+            const uint32_t* q = g.idx_perm + (size_t)slot * 3;
+            n0 = __ldg(q); n1 = __ldg(q + 1); n2 = __ldg(q + 2);
+        } else {
+            nm = slot;
+            n0 = vertex_index(g.idx, g.first_tri, slot, 0);
+            n1 = vertex_index(g.idx, g.first_tri, slot, 1);
+            n2 = vertex_index(g.idx, g.first_tri, slot, 2);
+        }
+    };
+    if (t_first < nslots) fetch_slot(t_first);
     #pragma unroll 1
     for (int chunk = 0; chunk < SETUP_CHUNKS; ++chunk) {
         const uint32_t t = t_first + chunk * TPB;
-        if (blockIdx.x * (TPB * SETUP_CHUNKS) + chunk * TPB >= g.ntris) break;   // uniform over the CTA
+        if (blockIdx.x * (TPB * SETUP_CHUNKS) + chunk * TPB >= nslots) break;   // uniform over the CTA
         const uint32_t i0 = n0, i1 = n1, i2 = n2;
-        if (chunk + 1 < SETUP_CHUNKS && t + TPB < g.ntris) {
-            n0 = vertex_index(g.idx, g.first_tri, t + TPB, 0);
-            n1 = vertex_index(g.idx, g.first_tri, t + TPB, 1);
-            n2 = vertex_index(g.idx, g.first_tri, t + TPB, 2);
-        }
+        const bool mine = t < nslots && nm < g.ntris;
+        if (chunk + 1 < SETUP_CHUNKS && t + TPB < nslots) fetch_slot(t + TPB);
         int res = SETUP_REJECT;
         TriSetup ts;
-        if (t < g.ntris) {
+        if (mine) {
             VRec a = load_vrec(vr + i0);
             VRec b = load_vrec(vr + i1);
             VRec c = load_vrec(vr + i2);
@@ -356,7 +375,7 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
                 uint32_t base = 0;
                 if ((int)lane_id == leader) base = atomicAdd(direct_n + view, (uint32_t)__popc(cm));
                 base = __shfl_sync(act, base, leader);
-                if (candidate) direct_list[(size_t)view * g.ntris + base + __popc(cm & ((1u << lane_id) - 1u))] = t;
+                if (candidate) direct_list[(size_t)view * nslots + base + __popc(cm & ((1u << lane_id) - 1u))] = t;
             }
         }
         if (res == SETUP_DRAW) {
@@ -365,9 +384,9 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
             box = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
             ntile = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
             acc_ne += ntile;
-            store_trirec(trirec + (size_t)view * g.ntris + t, ts);
+            store_trirec(trirec + (size_t)view * nslots + t, ts);
         }
-        if (t < g.ntris) tribox[(size_t)view * g.ntris + t] = box;
+        if (t < nslots) tribox[(size_t)view * nslots + t] = box;
         // per-tile counts; single-tile triangles (the common case for small triangles) are aggregated
         // across the warp with match_any so that coherent meshes do not serialise on one counter
         unsigned key = 0x80000000u | lane_id;  // unique: no aggregation
@@ -432,16 +451,17 @@ __global__ void __launch_bounds__(TPB) k_direct_resolve(FrameDev f, GeomArgs g, 
     const int view = blockIdx.y;
     const uint32_t i = blockIdx.x * TPB + threadIdx.x;
     if (i >= direct_n[view]) return;
-    const uint32_t t = direct_list[(size_t)view * g.ntris + i];
+    const uint32_t t = direct_list[(size_t)view * g.nslots + i];     // a slot
     const VRec* vr = g.vrec + (size_t)view * g.nverts;
-    VRec a = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 0));
-    VRec b_ = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 1));
-    VRec c = load_vrec(vr + vertex_index(g.idx, g.first_tri, t, 2));
+    const uint32_t* q = g.perm ? g.idx_perm + (size_t)t * 3 : nullptr;
+    VRec a = load_vrec(vr + (q ? __ldg(q) : vertex_index(g.idx, g.first_tri, t, 0)));
+    VRec b_ = load_vrec(vr + (q ? __ldg(q + 1) : vertex_index(g.idx, g.first_tri, t, 1)));
+    VRec c = load_vrec(vr + (q ? __ldg(q + 2) : vertex_index(g.idx, g.first_tri, t, 2)));
     TriSetup ts;
     setup_triangle(a, b_, c, f.W, f.H, ts);
     const unsigned long long* zk = f.zkey + (size_t)view * f.npix;
     uint32_t* vis = f.vis + (size_t)view * f.npix;
-    const uint32_t gid = g.id_base + t + 1u;
+    const uint32_t gid = slot_gid(g.id_base - (g.perm ? g.first_tri : 0u), g.perm, t);
     for (int y = ts.y0; y <= ts.y1; ++y)
         for (int x = ts.x0; x <= ts.x1; ++x) {
             double b[3], z;
@@ -610,7 +630,8 @@ constexpr int LARGE_NS_DEFAULT = 128;   // clipped-bbox samples from which a tri
 constexpr int SP_GROUP = 3;             // sample-parallel rounds (of TPB samples) between two resolves
 
 struct RasterArgs {
-    uint32_t ntris, id_base;
+    uint32_t ntris, id_base;  // slots of the draw; id offset of slot_gid
+    const uint32_t* idmap;    // slot -> mesh triangle (GeomArgs::perm) or nullptr
     const TriRec* trirec;     // [nviews][ntris]
     const uint2* tribox;      // [nviews][ntris] tile ranges (k_setup_count); BOX_NONE / BOX_DIRECT markers
     const uint32_t* counts;   // [nviews][ntiles]
@@ -700,7 +721,7 @@ __device__ __forceinline__ void raster_tile_cta(const FrameDev& f, const RasterA
         if (has) {
             const uint32_t t = __ldg(a.bins + off + base + tid);
             load_trirec(tr + t, ts);
-            gid = a.id_base + t + 1u;
+            gid = slot_gid(a.id_base, a.idmap, t);
             cx0 = max(ts.x0, tx0); cx1 = min(ts.x1, tx0 + TILE - 1);
             cy0 = max(ts.y0, ty0); cy1 = min(ts.y1, ty0 + TILE - 1);
             ns = (cx1 - cx0 + 1) * (cy1 - cy0 + 1);
@@ -833,7 +854,7 @@ __device__ __forceinline__ void raster_tile_cta(const FrameDev& f, const RasterA
 // ---------------------------------------------------------------------------------------------
 template <bool IDS>
 __device__ __noinline__ void unbinned_pass(unsigned long long* zkey, uint32_t* visp, DevStats* stats, size_t npix, int W, int H,
-                                           int view0, int view1, uint32_t ntris, uint32_t id_base,
+                                           int view0, int view1, uint32_t ntris, uint32_t id_base, const uint32_t* __restrict__ idmap,
                                            const uint2* __restrict__ tribox, const TriRec* __restrict__ trirec,
                                            uint32_t w0, uint32_t nwarps) {
     const unsigned FULL = 0xffffffffu;
@@ -847,7 +868,7 @@ __device__ __noinline__ void unbinned_pass(unsigned long long* zkey, uint32_t* v
             TriSetup ts;
             load_trirec(trirec + (size_t)view * ntris + t, ts);
             const uint32_t bw = (uint32_t)(ts.x1 - ts.x0 + 1), ns = bw * (uint32_t)(ts.y1 - ts.y0 + 1);
-            const uint32_t gid = id_base + t + 1u;
+            const uint32_t gid = slot_gid(id_base, idmap, t);
             for (uint32_t s = lane; s < ns; s += 32) {
                 const uint32_t row = s / bw;
                 const int x = ts.x0 + (int)(s - row * bw), y = ts.y0 + (int)row;
@@ -885,7 +906,7 @@ __device__ __noinline__ void unbinned_pass(unsigned long long* zkey, uint32_t* v
 // persistent grid over the (usually short or empty) list of long bins
 __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev f, RasterArgs a) {
     if (a.ctl->overflow) {   // the bins were not filled: depth pass of the unbinned fallback, warps over all triangles of all views
-        unbinned_pass<false>(f.zkey, f.vis, f.stats, f.npix, f.W, f.H, 0, f.nviews, a.ntris, a.id_base, a.tribox, a.trirec,
+        unbinned_pass<false>(f.zkey, f.vis, f.stats, f.npix, f.W, f.H, 0, f.nviews, a.ntris, a.id_base, a.idmap, a.tribox, a.trirec,
                              blockIdx.x * (TPB / 32) + (threadIdx.x >> 5), gridDim.x * (TPB / 32));
         return;
     }
@@ -1100,6 +1121,7 @@ k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, c
             const double2* q = reinterpret_cast<const double2*>(tr + t);
             // TriRec: ax ay | s00 s01 | s10 s11 | uz z0 | z1 z2 | ruz bbox
             const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
+            const uint32_t gid = slot_gid(a.id_base, a.idmap, t);
             if (base + 32 + lane < n) t_next = __ldg(a.bins + off + base + 32 + lane);
             const unsigned long long bbw = (unsigned long long)__double_as_longlong(r5.y);
             X0 = max((int)(bbw & 0xffff), tx0); X1 = min((int)((bbw >> 32) & 0xffff), tx0 + TILE - 1);
@@ -1113,7 +1135,7 @@ k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, c
             d[3] = make_double2(r3.x, r5.x);             // uz, ruz
             d[4] = make_double2(r3.y, r4.x);             // z0, z1
             const uint32_t flags = exponent_in_window(r3.x) ? 1u : 0u;
-            d[5] = make_double2(r4.y, __longlong_as_double((long long)(((unsigned long long)flags << 32) | (a.id_base + t + 1u))));
+            d[5] = make_double2(r4.y, __longlong_as_double((long long)(((unsigned long long)flags << 32) | gid)));
         }
         // ---- the rows of the batch's triangles laid end to end and dealt out 32 at a time (a lane per triangle walking
         //      its own rows would idle two lanes out of three: triangles have ~5 rows, the tallest of a batch 16).  A lane
@@ -1307,12 +1329,12 @@ k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, c
 
 // the id pass of the unbinned fallback (see unbinned_pass); the depth pass runs inside k_raster
 template <bool IDS>
-__global__ void __launch_bounds__(TPB) k_unbinned(FrameDev f, uint32_t ntris, uint32_t id_base,
+__global__ void __launch_bounds__(TPB) k_unbinned(FrameDev f, uint32_t ntris, uint32_t id_base, const uint32_t* __restrict__ idmap,
                                                   const uint2* __restrict__ tribox, const TriRec* __restrict__ trirec,
                                                   const DrawCtl* __restrict__ ctl) {
     if (!ctl->overflow) return;
     const int view = blockIdx.y;
-    unbinned_pass<IDS>(f.zkey, f.vis, f.stats, f.npix, f.W, f.H, view, view + 1, ntris, id_base, tribox, trirec,
+    unbinned_pass<IDS>(f.zkey, f.vis, f.stats, f.npix, f.W, f.H, view, view + 1, ntris, id_base, idmap, tribox, trirec,
                        blockIdx.x * (TPB / 32) + (threadIdx.x >> 5), gridDim.x * (TPB / 32));
 }
 

@@ -16,6 +16,11 @@
 
 using namespace trbk;
 
+// mesh_order.cu: coherent processing order of a large indexed mesh (Morton order of the triangle centroids)
+size_t trb_mesh_order_scratch_bytes(uint32_t ntris);
+cudaError_t trb_mesh_order_build(const float4* pos4, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint32_t* perm_out,
+                                 uint32_t* idx_perm_out, void* scratch, size_t scratch_bytes, int sms, cudaStream_t st);
+
 namespace {
 
 struct DevBuf {
@@ -198,6 +203,10 @@ struct Mesh {
     uint32_t nverts = 0;
     uint64_t nidx = 0;
     bool alive = false;
+    // processing order of a large indexed mesh (mesh_order.cu): slot j of a draw holds triangle perm[j], whose vertex
+    // indices are idx_perm[3j..3j+2]; nullptr for small meshes (their vertex records stay in L2 whatever the order)
+    uint32_t* perm = nullptr;
+    uint32_t* idx_perm = nullptr;
 };
 struct Tex {
     uint8_t* px = nullptr;
@@ -333,6 +342,9 @@ struct TrbCtx {
     bool maps_ok = false;
     bool use_tma = true;                // TRB_TMA=0: LDG / STG staging
     bool foreign_ids = false;   // trb_set_triangle_id_base was used: the id plane may hold winners other ranks rasterised
+    // indexed meshes of at least this many triangles get a processing order at upload (TRB_MESH_ORDER_MIN_TRIS; 0 = never).
+    // Default: from 2 M triangles up - below that the vertex records of a draw (32 B each) sit in the 126 MB L2 anyway.
+    uint64_t order_min_tris = 2ull << 20;
 };
 
 namespace {
@@ -593,8 +605,9 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     if (rs) return rs;
     const size_t nslots = (size_t)f.nviews * f.ntiles;
     if (nslots >= 0xFFFFFFFFull) return fail(c, TRB_E_ARG, "draw: too many tiles x views");
-    CU(c->tribox.ensure((size_t)f.nviews * g.ntris * sizeof(uint2), c->stream));
-    CU(c->trirec.ensure((size_t)f.nviews * g.ntris * sizeof(TriRec), c->stream));
+    const uint32_t ndslots = g.nslots;     // == g.ntris unless the mesh carries a processing order (GeomArgs::perm)
+    CU(c->tribox.ensure((size_t)f.nviews * ndslots * sizeof(uint2), c->stream));
+    CU(c->trirec.ensure((size_t)f.nviews * ndslots * sizeof(TriRec), c->stream));
     CU(c->offsets.ensure(nslots * 4, c->stream));
     CU(c->heavy_list.ensure(nslots * 4, c->stream));
     {
@@ -609,7 +622,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         c->cursor_p = reinterpret_cast<uint32_t*>(z + o_cursor);
         CU(cudaMemsetAsync(z, 0, bytes, c->stream));
     }
-    if (c->direct_area > 0) CU(c->direct_list.ensure((size_t)f.nviews * g.ntris * 4, c->stream));
+    if (c->direct_area > 0) CU(c->direct_list.ensure((size_t)f.nviews * ndslots * 4, c->stream));
     uint32_t capacity = 0xFFFFFFFFu;   // synchronous draws size the buffer after the scan
     if (!c->sync_draws) {
         // R of the most recent draw the device has finished scanning: a hint, never waited for
@@ -620,10 +633,10 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         CU(c->bins.ensure((size_t)want * 4, c->stream));
         capacity = c->bin_cap_fixed ? c->bin_cap_fixed : (uint32_t)std::min<uint64_t>(c->bins.cap / 4, 0xFFFFFFF0ull);
     }
-    dim3 tgrid(blocks_for(g.ntris), f.nviews);
+    dim3 tgrid(blocks_for(ndslots), f.nviews);
     {
         Launch L(c, "k_setup_count");
-        const dim3 sgrid((g.ntris + TPB * SETUP_CHUNKS - 1) / (TPB * SETUP_CHUNKS), f.nviews);
+        const dim3 sgrid((ndslots + TPB * SETUP_CHUNKS - 1) / (TPB * SETUP_CHUNKS), f.nviews);
         k_setup_count<<<sgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
                                                      c->counts_p, c->direct_area, c->direct_list.as<uint32_t>(),
                                                      c->direct_n_p);
@@ -647,12 +660,13 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     }
     {
         Launch L(c, "k_fill");
-        k_fill<<<tgrid, TPB, 0, c->stream>>>(f, g.ntris, c->tribox.as<uint2>(), c->offsets.as<uint32_t>(),
+        k_fill<<<tgrid, TPB, 0, c->stream>>>(f, ndslots, c->tribox.as<uint2>(), c->offsets.as<uint32_t>(),
                                             c->cursor_p, c->bins.as<uint32_t>(), c->ctl_p);
     }
     RasterArgs ra;
-    ra.ntris = g.ntris;
-    ra.id_base = g.id_base;
+    ra.ntris = ndslots;
+    ra.id_base = g.perm ? g.id_base - g.first_tri : g.id_base;   // slot_gid adds perm[slot] (a mesh triangle) or the slot
+    ra.idmap = g.perm;
     ra.trirec = c->trirec.as<TriRec>();
     ra.tribox = c->tribox.as<uint2>();
     ra.counts = c->counts_p;
@@ -683,10 +697,10 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     }
     {   // stand-in for a draw that overflowed its bins or 32-bit offsets (exits at once otherwise): the id pass of the
         // unbinned fallback; its depth pass ran inside k_raster's grid
-        const dim3 grid((unsigned)std::min<unsigned>(blocks_for((unsigned long long)g.ntris * 32),
+        const dim3 grid((unsigned)std::min<unsigned>(blocks_for((unsigned long long)ndslots * 32),
                                                     std::max(1u, (unsigned)c->sms * 8 / (unsigned)f.nviews)), f.nviews);
         Launch L(c, "k_unbinned_ids");
-        k_unbinned<true><<<grid, TPB, 0, c->stream>>>(f, g.ntris, g.id_base, c->tribox.as<uint2>(), c->trirec.as<TriRec>(), c->ctl_p);
+        k_unbinned<true><<<grid, TPB, 0, c->stream>>>(f, ndslots, ra.id_base, ra.idmap, c->tribox.as<uint2>(), c->trirec.as<TriRec>(), c->ctl_p);
     }
     CU(cudaGetLastError());
     return TRB_OK;
@@ -851,6 +865,7 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_TMA")) c->use_tma = atoi(e) != 0;
     if (const char* e = getenv("TRB_SYNC_DRAWS")) c->sync_draws = atoi(e) != 0;
     if (const char* e = getenv("TRB_BIN_CAP")) c->bin_cap_fixed = (uint32_t)std::max(1, atoi(e));
+    if (const char* e = getenv("TRB_MESH_ORDER_MIN_TRIS")) c->order_min_tris = (uint64_t)std::max(0ll, atoll(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->upload_ev, cudaEventDisableTiming) != cudaSuccess ||
@@ -879,6 +894,8 @@ int trb_destroy(TrbCtx* c) {
             cudaFree(m.pos4);
             cudaFree(m.attr8);
             if (m.idx) cudaFree(m.idx);
+            if (m.perm) cudaFree(m.perm);
+            if (m.idx_perm) cudaFree(m.idx_perm);
         }
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
@@ -980,6 +997,26 @@ int upload_pinned(TrbCtx* c, void** dev, const void* src, size_t bytes) {
     CU(cudaMemcpyAsync(*dev, src, bytes, cudaMemcpyHostToDevice, c->upload_stream));
     return TRB_OK;
 }
+// processing order of a freshly uploaded large indexed mesh, queued on the upload stream behind its arrays
+int build_mesh_order(TrbCtx* c, Mesh& m) {
+    const uint64_t ntris = m.nidx / 3;
+    if (!m.idx || c->order_min_tris == 0 || ntris < c->order_min_tris || ntris > 0x7fffffffull) return TRB_OK;
+    const size_t sbytes = trb_mesh_order_scratch_bytes((uint32_t)ntris);
+    void* scratch = nullptr;
+    cudaEvent_t w0 = nullptr, w1 = nullptr, w2 = nullptr;
+    CU(c->cache.get((void**)&m.perm, ntris * 4, &w0, c->upload_stream));
+    CU(c->cache.get((void**)&m.idx_perm, m.nidx * 4, &w1, c->upload_stream));
+    CU(c->cache.get(&scratch, sbytes, &w2, c->upload_stream));
+    if (w0) CU(cudaStreamWaitEvent(c->upload_stream, w0, 0));
+    if (w1) CU(cudaStreamWaitEvent(c->upload_stream, w1, 0));
+    if (w2) CU(cudaStreamWaitEvent(c->upload_stream, w2, 0));
+    {
+        Launch L(c, "mesh_order", c->upload_stream, /*kernel=*/false);   // several kernels incl. the library sort: timed as one span
+        CU(trb_mesh_order_build(m.pos4, m.nverts, m.idx, (uint32_t)ntris, m.perm, m.idx_perm, scratch, sbytes, c->sms, c->upload_stream));
+    }
+    c->cache.put(scratch, sbytes, c->upload_stream);
+    return TRB_OK;
+}
 // everything uploaded so far becomes visible to the render stream
 int publish_uploads(TrbCtx* c) {
     CU(cudaEventRecord(c->upload_ev, c->upload_stream));
@@ -1027,6 +1064,8 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
         c->cache.put(rp, (size_t)nverts * 12, c->upload_stream);   // raw arrays: free again once the kernel has run
         c->cache.put(rn, (size_t)nverts * 12, c->upload_stream);
         c->cache.put(ru, (size_t)nverts * 8, c->upload_stream);
+        rc = build_mesh_order(c, m);
+        if (rc) return rc;
         rc = publish_uploads(c);
         if (rc) return rc;
         m.alive = true;
@@ -1065,6 +1104,8 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
         });
         if (rc) return rc;
     }
+    rc = build_mesh_order(c, m);
+    if (rc) return rc;
     rc = publish_uploads(c);
     if (rc) return rc;
     m.alive = true;
@@ -1087,6 +1128,8 @@ int trb_free_mesh(TrbCtx* c, TrbMesh h) {
     c->cache.put(m.pos4, (size_t)m.nverts * 16, c->stream);   // tagged: reusable once the kernels queued so far are done
     c->cache.put(m.attr8, (size_t)m.nverts * 32, c->stream);
     if (m.idx) c->cache.put(m.idx, m.nidx * 4, c->stream);
+    if (m.perm) c->cache.put(m.perm, m.nidx / 3 * 4, c->stream);
+    if (m.idx_perm) c->cache.put(m.idx_perm, m.nidx * 4, c->stream);
     m = Mesh();
     return TRB_OK;
 }
@@ -1258,6 +1301,11 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
     g.nverts = m.nverts;
     g.id_base = (uint32_t)c->next_id;
     g.vrec = vrec;
+    // the mesh's processing order, unless the range is a small part of the mesh (the draw visits every slot of the mesh)
+    const bool ordered = m.perm && ntris * 16 >= m.nidx / 3;
+    g.perm = ordered ? m.perm : nullptr;
+    g.idx_perm = ordered ? m.idx_perm : nullptr;
+    g.nslots = ordered ? (uint32_t)(m.nidx / 3) : g.ntris;
     rc = raster_draw(c, g);   // `hm`, `hl` are pageable: their copies were staged before cudaMemcpyAsync returned
     if (rc) return rc;
     DrawDev d{};
@@ -1332,6 +1380,9 @@ int trb_submit_clip_triangles(TrbCtx* c, const double* clip12, const double* var
     g.nverts = nverts;
     g.id_base = (uint32_t)c->next_id;
     g.vrec = vrec;
+    g.perm = nullptr;
+    g.idx_perm = nullptr;
+    g.nslots = g.ntris;
     rc = raster_draw(c, g);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));  // caller may reuse clip12 / varyings / hm
