@@ -405,15 +405,14 @@ def measure(args, env, workload, steps, warmup, primary, composite="p2p"):
         if not sharded_c4:
             wl.render(up, wl.views(api, s, rank, world))
             return
-        # config 4 on N GPUs: triangle range per rank, sort-last composite, shade own rows
+        # config 4 on N GPUs: every rank draws its share of the mesh (trb_draw_shard: blocks of the mesh's processing
+        # order dealt out round robin, ids global), sort-last composite, shade own rows
         it = wl.scene.items[0]
-        first, count = multigpu.triangle_shard(it.mesh.ntris, rank, world)
         r.begin_frame(wl.width, wl.height)
         if p2p is not None and not p2p.opened:
             p2p.open()                    # once: the planes of this frame size are exported to the peers
-        r.set_triangle_id_base(first)
         mv = api.mat4_mul(wl.views(api, s, rank, world)[0], it.model_matrix)
-        r.draw(up.mesh_h[id(it.mesh)], mv, wl.perspective, kind=it.kind, first_tri=first, ntris=count)
+        r.draw_shard(up.mesh_h[id(it.mesh)], mv, wl.perspective, rank, world, kind=it.kind)
         if composite == "p2p":
             p2p.run()                     # fused NVLink composite + shade of the owned rows, stream-ordered against the peers
         else:

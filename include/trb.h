@@ -137,7 +137,11 @@ TRB_EXPORT const char* TRB_FN(backend_name)(void); /* "cuda-sm100a", "oracle-ref
  * Pageable arrays are consumed (staged through pinned chunks) when the call returns.
  * Page-locked arrays (cudaHostAlloc / cudaHostRegister) are read by the copy engine directly,
  * without a CPU copy: the caller keeps them alive and unchanged until the next synchronising
- * call (synchronize, read_*, readback_wait, get_stats).  Same for upload_texture. */
+ * call (synchronize, read_*, readback_wait, get_stats).  Same for upload_texture.
+ * Indexed meshes of 2 M triangles or more (TRB_MESH_ORDER_MIN_TRIS overrides; 0 = never) also get a PROCESSING ORDER
+ * at upload: the triangles sorted by the Morton code of their centroids (device-side, on the upload stream).  Draws
+ * visit the triangles in that order so that the vertex records a triangle gathers are the ones its predecessors just
+ * used; triangle ids - and with them every output bit - stay those of the index buffer. */
 TRB_EXPORT int TRB_FN(upload_mesh)(TrbCtx* ctx, const float* pos3, const float* nrm3,
                                    const float* uv2, uint32_t nverts, const uint32_t* idx,
                                    uint64_t nidx, TrbMesh* out);
@@ -174,6 +178,17 @@ TRB_EXPORT int TRB_FN(draw_batch)(TrbCtx* ctx, TrbMesh mesh, const double* model
                                   const double* perspective, int shader_kind,
                                   const void* uniforms, size_t uniform_bytes, uint64_t first_tri,
                                   uint64_t ntris);
+/* One rank's share of a mesh that shard_count ranks draw together into one picture (sort-last, config 4): the whole
+ * mesh is submitted, this context rasterises the triangles that fall to shard_rank.  Triangle ids are those of the whole
+ * mesh on every rank (the draw consumes the mesh's id range; trb_set_triangle_id_base is not needed), so after
+ * trb_composite the picture is bit for bit what one context drawing the mesh with trb_draw produces, depth ties included
+ * (our_gl.cpp:160-166).  Which triangles a rank gets is the backend's choice: meshes that carry a processing order
+ * (large indexed meshes, see trb_upload_mesh) are dealt out in blocks of 4096 consecutive positions of that order -
+ * every rank's share is spatially coherent and evenly spread over the surface; other meshes are split into contiguous
+ * ranges of the index buffer.  Single-view frames only; replaces the loop main.cpp:660-666 on N devices. */
+TRB_EXPORT int TRB_FN(draw_shard)(TrbCtx* ctx, TrbMesh mesh, const double modelview[16], const double perspective[16],
+                                  int shader_kind, const void* uniforms, size_t uniform_bytes, int shard_rank,
+                                  int shard_count);
 /* immediate mode behind rasterize(const Triangle&, const IShader&, TGAImage&)
  * (our_gl.cpp:89): n clip-space triangles, clip12 = n*12 doubles (3 x vec4).
  * varyings (may be NULL for FLAT_BARY/DEPTH): n*24 doubles per triangle =

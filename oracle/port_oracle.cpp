@@ -665,6 +665,16 @@ int orc_profile_read(TrbCtx* c, TrbKernelTime*, int, int* n, int) {
 uint64_t orc_launch_count(TrbCtx*) { return 0; }
 int orc_device_planes(TrbCtx* c, uint64_t*, uint64_t*, uint64_t*) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_set_triangle_id_base(TrbCtx* c, uint64_t) { return c ? TRB_OK : TRB_E_ARG; }
+// trb_draw_shard on the CPU checker: rank r's share is a contiguous range of the index buffer (any partition of the
+// triangles gives the same composited picture; the oracle keeps no ids)
+int orc_draw_shard(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
+                   size_t ubytes, int shard_rank, int shard_count) {
+    if (!c || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return fail(c, TRB_E_ARG, "draw_shard: bad rank / count");
+    if (mesh == 0 || mesh > c->meshes.size() || !c->meshes[mesh - 1]) return fail(c, TRB_E_ARG, "draw: bad mesh");
+    const uint64_t total = c->meshes[mesh - 1]->idx.size() / 3, n = (uint64_t)shard_count, r = (uint64_t)shard_rank;
+    const uint64_t base = total / n, rem = total % n;
+    return orc_draw(c, mesh, mv, pr, kind, uniforms, ubytes, r * base + (r < rem ? r : rem), base + (r < rem ? 1 : 0));
+}
 int orc_composite_save_local_depth(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_composite_mask(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_composite_finish(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }

@@ -266,6 +266,97 @@ def test_composite_group_on_one_gpu(cuda_api, port_api, nranks):
         r.close()
 
 
+def _phong(api, mv, tex_handle):
+    u = trb.PhongUniforms()
+    u.key_dir_eye[:] = api.light_dir_eye(mv, scenes.normalized(scenes.KEY_LIGHT))
+    u.fill_dir_eye[:] = api.light_dir_eye(mv, scenes.normalized(scenes.FILL_LIGHT))
+    u.rim_dir_eye[:] = api.light_dir_eye(mv, scenes.normalized(scenes.RIM_LIGHT))
+    u.normal_map_strength = 0.0
+    u.diffuse = tex_handle
+    return u
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order_min_tris", ["1", "0"])
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_draw_shard_composite_group_on_one_gpu(cuda_api, port_api, monkeypatch, nranks, order_min_tris):
+    """trb_draw_shard: every rank submits the WHOLE mesh and rasterises its share (blocks of the mesh's processing order
+    when it has one - TRB_MESH_ORDER_MIN_TRIS=1 forces it for this small mesh, the last block is partial - else a contiguous
+    range), ids global without trb_set_triangle_id_base, two draws per frame.  After trb_composite_group every frame equals
+    the unsharded render of the oracle, ties across ranks included."""
+    monkeypatch.setenv("TRB_MESH_ORDER_MIN_TRIS", order_min_tris)
+    m = scenes.icosphere(5)
+    w, h = 640, 400
+    pr = cuda_api.perspective(60, w / h, 0.1, 10)
+    idx = np.concatenate([m.idx, m.idx, m.idx[:300]])      # duplicates: exact depth ties across ranks; 41 060 triangles
+    ntris = idx.size // 3
+    tex = scenes.texture_diffuse(64, 3)
+    shift = np.eye(4)
+    shift[0, 3], shift[2, 3] = 0.9, -0.8                   # a second copy of the sphere, partly behind the first
+    rs = [trb.Renderer(cuda_api) for _ in range(nranks)]
+    meshes = [r.upload_mesh(m.pos, m.nrm, m.uv, idx) for r in rs]
+    texes = [r.upload_texture(tex) for r in rs]
+    for r in rs:
+        r.begin_frame(w, h)
+    trb.comm_init(rs)
+    cams = [[0.0, 0.0, 2.6], [0.7, 0.3, 2.4]]
+    for cam in cams:
+        view = cuda_api.lookat(cam, [0, 0, 0], [0, 1, 0])
+        mvs = [view, cuda_api.mat4_mul(view, shift)]
+        for rank, r in enumerate(rs):
+            r.begin_frame(w, h)
+            for mv in mvs:
+                r.draw_shard(meshes[rank], mv, pr, rank, nranks, kind=trb.SHADER_PHONG, uniforms=_phong(cuda_api, mv, texes[rank]))
+        trb.composite_group(rs)
+        color = np.zeros((h, w, 3), np.uint8)
+        depth = np.zeros((h, w))
+        for rank, r in enumerate(rs):
+            y0, y1 = r.comm_rows()
+            color[y0:y1] = r.read_color()[y0:y1]
+            depth[y0:y1] = r.read_depth()[y0:y1]
+        with trb.Renderer(port_api) as o:
+            mesh, th = o.upload_mesh(m.pos, m.nrm, m.uv, idx), o.upload_texture(tex)
+            o.begin_frame(w, h)
+            ov = port_api.lookat(cam, [0, 0, 0], [0, 1, 0])
+            for mv in (ov, port_api.mat4_mul(ov, shift)):
+                o.draw(mesh, mv, pr, kind=trb.SHADER_PHONG, uniforms=_phong(port_api, mv, th), ntris=ntris)
+            o.end_frame()
+            assert np.array_equal(depth.view(np.uint64), o.read_depth().view(np.uint64))
+            assert np.abs(color.astype(int) - o.read_color().astype(int)).max() <= 1
+    for r in rs:
+        r.close()
+
+
+@pytest.mark.gpu
+def test_draw_shard_shares_partition_the_mesh(cuda_api, monkeypatch):
+    """the shares of trb_draw_shard are disjoint and cover the mesh: the ranks' submitted-triangle counts add up, and
+    the union of the id planes of the ranks (each rendered alone, no composite) holds every id one context produces"""
+    monkeypatch.setenv("TRB_MESH_ORDER_MIN_TRIS", "1")
+    m = scenes.icosphere(5)
+    w, h = 512, 512
+    mv, pr = cuda_api.lookat([0, 0, 2.2], [0, 0, 0], [0, 1, 0]), cuda_api.perspective(60, 1.0, 0.1, 10)
+    with trb.Renderer(cuda_api) as r:
+        mesh = r.upload_mesh(m.pos, m.nrm, m.uv, m.idx)
+        r.begin_frame(w, h)
+        r.draw(mesh, mv, pr, ntris=m.ntris)
+        whole = r.read_visibility(0).copy()
+        whole_z = r.read_depth(0).copy()
+        r.end_frame()
+        seen = np.full((h, w), 0xFFFFFFFF, np.uint32)
+        zmin = np.full((h, w), np.inf)
+        total = 0
+        for rank in range(3):
+            r.begin_frame(w, h)
+            r.draw_shard(mesh, mv, pr, rank, 3)
+            total += r.stats(0)["triangles_submitted"]
+            vis, z = r.read_visibility(0), r.read_depth(0)
+            better = (z < zmin) | ((z == zmin) & (vis < seen))
+            seen[better], zmin[better] = vis[better], z[better]
+            r.end_frame()
+        assert total == m.ntris
+        assert np.array_equal(seen, whole) and np.array_equal(zmin.view(np.uint64), whole_z.view(np.uint64))
+
+
 def _ipc_rank(rank, world, out_dir):
     """one process per GPU: blobs exchanged through files, then frames without any host barrier"""
     import time
@@ -304,8 +395,11 @@ def _ipc_rank(rank, world, out_dir):
                 time.sleep(0.3)                   # a straggler: the peers' streams wait on the device, not the hosts
             mv = api.lookat(cam, [0, 0, 0], [0, 1, 0])
             r.begin_frame(w, h)
-            first, count = comm.shard(ntris)
-            _shard_frame(api, r, mesh, ntris, first, count, mv, pr, th)
+            if k % 2 == 0:
+                first, count = comm.shard(ntris)
+                _shard_frame(api, r, mesh, ntris, first, count, mv, pr, th)
+            else:                                  # the backend picks the share (trb_draw_shard)
+                r.draw_shard(mesh, mv, pr, rank, world, kind=trb.SHADER_PHONG, uniforms=_phong(api, mv, th))
             y0, y1 = comm.run()
             res.append((y0, r.read_depth()[y0:y1].copy(), r.read_color()[y0:y1].copy()))
         np.save(os.path.join(out_dir, "rank%d.npy" % rank), np.array(res, dtype=object), allow_pickle=True)

@@ -106,6 +106,7 @@ SIGNATURES = {
     "set_viewport": (C.c_int, [_P, _P]),
     "draw": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_int, _P, C.c_size_t, C.c_uint64, C.c_uint64]),
     "draw_batch": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_int, _P, C.c_size_t, C.c_uint64, C.c_uint64]),
+    "draw_shard": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_int, _P, C.c_size_t, C.c_int, C.c_int]),
     "submit_clip_triangles": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_int, _P, C.c_size_t]),
     "depth_snapshot": (C.c_int, [_P]),
     "depth_restore": (C.c_int, [_P]),
@@ -362,6 +363,14 @@ class Renderer:
             self._keep.append(arr)
         name = "draw" if self.nviews == 1 else "draw_batch"
         self._ck(self._fn[name](self.h, mesh, _ptr(mv), _ptr(pr), kind, up, ub, first_tri, ntris), name)
+
+    def draw_shard(self, mesh, modelview, perspective, shard_rank, shard_count, kind=SHADER_FLAT_BARY, uniforms=None):
+        """this context's share of a mesh that `shard_count` contexts draw into one picture (trb_draw_shard)"""
+        mv, pr = _f64(modelview, 16), _f64(perspective, 16)
+        up, ub = (None, 0) if uniforms is None else (C.cast(C.pointer(uniforms), _P), C.sizeof(uniforms))
+        if uniforms is not None:
+            self._keep.append(uniforms)
+        self._ck(self._fn["draw_shard"](self.h, mesh, _ptr(mv), _ptr(pr), kind, up, ub, shard_rank, shard_count), "draw_shard")
 
     def submit_clip_triangles(self, clip, varyings=None, modelview=None, kind=SHADER_FLAT_BARY, uniforms=None):
         clip = np.ascontiguousarray(clip, dtype=np.float64).reshape(-1, 12)

@@ -186,11 +186,24 @@ struct GeomArgs {
     // so depth ties still go to the triangle submitted first.  perm == nullptr: slot == triangle of the range.
     const uint32_t* perm;
     const uint32_t* idx_perm;
-    uint32_t nslots;           // perm ? triangles of the mesh : ntris
+    uint32_t nslots;           // perm ? slots this draw visits (the whole mesh, or this rank's share of it) : ntris
+    // trb_draw_shard: rank shard_r of shard_n draws the blocks b = shard_r (mod shard_n) of 2^shard_shift consecutive
+    // positions of the processing order - a spatially coherent AND evenly spread share of the mesh (a contiguous run
+    // of the order would be one patch of the surface, all of it back-facing for some ranks).  shard_n <= 1: no sharding
+    uint32_t shard_n, shard_r, shard_shift;
+    uint32_t nperm;            // entries of perm
 };
-// id of the triangle in slot `slot`: id_off = id_base - first_tri (mod 2^32) when idmap (= perm) is set, else id_base
-__device__ __forceinline__ uint32_t slot_gid(uint32_t id_off, const uint32_t* __restrict__ idmap, uint32_t slot) {
-    return id_off + (idmap ? __ldg(idmap + slot) : slot) + 1u;
+// position in the processing order of the draw's slot `slot` (identity unless the draw is one rank's share)
+__device__ __forceinline__ uint32_t slot_position(uint32_t slot, uint32_t shard_n, uint32_t shard_r, uint32_t shard_shift) {
+    return shard_n > 1u ? ((((slot >> shard_shift) * shard_n + shard_r) << shard_shift) | (slot & ((1u << shard_shift) - 1u))) : slot;
+}
+struct SlotIds {               // slot -> triangle id for the raster kernels
+    const uint32_t* perm;      // nullptr: id = id_off + slot + 1
+    uint32_t id_off;           // id_base - first_tri (mod 2^32) with perm, else id_base
+    uint32_t shard_n, shard_r, shard_shift;
+};
+__device__ __forceinline__ uint32_t slot_gid(const SlotIds& m, uint32_t slot) {
+    return m.id_off + (m.perm ? __ldg(m.perm + slot_position(slot, m.shard_n, m.shard_r, m.shard_shift)) : slot) + 1u;
 }
 
 constexpr uint32_t BOX_NONE = 0xFFFFFFFFu;
@@ -303,8 +316,10 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
     uint32_t n0 = 0, n1 = 0, n2 = 0, nm = 0;
     auto fetch_slot = [&](uint32_t slot) {
         if (g.perm) {
-            nm = __ldg(g.perm + slot) - g.first_tri;               // triangle inside the range, or >= ntris (wraps)
-            const uint32_t* q = g.idx_perm + (size_t)slot * 3;
+            const uint32_t j = slot_position(slot, g.shard_n, g.shard_r, g.shard_shift);
+            if (j >= g.nperm) { nm = 0xffffffffu; n0 = n1 = n2 = 0u; return; }   // past the end of the last block
+            nm = __ldg(g.perm + j) - g.first_tri;                  // triangle inside the range, or >= ntris (wraps)
+            const uint32_t* q = g.idx_perm + (size_t)j * 3;
             n0 = __ldg(q); n1 = __ldg(q + 1); n2 = __ldg(q + 2);
         } else {
             nm = slot;
@@ -453,7 +468,7 @@ __global__ void __launch_bounds__(TPB) k_direct_resolve(FrameDev f, GeomArgs g, 
     if (i >= direct_n[view]) return;
     const uint32_t t = direct_list[(size_t)view * g.nslots + i];     // a slot
     const VRec* vr = g.vrec + (size_t)view * g.nverts;
-    const uint32_t* q = g.perm ? g.idx_perm + (size_t)t * 3 : nullptr;
+    const uint32_t* q = g.perm ? g.idx_perm + (size_t)slot_position(t, g.shard_n, g.shard_r, g.shard_shift) * 3 : nullptr;
     VRec a = load_vrec(vr + (q ? __ldg(q) : vertex_index(g.idx, g.first_tri, t, 0)));
     VRec b_ = load_vrec(vr + (q ? __ldg(q + 1) : vertex_index(g.idx, g.first_tri, t, 1)));
     VRec c = load_vrec(vr + (q ? __ldg(q + 2) : vertex_index(g.idx, g.first_tri, t, 2)));
@@ -461,7 +476,7 @@ __global__ void __launch_bounds__(TPB) k_direct_resolve(FrameDev f, GeomArgs g, 
     setup_triangle(a, b_, c, f.W, f.H, ts);
     const unsigned long long* zk = f.zkey + (size_t)view * f.npix;
     uint32_t* vis = f.vis + (size_t)view * f.npix;
-    const uint32_t gid = slot_gid(g.id_base - (g.perm ? g.first_tri : 0u), g.perm, t);
+    const uint32_t gid = slot_gid(SlotIds{g.perm, g.id_base - (g.perm ? g.first_tri : 0u), g.shard_n, g.shard_r, g.shard_shift}, t);
     for (int y = ts.y0; y <= ts.y1; ++y)
         for (int x = ts.x0; x <= ts.x1; ++x) {
             double b[3], z;
@@ -630,8 +645,8 @@ constexpr int LARGE_NS_DEFAULT = 128;   // clipped-bbox samples from which a tri
 constexpr int SP_GROUP = 3;             // sample-parallel rounds (of TPB samples) between two resolves
 
 struct RasterArgs {
-    uint32_t ntris, id_base;  // slots of the draw; id offset of slot_gid
-    const uint32_t* idmap;    // slot -> mesh triangle (GeomArgs::perm) or nullptr
+    uint32_t ntris;           // slots of the draw
+    SlotIds ids;              // slot -> triangle id
     const TriRec* trirec;     // [nviews][ntris]
     const uint2* tribox;      // [nviews][ntris] tile ranges (k_setup_count); BOX_NONE / BOX_DIRECT markers
     const uint32_t* counts;   // [nviews][ntiles]
@@ -721,7 +736,7 @@ __device__ __forceinline__ void raster_tile_cta(const FrameDev& f, const RasterA
         if (has) {
             const uint32_t t = __ldg(a.bins + off + base + tid);
             load_trirec(tr + t, ts);
-            gid = slot_gid(a.id_base, a.idmap, t);
+            gid = slot_gid(a.ids, t);
             cx0 = max(ts.x0, tx0); cx1 = min(ts.x1, tx0 + TILE - 1);
             cy0 = max(ts.y0, ty0); cy1 = min(ts.y1, ty0 + TILE - 1);
             ns = (cx1 - cx0 + 1) * (cy1 - cy0 + 1);
@@ -854,7 +869,7 @@ __device__ __forceinline__ void raster_tile_cta(const FrameDev& f, const RasterA
 // ---------------------------------------------------------------------------------------------
 template <bool IDS>
 __device__ __noinline__ void unbinned_pass(unsigned long long* zkey, uint32_t* visp, DevStats* stats, size_t npix, int W, int H,
-                                           int view0, int view1, uint32_t ntris, uint32_t id_base, const uint32_t* __restrict__ idmap,
+                                           int view0, int view1, uint32_t ntris, const SlotIds& ids,
                                            const uint2* __restrict__ tribox, const TriRec* __restrict__ trirec,
                                            uint32_t w0, uint32_t nwarps) {
     const unsigned FULL = 0xffffffffu;
@@ -868,7 +883,7 @@ __device__ __noinline__ void unbinned_pass(unsigned long long* zkey, uint32_t* v
             TriSetup ts;
             load_trirec(trirec + (size_t)view * ntris + t, ts);
             const uint32_t bw = (uint32_t)(ts.x1 - ts.x0 + 1), ns = bw * (uint32_t)(ts.y1 - ts.y0 + 1);
-            const uint32_t gid = slot_gid(id_base, idmap, t);
+            const uint32_t gid = slot_gid(ids, t);
             for (uint32_t s = lane; s < ns; s += 32) {
                 const uint32_t row = s / bw;
                 const int x = ts.x0 + (int)(s - row * bw), y = ts.y0 + (int)row;
@@ -906,7 +921,7 @@ __device__ __noinline__ void unbinned_pass(unsigned long long* zkey, uint32_t* v
 // persistent grid over the (usually short or empty) list of long bins
 __global__ void __launch_bounds__(TPB, TRB_RASTER_MIN_BLOCKS) k_raster(FrameDev f, RasterArgs a) {
     if (a.ctl->overflow) {   // the bins were not filled: depth pass of the unbinned fallback, warps over all triangles of all views
-        unbinned_pass<false>(f.zkey, f.vis, f.stats, f.npix, f.W, f.H, 0, f.nviews, a.ntris, a.id_base, a.idmap, a.tribox, a.trirec,
+        unbinned_pass<false>(f.zkey, f.vis, f.stats, f.npix, f.W, f.H, 0, f.nviews, a.ntris, a.ids, a.tribox, a.trirec,
                              blockIdx.x * (TPB / 32) + (threadIdx.x >> 5), gridDim.x * (TPB / 32));
         return;
     }
@@ -1121,7 +1136,7 @@ k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, c
             const double2* q = reinterpret_cast<const double2*>(tr + t);
             // TriRec: ax ay | s00 s01 | s10 s11 | uz z0 | z1 z2 | ruz bbox
             const double2 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
-            const uint32_t gid = slot_gid(a.id_base, a.idmap, t);
+            const uint32_t gid = slot_gid(a.ids, t);
             if (base + 32 + lane < n) t_next = __ldg(a.bins + off + base + 32 + lane);
             const unsigned long long bbw = (unsigned long long)__double_as_longlong(r5.y);
             X0 = max((int)(bbw & 0xffff), tx0); X1 = min((int)((bbw >> 32) & 0xffff), tx0 + TILE - 1);
@@ -1329,12 +1344,12 @@ k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, c
 
 // the id pass of the unbinned fallback (see unbinned_pass); the depth pass runs inside k_raster
 template <bool IDS>
-__global__ void __launch_bounds__(TPB) k_unbinned(FrameDev f, uint32_t ntris, uint32_t id_base, const uint32_t* __restrict__ idmap,
+__global__ void __launch_bounds__(TPB) k_unbinned(FrameDev f, uint32_t ntris, SlotIds ids,
                                                   const uint2* __restrict__ tribox, const TriRec* __restrict__ trirec,
                                                   const DrawCtl* __restrict__ ctl) {
     if (!ctl->overflow) return;
     const int view = blockIdx.y;
-    unbinned_pass<IDS>(f.zkey, f.vis, f.stats, f.npix, f.W, f.H, view, view + 1, ntris, id_base, idmap, tribox, trirec,
+    unbinned_pass<IDS>(f.zkey, f.vis, f.stats, f.npix, f.W, f.H, view, view + 1, ntris, ids, tribox, trirec,
                        blockIdx.x * (TPB / 32) + (threadIdx.x >> 5), gridDim.x * (TPB / 32));
 }
 
@@ -1650,22 +1665,58 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
 struct PeerPlanes {
     const unsigned long long* key[MAX_PEERS];
     const uint32_t* vis[MAX_PEERS];
+    // one byte per COMPOSITE_CHUNK pixels of the rank's key plane: non-zero when the rank drew anything there
+    // (k_chunk_touched, published with the rank's "drawn" counter); nullptr: unknown, read the rank's keys
+    const uint8_t* touched[MAX_PEERS];
     int n;
 };
+constexpr int COMPOSITE_CHUNK = TPB;     // pixels per flag == pixels per CTA of k_composite_shade_p2p
+
+// which chunks of the local key plane hold a fragment: one warp per chunk
+__global__ void __launch_bounds__(TPB) k_chunk_touched(const unsigned long long* __restrict__ zkey, unsigned long long npix,
+                                                       uint8_t* __restrict__ touched) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long chunk = (unsigned long long)blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+    const unsigned long long p0 = chunk * COMPOSITE_CHUNK;
+    if (p0 >= npix) return;
+    bool any = false;
+    #pragma unroll
+    for (int j = 0; j < COMPOSITE_CHUNK / 32; ++j) {
+        const unsigned long long p = p0 + (unsigned)j * 32u + lane;
+        any |= p < npix && zkey[p] != KEY_PLUS_INF;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) touched[chunk] = m ? 1 : 0;
+}
 template <bool C2, bool FAST>
 __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p2p(FrameDev f, PeerPlanes peers,
                                                                                   const DrawDev* __restrict__ draws,
                                                                                   int ndraws, int row0, int row1) {
     __shared__ DrawDev sm_draws[SHADE_MAX_SM_DRAWS];
+    __shared__ unsigned sm_ranks;
     stage_draw_table(sm_draws, draws, ndraws);
     const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
-    const unsigned long long p = first + (unsigned long long)blockIdx.x * TPB + threadIdx.x;
-    if (p >= last) return;
-    // depth keys of every rank first (8 B each over NVLink), ids only from the ranks that hold the minimum - usually one;
-    // a pixel nobody drew (key of +inf everywhere: fragments have finite depths) needs no id at all
-    unsigned long long bk = ~0ull;
+    // a CTA takes one chunk of the peers' "touched" maps (chunks are aligned to the plane, not to the rows this rank owns)
+    const unsigned long long chunk = first / COMPOSITE_CHUNK + blockIdx.x;
+    if (threadIdx.x < 32) {
+        bool t = false;
+        if ((int)threadIdx.x < peers.n) {
+            const uint8_t* q = peers.touched[threadIdx.x];
+            t = q ? *reinterpret_cast<const volatile uint8_t*>(q + chunk) != 0 : true;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, t);
+        if (threadIdx.x == 0) sm_ranks = m;
+    }
+    __syncthreads();
+    if (sm_ranks == 0u) return;              // nobody drew here: the local planes already say so (cleared)
+    const unsigned long long p = chunk * COMPOSITE_CHUNK + threadIdx.x;
+    if (p < first || p >= last) return;
+    // depth keys of the ranks that drew into this chunk (8 B each over NVLink), ids only from the ranks that hold the
+    // minimum - usually one; a pixel nobody drew (key of +inf everywhere: fragments have finite depths) needs no id at all
+    unsigned long long bk = KEY_PLUS_INF;
     unsigned holders = 0u;
-    for (int r = 0; r < peers.n; ++r) {
+    for (unsigned m = sm_ranks; m; m &= m - 1u) {
+        const int r = __ffs(m) - 1;
         const unsigned long long kk = peers.key[r][p];
         if (kk < bk) { bk = kk; holders = 1u << r; }
         else if (kk == bk) holders |= 1u << r;

@@ -665,8 +665,8 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     }
     RasterArgs ra;
     ra.ntris = ndslots;
-    ra.id_base = g.perm ? g.id_base - g.first_tri : g.id_base;   // slot_gid adds perm[slot] (a mesh triangle) or the slot
-    ra.idmap = g.perm;
+    // slot_gid adds perm[position of the slot] (a mesh triangle) or the slot itself
+    ra.ids = SlotIds{g.perm, g.perm ? g.id_base - g.first_tri : g.id_base, g.shard_n, g.shard_r, g.shard_shift};
     ra.trirec = c->trirec.as<TriRec>();
     ra.tribox = c->tribox.as<uint2>();
     ra.counts = c->counts_p;
@@ -700,7 +700,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         const dim3 grid((unsigned)std::min<unsigned>(blocks_for((unsigned long long)ndslots * 32),
                                                     std::max(1u, (unsigned)c->sms * 8 / (unsigned)f.nviews)), f.nviews);
         Launch L(c, "k_unbinned_ids");
-        k_unbinned<true><<<grid, TPB, 0, c->stream>>>(f, ndslots, ra.id_base, ra.idmap, c->tribox.as<uint2>(), c->trirec.as<TriRec>(), c->ctl_p);
+        k_unbinned<true><<<grid, TPB, 0, c->stream>>>(f, ndslots, ra.ids, c->tribox.as<uint2>(), c->trirec.as<TriRec>(), c->ctl_p);
     }
     CU(cudaGetLastError());
     return TRB_OK;
@@ -808,7 +808,9 @@ int enqueue_composite_shade(TrbCtx* c, int y0, int y1) {
         CU(cudaMemcpyAsync(c->draw_table.p, c->draws.data(), bytes, cudaMemcpyHostToDevice, c->stream));
         bool config2 = false;
         for (const DrawDev& d : c->draws) config2 |= d.kind >= 4;
-        const unsigned long long n = (unsigned long long)(y1 - y0) * c->frame.W;
+        // one CTA per chunk of the "touched" maps that overlaps the rows [y0, y1)
+        const unsigned long long p_first = (unsigned long long)y0 * c->frame.W, p_last = (unsigned long long)y1 * c->frame.W;
+        const unsigned long long n = ((p_last - 1) / COMPOSITE_CHUNK - p_first / COMPOSITE_CHUNK + 1) * COMPOSITE_CHUNK;
         Launch L(c, "k_composite_shade_p2p");
         const DrawDev* table = c->draw_table.as<DrawDev>();
         const int nd = (int)c->draws.size();
@@ -1239,23 +1241,60 @@ int trb_set_viewport(TrbCtx* c, const double* v) {
     return TRB_OK;
 }
 
-int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
-                   size_t ubytes, uint64_t first_tri, uint64_t ntris) {
-    HostSpan host_span_("trb_draw_batch");
+}  // extern "C"
+
+namespace {
+constexpr uint32_t SHARD_SHIFT = 12;    // trb_draw_shard deals the processing order out in blocks of 4096 triangles
+
+// One mesh draw.  shard_n <= 1: the triangle range [first_tri, first_tri + ntris) of the index buffer.
+// shard_n > 1 (trb_draw_shard): rank shard_r's share of the WHOLE mesh - first_tri / ntris are ignored.
+int draw_mesh(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
+              size_t ubytes, uint64_t first_tri, uint64_t ntris, uint32_t shard_n, uint32_t shard_r) {
     if (!c || !c->in_frame) return fail(c, TRB_E_ARG, "draw: no frame");
     if (!mv || !pr) return fail(c, TRB_E_ARG, "draw: null matrix");
     if (mesh == 0 || mesh > c->meshes.size() || !c->meshes[mesh - 1].alive) return fail(c, TRB_E_ARG, "draw: bad mesh");
     const Mesh& m = c->meshes[mesh - 1];
+    const uint64_t mesh_tris = m.nidx / 3;
+    // ids of a sharded draw are those of the whole mesh on every rank: base + triangle + 1
+    const uint64_t id_base0 = c->next_id;
+    uint64_t id_span = ntris;               // ids this draw consumes
+    uint32_t share_slots = 0;               // shard in processing-order space: slots of this rank
+    bool shard_order = false;
+    if (shard_n > 1) {
+        if (shard_r >= shard_n) return fail(c, TRB_E_ARG, "draw_shard: rank outside the shard count");
+        id_span = mesh_tris;
+        c->foreign_ids = true;
+        if (m.perm) {
+            // blocks b = shard_r (mod shard_n) of 2^SHARD_SHIFT positions of the mesh's processing order
+            const uint64_t B = 1ull << SHARD_SHIFT, nblocks = (mesh_tris + B - 1) / B;
+            const uint64_t mine = nblocks > shard_r ? (nblocks - shard_r + shard_n - 1) / shard_n : 0;
+            uint64_t slots = mine * B;
+            if (mine && (nblocks - 1) % shard_n == shard_r) slots -= nblocks * B - mesh_tris;   // the last block is partial
+            share_slots = (uint32_t)slots;
+            shard_order = true;
+            first_tri = 0;
+            ntris = slots;
+        } else {
+            // small mesh (no processing order): a contiguous range of the index buffer
+            const uint64_t base = mesh_tris / shard_n, rem = mesh_tris % shard_n;
+            first_tri = shard_r * base + std::min<uint64_t>(shard_r, rem);
+            ntris = base + (shard_r < rem ? 1 : 0);
+            c->next_id = id_base0 + first_tri;
+        }
+    }
     {   // no wrap-around: both values end up below the mesh's 0xFFFFFFF0 triangle limit
-        const uint64_t mt = m.nidx / 3;
+        const uint64_t mt = mesh_tris;
         if (first_tri > mt || ntris > mt - first_tri) return fail(c, TRB_E_ARG, "draw: triangle range");
     }
-    if (c->next_id + ntris >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "draw: triangle id space exhausted");
+    if (id_base0 + id_span >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "draw: triangle id space exhausted");
     int rc = check_device(c);
     if (rc) return rc;
     const int nv = c->frame.nviews;
     c->tris_submitted += ntris;
-    if (ntris == 0) return TRB_OK;
+    if (ntris == 0) {
+        c->next_id = id_base0 + id_span;
+        return TRB_OK;
+    }
     const void* dun = nullptr;
     rc = resolve_uniforms(c, kind, uniforms, ubytes, nv, &dun);
     if (rc) return rc;
@@ -1302,10 +1341,15 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
     g.id_base = (uint32_t)c->next_id;
     g.vrec = vrec;
     // the mesh's processing order, unless the range is a small part of the mesh (the draw visits every slot of the mesh)
-    const bool ordered = m.perm && ntris * 16 >= m.nidx / 3;
+    const bool ordered = shard_order || (m.perm && ntris * 16 >= mesh_tris);
     g.perm = ordered ? m.perm : nullptr;
     g.idx_perm = ordered ? m.idx_perm : nullptr;
-    g.nslots = ordered ? (uint32_t)(m.nidx / 3) : g.ntris;
+    g.nslots = shard_order ? share_slots : ordered ? (uint32_t)mesh_tris : g.ntris;
+    g.shard_n = shard_order ? shard_n : 0u;
+    g.shard_r = shard_order ? shard_r : 0u;
+    g.shard_shift = SHARD_SHIFT;
+    g.nperm = (uint32_t)mesh_tris;
+    if (shard_order) g.ntris = (uint32_t)mesh_tris;   // every triangle of the order is "inside the range"; the slots pick the share
     rc = raster_draw(c, g);   // `hm`, `hl` are pageable: their copies were staged before cudaMemcpyAsync returned
     if (rc) return rc;
     DrawDev d{};
@@ -1324,8 +1368,27 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
     d.mesh_ntris = (uint32_t)(m.nidx / 3);
     d.mesh_id_base = (long long)g.id_base - (long long)g.first_tri;
     c->draws.push_back(d);
-    c->next_id += ntris;
+    c->next_id = id_base0 + id_span;
     return TRB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
+                   size_t ubytes, uint64_t first_tri, uint64_t ntris) {
+    HostSpan host_span_("trb_draw_batch");
+    return draw_mesh(c, mesh, mv, pr, kind, uniforms, ubytes, first_tri, ntris, 0, 0);
+}
+
+int trb_draw_shard(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
+                   size_t ubytes, int shard_rank, int shard_count) {
+    HostSpan host_span_("trb_draw_shard");
+    if (c && c->in_frame && c->frame.nviews != 1) return fail(c, TRB_E_ARG, "draw_shard: needs a single-view frame");
+    if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return fail(c, TRB_E_ARG, "draw_shard: bad rank / count");
+    if (c && mesh != 0 && mesh <= c->meshes.size() && c->meshes[mesh - 1].alive && shard_count == 1)
+        return draw_mesh(c, mesh, mv, pr, kind, uniforms, ubytes, 0, c->meshes[mesh - 1].nidx / 3, 0, 0);
+    return draw_mesh(c, mesh, mv, pr, kind, uniforms, ubytes, 0, 0, (uint32_t)shard_count, (uint32_t)shard_rank);
 }
 
 int trb_draw(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
@@ -1383,6 +1446,9 @@ int trb_submit_clip_triangles(TrbCtx* c, const double* clip12, const double* var
     g.perm = nullptr;
     g.idx_perm = nullptr;
     g.nslots = g.ntris;
+    g.shard_n = g.shard_r = 0;
+    g.shard_shift = 0;
+    g.nperm = 0;
     rc = raster_draw(c, g);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));  // caller may reuse clip12 / varyings / hm
@@ -2061,6 +2127,7 @@ int trb_ipc_open_peers(TrbCtx* c, const void* key_handles, const void* vis_handl
     const cudaIpcMemHandle_t* kh = (const cudaIpcMemHandle_t*)key_handles;
     const cudaIpcMemHandle_t* vh = (const cudaIpcMemHandle_t*)vis_handles;
     for (int r = 0; r < n; ++r) {
+        c->peers.touched[r] = nullptr;
         if (r == my_rank) {
             c->peers.key[r] = c->frame.zkey;
             c->peers.vis[r] = c->frame.vis;
@@ -2085,6 +2152,7 @@ int trb_open_peers_raw(TrbCtx* c, const uint64_t* key_ptrs, const uint64_t* vis_
     for (int r = 0; r < n; ++r) {
         c->peers.key[r] = (const unsigned long long*)(uintptr_t)key_ptrs[r];
         c->peers.vis[r] = (const uint32_t*)(uintptr_t)vis_ptrs[r];
+        c->peers.touched[r] = nullptr;
     }
     c->peers.n = n;
     c->peer_rank = my_rank;
@@ -2121,13 +2189,31 @@ int trb_comm_close(TrbCtx* c) {
     c->host_total[8] = 0;
     return TRB_OK;
 }
+// the rank's "touched" map lives in the same exported 2 MB block as its counters, 4 KB in: one byte per COMPOSITE_CHUNK
+// pixels (nullptr when the frame is too large for the block: the composite then reads every rank's keys)
+constexpr size_t COMM_BLOCK_BYTES = (size_t)2 << 20, COMM_TOUCHED_OFFSET = 4096;
+static const uint8_t* comm_touched_map(const CommFlags* flags, unsigned long long npix) {
+    const unsigned long long chunks = (npix + COMPOSITE_CHUNK - 1) / COMPOSITE_CHUNK;
+    if (!flags || chunks > COMM_BLOCK_BYTES - COMM_TOUCHED_OFFSET) return nullptr;
+    return reinterpret_cast<const uint8_t*>(flags) + COMM_TOUCHED_OFFSET;
+}
+// mark the chunks of the local key plane this rank drew into (queued behind its draws, in front of "drawn")
+static int comm_mark_touched(TrbCtx* c) {
+    uint8_t* map = const_cast<uint8_t*>(comm_touched_map(c->comm.my_flags, c->frame.npix));
+    if (!map) return TRB_OK;
+    const unsigned long long chunks = (c->frame.npix + COMPOSITE_CHUNK - 1) / COMPOSITE_CHUNK;
+    Launch L(c, "k_chunk_touched");
+    k_chunk_touched<<<(unsigned)((chunks + TPB / 32 - 1) / (TPB / 32)), TPB, 0, c->stream>>>(c->frame.zkey, c->frame.npix, map);
+    CU(cudaGetLastError());
+    return TRB_OK;
+}
 static int comm_prepare(TrbCtx* c, int n, int rank) {
     if (!c->in_frame || c->frame.nviews != 1) return fail(c, TRB_E_COMM, "composite group: begin a single-view frame of the final size first");
     int rc = check_device(c);
     if (rc) return rc;
     trb_comm_close(c);
     TrbCtx::Comm& m = c->comm;
-    CU(cudaMalloc((void**)&m.my_flags, (size_t)2 << 20));           // its own block: the IPC handle exports nothing else
+    CU(cudaMalloc((void**)&m.my_flags, COMM_BLOCK_BYTES));           // its own block: the IPC handle exports nothing else
     CU(cudaMemsetAsync(m.my_flags, 0, sizeof(CommFlags), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     m.n = n;
@@ -2138,6 +2224,7 @@ static int comm_prepare(TrbCtx* c, int n, int rank) {
     m.peer_flags[rank] = m.my_flags;
     c->peers.key[rank] = c->frame.zkey;
     c->peers.vis[rank] = c->frame.vis;
+    c->peers.touched[rank] = comm_touched_map(m.my_flags, c->frame.npix);
     c->peers.n = n;
     c->peer_rank = rank;
     return TRB_OK;
@@ -2171,6 +2258,7 @@ int trb_comm_init(TrbCtx* const* ctxs, int n) {
             }
             c->peers.key[j] = ctxs[j]->frame.zkey;
             c->peers.vis[j] = ctxs[j]->frame.vis;
+            c->peers.touched[j] = comm_touched_map(ctxs[j]->comm.my_flags, ctxs[j]->frame.npix);
             c->comm.peer_flags[j] = ctxs[j]->comm.my_flags;
         }
         if (one_device_twice) {     // a waiting kernel could starve the peer it waits for on the same device: events instead
@@ -2223,6 +2311,7 @@ int trb_comm_open(TrbCtx* c, const void* blobs, int n, int rank) {
         if (r == rank) {
             c->peers.key[r] = c->frame.zkey;
             c->peers.vis[r] = c->frame.vis;
+            c->peers.touched[r] = comm_touched_map(mine, c->frame.npix);
             m.peer_flags[r] = mine;
             continue;
         }
@@ -2233,6 +2322,7 @@ int trb_comm_open(TrbCtx* c, const void* blobs, int n, int rank) {
         m.opened[3 * r] = pk; m.opened[3 * r + 1] = pv; m.opened[3 * r + 2] = pf;
         c->peers.key[r] = (const unsigned long long*)pk;
         c->peers.vis[r] = (const uint32_t*)pv;
+        c->peers.touched[r] = comm_touched_map((const CommFlags*)pf, c->frame.npix);
         m.peer_flags[r] = (const CommFlags*)pf;
     }
     c->peers.n = n;
@@ -2261,6 +2351,8 @@ int trb_composite(TrbCtx* c) {
     if (rc) return rc;
     TrbCtx::Comm& m = c->comm;
     ++m.seq;
+    rc = comm_mark_touched(c);
+    if (rc) return rc;
     {
         Launch L(c, "k_comm_publish");
         k_comm_publish<<<1, 1, 0, c->stream>>>(&m.my_flags->drawn, m.seq);
@@ -2291,6 +2383,8 @@ int trb_composite_group(TrbCtx* const* ctxs, int n) {
         TrbCtx* c = ctxs[i];
         CU(cudaSetDevice(c->device));
         ++c->comm.seq;
+        int rc = comm_mark_touched(c);
+        if (rc) return rc;
         if (c->comm.ev_drawn) CU(cudaEventRecord(c->comm.ev_drawn, c->stream));
         else {
             Launch L(c, "k_comm_publish");

@@ -303,7 +303,7 @@ void gl_draw_model(const Model& model, const IShader& shader, TGAImage& framebuf
     const bool lit = d.kind == TRB_SHADER_PHONG || d.kind == TRB_SHADER_EYE;
     const size_t n = BS().size(), ntris = (size_t)model.nfaces();
     if (n > 1 && !B().views.empty()) throw std::runtime_error("tinyrenderder-b200: gl_draw_model inside gl_begin_views; use gl_draw_model_views");
-    // one GPU: the whole face loop is one draw.  Several GPUs: context k draws triangle range k of the model with GLOBAL
+    // one GPU: the whole face loop is one draw.  Several GPUs: context k draws share k of the model with GLOBAL
     // submission indices, so that gl_composite resolves depth ties exactly like one sequential loop would
     for (size_t k = 0; k < n; ++k) {
         Backend& b = BS()[k];
@@ -311,13 +311,14 @@ void gl_draw_model(const Model& model, const IShader& shader, TGAImage& framebuf
         TrbPhongUniforms u;
         fill_uniforms(d, u);
         u.diffuse = h.diffuse; u.normal = h.normal; u.specular = h.specular;
-        size_t first = 0, count = ntris;
-        if (n > 1) {
-            shard(ntris, k, n, first, count);
-            CK(trb_set_triangle_id_base(b.ctx, g_next_id + first));
-        }
         CK(trb_set_viewport(b.ctx, vp));
-        CK(trb_draw(b.ctx, h.mesh, mv, pr, d.kind, lit ? &u : nullptr, lit ? sizeof(u) : 0, first, count));
+        if (n > 1) {
+            // the backend deals the triangles out (trb_draw_shard); ids are g_next_id + face + 1 on every context
+            CK(trb_set_triangle_id_base(b.ctx, g_next_id));
+            CK(trb_draw_shard(b.ctx, h.mesh, mv, pr, d.kind, lit ? &u : nullptr, lit ? sizeof(u) : 0, (int)k, (int)n));
+        } else {
+            CK(trb_draw(b.ctx, h.mesh, mv, pr, d.kind, lit ? &u : nullptr, lit ? sizeof(u) : 0, 0, ntris));
+        }
     }
     g_next_id += ntris;
 }
