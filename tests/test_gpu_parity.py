@@ -208,6 +208,25 @@ def test_both_raster_kernels_match_oracle(cuda_api, port_api, monkeypatch, name,
     compare.assert_outputs_match(name, got, want)
 
 
+@pytest.mark.parametrize("env", [{"TRB_WARP_MAX": "8", "TRB_SPLIT_S": "32"},
+                                 {"TRB_WARP_MAX": "8", "TRB_SPLIT_S": "32", "TRB_SPLIT_CAP": "12"},
+                                 {"TRB_WARP_MAX": "64", "TRB_SPLIT_S": "64", "TRB_MESH_ORDER_MIN_TRIS": "1"},
+                                 {"TRB_WARP_MAX": "8", "TRB_SPLIT": "0"}])
+@pytest.mark.parametrize("name", ["k2", "k7b_small", "signed_zero_ties", "duplicate_triangles", "big_triangles", "queue_overflow",
+                                  "dense_tile", "soup_mesh_fp32", "orbit_small", "sub_range_draws", "indexed_duplicates",
+                                  "snapshot_restore_twice", "k5_far_near"])
+def test_split_bins_match_oracle(cuda_api, port_api, monkeypatch, name, env):
+    """bins longer than TRB_WARP_MAX are cut into slices of TRB_SPLIT_S triangles, one warp each; every slice starts from
+    an empty tile and the last one to finish folds the tile's slices into the frame.  Small values make almost every tile
+    take that path (and, with a 12-entry item list, spill most of them over to the CTA-per-tile kernel): the oracle's
+    bits and counters must come out, ties included."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run_case(cuda_api, name)
+    want = run_case(port_api, name)
+    compare.assert_outputs_match(name, got, want)
+
+
 LIT_CASES = ["head_small", "orbit_small", "shadow_small", "gouraud_small", "lit_clip_triangles"]
 
 
@@ -337,7 +356,8 @@ def checks_api(built):
 
 
 @pytest.mark.parametrize("env", [{}, {"TRB_WARP_MAX": "0"}, {"TRB_BIN_CAP": "16"}, {"TRB_SYNC_DRAWS": "1"},
-                                 {"TRB_MESH_ORDER_MIN_TRIS": "1"}, {"TRB_MESH_ORDER_MIN_TRIS": "1", "TRB_BIN_CAP": "16"}])
+                                 {"TRB_MESH_ORDER_MIN_TRIS": "1"}, {"TRB_MESH_ORDER_MIN_TRIS": "1", "TRB_BIN_CAP": "16"},
+                                 {"TRB_WARP_MAX": "8", "TRB_SPLIT_S": "32"}, {"TRB_WARP_MAX": "8", "TRB_SPLIT_S": "32", "TRB_SPLIT_CAP": "12"}])
 @pytest.mark.parametrize("name", ["k7b_small", "big_triangles", "dense_tile", "soup_mesh_fp32", "orbit_small",
                                   "snapshot_restore_twice", "shadow_small"])
 def test_kernels_hold_their_indexing_invariants(checks_api, port_api, monkeypatch, name, env):

@@ -499,6 +499,17 @@ struct DrawCtl {
     uint32_t longest;    // longest bin of the draw
     uint32_t total;      // R, the bin entries of the draw
     uint32_t overflow;   // R does not fit the bin buffer: the unbinned kernels take the draw instead
+    uint32_t split_n;    // slices of long bins handed to the split flavour of k_raster_warp (may overshoot its capacity)
+};
+// Long bins are cut into slices of split_s triangles, one warp each (k_raster_warp<.., true>): a bin of 8000 sub-pixel
+// triangles on the silhouette of the config-4 sphere would otherwise keep ONE warp busy for 250 batches while the rest
+// of the GPU has long finished.  The slices of a tile are consecutive entries of the item list.
+struct SplitArgs {
+    uint2* items;                 // [cap] {tile slot, slice | slices << 16}; tile slot 0xffffffff: not used
+    uint32_t* done;               // [tile slots] slices of the tile that have delivered (zeroed per draw)
+    unsigned long long* keys;     // [cap][256] the slices' private tiles
+    uint32_t* ids;                // [cap][256]
+    uint32_t cap, split_s;
 };
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sh, uint32_t& total) {
@@ -527,7 +538,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 
 __global__ void __launch_bounds__(TPB) k_scan_partial(const uint32_t* __restrict__ in, uint32_t n,
                                                       uint32_t* __restrict__ block_sum, DrawCtl* __restrict__ ctl,
-                                                      uint32_t warp_max, uint32_t* __restrict__ heavy_list) {
+                                                      uint32_t warp_max, uint32_t* __restrict__ heavy_list, SplitArgs sp) {
     __shared__ unsigned long long sh[TPB / 32];
     size_t base = (size_t)blockIdx.x * SCAN_BLOCK;
     unsigned long long s = 0;
@@ -538,7 +549,19 @@ __global__ void __launch_bounds__(TPB) k_scan_partial(const uint32_t* __restrict
             const uint32_t v = in[e];
             s += v;
             m = max(m, v);
-            if (v > warp_max) heavy_list[atomicAdd(&ctl->heavy_n, 1u)] = (uint32_t)e;   // rare: a CTA's worth of work each
+            if (v > warp_max) {
+                // long bin: slices for the split warp kernel while its item list has room, else the CTA-per-tile kernel
+                // (split_n counts what the draw asks for even while the list has no room: the host sizes the next one from it)
+                const uint32_t K = (v + sp.split_s - 1) / sp.split_s;
+                bool split = K <= 0xffffu;
+                if (split) {
+                    const uint32_t b = atomicAdd(&ctl->split_n, K);
+                    split = b + K <= sp.cap && b + K >= b;
+                    for (uint32_t j = 0; j < K && b + j < sp.cap && b + j >= b; ++j)
+                        sp.items[b + j] = split ? make_uint2((uint32_t)e, j | (K << 16)) : make_uint2(0xffffffffu, 0u);
+                }
+                if (!split) heavy_list[atomicAdd(&ctl->heavy_n, 1u)] = (uint32_t)e;
+            }
         }
     }
     s = block_reduce_sum(s, sh);
@@ -582,6 +605,7 @@ __global__ void __launch_bounds__(TPB) k_scan_final(const uint32_t* __restrict__
         host_out[0] = wide > 0xffffffffull ? 0xffffffffu : (uint32_t)wide;
         host_out[1] = ctl->longest;
         host_out[2] = ctl->overflow;
+        host_out[3] = ctl->split_n;      // slices the draw asked for: the host sizes the next draw's item list from it
     }
 }
 
@@ -1067,19 +1091,44 @@ struct TileMaps {           // tensor maps of the frame's two planes, passed by 
 
 // MINB = resident CTAs per SM the register allocation aims for.  TRB_RW_BLOCKS picks the instantiation at run time.
 constexpr int RW_BLOCKS_DEFAULT = 6;
-template <int MINB>
+// SPLIT = false: warp w of CTA (x, view) takes tile x * RW_WARPS + w when its bin holds 1..warp_max triangles, starts from
+//   the tile's current contents and writes the tile back.
+// SPLIT = true: a warp takes ONE SLICE of a long bin (SplitArgs), starts from an empty tile and delivers its private
+//   (key, id) tile to scratch memory; the warp that delivers the last slice of a tile folds all of them into the frame -
+//   the lexicographic (depth, id) minimum over the old contents and every slice, i.e. exactly what one warp walking the
+//   whole bin would have left.
+constexpr unsigned long long KEY_EMPTY = ~0ull;   // above every key a fragment or a cleared pixel can have
+template <int MINB, bool SPLIT>
 __global__ void __launch_bounds__(RW_WARPS * 32, MINB * (4 / RW_WARPS > 0 ? 4 / RW_WARPS : 1))
-k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, const int use_tma) {
+k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, const int use_tma_, SplitArgs sp) {
     __shared__ __align__(128) WarpTile tiles[RW_WARPS];
     __shared__ __align__(8) unsigned long long tile_bar[RW_WARPS];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = RW_WARPS > 1 ? (int)(threadIdx.x >> 5) : 0;
-    const int tile = blockIdx.x * RW_WARPS + warp, view = blockIdx.y;
-    if (tile >= f.ntiles) return;
-    const size_t tslot = (size_t)view * f.ntiles + tile;
-    const uint32_t n = __ldg(a.counts + tslot);
-    if (n == 0 || n > a.warp_max || a.ctl->overflow) return;
-    const uint32_t off = __ldg(a.offsets + tslot);
+    const int use_tma = SPLIT ? 0 : use_tma_;
+    int tile, view;
+    size_t tslot;
+    uint32_t n, off, item = 0, slice = 0, nslices = 1;
+    if constexpr (!SPLIT) {
+        tile = blockIdx.x * RW_WARPS + warp; view = blockIdx.y;
+        if (tile >= f.ntiles) return;
+        tslot = (size_t)view * f.ntiles + tile;
+        n = __ldg(a.counts + tslot);
+        if (n == 0 || n > a.warp_max || a.ctl->overflow) return;
+        off = __ldg(a.offsets + tslot);
+    } else {
+        item = blockIdx.x * RW_WARPS + warp;
+        if (a.ctl->overflow || item >= min(a.ctl->split_n, sp.cap)) return;
+        const uint2 it = sp.items[item];
+        if (it.x == 0xffffffffu) return;                     // the tail of a bin that found no room in the list
+        tslot = it.x;
+        slice = it.y & 0xffffu; nslices = it.y >> 16;
+        tile = (int)(it.x % (uint32_t)f.ntiles); view = (int)(it.x / (uint32_t)f.ntiles);
+        const uint32_t nt = __ldg(a.counts + tslot);
+        TRB_CHECK(slice < nslices && (unsigned long long)slice * sp.split_s < nt);
+        off = __ldg(a.offsets + tslot) + slice * sp.split_s;
+        n = min(sp.split_s, nt - slice * sp.split_s);
+    }
     WarpTile& sm = tiles[warp];
     const int tx0 = (tile % f.tw) << TILE_SHIFT, ty0 = (tile / f.tw) << TILE_SHIFT;
     unsigned long long* gz = f.zkey + (size_t)view * f.npix;
@@ -1105,9 +1154,15 @@ k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, c
             const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
             const bool valid = x < f.W && y < f.H;
             const size_t gp = (size_t)y * f.W + x;
-            sm.zk[p] = valid ? gz[gp] : 0ull;          // key 0 never loses: pixels outside the frame stay untouched
-            sm.vid[p] = valid ? gv[gp] : VIS_NONE;
+            if constexpr (SPLIT) {
+                sm.zk[p] = valid ? KEY_EMPTY : 0ull;   // a slice starts from an empty tile
+                sm.vid[p] = VIS_NONE;
+            } else {
+                sm.zk[p] = valid ? gz[gp] : 0ull;      // key 0 never loses: pixels outside the frame stay untouched
+                sm.vid[p] = valid ? gv[gp] : VIS_NONE;
+            }
         }
+        if constexpr (SPLIT) __syncwarp();
     }
     bool tile_landed = !use_tma;
     uint32_t covered = 0, touched = 0;
@@ -1309,6 +1364,61 @@ k_raster_warp(FrameDev f, RasterArgs a, const __grid_constant__ TileMaps maps, c
     // A tile without a single covered sample is left alone; otherwise the whole tile is stored (no read-back of the
     // old values to find out what changed: the loads cost more than the stores of unchanged pixels save)
     covered = __reduce_add_sync(FULL, covered);
+    if constexpr (SPLIT) {
+        // deliver the private tile, then count this slice in; the last one to arrive folds the tile's slices into the frame
+        __syncwarp();
+        unsigned long long* sk = sp.keys + (size_t)item * (TILE * TILE);
+        uint32_t* si = sp.ids + (size_t)item * (TILE * TILE);
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = j * 32 + lane;
+            __stcg(sk + p, sm.zk[p]);
+            __stcg(si + p, sm.vid[p]);
+        }
+        __threadfence();
+        __syncwarp();
+        uint32_t arrived = 0;
+        if (lane == 0) {
+            arrived = atomicAdd(sp.done + tslot, 1u);
+            if (covered) atomicAdd(&f.stats[view].frag_covered, (unsigned long long)covered);
+        }
+        arrived = __shfl_sync(FULL, arrived, 0);
+        if (arrived != nslices - 1u) return;
+        __threadfence();
+        const size_t first_item = (size_t)(item - slice);
+        uint32_t changed = 0;
+        unsigned long long zmin = ~0ull;
+        #pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            const int p = j * 32 + lane, x = tx0 + (p & 15), y = ty0 + (p >> 4);
+            if (x >= f.W || y >= f.H) continue;
+            const size_t gp = (size_t)y * f.W + x;
+            const unsigned long long k_in = gz[gp];
+            const uint32_t id_in = gv[gp];
+            unsigned long long bk = k_in;
+            uint32_t bi = id_in;
+            for (uint32_t s = 0; s < nslices; ++s) {
+                const unsigned long long k = __ldcg(sp.keys + (first_item + s) * (TILE * TILE) + p);
+                if (k > bk) continue;
+                const uint32_t id = __ldcg(sp.ids + (first_item + s) * (TILE * TILE) + p);
+                if (k < bk) { bk = k; bi = id; }
+                else if (id < bi) bi = id;                 // ties: lowest id = first submitted
+            }
+            if (bk != k_in || bi != id_in) {
+                gz[gp] = bk;
+                gv[gp] = bi;
+                ++changed;
+                if (bk != k_in) zmin = min(zmin, bk);      // min_z of our_gl.cpp:197, as in raster_tile_cta
+            }
+        }
+        changed = __reduce_add_sync(FULL, changed);
+        for (int o = 16; o; o >>= 1) zmin = min(zmin, __shfl_xor_sync(FULL, zmin, o));
+        if (lane == 0 && changed) {
+            atomicAdd(&f.stats[view].touched, (unsigned long long)changed);
+            atomicMin(&f.stats[view].zmin_key, zmin);
+        }
+        return;
+    }
     if (covered == 0) return;
     touched = __reduce_add_sync(FULL, touched);
     if (touched) {

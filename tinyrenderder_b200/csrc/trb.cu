@@ -268,6 +268,13 @@ struct TrbCtx {
     DrawCtl* ctl_p = nullptr;
     uint32_t *direct_n_p = nullptr, *counts_p = nullptr, *cursor_p = nullptr;
     DevBuf heavy_list;               // tile slots of the draw's long bins
+    // long bins cut into slices for the split flavour of k_raster_warp (kernels.cuh SplitArgs)
+    DevBuf split_items, split_keys, split_ids;
+    uint32_t* split_done_p = nullptr;   // per tile slot, inside the zeroed block
+    bool split_on = true;               // TRB_SPLIT=0: long bins go to the CTA-per-tile kernel
+    uint32_t split_s = 256;             // triangles per slice (TRB_SPLIT_S)
+    uint32_t split_cap_fixed = 0;       // TRB_SPLIT_CAP: fixed capacity of the item list (tests force the spill-over with it)
+    uint32_t split_hint = 0;            // slices recent draws asked for (+ 25 %)
     DevBuf direct_list;              // direct path: triangles that may own a pixel, per view
     DevBuf rle_work, rle_src, rle_out; // device-side TGA RLE encoder (tga_rle.cuh)
     bool sync_draws = false;         // TRB_SYNC_DRAWS=1: size the bins exactly (one stream sync per draw)
@@ -345,6 +352,7 @@ struct TrbCtx {
     // indexed meshes of at least this many triangles get a processing order at upload (TRB_MESH_ORDER_MIN_TRIS; 0 = never).
     // Default: from 2 M triangles up - below that the vertex records of a draw (32 B each) sit in the 126 MB L2 anyway.
     uint64_t order_min_tris = 2ull << 20;
+    uint32_t shard_shift = 12;  // trb_draw_shard deals the processing order out in blocks of 2^shard_shift triangles (TRB_SHARD_SHIFT)
 };
 
 namespace {
@@ -527,13 +535,13 @@ int do_flush(TrbCtx* c) {
     return TRB_OK;
 }
 
-int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t bin_capacity) {
+int exclusive_scan(TrbCtx* c, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t bin_capacity, const SplitArgs& sp) {
     uint32_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     CU(c->scan_sums.ensure((size_t)nblocks * 4, c->stream));
     {
         Launch L(c, "k_scan_partial");
         k_scan_partial<<<nblocks, TPB, 0, c->stream>>>(in, n, c->scan_sums.as<uint32_t>(), c->ctl_p, c->warp_max,
-                                                       c->heavy_list.as<uint32_t>());
+                                                       c->heavy_list.as<uint32_t>(), sp);
     }
     {
         Launch L(c, "k_scan_final");
@@ -612,7 +620,8 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     CU(c->heavy_list.ensure(nslots * 4, c->stream));
     {
         const size_t o_dn = 256, o_counts = o_dn + (((size_t)f.nviews * 4 + 255) & ~(size_t)255),
-                     o_cursor = o_counts + ((nslots * 4 + 255) & ~(size_t)255), bytes = o_cursor + nslots * 4;
+                     o_cursor = o_counts + ((nslots * 4 + 255) & ~(size_t)255),
+                     o_done = o_cursor + ((nslots * 4 + 255) & ~(size_t)255), bytes = o_done + nslots * 4;
         static_assert(sizeof(DrawCtl) <= 256, "DrawCtl sits in the first 256 bytes of the zeroed block");
         CU(c->drawzero.ensure(bytes, c->stream));
         char* z = c->drawzero.as<char>();
@@ -620,6 +629,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         c->direct_n_p = reinterpret_cast<uint32_t*>(z + o_dn);
         c->counts_p = reinterpret_cast<uint32_t*>(z + o_counts);
         c->cursor_p = reinterpret_cast<uint32_t*>(z + o_cursor);
+        c->split_done_p = reinterpret_cast<uint32_t*>(z + o_done);
         CU(cudaMemsetAsync(z, 0, bytes, c->stream));
     }
     if (c->direct_area > 0) CU(c->direct_list.ensure((size_t)f.nviews * ndslots * 4, c->stream));
@@ -646,7 +656,27 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         k_direct_resolve<<<tgrid, TPB, 0, c->stream>>>(f, g, c->direct_list.as<uint32_t>(), c->direct_n_p);
     }
     CU(cudaGetLastError());
-    int rc = exclusive_scan(c, c->counts_p, (uint32_t)nslots, c->offsets.as<uint32_t>(), capacity);
+    // item list of the split warp kernel: sized from what recent draws asked for (never waited for); a draw that needs
+    // more sends the bins that do not fit to the CTA-per-tile kernel
+    // (the kernel is only launched once a draw of this context has had long bins: config 3 never pays for it)
+    SplitArgs sp{};
+    sp.split_s = c->split_s;
+    if (c->split_on && c->warp_max > 0 && c->host_total[3])
+        c->split_hint = std::max<uint32_t>(c->split_hint, (uint32_t)std::min<uint64_t>((uint64_t)c->host_total[3] + c->host_total[3] / 4 + 256, 1u << 20));
+    if (c->split_on && c->warp_max > 0 && (c->split_hint || c->split_cap_fixed)) {
+        uint32_t cap = std::min<uint32_t>(std::max<uint32_t>(c->split_hint, 4096u), 65536u);
+        if (c->split_cap_fixed) cap = c->split_cap_fixed;
+        cap = (cap + RW_WARPS - 1) / RW_WARPS * RW_WARPS;
+        CU(c->split_items.ensure((size_t)cap * sizeof(uint2), c->stream));
+        CU(c->split_keys.ensure((size_t)cap * TILE * TILE * 8, c->stream));
+        CU(c->split_ids.ensure((size_t)cap * TILE * TILE * 4, c->stream));
+        sp.items = c->split_items.as<uint2>();
+        sp.done = c->split_done_p;
+        sp.keys = c->split_keys.as<unsigned long long>();
+        sp.ids = c->split_ids.as<uint32_t>();
+        sp.cap = cap;
+    }
+    int rc = exclusive_scan(c, c->counts_p, (uint32_t)nslots, c->offsets.as<uint32_t>(), capacity, sp);
     if (rc) return rc;
     bool long_bins = true;             // unknown without a round trip: k_raster's persistent grid finds an empty list
     if (c->sync_draws) {
@@ -683,10 +713,14 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         const dim3 grid((f.ntiles + RW_WARPS - 1) / RW_WARPS, f.nviews);
         const int tma = tile_maps_for(c) ? 1 : 0;
         switch (c->rw_blocks) {
-            case 8: k_raster_warp<8><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, tma); break;
-            case 7: k_raster_warp<7><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, tma); break;
-            default: k_raster_warp<6><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, tma); break;
+            case 8: k_raster_warp<8, false><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, tma, sp); break;
+            case 7: k_raster_warp<7, false><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, tma, sp); break;
+            default: k_raster_warp<6, false><<<grid, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, tma, sp); break;
         }
+    }
+    if (sp.cap) {            // slices of the longer bins: one warp each, the last one of a tile folds them into the frame
+        Launch L(c, "k_raster_split");
+        k_raster_warp<6, true><<<sp.cap / RW_WARPS, RW_WARPS * 32, 0, c->stream>>>(f, ra, c->tile_maps, 0, sp);
     }
     if (long_bins) {         // longer bins: one CTA per tile, persistent grid over the device-side list
         // asynchronous draws: the full persistent grid, because it may have to carry the unbinned depth pass
@@ -867,6 +901,10 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_TMA")) c->use_tma = atoi(e) != 0;
     if (const char* e = getenv("TRB_SYNC_DRAWS")) c->sync_draws = atoi(e) != 0;
     if (const char* e = getenv("TRB_BIN_CAP")) c->bin_cap_fixed = (uint32_t)std::max(1, atoi(e));
+    if (const char* e = getenv("TRB_SPLIT")) c->split_on = atoi(e) != 0;
+    if (const char* e = getenv("TRB_SPLIT_S")) c->split_s = (uint32_t)std::min(65535, std::max(32, atoi(e)));
+    if (const char* e = getenv("TRB_SPLIT_CAP")) c->split_cap_fixed = (uint32_t)std::max(1, atoi(e));
+    if (const char* e = getenv("TRB_SHARD_SHIFT")) c->shard_shift = (uint32_t)std::min(24, std::max(5, atoi(e)));
     if (const char* e = getenv("TRB_MESH_ORDER_MIN_TRIS")) c->order_min_tris = (uint64_t)std::max(0ll, atoll(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -879,9 +917,10 @@ int trb_create(int device, TrbCtx** out) {
     }
     memset(c->host_total, 0, 64);
     // 9 CTAs x 24 KB of per-warp tiles per SM: ask for the large shared-memory carveout
-    cudaFuncSetAttribute(k_raster_warp<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_raster_warp<7>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_raster_warp<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_raster_warp<6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_raster_warp<7, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_raster_warp<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_raster_warp<6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = c;
     return TRB_OK;
 }
@@ -902,7 +941,7 @@ int trb_destroy(TrbCtx* c) {
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
     DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
-                      &c->drawzero, &c->offsets, &c->bins, &c->scan_sums, &c->scan_total, &c->heavy_list, &c->direct_list, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
+                      &c->drawzero, &c->offsets, &c->bins, &c->scan_sums, &c->scan_total, &c->heavy_list, &c->split_items, &c->split_keys, &c->split_ids, &c->direct_list, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->shadow_maps) b.keys.release();
@@ -1244,7 +1283,6 @@ int trb_set_viewport(TrbCtx* c, const double* v) {
 }  // extern "C"
 
 namespace {
-constexpr uint32_t SHARD_SHIFT = 12;    // trb_draw_shard deals the processing order out in blocks of 4096 triangles
 
 // One mesh draw.  shard_n <= 1: the triangle range [first_tri, first_tri + ntris) of the index buffer.
 // shard_n > 1 (trb_draw_shard): rank shard_r's share of the WHOLE mesh - first_tri / ntris are ignored.
@@ -1266,7 +1304,7 @@ int draw_mesh(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int k
         c->foreign_ids = true;
         if (m.perm) {
             // blocks b = shard_r (mod shard_n) of 2^SHARD_SHIFT positions of the mesh's processing order
-            const uint64_t B = 1ull << SHARD_SHIFT, nblocks = (mesh_tris + B - 1) / B;
+            const uint64_t B = 1ull << c->shard_shift, nblocks = (mesh_tris + B - 1) / B;
             const uint64_t mine = nblocks > shard_r ? (nblocks - shard_r + shard_n - 1) / shard_n : 0;
             uint64_t slots = mine * B;
             if (mine && (nblocks - 1) % shard_n == shard_r) slots -= nblocks * B - mesh_tris;   // the last block is partial
@@ -1347,7 +1385,7 @@ int draw_mesh(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int k
     g.nslots = shard_order ? share_slots : ordered ? (uint32_t)mesh_tris : g.ntris;
     g.shard_n = shard_order ? shard_n : 0u;
     g.shard_r = shard_order ? shard_r : 0u;
-    g.shard_shift = SHARD_SHIFT;
+    g.shard_shift = c->shard_shift;
     g.nperm = (uint32_t)mesh_tris;
     if (shard_order) g.ntris = (uint32_t)mesh_tris;   // every triangle of the order is "inside the range"; the slots pick the share
     rc = raster_draw(c, g);   // `hm`, `hl` are pageable: their copies were staged before cudaMemcpyAsync returned
