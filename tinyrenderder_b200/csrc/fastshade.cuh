@@ -40,20 +40,53 @@ __device__ __forceinline__ F3 mul_m34f(const float* M, F3 v, float w) {
               __fmaf_rn(M[11], w, __fmaf_rn(M[10], v.z, __fmaf_rn(M[9], v.y, M[8] * v.x)))};
 }
 
-struct LitF {               // fp32 copies of what the lighting reads (built on the host per draw and view)
+struct alignas(16) LitF {   // what the fp32 lit pixel reads, per draw and view (built on the host): eight 16-byte loads
     float mv[12];           // ModelView rows 0..2
     F3 key, fill, rim;
     float normal_map_strength;
+    uint32_t dbpp, nbpp;    // bytes per texel of the diffuse / normal map (0: map absent)
+    uint32_t dw, dh, nw, nh;
+    const uint8_t* diffuse; // TGAImage order, BGR(A) or grey
+    const uint8_t* normal;
 };
+static_assert(sizeof(LitF) == 128, "LitF is loaded as eight float4");
+// the block is read in 16-byte pieces where they are needed (all eight at once would cost 32 registers)
+__device__ __forceinline__ float4 litf_q(const LitF* p, int i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
+struct LitTex {             // pieces 5 (second half) .. 7: what the texel fetch needs
+    uint32_t dbpp, nbpp, dw, dh, nw, nh;
+    const uint8_t *diffuse, *normal;
+};
+__device__ __forceinline__ LitTex load_lit_tex(const LitF* p) {
+    const float4 a = litf_q(p, 5), b = litf_q(p, 6), c = litf_q(p, 7);
+    LitTex t;
+    t.dbpp = __float_as_uint(a.z); t.nbpp = __float_as_uint(a.w);
+    t.dw = __float_as_uint(b.x); t.dh = __float_as_uint(b.y); t.nw = __float_as_uint(b.z); t.nh = __float_as_uint(b.w);
+    t.diffuse = reinterpret_cast<const uint8_t*>(((unsigned long long)__float_as_uint(c.y) << 32) | __float_as_uint(c.x));
+    t.normal = reinterpret_cast<const uint8_t*>(((unsigned long long)__float_as_uint(c.w) << 32) | __float_as_uint(c.z));
+    return t;
+}
 
 // One lit pixel.  attr = the three vertices' raw attributes (pos, nrm, uv as uploaded); pc = the
-// perspective-correct barycentrics (fp64, exact); base / nrm_texel / spec_c0 = the texels already
-// fetched at the exact fp64 texture coordinates (nrm_texel < 0: no normal map).  sf = shadow factor.
+// perspective-correct barycentrics (fp64, exact); base / nmc = the texels already fetched at the exact fp64
+// texture coordinates.  sf = shadow factor.
 // The vertex stage is linear, so the attributes are interpolated first and transformed once:
-// ModelView * (sum b_k p_k, 1) == sum b_k (ModelView * (p_k, 1)) because the weights sum to one.
-__device__ __forceinline__ void shade_lit_f32(bool eye, const LitF& L, const float (*attr)[8], const double pc[3],
-                                              const int base[4], bool has_nm, const int nmc[4], float spec_f, float sf,
+// ModelView * (sum b_k p_k, 1) == sum b_k (ModelView * (p_k, 1)) because the weights sum to one; for the same
+// reason the blend of main.cpp:121-125, g_eye * (1 - s) + (ModelView * nm) * s, is ModelView * (g * (1 - s) + nm * s).
+// The specular MAP does not enter: Model::specular returns c[0] / 255.0f <= 1 (model.cpp:448-458), so
+// std::max(1.0, specular) at main.cpp:107 / 246 is exactly 1.0 whatever the texel - the exponent is 1 (Phong) or
+// 8 (eyes), and the eye-pixel test's `specular_power <= 5` (main.cpp:111) always holds.
+__device__ __forceinline__ void shade_lit_f32(bool eye, const LitF* Lp, const float (*attr)[8], const double pc[3],
+                                              const int base[3], bool has_nm, const int nmc[3], float sf,
                                               uint8_t out[3]) {
+    struct { float mv[12]; F3 key, fill, rim; float normal_map_strength; } L;
+    {
+        const float4 q0 = litf_q(Lp, 0), q1 = litf_q(Lp, 1), q2 = litf_q(Lp, 2), q3 = litf_q(Lp, 3), q4 = litf_q(Lp, 4);
+        const float4 q5 = litf_q(Lp, 5);
+        L.mv[0] = q0.x; L.mv[1] = q0.y; L.mv[2] = q0.z; L.mv[3] = q0.w; L.mv[4] = q1.x; L.mv[5] = q1.y; L.mv[6] = q1.z; L.mv[7] = q1.w;
+        L.mv[8] = q2.x; L.mv[9] = q2.y; L.mv[10] = q2.z; L.mv[11] = q2.w;
+        L.key = F3{q3.x, q3.y, q3.z}; L.fill = F3{q3.w, q4.x, q4.y}; L.rim = F3{q4.z, q4.w, q5.x};
+        L.normal_map_strength = q5.y;
+    }
     const float b0 = (float)pc[0], b1 = (float)pc[1], b2 = (float)pc[2];
     F3 p, g;
     p.x = __fmaf_rn(attr[2][0], b2, __fmaf_rn(attr[1][0], b1, attr[0][0] * b0));
@@ -63,43 +96,34 @@ __device__ __forceinline__ void shade_lit_f32(bool eye, const LitF& L, const flo
     g.y = __fmaf_rn(attr[2][4], b2, __fmaf_rn(attr[1][4], b1, attr[0][4] * b0));
     g.z = __fmaf_rn(attr[2][5], b2, __fmaf_rn(attr[1][5], b1, attr[0][5] * b0));
     const F3 pos = mul_m34f(L.mv, p, b0 + b1 + b2);            // position_eye
-    const F3 gn = mul_m34f(L.mv, g, 0.0f);                     // normal_eye (main.cpp:84: ModelView, w = 0)
     const F3 V = normalize3f(scale3f(pos, -1.0f));
     F3 N;
-    float diff, spec_pow, spec_gain;
+    float diff, spec_gain;
     if (!eye) {
-        spec_pow = fmaxf(1.0f, spec_f);                                         // main.cpp:107
-        const bool eye_px = (base[0] + base[1] + base[2] >= 651) && spec_pow <= 5.0f;  // sum/765.0 >= 0.85, main.cpp:110-111
-        if (eye_px) {
-            N = gn;                                                             // main.cpp:123 (not normalised)
-        } else {
-            F3 nm = F3{0.0f, 0.0f, 1.0f};                                       // model.cpp:429-431
-            if (has_nm) {
-                const float k = 2.0f / 255.0f;
-                nm = normalize3f(F3{__fmaf_rn((float)nmc[2], k, -1.0f), __fmaf_rn((float)nmc[1], k, -1.0f),
-                                    __fmaf_rn((float)nmc[0], k, -1.0f)});       // model.cpp:440-442
-            }
-            const F3 nme = mul_m34f(L.mv, nm, 0.0f);                            // main.cpp:116-119
-            const float s = L.normal_map_strength, s1 = 1.0f - s;
-            N = normalize3f(F3{__fmaf_rn(nme.x, s, gn.x * s1), __fmaf_rn(nme.y, s, gn.y * s1), __fmaf_rn(nme.z, s, gn.z * s1)});
+        const bool eye_px = base[0] + base[1] + base[2] >= 651;                 // sum/765.0 >= 0.85, main.cpp:110-111
+        F3 nm = F3{0.0f, 0.0f, 1.0f};                                           // model.cpp:429-431
+        if (has_nm) {
+            const float k = 2.0f / 255.0f;
+            nm = normalize3f(F3{__fmaf_rn((float)nmc[2], k, -1.0f), __fmaf_rn((float)nmc[1], k, -1.0f),
+                                __fmaf_rn((float)nmc[0], k, -1.0f)});           // model.cpp:440-442
         }
+        const float s = eye_px ? 0.0f : L.normal_map_strength, s1 = 1.0f - s;   // main.cpp:116-125
+        const F3 ne = mul_m34f(L.mv, F3{__fmaf_rn(nm.x, s, g.x * s1), __fmaf_rn(nm.y, s, g.y * s1), __fmaf_rn(nm.z, s, g.z * s1)}, 0.0f);
+        const float l2 = dot3f(ne, ne);
+        const float inv = (!eye_px && l2 >= 1.17549435e-38f) ? rsqrt_fast(l2) : 1.0f;   // main.cpp:123: eye pixels keep the raw normal
+        N = scale3f(ne, inv);
         diff = fmaxf(0.0f, dot3f(N, L.key)) + fmaxf(0.0f, dot3f(N, L.fill)) * 0.35f + fmaxf(0.0f, dot3f(N, L.rim)) * 0.6f;
         spec_gain = 0.35f;
     } else {
-        N = normalize3f(gn);                                                    // main.cpp:225-227
+        N = normalize3f(mul_m34f(L.mv, g, 0.0f));                               // main.cpp:225-227
         diff = fmaxf(0.0f, dot3f(N, L.key)) + fmaxf(0.0f, dot3f(N, L.rim)) * 0.6f;
-        spec_pow = fmaxf(1.0f, spec_f) * 8.0f;                                  // main.cpp:246
         spec_gain = 1.5f;
     }
     const float nl2 = 2.0f * dot3f(N, L.key);
     const F3 R = normalize3f(F3{__fmaf_rn(N.x, nl2, -L.key.x), __fmaf_rn(N.y, nl2, -L.key.y), __fmaf_rn(N.z, nl2, -L.key.z)});
     const float rv = fmaxf(0.0f, dot3f(R, V));
-    float spec = 0.0f;
-    if (rv > 0.0f) {
-        if (spec_pow == 1.0f) spec = rv;
-        else if (spec_pow == 8.0f) { const float r2 = rv * rv, r4 = r2 * r2; spec = r4 * r4; }
-        else spec = powf(rv, spec_pow);
-    }
+    float spec = rv;                                                            // pow(rv, 1.0), main.cpp:150-152
+    if (eye) { const float r2 = rv * rv, r4 = r2 * r2; spec = r4 * r4; }       // pow(rv, 8.0), main.cpp:246-250
     const float gain = 0.1f + diff * sf, add = 255.0f * (spec_gain * spec * sf);
     #pragma unroll
     for (int ch = 0; ch < 3; ++ch)

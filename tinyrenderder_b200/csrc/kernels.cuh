@@ -1480,34 +1480,39 @@ constexpr int SHADE_PX_PER_THREAD = 4;   // one 16-byte id load per thread: spar
 // PhongShader / EyeShader / shadow-mapped Phong for one pixel with fp32 lighting: `at` = the three vertices' raw
 // attributes, pc = the perspective-correct barycentrics (fp64, exact).  Texture coordinates, the texel choice and the
 // shadow test stay fp64 (fastshade.cuh explains why that keeps every channel within one code of the reference).
+// Everything the pixel reads about its draw comes from the draw's LitF block (eight 16-byte loads).
+__device__ __forceinline__ uint32_t texel_index32(uint32_t w, uint32_t h, double u, double v) {   // model.cpp:420-423
+    const int x = clamp_i(x86_int(u * (double)(int)w), 0, (int)w - 1);
+    const int y = clamp_i(x86_int(v * (double)(int)h), 0, (int)h - 1);
+    return (uint32_t)x + (uint32_t)y * w;          // < 2^32: upload_texture caps w, h at 65536 and w * h below 2^32
+}
+// TGAColor(p, bpp) (tgaimage.h:47-51): the first min(bpp, 3) bytes, the rest 0
+__device__ __forceinline__ void fetch3(const uint8_t* px, uint32_t ti, uint32_t bpp, int c[3]) {
+    const uint8_t* q = px + (size_t)ti * bpp;
+    c[0] = (int)__ldg(q);
+    c[1] = bpp > 1 ? (int)__ldg(q + 1) : 0;
+    c[2] = bpp > 2 ? (int)__ldg(q + 2) : 0;
+}
 template <bool C2>
-__device__ __forceinline__ void lit_fast_core(const DrawDev& D, int view, const LitUniforms& U, const trbf::LitF& LF,
-                                              const float (*at)[8], const double pc[3], uint8_t col[3]) {
+__device__ __forceinline__ void lit_fast(const DrawDev& D, int view, const float (*at)[8], const double pc[3], uint8_t col[3]) {
     const bool shadowed = C2 && D.kind == 4 /*SHADOW_PHONG*/;
+    const trbf::LitF* LP = reinterpret_cast<const trbf::LitF*>(D.litf) + view;
+    const trbf::LitTex LF = trbf::load_lit_tex(LP);
     const double tu = (double)at[0][6] * pc[0] + (double)at[1][6] * pc[1] + (double)at[2][6] * pc[2];  // main.cpp:100-101
     const double tv = (double)at[0][7] * pc[0] + (double)at[1][7] * pc[1] + (double)at[2][7] * pc[2];
-    // the three maps are sampled at the same (u, v): one texel index serves every map of the same size
-    int base[4] = {255, 255, 255, 255}, nmc[4] = {0, 0, 0, 0};
-    size_t ti = 0;
-    int tw = -1, th = -1;
-    auto index_in = [&](const TexView& t) -> size_t {
-        if (t.w != tw || t.h != th) { ti = texel_index(t, tu, tv); tw = t.w; th = t.h; }
-        return ti;
-    };
-    if (U.diffuse.px) {
-        const uint8_t* q = U.diffuse.px + index_in(U.diffuse) * U.diffuse.bpp;
-        #pragma unroll
-        for (int i = 0; i < 3; ++i) base[i] = i < U.diffuse.bpp ? (int)__ldg(q + i) : 0;
+    // the maps are sampled at the same (u, v): one texel index serves both when they have one size
+    int base[3] = {255, 255, 255}, nmc[3] = {0, 0, 0};
+    uint32_t ti = 0;
+    if (LF.dbpp) {
+        ti = texel_index32(LF.dw, LF.dh, tu, tv);
+        fetch3(LF.diffuse, ti, LF.dbpp, base);
     }
     const bool eye = D.kind == 2 /*EYE*/;
-    const bool has_nm = !eye && U.normal.px != nullptr;
+    const bool has_nm = !eye && LF.nbpp != 0;
     if (has_nm) {
-        const uint8_t* q = U.normal.px + index_in(U.normal) * U.normal.bpp;
-        #pragma unroll
-        for (int i = 0; i < 3; ++i) nmc[i] = i < U.normal.bpp ? (int)__ldg(q + i) : 0;
+        if (!LF.dbpp || LF.nw != LF.dw || LF.nh != LF.dh) ti = texel_index32(LF.nw, LF.nh, tu, tv);
+        fetch3(LF.normal, ti, LF.nbpp, nmc);
     }
-    float spec_f = 1.0f;
-    if (U.specular.px) spec_f = (float)__ldg(U.specular.px + index_in(U.specular) * U.specular.bpp) / 255.0f;
     float sf = 1.0f;
     if (shadowed) {
         const ShadowUniformsDev& SU = reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view];
@@ -1516,14 +1521,7 @@ __device__ __forceinline__ void lit_fast_core(const DrawDev& D, int view, const 
             light_clip_from_position(SU.shadow, (double)at[k][0], (double)at[k][1], (double)at[k][2], lc[k]);
         sf = (float)shadow_factor(SU.shadow, lc, pc);
     }
-    trbf::shade_lit_f32(eye, LF, at, pc, base, has_nm, nmc, spec_f, sf, col);
-}
-template <bool C2>
-__device__ __forceinline__ void lit_fast(const DrawDev& D, int view, const float (*at)[8], const double pc[3], uint8_t col[3]) {
-    const bool shadowed = C2 && D.kind == 4 /*SHADOW_PHONG*/;
-    const LitUniforms& U = shadowed ? reinterpret_cast<const ShadowUniformsDev*>(D.uniforms)[view].lit
-                                    : reinterpret_cast<const LitUniforms*>(D.uniforms)[view];
-    lit_fast_core<C2>(D, view, U, reinterpret_cast<const trbf::LitF*>(D.litf)[view], at, pc, col);
+    trbf::shade_lit_f32(eye, LP, at, pc, base, has_nm, nmc, sf, col);
 }
 
 // one visible pixel: p = x + y*W inside `view`, id = its winning triangle.  C2 = the frame has a
@@ -1531,14 +1529,20 @@ __device__ __forceinline__ void lit_fast(const DrawDev& D, int view, const float
 // carry their registers.
 template <bool C2, bool FAST>
 __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
-                                            const DrawDev* sm_draws, int view, unsigned long long p, uint32_t id) {
+                                            const DrawDev* sm_draws, int view, unsigned long long p, int x, int y, uint32_t id) {
     constexpr int MAX_SM_DRAWS = SHADE_MAX_SM_DRAWS;
     const size_t gp = (size_t)view * f.npix + p;
-    int lo = 0, hi = ndraws - 1;  // last draw with id_base < id
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        const uint32_t bse = mid < MAX_SM_DRAWS ? sm_draws[mid].id_base : draws[mid].id_base;
-        if (bse < id) lo = mid; else hi = mid - 1;
+    int lo = 0;                   // last draw with id_base < id (bases ascend)
+    if (ndraws <= 8) {            // a frame loop's handful of draws: count instead of bisecting
+        #pragma unroll 1
+        for (int d = 1; d < ndraws; ++d) lo += sm_draws[d].id_base < id ? 1 : 0;
+    } else {
+        int hi = ndraws - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            const uint32_t bse = mid < MAX_SM_DRAWS ? sm_draws[mid].id_base : draws[mid].id_base;
+            if (bse < id) lo = mid; else hi = mid - 1;
+        }
     }
     // the draw table sits in shared memory: one level less in the dependent chain id -> draw -> indices -> records -> texels
     DrawDev D = lo < MAX_SM_DRAWS ? sm_draws[lo] : draws[lo];
@@ -1562,8 +1566,6 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
     const VRec va = load_vrec(vr + i0), vb = load_vrec(vr + i1), vc = load_vrec(vr + i2);
     TriSetup ts;
     setup_known_triangle(va, vb, vc, ts);   // a recorded winner passed every reject: no tests, no bbox
-    const uint32_t yq = (uint32_t)p / (uint32_t)f.W;     // p < 2^32: a frame has fewer than 2^32 pixels
-    const int x = (int)((uint32_t)p - yq * (uint32_t)f.W), y = (int)yq;
     double b[3], z, pc[3];
     eval_known_sample(ts, x, y, b, z);          // a recorded winner is covered: same arithmetic, no coverage tests
     {
@@ -1694,9 +1696,7 @@ __global__ void __launch_bounds__(TPB) k_shade_collect(FrameDev f, int row0, int
 #define TRB_SHADE_DENSE_PX 8   // measured on config 3 (ms per step): 1 -> 1.975, 2 -> 1.81, 4 -> 1.70, 8 -> 1.665, 16 -> 1.654
 #endif
 constexpr int SHADE_DENSE_PX = TRB_SHADE_DENSE_PX;   // pixels per thread of k_shade_dense
-#ifndef TRB_SHADE_2D
-#define TRB_SHADE_2D 0   // measured on B200 (config 3): 8x4 warp footprints 1.18 ms vs 1.10 ms for 32 pixels of a row
-#endif
+// (8x4 pixel warp footprints instead of 32 pixels of a row were measured on config 3: 1.18 ms vs 1.10 ms - not kept)
 template <bool C2, bool FAST>
 __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(FrameDev f, const DrawDev* __restrict__ draws, int ndraws,
                                                      int row0, int row1) {
@@ -1704,17 +1704,6 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(Frame
     __shared__ DrawDev sm_draws[SHADE_MAX_SM_DRAWS];
     stage_draw_table(sm_draws, draws, ndraws);
     const int view = blockIdx.y;
-#if TRB_SHADE_2D
-    // a CTA shades a 32x8 pixel block, each warp an 8x4 footprint: the lanes of a warp then share far
-    // fewer winning triangles than 32 pixels of one row do, so their VRec / attribute / texel gathers
-    // fall into fewer distinct sectors
-    const int nbx = (f.W + 31) >> 5;
-    const int bx = (int)(blockIdx.x % (unsigned)nbx), by = (int)(blockIdx.x / (unsigned)nbx);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = (bx << 5) + ((warp & 3) << 3) + (lane & 7), y = row0 + (by << 3) + ((warp >> 2) << 2) + (lane >> 3);
-    if (x >= f.W || y >= row1) return;
-    const unsigned long long p = (unsigned long long)y * f.W + x;
-#else
     // SHADE_DENSE_PX pixels per thread, TPB apart: their ids are requested together, so the first (cold: the id plane was
     // just written by the raster pass and is larger than L2) load of all of them is one wait instead of one each
     const unsigned long long first = (unsigned long long)row0 * f.W, last = (unsigned long long)row1 * f.W;
@@ -1726,15 +1715,18 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(Frame
         const unsigned long long p = p0 + (unsigned long long)k * TPB;
         ids[k] = p < last ? vis[p] : VIS_NONE;
     }
+    // pixel coordinates by one division per thread, then TPB columns further per pixel
+    int y = (int)((uint32_t)p0 / (uint32_t)f.W);         // p < 2^32: a frame has fewer than 2^32 pixels
+    int x = (int)((uint32_t)p0 - (uint32_t)y * (uint32_t)f.W);
     #pragma unroll 1
-    for (int k = 0; k < SHADE_DENSE_PX; ++k) {
+    for (int k = 0; k < SHADE_DENSE_PX; ++k, x += TPB) {
+        while (x >= f.W) { x -= f.W; ++y; }
         const uint32_t id = ids[k];
         if (id == VIS_NONE || id == VIS_SHADED) continue;
         const unsigned long long p = p0 + (unsigned long long)k * TPB;
-        shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, p, id);
+        shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, p, x, y, id);
         vis[p] = VIS_SHADED;
     }
-#endif
 }
 
 // Sparse frames, pass 2: persistent grid-stride loop over the compacted list
@@ -1762,7 +1754,8 @@ __global__ void __launch_bounds__(TPB, 3) k_shade(FrameDev f, const DrawDev* __r
         #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             if (ps[k] == 0xffffffffu) break;
-            shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, ps[k], ids[k]);
+            const uint32_t yq = ps[k] / (uint32_t)f.W;
+            shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, ps[k], (int)(ps[k] - yq * (uint32_t)f.W), (int)yq, ids[k]);
             vis[ps[k]] = VIS_SHADED;
         }
     }
@@ -1836,7 +1829,8 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p
         for (unsigned m = holders; m; m &= m - 1u) bid = min(bid, peers.vis[__ffs(m) - 1][p]);
     f.zkey[p] = bk;
     if (bid == VIS_NONE || bid == VIS_SHADED) { f.vis[p] = bid; return; }
-    shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, 0, p, bid);
+    const uint32_t yq = (uint32_t)p / (uint32_t)f.W;
+    shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, 0, p, (int)((uint32_t)p - yq * (uint32_t)f.W), (int)yq, bid);
     f.vis[p] = VIS_SHADED;
 }
 

@@ -514,11 +514,7 @@ int do_flush(TrbCtx* c) {
             }
         }
         {   // dense views only
-#if TRB_SHADE_2D
-            const dim3 grid((unsigned)(((f.W + 31) / 32) * ((r1 - r0 + 7) / 8)), f.nviews);
-#else
             const dim3 grid((unsigned)((n + (unsigned long long)TPB * SHADE_DENSE_PX - 1) / ((unsigned long long)TPB * SHADE_DENSE_PX)), f.nviews);
-#endif
             Launch L(c, "k_shade_dense");
             switch (variant) {
                 case 0: k_shade_dense<false, false><<<grid, TPB, 0, c->stream>>>(f, table, nd, r0, r1); break;
@@ -1177,7 +1173,8 @@ int trb_free_mesh(TrbCtx* c, TrbMesh h) {
 
 int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, TrbTex* out) {
     HostSpan host_span_("trb_upload_texture");
-    if (!c || !texels || !out || w <= 0 || h <= 0 || (bpp != 1 && bpp != 3 && bpp != 4))
+    // 65535: the TGA header's 16-bit sizes (tgaimage.h); it also keeps every texel index below 2^32
+    if (!c || !texels || !out || w <= 0 || h <= 0 || w > 65535 || h > 65535 || (bpp != 1 && bpp != 3 && bpp != 4))
         return fail(c, TRB_E_ARG, "upload_texture: bad argument");
     int rc = check_device(c);
     if (rc) return rc;
@@ -1358,6 +1355,18 @@ int draw_mesh(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int k
             L.fill = trbf::F3{(float)u.fill_dir_eye[0], (float)u.fill_dir_eye[1], (float)u.fill_dir_eye[2]};
             L.rim = trbf::F3{(float)u.rim_dir_eye[0], (float)u.rim_dir_eye[1], (float)u.rim_dir_eye[2]};
             L.normal_map_strength = (float)u.normal_map_strength;
+            // the maps the lit pixel samples (handles were validated by resolve_uniforms); the specular map never
+            // changes a pixel (fastshade.cuh) and is not passed on
+            L.dbpp = L.nbpp = L.dw = L.dh = L.nw = L.nh = 0;
+            L.diffuse = L.normal = nullptr;
+            if (u.diffuse) {
+                const Tex& t = c->textures[u.diffuse - 1];
+                L.diffuse = t.px; L.dw = (uint32_t)t.w; L.dh = (uint32_t)t.h; L.dbpp = (uint32_t)t.bpp;
+            }
+            if (u.normal) {
+                const Tex& t = c->textures[u.normal - 1];
+                L.normal = t.px; L.nw = (uint32_t)t.w; L.nh = (uint32_t)t.h; L.nbpp = (uint32_t)t.bpp;
+            }
         }
         void* dl = c->arena.alloc(sizeof(trbf::LitF) * nv, e);
         CU(e);
