@@ -215,6 +215,37 @@ TRB_EXPORT int TRB_FN(release_shadow_maps)(TrbCtx* ctx);
 TRB_EXPORT int TRB_FN(flush)(TrbCtx* ctx);
 TRB_EXPORT int TRB_FN(end_frame)(TrbCtx* ctx);
 
+/* ---- frame recordings: a launch-bound frame loop as one CUDA graph launch per frame -------------------------
+ * A small frame (config 1: 2 520 triangles at 800x800; config 2: two passes at 2048x2048) costs ~40 kernel launches
+ * of a few microseconds each: the GPU waits for the host, not the other way round.  A recording captures everything
+ * the calls between record_begin and record_end queue (begin_frame / begin_batch, set_viewport, draw*, depth_snapshot
+ * / restore, keep_depth_as_shadow_map, flush) into a CUDA graph; trb_replay then re-runs the whole frame with ONE
+ * launch - optionally with new matrices and uniform blocks, i.e. the next camera of main.cpp's frame loop
+ * (main.cpp:647-730 with a moving camera).  Results are bit for bit those of issuing the calls again.
+ *   - The frame must have been rendered once by plain calls before it is recorded (same sizes, same meshes): while
+ *     recording, no buffer may grow (TRB_E_ARG "render the frame once before recording it").
+ *   - Calls that synchronise, upload, read back or use other streams are refused inside a recording; record_end
+ *     resolves the frame (an implicit flush), runs it once, and leaves the context as the calls would have.
+ *   - A recording holds device addresses: it goes stale (trb_replay -> TRB_E_ARG) when a mesh or texture is freed
+ *     or any working buffer of the context is reallocated (a larger frame, a larger draw) after it was made.
+ *   - replay resolves the frame in flight, then IS a frame: read_* / readback_async / encode_tga* work on it as
+ *     usual, and a shadow map the recorded frame kept is held again (release it as after the recorded frame).
+ *   - `draws` (may be NULL = replay unchanged): one entry per trb_draw* call of the recording, in order; NULL
+ *     members keep what was recorded.  Matrices / uniform blocks are [nviews] arrays as in trb_draw_batch; texture
+ *     handles and shadow-map indices in a new uniform block are resolved again.  Rewriting parameters waits for the
+ *     previous replay of the same recording to have started its last copy (host-side, microseconds). */
+typedef uint64_t TrbRecording; /* 0 = invalid */
+typedef struct TrbReplayDraw {
+    const double* modelview;    /* [nviews][16] or NULL */
+    const double* perspective;  /* [nviews][16] or NULL */
+    const void* uniforms;       /* [nviews] uniform blocks of the draw's shader kind, or NULL */
+    size_t uniform_bytes;       /* size of ONE block (as passed to trb_draw) */
+} TrbReplayDraw;
+TRB_EXPORT int TRB_FN(record_begin)(TrbCtx* ctx);
+TRB_EXPORT int TRB_FN(record_end)(TrbCtx* ctx, TrbRecording* out);
+TRB_EXPORT int TRB_FN(replay)(TrbCtx* ctx, TrbRecording recording, const TrbReplayDraw* draws, int ndraws);
+TRB_EXPORT int TRB_FN(recording_free)(TrbCtx* ctx, TrbRecording recording);
+
 /* ---- post passes on the resident z-buffer ------------------------- */
 /* compute_ssao_at over the frame (main.cpp:324-362, 756-763): ao[x+y*w] = (u8)(255*ao) */
 TRB_EXPORT int TRB_FN(ssao)(TrbCtx* ctx, int view, uint8_t* ao_out);

@@ -684,6 +684,11 @@ int orc_open_peers_raw(TrbCtx* c, const uint64_t*, const uint64_t*, int, int) { 
 int orc_ipc_close_peers(TrbCtx* c) { return c ? TRB_OK : TRB_E_ARG; }
 int orc_composite_shade_p2p(TrbCtx* c, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_comm_init(TrbCtx* const*, int) { return TRB_E_COMM; }
+// frame recordings are CUDA graphs: the CPU checker renders every frame by plain calls
+int orc_record_begin(TrbCtx* c) { return fail(c, TRB_E_ARG, "oracle has no device"); }
+int orc_record_end(TrbCtx* c, TrbRecording*) { return fail(c, TRB_E_ARG, "oracle has no device"); }
+int orc_replay(TrbCtx* c, TrbRecording, const TrbReplayDraw*, int) { return fail(c, TRB_E_ARG, "oracle has no device"); }
+int orc_recording_free(TrbCtx* c, TrbRecording) { return fail(c, TRB_E_ARG, "oracle has no device"); }
 int orc_comm_export(TrbCtx* c, void*, size_t) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_comm_open(TrbCtx* c, const void*, int, int) { return fail(c, TRB_E_COMM, "oracle has no device"); }
 int orc_comm_close(TrbCtx* c) { return fail(c, TRB_E_COMM, "oracle has no device"); }

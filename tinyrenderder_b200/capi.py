@@ -6,6 +6,7 @@ bench.py's cpu_baseline leg bind the CPU oracle (prefix ``orc``) through the sam
 is what makes the parity tests read the same for both sides.  Nothing in this package imports
 or falls back to the oracle: if libtrb.so is missing, `load_cuda()` raises.
 """
+import contextlib
 import ctypes as C
 import os
 
@@ -58,6 +59,15 @@ class ShadowUniforms(C.Structure):
         ("shadow_w", C.c_int32),
         ("shadow_h", C.c_int32),
         ("_pad", C.c_int32),
+    ]
+
+
+class ReplayDraw(C.Structure):
+    _fields_ = [
+        ("modelview", C.c_void_p),
+        ("perspective", C.c_void_p),
+        ("uniforms", C.c_void_p),
+        ("uniform_bytes", C.c_size_t),
     ]
 
 
@@ -114,6 +124,10 @@ SIGNATURES = {
     "release_shadow_maps": (C.c_int, [_P]),
     "flush": (C.c_int, [_P]),
     "end_frame": (C.c_int, [_P]),
+    "record_begin": (C.c_int, [_P]),
+    "record_end": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "replay": (C.c_int, [_P, C.c_uint64, _P, C.c_int]),
+    "recording_free": (C.c_int, [_P, C.c_uint64]),
     "ssao": (C.c_int, [_P, C.c_int, _P]),
     "depth_image": (C.c_int, [_P, C.c_int, _P]),
     "composite_ao": (C.c_int, [_P, C.c_int, _P]),
@@ -271,6 +285,7 @@ class Renderer:
         self.width = self.height = 0
         self.nviews = 0
         self._keep = []
+        self._collect = None
 
     def close(self):
         if self.h:
@@ -361,6 +376,9 @@ class Renderer:
                 arr = uniforms
             up, ub = C.cast(arr, _P), C.sizeof(arr._type_)
             self._keep.append(arr)
+        if self._collect is not None:       # collect_draws(): the parameters a replay of this frame would pass
+            self._collect.append({"modelview": mv, "perspective": pr, "uniforms": None if uniforms is None else arr})
+            return
         name = "draw" if self.nviews == 1 else "draw_batch"
         self._ck(self._fn[name](self.h, mesh, _ptr(mv), _ptr(pr), kind, up, ub, first_tri, ntris), name)
 
@@ -401,6 +419,85 @@ class Renderer:
     def end_frame(self):
         self._ck(self._fn["end_frame"](self.h), "end_frame")
         self._keep.clear()
+
+    # frame recordings (CUDA graphs) --------------------------------------------------------
+    @contextlib.contextmanager
+    def collect_draws(self):
+        """Run a frame's call sequence WITHOUT touching the device and collect what its draw calls pass: the `draws`
+        list for replay() of a recording of the same sequence with other cameras / lights.
+            with r.collect_draws() as draws: render_frame(r, new_camera)
+            r.replay(rec, draws)
+        Inside, begin_frame / snapshot / restore / flush / end_frame do nothing and keep_depth_as_shadow_map returns the
+        index the recorded frame got (0, 1, ... after a release_shadow_maps)."""
+        real, state = self._fn, (self.width, self.height, self.nviews)
+        maps = [0]
+
+        def stub(name):
+            if name == "last_error":
+                return real[name]
+            if name == "keep_depth_as_shadow_map":
+                def keep(h, out):
+                    out._obj.value = maps[0]
+                    maps[0] += 1
+                    return 0
+                return keep
+            if name == "release_shadow_maps":
+                def release(h):
+                    maps[0] = 0
+                    return 0
+                return release
+            return lambda *a: 0
+
+        class Table(dict):
+            def __missing__(self, name):
+                self[name] = stub(name)
+                return self[name]
+
+        self._collect, self._fn = [], Table()
+        try:
+            yield self._collect
+        finally:
+            self._fn, self._collect = real, None
+            self.width, self.height, self.nviews = state
+
+    def record_begin(self):
+        self._ck(self._fn["record_begin"](self.h), "record_begin")
+
+    def record_end(self):
+        out = C.c_uint64(0)
+        self._ck(self._fn["record_end"](self.h, C.byref(out)), "record_end")
+        self._keep.clear()
+        return out.value
+
+    def replay(self, recording, draws=None):
+        """draws: None (replay unchanged) or one dict per recorded draw call with optional keys
+        modelview / perspective ((nviews,4,4) or (4,4)) and uniforms (a struct or a ctypes array)"""
+        if draws is None:
+            self._ck(self._fn["replay"](self.h, recording, None, 0), "replay")
+            return
+        arr = (ReplayDraw * len(draws))()
+        keep = []
+        for i, d in enumerate(draws):
+            d = d or {}
+            for key in ("modelview", "perspective"):
+                if d.get(key) is not None:
+                    m = np.ascontiguousarray(d[key], dtype=np.float64)
+                    if m.size == 16 and self.nviews > 1:
+                        m = np.tile(m.reshape(1, 16), (self.nviews, 1))
+                    m = _f64(m, 16 * self.nviews)
+                    keep.append(m)
+                    setattr(arr[i], key, m.ctypes.data)
+            u = d.get("uniforms")
+            if u is not None:
+                if not isinstance(u, C.Array):
+                    u = (type(u) * self.nviews)(*([u] * self.nviews))
+                keep.append(u)
+                arr[i].uniforms = C.cast(u, _P).value
+                arr[i].uniform_bytes = C.sizeof(u._type_)
+        self._ck(self._fn["replay"](self.h, recording, C.cast(arr, _P), len(draws)), "replay")
+
+    def recording_free(self, recording):
+        self._ck(self._fn["recording_free"](self.h, recording), "recording_free")
 
     # readback ----------------------------------------------------------------------------
     def read_color(self, view=0, out=None):

@@ -459,31 +459,34 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
 // second half of the direct path: ids of the fragments that sit at a pixel's final depth, over the
 // compacted list of the triangles that were (for a moment at least) nearest somewhere
 __global__ void __launch_bounds__(TPB) k_direct_resolve(FrameDev f, GeomArgs g, const uint32_t* __restrict__ direct_list,
-                                                        const uint32_t* __restrict__ direct_n) {
-    // one thread per list entry on a grid sized for the whole draw (the list length is only known on the device).  A
-    // capped grid-stride version costs 9 us less per draw when the list is empty, but doubles the kernel on the 100 M soup
-    // (4.5 vs 2.3 ms) - measured, not kept.
+                                                        const uint32_t* __restrict__ direct_n, uint32_t* __restrict__ host_seen) {
+    // one thread per list entry.  The list length is only known on the device: a context whose draws have had direct
+    // candidates (host_seen, mapped memory, read by the host at the next draw) launches a grid sized for the whole draw -
+    // a capped grid doubles the kernel on the 100 M soup (4.5 vs 2.3 ms) -, any other context a small one (an empty list
+    // then costs 3 us instead of 12 us per draw); the stride loop makes either grid correct for any length.
     const int view = blockIdx.y;
-    const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-    if (i >= direct_n[view]) return;
-    const uint32_t t = direct_list[(size_t)view * g.nslots + i];     // a slot
-    const VRec* vr = g.vrec + (size_t)view * g.nverts;
-    const uint32_t* q = g.perm ? g.idx_perm + (size_t)slot_position(t, g.shard_n, g.shard_r, g.shard_shift) * 3 : nullptr;
-    VRec a = load_vrec(vr + (q ? __ldg(q) : vertex_index(g.idx, g.first_tri, t, 0)));
-    VRec b_ = load_vrec(vr + (q ? __ldg(q + 1) : vertex_index(g.idx, g.first_tri, t, 1)));
-    VRec c = load_vrec(vr + (q ? __ldg(q + 2) : vertex_index(g.idx, g.first_tri, t, 2)));
-    TriSetup ts;
-    setup_triangle(a, b_, c, f.W, f.H, ts);
-    const unsigned long long* zk = f.zkey + (size_t)view * f.npix;
-    uint32_t* vis = f.vis + (size_t)view * f.npix;
-    const uint32_t gid = slot_gid(SlotIds{g.perm, g.id_base - (g.perm ? g.first_tri : 0u), g.shard_n, g.shard_r, g.shard_shift}, t);
-    for (int y = ts.y0; y <= ts.y1; ++y)
-        for (int x = ts.x0; x <= ts.x1; ++x) {
-            double b[3], z;
-            if (!eval_sample(ts, x, y, b, z)) continue;
-            const size_t p = (size_t)y * f.W + x;
-            if (fragment_key(z) == zk[p]) atomicMin(vis + p, gid);   // ties: lowest id = first submitted
-        }
+    const uint32_t n = direct_n[view];
+    if (n && blockIdx.x == 0 && threadIdx.x == 0) *host_seen = 1u;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * TPB) {
+        const uint32_t t = direct_list[(size_t)view * g.nslots + i];     // a slot
+        const VRec* vr = g.vrec + (size_t)view * g.nverts;
+        const uint32_t* q = g.perm ? g.idx_perm + (size_t)slot_position(t, g.shard_n, g.shard_r, g.shard_shift) * 3 : nullptr;
+        VRec a = load_vrec(vr + (q ? __ldg(q) : vertex_index(g.idx, g.first_tri, t, 0)));
+        VRec b_ = load_vrec(vr + (q ? __ldg(q + 1) : vertex_index(g.idx, g.first_tri, t, 1)));
+        VRec c = load_vrec(vr + (q ? __ldg(q + 2) : vertex_index(g.idx, g.first_tri, t, 2)));
+        TriSetup ts;
+        setup_triangle(a, b_, c, f.W, f.H, ts);
+        const unsigned long long* zk = f.zkey + (size_t)view * f.npix;
+        uint32_t* vis = f.vis + (size_t)view * f.npix;
+        const uint32_t gid = slot_gid(SlotIds{g.perm, g.id_base - (g.perm ? g.first_tri : 0u), g.shard_n, g.shard_r, g.shard_shift}, t);
+        for (int y = ts.y0; y <= ts.y1; ++y)
+            for (int x = ts.x0; x <= ts.x1; ++x) {
+                double b[3], z;
+                if (!eval_sample(ts, x, y, b, z)) continue;
+                const size_t p = (size_t)y * f.W + x;
+                if (fragment_key(z) == zk[p]) atomicMin(vis + p, gid);   // ties: lowest id = first submitted
+            }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1527,11 +1530,19 @@ __device__ __forceinline__ void lit_fast(const DrawDev& D, int view, const float
 // one visible pixel: p = x + y*W inside `view`, id = its winning triangle.  C2 = the frame has a
 // config-2 shader (SHADOW_PHONG / GOURAUD); frames without one run the instantiation that does not
 // carry their registers.
-template <bool C2, bool FAST>
-__device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
-                                            const DrawDev* sm_draws, int view, unsigned long long p, int x, int y, uint32_t id) {
+// base + i * STRIDE for a 32-bit element index as ONE multiply-add (the compiler's shift-and-add form costs two
+// instructions per address, and a pixel forms nine of them)
+template <unsigned STRIDE>
+__device__ __forceinline__ const void* elem_addr(const void* base, uint32_t i) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(i), "r"(STRIDE), "l"((unsigned long long)base));
+    return reinterpret_cast<const void*>(r);
+}
+
+// id -> (draw, triangle of the draw's mesh).  false: a winner of another rank's mesh that this context does not hold.
+__device__ __forceinline__ bool resolve_winner(const DrawDev* __restrict__ draws, int ndraws, const DrawDev* sm_draws,
+                                               uint32_t id, int& draw, uint32_t& g0) {
     constexpr int MAX_SM_DRAWS = SHADE_MAX_SM_DRAWS;
-    const size_t gp = (size_t)view * f.npix + p;
     int lo = 0;                   // last draw with id_base < id (bases ascend)
     if (ndraws <= 8) {            // a frame loop's handful of draws: count instead of bisecting
         #pragma unroll 1
@@ -1545,25 +1556,47 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
         }
     }
     // the draw table sits in shared memory: one level less in the dependent chain id -> draw -> indices -> records -> texels
-    DrawDev D = lo < MAX_SM_DRAWS ? sm_draws[lo] : draws[lo];
-    uint32_t t = id - D.id_base - 1u;                    // triangle inside the range this context drew
-    if (t >= D.ntris) {
+    const DrawDev* D = lo < MAX_SM_DRAWS ? sm_draws + lo : draws + lo;
+    uint32_t t = id - D->id_base - 1u;                   // triangle inside the range this context drew
+    uint32_t first = D->first_tri;
+    if (t >= D->ntris) {
         // a winner another rank rasterised (sort-last composite): find the draw whose MESH holds it
         int found = -1;
         for (int d = 0; d < ndraws && found < 0; ++d) {
             const long long g = (long long)id - draws[d].mesh_id_base - 1;
             if (g >= 0 && g < (long long)draws[d].mesh_ntris) found = d;
         }
-        if (found < 0) return;                           // not ours to shade
-        D = draws[found];
-        t = (uint32_t)((long long)id - D.mesh_id_base - 1) - D.first_tri;  // may wrap: first_tri + t is exact mod 2^32
+        if (found < 0) return false;                     // not ours to shade
+        lo = found;
+        first = draws[found].first_tri;
+        t = (uint32_t)((long long)id - draws[found].mesh_id_base - 1) - first;  // may wrap: first_tri + t is exact mod 2^32
     }
-    const uint32_t g0 = D.first_tri + t;                 // triangle index in the mesh
-    const uint32_t i0 = vertex_index(D.idx, 0, g0, 0);
-    const uint32_t i1 = vertex_index(D.idx, 0, g0, 1);
-    const uint32_t i2 = vertex_index(D.idx, 0, g0, 2);
+    draw = lo;
+    g0 = first + t;                                      // triangle index in the mesh
+    return true;
+}
+__device__ __forceinline__ void winner_vertices(const DrawDev* __restrict__ draws, const DrawDev* sm_draws, int draw, uint32_t g0,
+                                                uint32_t vi[3]) {
+    const uint32_t* idx = draw < SHADE_MAX_SM_DRAWS ? sm_draws[draw].idx : draws[draw].idx;
+    if (idx) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(elem_addr<12>(idx, g0));
+        vi[0] = __ldg(q); vi[1] = __ldg(q + 1); vi[2] = __ldg(q + 2);
+    } else {
+        vi[0] = g0 * 3u; vi[1] = g0 * 3u + 1u; vi[2] = g0 * 3u + 2u;     // implicit soup
+    }
+}
+
+// one visible pixel (x, y) of `view`, p = x + y*W: its winner is triangle g0 (vertices i0, i1, i2) of draw `draw`
+template <bool C2, bool FAST>
+__device__ __forceinline__ void shade_resolved(const FrameDev& f, const DrawDev* __restrict__ draws, const DrawDev* sm_draws,
+                                               int view, unsigned long long p, int x, int y, int draw, uint32_t g0,
+                                               uint32_t i0, uint32_t i1, uint32_t i2) {
+    const size_t gp = (size_t)view * f.npix + p;
+    const DrawDev D = draw < SHADE_MAX_SM_DRAWS ? sm_draws[draw] : draws[draw];
     const VRec* vr = D.vrec + (size_t)view * D.nverts;
-    const VRec va = load_vrec(vr + i0), vb = load_vrec(vr + i1), vc = load_vrec(vr + i2);
+    const VRec va = load_vrec(reinterpret_cast<const VRec*>(elem_addr<32>(vr, i0))),
+               vb = load_vrec(reinterpret_cast<const VRec*>(elem_addr<32>(vr, i1))),
+               vc = load_vrec(reinterpret_cast<const VRec*>(elem_addr<32>(vr, i2)));
     TriSetup ts;
     setup_known_triangle(va, vb, vc, ts);   // a recorded winner passed every reject: no tests, no bbox
     double b[3], z, pc[3];
@@ -1584,7 +1617,7 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
             float at[3][8];
             #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float4* q = reinterpret_cast<const float4*>(D.attr8 + (size_t)vi[k] * 8);
+                const float4* q = reinterpret_cast<const float4*>(elem_addr<32>(D.attr8, vi[k]));
                 const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
                 at[k][0] = q0.x; at[k][1] = q0.y; at[k][2] = q0.z; at[k][3] = q0.w;
                 at[k][4] = q1.x; at[k][5] = q1.y; at[k][6] = q1.z; at[k][7] = q1.w;
@@ -1631,6 +1664,15 @@ __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __
             c[0] = col[0]; c[1] = col[1]; c[2] = col[2];
         }
     }
+}
+template <bool C2, bool FAST>
+__device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
+                                            const DrawDev* sm_draws, int view, unsigned long long p, int x, int y, uint32_t id) {
+    int draw;
+    uint32_t g0, vi[3];
+    if (!resolve_winner(draws, ndraws, sm_draws, id, draw, g0)) return;
+    winner_vertices(draws, sm_draws, draw, g0, vi);
+    shade_resolved<C2, FAST>(f, draws, sm_draws, view, p, x, y, draw, g0, vi[0], vi[1], vi[2]);
 }
 
 // The flush picks its kernel on the device (no host round trip): sparse frames (configs 4, 5) shade
@@ -1715,17 +1757,19 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_shade_dense(Frame
         const unsigned long long p = p0 + (unsigned long long)k * TPB;
         ids[k] = p < last ? vis[p] : VIS_NONE;
     }
+    // (requesting the index triples of all the pixels up front as well was measured: 1.42 vs 1.30 ms - the kernel is bound
+    // by instruction issue, and the extra local-memory traffic costs more than the overlapped wait saves)
     // pixel coordinates by one division per thread, then TPB columns further per pixel
     int y = (int)((uint32_t)p0 / (uint32_t)f.W);         // p < 2^32: a frame has fewer than 2^32 pixels
     int x = (int)((uint32_t)p0 - (uint32_t)y * (uint32_t)f.W);
+    uint32_t* visp = vis + p0;
     #pragma unroll 1
-    for (int k = 0; k < SHADE_DENSE_PX; ++k, x += TPB) {
+    for (int k = 0; k < SHADE_DENSE_PX; ++k, x += TPB, visp += TPB) {
         while (x >= f.W) { x -= f.W; ++y; }
         const uint32_t id = ids[k];
         if (id == VIS_NONE || id == VIS_SHADED) continue;
-        const unsigned long long p = p0 + (unsigned long long)k * TPB;
-        shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, p, x, y, id);
-        vis[p] = VIS_SHADED;
+        shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, view, p0 + (unsigned long long)k * TPB, x, y, id);
+        *visp = VIS_SHADED;
     }
 }
 

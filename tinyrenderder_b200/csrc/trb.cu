@@ -6,6 +6,7 @@
 #include "tga_rle.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -23,11 +24,20 @@ cudaError_t trb_mesh_order_build(const float4* pos4, uint32_t nverts, const uint
 
 namespace {
 
+// Frame recordings (trb_record_begin .. trb_replay, below) bake device addresses into a CUDA graph.  g_generation moves
+// whenever an address a recording may hold stops being valid (a scratch buffer is reallocated or released, a mesh or
+// texture is freed): a replay checks that it has not moved since the recording ended.  While a thread records, buffers
+// may not grow (growth synchronises the stream, which a capturing stream cannot): the frame is rendered once first.
+std::atomic<uint64_t> g_generation{0};
+thread_local bool t_recording = false;
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes, cudaStream_t st) {
         if (bytes <= cap) return cudaSuccess;
+        if (t_recording) return cudaErrorNotPermitted;
+        ++g_generation;
         if (p) {
             cudaStreamSynchronize(st);  // kernels in flight may still read the old block
             cudaFree(p);
@@ -40,7 +50,10 @@ struct DevBuf {
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            cudaFree(p);
+            ++g_generation;
+        }
         p = nullptr;
         cap = 0;
     }
@@ -61,6 +74,10 @@ struct Arena {
                 b.used += bytes;
                 return r;
             }
+        if (t_recording) {       // a recorded frame lives in the blocks the frame before it sized
+            err = cudaErrorNotPermitted;
+            return nullptr;
+        }
         size_t cap = next_cap;
         while (cap < bytes) cap *= 2;
         Block nb{nullptr, cap, 0};
@@ -231,6 +248,36 @@ struct ProfAcc {
 
 }  // namespace
 
+// One recorded frame (trb_record_begin .. trb_record_end): the launch sequence as an instantiated CUDA graph, the pinned
+// block its host-to-device parameter copies read from, where in that block each draw's matrices / uniforms sit (so that
+// trb_replay can rewrite them for a new camera), and the context state the frame leaves behind.
+struct Recording {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    char* params = nullptr;             // pinned; the graph's memcpy nodes read it when the graph RUNS
+    size_t params_cap = 0, params_used = 0;
+    struct Draw {
+        int kind, nviews;
+        size_t mats_off, litf_off, uni_off;   // (size_t)-1: the draw has no such block
+        size_t uni_host_bytes;                // size of the caller's uniform block per view
+        std::vector<double> mv;               // the caller's ModelViews and uniform blocks as last passed
+        std::vector<char> uni;
+    };
+    size_t maps_before = 0;             // shadow maps the context held when the recording began ...
+    std::vector<ShadowMap> maps_kept;   // ... and the ones trb_keep_depth_as_shadow_map made inside it
+    std::vector<Draw> draws;
+    cudaEvent_t done = nullptr;         // the last replay has finished reading `params`
+    std::string failed;                 // first error of a call inside the recording
+    uint64_t generation = 0;
+    uint64_t launches = 0;              // kernel launches of one replay
+    // what the context looks like after the frame
+    FrameDev frame{};
+    DevBuf zkey, zsnap;                 // roles of the two depth planes (trb_depth_restore swaps them)
+    bool have_snapshot = false, snap_stale = false, foreign_ids = false;
+    uint64_t next_id = 0, tris_submitted = 0;
+    int shade_row0 = 0, shade_row1 = -1;
+};
+
 struct TrbCtx {
     int device = 0;
     int sms = 148;
@@ -353,17 +400,31 @@ struct TrbCtx {
     // Default: from 2 M triangles up - below that the vertex records of a draw (32 B each) sit in the 126 MB L2 anyway.
     uint64_t order_min_tris = 2ull << 20;
     uint32_t shard_shift = 12;  // trb_draw_shard deals the processing order out in blocks of 2^shard_shift triangles (TRB_SHARD_SHIFT)
+
+    // frame recordings (CUDA graphs): `rec` is the one being recorded, if any
+    Recording* rec = nullptr;
+    std::vector<Recording*> recordings;   // slot = handle - 1; nullptr = freed
+    uint64_t launches_at_record = 0;
 };
 
 namespace {
 
 int fail(TrbCtx* c, int code, const std::string& msg) {
-    if (c) c->err = msg;
+    if (c) {
+        c->err = msg;
+        if (c->rec && c->rec->failed.empty()) c->rec->failed = msg;   // a call of the recording failed: record_end reports it
+    }
     return code;
+}
+int refused(TrbCtx* c, const char* msg) {   // a call that may not run inside a recording: nothing was captured, nothing is lost
+    if (c) c->err = msg;
+    return TRB_E_ARG;
 }
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
+        if (e_ == cudaErrorNotPermitted && t_recording)                                            \
+            return fail(c, TRB_E_ARG, "record: " #call " would have to grow a buffer - render the frame once before recording it"); \
         if (e_ != cudaSuccess)                                                                     \
             return fail(c, e_ == cudaErrorMemoryAllocation ? TRB_E_NOMEM : TRB_E_CUDA,             \
                         std::string(#call) + ": " + cudaGetErrorString(e_));                       \
@@ -463,6 +524,39 @@ int check_device(TrbCtx* c) {
     return TRB_OK;
 }
 
+void recording_destroy(Recording* r) {
+    if (!r) return;
+    if (r->exec) cudaGraphExecDestroy(r->exec);
+    if (r->graph) cudaGraphDestroy(r->graph);
+    if (r->done) cudaEventDestroy(r->done);
+    if (r->params) cudaFreeHost(r->params);
+    delete r;
+}
+// Host-to-device copy of a small parameter block (matrices, uniforms, the draw table) behind the context's stream.  The
+// source is pageable and transient: outside a recording cudaMemcpyAsync stages it before it returns.  While recording the
+// bytes go to the recording's pinned block and the captured copy reads them from there each time the graph runs;
+// *slot (optional) receives their offset so that trb_replay can overwrite them.
+int param_copy(TrbCtx* c, void* dst, const void* src, size_t bytes, size_t* slot = nullptr) {
+    if (slot) *slot = (size_t)-1;
+    if (!c->rec) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        return TRB_OK;
+    }
+    Recording& r = *c->rec;
+    const size_t off = (r.params_used + 15) & ~(size_t)15;
+    if (off + bytes > r.params_cap) return fail(c, TRB_E_NOMEM, "record: the frame's parameter blocks exceed the recording's 4 MB");
+    memcpy(r.params + off, src, bytes);
+    r.params_used = off + bytes;
+    if (slot) *slot = off;
+    CU(cudaMemcpyAsync(dst, r.params + off, bytes, cudaMemcpyHostToDevice, c->stream));
+    return TRB_OK;
+}
+// entry points that synchronise, allocate or touch other streams cannot run inside a recording
+#define NOT_WHILE_RECORDING(c, what)                                                                       \
+    do {                                                                                                   \
+        if ((c) && (c)->rec) return refused(c, what ": not inside trb_record_begin / trb_record_end"); \
+    } while (0)
+
 // upload the draw table and run the shade kernel over [row0,row1)
 int do_flush(TrbCtx* c) {
     if (!c->in_frame) return fail(c, TRB_E_ARG, "flush: no frame");
@@ -471,7 +565,8 @@ int do_flush(TrbCtx* c) {
     if (rc) return rc;
     size_t bytes = c->draws.size() * sizeof(DrawDev);
     CU(c->draw_table.ensure(bytes, c->stream));
-    CU(cudaMemcpyAsync(c->draw_table.p, c->draws.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    rc = param_copy(c, c->draw_table.p, c->draws.data(), bytes);
+    if (rc) return rc;
     int r0 = 0, r1 = c->frame.H;
     if (c->shade_row1 >= 0) {
         r0 = c->shade_row0;
@@ -648,8 +743,11 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
                                                      c->direct_n_p);
     }
     if (c->direct_area > 0) {
+        // full grid once a draw of this context has had direct candidates (mapped flag, never waited for), else a few CTAs
+        const dim3 dgrid(c->host_total[9] ? tgrid.x : std::min<unsigned>(tgrid.x, std::max(1u, (unsigned)c->sms * 4 / (unsigned)f.nviews)),
+                         f.nviews);
         Launch L(c, "k_direct_resolve");
-        k_direct_resolve<<<tgrid, TPB, 0, c->stream>>>(f, g, c->direct_list.as<uint32_t>(), c->direct_n_p);
+        k_direct_resolve<<<dgrid, TPB, 0, c->stream>>>(f, g, c->direct_list.as<uint32_t>(), c->direct_n_p, c->host_total_dev + 9);
     }
     CU(cudaGetLastError());
     // item list of the split warp kernel: sized from what recent draws asked for (never waited for); a draw that needs
@@ -736,8 +834,10 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     return TRB_OK;
 }
 
-int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, int nviews, const void** dev_out) {
-    *dev_out = nullptr;
+// the per-view uniform blocks of a lit draw as the device reads them (LitUniforms, or ShadowUniformsDev for SHADOW_PHONG);
+// `out` stays empty for the shaders without uniforms
+int build_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, int nviews, std::vector<char>& out) {
+    out.clear();
     if (kind == TRB_SHADER_FLAT_BARY || kind == TRB_SHADER_DEPTH) return TRB_OK;
     const bool shadow = kind == TRB_SHADER_SHADOW_PHONG;
     if (kind != TRB_SHADER_PHONG && kind != TRB_SHADER_EYE && kind != TRB_SHADER_GOURAUD && !shadow)
@@ -759,20 +859,16 @@ int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, i
         L.normal_map_strength = u.normal_map_strength;
         return tex(u.diffuse, L.diffuse) && tex(u.normal, L.normal) && tex(u.specular, L.specular);
     };
-    cudaError_t e = cudaSuccess;
     if (!shadow) {
-        std::vector<LitUniforms> host(nviews);
+        out.resize(sizeof(LitUniforms) * nviews);
+        LitUniforms* host = reinterpret_cast<LitUniforms*>(out.data());
         const TrbPhongUniforms* u = (const TrbPhongUniforms*)uniforms;
         for (int v = 0; v < nviews; ++v)
             if (!lit_of(u[v], host[v])) return fail(c, TRB_E_ARG, "draw: bad texture handle");
-        void* d = c->arena.alloc(sizeof(LitUniforms) * nviews, e);
-        CU(e);
-        // `host` is pageable: the copy is staged before cudaMemcpyAsync returns
-        CU(cudaMemcpyAsync(d, host.data(), sizeof(LitUniforms) * nviews, cudaMemcpyHostToDevice, c->stream));
-        *dev_out = d;
         return TRB_OK;
     }
-    std::vector<ShadowUniformsDev> host(nviews);
+    out.resize(sizeof(ShadowUniformsDev) * nviews);
+    ShadowUniformsDev* host = reinterpret_cast<ShadowUniformsDev*>(out.data());
     const TrbShadowUniforms* u = (const TrbShadowUniforms*)uniforms;
     for (int v = 0; v < nviews; ++v) {
         if (!lit_of(u[v].phong, host[v].lit)) return fail(c, TRB_E_ARG, "draw: bad texture handle");
@@ -791,11 +887,57 @@ int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, i
         S.w = sm.w;
         S.h = sm.h;
     }
-    void* d = c->arena.alloc(sizeof(ShadowUniformsDev) * nviews, e);
+    return TRB_OK;
+}
+int resolve_uniforms(TrbCtx* c, int kind, const void* uniforms, size_t ubytes, int nviews, const void** dev_out,
+                     size_t* slot = nullptr) {
+    *dev_out = nullptr;
+    if (slot) *slot = (size_t)-1;
+    std::vector<char> host;
+    int rc = build_uniforms(c, kind, uniforms, ubytes, nviews, host);
+    if (rc || host.empty()) return rc;
+    cudaError_t e = cudaSuccess;
+    void* d = c->arena.alloc(host.size(), e);
     CU(e);
-    CU(cudaMemcpyAsync(d, host.data(), sizeof(ShadowUniformsDev) * nviews, cudaMemcpyHostToDevice, c->stream));
+    rc = param_copy(c, d, host.data(), host.size(), slot);   // `host` is pageable: staged (or kept by the recording) on return
+    if (rc) return rc;
     *dev_out = d;
     return TRB_OK;
+}
+// [nviews][32] doubles: ModelView, Perspective of every view
+void build_mats(const double* mv, const double* pr, int nv, std::vector<double>& hm) {
+    hm.resize((size_t)32 * nv);
+    for (int v = 0; v < nv; ++v) {
+        memcpy(&hm[(size_t)v * 32], mv + 16 * v, 128);
+        memcpy(&hm[(size_t)v * 32 + 16], pr + 16 * v, 128);
+    }
+}
+// the LitF blocks of a lit mesh draw (fastshade.cuh); empty for the other shaders.  Handles were validated by build_uniforms.
+void build_litf(TrbCtx* c, int kind, const void* uniforms, const double* mv, int nv, std::vector<trbf::LitF>& hl) {
+    hl.clear();
+    if (kind != TRB_SHADER_PHONG && kind != TRB_SHADER_EYE && kind != TRB_SHADER_SHADOW_PHONG) return;
+    hl.resize(nv);
+    for (int v = 0; v < nv; ++v) {
+        const TrbPhongUniforms& u = kind == TRB_SHADER_SHADOW_PHONG ? ((const TrbShadowUniforms*)uniforms)[v].phong
+                                                                    : ((const TrbPhongUniforms*)uniforms)[v];
+        trbf::LitF& L = hl[v];
+        for (int i = 0; i < 12; ++i) L.mv[i] = (float)mv[16 * v + i];
+        L.key = trbf::F3{(float)u.key_dir_eye[0], (float)u.key_dir_eye[1], (float)u.key_dir_eye[2]};
+        L.fill = trbf::F3{(float)u.fill_dir_eye[0], (float)u.fill_dir_eye[1], (float)u.fill_dir_eye[2]};
+        L.rim = trbf::F3{(float)u.rim_dir_eye[0], (float)u.rim_dir_eye[1], (float)u.rim_dir_eye[2]};
+        L.normal_map_strength = (float)u.normal_map_strength;
+        // the maps the lit pixel samples; the specular map never changes a pixel (fastshade.cuh) and is not passed on
+        L.dbpp = L.nbpp = L.dw = L.dh = L.nw = L.nh = 0;
+        L.diffuse = L.normal = nullptr;
+        if (u.diffuse) {
+            const Tex& t = c->textures[u.diffuse - 1];
+            L.diffuse = t.px; L.dw = (uint32_t)t.w; L.dh = (uint32_t)t.h; L.dbpp = (uint32_t)t.bpp;
+        }
+        if (u.normal) {
+            const Tex& t = c->textures[u.normal - 1];
+            L.normal = t.px; L.nw = (uint32_t)t.w; L.nh = (uint32_t)t.h; L.nbpp = (uint32_t)t.bpp;
+        }
+    }
 }
 
 int tga_finish(TrbCtx* c, TrbCtx::TgaJob& j, bool wait_copies);   // asynchronous TGA writer, defined with trb_encode_tga_async
@@ -924,6 +1066,15 @@ int trb_create(int device, TrbCtx** out) {
 int trb_destroy(TrbCtx* c) {
     if (!c) return TRB_E_ARG;
     cudaSetDevice(c->device);
+    if (c->rec) {                         // destroyed in the middle of a recording: end the capture first
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(c->stream, &g);
+        c->rec->graph = g;
+        recording_destroy(c->rec);
+        c->rec = nullptr;
+        t_recording = false;
+        (void)cudaGetLastError();
+    }
     cudaStreamSynchronize(c->stream);
     if (c->upload_stream) cudaStreamSynchronize(c->upload_stream);
     for (auto& m : c->meshes)
@@ -959,6 +1110,7 @@ int trb_destroy(TrbCtx* c) {
         if (j.offs_ready) cudaEventDestroy(j.offs_ready);
         if (j.done) cudaEventDestroy(j.done);
     }
+    for (Recording* r : c->recordings) recording_destroy(r);
     c->arena.release();
     c->cache.release();
     c->ring.release();
@@ -1066,6 +1218,7 @@ extern "C" {
 
 int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float* uv2, uint32_t nverts,
                     const uint32_t* idx, uint64_t nidx, TrbMesh* out) {
+    NOT_WHILE_RECORDING(c, "upload_mesh");
     HostSpan host_span_("trb_upload_mesh");
     if (!c || !pos3 || !out || nidx % 3 || nverts == 0) return fail(c, TRB_E_ARG, "upload_mesh: bad argument");
     if (nidx / 3 >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "upload_mesh: too many triangles");
@@ -1154,6 +1307,7 @@ int trb_upload_mesh(TrbCtx* c, const float* pos3, const float* nrm3, const float
 }
 
 int trb_free_mesh(TrbCtx* c, TrbMesh h) {
+    NOT_WHILE_RECORDING(c, "free_mesh");
     HostSpan host_span_("trb_free_mesh");
     if (!c || h == 0 || h > c->meshes.size() || !c->meshes[h - 1].alive) return fail(c, TRB_E_ARG, "free_mesh");
     int rc = check_device(c);
@@ -1162,6 +1316,7 @@ int trb_free_mesh(TrbCtx* c, TrbMesh h) {
     // flush): shade first, so the event the block is tagged with covers its last reader
     if (!c->draws.empty() && (rc = do_flush(c))) return rc;
     Mesh& m = c->meshes[h - 1];
+    ++g_generation;                    // recordings that draw it are stale now
     c->cache.put(m.pos4, (size_t)m.nverts * 16, c->stream);   // tagged: reusable once the kernels queued so far are done
     c->cache.put(m.attr8, (size_t)m.nverts * 32, c->stream);
     if (m.idx) c->cache.put(m.idx, m.nidx * 4, c->stream);
@@ -1172,6 +1327,7 @@ int trb_free_mesh(TrbCtx* c, TrbMesh h) {
 }
 
 int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, TrbTex* out) {
+    NOT_WHILE_RECORDING(c, "upload_texture");
     HostSpan host_span_("trb_upload_texture");
     // 65535: the TGA header's 16-bit sizes (tgaimage.h); it also keeps every texel index below 2^32
     if (!c || !texels || !out || w <= 0 || h <= 0 || w > 65535 || h > 65535 || (bpp != 1 && bpp != 3 && bpp != 4))
@@ -1199,11 +1355,13 @@ int trb_upload_texture(TrbCtx* c, const uint8_t* texels, int w, int h, int bpp, 
 }
 
 int trb_free_texture(TrbCtx* c, TrbTex h) {
+    NOT_WHILE_RECORDING(c, "free_texture");
     HostSpan host_span_("trb_free_texture");
     if (!c || h == 0 || h > c->textures.size() || !c->textures[h - 1].alive) return fail(c, TRB_E_ARG, "free_texture");
     int rc = check_device(c);
     if (rc) return rc;
     if (!c->draws.empty() && (rc = do_flush(c))) return rc;   // pending draws sample it at the next flush (see free_mesh)
+    ++g_generation;                    // recordings that sample it are stale now
     Tex& x = c->textures[h - 1];
     c->cache.put(x.px, (size_t)x.w * x.h * x.bpp, c->stream);
     x = Tex();
@@ -1328,50 +1486,34 @@ int draw_mesh(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int k
     c->tris_submitted += ntris;
     if (ntris == 0) {
         c->next_id = id_base0 + id_span;
+        if (c->rec) c->rec->draws.push_back(Recording::Draw{kind, nv, (size_t)-1, (size_t)-1, (size_t)-1, ubytes, {}, {}});
         return TRB_OK;
     }
     const void* dun = nullptr;
-    rc = resolve_uniforms(c, kind, uniforms, ubytes, nv, &dun);
+    Recording::Draw slots{kind, nv, (size_t)-1, (size_t)-1, (size_t)-1, ubytes, {}, {}};
+    rc = resolve_uniforms(c, kind, uniforms, ubytes, nv, &dun, &slots.uni_off);
     if (rc) return rc;
     cudaError_t e = cudaSuccess;
     double* mats = (double*)c->arena.alloc(sizeof(double) * 32 * nv, e);
     CU(e);
-    std::vector<double> hm((size_t)32 * nv);
-    for (int v = 0; v < nv; ++v) {
-        memcpy(&hm[(size_t)v * 32], mv + 16 * v, 128);
-        memcpy(&hm[(size_t)v * 32 + 16], pr + 16 * v, 128);
-    }
-    CU(cudaMemcpyAsync(mats, hm.data(), hm.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    std::vector<double> hm;
+    build_mats(mv, pr, nv, hm);
+    rc = param_copy(c, mats, hm.data(), hm.size() * 8, &slots.mats_off);
+    if (rc) return rc;
     const void* litf = nullptr;
     std::vector<trbf::LitF> hl;
-    if (kind == TRB_SHADER_PHONG || kind == TRB_SHADER_EYE || kind == TRB_SHADER_SHADOW_PHONG) {
-        hl.resize(nv);
-        for (int v = 0; v < nv; ++v) {
-            const TrbPhongUniforms& u = kind == TRB_SHADER_SHADOW_PHONG ? ((const TrbShadowUniforms*)uniforms)[v].phong
-                                                                        : ((const TrbPhongUniforms*)uniforms)[v];
-            trbf::LitF& L = hl[v];
-            for (int i = 0; i < 12; ++i) L.mv[i] = (float)mv[16 * v + i];
-            L.key = trbf::F3{(float)u.key_dir_eye[0], (float)u.key_dir_eye[1], (float)u.key_dir_eye[2]};
-            L.fill = trbf::F3{(float)u.fill_dir_eye[0], (float)u.fill_dir_eye[1], (float)u.fill_dir_eye[2]};
-            L.rim = trbf::F3{(float)u.rim_dir_eye[0], (float)u.rim_dir_eye[1], (float)u.rim_dir_eye[2]};
-            L.normal_map_strength = (float)u.normal_map_strength;
-            // the maps the lit pixel samples (handles were validated by resolve_uniforms); the specular map never
-            // changes a pixel (fastshade.cuh) and is not passed on
-            L.dbpp = L.nbpp = L.dw = L.dh = L.nw = L.nh = 0;
-            L.diffuse = L.normal = nullptr;
-            if (u.diffuse) {
-                const Tex& t = c->textures[u.diffuse - 1];
-                L.diffuse = t.px; L.dw = (uint32_t)t.w; L.dh = (uint32_t)t.h; L.dbpp = (uint32_t)t.bpp;
-            }
-            if (u.normal) {
-                const Tex& t = c->textures[u.normal - 1];
-                L.normal = t.px; L.nw = (uint32_t)t.w; L.nh = (uint32_t)t.h; L.nbpp = (uint32_t)t.bpp;
-            }
-        }
+    build_litf(c, kind, uniforms, mv, nv, hl);
+    if (!hl.empty()) {
         void* dl = c->arena.alloc(sizeof(trbf::LitF) * nv, e);
         CU(e);
-        CU(cudaMemcpyAsync(dl, hl.data(), sizeof(trbf::LitF) * nv, cudaMemcpyHostToDevice, c->stream));
+        rc = param_copy(c, dl, hl.data(), sizeof(trbf::LitF) * nv, &slots.litf_off);
+        if (rc) return rc;
         litf = dl;
+    }
+    if (c->rec) {      // what the caller passed, kept so that a replay can change the matrices or the uniforms alone
+        slots.mv.assign(mv, mv + (size_t)16 * nv);
+        if (uniforms && ubytes) slots.uni.assign((const char*)uniforms, (const char*)uniforms + ubytes * nv);
+        c->rec->draws.push_back(slots);
     }
     VRec* vrec = (VRec*)c->arena.alloc(sizeof(VRec) * (size_t)m.nverts * nv, e);
     CU(e);
@@ -1430,6 +1572,7 @@ int trb_draw_batch(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, 
 
 int trb_draw_shard(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int kind, const void* uniforms,
                    size_t ubytes, int shard_rank, int shard_count) {
+    NOT_WHILE_RECORDING(c, "draw_shard");
     HostSpan host_span_("trb_draw_shard");
     if (c && c->in_frame && c->frame.nviews != 1) return fail(c, TRB_E_ARG, "draw_shard: needs a single-view frame");
     if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return fail(c, TRB_E_ARG, "draw_shard: bad rank / count");
@@ -1446,6 +1589,7 @@ int trb_draw(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int ki
 
 int trb_submit_clip_triangles(TrbCtx* c, const double* clip12, const double* varyings, uint64_t n, const double* mv,
                               int kind, const void* uniforms, size_t ubytes) {
+    NOT_WHILE_RECORDING(c, "submit_clip_triangles");
     if (!c || !c->in_frame || c->frame.nviews != 1) return fail(c, TRB_E_ARG, "submit: needs a single-view frame");
     if (!clip12 && n) return fail(c, TRB_E_ARG, "submit: null clip");
     if (n * 3 >= 0xFFFFFFF0ull || c->next_id + n >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "submit: too many triangles");
@@ -1580,6 +1724,7 @@ int trb_keep_depth_as_shadow_map(TrbCtx* c, int32_t* out) {
 }
 
 int trb_release_shadow_maps(TrbCtx* c) {
+    NOT_WHILE_RECORDING(c, "release_shadow_maps");
     if (!c) return TRB_E_ARG;
     CU(cudaSetDevice(c->device));
     for (auto& b : c->shadow_maps) c->shadow_pool.push_back(b.keys);   // no sync, no cudaFree: reused by the next keep
@@ -1602,7 +1747,178 @@ int trb_end_frame(TrbCtx* c) {
     return do_flush(c);
 }
 
+// ---- frame recordings: a launch-bound frame as ONE CUDA graph launch ---------------------------------------------
+// the frame a recording describes has (re)run: make the context look like it
+static int recording_adopt_state(TrbCtx* c, Recording& r) {
+    // shadow-map planes the frame kept go back from the pool (or stay) in the slots the frame gave them
+    if (c->shadow_maps.size() < r.maps_before) return fail(c, TRB_E_ARG, "replay: shadow maps the recording uses were released");
+    for (size_t i = 0; i < r.maps_kept.size(); ++i) {
+        const size_t slot = r.maps_before + i;
+        if (slot < c->shadow_maps.size()) {
+            if (c->shadow_maps[slot].keys.p != r.maps_kept[i].keys.p)
+                return fail(c, TRB_E_ARG, "replay: release the shadow maps of the frame before (trb_release_shadow_maps)");
+            continue;
+        }
+        bool found = false;
+        for (size_t k = 0; k < c->shadow_pool.size() && !found; ++k)
+            if (c->shadow_pool[k].p == r.maps_kept[i].keys.p) {
+                c->shadow_pool.erase(c->shadow_pool.begin() + k);
+                found = true;
+            }
+        if (!found) return fail(c, TRB_E_ARG, "replay: a shadow-map plane of the recording is in use elsewhere");
+        c->shadow_maps.push_back(r.maps_kept[i]);
+    }
+    c->frame = r.frame;
+    c->zkey = r.zkey;
+    c->zsnap = r.zsnap;
+    c->have_snapshot = r.have_snapshot;
+    c->snap_stale = r.snap_stale;
+    c->foreign_ids = r.foreign_ids;
+    c->next_id = r.next_id;
+    c->tris_submitted = r.tris_submitted;
+    c->shade_row0 = r.shade_row0;
+    c->shade_row1 = r.shade_row1;
+    c->draws.clear();
+    c->in_frame = true;
+    return TRB_OK;
+}
+
+int trb_record_begin(TrbCtx* c) {
+    if (!c) return TRB_E_ARG;
+    if (c->rec) return fail(c, TRB_E_ARG, "record_begin: already recording");
+    if (c->sync_draws || c->profiling || c->comm.n > 0 || c->peers.n > 0)
+        return fail(c, TRB_E_ARG, "record_begin: not with TRB_SYNC_DRAWS, kernel profiling or a composite group");
+    int rc = check_device(c);
+    if (rc) return rc;
+    if (c->in_frame && (rc = do_flush(c))) return rc;      // what was drawn before is not part of the recording
+    Recording* r = new Recording();
+    r->params_cap = (size_t)4 << 20;
+    if (cudaHostAlloc((void**)&r->params, r->params_cap, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->done, cudaEventDisableTiming) != cudaSuccess) {
+        recording_destroy(r);
+        return fail(c, TRB_E_NOMEM, "record_begin: pinned parameter block");
+    }
+    r->maps_before = c->shadow_maps.size();
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) {
+        recording_destroy(r);
+        return fail(c, TRB_E_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+    }
+    c->rec = r;
+    c->launches_at_record = c->launches;
+    t_recording = true;
+    return TRB_OK;
+}
+
+int trb_record_end(TrbCtx* c, TrbRecording* out) {
+    if (!c || !out) return fail(c, TRB_E_ARG, "record_end");
+    if (!c->rec) return fail(c, TRB_E_ARG, "record_end: not recording");
+    Recording* r = c->rec;
+    *out = 0;
+    int rc = check_device(c);
+    if (!rc && r->failed.empty() && c->in_frame) rc = do_flush(c);   // a recording ends with its frame resolved
+    if (!rc && !r->failed.empty()) {
+        rc = TRB_E_ARG;
+        c->err = "a call inside the recording failed: " + r->failed;
+    }
+    const std::string why = rc ? c->err : std::string();
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->rec = nullptr;
+    t_recording = false;
+    if (!rc && e == cudaSuccess && g) e = cudaGraphInstantiate(&r->exec, g, 0);
+    r->graph = g;
+    if (rc || e != cudaSuccess || !r->exec) {
+        recording_destroy(r);
+        (void)cudaGetLastError();
+        c->in_frame = false;                               // nothing of the frame ran: its calls were only captured
+        c->draws.clear();
+        return rc ? fail(c, rc, "record_end: " + why)
+                  : fail(c, TRB_E_CUDA, std::string("record_end: the capture failed: ") + cudaGetErrorString(e));
+    }
+    r->launches = c->launches - c->launches_at_record;
+    r->frame = c->frame;
+    r->zkey = c->zkey;
+    r->zsnap = c->zsnap;
+    r->have_snapshot = c->have_snapshot;
+    r->snap_stale = c->snap_stale;
+    r->foreign_ids = c->foreign_ids;
+    r->next_id = c->next_id;
+    r->tris_submitted = c->tris_submitted;
+    r->shade_row0 = c->shade_row0;
+    r->shade_row1 = c->shade_row1;
+    for (size_t i = r->maps_before; i < c->shadow_maps.size(); ++i) r->maps_kept.push_back(c->shadow_maps[i]);
+    r->generation = g_generation.load();
+    // capturing ran nothing: run the frame now, so that the context is where the calls left it
+    CU(cudaGraphLaunch(r->exec, c->stream));
+    CU(cudaEventRecord(r->done, c->stream));
+    size_t slot = 0;
+    while (slot < c->recordings.size() && c->recordings[slot]) ++slot;
+    if (slot == c->recordings.size()) c->recordings.push_back(r); else c->recordings[slot] = r;
+    *out = slot + 1;
+    return TRB_OK;
+}
+
+int trb_replay(TrbCtx* c, TrbRecording h, const TrbReplayDraw* draws, int ndraws) {
+    HostSpan host_span_("trb_replay");
+    if (!c || h == 0 || h > c->recordings.size() || !c->recordings[h - 1]) return fail(c, TRB_E_ARG, "replay: bad recording");
+    NOT_WHILE_RECORDING(c, "replay");
+    Recording& r = *c->recordings[h - 1];
+    if (r.generation != g_generation.load())
+        return fail(c, TRB_E_ARG, "replay: the recording is stale (a buffer, mesh or texture it refers to was reallocated or freed)");
+    int rc = check_device(c);
+    if (rc) return rc;
+    if (c->in_frame && (rc = do_flush(c))) return rc;      // the frame in flight resolves first
+    rc = recording_adopt_state(c, r);                      // first: the uniforms below are validated against this state
+    if (rc) return rc;
+    if (draws) {
+        if (ndraws != (int)r.draws.size()) return fail(c, TRB_E_ARG, "replay: one entry per draw call of the recording");
+        CU(cudaEventSynchronize(r.done));                  // the replay before this one has read the parameter block
+        std::vector<char> ub;
+        std::vector<trbf::LitF> hl;
+        for (int i = 0; i < ndraws; ++i) {
+            Recording::Draw& s = r.draws[i];
+            const TrbReplayDraw& d = draws[i];
+            if (s.mats_off == (size_t)-1) continue;        // an empty draw
+            double* mats = reinterpret_cast<double*>(r.params + s.mats_off);
+            for (int v = 0; v < s.nviews; ++v) {
+                if (d.modelview) memcpy(mats + (size_t)v * 32, d.modelview + 16 * v, 128);
+                if (d.perspective) memcpy(mats + (size_t)v * 32 + 16, d.perspective + 16 * v, 128);
+            }
+            if (d.modelview) s.mv.assign(d.modelview, d.modelview + (size_t)16 * s.nviews);
+            if (d.uniforms) {
+                if (d.uniform_bytes != s.uni_host_bytes || s.uni_off == (size_t)-1)
+                    return fail(c, TRB_E_ARG, "replay: uniform block size differs from the recorded draw's");
+                rc = build_uniforms(c, s.kind, d.uniforms, d.uniform_bytes, s.nviews, ub);
+                if (rc) return rc;
+                memcpy(r.params + s.uni_off, ub.data(), ub.size());
+                s.uni.assign((const char*)d.uniforms, (const char*)d.uniforms + d.uniform_bytes * s.nviews);
+            }
+            if (s.litf_off != (size_t)-1 && (d.modelview || d.uniforms)) {
+                build_litf(c, s.kind, s.uni.data(), s.mv.data(), s.nviews, hl);
+                memcpy(r.params + s.litf_off, hl.data(), hl.size() * sizeof(trbf::LitF));
+            }
+        }
+    }
+    CU(cudaGraphLaunch(r.exec, c->stream));
+    CU(cudaEventRecord(r.done, c->stream));
+    c->launches += r.launches;
+    return TRB_OK;
+}
+
+int trb_recording_free(TrbCtx* c, TrbRecording h) {
+    if (!c || h == 0 || h > c->recordings.size() || !c->recordings[h - 1]) return fail(c, TRB_E_ARG, "recording_free");
+    NOT_WHILE_RECORDING(c, "recording_free");
+    int rc = check_device(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    recording_destroy(c->recordings[h - 1]);
+    c->recordings[h - 1] = nullptr;
+    return TRB_OK;
+}
+
 int trb_read_color(TrbCtx* c, int view, uint8_t* out) {
+    NOT_WHILE_RECORDING(c, "read_color");
     if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "read_color");
     int rc = do_flush(c);
     if (rc) return rc;
@@ -1612,6 +1928,7 @@ int trb_read_color(TrbCtx* c, int view, uint8_t* out) {
     return TRB_OK;
 }
 int trb_write_color(TrbCtx* c, int view, const uint8_t* bgr) {
+    NOT_WHILE_RECORDING(c, "write_color");
     if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !bgr) return fail(c, TRB_E_ARG, "write_color");
     int rc = do_flush(c);
     if (rc) return rc;
@@ -1621,6 +1938,7 @@ int trb_write_color(TrbCtx* c, int view, const uint8_t* bgr) {
     return TRB_OK;
 }
 int trb_read_depth(TrbCtx* c, int view, double* out) {
+    NOT_WHILE_RECORDING(c, "read_depth");
     if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "read_depth");
     int rc = do_flush(c);
     if (rc) return rc;
@@ -1636,6 +1954,7 @@ int trb_read_depth(TrbCtx* c, int view, double* out) {
     return TRB_OK;
 }
 int trb_readback_wait(TrbCtx* c) {
+    NOT_WHILE_RECORDING(c, "readback_wait");
     if (!c) return TRB_E_ARG;
     CU(cudaSetDevice(c->device));
     for (int i = 0; i < TrbCtx::RB_SLOTS; ++i)
@@ -1650,6 +1969,7 @@ int trb_readback_wait(TrbCtx* c) {
     return TRB_OK;
 }
 int trb_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* depth_out) {
+    NOT_WHILE_RECORDING(c, "readback_async");
     HostSpan host_span_("trb_readback_async");
     if (!c || !c->in_frame) return fail(c, TRB_E_ARG, "readback_async: no frame");
     int rc = do_flush(c);
@@ -1698,6 +2018,7 @@ int trb_readback_async(TrbCtx* c, uint8_t* const* color_out, double* const* dept
     return TRB_OK;
 }
 int trb_read_visibility(TrbCtx* c, int view, uint32_t* out) {
+    NOT_WHILE_RECORDING(c, "read_visibility");
     if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "read_visibility");
     int rc = check_device(c);
     if (rc) return rc;
@@ -1708,6 +2029,7 @@ int trb_read_visibility(TrbCtx* c, int view, uint32_t* out) {
 }
 
 int trb_get_stats(TrbCtx* c, int view, TrbStats* out) {
+    NOT_WHILE_RECORDING(c, "get_stats");
     if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, "get_stats");
     int rc = check_device(c);
     if (rc) return rc;
@@ -1751,6 +2073,7 @@ int trb_get_stats(TrbCtx* c, int view, TrbStats* out) {
 }
 
 int trb_synchronize(TrbCtx* c) {
+    NOT_WHILE_RECORDING(c, "synchronize");
     if (!c) return TRB_E_ARG;
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
@@ -1795,6 +2118,7 @@ int post_plane(TrbCtx* c, int which, int view, uint8_t* dst) {
     return TRB_OK;
 }
 int post_to_host(TrbCtx* c, int which, int view, uint8_t* out, const char* what) {
+    NOT_WHILE_RECORDING(c, "post passes");
     if (!c || !c->in_frame || view < 0 || view >= c->frame.nviews || !out) return fail(c, TRB_E_ARG, what);
     int rc = do_flush(c);
     if (rc) return rc;
@@ -1964,6 +2288,7 @@ int tga_finish(TrbCtx* c, TrbCtx::TgaJob& j, bool wait_copies) {
 extern "C" {
 
 int trb_encode_tga(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity, uint64_t* sizes) {
+    NOT_WHILE_RECORDING(c, "encode_tga");
     if (!c || !c->in_frame || !out || !sizes || which < TRB_IMAGE_COLOR || which > TRB_IMAGE_FINAL)
         return fail(c, TRB_E_ARG, "encode_tga: bad argument");
     uint32_t* offs_dev = nullptr;
@@ -1989,6 +2314,7 @@ int trb_encode_tga(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity,
 // pinned host memory, and the packets themselves come home on the copy stream as soon as the host knows the sizes -
 // at the latest inside the next trb_encode_tga_async / trb_readback_wait.  Two encodes may be in flight.
 int trb_encode_tga_async(TrbCtx* c, int which, uint8_t* const* out, uint64_t capacity, uint64_t* sizes) {
+    NOT_WHILE_RECORDING(c, "encode_tga_async");
     HostSpan host_span_("trb_encode_tga_async");
     if (!c || !c->in_frame || !out || !sizes || which < TRB_IMAGE_COLOR || which > TRB_IMAGE_FINAL)
         return fail(c, TRB_E_ARG, "encode_tga_async: bad argument");
@@ -2041,12 +2367,14 @@ int trb_encode_tga_async(TrbCtx* c, int which, uint8_t* const* out, uint64_t cap
 
 // ---- timing -------------------------------------------------------------------------------------
 int trb_timer_start(TrbCtx* c) {
+    NOT_WHILE_RECORDING(c, "timer_start");
     if (!c) return TRB_E_ARG;
     CU(cudaSetDevice(c->device));
     CU(cudaEventRecord(c->ev_a, c->stream));
     return TRB_OK;
 }
 int trb_timer_stop_ms(TrbCtx* c, float* ms) {
+    NOT_WHILE_RECORDING(c, "timer_stop_ms");
     if (!c || !ms) return TRB_E_ARG;
     CU(cudaSetDevice(c->device));
     CU(cudaEventRecord(c->ev_b, c->stream));
@@ -2055,6 +2383,7 @@ int trb_timer_stop_ms(TrbCtx* c, float* ms) {
     return TRB_OK;
 }
 int trb_profile_enable(TrbCtx* c, int on) {
+    NOT_WHILE_RECORDING(c, "profile_enable");
     if (!c) return TRB_E_ARG;
     cudaSetDevice(c->device);
     prof_collect(c);
@@ -2062,6 +2391,7 @@ int trb_profile_enable(TrbCtx* c, int on) {
     return TRB_OK;
 }
 int trb_profile_read(TrbCtx* c, TrbKernelTime* out, int capacity, int* n_out, int reset) {
+    NOT_WHILE_RECORDING(c, "profile_read");
     if (!c || !n_out) return TRB_E_ARG;
     cudaSetDevice(c->device);
     prof_collect(c);
@@ -2089,6 +2419,7 @@ int trb_device_planes(TrbCtx* c, uint64_t* key_ptr, uint64_t* vis_ptr, uint64_t*
     return TRB_OK;
 }
 int trb_set_triangle_id_base(TrbCtx* c, uint64_t base) {
+    NOT_WHILE_RECORDING(c, "set_triangle_id_base");
     if (!c || base >= 0xFFFFFFF0ull) return fail(c, TRB_E_ARG, "set_triangle_id_base");
     c->next_id = base;
     c->foreign_ids = true;
@@ -2097,6 +2428,7 @@ int trb_set_triangle_id_base(TrbCtx* c, uint64_t base) {
 // The host all-reduces (min) the depth-key plane in place as int64; keys are made signed-sortable
 // for the collective and restored by composite_mask.
 int trb_composite_save_local_depth(TrbCtx* c) {
+    NOT_WHILE_RECORDING(c, "composite_save_local_depth");
     if (!c || !c->in_frame || c->frame.nviews != 1) return fail(c, TRB_E_COMM, "composite: needs a single-view frame");
     int rc = check_device(c);
     if (rc) return rc;
@@ -2112,6 +2444,7 @@ int trb_composite_save_local_depth(TrbCtx* c) {
     return TRB_OK;
 }
 int trb_composite_mask(TrbCtx* c) {
+    NOT_WHILE_RECORDING(c, "composite_mask");
     if (!c || !c->in_frame || c->frame.nviews != 1 || c->zlocal.cap < c->frame.npix * 8)
         return fail(c, TRB_E_COMM, "composite_mask: call composite_save_local_depth first");
     int rc = check_device(c);
@@ -2131,6 +2464,7 @@ int trb_composite_mask(TrbCtx* c) {
     return TRB_OK;
 }
 int trb_composite_finish(TrbCtx* c) {
+    NOT_WHILE_RECORDING(c, "composite_finish");
     if (!c || !c->in_frame || c->frame.nviews != 1) return fail(c, TRB_E_COMM, "composite_finish: needs a single-view frame");
     int rc = check_device(c);
     if (rc) return rc;
@@ -2144,6 +2478,7 @@ int trb_composite_finish(TrbCtx* c) {
     return TRB_OK;
 }
 int trb_ipc_export_planes(TrbCtx* c, void* key_handle, void* vis_handle) {
+    NOT_WHILE_RECORDING(c, "ipc_export_planes");
     if (!c || !c->in_frame || !key_handle || !vis_handle) return fail(c, TRB_E_COMM, "ipc_export_planes: no frame");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
     int rc = check_device(c);
@@ -2166,6 +2501,7 @@ int trb_ipc_close_peers(TrbCtx* c) {
     return TRB_OK;
 }
 int trb_ipc_open_peers(TrbCtx* c, const void* key_handles, const void* vis_handles, int n, int my_rank) {
+    NOT_WHILE_RECORDING(c, "ipc_open_peers");
     if (!c || !c->in_frame || !key_handles || !vis_handles || n < 1 || n > MAX_PEERS || my_rank < 0 || my_rank >= n)
         return fail(c, TRB_E_COMM, "ipc_open_peers: bad argument");
     int rc = check_device(c);
@@ -2193,6 +2529,7 @@ int trb_ipc_open_peers(TrbCtx* c, const void* key_handles, const void* vis_handl
     return TRB_OK;
 }
 int trb_open_peers_raw(TrbCtx* c, const uint64_t* key_ptrs, const uint64_t* vis_ptrs, int n, int my_rank) {
+    NOT_WHILE_RECORDING(c, "open_peers_raw");
     if (!c || !c->in_frame || !key_ptrs || !vis_ptrs || n < 1 || n > MAX_PEERS || my_rank < 0 || my_rank >= n)
         return fail(c, TRB_E_COMM, "open_peers_raw: bad argument");
     trb_ipc_close_peers(c);
@@ -2206,6 +2543,7 @@ int trb_open_peers_raw(TrbCtx* c, const uint64_t* key_ptrs, const uint64_t* vis_
     return TRB_OK;
 }
 int trb_composite_shade_p2p(TrbCtx* c, int y0, int y1) {
+    NOT_WHILE_RECORDING(c, "composite_shade_p2p");
     if (!c || !c->in_frame || c->frame.nviews != 1 || c->peers.n < 1 || y0 < 0 || y1 < y0 || y1 > c->frame.H)
         return fail(c, TRB_E_COMM, "composite_shade_p2p: open the peers first (single-view frame)");
     int rc = check_device(c);
@@ -2316,6 +2654,7 @@ int trb_comm_init(TrbCtx* const* ctxs, int n) {
     return TRB_OK;
 }
 int trb_comm_export(TrbCtx* c, void* blob, size_t blob_bytes) {
+    NOT_WHILE_RECORDING(c, "comm_export");
     if (!c || !blob || blob_bytes < TRB_COMM_BLOB_BYTES) return fail(c, TRB_E_ARG, "comm_export: blob too small");
     if (c->comm.n == 0) {                      // first the local half: flags, frame geometry (rank / size follow in comm_open)
         int rc = comm_prepare(c, 1, 0);
@@ -2333,6 +2672,7 @@ int trb_comm_export(TrbCtx* c, void* blob, size_t blob_bytes) {
     return TRB_OK;
 }
 int trb_comm_open(TrbCtx* c, const void* blobs, int n, int rank) {
+    NOT_WHILE_RECORDING(c, "comm_open");
     if (!c || !blobs || n < 1 || n > MAX_PEERS || rank < 0 || rank >= n) return fail(c, TRB_E_ARG, "comm_open: bad argument");
     if (c->comm.n == 0 || !c->comm.my_flags) return fail(c, TRB_E_COMM, "comm_open: call trb_comm_export on this context first");
     int rc = check_device(c);
@@ -2391,6 +2731,7 @@ int trb_comm_rows(TrbCtx* c, int* y0, int* y1) {
 // One rank's half of a frame's composite, entirely on its stream: publish "my draws are complete", wait for the peers'
 // draws, composite + shade the rows this rank owns, publish "I have finished reading".  Nothing here waits on the host.
 int trb_composite(TrbCtx* c) {
+    NOT_WHILE_RECORDING(c, "composite");
     if (!c || !c->in_frame || c->frame.nviews != 1 || c->comm.n < 1) return fail(c, TRB_E_COMM, "composite: no composite group (trb_comm_init / trb_comm_open)");
     if (c->comm.in_process && c->comm.ev_drawn)
         return fail(c, TRB_E_COMM, "composite: contexts that share a device are composited together, with trb_composite_group");
@@ -2457,6 +2798,7 @@ int trb_composite_group(TrbCtx* const* ctxs, int n) {
     return TRB_OK;
 }
 int trb_set_shade_rows(TrbCtx* c, int y0, int y1) {
+    NOT_WHILE_RECORDING(c, "set_shade_rows");
     if (!c || !c->in_frame || y0 < 0 || y1 < y0 || y1 > c->frame.H) return fail(c, TRB_E_ARG, "set_shade_rows");
     c->shade_row0 = y0;
     c->shade_row1 = y1;

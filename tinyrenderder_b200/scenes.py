@@ -326,6 +326,32 @@ class UploadedScene:
             self.r.free_texture(h)
         self.mesh_h, self.tex_h = {}, {}
 
+    def _item_params(self, it, views, seen_i):
+        """ModelViews and the uniform blocks of one model for every camera: main.cpp:653 (ModelView = view * model),
+        main.cpp:55-69 (light directions through the upper-left 3x3)"""
+        api = self.r.api
+        n = views.shape[0]
+        key, fill, rim = normalized(KEY_LIGHT), normalized(FILL_LIGHT), normalized(RIM_LIGHT)
+        mvs = api.mat4_mul_batch(views, it.model_matrix)
+        if seen_i is not None and not seen_i.all():
+            # a batch draws into every frame: cameras that cull the model get a ModelView of zeros, which sends
+            # every vertex to w = 0 and every triangle to the reject of our_gl.cpp:94 - nothing is drawn there
+            mvs = np.where(seen_i[:, None, None], mvs, 0.0)
+        uni = None
+        if it.kind in (SHADER_PHONG, SHADER_EYE):
+            # PhongUniforms for every view, filled through a numpy view of the ctypes array
+            arr = (PhongUniforms * n)()
+            rec = np.frombuffer(arr, dtype=_PHONG_DTYPE)
+            rec["key"] = api.light_dir_eye_batch(mvs, key)
+            rec["fill"] = api.light_dir_eye_batch(mvs, fill)
+            rec["rim"] = api.light_dir_eye_batch(mvs, rim)
+            rec["nms"] = it.normal_map_strength
+            rec["diffuse"] = self.tex_h.get(id(it.textures.get("diffuse")), 0)
+            rec["normal"] = self.tex_h.get(id(it.textures.get("normal")), 0)
+            rec["specular"] = self.tex_h.get(id(it.textures.get("specular")), 0)
+            uni = arr
+        return mvs, uni
+
     def render(self, views, perspective, cull=True):
         """views: (n,4,4) view matrices.  Mirrors main.cpp:606-730 for every view: begin frame, the model-level
         frustum test (main.cpp:623-624, 647, 680, 706; bug-for-bug), per model ModelView = view*model
@@ -335,37 +361,48 @@ class UploadedScene:
         views = np.asarray(views, dtype=np.float64).reshape(-1, 4, 4)
         n = views.shape[0]
         r.begin_frame(sc.width, sc.height, nviews=n)
-        key, fill, rim = normalized(KEY_LIGHT), normalized(FILL_LIGHT), normalized(RIM_LIGHT)
         seen = visible_items(sc, views, perspective, api) if cull else None
         self.culled = 0 if seen is None else int((~seen).sum())
+        self.drawn_items = []
         for i, it in enumerate(sc.items):
             if seen is not None and not seen[i].any():
                 continue                                  # culled for every camera of the batch: the block is skipped
             if it.snapshot_before:
                 r.depth_snapshot()
-            mvs = api.mat4_mul_batch(views, it.model_matrix)
-            if seen is not None and not seen[i].all():
-                # a batch draws into every frame: cameras that cull the model get a ModelView of zeros, which sends
-                # every vertex to w = 0 and every triangle to the reject of our_gl.cpp:94 - nothing is drawn there
-                mvs = np.where(seen[i][:, None, None], mvs, 0.0)
-            uni = None
-            if it.kind in (SHADER_PHONG, SHADER_EYE):
-                # PhongUniforms for every view, filled through a numpy view of the ctypes array
-                arr = (PhongUniforms * n)()
-                rec = np.frombuffer(arr, dtype=_PHONG_DTYPE)
-                rec["key"] = api.light_dir_eye_batch(mvs, key)
-                rec["fill"] = api.light_dir_eye_batch(mvs, fill)
-                rec["rim"] = api.light_dir_eye_batch(mvs, rim)
-                rec["nms"] = it.normal_map_strength
-                rec["diffuse"] = self.tex_h.get(id(it.textures.get("diffuse")), 0)
-                rec["normal"] = self.tex_h.get(id(it.textures.get("normal")), 0)
-                rec["specular"] = self.tex_h.get(id(it.textures.get("specular")), 0)
-                uni = arr
+            mvs, uni = self._item_params(it, views, None if seen is None else seen[i])
             r.draw(self.mesh_h[id(it.mesh)], mvs, perspective, kind=it.kind, uniforms=uni,
                    ntris=it.mesh.ntris)
+            self.drawn_items.append(i)
             if it.restore_after:
                 r.depth_restore()
         r.end_frame()
+
+    def record(self, views, perspective, cull=True):
+        """The frame loop body above as a frame recording (trb_record_begin / trb_record_end: one CUDA graph launch per
+        frame instead of ~40 kernel launches).  The frame is rendered once by plain calls first, so that every buffer
+        has its size.  Returns the recording; the context holds the rendered frame."""
+        self.render(views, perspective, cull)
+        self.r.record_begin()
+        try:
+            self.render(views, perspective, cull)
+        finally:
+            rec = self.r.record_end()
+        self.recorded_items = list(self.drawn_items)
+        return rec
+
+    def replay(self, recording, views, perspective, cull=True):
+        """The recorded frame for new cameras: same draw calls, new ModelViews / light directions.  A model the new
+        camera culls but the recorded one drew gets a ModelView of zeros (nothing is drawn); a model the recorded camera
+        culled cannot come back - record with cull=False if the orbit needs every model."""
+        sc, api = self.scene, self.r.api
+        views = np.asarray(views, dtype=np.float64).reshape(-1, 4, 4)
+        seen = visible_items(sc, views, perspective, api) if cull else None
+        draws = []
+        for i in self.recorded_items:
+            it = sc.items[i]
+            mvs, uni = self._item_params(it, views, None if seen is None else seen[i])
+            draws.append({"modelview": mvs, "perspective": perspective, "uniforms": uni})
+        self.r.replay(recording, draws)
 
 
 def head_scene(width=800, height=800, n_around=36, n_stacks=35, tex_size=1024, name="c1_head"):
@@ -451,7 +488,7 @@ def shadow_scene(width=2048, height=2048, body_res=(42, 60), ground_quads=32, te
     return Scene(name, width, height, items, 60.0, 0.1, 100.0)
 
 
-def render_shadowed(up, view, perspective, shadow_size=None, bias=2e-3, darkening=0.35, kind=SHADER_SHADOW_PHONG):
+def render_shadowed(up, view, perspective, shadow_size=None, bias=2e-3, darkening=0.35, kind=SHADER_SHADOW_PHONG, release=True):
     """Pass 1: depth-only draw of every model from the light (TRB_SHADER_DEPTH) kept as the shadow map.
     Pass 2: the camera frame with `kind` (SHADOW_PHONG, or GOURAUD / PHONG for the plain variants)."""
     r, sc, api = up.r, up.scene, up.r.api
@@ -459,7 +496,8 @@ def render_shadowed(up, view, perspective, shadow_size=None, bias=2e-3, darkenin
     light_view = api.lookat(LIGHT_POS, [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
     light_proj = api.perspective(40.0, sw / sh, 1.0, 20.0)
     light_vp = api.viewport(0, 0, sw, sh)
-    r.release_shadow_maps()
+    if release:            # (a frame recording releases before it begins: trb_release_shadow_maps is refused inside)
+        r.release_shadow_maps()
     r.begin_frame(sw, sh)
     for it in sc.items:
         r.draw(up.mesh_h[id(it.mesh)], api.mat4_mul(light_view, it.model_matrix), light_proj, kind=SHADER_DEPTH,
