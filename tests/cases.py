@@ -380,6 +380,30 @@ def sub_range_draws(api, r):
     return _grab(r)
 
 
+def soup_duplicates_lit(api, r):
+    """a lit SOUP (no index buffer: vertex 3t + k) that lists every triangle of a small sphere three times, shuffled, drawn
+    as two triangle ranges with PhongShader: every covered pixel is a depth tie between three ids, the first submitted must
+    win it, and its normals / texture coordinates must be those of ITS vertices - also when the backend keeps the soup's
+    vertex arrays in a processing order of its own (mesh_order.cu, TRB_MESH_ORDER_MIN_TRIS)"""
+    sc = scenes.head_scene(200, 160, 16, 12, tex_size=64)
+    m = sc.items[0].mesh
+    tri = m.idx.reshape(-1, 3)
+    rng = np.random.Generator(np.random.PCG64(12))
+    tri = np.concatenate([tri, tri, tri], axis=0)[rng.permutation(3 * tri.shape[0])].reshape(-1)
+    flat = scenes.MeshData(m.pos[tri], m.nrm[tri], m.uv[tri], None, "soup")
+    sc.items[0].mesh = flat
+    up = scenes.UploadedScene(r, sc)
+    view = scenes.head_view(api)[None]
+    pr = api.perspective(sc.fov, 200 / 160, sc.znear, sc.zfar)
+    r.begin_frame(sc.width, sc.height)
+    mvs, uni = up._item_params(sc.items[0], view, None)
+    n = tri.size // 3
+    for a, b in ((0, n // 4), (n // 4, n)):
+        r.draw(up.mesh_h[id(flat)], mvs, pr, kind=sc.items[0].kind, uniforms=uni, first_tri=a, ntris=b - a)
+    r.end_frame()
+    return _grab(r)
+
+
 def indexed_duplicates(api, r):
     """an INDEXED mesh whose index buffer lists every triangle of a small sphere three times, shuffled, drawn as two
     triangle ranges: every covered pixel is a depth tie between three ids from different parts of the buffer, and
@@ -471,7 +495,7 @@ CASES = {
     "depth_only_then_color": depth_only_then_color, "sub_range_draws": sub_range_draws,
     "snapshot_restore_twice": snapshot_restore_twice, "snapshot_signed_zero": snapshot_signed_zero,
     "lit_clip_triangles": lit_clip_triangles, "shadow_small": shadow_small, "gouraud_small": gouraud_small,
-    "orbit_culled": orbit_culled, "indexed_duplicates": indexed_duplicates,
+    "orbit_culled": orbit_culled, "indexed_duplicates": indexed_duplicates, "soup_duplicates_lit": soup_duplicates_lit,
 }
 FULL_SIZE_CASES = {"k7a": k7a, "k7b": k7b, "k7c": k7c, "head_c1": head_c1, "orbit_mid": orbit_mid,
                    "shadow_c2": shadow_c2, "orbit_c3": orbit_c3, "sphere_c4": sphere_c4}

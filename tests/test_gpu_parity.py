@@ -287,7 +287,8 @@ def test_synchronous_draws_match_oracle(cuda_api, port_api, monkeypatch, name):
 
 @pytest.mark.parametrize("env", [{}, {"TRB_WARP_MAX": "0"}, {"TRB_BIN_CAP": "16"}, {"TRB_SYNC_DRAWS": "1"}, {"TRB_DIRECT_AREA": "0"}])
 @pytest.mark.parametrize("name", ["indexed_duplicates", "head_small", "orbit_small", "sub_range_draws", "orbit_culled",
-                                  "snapshot_restore_twice", "shadow_small", "gouraud_small"])
+                                  "snapshot_restore_twice", "shadow_small", "gouraud_small", "soup_mesh_fp32",
+                                  "soup_duplicates_lit"])
 def test_mesh_processing_order_matches_oracle(cuda_api, port_api, monkeypatch, name, env):
     """TRB_MESH_ORDER_MIN_TRIS=1 gives EVERY indexed mesh the Morton processing order that only multi-million-triangle
     meshes get by default (mesh_order.cu): set-up, bin fill, both raster kernels, the direct path and the unbinned fallback

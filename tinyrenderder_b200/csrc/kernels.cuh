@@ -79,6 +79,7 @@ struct DrawDev {               // one draw call, kept until flush (the shade ker
     int kind;
     uint32_t mesh_ntris;       // triangles of the whole mesh (ids of ranges other ranks drew map here too)
     long long mesh_id_base;    // id of mesh triangle g is mesh_id_base + g + 1  (= id_base - first_tri)
+    const uint32_t* inv_perm;  // ordered soup (idx == nullptr): triangle g sits in slot inv_perm[g], vertices 3 * slot + k
 };
 
 __device__ __forceinline__ uint32_t vertex_index(const uint32_t* idx, uint32_t first_tri, uint32_t t, int k) {
@@ -295,7 +296,7 @@ constexpr int DIRECT_AREA_DEFAULT = 16;
 __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(FrameDev f, GeomArgs g, uint2* __restrict__ tribox,
                                                      TriRec* __restrict__ trirec, uint32_t* __restrict__ tile_count,
                                                      int direct_area, uint32_t* __restrict__ direct_list,
-                                                     uint32_t* __restrict__ direct_n) {
+                                                     uint32_t* __restrict__ direct_n, int direct_by_pixel) {
     __shared__ int sh_i[4 * 8];
     __shared__ unsigned sh_w[5 * 8];
     static_assert(TPB / 32 == 8, "block totals are laid out for 8 warps");
@@ -319,8 +320,12 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
             const uint32_t j = slot_position(slot, g.shard_n, g.shard_r, g.shard_shift);
             if (j >= g.nperm) { nm = 0xffffffffu; n0 = n1 = n2 = 0u; return; }   // past the end of the last block
             nm = __ldg(g.perm + j) - g.first_tri;                  // triangle inside the range, or >= ntris (wraps)
-            const uint32_t* q = g.idx_perm + (size_t)j * 3;
-            n0 = __ldg(q); n1 = __ldg(q + 1); n2 = __ldg(q + 2);
+            if (g.idx_perm) {
+                const uint32_t* q = g.idx_perm + (size_t)j * 3;
+                n0 = __ldg(q); n1 = __ldg(q + 1); n2 = __ldg(q + 2);
+            } else {                                               // ordered soup: the vertex arrays are in slot order
+                n0 = 3u * j; n1 = 3u * j + 1u; n2 = 3u * j + 2u;
+            }
         } else {
             nm = slot;
             n0 = vertex_index(g.idx, g.first_tri, slot, 0);
@@ -358,7 +363,13 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
         // hitting the same pixels the two direct passes cost more than the compacted bins of the tile path
         // (config 4: 1.0 ms binned vs 1.55 ms direct at level 9; config 5: 6.3 ms binned vs 2.7 ms direct).
         const bool small_tri = res == SETUP_DRAW && (ts.x1 - ts.x0 + 1) * (ts.y1 - ts.y0 + 1) <= direct_area;
-        const unsigned tkey = small_tri ? (unsigned)((ts.y0 >> TILE_SHIFT) * f.tw + (ts.x0 >> TILE_SHIFT)) : (0x80000000u | lane_id);
+        // "distinct" = tile, or - for a soup that is processed in a coherent order (mesh_order.cu: direct_by_pixel) - first
+        // pixel of the bbox: its warps sit in a handful of tiles but still in different pixels, and its atomics hit lines
+        // that are in L2.  Measured: ordered 100 M soup 18.0 ms with the tile vote (everything binned), 13.5 ms with the
+        // pixel vote, 14.3 ms unordered; the pixel vote on indexed meshes costs config 4 6 % and config 3 1 % (not used).
+        const unsigned long long tkey = !small_tri ? ((1ull << 40) | lane_id)
+                                        : direct_by_pixel ? (((unsigned long long)(unsigned)ts.y0 << 16) | (unsigned)ts.x0)
+                                                          : (unsigned long long)((ts.y0 >> TILE_SHIFT) * f.tw + (ts.x0 >> TILE_SHIFT));
         const unsigned same_tile = __match_any_sync(0xffffffffu, tkey);   // every lane takes part: no short-circuit
         const bool lonely = small_tri && __popc(same_tile) <= 2;
         const unsigned m_lonely = __ballot_sync(0xffffffffu, lonely);
@@ -458,35 +469,53 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
 
 // second half of the direct path: ids of the fragments that sit at a pixel's final depth, over the
 // compacted list of the triangles that were (for a moment at least) nearest somewhere
+__device__ __forceinline__ void direct_resolve_entry(const FrameDev& f, const GeomArgs& g, int view, uint32_t t) {   // t: a slot
+    const VRec* vr = g.vrec + (size_t)view * g.nverts;
+    uint32_t v0, v1, v2;
+    if (g.perm) {
+        const uint32_t j = slot_position(t, g.shard_n, g.shard_r, g.shard_shift);
+        if (g.idx_perm) {
+            const uint32_t* q = g.idx_perm + (size_t)j * 3;
+            v0 = __ldg(q); v1 = __ldg(q + 1); v2 = __ldg(q + 2);
+        } else {
+            v0 = 3u * j; v1 = 3u * j + 1u; v2 = 3u * j + 2u;      // ordered soup
+        }
+    } else {
+        v0 = vertex_index(g.idx, g.first_tri, t, 0); v1 = vertex_index(g.idx, g.first_tri, t, 1); v2 = vertex_index(g.idx, g.first_tri, t, 2);
+    }
+    VRec a = load_vrec(vr + v0), b_ = load_vrec(vr + v1), c = load_vrec(vr + v2);
+    TriSetup ts;
+    setup_triangle(a, b_, c, f.W, f.H, ts);
+    const unsigned long long* zk = f.zkey + (size_t)view * f.npix;
+    uint32_t* vis = f.vis + (size_t)view * f.npix;
+    const uint32_t gid = slot_gid(SlotIds{g.perm, g.id_base - (g.perm ? g.first_tri : 0u), g.shard_n, g.shard_r, g.shard_shift}, t);
+    for (int y = ts.y0; y <= ts.y1; ++y)
+        for (int x = ts.x0; x <= ts.x1; ++x) {
+            double b[3], z;
+            if (!eval_sample(ts, x, y, b, z)) continue;
+            const size_t p = (size_t)y * f.W + x;
+            if (fragment_key(z) == zk[p]) atomicMin(vis + p, gid);   // ties: lowest id = first submitted
+        }
+}
+// One thread per list entry.  The list length is only known on the device.  A context whose draws have had direct
+// candidates (host_seen: mapped memory, read by the host at the next draw) launches STRIDE = false on a grid sized for
+// the whole draw; any other context launches STRIDE = true on a few CTAs, which is correct for any length and costs
+// 3 us instead of 12 us per draw when the list is empty (config 3).  Two instantiations because the loop form costs the
+// 100 M soup 16 % (2.73 vs 2.35 ms) even on the full grid, and a capped grid doubles it.
+template <bool STRIDE>
 __global__ void __launch_bounds__(TPB) k_direct_resolve(FrameDev f, GeomArgs g, const uint32_t* __restrict__ direct_list,
                                                         const uint32_t* __restrict__ direct_n, uint32_t* __restrict__ host_seen) {
-    // one thread per list entry.  The list length is only known on the device: a context whose draws have had direct
-    // candidates (host_seen, mapped memory, read by the host at the next draw) launches a grid sized for the whole draw -
-    // a capped grid doubles the kernel on the 100 M soup (4.5 vs 2.3 ms) -, any other context a small one (an empty list
-    // then costs 3 us instead of 12 us per draw); the stride loop makes either grid correct for any length.
     const int view = blockIdx.y;
     const uint32_t n = direct_n[view];
-    if (n && blockIdx.x == 0 && threadIdx.x == 0) *host_seen = 1u;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * TPB) {
-        const uint32_t t = direct_list[(size_t)view * g.nslots + i];     // a slot
-        const VRec* vr = g.vrec + (size_t)view * g.nverts;
-        const uint32_t* q = g.perm ? g.idx_perm + (size_t)slot_position(t, g.shard_n, g.shard_r, g.shard_shift) * 3 : nullptr;
-        VRec a = load_vrec(vr + (q ? __ldg(q) : vertex_index(g.idx, g.first_tri, t, 0)));
-        VRec b_ = load_vrec(vr + (q ? __ldg(q + 1) : vertex_index(g.idx, g.first_tri, t, 1)));
-        VRec c = load_vrec(vr + (q ? __ldg(q + 2) : vertex_index(g.idx, g.first_tri, t, 2)));
-        TriSetup ts;
-        setup_triangle(a, b_, c, f.W, f.H, ts);
-        const unsigned long long* zk = f.zkey + (size_t)view * f.npix;
-        uint32_t* vis = f.vis + (size_t)view * f.npix;
-        const uint32_t gid = slot_gid(SlotIds{g.perm, g.id_base - (g.perm ? g.first_tri : 0u), g.shard_n, g.shard_r, g.shard_shift}, t);
-        for (int y = ts.y0; y <= ts.y1; ++y)
-            for (int x = ts.x0; x <= ts.x1; ++x) {
-                double b[3], z;
-                if (!eval_sample(ts, x, y, b, z)) continue;
-                const size_t p = (size_t)y * f.W + x;
-                if (fragment_key(z) == zk[p]) atomicMin(vis + p, gid);   // ties: lowest id = first submitted
-            }
+    if (!STRIDE) {
+        const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+        if (i >= n) return;
+        direct_resolve_entry(f, g, view, direct_list[(size_t)view * g.nslots + i]);
+        return;
     }
+    if (n && blockIdx.x == 0 && threadIdx.x == 0) *host_seen = 1u;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * TPB)
+        direct_resolve_entry(f, g, view, direct_list[(size_t)view * g.nslots + i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1577,12 +1606,15 @@ __device__ __forceinline__ bool resolve_winner(const DrawDev* __restrict__ draws
 }
 __device__ __forceinline__ void winner_vertices(const DrawDev* __restrict__ draws, const DrawDev* sm_draws, int draw, uint32_t g0,
                                                 uint32_t vi[3]) {
-    const uint32_t* idx = draw < SHADE_MAX_SM_DRAWS ? sm_draws[draw].idx : draws[draw].idx;
+    const DrawDev* D = draw < SHADE_MAX_SM_DRAWS ? sm_draws + draw : draws + draw;
+    const uint32_t* idx = D->idx;
     if (idx) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(elem_addr<12>(idx, g0));
         vi[0] = __ldg(q); vi[1] = __ldg(q + 1); vi[2] = __ldg(q + 2);
     } else {
-        vi[0] = g0 * 3u; vi[1] = g0 * 3u + 1u; vi[2] = g0 * 3u + 2u;     // implicit soup
+        const uint32_t* inv = D->inv_perm;                               // ordered soup: the triangle's slot
+        const uint32_t s = inv ? __ldg(inv + g0) : g0;
+        vi[0] = s * 3u; vi[1] = s * 3u + 1u; vi[2] = s * 3u + 2u;        // implicit soup
     }
 }
 

@@ -74,8 +74,9 @@ __global__ void __launch_bounds__(TPB) k_morton(const float4* __restrict__ pos4,
         const float ext = l <= h ? from_ordered_bits(h) - lo[k] : 0.0f;
         scale[k] = ext > 0.0f ? 1023.0f / ext : 0.0f;
     }
-    const float4 a = __ldg(pos4 + __ldg(idx + 3 * (size_t)t)), b = __ldg(pos4 + __ldg(idx + 3 * (size_t)t + 1)),
-                 c = __ldg(pos4 + __ldg(idx + 3 * (size_t)t + 2));
+    // idx == nullptr: a triangle soup, triangle t = vertices 3t .. 3t + 2
+    const float4 a = __ldg(pos4 + (idx ? __ldg(idx + 3 * (size_t)t) : 3u * t)), b = __ldg(pos4 + (idx ? __ldg(idx + 3 * (size_t)t + 1) : 3u * t + 1u)),
+                 c = __ldg(pos4 + (idx ? __ldg(idx + 3 * (size_t)t + 2) : 3u * t + 2u));
     const float cen[3] = {(a.x + b.x + c.x) * (1.0f / 3.0f), (a.y + b.y + c.y) * (1.0f / 3.0f), (a.z + b.z + c.z) * (1.0f / 3.0f)};
     unsigned q[3];
     for (int k = 0; k < 3; ++k) {
@@ -96,7 +97,41 @@ __global__ void __launch_bounds__(TPB) k_gather_idx(const uint32_t* __restrict__
     o[0] = __ldg(q); o[1] = __ldg(q + 1); o[2] = __ldg(q + 2);
 }
 
+// A soup shares no vertex, so its VERTEX ARRAYS are put into processing order themselves: slot j's vertices become
+// 3j .. 3j + 2 (the set-up kernel then streams its vertex records instead of gathering them), inv[t] = slot of triangle t
+// (the shade pass finds the vertices of a winning triangle id through it).
+__global__ void __launch_bounds__(TPB) k_permute_soup(const float4* __restrict__ pos_in, const float4* __restrict__ attr_in,
+                                                      const uint32_t* __restrict__ perm, uint32_t ntris, float4* __restrict__ pos_out,
+                                                      float4* __restrict__ attr_out, uint32_t* __restrict__ inv) {
+    const uint32_t v = blockIdx.x * TPB + threadIdx.x;          // a vertex of the ordered arrays
+    if (v >= 3u * ntris) return;
+    const uint32_t j = v / 3u, k = v - 3u * j, t = __ldg(perm + j);
+    const size_t src = 3 * (size_t)t + k;
+    pos_out[v] = __ldg(pos_in + src);
+    attr_out[2 * (size_t)v] = __ldg(attr_in + 2 * src);
+    attr_out[2 * (size_t)v + 1] = __ldg(attr_in + 2 * src + 1);
+    if (k == 0) inv[t] = j;
+}
+
 }  // namespace trbmo
+
+// vertex arrays of a soup in processing order (pos_out / attr_out hold nverts entries; vertices past 3 * ntris are copied
+// as they are) and the inverse permutation; queued on `st`
+cudaError_t trb_soup_order_apply(const float4* pos_in, const float* attr_in, uint32_t nverts, const uint32_t* perm, uint32_t ntris,
+                                 float4* pos_out, float* attr_out, uint32_t* inv_perm, cudaStream_t st) {
+    using namespace trbmo;
+    if (ntris == 0 || ntris > 0x55555555u || 3ull * ntris > nverts) return cudaErrorInvalidValue;
+    const uint32_t used = 3u * ntris;
+    k_permute_soup<<<(used + TPB - 1) / TPB, TPB, 0, st>>>(pos_in, reinterpret_cast<const float4*>(attr_in), perm, ntris, pos_out,
+                                                          reinterpret_cast<float4*>(attr_out), inv_perm);
+    if (nverts > used) {
+        cudaError_t e = cudaMemcpyAsync(pos_out + used, pos_in + used, (size_t)(nverts - used) * 16, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(attr_out + (size_t)used * 8, attr_in + (size_t)used * 8, (size_t)(nverts - used) * 32, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaGetLastError();
+}
 
 // scratch the build needs besides its outputs: [keys_in | keys_out | vals_in | box (256 B) | cub temp]
 size_t trb_mesh_order_scratch_bytes(uint32_t ntris) {
@@ -130,6 +165,6 @@ cudaError_t trb_mesh_order_build(const float4* pos4, uint32_t nverts, const uint
     e = cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, (const uint32_t*)keys_in, keys_out, (const uint32_t*)vals_in, perm_out,
                                         (int)ntris, 0, 30, st);
     if (e != cudaSuccess) return e;
-    k_gather_idx<<<tb, TPB, 0, st>>>(idx, perm_out, ntris, idx_perm_out);
+    if (idx) k_gather_idx<<<tb, TPB, 0, st>>>(idx, perm_out, ntris, idx_perm_out);
     return cudaGetLastError();
 }

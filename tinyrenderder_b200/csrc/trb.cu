@@ -21,6 +21,8 @@ using namespace trbk;
 size_t trb_mesh_order_scratch_bytes(uint32_t ntris);
 cudaError_t trb_mesh_order_build(const float4* pos4, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint32_t* perm_out,
                                  uint32_t* idx_perm_out, void* scratch, size_t scratch_bytes, int sms, cudaStream_t st);
+cudaError_t trb_soup_order_apply(const float4* pos_in, const float* attr_in, uint32_t nverts, const uint32_t* perm, uint32_t ntris,
+                                 float4* pos_out, float* attr_out, uint32_t* inv_perm, cudaStream_t st);
 
 namespace {
 
@@ -224,6 +226,9 @@ struct Mesh {
     // indices are idx_perm[3j..3j+2]; nullptr for small meshes (their vertex records stay in L2 whatever the order)
     uint32_t* perm = nullptr;
     uint32_t* idx_perm = nullptr;
+    // a large SOUP (idx == nullptr) has its vertex arrays themselves in processing order: slot j = vertices 3j .. 3j + 2
+    // (idx_perm stays nullptr), inv_perm[t] = slot of triangle t for the shade pass.  Every draw of it runs over the slots.
+    uint32_t* inv_perm = nullptr;
 };
 struct Tex {
     uint8_t* px = nullptr;
@@ -385,6 +390,7 @@ struct TrbCtx {
     uint64_t launches = 0;
     int big_ns = BIG_NS_DEFAULT, small_min = SMALL_MIN_DEFAULT, large_ns = LARGE_NS_DEFAULT;
     int direct_area = DIRECT_AREA_DEFAULT;
+    int direct_by_pixel = 1;             // ordered soups: the direct path's warp vote looks at pixels, not tiles (TRB_DIRECT_BY_PIXEL=0: tiles)
     uint32_t warp_max = WARP_MAX_DEFAULT;
     int rw_blocks = RW_BLOCKS_DEFAULT;   // k_raster_warp instantiation (resident CTAs per SM the registers are sized for)
     bool shade_exact = false;   // true: all-fp64 lighting (exact.cuh); false: fp32 lighting (fastshade.cuh)
@@ -740,14 +746,17 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         const dim3 sgrid((ndslots + TPB * SETUP_CHUNKS - 1) / (TPB * SETUP_CHUNKS), f.nviews);
         k_setup_count<<<sgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
                                                      c->counts_p, c->direct_area, c->direct_list.as<uint32_t>(),
-                                                     c->direct_n_p);
+                                                     c->direct_n_p, (c->direct_by_pixel && g.perm && !g.idx_perm) ? 1 : 0);
     }
     if (c->direct_area > 0) {
         // full grid once a draw of this context has had direct candidates (mapped flag, never waited for), else a few CTAs
-        const dim3 dgrid(c->host_total[9] ? tgrid.x : std::min<unsigned>(tgrid.x, std::max(1u, (unsigned)c->sms * 4 / (unsigned)f.nviews)),
-                         f.nviews);
         Launch L(c, "k_direct_resolve");
-        k_direct_resolve<<<dgrid, TPB, 0, c->stream>>>(f, g, c->direct_list.as<uint32_t>(), c->direct_n_p, c->host_total_dev + 9);
+        if (c->host_total[9]) {
+            k_direct_resolve<false><<<tgrid, TPB, 0, c->stream>>>(f, g, c->direct_list.as<uint32_t>(), c->direct_n_p, c->host_total_dev + 9);
+        } else {
+            const dim3 dgrid(std::min<unsigned>(tgrid.x, std::max(1u, (unsigned)c->sms * 4 / (unsigned)f.nviews)), f.nviews);
+            k_direct_resolve<true><<<dgrid, TPB, 0, c->stream>>>(f, g, c->direct_list.as<uint32_t>(), c->direct_n_p, c->host_total_dev + 9);
+        }
     }
     CU(cudaGetLastError());
     // item list of the split warp kernel: sized from what recent draws asked for (never waited for); a draw that needs
@@ -1033,6 +1042,7 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_SMALL_MIN")) c->small_min = std::max(1, atoi(e));
     if (const char* e = getenv("TRB_LARGE_NS")) c->large_ns = std::max(1, atoi(e));
     if (const char* e = getenv("TRB_DIRECT_AREA")) c->direct_area = std::max(0, atoi(e));
+    if (const char* e = getenv("TRB_DIRECT_BY_PIXEL")) c->direct_by_pixel = atoi(e) != 0;
     if (const char* e = getenv("TRB_WARP_MAX")) c->warp_max = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("TRB_RW_BLOCKS")) c->rw_blocks = atoi(e);
     if (const char* e = getenv("TRB_SHADE_EXACT")) c->shade_exact = atoi(e) != 0;
@@ -1084,6 +1094,7 @@ int trb_destroy(TrbCtx* c) {
             if (m.idx) cudaFree(m.idx);
             if (m.perm) cudaFree(m.perm);
             if (m.idx_perm) cudaFree(m.idx_perm);
+            if (m.inv_perm) cudaFree(m.inv_perm);
         }
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
@@ -1189,12 +1200,12 @@ int upload_pinned(TrbCtx* c, void** dev, const void* src, size_t bytes) {
 // processing order of a freshly uploaded large indexed mesh, queued on the upload stream behind its arrays
 int build_mesh_order(TrbCtx* c, Mesh& m) {
     const uint64_t ntris = m.nidx / 3;
-    if (!m.idx || c->order_min_tris == 0 || ntris < c->order_min_tris || ntris > 0x7fffffffull) return TRB_OK;
+    if (c->order_min_tris == 0 || ntris < c->order_min_tris || ntris > 0x55555555ull || ntris == 0) return TRB_OK;
     const size_t sbytes = trb_mesh_order_scratch_bytes((uint32_t)ntris);
     void* scratch = nullptr;
     cudaEvent_t w0 = nullptr, w1 = nullptr, w2 = nullptr;
     CU(c->cache.get((void**)&m.perm, ntris * 4, &w0, c->upload_stream));
-    CU(c->cache.get((void**)&m.idx_perm, m.nidx * 4, &w1, c->upload_stream));
+    if (m.idx) CU(c->cache.get((void**)&m.idx_perm, m.nidx * 4, &w1, c->upload_stream));
     CU(c->cache.get(&scratch, sbytes, &w2, c->upload_stream));
     if (w0) CU(cudaStreamWaitEvent(c->upload_stream, w0, 0));
     if (w1) CU(cudaStreamWaitEvent(c->upload_stream, w1, 0));
@@ -1204,6 +1215,26 @@ int build_mesh_order(TrbCtx* c, Mesh& m) {
         CU(trb_mesh_order_build(m.pos4, m.nverts, m.idx, (uint32_t)ntris, m.perm, m.idx_perm, scratch, sbytes, c->sms, c->upload_stream));
     }
     c->cache.put(scratch, sbytes, c->upload_stream);
+    if (!m.idx) {
+        // soup: the vertex arrays go into processing order themselves (second copies, the first ones are recycled)
+        float4* pos2 = nullptr;
+        float* attr2 = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        CU(c->cache.get((void**)&pos2, (size_t)m.nverts * 16, &e0, c->upload_stream));
+        CU(c->cache.get((void**)&attr2, (size_t)m.nverts * 32, &e1, c->upload_stream));
+        CU(c->cache.get((void**)&m.inv_perm, ntris * 4, &e2, c->upload_stream));
+        if (e0) CU(cudaStreamWaitEvent(c->upload_stream, e0, 0));
+        if (e1) CU(cudaStreamWaitEvent(c->upload_stream, e1, 0));
+        if (e2) CU(cudaStreamWaitEvent(c->upload_stream, e2, 0));
+        {
+            Launch L(c, "soup_order", c->upload_stream, /*kernel=*/false);
+            CU(trb_soup_order_apply(m.pos4, m.attr8, m.nverts, m.perm, (uint32_t)ntris, pos2, attr2, m.inv_perm, c->upload_stream));
+        }
+        c->cache.put(m.pos4, (size_t)m.nverts * 16, c->upload_stream);
+        c->cache.put(m.attr8, (size_t)m.nverts * 32, c->upload_stream);
+        m.pos4 = pos2;
+        m.attr8 = attr2;
+    }
     return TRB_OK;
 }
 // everything uploaded so far becomes visible to the render stream
@@ -1322,6 +1353,7 @@ int trb_free_mesh(TrbCtx* c, TrbMesh h) {
     if (m.idx) c->cache.put(m.idx, m.nidx * 4, c->stream);
     if (m.perm) c->cache.put(m.perm, m.nidx / 3 * 4, c->stream);
     if (m.idx_perm) c->cache.put(m.idx_perm, m.nidx * 4, c->stream);
+    if (m.inv_perm) c->cache.put(m.inv_perm, m.nidx / 3 * 4, c->stream);
     m = Mesh();
     return TRB_OK;
 }
@@ -1530,7 +1562,7 @@ int draw_mesh(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int k
     g.id_base = (uint32_t)c->next_id;
     g.vrec = vrec;
     // the mesh's processing order, unless the range is a small part of the mesh (the draw visits every slot of the mesh)
-    const bool ordered = shard_order || (m.perm && ntris * 16 >= mesh_tris);
+    const bool ordered = shard_order || (m.perm && (m.inv_perm || ntris * 16 >= mesh_tris));   // an ordered soup has no other order left
     g.perm = ordered ? m.perm : nullptr;
     g.idx_perm = ordered ? m.idx_perm : nullptr;
     g.nslots = shard_order ? share_slots : ordered ? (uint32_t)mesh_tris : g.ntris;
@@ -1547,6 +1579,7 @@ int draw_mesh(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int k
     d.first_tri = g.first_tri;
     d.nverts = g.nverts;
     d.idx = m.idx;
+    d.inv_perm = m.inv_perm;
     d.attr8 = m.attr8;
     d.vrec = vrec;
     d.mats = mats;
