@@ -285,6 +285,85 @@ int main(int argc, char** argv) {
 
 
 @pytest.mark.gpu
+def test_views_recording_replays_for_other_cameras(assets, tmp_path, built):
+    """gl_record_views_begin / gl_record_views_end / gl_replay_views: a batch (head, z snapshot, eyes, restore) captured as
+    one CUDA graph per context and re-run for other cameras gives the frames the plain calls give - on one context and on
+    two (cameras split in blocks)"""
+    d, _ = assets
+    src = tmp_path / "record.cpp"
+    src.write_text(r'''#include <our_gl.h>
+#include <model.h>
+#include <model_manager.h>
+#include <shaders.h>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+static void dump(const std::string& name, int nviews) {
+    for (int k = 0; k < nviews; ++k) {
+        TGAImage fb;
+        gl_read_view(k, fb);
+        std::ofstream c(name + std::to_string(k) + ".bgr", std::ios::binary);
+        c.write((const char*)fb.buffer(), (std::streamsize)fb.width() * fb.height() * 3);
+        std::ofstream z(name + std::to_string(k) + ".z", std::ios::binary);
+        z.write((const char*)zbuffer.data(), (std::streamsize)zbuffer.size() * sizeof(double));
+    }
+}
+int main(int argc, char** argv) {
+    const std::string dir = argv[1], out = argv[2];
+    const int ndev = atoi(argv[3]);
+    if (ndev > 1) gl_set_devices(std::vector<int>((size_t)ndev, 0));
+    const int W = 320, H = 200;
+    auto head = ModelManager::getInstance().loadModel(dir + "/head.obj");
+    auto eyes = ModelManager::getInstance().loadModel(dir + "/eyes.obj");
+    if (!head || !eyes) return 2;
+    const vec3 key{1.0, 1.2, 1.0}, fill{-1.0, 0.3, 0.5}, rim{0.0, 0.8, -1.0}, center{0.0, 0.0, 0.0}, up{0.0, 1.0, 0.0};
+    const vec3 cams[2][3] = {{vec3{1.0, 1.0, 3.0}, vec3{-2.0, 0.5, 2.5}, vec3{0.3, 2.2, 2.0}},
+                             {vec3{2.0, 0.2, 2.0}, vec3{-1.0, 1.5, 2.8}, vec3{0.1, -1.0, 3.0}}};
+    init_perspective(60.0, (double)W / H, 0.1, 100.0);
+    init_viewport(0, 0, W, H);
+    std::vector<mat<4, 4>> views[2];
+    for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < 3; ++k) { lookat(cams[s][k], center, up); views[s].push_back(ModelView); }
+    auto batch = [&](const std::vector<mat<4, 4>>& v) {
+        gl_begin_views(v, W, H);
+        gl_draw_model_views(*head, 1, mat<4, 4>::identity(), key, fill, rim, 1.0);
+        gl_zbuffer_snapshot();
+        gl_draw_model_views(*eyes, 2, mat<4, 4>::identity(), key, fill, rim, 1.0);
+        TGAImage none;
+        gl_zbuffer_restore(none);
+    };
+    batch(views[1]); dump(out + "/plainB", 3);
+    batch(views[0]); dump(out + "/plainA", 3);          // also the warm-up of the recording
+    gl_record_views_begin();
+    batch(views[0]);
+    const int rec = gl_record_views_end();
+    dump(out + "/recA", 3);
+    gl_replay_views(rec, views[1]); dump(out + "/repB", 3);
+    gl_replay_views(rec, views[0]); dump(out + "/repA", 3);
+    std::cout << "ok" << std::endl;
+    return 0;
+}
+''')
+    host = os.path.join(ROOT, "tinyrenderder_b200", "host")
+    exe = str(tmp_path / "record")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", host, str(src)] +
+                          [os.path.join(host, f) for f in ("our_gl.cpp", "model.cpp", "model_manager.cpp", "tgaimage.cpp")] +
+                          ["-L", os.path.join(ROOT, "tinyrenderder_b200"), "-ltrb",
+                           "-Wl,-rpath," + os.path.join(ROOT, "tinyrenderder_b200"), "-o", exe])
+    for ndev in (1, 2):
+        out = tmp_path / ("record_out%d" % ndev)
+        out.mkdir()
+        res = subprocess.run([exe, d, str(out), str(ndev)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        for a, b in (("plainA", "recA"), ("plainB", "repB"), ("plainA", "repA")):
+            for k in range(3):
+                for ext in ("bgr", "z"):
+                    x = open(out / ("%s%d.%s" % (a, k, ext)), "rb").read()
+                    y = open(out / ("%s%d.%s" % (b, k, ext)), "rb").read()
+                    assert x == y and len(x) > 0, (ndev, a, b, k, ext)
+
+
+@pytest.mark.gpu
 def test_two_contexts_from_cpp_equal_one(assets, tmp_path, built):
     """gl_set_devices: the C++ host layer driving two contexts (both on GPU 0 here).  A batch of cameras is split over
     the contexts in blocks (config 3, nothing exchanged); one picture is split by triangle ranges and put together by

@@ -367,9 +367,11 @@ __global__ void __launch_bounds__(TPB, TRB_SETUP_MIN_BLOCKS) k_setup_count(Frame
         // pixel of the bbox: its warps sit in a handful of tiles but still in different pixels, and its atomics hit lines
         // that are in L2.  Measured: ordered 100 M soup 18.0 ms with the tile vote (everything binned), 13.5 ms with the
         // pixel vote, 14.3 ms unordered; the pixel vote on indexed meshes costs config 4 6 % and config 3 1 % (not used).
-        const unsigned long long tkey = !small_tri ? ((1ull << 40) | lane_id)
-                                        : direct_by_pixel ? (((unsigned long long)(unsigned)ts.y0 << 16) | (unsigned)ts.x0)
-                                                          : (unsigned long long)((ts.y0 >> TILE_SHIFT) * f.tw + (ts.x0 >> TILE_SHIFT));
+        // (31-bit keys: two pixels of a frame beyond 2^31 pixels may alias, which only makes lanes look less lonely;
+        // a 64-bit MATCH costs the set-up kernel 14 % on configs 3 and 4)
+        const unsigned tkey = !small_tri ? (0x80000000u | lane_id)
+                              : direct_by_pixel ? (((unsigned)ts.y0 * (unsigned)f.W + (unsigned)ts.x0) & 0x7fffffffu)
+                                                : (unsigned)((ts.y0 >> TILE_SHIFT) * f.tw + (ts.x0 >> TILE_SHIFT));
         const unsigned same_tile = __match_any_sync(0xffffffffu, tkey);   // every lane takes part: no short-circuit
         const bool lonely = small_tri && __popc(same_tile) <= 2;
         const unsigned m_lonely = __ballot_sync(0xffffffffu, lonely);
@@ -1569,50 +1571,46 @@ __device__ __forceinline__ const void* elem_addr(const void* base, uint32_t i) {
 }
 
 // id -> (draw, triangle of the draw's mesh).  false: a winner of another rank's mesh that this context does not hold.
-__device__ __forceinline__ bool resolve_winner(const DrawDev* __restrict__ draws, int ndraws, const DrawDev* sm_draws,
-                                               uint32_t id, int& draw, uint32_t& g0) {
-    constexpr int MAX_SM_DRAWS = SHADE_MAX_SM_DRAWS;
+// `tab` is the draw table: the CTA's shared-memory copy when the frame has at most SHADE_MAX_SM_DRAWS draws (one level
+// less in the dependent chain id -> draw -> indices -> records -> texels), else the table in global memory - never a
+// per-access choice between the two, which would turn every field read into a generic load.
+__device__ __forceinline__ bool resolve_winner(const DrawDev* tab, int ndraws, uint32_t id, int& draw, uint32_t& g0) {
     int lo = 0;                   // last draw with id_base < id (bases ascend)
     if (ndraws <= 8) {            // a frame loop's handful of draws: count instead of bisecting
         #pragma unroll 1
-        for (int d = 1; d < ndraws; ++d) lo += sm_draws[d].id_base < id ? 1 : 0;
+        for (int d = 1; d < ndraws; ++d) lo += tab[d].id_base < id ? 1 : 0;
     } else {
         int hi = ndraws - 1;
         while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;
-            const uint32_t bse = mid < MAX_SM_DRAWS ? sm_draws[mid].id_base : draws[mid].id_base;
-            if (bse < id) lo = mid; else hi = mid - 1;
+            if (tab[mid].id_base < id) lo = mid; else hi = mid - 1;
         }
     }
-    // the draw table sits in shared memory: one level less in the dependent chain id -> draw -> indices -> records -> texels
-    const DrawDev* D = lo < MAX_SM_DRAWS ? sm_draws + lo : draws + lo;
-    uint32_t t = id - D->id_base - 1u;                   // triangle inside the range this context drew
-    uint32_t first = D->first_tri;
-    if (t >= D->ntris) {
+    uint32_t t = id - tab[lo].id_base - 1u;              // triangle inside the range this context drew
+    uint32_t first = tab[lo].first_tri;
+    if (t >= tab[lo].ntris) {
         // a winner another rank rasterised (sort-last composite): find the draw whose MESH holds it
         int found = -1;
         for (int d = 0; d < ndraws && found < 0; ++d) {
-            const long long g = (long long)id - draws[d].mesh_id_base - 1;
-            if (g >= 0 && g < (long long)draws[d].mesh_ntris) found = d;
+            const long long g = (long long)id - tab[d].mesh_id_base - 1;
+            if (g >= 0 && g < (long long)tab[d].mesh_ntris) found = d;
         }
         if (found < 0) return false;                     // not ours to shade
         lo = found;
-        first = draws[found].first_tri;
-        t = (uint32_t)((long long)id - draws[found].mesh_id_base - 1) - first;  // may wrap: first_tri + t is exact mod 2^32
+        first = tab[found].first_tri;
+        t = (uint32_t)((long long)id - tab[found].mesh_id_base - 1) - first;  // may wrap: first_tri + t is exact mod 2^32
     }
     draw = lo;
     g0 = first + t;                                      // triangle index in the mesh
     return true;
 }
-__device__ __forceinline__ void winner_vertices(const DrawDev* __restrict__ draws, const DrawDev* sm_draws, int draw, uint32_t g0,
-                                                uint32_t vi[3]) {
-    const DrawDev* D = draw < SHADE_MAX_SM_DRAWS ? sm_draws + draw : draws + draw;
-    const uint32_t* idx = D->idx;
+__device__ __forceinline__ void winner_vertices(const DrawDev* tab, int draw, uint32_t g0, uint32_t vi[3]) {
+    const uint32_t* idx = tab[draw].idx;
     if (idx) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(elem_addr<12>(idx, g0));
         vi[0] = __ldg(q); vi[1] = __ldg(q + 1); vi[2] = __ldg(q + 2);
     } else {
-        const uint32_t* inv = D->inv_perm;                               // ordered soup: the triangle's slot
+        const uint32_t* inv = tab[draw].inv_perm;                        // ordered soup: the triangle's slot
         const uint32_t s = inv ? __ldg(inv + g0) : g0;
         vi[0] = s * 3u; vi[1] = s * 3u + 1u; vi[2] = s * 3u + 2u;        // implicit soup
     }
@@ -1620,11 +1618,10 @@ __device__ __forceinline__ void winner_vertices(const DrawDev* __restrict__ draw
 
 // one visible pixel (x, y) of `view`, p = x + y*W: its winner is triangle g0 (vertices i0, i1, i2) of draw `draw`
 template <bool C2, bool FAST>
-__device__ __forceinline__ void shade_resolved(const FrameDev& f, const DrawDev* __restrict__ draws, const DrawDev* sm_draws,
-                                               int view, unsigned long long p, int x, int y, int draw, uint32_t g0,
-                                               uint32_t i0, uint32_t i1, uint32_t i2) {
+__device__ __forceinline__ void shade_resolved(const FrameDev& f, const DrawDev* tab, int view, unsigned long long p, int x, int y,
+                                               int draw, uint32_t g0, uint32_t i0, uint32_t i1, uint32_t i2) {
     const size_t gp = (size_t)view * f.npix + p;
-    const DrawDev D = draw < SHADE_MAX_SM_DRAWS ? sm_draws[draw] : draws[draw];
+    const DrawDev D = tab[draw];
     const VRec* vr = D.vrec + (size_t)view * D.nverts;
     const VRec va = load_vrec(reinterpret_cast<const VRec*>(elem_addr<32>(vr, i0))),
                vb = load_vrec(reinterpret_cast<const VRec*>(elem_addr<32>(vr, i1))),
@@ -1698,13 +1695,20 @@ __device__ __forceinline__ void shade_resolved(const FrameDev& f, const DrawDev*
     }
 }
 template <bool C2, bool FAST>
-__device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
-                                            const DrawDev* sm_draws, int view, unsigned long long p, int x, int y, uint32_t id) {
+__device__ __forceinline__ void shade_pixel_tab(const FrameDev& f, const DrawDev* tab, int ndraws, int view, unsigned long long p,
+                                                int x, int y, uint32_t id) {
     int draw;
     uint32_t g0, vi[3];
-    if (!resolve_winner(draws, ndraws, sm_draws, id, draw, g0)) return;
-    winner_vertices(draws, sm_draws, draw, g0, vi);
-    shade_resolved<C2, FAST>(f, draws, sm_draws, view, p, x, y, draw, g0, vi[0], vi[1], vi[2]);
+    if (!resolve_winner(tab, ndraws, id, draw, g0)) return;
+    winner_vertices(tab, draw, g0, vi);
+    shade_resolved<C2, FAST>(f, tab, view, p, x, y, draw, g0, vi[0], vi[1], vi[2]);
+}
+template <bool C2, bool FAST>
+__device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
+                                            const DrawDev* sm_draws, int view, unsigned long long p, int x, int y, uint32_t id) {
+    // ONE table per frame: the shared-memory copy, or - frames with more draws than it holds (long immediate-mode
+    // frames) - the table in global memory
+    shade_pixel_tab<C2, FAST>(f, ndraws <= SHADE_MAX_SM_DRAWS ? sm_draws : draws, ndraws, view, p, x, y, id);
 }
 
 // The flush picks its kernel on the device (no host round trip): sparse frames (configs 4, 5) shade

@@ -31,7 +31,7 @@ namespace {
 // texture is freed): a replay checks that it has not moved since the recording ended.  While a thread records, buffers
 // may not grow (growth synchronises the stream, which a capturing stream cannot): the frame is rendered once first.
 std::atomic<uint64_t> g_generation{0};
-thread_local bool t_recording = false;
+thread_local int t_recording = 0;      // contexts recording on this thread (the host layer records on several at once)
 
 struct DevBuf {
     void* p = nullptr;
@@ -1082,7 +1082,7 @@ int trb_destroy(TrbCtx* c) {
         c->rec->graph = g;
         recording_destroy(c->rec);
         c->rec = nullptr;
-        t_recording = false;
+        if (t_recording > 0) --t_recording;
         (void)cudaGetLastError();
     }
     cudaStreamSynchronize(c->stream);
@@ -1839,7 +1839,7 @@ int trb_record_begin(TrbCtx* c) {
     }
     c->rec = r;
     c->launches_at_record = c->launches;
-    t_recording = true;
+    ++t_recording;
     return TRB_OK;
 }
 
@@ -1858,7 +1858,7 @@ int trb_record_end(TrbCtx* c, TrbRecording* out) {
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     c->rec = nullptr;
-    t_recording = false;
+    if (t_recording > 0) --t_recording;
     if (!rc && e == cudaSuccess && g) e = cudaGraphInstantiate(&r->exec, g, 0);
     r->graph = g;
     if (rc || e != cudaSuccess || !r->exec) {

@@ -39,6 +39,13 @@ struct Backend {
     size_t view0 = 0;            // gl_begin_views: first global frame index of this context's block
     struct Handles { std::uint64_t mesh = 0, diffuse = 0, normal = 0, specular = 0; };
     std::map<const Model*, Handles> models;   // contexts 1..n-1 keep their copies of the models here (context 0: Model::dev_*)
+    // frame recordings of a views batch (gl_record_views_begin .. gl_replay_views): per recording the library's handle and,
+    // per gl_draw_model_views call, what is needed to compute the call's matrices / uniforms for other cameras
+    struct RecDraw { int kind; double mm[16], pr[16], kw[3], fw[3], rw[3], nms; Handles h; };
+    struct Rec { std::uint64_t handle = 0; size_t nviews = 0; std::vector<RecDraw> draws; };
+    std::vector<Rec> recs;
+    bool recording = false;
+    Rec pending;
 };
 std::vector<Backend>& BS() {
     static std::vector<Backend> v(1);
@@ -430,6 +437,35 @@ void gl_composite_ao(TGAImage& final_result) {
     std::memcpy(final_result.buffer(), c.data(), c.size());
 }
 
+namespace {
+// what one gl_draw_model_views call passes to trb_draw_batch for the cameras `views` (row-major, n x 16)
+void view_params(const std::vector<double>& views, const Backend::RecDraw& d, std::vector<double>& mvs, std::vector<double>& prs,
+                 std::vector<TrbPhongUniforms>& u) {
+    const int n = (int)(views.size() / 16);
+    mvs.resize((size_t)n * 16);
+    prs.resize((size_t)n * 16);
+    trb_mat4_mul_batch(views.data(), n, d.mm, mvs.data());               // ModelView_i = view_i * model (main.cpp:653)
+    for (int v = 0; v < n; ++v) std::memcpy(&prs[(size_t)v * 16], d.pr, sizeof(d.pr));
+    std::vector<double> ke((size_t)n * 3), fe((size_t)n * 3), re((size_t)n * 3);
+    trb_light_dir_eye_batch(mvs.data(), n, d.kw, ke.data());             // initLightDirections per view
+    trb_light_dir_eye_batch(mvs.data(), n, d.fw, fe.data());
+    trb_light_dir_eye_batch(mvs.data(), n, d.rw, re.data());
+    u.resize((size_t)n);
+    for (int v = 0; v < n; ++v) {
+        std::memset(&u[v], 0, sizeof(TrbPhongUniforms));
+        for (int i = 0; i < 3; ++i) {
+            u[v].key_dir_eye[i] = ke[(size_t)v * 3 + i];
+            u[v].fill_dir_eye[i] = fe[(size_t)v * 3 + i];
+            u[v].rim_dir_eye[i] = re[(size_t)v * 3 + i];
+        }
+        u[v].normal_map_strength = d.nms;
+        u[v].diffuse = d.h.diffuse;
+        u[v].normal = d.h.normal;
+        u[v].specular = d.h.specular;
+    }
+}
+}  // namespace
+
 void gl_begin_views(const std::vector<mat<4, 4>>& views, int width, int height) {
     if (views.empty()) throw std::runtime_error("tinyrenderder-b200: gl_begin_views needs at least one view");
     zbuffer.assign((size_t)width * height, std::numeric_limits<double>::infinity());
@@ -477,30 +513,68 @@ void gl_draw_model_views(const Model& model, int kind, const mat<4, 4>& model_ma
         Backend& b = BS()[k];
         if (!b.frame || b.views.empty()) continue;
         const Backend::Handles h = handles_of(k, model);
-        const int n = (int)(b.views.size() / 16);
-        std::vector<double> mvs((size_t)n * 16), prs((size_t)n * 16);
-        trb_mat4_mul_batch(b.views.data(), n, mm, mvs.data());            // ModelView_i = view_i * model (main.cpp:653)
-        for (int v = 0; v < n; ++v) std::memcpy(&prs[(size_t)v * 16], pr, sizeof(pr));
-        std::vector<double> ke((size_t)n * 3), fe((size_t)n * 3), re((size_t)n * 3);
-        trb_light_dir_eye_batch(mvs.data(), n, kw, ke.data());            // initLightDirections per view
-        trb_light_dir_eye_batch(mvs.data(), n, fw, fe.data());
-        trb_light_dir_eye_batch(mvs.data(), n, rw, re.data());
-        std::vector<TrbPhongUniforms> u((size_t)n);
-        for (int v = 0; v < n; ++v) {
-            std::memset(&u[v], 0, sizeof(TrbPhongUniforms));
-            for (int i = 0; i < 3; ++i) {
-                u[v].key_dir_eye[i] = ke[(size_t)v * 3 + i];
-                u[v].fill_dir_eye[i] = fe[(size_t)v * 3 + i];
-                u[v].rim_dir_eye[i] = re[(size_t)v * 3 + i];
-            }
-            u[v].normal_map_strength = normal_map_strength;
-            u[v].diffuse = h.diffuse;
-            u[v].normal = h.normal;
-            u[v].specular = h.specular;
-        }
+        std::vector<double> mvs, prs;
+        std::vector<TrbPhongUniforms> u;
+        Backend::RecDraw rd;
+        rd.kind = kind;
+        std::memcpy(rd.mm, mm, sizeof(mm)); std::memcpy(rd.pr, pr, sizeof(pr));
+        std::memcpy(rd.kw, kw, sizeof(kw)); std::memcpy(rd.fw, fw, sizeof(fw)); std::memcpy(rd.rw, rw, sizeof(rw));
+        rd.nms = normal_map_strength;
+        rd.h = h;
+        view_params(b.views, rd, mvs, prs, u);
+        if (b.recording) b.pending.draws.push_back(rd);
         CK(trb_set_viewport(b.ctx, vp));
         CK(trb_draw_batch(b.ctx, h.mesh, mvs.data(), prs.data(), kind, u.data(), sizeof(TrbPhongUniforms), 0,
                           (uint64_t)model.nfaces()));
+    }
+}
+
+// ---- frame recordings of a views batch: trb_record_begin / trb_record_end / trb_replay on every context ------------
+void gl_record_views_begin() {
+    for (Backend& b : BS()) {
+        if (b.recording) throw std::runtime_error("tinyrenderder-b200: gl_record_views_begin: already recording");
+        context_of(b);
+        CK(trb_record_begin(b.ctx));
+        b.recording = true;
+        b.pending = Backend::Rec();
+    }
+}
+int gl_record_views_end() {
+    int handle = 0;
+    for (Backend& b : BS()) {
+        if (!b.recording) throw std::runtime_error("tinyrenderder-b200: gl_record_views_end: not recording");
+        b.recording = false;
+        TrbRecording r = 0;
+        CK(trb_record_end(b.ctx, &r));
+        b.pending.handle = r;
+        b.pending.nviews = b.views.size() / 16;
+        b.recs.push_back(b.pending);
+        handle = (int)b.recs.size();
+    }
+    return handle;
+}
+void gl_replay_views(int recording, const std::vector<mat<4, 4>>& views) {
+    const size_t n = BS().size();
+    for (size_t k = 0; k < n; ++k) {
+        Backend& b = BS()[k];
+        if (recording < 1 || (size_t)recording > b.recs.size()) throw std::runtime_error("tinyrenderder-b200: gl_replay_views: no such recording");
+        const Backend::Rec& rec = b.recs[(size_t)recording - 1];
+        size_t first = 0, count = views.size();
+        shard(views.size(), k, n, first, count);
+        if (count != rec.nviews) throw std::runtime_error("tinyrenderder-b200: gl_replay_views needs as many cameras as were recorded");
+        if (count == 0) continue;
+        b.views.resize(count * 16);
+        b.view0 = first;
+        for (size_t v = 0; v < count; ++v) flat(views[first + v], &b.views[v * 16]);
+        std::vector<std::vector<double>> mvs(rec.draws.size()), prs(rec.draws.size());
+        std::vector<std::vector<TrbPhongUniforms>> us(rec.draws.size());
+        std::vector<TrbReplayDraw> draws(rec.draws.size());
+        for (size_t i = 0; i < rec.draws.size(); ++i) {
+            view_params(b.views, rec.draws[i], mvs[i], prs[i], us[i]);
+            draws[i] = TrbReplayDraw{mvs[i].data(), prs[i].data(), us[i].data(), sizeof(TrbPhongUniforms)};
+        }
+        CK(trb_replay(b.ctx, rec.handle, draws.data(), (int)draws.size()));
+        b.frame = true;
     }
 }
 

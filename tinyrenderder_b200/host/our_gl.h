@@ -99,6 +99,14 @@ void gl_draw_model_views(const Model& model, int kind, const mat<4, 4>& model_ma
 void gl_read_view(int view, TGAImage& framebuffer);
 // gl_write_tga_file for every frame of the batch: filenames[i] receives frame i
 bool gl_write_tga_files(int image, const std::vector<std::string>& filenames);
+// Frame recordings of a batch (trb_record_begin / trb_record_end / trb_replay, trb.h): after a batch of this shape has been
+// rendered once, everything between gl_record_views_begin and gl_record_views_end (gl_begin_views, gl_draw_model_views,
+// gl_zbuffer_snapshot / restore) is captured into one CUDA graph per context; gl_replay_views re-runs it for other cameras
+// (as many as were recorded) with ONE launch per context - the frame loop of main.cpp:606-730 for frames so small that the
+// kernel launches cost more than the kernels.  gl_read_view / gl_write_tga_files then work on the replayed batch.
+void gl_record_views_begin();
+int gl_record_views_end();
+void gl_replay_views(int recording, const std::vector<mat<4, 4>>& views);
 struct TrbCtx;
 TrbCtx* gl_context();        // the process-wide device context (device = $TRB_DEVICE, default 0)
 // ---- several GPUs from one C++ program ---------------------------------------------------
