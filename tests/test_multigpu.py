@@ -285,6 +285,8 @@ def test_draw_shard_composite_group_on_one_gpu(cuda_api, port_api, monkeypatch, 
     range), ids global without trb_set_triangle_id_base, two draws per frame.  After trb_composite_group every frame equals
     the unsharded render of the oracle, ties across ranks included."""
     monkeypatch.setenv("TRB_MESH_ORDER_MIN_TRIS", order_min_tris)
+    # the masked vertex stage of a share (and the composite's on-demand vertex records) normally starts at 4 ranks
+    monkeypatch.setenv("TRB_SHARE_VERTEX_MIN_RANKS", "2")
     m = scenes.icosphere(5)
     w, h = 640, 400
     pr = cuda_api.perspective(60, w / h, 0.1, 10)

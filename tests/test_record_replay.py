@@ -47,6 +47,9 @@ def test_head_frame_replays_for_other_cameras(cuda_api):
             if k == 1:
                 r.replay(rec)
                 _same(_frame(r), want[1])
+        # first use of another subsystem (the TGA packetiser allocates its work areas) does not make the recording stale
+        files = r.encode_tga()
+        assert len(files) == 1 and len(files[0]) > 18
         # plain frames and replays interleave
         up.render(cams[2][None], pr)
         _same(_frame(r), want[2])

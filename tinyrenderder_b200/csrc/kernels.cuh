@@ -80,6 +80,10 @@ struct DrawDev {               // one draw call, kept until flush (the shade ker
     uint32_t mesh_ntris;       // triangles of the whole mesh (ids of ranges other ranks drew map here too)
     long long mesh_id_base;    // id of mesh triangle g is mesh_id_base + g + 1  (= id_base - first_tri)
     const uint32_t* inv_perm;  // ordered soup (idx == nullptr): triangle g sits in slot inv_perm[g], vertices 3 * slot + k
+    // trb_draw_shard inside a composite group: the vertex stage only ran for the vertices of this rank's share
+    // (vmark[v] != 0); the composite's shade pass computes the record of any other vertex it meets from pos4
+    const uint8_t* vmark;
+    const float4* pos4;
 };
 
 __device__ __forceinline__ uint32_t vertex_index(const uint32_t* idx, uint32_t first_tri, uint32_t t, int k) {
@@ -151,14 +155,17 @@ __global__ void __launch_bounds__(TPB) k_interleave_mesh(const float* __restrict
 // ---------------------------------------------------------------------------------------------
 // vertex stage
 // ---------------------------------------------------------------------------------------------
+// mark != nullptr: only the vertices with mark[v] != 0 (one rank's share of a mesh, k_mark_share_vertices)
 __global__ void __launch_bounds__(TPB) k_vertex_mesh(FrameDev f, const float4* __restrict__ pos4, uint32_t nverts,
-                                                     const double* __restrict__ mats, VRec* __restrict__ out) {
+                                                     const double* __restrict__ mats, VRec* __restrict__ out,
+                                                     const uint8_t* __restrict__ mark) {
     __shared__ double m[32];
     const int view = blockIdx.y;
     if (threadIdx.x < 32) m[threadIdx.x] = mats[view * 32 + threadIdx.x];
     __syncthreads();
     uint32_t v = blockIdx.x * TPB + threadIdx.x;
     if (v >= nverts) return;
+    if (mark && !__ldg(mark + v)) return;
     float4 p = __ldg(pos4 + v);
     VRec r = vrec_from_position(m, m + 16, f.viewport, (double)p.x, (double)p.y, (double)p.z);
     store_vrec(out + (size_t)view * nverts + v, r);
@@ -205,6 +212,18 @@ struct SlotIds {               // slot -> triangle id for the raster kernels
 };
 __device__ __forceinline__ uint32_t slot_gid(const SlotIds& m, uint32_t slot) {
     return m.id_off + (m.perm ? __ldg(m.perm + slot_position(slot, m.shard_n, m.shard_r, m.shard_shift)) : slot) + 1u;
+}
+
+// the vertices one rank's share of an ordered indexed mesh refers to (trb_draw_shard): mark[v] = 1
+__global__ void __launch_bounds__(TPB) k_mark_share_vertices(const uint32_t* __restrict__ idx_perm, uint32_t nperm, uint32_t nslots,
+                                                             uint32_t shard_n, uint32_t shard_r, uint32_t shard_shift,
+                                                             uint8_t* __restrict__ mark) {
+    const uint32_t slot = blockIdx.x * TPB + threadIdx.x;
+    if (slot >= nslots) return;
+    const uint32_t j = slot_position(slot, shard_n, shard_r, shard_shift);
+    if (j >= nperm) return;
+    const uint32_t* q = idx_perm + (size_t)j * 3;
+    mark[__ldg(q)] = 1; mark[__ldg(q + 1)] = 1; mark[__ldg(q + 2)] = 1;
 }
 
 constexpr uint32_t BOX_NONE = 0xFFFFFFFFu;
@@ -1617,15 +1636,25 @@ __device__ __forceinline__ void winner_vertices(const DrawDev* tab, int draw, ui
 }
 
 // one visible pixel (x, y) of `view`, p = x + y*W: its winner is triangle g0 (vertices i0, i1, i2) of draw `draw`
-template <bool C2, bool FAST>
+// vertex record of a winner's vertex.  LAZYV (the composite's shade pass): a vertex the rank's masked vertex stage skipped
+// is transformed here - the same vrec_from_position on the same inputs as k_vertex_mesh, hence the same bits
+template <bool LAZYV>
+__device__ __forceinline__ VRec winner_vrec(const FrameDev& f, const DrawDev& D, int view, const VRec* vr, uint32_t i) {
+    if (LAZYV && D.vmark && !__ldg(D.vmark + i)) {
+        const float4 q = __ldg(D.pos4 + i);
+        const double* m = D.mats + (size_t)view * 32;
+        return vrec_from_position(m, m + 16, f.viewport, (double)q.x, (double)q.y, (double)q.z);
+    }
+    return load_vrec(reinterpret_cast<const VRec*>(elem_addr<32>(vr, i)));
+}
+template <bool C2, bool FAST, bool LAZYV>
 __device__ __forceinline__ void shade_resolved(const FrameDev& f, const DrawDev* tab, int view, unsigned long long p, int x, int y,
                                                int draw, uint32_t g0, uint32_t i0, uint32_t i1, uint32_t i2) {
     const size_t gp = (size_t)view * f.npix + p;
     const DrawDev D = tab[draw];
     const VRec* vr = D.vrec + (size_t)view * D.nverts;
-    const VRec va = load_vrec(reinterpret_cast<const VRec*>(elem_addr<32>(vr, i0))),
-               vb = load_vrec(reinterpret_cast<const VRec*>(elem_addr<32>(vr, i1))),
-               vc = load_vrec(reinterpret_cast<const VRec*>(elem_addr<32>(vr, i2)));
+    const VRec va = winner_vrec<LAZYV>(f, D, view, vr, i0), vb = winner_vrec<LAZYV>(f, D, view, vr, i1),
+               vc = winner_vrec<LAZYV>(f, D, view, vr, i2);
     TriSetup ts;
     setup_known_triangle(va, vb, vc, ts);   // a recorded winner passed every reject: no tests, no bbox
     double b[3], z, pc[3];
@@ -1694,21 +1723,21 @@ __device__ __forceinline__ void shade_resolved(const FrameDev& f, const DrawDev*
         }
     }
 }
-template <bool C2, bool FAST>
+template <bool C2, bool FAST, bool LAZYV>
 __device__ __forceinline__ void shade_pixel_tab(const FrameDev& f, const DrawDev* tab, int ndraws, int view, unsigned long long p,
                                                 int x, int y, uint32_t id) {
     int draw;
     uint32_t g0, vi[3];
     if (!resolve_winner(tab, ndraws, id, draw, g0)) return;
     winner_vertices(tab, draw, g0, vi);
-    shade_resolved<C2, FAST>(f, tab, view, p, x, y, draw, g0, vi[0], vi[1], vi[2]);
+    shade_resolved<C2, FAST, LAZYV>(f, tab, view, p, x, y, draw, g0, vi[0], vi[1], vi[2]);
 }
-template <bool C2, bool FAST>
+template <bool C2, bool FAST, bool LAZYV = false>
 __device__ __forceinline__ void shade_pixel(const FrameDev& f, const DrawDev* __restrict__ draws, int ndraws,
                                             const DrawDev* sm_draws, int view, unsigned long long p, int x, int y, uint32_t id) {
     // ONE table per frame: the shared-memory copy, or - frames with more draws than it holds (long immediate-mode
     // frames) - the table in global memory
-    shade_pixel_tab<C2, FAST>(f, ndraws <= SHADE_MAX_SM_DRAWS ? sm_draws : draws, ndraws, view, p, x, y, id);
+    shade_pixel_tab<C2, FAST, LAZYV>(f, ndraws <= SHADE_MAX_SM_DRAWS ? sm_draws : draws, ndraws, view, p, x, y, id);
 }
 
 // The flush picks its kernel on the device (no host round trip): sparse frames (configs 4, 5) shade
@@ -1910,7 +1939,7 @@ __global__ void __launch_bounds__(TPB, TRB_SHADE_MIN_BLOCKS) k_composite_shade_p
     f.zkey[p] = bk;
     if (bid == VIS_NONE || bid == VIS_SHADED) { f.vis[p] = bid; return; }
     const uint32_t yq = (uint32_t)p / (uint32_t)f.W;
-    shade_pixel<C2, FAST>(f, draws, ndraws, sm_draws, 0, p, (int)((uint32_t)p - yq * (uint32_t)f.W), (int)yq, bid);
+    shade_pixel<C2, FAST, true>(f, draws, ndraws, sm_draws, 0, p, (int)((uint32_t)p - yq * (uint32_t)f.W), (int)yq, bid);
     f.vis[p] = VIS_SHADED;
 }
 

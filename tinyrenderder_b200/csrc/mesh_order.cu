@@ -113,7 +113,85 @@ __global__ void __launch_bounds__(TPB) k_permute_soup(const float4* __restrict__
     if (k == 0) inv[t] = j;
 }
 
+// ---- vertex numbering of a large indexed mesh ------------------------------------------------------------------
+// A subdivided mesh numbers its vertices by subdivision level: the three vertices of a triangle sit megabytes apart, and
+// the vertices one rank's share of the mesh refers to (trb_draw_shard) are sprinkled evenly over the whole array.  The
+// vertices are renumbered in Morton order of their positions (arrays permuted, index buffer rewritten): neighbouring
+// triangles then gather neighbouring records, and a rank's vertices form runs that a masked vertex stage can skip over
+// warp by warp.  Vertex numbers are internal (no entry point exposes them); triangle ids do not change.
+__global__ void __launch_bounds__(TPB) k_vmorton(const float4* __restrict__ pos4, uint32_t nverts, const unsigned* __restrict__ box,
+                                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t v = blockIdx.x * TPB + threadIdx.x;
+    if (v >= nverts) return;
+    const float4 a = __ldg(pos4 + v);
+    const float c[3] = {a.x, a.y, a.z};
+    unsigned q[3];
+    for (int k = 0; k < 3; ++k) {
+        const unsigned l = box[k], h = box[3 + k];
+        const float lo = l <= h ? from_ordered_bits(l) : 0.0f;
+        const float ext = l <= h ? from_ordered_bits(h) - lo : 0.0f;
+        const float f = (c[k] - lo) * (ext > 0.0f ? 1023.0f / ext : 0.0f);
+        q[k] = f >= 0.0f ? (unsigned)fminf(f, 1023.0f) : 0u;    // NaN -> 0
+    }
+    keys[v] = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+    vals[v] = v;
+}
+// vperm[new] = old: gather the vertex arrays into the new numbering and note where every old vertex went
+__global__ void __launch_bounds__(TPB) k_permute_vertices(const float4* __restrict__ pos_in, const float4* __restrict__ attr_in,
+                                                          const uint32_t* __restrict__ vperm, uint32_t nverts,
+                                                          float4* __restrict__ pos_out, float4* __restrict__ attr_out,
+                                                          uint32_t* __restrict__ inv) {
+    const uint32_t n = blockIdx.x * TPB + threadIdx.x;
+    if (n >= nverts) return;
+    const uint32_t o = __ldg(vperm + n);
+    pos_out[n] = __ldg(pos_in + o);
+    attr_out[2 * (size_t)n] = __ldg(attr_in + 2 * (size_t)o);
+    attr_out[2 * (size_t)n + 1] = __ldg(attr_in + 2 * (size_t)o + 1);
+    inv[o] = n;
+}
+__global__ void __launch_bounds__(TPB) k_remap_indices(uint32_t* __restrict__ idx, uint64_t nidx, const uint32_t* __restrict__ inv) {
+    for (uint64_t i = (uint64_t)blockIdx.x * TPB + threadIdx.x; i < nidx; i += (uint64_t)gridDim.x * TPB) idx[i] = __ldg(inv + idx[i]);
+}
+
 }  // namespace trbmo
+
+// scratch of trb_vertex_order_apply: [keys_in | keys_out | vals_in | vperm | inv | box (256 B) | cub temp]
+size_t trb_vertex_order_scratch_bytes(uint32_t nverts) {
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)nverts, 0, 30, (cudaStream_t)0);
+    const size_t n4 = ((size_t)nverts * 4 + 255) & ~(size_t)255;
+    return 5 * n4 + 256 + cub_bytes + 256;
+}
+// vertex arrays into Morton numbering (pos_out / attr_out), the index buffer rewritten in place; queued on `st`
+cudaError_t trb_vertex_order_apply(const float4* pos_in, const float* attr_in, uint32_t nverts, uint32_t* idx, uint64_t nidx,
+                                   float4* pos_out, float* attr_out, void* scratch, size_t scratch_bytes, int sms, cudaStream_t st) {
+    using namespace trbmo;
+    if (nverts == 0 || nverts > 0x7fffffffu) return cudaErrorInvalidValue;
+    const size_t n4 = ((size_t)nverts * 4 + 255) & ~(size_t)255;
+    char* s = (char*)scratch;
+    uint32_t* keys_in = (uint32_t*)s;
+    uint32_t* keys_out = (uint32_t*)(s + n4);
+    uint32_t* vals_in = (uint32_t*)(s + 2 * n4);
+    uint32_t* vperm = (uint32_t*)(s + 3 * n4);
+    uint32_t* inv = (uint32_t*)(s + 4 * n4);
+    unsigned* box = (unsigned*)(s + 5 * n4);
+    void* cub_temp = s + 5 * n4 + 256;
+    size_t cub_bytes = scratch_bytes - (5 * n4 + 256);
+    const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    cudaError_t e = cudaMemcpyAsync(box, init, sizeof(init), cudaMemcpyHostToDevice, st);   // pageable: staged before the call returns
+    if (e != cudaSuccess) return e;
+    const unsigned vb = (unsigned)((nverts + TPB - 1) / TPB);
+    k_bbox<<<vb < (unsigned)sms * 8 ? vb : (unsigned)sms * 8, TPB, 0, st>>>(pos_in, nverts, box);
+    k_vmorton<<<vb, TPB, 0, st>>>(pos_in, nverts, box, keys_in, vals_in);
+    e = cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, (const uint32_t*)keys_in, keys_out, (const uint32_t*)vals_in, vperm,
+                                        (int)nverts, 0, 30, st);
+    if (e != cudaSuccess) return e;
+    k_permute_vertices<<<vb, TPB, 0, st>>>(pos_in, reinterpret_cast<const float4*>(attr_in), vperm, nverts, pos_out,
+                                           reinterpret_cast<float4*>(attr_out), inv);
+    k_remap_indices<<<(unsigned)sms * 8, TPB, 0, st>>>(idx, nidx, inv);
+    return cudaGetLastError();
+}
 
 // vertex arrays of a soup in processing order (pos_out / attr_out hold nverts entries; vertices past 3 * ntris are copied
 // as they are) and the inverse permutation; queued on `st`

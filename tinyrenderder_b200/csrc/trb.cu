@@ -21,6 +21,9 @@ using namespace trbk;
 size_t trb_mesh_order_scratch_bytes(uint32_t ntris);
 cudaError_t trb_mesh_order_build(const float4* pos4, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint32_t* perm_out,
                                  uint32_t* idx_perm_out, void* scratch, size_t scratch_bytes, int sms, cudaStream_t st);
+size_t trb_vertex_order_scratch_bytes(uint32_t nverts);
+cudaError_t trb_vertex_order_apply(const float4* pos_in, const float* attr_in, uint32_t nverts, uint32_t* idx, uint64_t nidx,
+                                   float4* pos_out, float* attr_out, void* scratch, size_t scratch_bytes, int sms, cudaStream_t st);
 cudaError_t trb_soup_order_apply(const float4* pos_in, const float* attr_in, uint32_t nverts, const uint32_t* perm, uint32_t ntris,
                                  float4* pos_out, float* attr_out, uint32_t* inv_perm, cudaStream_t st);
 
@@ -39,8 +42,8 @@ struct DevBuf {
     cudaError_t ensure(size_t bytes, cudaStream_t st) {
         if (bytes <= cap) return cudaSuccess;
         if (t_recording) return cudaErrorNotPermitted;
-        ++g_generation;
         if (p) {
+            ++g_generation;             // a first allocation invalidates nothing: no graph can hold an address that did not exist
             cudaStreamSynchronize(st);  // kernels in flight may still read the old block
             cudaFree(p);
             p = nullptr;
@@ -229,6 +232,10 @@ struct Mesh {
     // a large SOUP (idx == nullptr) has its vertex arrays themselves in processing order: slot j = vertices 3j .. 3j + 2
     // (idx_perm stays nullptr), inv_perm[t] = slot of triangle t for the shade pass.  Every draw of it runs over the slots.
     uint32_t* inv_perm = nullptr;
+    // trb_draw_shard inside a composite group: which vertices this rank's share refers to (built at the first such draw,
+    // kept for the (shard count, rank, block size) it was built for)
+    uint8_t* vmark = nullptr;
+    uint32_t vmark_n = 0, vmark_r = 0, vmark_shift = 0;
 };
 struct Tex {
     uint8_t* px = nullptr;
@@ -405,6 +412,12 @@ struct TrbCtx {
     // indexed meshes of at least this many triangles get a processing order at upload (TRB_MESH_ORDER_MIN_TRIS; 0 = never).
     // Default: from 2 M triangles up - below that the vertex records of a draw (32 B each) sit in the 126 MB L2 anyway.
     uint64_t order_min_tris = 2ull << 20;
+    bool share_vertex = true;    // draw_shard in a composite group: vertex stage over the share's vertices only (TRB_SHARE_VERTEX=0: all)
+    // ... from this many ranks up.  Measured on config 4: 8 ranks 0.595 -> 0.570 ms per frame (vertex stage 0.100 -> 0.062 ms,
+    // composite + 0.003); 2 ranks 1.053 -> 1.086 (75 % of the vertex warps still have a marked lane, and half of the
+    // pixels a rank shades then transform their three vertices themselves)
+    int share_vertex_min_ranks = 4;
+    bool order_vertices = true;  // ... and their vertices a Morton numbering (TRB_MESH_ORDER_VERTICES=0: keep the caller's)
     uint32_t shard_shift = 12;  // trb_draw_shard deals the processing order out in blocks of 2^shard_shift triangles (TRB_SHARD_SHIFT)
 
     // frame recordings (CUDA graphs): `rec` is the one being recorded, if any
@@ -1054,6 +1067,9 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_SPLIT_CAP")) c->split_cap_fixed = (uint32_t)std::max(1, atoi(e));
     if (const char* e = getenv("TRB_SHARD_SHIFT")) c->shard_shift = (uint32_t)std::min(24, std::max(5, atoi(e)));
     if (const char* e = getenv("TRB_MESH_ORDER_MIN_TRIS")) c->order_min_tris = (uint64_t)std::max(0ll, atoll(e));
+    if (const char* e = getenv("TRB_MESH_ORDER_VERTICES")) c->order_vertices = atoi(e) != 0;
+    if (const char* e = getenv("TRB_SHARE_VERTEX")) c->share_vertex = atoi(e) != 0;
+    if (const char* e = getenv("TRB_SHARE_VERTEX_MIN_RANKS")) c->share_vertex_min_ranks = std::max(2, atoi(e));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->upload_ev, cudaEventDisableTiming) != cudaSuccess ||
@@ -1095,6 +1111,7 @@ int trb_destroy(TrbCtx* c) {
             if (m.perm) cudaFree(m.perm);
             if (m.idx_perm) cudaFree(m.idx_perm);
             if (m.inv_perm) cudaFree(m.inv_perm);
+            if (m.vmark) cudaFree(m.vmark);
         }
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
@@ -1201,6 +1218,30 @@ int upload_pinned(TrbCtx* c, void** dev, const void* src, size_t bytes) {
 int build_mesh_order(TrbCtx* c, Mesh& m) {
     const uint64_t ntris = m.nidx / 3;
     if (c->order_min_tris == 0 || ntris < c->order_min_tris || ntris > 0x55555555ull || ntris == 0) return TRB_OK;
+    if (m.idx && c->order_vertices && m.nverts <= 0x7fffffffu) {
+        // indexed mesh: first the vertices into Morton numbering (second copies of the arrays, the first ones are recycled;
+        // the index buffer is rewritten in place)
+        const size_t vbytes = trb_vertex_order_scratch_bytes(m.nverts);
+        void* vs = nullptr;
+        float4* pos2 = nullptr;
+        float* attr2 = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        CU(c->cache.get(&vs, vbytes, &e0, c->upload_stream));
+        CU(c->cache.get((void**)&pos2, (size_t)m.nverts * 16, &e1, c->upload_stream));
+        CU(c->cache.get((void**)&attr2, (size_t)m.nverts * 32, &e2, c->upload_stream));
+        if (e0) CU(cudaStreamWaitEvent(c->upload_stream, e0, 0));
+        if (e1) CU(cudaStreamWaitEvent(c->upload_stream, e1, 0));
+        if (e2) CU(cudaStreamWaitEvent(c->upload_stream, e2, 0));
+        {
+            Launch L(c, "vertex_order", c->upload_stream, /*kernel=*/false);
+            CU(trb_vertex_order_apply(m.pos4, m.attr8, m.nverts, m.idx, m.nidx, pos2, attr2, vs, vbytes, c->sms, c->upload_stream));
+        }
+        c->cache.put(vs, vbytes, c->upload_stream);
+        c->cache.put(m.pos4, (size_t)m.nverts * 16, c->upload_stream);
+        c->cache.put(m.attr8, (size_t)m.nverts * 32, c->upload_stream);
+        m.pos4 = pos2;
+        m.attr8 = attr2;
+    }
     const size_t sbytes = trb_mesh_order_scratch_bytes((uint32_t)ntris);
     void* scratch = nullptr;
     cudaEvent_t w0 = nullptr, w1 = nullptr, w2 = nullptr;
@@ -1354,6 +1395,10 @@ int trb_free_mesh(TrbCtx* c, TrbMesh h) {
     if (m.perm) c->cache.put(m.perm, m.nidx / 3 * 4, c->stream);
     if (m.idx_perm) c->cache.put(m.idx_perm, m.nidx * 4, c->stream);
     if (m.inv_perm) c->cache.put(m.inv_perm, m.nidx / 3 * 4, c->stream);
+    if (m.vmark) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(m.vmark);
+    }
     m = Mesh();
     return TRB_OK;
 }
@@ -1549,9 +1594,29 @@ int draw_mesh(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int k
     }
     VRec* vrec = (VRec*)c->arena.alloc(sizeof(VRec) * (size_t)m.nverts * nv, e);
     CU(e);
+    // One rank's share of an ordered mesh inside a composite group: only the vertices the share refers to go through
+    // the vertex stage (the composite's shade pass transforms the vertices of other ranks' winners itself, a few per
+    // pixel row it owns, instead of every rank transforming every vertex).  Not for the NCCL composite, whose shade
+    // pass is the ordinary one.
+    const uint8_t* vmark = nullptr;
+    if (shard_order && c->comm.n > 0 && m.idx_perm && c->share_vertex && shard_n >= (uint32_t)c->share_vertex_min_ranks) {
+        Mesh& mm = c->meshes[mesh - 1];
+        if (!mm.vmark || mm.vmark_n != shard_n || mm.vmark_r != shard_r || mm.vmark_shift != c->shard_shift) {
+            if (!mm.vmark) {
+                if (t_recording) return fail(c, TRB_E_ARG, "record: draw_shard: render the frame once before recording it");
+                CU(cudaMalloc((void**)&mm.vmark, mm.nverts));
+            }
+            CU(cudaMemsetAsync(mm.vmark, 0, mm.nverts, c->stream));
+            Launch L(c, "k_mark_share_vertices");
+            k_mark_share_vertices<<<blocks_for(share_slots), TPB, 0, c->stream>>>(mm.idx_perm, (uint32_t)mesh_tris, share_slots, shard_n,
+                                                                                 shard_r, c->shard_shift, mm.vmark);
+            mm.vmark_n = shard_n; mm.vmark_r = shard_r; mm.vmark_shift = c->shard_shift;
+        }
+        vmark = mm.vmark;
+    }
     {
         Launch L(c, "k_vertex_mesh");
-        k_vertex_mesh<<<dim3(blocks_for(m.nverts), nv), TPB, 0, c->stream>>>(c->frame, m.pos4, m.nverts, mats, vrec);
+        k_vertex_mesh<<<dim3(blocks_for(m.nverts), nv), TPB, 0, c->stream>>>(c->frame, m.pos4, m.nverts, mats, vrec, vmark);
     }
     CU(cudaGetLastError());
     GeomArgs g;
@@ -1580,6 +1645,8 @@ int draw_mesh(TrbCtx* c, TrbMesh mesh, const double* mv, const double* pr, int k
     d.nverts = g.nverts;
     d.idx = m.idx;
     d.inv_perm = m.inv_perm;
+    d.vmark = vmark;
+    d.pos4 = m.pos4;
     d.attr8 = m.attr8;
     d.vrec = vrec;
     d.mats = mats;
@@ -2463,6 +2530,9 @@ int trb_set_triangle_id_base(TrbCtx* c, uint64_t base) {
 int trb_composite_save_local_depth(TrbCtx* c) {
     NOT_WHILE_RECORDING(c, "composite_save_local_depth");
     if (!c || !c->in_frame || c->frame.nviews != 1) return fail(c, TRB_E_COMM, "composite: needs a single-view frame");
+    for (const DrawDev& d : c->draws)
+        if (d.vmark) return fail(c, TRB_E_COMM, "composite: shares drawn while a composite group is open are composited with trb_composite "
+                                               "(their vertex stage only covers the share)");
     int rc = check_device(c);
     if (rc) return rc;
     const unsigned long long n = c->frame.npix;
