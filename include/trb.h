@@ -141,7 +141,9 @@ TRB_EXPORT const char* TRB_FN(backend_name)(void); /* "cuda-sm100a", "oracle-ref
  * Indexed meshes of 2 M triangles or more (TRB_MESH_ORDER_MIN_TRIS overrides; 0 = never) also get a PROCESSING ORDER
  * at upload: the triangles sorted by the Morton code of their centroids (device-side, on the upload stream).  Draws
  * visit the triangles in that order so that the vertex records a triangle gathers are the ones its predecessors just
- * used; triangle ids - and with them every output bit - stay those of the index buffer. */
+ * used; triangle ids - and with them every output bit - stay those of the index buffer.  The vertices of such a mesh are
+ * renumbered in the same spirit (internal: no entry point exposes vertex numbers), and a SOUP of that size (idx == NULL)
+ * has its vertex arrays put into the processing order themselves. */
 TRB_EXPORT int TRB_FN(upload_mesh)(TrbCtx* ctx, const float* pos3, const float* nrm3,
                                    const float* uv2, uint32_t nverts, const uint32_t* idx,
                                    uint64_t nidx, TrbMesh* out);
