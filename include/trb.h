@@ -204,7 +204,10 @@ TRB_EXPORT int TRB_FN(submit_clip_triangles)(TrbCtx* ctx, const double* clip12,
 
 /* z-buffer copy at a draw boundary (std::vector<double> zbuffer_before_eyes = zbuffer,
  * main.cpp:700) and roll-back (zbuffer = zbuffer_before_eyes, main.cpp:730).  Restore
- * shades everything drawn so far first, so colours persist like in the reference. */
+ * shades everything drawn so far first, so colours persist like in the reference.
+ * Cost: the snapshot is tile granular - the draws between the two calls save the 16x16 tiles they are about to change
+ * and the restore copies those back, so a few small draws (the eyes) cost a few tiles, not two passes over the plane.
+ * Results are those of the full copy (TRB_LAZY_SNAPSHOT=0 selects it). */
 TRB_EXPORT int TRB_FN(depth_snapshot)(TrbCtx* ctx);
 TRB_EXPORT int TRB_FN(depth_restore)(TrbCtx* ctx);
 /* keep the current depth buffer of view 0 as a shadow map for later frames */

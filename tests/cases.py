@@ -366,6 +366,36 @@ def snapshot_signed_zero(api, r):
     return _grab(r)
 
 
+def snapshot_small_triangles(api, r):
+    """sub-pixel and few-pixel triangles (the direct path's kind) drawn between a snapshot and its restore, on a frame
+    whose last tile row and column are ragged: the tile-granular snapshot (k_snap_save / k_snap_restore) has to save every
+    tile such a draw changes, whichever raster path takes it, and nothing may leak through the restore"""
+    w, h = 100, 70
+    rng = np.random.default_rng(77)
+
+    def cloud(n, zlo, zhi, size):
+        c = rng.uniform([1, 1], [w - 1, h - 1], size=(n, 2))
+        tris = []
+        for (cx, cy), z in zip(c, rng.uniform(zlo, zhi, size=n)):
+            d = rng.uniform(-size, size, size=(3, 2))
+            tris.append(_screen_tri([(cx + d[0, 0], cy + d[0, 1]), (cx + d[1, 0], cy + d[1, 1]), (cx + d[2, 0], cy + d[2, 1])],
+                                    float(z), w, h)[0])
+        return np.array(tris, dtype=np.float64)
+
+    r.begin_frame(w, h)
+    r.submit_clip_triangles(_screen_tri([(2, 2), (97, 6), (40, 68)], 0.5, w, h))
+    r.submit_clip_triangles(cloud(150, 0.3, 0.7, 2.5))
+    r.depth_snapshot()
+    r.submit_clip_triangles(cloud(300, -0.2, 0.9, 1.5))       # nearer and farther than the saved state, all over the frame
+    r.submit_clip_triangles(_screen_tri([(60, 30), (99.5, 40), (70, 69.5)], 0.1, w, h))
+    r.depth_restore()
+    r.submit_clip_triangles(cloud(200, 0.2, 0.8, 3.0))        # tested against the restored depths
+    r.depth_restore()
+    r.submit_clip_triangles(cloud(50, 0.45, 0.55, 6.0))
+    r.end_frame()
+    return _grab(r)
+
+
 def sub_range_draws(api, r):
     """drawing a mesh as three triangle ranges == drawing it at once (config-4 sharding unit)"""
     m = scenes.icosphere(3)
@@ -493,7 +523,7 @@ CASES = {
     "big_triangles": big_triangles, "queue_overflow": queue_overflow, "dense_tile": dense_tile,
     "soup_mesh_fp32": soup_mesh_fp32, "head_small": head_small, "orbit_small": orbit_small,
     "depth_only_then_color": depth_only_then_color, "sub_range_draws": sub_range_draws,
-    "snapshot_restore_twice": snapshot_restore_twice, "snapshot_signed_zero": snapshot_signed_zero,
+    "snapshot_restore_twice": snapshot_restore_twice, "snapshot_signed_zero": snapshot_signed_zero, "snapshot_small_triangles": snapshot_small_triangles,
     "lit_clip_triangles": lit_clip_triangles, "shadow_small": shadow_small, "gouraud_small": gouraud_small,
     "orbit_culled": orbit_culled, "indexed_duplicates": indexed_duplicates, "soup_duplicates_lit": soup_duplicates_lit,
 }

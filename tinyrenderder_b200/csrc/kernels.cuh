@@ -565,6 +565,59 @@ struct SplitArgs {
     uint32_t cap, split_s;
 };
 
+// ---------------------------------------------------------------------------------------------
+// Tile-granular depth snapshot: `zbuffer_before_eyes = zbuffer` ... `zbuffer = zbuffer_before_eyes` (main.cpp:700, 730)
+// without copying the plane.  trb_depth_snapshot only zeroes one byte per tile slot; every draw between the snapshot and
+// the restore runs k_snap_save between its scan and its raster kernels, which copies the tiles the draw is about to
+// change (per-tile bin count > 0; every tile when the draw overflowed into the unbinned kernels, or when the caller
+// asks for `all`) into the snapshot plane ONCE; k_snap_restore copies the saved tiles back.  Invariant: a tile whose
+// byte is 0 still holds the snapshot's keys.  A warp looks at 32 consecutive slots and copies the flagged ones together.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void snap_copy_tile(const FrameDev& f, uint32_t slot, const unsigned long long* __restrict__ from,
+                                               unsigned long long* __restrict__ to, unsigned lane) {
+    const uint32_t view = slot / (uint32_t)f.ntiles, tile = slot - view * (uint32_t)f.ntiles;
+    const int tx0 = (int)(tile % (uint32_t)f.tw) << TILE_SHIFT, ty0 = (int)(tile / (uint32_t)f.tw) << TILE_SHIFT;
+    const unsigned long long base = (unsigned long long)view * f.npix;
+#pragma unroll
+    for (int it = 0; it < TILE * TILE / 32; ++it) {
+        const int e = it * 32 + (int)lane, x = tx0 + (e & (TILE - 1)), y = ty0 + (e >> TILE_SHIFT);
+        if (x < f.W && y < f.H) {
+            const unsigned long long p = base + (unsigned long long)y * f.W + x;
+            to[p] = from[p];
+        }
+    }
+}
+__global__ void __launch_bounds__(TPB) k_snap_save(FrameDev f, uint32_t nslots, const uint32_t* __restrict__ counts,
+                                                   const DrawCtl* __restrict__ ctl, int all, uint8_t* __restrict__ saved,
+                                                   unsigned long long* __restrict__ snap) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t first = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 32u;
+    if (first >= nslots) return;
+    const uint32_t slot = first + lane;
+    const bool every = all || (ctl && ctl->overflow);
+    bool need = slot < nslots && !saved[slot] && (every || counts[slot] != 0);
+    unsigned m = __ballot_sync(0xffffffffu, need);
+    if (need) saved[slot] = 1;            // only this warp ever looks at these 32 bytes inside one launch
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        snap_copy_tile(f, first + b, f.zkey, snap, lane);
+    }
+}
+__global__ void __launch_bounds__(TPB) k_snap_restore(FrameDev f, uint32_t nslots, const uint8_t* __restrict__ saved,
+                                                      const unsigned long long* __restrict__ snap) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t first = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 32u;
+    if (first >= nslots) return;
+    const uint32_t slot = first + lane;
+    unsigned m = __ballot_sync(0xffffffffu, slot < nslots && saved[slot]);
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        snap_copy_tile(f, first + b, snap, f.zkey, lane);
+    }
+}
+
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sh, uint32_t& total) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t x = v;

@@ -285,7 +285,7 @@ struct Recording {
     // what the context looks like after the frame
     FrameDev frame{};
     DevBuf zkey, zsnap;                 // roles of the two depth planes (trb_depth_restore swaps them)
-    bool have_snapshot = false, snap_stale = false, foreign_ids = false;
+    bool have_snapshot = false, snap_stale = false, snap_lazy = false, snap_all = false, foreign_ids = false;
     uint64_t next_id = 0, tris_submitted = 0;
     int shade_row0 = 0, shade_row1 = -1;
 };
@@ -310,6 +310,13 @@ struct TrbCtx {
     DevBuf zkey, vis, color, stats, zsnap, zlocal;
     bool have_snapshot = false;
     bool snap_stale = false;        // restored by pointer swap: zsnap must be refreshed before the key plane changes
+    // tile-granular snapshot (default; TRB_LAZY_SNAPSHOT=0: the whole-plane copy + pointer swap above): zsnap only receives
+    // the tiles the draws after the snapshot change, snap_saved holds one byte per tile slot (kernels.cuh k_snap_save)
+    bool lazy_snapshot = true;
+    bool snap_lazy = false;         // the current snapshot is a tile-granular one
+    bool snap_all = false;          // ... and every tile has been saved (nothing left to do per draw)
+    DevBuf snap_saved;
+    uint64_t lazy_max_tris = 1u << 20;   // draws with more triangles x views keep the direct path and save every tile first
     std::vector<ShadowMap> shadow_maps;
     std::vector<DevBuf> shadow_pool;   // planes of released shadow maps, recycled by trb_keep_depth_as_shadow_map
     Arena arena;
@@ -672,6 +679,21 @@ int refresh_snapshot(TrbCtx* c) {
     return TRB_OK;
 }
 
+// tile-granular snapshot: save the tiles a draw is about to change (`counts` / `ctl` of that draw), or every tile not
+// saved yet (`counts == nullptr`: a writer that does not go through the bins - a draw too large to give up the direct
+// path for, a composite)
+int snapshot_save_tiles(TrbCtx* c, const uint32_t* counts, const DrawCtl* ctl) {
+    const FrameDev& f = c->frame;
+    const uint32_t nslots = (uint32_t)((size_t)f.nviews * f.ntiles);
+    Launch L(c, "k_snap_save");
+    k_snap_save<<<(nslots + TPB - 1) / TPB, TPB, 0, c->stream>>>(f, nslots, counts, ctl, counts ? 0 : 1, c->snap_saved.as<uint8_t>(),
+                                                               c->zsnap.as<unsigned long long>());
+    CU(cudaGetLastError());
+    if (!counts) c->snap_all = true;
+    return TRB_OK;
+}
+inline bool snapshot_window(const TrbCtx* c) { return c->have_snapshot && c->snap_lazy && !c->snap_all; }
+
 // Tensor maps of the frame's planes for the TMA tile staging of k_raster_warp.  cuTensorMapEncodeTiled is a driver
 // entry point; it is looked up at run time so that the library carries no link-time dependency on libcuda.
 bool tile_maps_for(TrbCtx* c) {
@@ -723,6 +745,15 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
     if (rs) return rs;
     const size_t nslots = (size_t)f.nviews * f.ntiles;
     if (nslots >= 0xFFFFFFFFull) return fail(c, TRB_E_ARG, "draw: too many tiles x views");
+    // Between a tile-granular snapshot and its restore a draw saves the tiles it is about to change.  The bins say which
+    // ones, so such a draw does without the direct path (whose atomics run inside the set-up kernel, before anything is
+    // known about the draw) - the same exact (depth, id) minimum either way.  A draw too large for that saves every tile.
+    bool save_tiles = snapshot_window(c);
+    if (save_tiles && (uint64_t)g.nslots * (uint64_t)f.nviews > c->lazy_max_tris) {
+        if ((rs = snapshot_save_tiles(c, nullptr, nullptr))) return rs;
+        save_tiles = false;
+    }
+    const int direct_area = save_tiles ? 0 : c->direct_area;
     const uint32_t ndslots = g.nslots;     // == g.ntris unless the mesh carries a processing order (GeomArgs::perm)
     CU(c->tribox.ensure((size_t)f.nviews * ndslots * sizeof(uint2), c->stream));
     CU(c->trirec.ensure((size_t)f.nviews * ndslots * sizeof(TriRec), c->stream));
@@ -742,7 +773,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         c->split_done_p = reinterpret_cast<uint32_t*>(z + o_done);
         CU(cudaMemsetAsync(z, 0, bytes, c->stream));
     }
-    if (c->direct_area > 0) CU(c->direct_list.ensure((size_t)f.nviews * ndslots * 4, c->stream));
+    if (direct_area > 0) CU(c->direct_list.ensure((size_t)f.nviews * ndslots * 4, c->stream));
     uint32_t capacity = 0xFFFFFFFFu;   // synchronous draws size the buffer after the scan
     if (!c->sync_draws) {
         // R of the most recent draw the device has finished scanning: a hint, never waited for
@@ -758,10 +789,10 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         Launch L(c, "k_setup_count");
         const dim3 sgrid((ndslots + TPB * SETUP_CHUNKS - 1) / (TPB * SETUP_CHUNKS), f.nviews);
         k_setup_count<<<sgrid, TPB, 0, c->stream>>>(f, g, c->tribox.as<uint2>(), c->trirec.as<TriRec>(),
-                                                     c->counts_p, c->direct_area, c->direct_list.as<uint32_t>(),
+                                                     c->counts_p, direct_area, c->direct_list.as<uint32_t>(),
                                                      c->direct_n_p, (c->direct_by_pixel && g.perm && !g.idx_perm) ? 1 : 0);
     }
-    if (c->direct_area > 0) {
+    if (direct_area > 0) {
         // full grid once a draw of this context has had direct candidates (mapped flag, never waited for), else a few CTAs
         Launch L(c, "k_direct_resolve");
         if (c->host_total[9]) {
@@ -804,6 +835,7 @@ int raster_draw(TrbCtx* c, const GeomArgs& g) {
         long_bins = c->host_total[1] > c->warp_max || c->host_total[2];   // k_raster also carries the overflow fallback's depth pass
         if (!c->host_total[2]) CU(c->bins.ensure((size_t)R * 4, c->stream));   // overflow (R >= 2^32): the unbinned kernels draw it
     }
+    if (save_tiles && (rc = snapshot_save_tiles(c, c->counts_p, c->ctl_p))) return rc;
     {
         Launch L(c, "k_fill");
         k_fill<<<tgrid, TPB, 0, c->stream>>>(f, ndslots, c->tribox.as<uint2>(), c->offsets.as<uint32_t>(),
@@ -993,6 +1025,10 @@ int comm_wait_peers(TrbCtx* c, bool done) {
 }
 // the fused composite + shade of rows [y0, y1) queued on the context's stream; no synchronisation
 int enqueue_composite_shade(TrbCtx* c, int y0, int y1) {
+    if (snapshot_window(c)) {               // the composite rewrites keys of pixels no bin of this rank knows about
+        int rs = snapshot_save_tiles(c, nullptr, nullptr);
+        if (rs) return rs;
+    }
     // the local planes may have been reallocated since the peers were opened
     c->peers.key[c->peer_rank] = c->frame.zkey;
     c->peers.vis[c->peer_rank] = c->frame.vis;
@@ -1060,6 +1096,8 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_RW_BLOCKS")) c->rw_blocks = atoi(e);
     if (const char* e = getenv("TRB_SHADE_EXACT")) c->shade_exact = atoi(e) != 0;
     if (const char* e = getenv("TRB_TMA")) c->use_tma = atoi(e) != 0;
+    if (const char* e = getenv("TRB_LAZY_SNAPSHOT")) c->lazy_snapshot = atoi(e) != 0;
+    if (const char* e = getenv("TRB_LAZY_SNAPSHOT_MAX_TRIS")) c->lazy_max_tris = (uint64_t)std::max(0ll, atoll(e));
     if (const char* e = getenv("TRB_SYNC_DRAWS")) c->sync_draws = atoi(e) != 0;
     if (const char* e = getenv("TRB_BIN_CAP")) c->bin_cap_fixed = (uint32_t)std::max(1, atoi(e));
     if (const char* e = getenv("TRB_SPLIT")) c->split_on = atoi(e) != 0;
@@ -1115,7 +1153,7 @@ int trb_destroy(TrbCtx* c) {
         }
     for (auto& t : c->textures)
         if (t.alive) cudaFree(t.px);
-    DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
+    DevBuf* bufs[] = {&c->zkey, &c->vis, &c->color, &c->stats, &c->zsnap, &c->zlocal, &c->snap_saved, &c->draw_table, &c->shade_list, &c->tribox, &c->trirec,
                       &c->drawzero, &c->offsets, &c->bins, &c->scan_sums, &c->scan_total, &c->heavy_list, &c->split_items, &c->split_keys, &c->split_ids, &c->direct_list, &c->rle_work, &c->rle_src, &c->rle_out, &c->scratch_a,
                       &c->scratch_b};
     for (DevBuf* b : bufs) b->release();
@@ -1477,6 +1515,7 @@ int trb_begin_batch(TrbCtx* c, int w, int h, int nviews) {
     c->tris_submitted = 0;
     c->have_snapshot = false;
     c->snap_stale = false;
+    c->snap_lazy = c->snap_all = false;
     c->shade_row0 = 0;
     c->shade_row1 = -1;
     if (c->comm.n > 0) {
@@ -1773,7 +1812,14 @@ int trb_depth_snapshot(TrbCtx* c) {
     // so resolve first to snapshot what the reference's vector copy (main.cpp:700) would hold
     rc = do_flush(c);
     if (rc) return rc;
-    {
+    c->snap_lazy = c->lazy_snapshot;
+    c->snap_all = false;
+    if (c->snap_lazy) {
+        const size_t nslots = (size_t)c->frame.nviews * c->frame.ntiles;
+        CU(c->snap_saved.ensure(nslots, c->stream));
+        Launch L(c, "clear_snapshot_tiles", nullptr, false);
+        CU(cudaMemsetAsync(c->snap_saved.p, 0, nslots, c->stream));
+    } else {
         Launch L(c, "copy_depth_snapshot", nullptr, false);
         CU(cudaMemcpyAsync(c->zsnap.p, c->zkey.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -1786,6 +1832,15 @@ int trb_depth_restore(TrbCtx* c) {
     if (!c || !c->in_frame || !c->have_snapshot) return fail(c, TRB_E_ARG, "depth_restore: no snapshot");
     int rc = do_flush(c);  // colours of everything drawn so far persist (main.cpp:730)
     if (rc) return rc;
+    if (c->snap_lazy) {                 // copy the saved tiles back; the others were never changed
+        const FrameDev& f = c->frame;
+        const uint32_t nslots = (uint32_t)((size_t)f.nviews * f.ntiles);
+        Launch L(c, "k_snap_restore");
+        k_snap_restore<<<(nslots + TPB - 1) / TPB, TPB, 0, c->stream>>>(f, nslots, c->snap_saved.as<uint8_t>(),
+                                                                      c->zsnap.as<unsigned long long>());
+        CU(cudaGetLastError());
+        return TRB_OK;
+    }
     if (c->snap_stale) return TRB_OK;   // restored already and nothing drawn since: the key plane IS the snapshot
     size_t bytes = (size_t)c->frame.npix * c->frame.nviews * 8;
     if (c->peers.n > 0) {               // peers hold the address of the key plane: copy
@@ -1873,6 +1928,8 @@ static int recording_adopt_state(TrbCtx* c, Recording& r) {
     c->zsnap = r.zsnap;
     c->have_snapshot = r.have_snapshot;
     c->snap_stale = r.snap_stale;
+    c->snap_lazy = r.snap_lazy;
+    c->snap_all = r.snap_all;
     c->foreign_ids = r.foreign_ids;
     c->next_id = r.next_id;
     c->tris_submitted = r.tris_submitted;
@@ -1942,6 +1999,8 @@ int trb_record_end(TrbCtx* c, TrbRecording* out) {
     r->zsnap = c->zsnap;
     r->have_snapshot = c->have_snapshot;
     r->snap_stale = c->snap_stale;
+    r->snap_lazy = c->snap_lazy;
+    r->snap_all = c->snap_all;
     r->foreign_ids = c->foreign_ids;
     r->next_id = c->next_id;
     r->tris_submitted = c->tris_submitted;
@@ -2535,6 +2594,7 @@ int trb_composite_save_local_depth(TrbCtx* c) {
                                                "(their vertex stage only covers the share)");
     int rc = check_device(c);
     if (rc) return rc;
+    if (snapshot_window(c) && (rc = snapshot_save_tiles(c, nullptr, nullptr))) return rc;   // the key plane is rewritten below
     const unsigned long long n = c->frame.npix;
     CU(c->zlocal.ensure(n * 8, c->stream));
     CU(cudaMemcpyAsync(c->zlocal.p, c->zkey.p, n * 8, cudaMemcpyDeviceToDevice, c->stream));
