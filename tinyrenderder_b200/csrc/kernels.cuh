@@ -571,51 +571,55 @@ struct SplitArgs {
 // the restore runs k_snap_save between its scan and its raster kernels, which copies the tiles the draw is about to
 // change (per-tile bin count > 0; every tile when the draw overflowed into the unbinned kernels, or when the caller
 // asks for `all`) into the snapshot plane ONCE; k_snap_restore copies the saved tiles back.  Invariant: a tile whose
-// byte is 0 still holds the snapshot's keys.  A warp looks at 32 consecutive slots and copies the flagged ones together.
+// byte is 0 still holds the snapshot's keys.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void snap_copy_tile(const FrameDev& f, uint32_t slot, const unsigned long long* __restrict__ from,
                                                unsigned long long* __restrict__ to, unsigned lane) {
     const uint32_t view = slot / (uint32_t)f.ntiles, tile = slot - view * (uint32_t)f.ntiles;
     const int tx0 = (int)(tile % (uint32_t)f.tw) << TILE_SHIFT, ty0 = (int)(tile / (uint32_t)f.tw) << TILE_SHIFT;
     const unsigned long long base = (unsigned long long)view * f.npix;
+    constexpr int N = TILE * TILE / 32;
+    unsigned long long v[N];
+    const unsigned long long p0 = base + (unsigned long long)(ty0 + (int)(lane >> TILE_SHIFT)) * f.W + tx0 + (int)(lane & (TILE - 1));
+    const unsigned long long step = 2ull * f.W;       // a warp covers two rows of the tile per pass
+    if (tx0 + TILE <= f.W && ty0 + TILE <= f.H) {     // whole tile inside the frame: all loads in flight, then the stores
 #pragma unroll
-    for (int it = 0; it < TILE * TILE / 32; ++it) {
-        const int e = it * 32 + (int)lane, x = tx0 + (e & (TILE - 1)), y = ty0 + (e >> TILE_SHIFT);
-        if (x < f.W && y < f.H) {
-            const unsigned long long p = base + (unsigned long long)y * f.W + x;
-            to[p] = from[p];
-        }
+        for (int it = 0; it < N; ++it) v[it] = __ldg(from + p0 + it * step);
+#pragma unroll
+        for (int it = 0; it < N; ++it) to[p0 + it * step] = v[it];
+        return;
     }
+    const bool in_x = tx0 + (int)(lane & (TILE - 1)) < f.W;
+#pragma unroll
+    for (int it = 0; it < N; ++it)
+        if (in_x && ty0 + (int)(lane >> TILE_SHIFT) + 2 * it < f.H) to[p0 + it * step] = from[p0 + it * step];
+}
+// the flagged slots of a CTA's 256 are collected in shared memory and dealt out to its 8 warps: the tiles an object touches
+// are runs of consecutive slots, and one warp copying a run tile after tile is a chain of memory latencies
+__device__ __forceinline__ void snap_copy_flagged(const FrameDev& f, bool need, uint32_t slot, const unsigned long long* __restrict__ from,
+                                                  unsigned long long* __restrict__ to) {
+    __shared__ uint32_t list[TPB];
+    __shared__ uint32_t n_sh;
+    if (threadIdx.x == 0) n_sh = 0;
+    __syncthreads();
+    if (need) list[atomicAdd(&n_sh, 1u)] = slot;
+    __syncthreads();
+    const uint32_t n = n_sh;
+    for (uint32_t i = threadIdx.x >> 5; i < n; i += TPB / 32) snap_copy_tile(f, list[i], from, to, threadIdx.x & 31);
 }
 __global__ void __launch_bounds__(TPB) k_snap_save(FrameDev f, uint32_t nslots, const uint32_t* __restrict__ counts,
                                                    const DrawCtl* __restrict__ ctl, int all, uint8_t* __restrict__ saved,
                                                    unsigned long long* __restrict__ snap) {
-    const unsigned lane = threadIdx.x & 31;
-    const uint32_t first = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 32u;
-    if (first >= nslots) return;
-    const uint32_t slot = first + lane;
+    const uint32_t slot = blockIdx.x * TPB + threadIdx.x;
     const bool every = all || (ctl && ctl->overflow);
-    bool need = slot < nslots && !saved[slot] && (every || counts[slot] != 0);
-    unsigned m = __ballot_sync(0xffffffffu, need);
-    if (need) saved[slot] = 1;            // only this warp ever looks at these 32 bytes inside one launch
-    while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        snap_copy_tile(f, first + b, f.zkey, snap, lane);
-    }
+    const bool need = slot < nslots && !saved[slot] && (every || counts[slot] != 0);
+    if (need) saved[slot] = 1;            // one thread per slot: nobody else looks at this byte inside the launch
+    snap_copy_flagged(f, need, slot, f.zkey, snap);
 }
 __global__ void __launch_bounds__(TPB) k_snap_restore(FrameDev f, uint32_t nslots, const uint8_t* __restrict__ saved,
                                                       const unsigned long long* __restrict__ snap) {
-    const unsigned lane = threadIdx.x & 31;
-    const uint32_t first = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 32u;
-    if (first >= nslots) return;
-    const uint32_t slot = first + lane;
-    unsigned m = __ballot_sync(0xffffffffu, slot < nslots && saved[slot]);
-    while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        snap_copy_tile(f, first + b, snap, f.zkey, lane);
-    }
+    const uint32_t slot = blockIdx.x * TPB + threadIdx.x;
+    snap_copy_flagged(f, slot < nslots && saved[slot], slot, snap, f.zkey);
 }
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sh, uint32_t& total) {
