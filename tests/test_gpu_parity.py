@@ -227,7 +227,7 @@ def test_split_bins_match_oracle(cuda_api, port_api, monkeypatch, name, env):
     compare.assert_outputs_match(name, got, want)
 
 
-@pytest.mark.parametrize("env", [{}, {"TRB_LAZY_SNAPSHOT": "0"}, {"TRB_LAZY_SNAPSHOT_MAX_TRIS": "0"}, {"TRB_BIN_CAP": "16"},
+@pytest.mark.parametrize("env", [{}, {"TRB_LAZY_SNAPSHOT": "0"}, {"TRB_LAZY_SNAPSHOT_MAX_TRIS": "0"}, {"TRB_BIN_CAP": "16"}, {"TRB_COLLECT_BY_TILES": "0"},
                                  {"TRB_SYNC_DRAWS": "1"}, {"TRB_WARP_MAX": "0"}, {"TRB_WARP_MAX": "8", "TRB_SPLIT_S": "32"}])
 @pytest.mark.parametrize("name", ["snapshot_restore_twice", "snapshot_signed_zero", "snapshot_small_triangles", "orbit_small",
                                   "orbit_culled"])
@@ -236,7 +236,8 @@ def test_depth_snapshot_variants_match_oracle(cuda_api, port_api, monkeypatch, n
     snapshot - draws inside the window save the tiles their bins name (and give up the direct path for it);
     TRB_LAZY_SNAPSHOT_MAX_TRIS=0 makes every such draw save ALL tiles and keep the direct path (what a draw of more than
     2^20 triangles does), a 16-entry bin buffer makes it overflow into the unbinned kernels (again all tiles);
-    TRB_LAZY_SNAPSHOT=0 is the whole-plane copy with the pointer-swap restore.  Same bits, same counters, every time."""
+    TRB_LAZY_SNAPSHOT=0 is the whole-plane copy with the pointer-swap restore.  Flushes inside the window collect their
+    pixel list from the saved tiles (TRB_COLLECT_BY_TILES=0: from the whole id plane).  Same bits, same counters, every time."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     got = run_case(cuda_api, name)

@@ -1852,6 +1852,53 @@ __global__ void __launch_bounds__(TPB) k_shade_collect(FrameDev f, int row0, int
     }
 }
 
+// The same list for a flush inside a tile-granular depth snapshot window (k_snap_save above): the snapshot flushed, so every
+// pixel drawn since lies in a tile whose byte in `saved` is set - the list comes from those tiles instead of from a pass
+// over the whole id plane (config 3: the eyes' flush read 265 MB of ids to find a few thousand pixels).
+__global__ void __launch_bounds__(TPB) k_shade_collect_tiles(FrameDev f, uint32_t nslots, const uint8_t* __restrict__ saved,
+                                                             int row0, int row1, uint32_t* __restrict__ list) {
+    __shared__ uint32_t tiles[TPB];
+    __shared__ uint32_t n_sh;
+    const uint32_t slot = blockIdx.x * TPB + threadIdx.x;
+    if (threadIdx.x == 0) n_sh = 0;
+    __syncthreads();
+    if (slot < nslots && saved[slot]) tiles[atomicAdd(&n_sh, 1u)] = slot;
+    __syncthreads();
+    const uint32_t n = n_sh;
+    const unsigned lane = threadIdx.x & 31;
+    constexpr int N = TILE * TILE / 32;
+    for (uint32_t i = threadIdx.x >> 5; i < n; i += TPB / 32) {
+        const uint32_t s = tiles[i], view = s / (uint32_t)f.ntiles, tile = s - view * (uint32_t)f.ntiles;
+        if (!f.stats[view].shade_mode) continue;                       // a dense view: k_shade_dense takes it
+        const int x = ((int)(tile % (uint32_t)f.tw) << TILE_SHIFT) + (int)(lane & (TILE - 1));
+        const int y0 = ((int)(tile / (uint32_t)f.tw) << TILE_SHIFT) + (int)(lane >> TILE_SHIFT);
+        const uint32_t* vis = f.vis + (size_t)view * f.npix;
+        uint32_t ids[N];
+        unsigned mine = 0;
+#pragma unroll
+        for (int it = 0; it < N; ++it) {
+            const int y = y0 + 2 * it;
+            ids[it] = (x < f.W && y >= row0 && y < row1) ? vis[(uint32_t)y * (uint32_t)f.W + (uint32_t)x] : VIS_NONE;
+        }
+#pragma unroll
+        for (int it = 0; it < N; ++it) mine += (ids[it] != VIS_NONE && ids[it] != VIS_SHADED) ? 1u : 0u;
+        unsigned incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += up;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 31) base = atomicAdd(&f.stats[view].list_len, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t* out = list + (size_t)view * f.npix + base + (incl - mine);
+#pragma unroll
+        for (int it = 0; it < N; ++it)
+            if (ids[it] != VIS_NONE && ids[it] != VIS_SHADED) *out++ = (uint32_t)(y0 + 2 * it) * (uint32_t)f.W + (uint32_t)x;
+    }
+}
+
 // Dense frames (most pixels have an unshaded winner): one thread per pixel, no list
 #ifndef TRB_SHADE_MIN_BLOCKS
 #define TRB_SHADE_MIN_BLOCKS 4

@@ -313,6 +313,7 @@ struct TrbCtx {
     // tile-granular snapshot (default; TRB_LAZY_SNAPSHOT=0: the whole-plane copy + pointer swap above): zsnap only receives
     // the tiles the draws after the snapshot change, snap_saved holds one byte per tile slot (kernels.cuh k_snap_save)
     bool lazy_snapshot = true;
+    bool collect_by_tiles = true;   // flushes inside the window collect their pixel list from the saved tiles (TRB_COLLECT_BY_TILES=0: whole plane)
     bool snap_lazy = false;         // the current snapshot is a tile-granular one
     bool snap_all = false;          // ... and every tile has been saved (nothing left to do per draw)
     DevBuf snap_saved;
@@ -583,6 +584,9 @@ int param_copy(TrbCtx* c, void* dst, const void* src, size_t bytes, size_t* slot
         if ((c) && (c)->rec) return refused(c, what ": not inside trb_record_begin / trb_record_end"); \
     } while (0)
 
+// between a tile-granular snapshot and the next one (or the end of the frame), as long as single tiles are being saved
+inline bool snapshot_window(const TrbCtx* c) { return c->have_snapshot && c->snap_lazy && !c->snap_all; }
+
 // upload the draw table and run the shade kernel over [row0,row1)
 int do_flush(TrbCtx* c) {
     if (!c->in_frame) return fail(c, TRB_E_ARG, "flush: no frame");
@@ -608,7 +612,14 @@ int do_flush(TrbCtx* c) {
             Launch L(c, "k_shade_decide");
             k_shade_decide<<<(f.nviews + TPB - 1) / TPB, TPB, 0, c->stream>>>(f, n);
         }
-        {   // sparse views only (device-side predicate)
+        if (snapshot_window(c) && c->collect_by_tiles) {
+            // sparse views, inside a tile-granular snapshot window: what was drawn since the snapshot (which flushed) lies
+            // in the tiles marked as saved - collect from those, not from the whole id plane
+            const uint32_t nslots = (uint32_t)((size_t)f.nviews * f.ntiles);
+            Launch L(c, "k_shade_collect_tiles");
+            k_shade_collect_tiles<<<(nslots + TPB - 1) / TPB, TPB, 0, c->stream>>>(f, nslots, c->snap_saved.as<uint8_t>(), r0, r1,
+                                                                                 c->shade_list.as<uint32_t>());
+        } else {   // sparse views only (device-side predicate)
             const unsigned need = blocks_for((n + SHADE_PX_PER_THREAD - 1) / SHADE_PX_PER_THREAD);
             dim3 grid(std::min(need, std::max(1u, (unsigned)c->sms * 16 / (unsigned)f.nviews)), f.nviews);
             Launch L(c, "k_shade_collect");
@@ -692,7 +703,6 @@ int snapshot_save_tiles(TrbCtx* c, const uint32_t* counts, const DrawCtl* ctl) {
     if (!counts) c->snap_all = true;
     return TRB_OK;
 }
-inline bool snapshot_window(const TrbCtx* c) { return c->have_snapshot && c->snap_lazy && !c->snap_all; }
 
 // Tensor maps of the frame's planes for the TMA tile staging of k_raster_warp.  cuTensorMapEncodeTiled is a driver
 // entry point; it is looked up at run time so that the library carries no link-time dependency on libcuda.
@@ -1097,6 +1107,7 @@ int trb_create(int device, TrbCtx** out) {
     if (const char* e = getenv("TRB_SHADE_EXACT")) c->shade_exact = atoi(e) != 0;
     if (const char* e = getenv("TRB_TMA")) c->use_tma = atoi(e) != 0;
     if (const char* e = getenv("TRB_LAZY_SNAPSHOT")) c->lazy_snapshot = atoi(e) != 0;
+    if (const char* e = getenv("TRB_COLLECT_BY_TILES")) c->collect_by_tiles = atoi(e) != 0;
     if (const char* e = getenv("TRB_LAZY_SNAPSHOT_MAX_TRIS")) c->lazy_max_tris = (uint64_t)std::max(0ll, atoll(e));
     if (const char* e = getenv("TRB_SYNC_DRAWS")) c->sync_draws = atoi(e) != 0;
     if (const char* e = getenv("TRB_BIN_CAP")) c->bin_cap_fixed = (uint32_t)std::max(1, atoi(e));
